@@ -1,0 +1,311 @@
+"""SymPy -> straight-line C / CUDA code generator for IPDDP2 model functions.
+
+This is the build's counterpart of the reference's Symbolics.jl tracing + `build_function`
+(reference src/dynamics.jl:15-47, src/objectives.jl:12-33, src/constraints.jl:16-50): user closures
+are traced with symbolic x, u, the Jacobians / Hessians / Hessian contractions are formed
+symbolically, and in-place straight-line functions are emitted.  Two flavours are written from ONE
+intermediate representation, so both evaluate the same floating-point expression trees in the same
+order (both are compiled with FP contraction disabled):
+
+  * oracle flavour (plain C, dense column-major outputs incl. structural zeros) -> oracle/models_gen/<name>.h
+  * device flavour (CUDA `__device__`, only structurally non-constant entries go through HBM as a
+    compact "tile"; scatter tables tell the backward kernel where each entry lives) ->
+    interiorpointddp.jl_b200/csrc/models_gen/<name>.cuh
+
+Bundles (one CSE pass each):
+  dyn     f(x,u,p)                         reference Dynamics.evaluate
+  cost    l(x,u,p), costN  l_N(x,p)        reference Objective.evaluate
+  con     c(x,u,p)                         reference Constraint.evaluate
+  derivs  fx fu lx lu lxx luu lux cx cu vcxx vcux vcuu   (x,u,phi,p)   reference src/derivatives.jl:1-35
+  vf      vfxx vfux vfuu (x,u,lam,p)       reference src/dynamics.jl:63-70 (needs the costate of the sweep)
+  derivsN lx lxx (x,p)                     terminal stage
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import workloads  # noqa: E402
+
+
+class _Printer(C99CodePrinter):
+    """Prints doubles with 17 significant digits, integer powers as products and
+    transcendental calls through the deterministic DM_* math layer."""
+
+    def _print_Float(self, expr):
+        return repr(float(expr))
+
+    def _print_Integer(self, expr):
+        return f"{int(expr)}.0"
+
+    def _print_Rational(self, expr):
+        return f"({int(expr.p)}.0/{int(expr.q)}.0)"
+
+    def _print_Pow(self, expr):
+        b, e = expr.base, expr.exp
+        if e.is_Integer:
+            n = int(e)
+            bs = self.parenthesize(b, 1000)
+            if n > 0 and n <= 4:
+                return "(" + "*".join([bs] * n) + ")"
+            if n < 0 and n >= -4:
+                return "(1.0/(" + "*".join([bs] * (-n)) + "))"
+        if e == sp.Rational(1, 2):
+            return f"sqrt({self._print(b)})"
+        return f"DM_POW({self._print(b)}, {self._print(e)})"
+
+    def _print_sin(self, expr):
+        return f"DM_SIN({self._print(expr.args[0])})"
+
+    def _print_cos(self, expr):
+        return f"DM_COS({self._print(expr.args[0])})"
+
+    def _print_tan(self, expr):
+        return f"DM_TAN({self._print(expr.args[0])})"
+
+    def _print_log(self, expr):
+        return f"DM_LOG({self._print(expr.args[0])})"
+
+    def _print_exp(self, expr):
+        return f"DM_EXP({self._print(expr.args[0])})"
+
+
+_P = _Printer()
+
+
+def _sym(prefix, n):
+    return [sp.Symbol(f"{prefix}[{i}]", real=True) for i in range(n)]
+
+
+@dataclass
+class Entry:
+    mat: str
+    i: int
+    j: int
+    kind: str          # 'zero' | 'const' | 'dyn'
+    text: str          # C expression (for 'const' a literal, for 'dyn' an expression over temps/inputs)
+    value: float = 0.0
+
+
+@dataclass
+class Bundle:
+    name: str
+    inputs: List[str]                       # names of input arrays in call order
+    outputs: List[Tuple[str, int, int]]     # (name, rows, cols) column-major
+    temps: List[Tuple[str, str]]            # (tmp name, expression text)
+    entries: List[Entry]
+
+
+def _make_bundle(name, inputs, mats: List[Tuple[str, sp.Matrix]]) -> Bundle:
+    flat = []
+    for mname, M in mats:
+        M = sp.Matrix(M)
+        for j in range(M.cols):
+            for i in range(M.rows):
+                flat.append((mname, i, j, M[i, j]))
+    exprs = [sp.nsimplify(e, rational=False) if False else e for (_, _, _, e) in flat]
+    repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("w"), order="canonical")
+    temps = [(str(s), _P.doprint(e)) for s, e in repl]
+    entries = []
+    for (mname, i, j, _), e in zip(flat, red):
+        e = sp.sympify(e)
+        if e == 0:
+            entries.append(Entry(mname, i, j, "zero", "0.0", 0.0))
+        elif e.is_number:
+            entries.append(Entry(mname, i, j, "const", repr(float(e)), float(e)))
+        else:
+            entries.append(Entry(mname, i, j, "dyn", _P.doprint(e)))
+    outs = [(mname, sp.Matrix(M).rows, sp.Matrix(M).cols) for mname, M in mats]
+    return Bundle(name, inputs, outs, temps, entries)
+
+
+def trace(md: workloads.ModelDef) -> Dict[str, Bundle]:
+    nx, nu, npar = md.nx, md.nu, md.np_
+    x, u, p = _sym("x", nx), _sym("u", nu), _sym("p", max(npar, 1))
+    fx_ = sp.Matrix(md.f(x, u, p))
+    nxn = fx_.rows
+    c_ = sp.Matrix(md.c(x, u, p)) if md.nc > 0 else sp.zeros(0, 1)
+    nc = c_.rows
+    l_ = sp.sympify(md.stage_cost(x, u, p))
+    lN_ = sp.sympify(md.term_cost(x, p))
+    v = _sym("v", max(nc, 1))
+    lam = _sym("v", nxn)
+    X, U = sp.Matrix(x), sp.Matrix(u)
+
+    b: Dict[str, Bundle] = {}
+    b["dyn"] = _make_bundle("dyn", ["x", "u", "p"], [("f", fx_)])
+    b["cost"] = _make_bundle("cost", ["x", "u", "p"], [("l", sp.Matrix([l_]))])
+    b["costN"] = _make_bundle("costN", ["x", "p"], [("l", sp.Matrix([lN_]))])
+    b["con"] = _make_bundle("con", ["x", "u", "p"], [("c", c_)])
+
+    Jfx, Jfu = fx_.jacobian(X), fx_.jacobian(U)
+    lx = sp.Matrix([l_]).jacobian(X).T
+    lu = sp.Matrix([l_]).jacobian(U).T
+    lxx, luu, lux = lx.jacobian(X), lu.jacobian(U), lu.jacobian(X)
+    cx, cu = c_.jacobian(X), c_.jacobian(U)
+    vv = sp.Matrix(v[:nc])
+    vcxx = (cx.T * vv).jacobian(X)
+    vcux = (cu.T * vv).jacobian(X)
+    vcuu = (cu.T * vv).jacobian(U)
+    b["derivs"] = _make_bundle("derivs", ["x", "u", "v", "p"], [
+        ("fx", Jfx), ("fu", Jfu), ("lx", lx), ("lu", lu), ("lxx", lxx), ("luu", luu), ("lux", lux),
+        ("cx", cx), ("cu", cu), ("vcxx", vcxx), ("vcux", vcux), ("vcuu", vcuu)])
+
+    lv = sp.Matrix(lam)
+    vfxx = (Jfx.T * lv).jacobian(X)
+    vfux = (Jfu.T * lv).jacobian(X)
+    vfuu = (Jfu.T * lv).jacobian(U)
+    b["vf"] = _make_bundle("vf", ["x", "u", "v", "p"], [("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu)])
+
+    lNx = sp.Matrix([lN_]).jacobian(X).T
+    b["derivsN"] = _make_bundle("derivsN", ["x", "p"], [("lx", lNx), ("lxx", lNx.jacobian(X))])
+    return b
+
+
+# ----------------------------------------------------------------------------------------
+# oracle flavour
+# ----------------------------------------------------------------------------------------
+def emit_oracle(md, bundles) -> str:
+    n = md.name
+    nc = bundles["con"].outputs[0][1]
+    nxn = bundles["dyn"].outputs[0][1]
+    o = []
+    o.append(f"// GENERATED by interiorpointddp.jl_b200/codegen/generate.py -- do not edit.\n"
+             f"// Oracle (CPU, dense) model functions for workload '{n}'.  {md.doc}\n"
+             f"// Dense column-major outputs; every entry is written (as the reference's generated closures do,\n"
+             f"// reference src/dynamics.jl:26-34).\n#pragma once\n#include \"../oracle_model.h\"\n")
+    o.append(f"namespace gen_{n} {{\n")
+    for bname, b in bundles.items():
+        args = ", ".join(f"const double* {a}" for a in b.inputs)
+        outs = ", ".join(f"double* {m}" for (m, _, _) in b.outputs)
+        o.append(f"static void {bname}({args}, {outs}) {{\n")
+        for a in b.inputs:
+            o.append(f"  (void){a};\n")
+        for t, e in b.temps:
+            o.append(f"  const double {t} = {e};\n")
+        rows = {m: r for (m, r, _) in b.outputs}
+        for en in b.entries:
+            o.append(f"  {en.mat}[{en.i + en.j * rows[en.mat]}] = {en.text};\n")
+        o.append("}\n")
+    o.append(f"static const OracleModel model = {{\"{n}\", {md.nx}, {md.nu}, {nc}, {nxn}, {md.np_}, "
+             f"dyn, cost, costN, con, derivs, vf, derivsN}};\n")
+    o.append("}\n")
+    return "".join(o)
+
+
+# ----------------------------------------------------------------------------------------
+# device flavour
+# ----------------------------------------------------------------------------------------
+def device_layout(md, bundles):
+    """Slot assignment of the compact derivative tile.  Only 'dyn' entries travel through HBM;
+    'const' entries are baked into the scatter tables.  Returns dict with per-matrix lists."""
+    slots = []   # (mat, i, j) in slot order
+    consts = []  # (mat, i, j, value)
+    for en in bundles["derivs"].entries:
+        if en.kind == "dyn":
+            slots.append((en.mat, en.i, en.j))
+        elif en.kind == "const":
+            consts.append((en.mat, en.i, en.j, en.value))
+    return slots, consts
+
+
+def emit_device(md, bundles) -> str:
+    n = md.name
+    nc = bundles["con"].outputs[0][1]
+    nxn = bundles["dyn"].outputs[0][1]
+    nx, nu = md.nx, md.nu
+    o = []
+    o.append(f"// GENERATED by interiorpointddp.jl_b200/codegen/generate.py -- do not edit.\n"
+             f"// Device model functions for workload '{n}'.  {md.doc}\n"
+             f"// Same temporaries / expression trees as oracle/models_gen/{n}.h; only structurally\n"
+             f"// non-constant derivative entries are stored (compact tile), constants live in the tables.\n"
+             f"#pragma once\n#include \"../model_common.cuh\"\n")
+    o.append(f"struct Model_{n} {{\n")
+    o.append(f"  static constexpr const char* NAME = \"{n}\";\n")
+    o.append(f"  static constexpr int NX = {nx}, NU = {nu}, NC = {nc}, NXN = {nxn}, NP = {md.np_};\n")
+
+    def fn(bname, compact=None):
+        b = bundles[bname]
+        args = ", ".join(f"const double* __restrict__ {a}" for a in b.inputs)
+        if compact is None:
+            outs = ", ".join(f"double* __restrict__ {m}" for (m, _, _) in b.outputs)
+            o.append(f"  static __device__ __forceinline__ void {bname}({args}, {outs}) {{\n")
+        else:
+            o.append(f"  template <class Store> static __device__ __forceinline__ void {bname}({args}, Store st) {{\n")
+        for a in b.inputs:
+            o.append(f"    (void){a};\n")
+        for t, e in b.temps:
+            o.append(f"    const double {t} = {e};\n")
+        rows = {m: r for (m, r, _) in b.outputs}
+        if compact is None:
+            for en in b.entries:
+                o.append(f"    {en.mat}[{en.i + en.j * rows[en.mat]}] = {en.text};\n")
+        else:
+            k = 0
+            for en in b.entries:
+                if en.kind == "dyn":
+                    o.append(f"    st({k}, {en.text});  // {en.mat}[{en.i},{en.j}]\n")
+                    k += 1
+        o.append("  }\n")
+
+    fn("dyn"); fn("cost"); fn("costN"); fn("con")
+    fn("derivs", compact=True)
+    fn("vf", compact=True)
+    fn("derivsN", compact=True)
+
+    # tables: for each bundle with compact output, list entries per matrix: (slot or -1, i, j, const)
+    def tables(bname, prefix):
+        b = bundles[bname]
+        k = 0
+        per = {m: [] for (m, _, _) in b.outputs}
+        for en in b.entries:
+            if en.kind == "dyn":
+                per[en.mat].append((k, en.i, en.j, 0.0)); k += 1
+            elif en.kind == "const":
+                per[en.mat].append((-1, en.i, en.j, en.value))
+        o.append(f"  static constexpr int {prefix}_NSLOT = {k};\n")
+        for m, lst in per.items():
+            cnt = len(lst)
+            o.append(f"  static constexpr int {prefix}_{m}_N = {cnt};\n")
+            z = lst if cnt else [(-1, 0, 0, 0.0)]
+            o.append(f"  static constexpr MEntry {prefix}_{m}[{max(cnt, 1)}] = {{"
+                     + ", ".join(f"{{{s}, {i}, {j}, {repr(float(cv))}}}" for (s, i, j, cv) in z) + "};\n")
+
+    tables("derivs", "D")
+    tables("vf", "VF")
+    tables("derivsN", "DN")
+    o.append("};\n")
+    return "".join(o)
+
+
+def generate_all(names=None, oracle_dir=None, device_dir=None):
+    root = os.path.dirname(os.path.dirname(HERE))
+    oracle_dir = oracle_dir or os.path.join(root, "oracle", "models_gen")
+    device_dir = device_dir or os.path.join(HERE, "..", "csrc", "models_gen")
+    os.makedirs(oracle_dir, exist_ok=True)
+    os.makedirs(device_dir, exist_ok=True)
+    names = names or list(workloads.WORKLOADS)
+    for nm in names:
+        md = workloads.get(nm)
+        b = trace(md)
+        with open(os.path.join(oracle_dir, f"{nm}.h"), "w") as fh:
+            fh.write(emit_oracle(md, b))
+        with open(os.path.join(device_dir, f"{nm}.cuh"), "w") as fh:
+            fh.write(emit_device(md, b))
+        nd = sum(1 for e in b["derivs"].entries if e.kind == "dyn")
+        ncst = sum(1 for e in b["derivs"].entries if e.kind == "const")
+        nvf = sum(1 for e in b["vf"].entries if e.kind != "zero")
+        print(f"{nm}: nx={md.nx} nu={md.nu} nc={b['con'].outputs[0][1]} tile slots={nd} consts={ncst} "
+              f"dense={len(b['derivs'].entries)} vf_nonzero={nvf} temps={len(b['derivs'].temps)}")
+
+
+if __name__ == "__main__":
+    generate_all(sys.argv[1:] or None)
