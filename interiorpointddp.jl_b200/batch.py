@@ -1,0 +1,167 @@
+"""BatchSolver: the batched counterpart of the reference's `Solver` + `solve!` over the C ABI.
+
+One BatchSolver owns one `ipddp_problem` handle (B instances of one model, up to N knots, one GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import Options, Stats, dptr, iptr
+
+
+@dataclass
+class BatchResult:
+    """Per-instance SolverData fields (reference src/data/solver.jl:8-33)."""
+    status: np.ndarray
+    k: np.ndarray
+    j: np.ndarray
+    l: np.ndarray
+    objective: np.ndarray
+    primal_inf: np.ndarray
+    dual_inf: np.ndarray
+    cs_inf: np.ndarray
+    mu: np.ndarray
+    reg_last: np.ndarray
+    step_size: np.ndarray
+
+    @property
+    def converged(self) -> np.ndarray:
+        return self.status == 0
+
+
+class BatchSolver:
+    def __init__(self, model: str, B: int, N: int, options: Optional[Options] = None, device: int = 0,
+                 trace_capacity: int = 0, indices_compl=None, lib: Optional[_lib.Lib] = None):
+        self.lib = lib or _lib.load()
+        self.model, self.B, self.N = model, int(B), int(N)
+        self.nx, self.nu, self.nc, self.np, self.tile_slots = self.lib.model_dims(model)
+        self.options = options or self.lib.default_options()
+        ic = np.ascontiguousarray(indices_compl if indices_compl is not None else [], dtype=np.int32)
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.ipddp_problem_create(model.encode(), self.B, self.N, iptr(ic) if ic.size else None,
+                                                       int(ic.size), C.byref(self.options), int(device),
+                                                       int(trace_capacity), C.byref(h)), "ipddp_problem_create")
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.L.ipddp_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ inputs
+    def set_inputs(self, x1, ubar, params=None, lower=None, upper=None, horizons=None):
+        """Host buffers (numpy), copied H2D.  Shapes: x1 [B,nx], ubar [B,(N-1)*nu], params [B,np],
+        lower/upper [B,nu] (default: unbounded), horizons [B] int."""
+        B, N = self.B, self.N
+        x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(B, self.nx)
+        ubar = np.ascontiguousarray(ubar, dtype=np.float64).reshape(B, (N - 1) * self.nu)
+        if lower is None:
+            lower = np.full((B, self.nu), -np.inf)
+        if upper is None:
+            upper = np.full((B, self.nu), np.inf)
+        lower = np.ascontiguousarray(np.broadcast_to(np.asarray(lower, dtype=np.float64), (B, self.nu)))
+        upper = np.ascontiguousarray(np.broadcast_to(np.asarray(upper, dtype=np.float64), (B, self.nu)))
+        p = None
+        if self.np > 0:
+            p = np.ascontiguousarray(params, dtype=np.float64).reshape(B, self.np)
+        hz = None
+        if horizons is not None:
+            hz = np.ascontiguousarray(horizons, dtype=np.int32).reshape(B)
+        self._keep = (x1, ubar, p, lower, upper, hz)
+        self.lib.check(self.lib.L.ipddp_set_inputs(self.h, dptr(x1), dptr(ubar), dptr(p) if p is not None else None,
+                                                   dptr(lower), dptr(upper), iptr(hz) if hz is not None else None),
+                       "ipddp_set_inputs")
+
+    def set_inputs_device(self, x1_ptr, ubar_ptr, params_ptr, lower_ptr, upper_ptr, horizons_ptr=None):
+        """Raw device pointers (ints), e.g. torch.Tensor.data_ptr(); D2D copy."""
+        self.lib.check(self.lib.L.ipddp_set_inputs_device(self.h, x1_ptr, ubar_ptr, params_ptr, lower_ptr, upper_ptr,
+                                                          horizons_ptr), "ipddp_set_inputs_device")
+
+    def set_batch(self, batch):
+        self.set_inputs(batch.x1, batch.ubar, batch.p if self.np > 0 else None, batch.lower, batch.upper,
+                        batch.horizons)
+
+    # ------------------------------------------------------------------ solve and phases
+    def solve(self, warm_start: bool = False) -> BatchResult:
+        self.lib.check(self.lib.L.ipddp_solve(self.h, int(warm_start)), "ipddp_solve")
+        return self.results()
+
+    def initialize(self):
+        self.lib.check(self.lib.L.ipddp_initialize(self.h), "ipddp_initialize")
+
+    def eval_derivatives(self):
+        self.lib.check(self.lib.L.ipddp_eval_derivatives(self.h), "ipddp_eval_derivatives")
+
+    def backward_pass(self):
+        self.lib.check(self.lib.L.ipddp_backward_pass(self.h), "ipddp_backward_pass")
+
+    def check(self) -> int:
+        n = C.c_int()
+        self.lib.check(self.lib.L.ipddp_check(self.h, C.byref(n)), "ipddp_check")
+        return n.value
+
+    def forward_pass(self):
+        self.lib.check(self.lib.L.ipddp_forward_pass(self.h), "ipddp_forward_pass")
+
+    # ------------------------------------------------------------------ outputs
+    def results(self) -> BatchResult:
+        B = self.B
+        ints = [np.zeros(B, dtype=np.int32) for _ in range(4)]
+        dbl = [np.zeros(B) for _ in range(7)]
+        self.lib.check(self.lib.L.ipddp_get_results(self.h, *[iptr(a) for a in ints], *[dptr(a) for a in dbl]),
+                       "ipddp_get_results")
+        return BatchResult(*ints, *dbl)
+
+    def trajectory(self):
+        """get_trajectory(solver): nominal states [B,N,nx] and controls [B,N-1,nu]."""
+        x = np.zeros((self.B, self.N, self.nx))
+        u = np.zeros((self.B, self.N - 1, self.nu))
+        self.lib.check(self.lib.L.ipddp_get_trajectory(self.h, dptr(x), dptr(u)), "ipddp_get_trajectory")
+        return x, u
+
+    def duals(self):
+        phi = np.zeros((self.B, self.N - 1, self.nc))
+        zl = np.zeros((self.B, self.N - 1, self.nu))
+        zu = np.zeros((self.B, self.N - 1, self.nu))
+        lam = np.zeros((self.B, self.N, self.nx))
+        self.lib.check(self.lib.L.ipddp_get_duals(self.h, dptr(phi), dptr(zl), dptr(zu), dptr(lam)), "ipddp_get_duals")
+        return phi, zl, zu, lam
+
+    def counters(self):
+        a = [np.zeros(self.B, dtype=np.int32) for _ in range(4)]
+        self.lib.check(self.lib.L.ipddp_get_counters(self.h, *[iptr(x) for x in a]), "ipddp_get_counters")
+        return dict(n_backward=a[0], n_sweeps=a[1], n_kkt=a[2], n_rollouts=a[3])
+
+    def array(self, name: str) -> np.ndarray:
+        n = self.lib.L.ipddp_get_array(self.h, name.encode(), None)
+        if n < 0:
+            raise KeyError(f"{name}: {self.lib.L.ipddp_last_error().decode()}")
+        out = np.zeros(int(n))
+        if n:
+            self.lib.L.ipddp_get_array(self.h, name.encode(), dptr(out))
+        return out
+
+    def trace(self, b: int) -> np.ndarray:
+        n = C.c_int()
+        self.lib.check(self.lib.L.ipddp_get_trace(self.h, b, None, C.byref(n)), "ipddp_get_trace")
+        out = np.zeros((n.value, _lib.TRACE_COLS))
+        if n.value:
+            self.lib.check(self.lib.L.ipddp_get_trace(self.h, b, dptr(out), C.byref(n)), "ipddp_get_trace")
+        return out
+
+    def stats(self) -> Stats:
+        st = Stats()
+        self.lib.check(self.lib.L.ipddp_get_stats(self.h, C.byref(st)), "ipddp_get_stats")
+        return st

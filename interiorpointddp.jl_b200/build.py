@@ -1,0 +1,71 @@
+"""In-tree build of libipddp_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+
+    python interiorpointddp.jl_b200/build.py [--force] [--verbose]
+
+-fmad=false: no implicit FMA contraction.  FMAs are written explicitly (IPDDP_FMA) where the algorithm
+wants them, so results do not depend on the compiler's contraction choices (bit parity with the test
+oracle).
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libipddp_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+         "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+
+
+def sources():
+    return [os.path.join(CSRC, "ipddp_api.cu")] + sorted(glob.glob(os.path.join(CSRC, "models", "*.cu")))
+
+
+def _deps_mtime():
+    files = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
+        glob.glob(os.path.join(CSRC, "models_gen", "*.cuh")) + [os.path.join(HERE, "..", "include", "ipddp_b200.h")]
+    return max(os.path.getmtime(f) for f in files)
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ, os.path.basename(src).replace(".cu", ".o"))
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, obj, r.returncode, r.stdout + r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = sources()
+    dep = _deps_mtime()
+    todo = []
+    for s in srcs:
+        o = os.path.join(OBJ, os.path.basename(s).replace(".cu", ".o"))
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(dep, os.path.getmtime(s)):
+            todo.append(s)
+    if todo:
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
+            for src, obj, rc, out in ex.map(lambda s: _compile(s, verbose), todo):
+                if verbose or rc != 0:
+                    sys.stderr.write(out)
+                if rc != 0:
+                    raise RuntimeError(f"nvcc failed on {src}")
+    objs = [os.path.join(OBJ, os.path.basename(s).replace(".cu", ".o")) for s in srcs]
+    if todo or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",
+                                                     "-Xcompiler", "-fPIC", "-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

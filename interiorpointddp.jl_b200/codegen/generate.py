@@ -204,17 +204,23 @@ def emit_oracle(md, bundles) -> str:
 # ----------------------------------------------------------------------------------------
 # device flavour
 # ----------------------------------------------------------------------------------------
-def device_layout(md, bundles):
-    """Slot assignment of the compact derivative tile.  Only 'dyn' entries travel through HBM;
-    'const' entries are baked into the scatter tables.  Returns dict with per-matrix lists."""
-    slots = []   # (mat, i, j) in slot order
-    consts = []  # (mat, i, j, value)
-    for en in bundles["derivs"].entries:
+_UPPER_ONLY = {"luu", "vcuu", "vfuu"}     # only the upper triangle of H-type blocks is ever read (sytrf 'U')
+
+
+def _device_entries(b: Bundle):
+    """Entries the device keeps: structural zeros dropped, strictly-lower part of H-type blocks dropped.
+    Returns list of (Entry, slot) with slot >= 0 for tile entries, -1-constidx for constants."""
+    out, consts, k = [], [], 0
+    for en in b.entries:
+        if en.kind == "zero":
+            continue
+        if en.mat in _UPPER_ONLY and en.i > en.j:
+            continue
         if en.kind == "dyn":
-            slots.append((en.mat, en.i, en.j))
-        elif en.kind == "const":
-            consts.append((en.mat, en.i, en.j, en.value))
-    return slots, consts
+            out.append((en, k)); k += 1
+        else:
+            out.append((en, -1 - len(consts))); consts.append(en.value)
+    return out, consts, k
 
 
 def emit_device(md, bundles) -> str:
@@ -225,63 +231,90 @@ def emit_device(md, bundles) -> str:
     o = []
     o.append(f"// GENERATED by interiorpointddp.jl_b200/codegen/generate.py -- do not edit.\n"
              f"// Device model functions for workload '{n}'.  {md.doc}\n"
-             f"// Same temporaries / expression trees as oracle/models_gen/{n}.h; only structurally\n"
-             f"// non-constant derivative entries are stored (compact tile), constants live in the tables.\n"
+             f"// Same temporaries / expression trees as the dense CPU flavour; only structurally non-constant\n"
+             f"// derivative entries are stored (compact tile), constants live in the scatter tables.\n"
              f"#pragma once\n#include \"../model_common.cuh\"\n")
+    o.append(f"namespace gen_{n} {{\n")
+
+    tbl_defs = []   # (prefix, mat, offset, count)
+    all_entries = []
+    all_consts = []
+    nslots = {}
+    for bname, prefix in (("derivs", "D"), ("vf", "VF"), ("derivsN", "DN")):
+        ents, consts, k = _device_entries(bundles[bname])
+        nslots[prefix] = k
+        cbase = len(all_consts)
+        all_consts += consts
+        for (m, _, _) in bundles[bname].outputs:
+            lst = [(en, s) for (en, s) in ents if en.mat == m]
+            tbl_defs.append((prefix, m, len(all_entries), len(lst)))
+            for en, s in lst:
+                slot = s if s >= 0 else -1 - (cbase + (-1 - s))
+                all_entries.append((slot, en.i, en.j, f"{prefix}.{m}"))
+    o.append(f"IPDDP_TABLE MEntry TBL[{max(len(all_entries), 1)}] = {{\n")
+    if not all_entries:
+        o.append("  {0, 0, 0}\n")
+    for (slot, i, j, tag) in all_entries:
+        o.append(f"  {{{slot}, {i}, {j}}},  // {tag}\n")
+    o.append("};\n")
+    o.append(f"IPDDP_TABLE double CONSTS[{max(len(all_consts), 1)}] = {{"
+             + (", ".join(repr(float(c)) for c in all_consts) if all_consts else "0.0") + "};\n")
+    o.append("}\n")
+
     o.append(f"struct Model_{n} {{\n")
     o.append(f"  static constexpr const char* NAME = \"{n}\";\n")
     o.append(f"  static constexpr int NX = {nx}, NU = {nu}, NC = {nc}, NXN = {nxn}, NP = {md.np_};\n")
+    o.append(f"  static constexpr int NTBL = {len(all_entries)}, NCONST = {len(all_consts)};\n")
+    o.append(f"  static constexpr int D_NSLOT = {nslots['D']}, VF_NSLOT = {nslots['VF']}, DN_NSLOT = {nslots['DN']};\n")
+    for (prefix, m, off, cnt) in tbl_defs:
+        o.append(f"  static constexpr int {prefix}_{m}_OFF = {off}, {prefix}_{m}_N = {cnt};\n")
+    o.append(f"  static IPDDP_D const MEntry* tbl() {{ return gen_{n}::TBL; }}\n")
+    o.append(f"  static IPDDP_D const double* consts() {{ return gen_{n}::CONSTS; }}\n")
 
-    def fn(bname, compact=None):
+    def fn(bname, compact):
         b = bundles[bname]
         args = ", ".join(f"const double* __restrict__ {a}" for a in b.inputs)
-        if compact is None:
+        if not compact:
             outs = ", ".join(f"double* __restrict__ {m}" for (m, _, _) in b.outputs)
-            o.append(f"  static __device__ __forceinline__ void {bname}({args}, {outs}) {{\n")
+            o.append(f"  static IPDDP_D void {bname}({args}, {outs}) {{\n")
         else:
-            o.append(f"  template <class Store> static __device__ __forceinline__ void {bname}({args}, Store st) {{\n")
+            o.append(f"  template <class Store> static IPDDP_D void {bname}({args}, Store st) {{\n")
         for a in b.inputs:
             o.append(f"    (void){a};\n")
-        for t, e in b.temps:
-            o.append(f"    const double {t} = {e};\n")
+        if compact:
+            ents, _, _ = _device_entries(b)
+            needed = [en for (en, s) in ents if s >= 0]
+        else:
+            needed = b.entries
+        # prune temporaries that no kept output needs (same expression text for the kept ones)
+        used = set()
+        import re
+        tok = re.compile(r"\bw\d+\b")
+        for en in needed:
+            used.update(tok.findall(en.text))
+        tdict = dict(b.temps)
+        order = [t for t, _ in b.temps]
+        stack = list(used)
+        while stack:
+            t = stack.pop()
+            for d in tok.findall(tdict[t]):
+                if d not in used:
+                    used.add(d); stack.append(d)
+        for t in order:
+            if t in used:
+                o.append(f"    const double {t} = {tdict[t]};\n")
         rows = {m: r for (m, r, _) in b.outputs}
-        if compact is None:
+        if not compact:
             for en in b.entries:
                 o.append(f"    {en.mat}[{en.i + en.j * rows[en.mat]}] = {en.text};\n")
         else:
-            k = 0
-            for en in b.entries:
-                if en.kind == "dyn":
-                    o.append(f"    st({k}, {en.text});  // {en.mat}[{en.i},{en.j}]\n")
-                    k += 1
+            for (en, s) in ents:
+                if s >= 0:
+                    o.append(f"    st({s}, {en.text});  // {en.mat}[{en.i},{en.j}]\n")
         o.append("  }\n")
 
-    fn("dyn"); fn("cost"); fn("costN"); fn("con")
-    fn("derivs", compact=True)
-    fn("vf", compact=True)
-    fn("derivsN", compact=True)
-
-    # tables: for each bundle with compact output, list entries per matrix: (slot or -1, i, j, const)
-    def tables(bname, prefix):
-        b = bundles[bname]
-        k = 0
-        per = {m: [] for (m, _, _) in b.outputs}
-        for en in b.entries:
-            if en.kind == "dyn":
-                per[en.mat].append((k, en.i, en.j, 0.0)); k += 1
-            elif en.kind == "const":
-                per[en.mat].append((-1, en.i, en.j, en.value))
-        o.append(f"  static constexpr int {prefix}_NSLOT = {k};\n")
-        for m, lst in per.items():
-            cnt = len(lst)
-            o.append(f"  static constexpr int {prefix}_{m}_N = {cnt};\n")
-            z = lst if cnt else [(-1, 0, 0, 0.0)]
-            o.append(f"  static constexpr MEntry {prefix}_{m}[{max(cnt, 1)}] = {{"
-                     + ", ".join(f"{{{s}, {i}, {j}, {repr(float(cv))}}}" for (s, i, j, cv) in z) + "};\n")
-
-    tables("derivs", "D")
-    tables("vf", "VF")
-    tables("derivsN", "DN")
+    fn("dyn", False); fn("cost", False); fn("costN", False); fn("con", False)
+    fn("derivs", True); fn("vf", True); fn("derivsN", True)
     o.append("};\n")
     return "".join(o)
 
@@ -300,8 +333,8 @@ def generate_all(names=None, oracle_dir=None, device_dir=None):
             fh.write(emit_oracle(md, b))
         with open(os.path.join(device_dir, f"{nm}.cuh"), "w") as fh:
             fh.write(emit_device(md, b))
-        nd = sum(1 for e in b["derivs"].entries if e.kind == "dyn")
-        ncst = sum(1 for e in b["derivs"].entries if e.kind == "const")
+        _e, _c, nd = _device_entries(b["derivs"])
+        ncst = len(_c)
         nvf = sum(1 for e in b["vf"].entries if e.kind != "zero")
         print(f"{nm}: nx={md.nx} nu={md.nu} nc={b['con'].outputs[0][1]} tile slots={nd} consts={ncst} "
               f"dense={len(b['derivs'].entries)} vf_nonzero={nvf} temps={len(b['derivs'].temps)}")

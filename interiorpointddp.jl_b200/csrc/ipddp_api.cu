@@ -1,0 +1,549 @@
+// libipddp_b200.so -- C ABI (include/ipddp_b200.h): handle management, device memory, the lock-step
+// batched solve loop (reference src/solve.jl:40-88 for every instance at once) and result access.
+//
+// Solve loop per round, over the list of still-active instances (active-set compaction = list of
+// instance ids rebuilt by the kernels with atomics; finished instances cost nothing):
+//   k_derivs   (instance x knot grid)        evaluate_derivatives!
+//   k_backward (one warp per instance)       backward_pass! + inertia_correction!
+//   k_check    (one thread per instance)     errors, convergence, barrier update -> forward list / next list
+//   k_forward  (one thread per instance)     forward_pass! + accept -> next list
+// then one 32-byte D2H of the list counters decides the next round's grid sizes.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels_common.cuh"
+#include "vtable.h"
+
+extern "C" {
+const ModelVTable* ipddp_vtable_cartpole();
+const ModelVTable* ipddp_vtable_acrobot();
+const ModelVTable* ipddp_vtable_concar();
+const ModelVTable* ipddp_vtable_concar_quad();
+const ModelVTable* ipddp_vtable_pushing();
+const ModelVTable* ipddp_vtable_double_integrator();
+}
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+std::vector<const ModelVTable*>& registry() {
+  static std::vector<const ModelVTable*> r = {ipddp_vtable_cartpole(),    ipddp_vtable_acrobot(),
+                                              ipddp_vtable_concar(),      ipddp_vtable_concar_quad(),
+                                              ipddp_vtable_pushing(),     ipddp_vtable_double_integrator()};
+  return r;
+}
+const ModelVTable* find(const char* name) {
+  for (auto* m : registry())
+    if (strcmp(m->name, name) == 0) return m;
+  return nullptr;
+}
+
+// gather one field of the trajectory records into a dense [B][nst][dim] array
+__global__ void k_gather(DevView v, int use_cur, int off, int dim, int nst, double* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)v.B * nst * dim;
+  if (idx >= total) return;
+  const int i = (int)(idx % dim);
+  const int t = (int)((idx / dim) % nst);
+  const int b = (int)(idx / ((long long)dim * nst));
+  const int set = use_cur ? 1 - v.nomsel[b] : v.nomsel[b];
+  out[idx] = (t < v.horizon[b]) ? v.rec(set, b, t)[off + i] : 0.0;
+}
+
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5,
+         a6 = a0 + 0.6, a7 = a0 + 0.7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = IPDDP_FMA(a0, m, c); a1 = IPDDP_FMA(a1, m, c); a2 = IPDDP_FMA(a2, m, c); a3 = IPDDP_FMA(a3, m, c);
+    a4 = IPDDP_FMA(a4, m, c); a5 = IPDDP_FMA(a5, m, c); a6 = IPDDP_FMA(a6, m, c); a7 = IPDDP_FMA(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+__global__ void k_copy(const double4* __restrict__ a, double4* __restrict__ b, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    b[i] = a[i];
+}
+
+}  // namespace
+
+struct ipddp_problem {
+  const ModelVTable* vt = nullptr;
+  DevView v;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  int* d_compl = nullptr;
+  double *d_p = nullptr, *d_lower = nullptr, *d_upper = nullptr, *d_x1 = nullptr, *d_ubar = nullptr;
+  int* d_horizon = nullptr;
+  int* d_list[2] = {nullptr, nullptr};
+  int* d_list_fwd = nullptr;
+  int* d_counters = nullptr;
+  int* h_counters = nullptr;
+  int cur = 0, n_active = 0;
+  bool inputs_set = false;
+  cudaEvent_t ev[8];
+  ipddp_stats st;
+
+  template <class T> int alloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (n > 0 ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+  }
+};
+
+namespace {
+
+int run_init(ipddp_problem* h, int warm) {
+  CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
+  h->cur = 0;
+  h->vt->init(h->v, warm, h->d_list[0], h->d_counters, h->stream);
+  h->st.launches += 1;
+  CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->n_active = h->h_counters[CNT_NEXT];
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ipddp_abi_version(void) { return IPDDP_ABI_VERSION; }
+const char* ipddp_last_error(void) { return g_err.c_str(); }
+
+void ipddp_default_options(ipddp_options* o) {  // reference src/options.jl:1-38
+  o->quasi_newton = 0; o->optimality_tolerance = 1.0e-8; o->max_iterations = 1000; o->reset_cache = 1;
+  o->verbose = 0; o->print_frequency = 10; o->mu_init = 1.0; o->ineq_dual_init = 1.0; o->kappa_1 = 0.01;
+  o->kappa_2 = 0.01; o->reg_1 = 1e-4; o->reg_min = 1e-20; o->reg_max = 1e40; o->kappa_bar_w_p = 100.0;
+  o->kappa_w_p = 8.0; o->kappa_w_m = 1.0 / 3.0; o->kappa_c = 0.25; o->delta_c = 1e-8; o->kappa_eps = 10.0;
+  o->kappa_mu = 0.2; o->theta_mu = 1.2; o->tau_min = 0.99; o->s_max = 100.0; o->eta_L = 1e-4; o->s_L = 2.3;
+  o->delta = 1.0; o->s_theta = 1.1; o->gamma_alpha = 0.05; o->gamma_theta = 1e-5; o->gamma_L = 1e-5;
+  o->kappa_Sigma = 1e10;
+}
+
+int ipddp_num_models(void) { return (int)registry().size(); }
+const char* ipddp_model_name(int i) { return (i >= 0 && i < (int)registry().size()) ? registry()[i]->name : nullptr; }
+int ipddp_model_dims(const char* model, int* nx, int* nu, int* nc, int* np, int* tile_slots) {
+  const ModelVTable* m = find(model);
+  if (!m) return fail(std::string("unknown model ") + model);
+  if (nx) *nx = m->nx; if (nu) *nu = m->nu; if (nc) *nc = m->nc; if (np) *np = m->np;
+  if (tile_slots) *tile_slots = m->d_nslot;
+  return 0;
+}
+int ipddp_model_load(const char* path) {
+  void* so = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!so) return fail(std::string("dlopen: ") + dlerror());
+  typedef const ModelVTable* (*fn_t)();
+  fn_t f = (fn_t)dlsym(so, "ipddp_plugin_vtable");
+  if (!f) return fail("plugin does not export ipddp_plugin_vtable");
+  const ModelVTable* vt = f();
+  for (auto*& m : registry())
+    if (strcmp(m->name, vt->name) == 0) { m = vt; return 0; }
+  registry().push_back(vt);
+  return 0;
+}
+
+int ipddp_problem_create(const char* model, int B, int N, const int* indices_compl, int n_compl,
+                         const ipddp_options* opt, int device, int trace_capacity, ipddp_problem** out) {
+  const ModelVTable* vt = find(model);
+  if (!vt) return fail(std::string("unknown model ") + model);
+  if (B < 1 || N < 2) return fail("need B >= 1 and N >= 2");
+  if (vt->nu + vt->nc > 64) return fail("KKT dimension nu+nc > 64 not supported");
+  CK(cudaSetDevice(device));
+  if (vt->prepare() != 0) return fail("cudaFuncSetAttribute failed");
+  ipddp_problem* h = new ipddp_problem();
+  memset(&h->st, 0, sizeof(h->st));
+  h->vt = vt;
+  h->device = device;
+  DevView& v = h->v;
+  memset(&v, 0, sizeof(v));
+  v.B = B; v.N = N; v.nx = vt->nx; v.nu = vt->nu; v.nc = vt->nc; v.np = vt->np;
+  v.TR = vt->nx + 5 * vt->nu + 2 * vt->nc;
+  v.G = (vt->nu + vt->nc + 2 * vt->nu) * (vt->nx + 1);
+  if (opt) v.opt = *opt; else ipddp_default_options(&v.opt);
+  v.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
+  v.n_compl = (indices_compl && n_compl > 0) ? n_compl : 0;
+  const size_t np1 = vt->np > 0 ? vt->np : 1;
+  int rc = 0;
+  rc |= h->alloc(&h->d_compl, (size_t)v.n_compl);
+  rc |= h->alloc(&h->d_p, (size_t)B * np1);
+  rc |= h->alloc(&h->d_lower, (size_t)B * vt->nu);
+  rc |= h->alloc(&h->d_upper, (size_t)B * vt->nu);
+  rc |= h->alloc(&h->d_x1, (size_t)B * vt->nx);
+  rc |= h->alloc(&h->d_ubar, (size_t)B * (N - 1) * vt->nu);
+  rc |= h->alloc(&h->d_horizon, (size_t)B);
+  rc |= h->alloc(&v.traj, (size_t)2 * B * N * v.TR);
+  rc |= h->alloc(&v.nomsel, (size_t)B);
+  rc |= h->alloc(&v.lam, (size_t)B * N * vt->nx);
+  rc |= h->alloc(&v.tile, (size_t)B * (vt->d_nslot > 0 ? vt->d_nslot : 1) * N);
+  rc |= h->alloc(&v.tileN, (size_t)B * (vt->dn_nslot > 0 ? vt->dn_nslot : 1));
+  rc |= h->alloc(&v.gains, (size_t)B * (N - 1) * v.G);
+  rc |= h->alloc(&v.Qu, (size_t)B * (N - 1) * vt->nu);
+  rc |= h->alloc(&v.sd, (size_t)SD_COUNT * B);
+  rc |= h->alloc(&v.si, (size_t)SI_COUNT * B);
+  rc |= h->alloc(&v.filter, (size_t)2 * IPDDP_FILTER_CAPACITY * B);
+  rc |= h->alloc(&v.trace, (size_t)B * v.trace_cap * IPDDP_TRACE_COLS);
+  rc |= h->alloc(&h->d_list[0], (size_t)B);
+  rc |= h->alloc(&h->d_list[1], (size_t)B);
+  rc |= h->alloc(&h->d_list_fwd, (size_t)B);
+  rc |= h->alloc(&h->d_counters, (size_t)CNT_COUNT);
+  if (rc != 0) { ipddp_problem_destroy(h); return -1; }
+  v.compl_idx = h->d_compl; v.p = h->d_p; v.lower = h->d_lower; v.upper = h->d_upper; v.x1 = h->d_x1;
+  v.ubar = h->d_ubar; v.horizon = h->d_horizon;
+  if (v.n_compl) CK(cudaMemcpy(h->d_compl, indices_compl, v.n_compl * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemset(v.traj, 0, (size_t)2 * B * N * v.TR * sizeof(double)));
+  CK(cudaMemset(v.si, 0, (size_t)SI_COUNT * B * sizeof(int)));
+  CK(cudaMemset(v.sd, 0, (size_t)SD_COUNT * B * sizeof(double)));
+  CK(cudaMemset(v.nomsel, 0, (size_t)B * sizeof(int)));
+  CK(cudaStreamCreate(&h->stream));
+  CK(cudaMallocHost((void**)&h->h_counters, CNT_COUNT * sizeof(int)));
+  for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->ev[i]));
+  *out = h;
+  return 0;
+}
+
+int ipddp_problem_destroy(ipddp_problem* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->stream) {
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream);
+  }
+  delete h;
+  return 0;
+}
+
+int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt) { h->v.opt = *opt; return 0; }
+
+int ipddp_layout(ipddp_problem* h, long long* traj_off, long long* gain_off, long long* traj_stride,
+                 long long* gain_stride, long long* tile_stride) {
+  const DevView& v = h->v;
+  for (int t = 0; t < v.N; ++t) {
+    if (traj_off) traj_off[t] = (long long)t * v.TR;
+    if (gain_off) gain_off[t] = (long long)t * v.G;
+  }
+  if (traj_stride) *traj_stride = (long long)v.N * v.TR;
+  if (gain_stride) *gain_stride = (long long)(v.N - 1) * v.G;
+  if (tile_stride) *tile_stride = (long long)h->vt->d_nslot * v.N;
+  return 0;
+}
+
+static int set_inputs_impl(ipddp_problem* h, const double* x1, const double* ubar, const double* params,
+                           const double* lower, const double* upper, const int* horizons, cudaMemcpyKind kind) {
+  const DevView& v = h->v;
+  CK(cudaSetDevice(h->device));
+  if (!x1 || !ubar || !lower || !upper) return fail("x1, ubar, lower, upper are required");
+  CK(cudaMemcpyAsync(h->d_x1, x1, (size_t)v.B * v.nx * sizeof(double), kind, h->stream));
+  CK(cudaMemcpyAsync(h->d_ubar, ubar, (size_t)v.B * (v.N - 1) * v.nu * sizeof(double), kind, h->stream));
+  if (v.np > 0) {
+    if (!params) return fail("params required (np > 0)");
+    CK(cudaMemcpyAsync(h->d_p, params, (size_t)v.B * v.np * sizeof(double), kind, h->stream));
+  } else {
+    CK(cudaMemsetAsync(h->d_p, 0, (size_t)v.B * sizeof(double), h->stream));
+  }
+  CK(cudaMemcpyAsync(h->d_lower, lower, (size_t)v.B * v.nu * sizeof(double), kind, h->stream));
+  CK(cudaMemcpyAsync(h->d_upper, upper, (size_t)v.B * v.nu * sizeof(double), kind, h->stream));
+  if (horizons) {
+    if (kind == cudaMemcpyHostToDevice)
+      for (int b = 0; b < v.B; ++b)
+        if (horizons[b] < 2 || horizons[b] > v.N) return fail("horizon out of range [2, N]");
+    CK(cudaMemcpyAsync(h->d_horizon, horizons, (size_t)v.B * sizeof(int), kind, h->stream));
+  } else {
+    std::vector<int> hz(v.B, v.N);
+    CK(cudaMemcpyAsync(h->d_horizon, hz.data(), (size_t)v.B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->inputs_set = true;
+  return 0;
+}
+
+int ipddp_set_inputs(ipddp_problem* h, const double* x1, const double* ubar, const double* params,
+                     const double* lower, const double* upper, const int* horizons) {
+  return set_inputs_impl(h, x1, ubar, params, lower, upper, horizons, cudaMemcpyHostToDevice);
+}
+int ipddp_set_inputs_device(ipddp_problem* h, const double* x1, const double* ubar, const double* params,
+                            const double* lower, const double* upper, const int* horizons) {
+  return set_inputs_impl(h, x1, ubar, params, lower, upper, horizons, cudaMemcpyDeviceToDevice);
+}
+
+int ipddp_initialize(ipddp_problem* h) {
+  if (!h->inputs_set) return fail("ipddp_set_inputs not called");
+  CK(cudaSetDevice(h->device));
+  return run_init(h, 0);
+}
+int ipddp_eval_derivatives(ipddp_problem* h) {
+  CK(cudaSetDevice(h->device));
+  h->vt->derivs(h->v, h->d_list[h->cur], h->n_active, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+int ipddp_backward_pass(ipddp_problem* h) {
+  CK(cudaSetDevice(h->device));
+  h->vt->backward(h->v, h->d_list[h->cur], h->n_active, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+int ipddp_check(ipddp_problem* h, int* n_forward) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
+  h->vt->check(h->v, h->d_list[h->cur], h->n_active, h->d_list[1 - h->cur], h->d_list_fwd, h->d_counters, h->stream);
+  CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (n_forward) *n_forward = h->h_counters[CNT_FWD];
+  return 0;
+}
+int ipddp_forward_pass(ipddp_problem* h) {
+  CK(cudaSetDevice(h->device));
+  h->vt->forward(h->v, h->d_list_fwd, h->n_active, h->d_list[1 - h->cur], h->d_counters, h->stream);
+  CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->n_active = h->h_counters[CNT_NEXT];
+  h->cur = 1 - h->cur;
+  return 0;
+}
+
+int ipddp_solve(ipddp_problem* h, int warm_start) {
+  if (!h->inputs_set) return fail("ipddp_set_inputs not called");
+  CK(cudaSetDevice(h->device));
+  const DevView& v = h->v;
+  ipddp_stats& st = h->st;
+  memset(&st, 0, sizeof(st));
+  cudaStream_t s = h->stream;
+  cudaEvent_t* ev = h->ev;
+  CK(cudaEventRecord(ev[6], s));
+  CK(cudaEventRecord(ev[0], s));
+  if (run_init(h, warm_start) != 0) return -1;
+  CK(cudaEventRecord(ev[1], s));
+  CK(cudaEventSynchronize(ev[1]));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+  st.ms_init = ms;
+  while (h->n_active > 0) {
+    const int n = h->n_active;
+    const int cur = h->cur;
+    st.iterations += 1;
+    st.n_active_rounds += n;
+    CK(cudaEventRecord(ev[0], s));
+    h->vt->derivs(v, h->d_list[cur], n, s);
+    CK(cudaEventRecord(ev[1], s));
+    h->vt->backward(v, h->d_list[cur], n, s);
+    CK(cudaEventRecord(ev[2], s));
+    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
+    h->vt->check(v, h->d_list[cur], n, h->d_list[1 - cur], h->d_list_fwd, h->d_counters, s);
+    CK(cudaEventRecord(ev[3], s));
+    h->vt->forward(v, h->d_list_fwd, n, h->d_list[1 - cur], h->d_counters, s);
+    CK(cudaEventRecord(ev[4], s));
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    st.launches += 4;
+    CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); st.ms_derivs += ms;
+    CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); st.ms_backward += ms;
+    CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); st.ms_check += ms;
+    CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); st.ms_forward += ms;
+    h->n_active = h->h_counters[CNT_NEXT];
+    h->cur = 1 - cur;
+  }
+  CK(cudaEventRecord(ev[7], s));
+  CK(cudaEventSynchronize(ev[7]));
+  CK(cudaEventElapsedTime(&ms, ev[6], ev[7]));
+  st.ms_total = ms;
+  // summed counters
+  std::vector<int> si((size_t)SI_COUNT * v.B);
+  CK(cudaMemcpy(si.data(), v.si, si.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int b = 0; b < v.B; ++b) {
+    st.sum_backward += si[(size_t)SI_NBACK * v.B + b];
+    st.sum_sweeps += si[(size_t)SI_NSWEEP * v.B + b];
+    st.sum_kkt += si[(size_t)SI_NKKT * v.B + b];
+    st.sum_rollouts += si[(size_t)SI_NROLL * v.B + b];
+    st.sum_deriv_stages += (long long)si[(size_t)SI_NDERIV * v.B + b];
+    st.n_converged += (si[(size_t)SI_STATUS * v.B + b] == 0);
+  }
+  return 0;
+}
+
+int ipddp_get_results(ipddp_problem* h, int* status, int* k, int* j, int* l, double* objective,
+                      double* primal_inf, double* dual_inf, double* cs_inf, double* mu, double* reg_last,
+                      double* step_size) {
+  const DevView& v = h->v;
+  CK(cudaSetDevice(h->device));
+  auto gi = [&](int f, int* dst) -> cudaError_t {
+    return dst ? cudaMemcpy(dst, v.si + (size_t)f * v.B, v.B * sizeof(int), cudaMemcpyDeviceToHost) : cudaSuccess;
+  };
+  auto gd = [&](int f, double* dst) -> cudaError_t {
+    return dst ? cudaMemcpy(dst, v.sd + (size_t)f * v.B, v.B * sizeof(double), cudaMemcpyDeviceToHost) : cudaSuccess;
+  };
+  CK(gi(SI_STATUS, status)); CK(gi(SI_K, k)); CK(gi(SI_J, j)); CK(gi(SI_L, l));
+  CK(gd(SD_OBJECTIVE, objective)); CK(gd(SD_PRIMAL_INF, primal_inf)); CK(gd(SD_DUAL_INF, dual_inf));
+  CK(gd(SD_CS_INF, cs_inf)); CK(gd(SD_MU, mu)); CK(gd(SD_REG_LAST, reg_last)); CK(gd(SD_STEP, step_size));
+  return 0;
+}
+
+static int gather(ipddp_problem* h, int use_cur, int off, int dim, int nst, double* out_host) {
+  const DevView& v = h->v;
+  const long long total = (long long)v.B * nst * dim;
+  if (total == 0) return 0;
+  double* d = nullptr;
+  CK(cudaMalloc((void**)&d, total * sizeof(double)));
+  const int th = 256;
+  IPDDP_LAUNCH(k_gather, (unsigned)((total + th - 1) / th), th, 0, h->stream, v, use_cur, off, dim, nst, d);
+  cudaError_t e = cudaMemcpyAsync(out_host, d, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(std::string("gather: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int ipddp_get_trajectory(ipddp_problem* h, double* x, double* u) {
+  const DevView& v = h->v;
+  CK(cudaSetDevice(h->device));
+  if (x && gather(h, 0, 0, v.nx, v.N, x) != 0) return -1;
+  if (u && gather(h, 0, v.nx, v.nu, v.N - 1, u) != 0) return -1;
+  return 0;
+}
+
+int ipddp_get_duals(ipddp_problem* h, double* phi, double* zl, double* zu, double* lam) {
+  const DevView& v = h->v;
+  CK(cudaSetDevice(h->device));
+  const int oPHI = v.nx + v.nu + v.nc + 2 * v.nu, oZL = oPHI + v.nc, oZU = oZL + v.nu;
+  if (phi && gather(h, 0, oPHI, v.nc, v.N - 1, phi) != 0) return -1;
+  if (zl && gather(h, 0, oZL, v.nu, v.N - 1, zl) != 0) return -1;
+  if (zu && gather(h, 0, oZU, v.nu, v.N - 1, zu) != 0) return -1;
+  if (lam) CK(cudaMemcpy(lam, v.lam, (size_t)v.B * v.N * v.nx * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ipddp_get_counters(ipddp_problem* h, int* n_backward, int* n_sweeps, int* n_kkt, int* n_rollouts) {
+  const DevView& v = h->v;
+  CK(cudaSetDevice(h->device));
+  int* dst[4] = {n_backward, n_sweeps, n_kkt, n_rollouts};
+  const int f[4] = {SI_NBACK, SI_NSWEEP, SI_NKKT, SI_NROLL};
+  for (int q = 0; q < 4; ++q)
+    if (dst[q]) CK(cudaMemcpy(dst[q], v.si + (size_t)f[q] * v.B, v.B * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+long long ipddp_get_array(ipddp_problem* h, const char* name, double* out) {
+  const DevView& v = h->v;
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail("cudaSetDevice");
+  std::string nm = name;
+  int use_cur = 0;
+  if (nm.rfind("cur_", 0) == 0) { use_cur = 1; nm = nm.substr(4); }
+  const int oX = 0, oU = v.nx, oC = oU + v.nu, oIL = oC + v.nc, oIU = oIL + v.nu, oPHI = oIU + v.nu,
+            oZL = oPHI + v.nc, oZU = oZL + v.nu;
+  struct F { const char* n; int off, dim, nst; } fields[] = {
+      {"x", oX, v.nx, v.N}, {"u", oU, v.nu, v.N - 1}, {"c", oC, v.nc, v.N - 1}, {"il", oIL, v.nu, v.N - 1},
+      {"iu", oIU, v.nu, v.N - 1}, {"phi", oPHI, v.nc, v.N - 1}, {"zl", oZL, v.nu, v.N - 1}, {"zu", oZU, v.nu, v.N - 1}};
+  for (auto& f : fields)
+    if (nm == f.n) {
+      const long long n = (long long)v.B * f.nst * f.dim;
+      if (out && gather(h, use_cur, f.off, f.dim, f.nst, out) != 0) return -1;
+      return n;
+    }
+  const double* src = nullptr;
+  long long n = 0;
+  if (nm == "lam") { src = v.lam; n = (long long)v.B * v.N * v.nx; }
+  else if (nm == "gains") { src = v.gains; n = (long long)v.B * (v.N - 1) * v.G; }
+  else if (nm == "Qu") { src = v.Qu; n = (long long)v.B * (v.N - 1) * v.nu; }
+  else if (nm == "tile") { src = v.tile; n = (long long)v.B * h->vt->d_nslot * v.N; }
+  else if (nm == "tileN") { src = v.tileN; n = (long long)v.B * h->vt->dn_nslot; }
+  else if (nm == "sd") { src = v.sd; n = (long long)SD_COUNT * v.B; }
+  else return fail("unknown array " + nm);
+  if (out && n > 0) {
+    cudaError_t e = cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  }
+  return n;
+}
+
+int ipddp_get_trace(ipddp_problem* h, int b, double* rows, int* nrows) {
+  const DevView& v = h->v;
+  CK(cudaSetDevice(h->device));
+  if (b < 0 || b >= v.B) return fail("instance out of range");
+  int n = 0;
+  CK(cudaMemcpy(&n, v.si + (size_t)SI_TRACE_N * v.B + b, sizeof(int), cudaMemcpyDeviceToHost));
+  if (nrows) *nrows = n;
+  if (rows && n > 0)
+    CK(cudaMemcpy(rows, v.trace + (size_t)b * v.trace_cap * IPDDP_TRACE_COLS,
+                  (size_t)n * IPDDP_TRACE_COLS * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ipddp_get_stats(ipddp_problem* h, ipddp_stats* st) { *st = h->st; return 0; }
+void* ipddp_stream(ipddp_problem* h) { return (void*)h->stream; }
+
+double ipddp_measure_fp64_tflops(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+  const int blocks = prop.multiProcessorCount * 8, th = 256, iters = 20000;
+  double* d = nullptr;
+  if (cudaMalloc((void**)&d, (size_t)blocks * th * sizeof(double)) != cudaSuccess) return -1.0;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  IPDDP_LAUNCH(k_fp64_peak, blocks, th, 0, 0, d, 1000);
+  double best = 0.0;
+  for (int r = 0; r < 5; ++r) {
+    cudaEventRecord(a, 0);
+    IPDDP_LAUNCH(k_fp64_peak, blocks, th, 0, 0, d, iters);
+    cudaEventRecord(b, 0);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    const double tf = 2.0 * 8.0 * (double)iters * blocks * th / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(d);
+  return best;
+}
+
+double ipddp_measure_hbm_gbs(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  const long long n4 = (1ll << 30) / 32;   // 1 GiB per buffer
+  double4 *x = nullptr, *y = nullptr;
+  if (cudaMalloc((void**)&x, n4 * 32) != cudaSuccess) return -1.0;
+  if (cudaMalloc((void**)&y, n4 * 32) != cudaSuccess) { cudaFree(x); return -1.0; }
+  cudaMemset(x, 0, n4 * 32);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  double best = 0.0;
+  for (int r = 0; r < 6; ++r) {
+    cudaEventRecord(a, 0);
+    IPDDP_LAUNCH(k_copy, 148 * 16, 512, 0, 0, x, y, n4);
+    cudaEventRecord(b, 0);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    const double gbs = 2.0 * n4 * 32 / (ms * 1e-3) / 1e9;
+    if (r > 0 && gbs > best) best = gbs;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(x); cudaFree(y);
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+// k_backward: backward_pass! + inertia_correction! (reference src/backward_pass.jl:1-195,
+// src/inertia_correction.jl:257-276), one warp per active instance.
+//
+// The sweep is sequential in time (t = N-1 .. 0) with a restart-from-the-end loop on inertia failure;
+// per knot the warp assembles the (nu+nc)^2 KKT matrix in shared memory from the compact derivative
+// tile (scatter tables generated with the model), factorises it (ldlt_warp.cuh), solves for the
+// nx+1 right-hand sides, forms the gains and updates Vx, Vxx, lambda.  Vx/Vxx/lambda are a
+// shared-memory carry between knots and never touch HBM; only gains, Qu, lambda and the per-instance
+// scalars are written back.  The numerator of the dual infeasibility (src/solve.jl:118-137) is
+// accumulated on the fly because it needs lu, cu, fu (tile) and lambda (sweep) which are in hand here.
+//
+// Bit-parity notes: every output element is computed by exactly one lane with the operation order the
+// CPU oracle uses (dot4 contractions; lhs/rhs terms added in the reference's order:
+// lxx -> +fx'Vxx fx -> +vfxx -> +vcxx, ...).  Structural zeros are skipped, which is exact for finite data.
+#pragma once
+#include "ldlt_warp.cuh"
+
+namespace ipk {
+
+template <class M> struct BwLayout {
+  static_assert(M::NXN == M::NX, "state dimension must be constant along the horizon");
+  static constexpr int NX = M::NX, NU = M::NU, NC = M::NC, K = NU + NC, NR = NX + 1;
+  static constexpr int KP = K * (K + 1) / 2;
+  static constexpr int pad(int n) { return n > 0 ? n : 1; }
+  // offsets in doubles
+  static constexpr int LHS = 0;
+  static constexpr int RHS = LHS + pad(KP);          // K x NR, becomes [alpha beta; psi omega]
+  static constexpr int RHS0 = RHS + pad(K * NR);     // un-negated copy: [Qu B; c cx]
+  static constexpr int FX = RHS0 + pad(K * NR);      // NX x NX (row index = next-state component)
+  static constexpr int FU = FX + NX * NX;            // NX x NU
+  static constexpr int VXX = FU + pad(NX * NU);      // value Hessian of knot t+1
+  static constexpr int VX = VXX + NX * NX;
+  static constexpr int LAM = VX + NX;
+  static constexpr int CM = LAM + NX;                // C (NX x NX)
+  static constexpr int XXT = CM + NX * NX;           // fx' Vxx+  (NX x NX)
+  static constexpr int UXT = XXT + NX * NX;          // fu' Vxx+  (NU x NX)
+  static constexpr int VEC = UXT + pad(NU * NX);     // il iu zl zu t1 t2 chil chiu  (8 x NU)
+  static constexpr int PHI = VEC + pad(8 * NU);
+  static constexpr int XS = PHI + pad(NC);
+  static constexpr int US = XS + NX;
+  static constexpr int LX = US + pad(NU);
+  static constexpr int TILE = LX + NX;
+  static constexpr int VFS = TILE + pad(M::D_NSLOT > M::DN_NSLOT ? M::D_NSLOT : M::DN_NSLOT);
+  static constexpr int WS = VFS + pad(M::VF_NSLOT);  // 4K scratch for the 2x2 update
+  static constexpr int CST = WS + pad(4 * K);
+  static constexpr int NEWV = CST + pad(M::NCONST);  // new Vxx (NX*NX), Vx (NX), lam (NX)
+  static constexpr int DBL_END = NEWV + NX * NX + 2 * NX;
+  // ints (4 bytes) after the doubles
+  static constexpr int IPIV_B = DBL_END * 8;
+  static constexpr int TBL_B = IPIV_B + pad(K) * 4;
+  static constexpr int IJ_B = TBL_B + pad(M::NTBL) * 4;
+  static constexpr int BYTES = ((IJ_B + pad(KP) * 2 + 15) / 16) * 16;
+};
+
+template <class M>
+__global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int n_list) {
+  typedef BwLayout<M> L;
+  typedef Rec<M> R;
+  constexpr int NX = L::NX, NU = L::NU, NC = L::NC, K = L::K, NR = L::NR;
+  IPDDP_DYN_SMEM(double, sm);
+  const int lane = threadIdx.x;
+  const int inst = blockIdx.x;
+  if (inst >= n_list) return;
+  const int b = list[inst];
+  const int Nb = v.horizon[b];
+  const int set = v.nomsel[b];
+
+  double* lhs = sm + L::LHS; double* rhs = sm + L::RHS; double* rhs0 = sm + L::RHS0;
+  double* fx = sm + L::FX; double* fu = sm + L::FU; double* Vxx = sm + L::VXX; double* Vx = sm + L::VX;
+  double* lamn = sm + L::LAM; double* Cm = sm + L::CM; double* xxt = sm + L::XXT; double* uxt = sm + L::UXT;
+  double* il = sm + L::VEC; double* iu = il + NU; double* zl = iu + NU; double* zu = zl + NU;
+  double* t1 = zu + NU; double* t2 = t1 + NU; double* chil = t2 + NU; double* chiu = chil + NU;
+  double* phi = sm + L::PHI; double* xs = sm + L::XS; double* us = sm + L::US; double* lx = sm + L::LX;
+  double* tile = sm + L::TILE; double* vfs = sm + L::VFS; double* ws = sm + L::WS; double* cst = sm + L::CST;
+  double* nVxx = sm + L::NEWV; double* nVx = nVxx + NX * NX; double* nlam = nVx + NX;
+  unsigned char* smb = reinterpret_cast<unsigned char*>(sm);
+  int* ipiv = reinterpret_cast<int*>(smb + L::IPIV_B);
+  MEntry* tbl = reinterpret_cast<MEntry*>(smb + L::TBL_B);
+  unsigned short* ij = reinterpret_cast<unsigned short*>(smb + L::IJ_B);
+
+  // ---- one-time setup: scatter tables, constants, packed-index table, constant parts of fx / fu
+  for (int e = lane; e < M::NTBL; e += 32) tbl[e] = M::tbl()[e];
+  for (int e = lane; e < M::NCONST; e += 32) cst[e] = M::consts()[e];
+  for (int j = 0; j < K; ++j)
+    for (int i = lane; i <= j; i += 32) ij[pk(i, j)] = (unsigned short)(i | (j << 8));
+  for (int e = lane; e < NX * NX; e += 32) fx[e] = 0.0;
+  for (int e = lane; e < NX * NU; e += 32) fu[e] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < M::D_fx_N; e += 32) {
+    const MEntry q = tbl[M::D_fx_OFF + e];
+    if (q.slot < 0) fx[q.i + q.j * NX] = cst[-1 - q.slot];
+  }
+  for (int e = lane; e < M::D_fu_N; e += 32) {
+    const MEntry q = tbl[M::D_fu_OFF + e];
+    if (q.slot < 0) fu[q.i + q.j * NX] = cst[-1 - q.slot];
+  }
+  __syncwarp();
+
+  const double mu = v.sdv(SD_MU, b);
+  const double reg_last = v.sdv(SD_REG_LAST, b);
+  const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
+  const bool second_order = (v.opt.quasi_newton == 0);
+  double reg = 0.0, delta_c = 0.0;
+  int status = 0, nsweep = 0, nkkt = 0;
+  double dual_num = 0.0;
+
+  auto val = [&](const MEntry& q) -> double { return q.slot >= 0 ? tile[q.slot] : cst[-1 - q.slot]; };
+
+  while (reg <= v.opt.reg_max) {
+    status = 0;
+    nsweep++;
+    dual_num = 0.0;
+    // ================= terminal knot (K = 0): Vxx = lxx_N, Vx = lx_N, lambda = lx_N =================
+    {
+      const int t = Nb - 1;
+      nkkt++;
+      for (int e = lane; e < M::DN_NSLOT; e += 32) tile[e] = v.tileN[(size_t)b * (M::DN_NSLOT > 0 ? M::DN_NSLOT : 1) + e];
+      for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
+      for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
+      __syncwarp();
+      for (int e = lane; e < M::DN_lxx_N; e += 32) { const MEntry q = tbl[M::DN_lxx_OFF + e]; Cm[q.i + q.j * NX] = val(q); }
+      for (int e = lane; e < M::DN_lx_N; e += 32) { const MEntry q = tbl[M::DN_lx_OFF + e]; lx[q.i] = val(q); }
+      __syncwarp();
+      // C = lxx (+ vcxx = 0 unless quasi_newton);  Vxx = (0 + 0) + C ;  Vx = lambda = 0 + lx
+      // inertia_correction! on the empty KKT matrix resets delta_c (Q4: the value set by a failed knot
+      // never reaches a non-empty KKT matrix)
+      delta_c = 0.0;
+      for (int e = lane; e < NX * NX; e += 32) Vxx[e] = (0.0 + 0.0) + (second_order ? (Cm[e] + 0.0) : Cm[e]);
+      for (int e = lane; e < NX; e += 32) {
+        const double l0 = 0.0 + lx[e];
+        lamn[e] = l0;
+        Vx[e] = (l0 + 0.0) + 0.0;
+        v.lam[((size_t)b * v.N + t) * NX + e] = l0;
+      }
+      __syncwarp();
+    }
+    // ================= running knots =================
+    for (int t = Nb - 2; t >= 0; --t) {
+      nkkt++;
+      const double* r = v.rec(set, b, t);
+      // ---- stage inputs
+      for (int e = lane; e < M::D_NSLOT; e += 32) tile[e] = v.tile[((size_t)b * M::D_NSLOT + e) * v.N + t];
+      for (int e = lane; e < NU; e += 32) {
+        us[e] = r[R::U + e]; il[e] = r[R::IL + e]; iu[e] = r[R::IU + e]; zl[e] = r[R::ZL + e]; zu[e] = r[R::ZU + e];
+      }
+      for (int e = lane; e < NC; e += 32) phi[e] = r[R::PHI + e];
+      for (int e = lane; e < NX; e += 32) xs[e] = r[R::X + e];
+      for (int e = lane; e < L::KP; e += 32) lhs[e] = 0.0;
+      for (int e = lane; e < K * NR; e += 32) rhs0[e] = 0.0;
+      for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
+      for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
+      __syncwarp();
+      // ---- scatter pass 1: fx, fu (non-constant part), cu -> lhs top-right, cx -> rhs0, lu -> rhs0 col 0,
+      //      lux -> rhs0 B block, lxx -> C, lx, c -> rhs0
+      for (int e = lane; e < M::D_fx_N; e += 32) { const MEntry q = tbl[M::D_fx_OFF + e]; if (q.slot >= 0) fx[q.i + q.j * NX] = tile[q.slot]; }
+      for (int e = lane; e < M::D_fu_N; e += 32) { const MEntry q = tbl[M::D_fu_OFF + e]; if (q.slot >= 0) fu[q.i + q.j * NX] = tile[q.slot]; }
+      for (int e = lane; e < M::D_cu_N; e += 32) { const MEntry q = tbl[M::D_cu_OFF + e]; lhs[pk(q.j, NU + q.i)] = val(q); }
+      for (int e = lane; e < M::D_cx_N; e += 32) { const MEntry q = tbl[M::D_cx_OFF + e]; rhs0[NU + q.i + (1 + q.j) * K] = val(q); }
+      for (int e = lane; e < M::D_lu_N; e += 32) { const MEntry q = tbl[M::D_lu_OFF + e]; rhs0[q.i] = val(q); }
+      for (int e = lane; e < M::D_lux_N; e += 32) { const MEntry q = tbl[M::D_lux_OFF + e]; rhs0[q.i + (1 + q.j) * K] = val(q); }
+      for (int e = lane; e < M::D_lxx_N; e += 32) { const MEntry q = tbl[M::D_lxx_OFF + e]; Cm[q.i + q.j * NX] = val(q); }
+      for (int e = lane; e < M::D_lx_N; e += 32) { const MEntry q = tbl[M::D_lx_OFF + e]; lx[q.i] = val(q); }
+      for (int e = lane; e < NC; e += 32) rhs0[NU + e] = r[R::C + e];
+      __syncwarp();
+      // ---- barrier terms, Qu, dual-infeasibility numerator            (src/backward_pass.jl:62-75)
+      for (int i = lane; i < NU; i += 32) {
+        double a1 = 1.0 / il[i], a2 = 1.0 / iu[i];
+        const double cl = a1 * mu, cu_ = a2 * mu;
+        chil[i] = cl; chiu[i] = cu_;
+        const double lu_i = rhs0[i];
+        double dq = 0.0;   // cu' phi
+        {
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          int rr = 0;
+          for (; rr + 3 < NC; rr += 4) {
+            s0 = IPDDP_FMA(lhs[pk(i, NU + rr + 0)], phi[rr + 0], s0);
+            s1 = IPDDP_FMA(lhs[pk(i, NU + rr + 1)], phi[rr + 1], s1);
+            s2 = IPDDP_FMA(lhs[pk(i, NU + rr + 2)], phi[rr + 2], s2);
+            s3 = IPDDP_FMA(lhs[pk(i, NU + rr + 3)], phi[rr + 3], s3);
+          }
+          if (rr < NC) s0 = IPDDP_FMA(lhs[pk(i, NU + rr)], phi[rr], s0);
+          if (rr + 1 < NC) s1 = IPDDP_FMA(lhs[pk(i, NU + rr + 1)], phi[rr + 1], s1);
+          if (rr + 2 < NC) s2 = IPDDP_FMA(lhs[pk(i, NU + rr + 2)], phi[rr + 2], s2);
+          dq = (s0 + s1) + (s2 + s3);
+        }
+        double q = dq + lu_i;
+        q = dot4c<NX>(fu + i * NX, 1, Vx, 1) + q;
+        q -= cl;
+        q += cu_;
+        rhs0[i] = q;   // Qu
+        // dual error numerator: lu + cu'phi - zl + zu + fu'lambda+      (src/solve.jl:127-132)
+        double d = dq + lu_i;
+        d -= zl[i];
+        d += zu[i];
+        d = dot4c<NX>(fu + i * NX, 1, lamn, 1) + d;
+        t1[i] = a1 * zl[i];   // Sigma^L
+        t2[i] = a2 * zu[i];   // Sigma^U
+        ws[i] = fabs(d);
+      }
+      // ---- xx_tmp = fx' Vxx+ ; ux_tmp = fu' Vxx+                        (:80, :91)
+      for (int e = lane; e < NX * NX; e += 32) {
+        const int i = e % NX, j = e / NX;
+        xxt[e] = dot4c<NX>(fx + i * NX, 1, Vxx + j * NX, 1);
+      }
+      for (int e = lane; e < NU * NX; e += 32) {
+        const int i = e % NU, j = e / NU;
+        uxt[e] = dot4c<NX>(fu + i * NX, 1, Vxx + j * NX, 1);
+      }
+      __syncwarp();
+      {  // dual_num = max(dual_num, |.|_inf) -- uniform scan, NaN propagating like Julia's max
+        double m = 0.0;
+        for (int i = 0; i < NU; ++i) m = jmax(m, ws[i]);
+        dual_num = jmax(dual_num, m);
+      }
+      // ---- C += xx_tmp fx ;  H = Sigma + ux_tmp fu (upper) ; B += ux_tmp fx    (:81, :86-99)
+      for (int e = lane; e < NX * NX; e += 32) {
+        const int i = e % NX, j = e / NX;
+        Cm[e] = dot4c<NX>(xxt + i, NX, fx + j * NX, 1) + Cm[e];
+      }
+      for (int e = lane; e < NU * (NU + 1) / 2; e += 32) {
+        const unsigned short q = ij[e];
+        const int i = q & 0xff, j = q >> 8;
+        const double h0 = (i == j) ? (t1[i] + t2[i]) : 0.0;
+        lhs[e] = dot4c<NX>(uxt + i, NU, fu + j * NX, 1) + h0;
+      }
+      for (int e = lane; e < NU * NX; e += 32) {
+        const int i = e % NU, j = e / NU;
+        rhs0[i + (1 + j) * K] = dot4c<NX>(uxt + i, NU, fx + j * NX, 1) + rhs0[i + (1 + j) * K];
+      }
+      __syncwarp();
+      // ---- H += luu
+      for (int e = lane; e < M::D_luu_N; e += 32) { const MEntry q = tbl[M::D_luu_OFF + e]; lhs[pk(q.i, q.j)] += val(q); }
+      __syncwarp();
+      if (second_order) {
+        if constexpr (M::VF_NSLOT > 0) {   // dynamics Hessian contraction with lambda+ (:102-110), evaluated redundantly per lane
+          double vfl[M::VF_NSLOT > 0 ? M::VF_NSLOT : 1];
+          auto st = [&](int s, double x_) { vfl[s] = x_; };
+          M::vf(xs, us, lamn, p, st);
+          if (lane == 0)
+            for (int s = 0; s < M::VF_NSLOT; ++s) vfs[s] = vfl[s];
+          __syncwarp();
+          for (int e = lane; e < M::VF_vfxx_N; e += 32) { const MEntry q = tbl[M::VF_vfxx_OFF + e]; Cm[q.i + q.j * NX] += (q.slot >= 0 ? vfs[q.slot] : cst[-1 - q.slot]); }
+          for (int e = lane; e < M::VF_vfux_N; e += 32) { const MEntry q = tbl[M::VF_vfux_OFF + e]; rhs0[q.i + (1 + q.j) * K] += (q.slot >= 0 ? vfs[q.slot] : cst[-1 - q.slot]); }
+          for (int e = lane; e < M::VF_vfuu_N; e += 32) { const MEntry q = tbl[M::VF_vfuu_OFF + e]; lhs[pk(q.i, q.j)] += (q.slot >= 0 ? vfs[q.slot] : cst[-1 - q.slot]); }
+          __syncwarp();
+        }
+        for (int e = lane; e < M::D_vcuu_N; e += 32) { const MEntry q = tbl[M::D_vcuu_OFF + e]; lhs[pk(q.i, q.j)] += val(q); }
+        for (int e = lane; e < M::D_vcux_N; e += 32) { const MEntry q = tbl[M::D_vcux_OFF + e]; rhs0[q.i + (1 + q.j) * K] += val(q); }
+        for (int e = lane; e < M::D_vcxx_N; e += 32) { const MEntry q = tbl[M::D_vcxx_OFF + e]; Cm[q.i + q.j * NX] += val(q); }
+        __syncwarp();
+      }
+      if (reg > 0.0)
+        for (int i = lane; i < NU; i += 32) lhs[pk(i, i)] += reg;
+      if (delta_c > 0.0)
+        for (int i = lane; i < NC; i += 32) lhs[pk(NU + i, NU + i)] -= delta_c;
+      // ---- rhs = -rhs0                                                  (:129-136)
+      for (int e = lane; e < K * NR; e += 32) rhs[e] = rhs0[e] * -1.0;
+      __syncwarp();
+      // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
+      const int info = warp_sytf2_rook(K, lhs, ipiv, ij, ws, lane);
+      delta_c = 0.0;
+      if (info > 0) delta_c = v.opt.delta_c * dm::pow(mu, v.opt.kappa_c);
+      const int np = warp_inertia_np(K, lhs, ipiv, 1e-12);
+      if (np != NU || info != 0) {
+        if (reg == 0.0) reg = (reg_last == 0.0) ? v.opt.reg_1 : jmax(v.opt.reg_min, v.opt.kappa_w_m * reg_last);
+        else reg = (reg_last == 0.0) ? v.opt.kappa_bar_w_p * reg : v.opt.kappa_w_p * reg;
+        status = 1;
+        break;
+      }
+      warp_sytrs_rook<NR>(K, lhs, ipiv, rhs, lane);
+      // ---- gains to HBM: eq block, then ineq block                      (:159-172)
+      double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
+      for (int e = lane; e < K * NR; e += 32) g[e] = rhs[e];
+      double* gi = g + K * NR;
+      for (int e = lane; e < NU * NR; e += 32) {
+        const int i = e % NU, j = e / NU;
+        if (j == 0) {
+          const double al = rhs[i];
+          double cl = chil[i];
+          cl -= zl[i];
+          cl -= t1[i] * al;
+          double cu_ = chiu[i];
+          cu_ -= zu[i];
+          cu_ += t2[i] * al;
+          gi[i] = cl;
+          gi[NU + i] = cu_;
+        } else {
+          const double be = rhs[i + j * K];
+          gi[i + j * 2 * NU] = (be * t1[i]) * -1.0;
+          gi[NU + i + j * 2 * NU] = be * t2[i];
+        }
+      }
+      double* qo = v.Qu + ((size_t)b * (v.N - 1) + t) * NU;
+      for (int e = lane; e < NU; e += 32) qo[e] = rhs0[e];
+      // ---- Vxx = beta' B + omega' cx + C ; Vx ; lambda                  (:176-189)
+      // 4 lanes per output element: partial sums over i mod 4, butterfly combine = dot4 order
+      {
+        const int g4 = lane & 3;
+        for (int e0 = 0; e0 < NX * NX; e0 += 8) {
+          const int e = e0 + (lane >> 2);
+          const int i = e % NX, j = e / NX;
+          double sa = 0.0, sb = 0.0;
+          if (e < NX * NX) {
+            for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], rhs0[q + (1 + j) * K], sa);
+            for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], rhs0[NU + q + (1 + j) * K], sb);
+          }
+          sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
+          sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
+          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
+          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
+          if (e < NX * NX && g4 == 0) {
+            double w = sa;
+            w = sb + w;
+            w += Cm[e];
+            nVxx[e] = w;
+          }
+        }
+        for (int e0 = 0; e0 < NX; e0 += 8) {
+          const int i = e0 + (lane >> 2);
+          double sa = 0.0, sb = 0.0, sc = 0.0;
+          if (i < NX) {
+            for (int q = g4; q < NC; q += 4) sc = IPDDP_FMA(rhs0[NU + q + (1 + i) * K], phi[q], sc);        // cx' phi
+            for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], rhs0[q], sa);             // beta' Qu
+            for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], rhs0[NU + q], sb);   // omega' c
+          }
+          sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
+          sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
+          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
+          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
+          sc = sc + __shfl_xor_sync(IPDDP_FULL_MASK, sc, 1);
+          sc = sc + __shfl_xor_sync(IPDDP_FULL_MASK, sc, 2);
+          if (i < NX && g4 == 0) {
+            double w = lx[i];
+            w = sc + w;
+            double lv = w;
+            w = sa + w;
+            w = sb + w;
+            w = dot4c<NX>(fx + i * NX, 1, Vx, 1) + w;
+            lv = dot4c<NX>(fx + i * NX, 1, lamn, 1) + lv;
+            nVx[i] = w;
+            nlam[i] = lv;
+          }
+        }
+      }
+      __syncwarp();
+      for (int e = lane; e < NX * NX; e += 32) Vxx[e] = nVxx[e];
+      for (int e = lane; e < NX; e += 32) {
+        Vx[e] = nVx[e];
+        lamn[e] = nlam[e];
+        v.lam[((size_t)b * v.N + t) * NX + e] = nlam[e];
+      }
+      __syncwarp();
+    }
+    if (status == 0) break;
+  }
+  if (lane == 0) {
+    v.sdv(SD_REG_LAST, b) = reg;
+    v.sdv(SD_DUAL_NUM, b) = dual_num;
+    v.siv(SI_STATUS, b) = status;
+    v.siv(SI_NBACK, b) += 1;
+    v.siv(SI_NSWEEP, b) += nsweep;
+    v.siv(SI_NKKT, b) += nkkt;
+  }
+}
+
+}  // namespace ipk

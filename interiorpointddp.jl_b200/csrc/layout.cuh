@@ -1,0 +1,73 @@
+// Device data layout of one batched problem (all FP64 unless noted).
+//
+// Instance-major records ("array of instance records"): every kernel addresses instance b through
+// b * stride, so active-set compaction is a pure index indirection (list of instance ids) and never
+// moves data.  Inside an instance:
+//   traj   [2 sets][B][N][TR]   one record per knot: x | u | c | il | iu | phi | zl | zu  (TR = nx+5nu+2nc)
+//                               set `nomsel[b]` is the nominal trajectory, the other one the trial
+//                               ("current") trajectory; accepting a step flips nomsel (no copy;
+//                               reference copies 9 arrays, src/data/methods.jl:78-91)
+//   lam    [B][N][nx]           costate of the last sweep
+//   tile   [B][D_NSLOT][N]      compact derivative tile, knot index fastest: the derivative kernel
+//                               (one thread per (instance, knot)) writes 32 consecutive knots per warp
+//                               store = coalesced; the backward kernel reads a knot's slots with one
+//                               32-byte sector per slot covering 4 consecutive knots
+//   tileN  [B][DN_NSLOT]        terminal-stage derivative slots
+//   gains  [B][N-1][G]          eq block K x (nx+1) col-major ([alpha beta; psi omega]) followed by the
+//                               ineq block 2nu x (nx+1) ([chil zetal; chiu zetau]) -- the reference's
+//                               `eq`/`ineq` matrices (src/data/update_rule.jl:71-84); G = (K+2nu)(nx+1)
+//   Qu     [B][N-1][nu]
+//   sd/si  [field][B]           SolverData scalars, structure of arrays
+//   filter [2][FCAP][B]
+#pragma once
+#include "../../include/ipddp_b200.h"
+#include "simt_compat.cuh"
+
+enum SD {  // double scalars
+  SD_MU = 0, SD_REG_LAST, SD_OBJECTIVE, SD_PRIMAL_INF, SD_DUAL_INF, SD_CS_INF, SD_L_CURR, SD_THETA_CURR,
+  SD_L_NEXT, SD_THETA_NEXT, SD_THETA_MAX, SD_THETA_MIN, SD_STEP, SD_DUAL_NUM, SD_COUNT
+};
+enum SI {  // int scalars
+  SI_STATUS = 0, SI_K, SI_J, SI_L, SI_FILTER_N, SI_SWITCHING, SI_ARMIJO, SI_DONE, SI_NBACK, SI_NSWEEP, SI_NKKT,
+  SI_NROLL, SI_NDERIV, SI_TRACE_N, SI_COUNT
+};
+enum CNT { CNT_NEXT = 0, CNT_FWD = 1, CNT_DONE = 2, CNT_COUNT = 8 };
+
+struct DevView {
+  int B, N;
+  int nx, nu, nc, np;
+  int TR, G;                 // record sizes (doubles)
+  int n_compl;
+  const int* compl_idx;
+  // inputs
+  const double* p;           // [B][np]
+  const double* lower;       // [B][nu]
+  const double* upper;       // [B][nu]
+  const double* x1;          // [B][nx]
+  const double* ubar;        // [B][(N-1) nu]
+  const int* horizon;        // [B]
+  // state
+  double* traj;              // [2][B][N][TR]
+  int* nomsel;               // [B]
+  double* lam;               // [B][N][nx]
+  double* tile;              // [B][D_NSLOT][N]
+  double* tileN;             // [B][DN_NSLOT]
+  double* gains;             // [B][N-1][G]
+  double* Qu;                // [B][N-1][nu]
+  double* sd;                // [SD_COUNT][B]
+  int* si;                   // [SI_COUNT][B]
+  double* filter;            // [2][FCAP][B]
+  double* trace;             // [B][trace_cap][IPDDP_TRACE_COLS]
+  int trace_cap;
+  ipddp_options opt;
+
+  IPDDP_D double* rec(int set, int b, int t) const { return traj + (((size_t)set * B + b) * N + t) * TR; }
+  IPDDP_D double& sdv(int f, int b) const { return sd[(size_t)f * B + b]; }
+  IPDDP_D int& siv(int f, int b) const { return si[(size_t)f * B + b]; }
+};
+
+// offsets inside a trajectory record
+template <class M> struct Rec {
+  static constexpr int X = 0, U = M::NX, C = U + M::NU, IL = C + M::NC, IU = IL + M::NU, PHI = IU + M::NU,
+                       ZL = PHI + M::NC, ZU = ZL + M::NU, SIZE = ZU + M::NU;
+};

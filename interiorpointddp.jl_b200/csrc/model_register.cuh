@@ -1,0 +1,60 @@
+// Per-model host launchers.  Each model translation unit (csrc/models/<name>.cu, or a generated plugin)
+// instantiates the kernel templates for its Model_<name> struct and exports one vtable.
+#pragma once
+#include "kernels_thread.cuh"
+#include "kernel_backward.cuh"
+#include "vtable.h"
+
+namespace ipk {
+
+template <class M> struct Launch {
+  static void init(const DevView& v, int warm, int* list_next, int* counters, cudaStream_t s) {
+    const int th = 64;
+    IPDDP_LAUNCH((k_init<M>), (v.B + th - 1) / th, th, 0, s, v, warm, list_next, counters);
+  }
+  static void derivs(const DevView& v, const int* list, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    const int th = 128;
+    const long long total = (long long)n * v.N;
+    IPDDP_LAUNCH((k_derivs<M>), (unsigned)((total + th - 1) / th), th, 0, s, v, list, n);
+  }
+  static void backward(const DevView& v, const int* list, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    IPDDP_LAUNCH((k_backward<M>), n, 32, BwLayout<M>::BYTES, s, v, list, n);
+  }
+  static void check(const DevView& v, const int* list, int n, int* list_next, int* list_fwd, int* counters,
+                    cudaStream_t s) {
+    if (n <= 0) return;
+    const int th = 64;
+    IPDDP_LAUNCH((k_check<M>), (n + th - 1) / th, th, 0, s, v, list, n, list_next, list_fwd, counters);
+  }
+  static void forward(const DevView& v, const int* list_fwd, int n_upper, int* list_next, int* counters,
+                      cudaStream_t s) {
+    if (n_upper <= 0) return;
+    const int th = 32;
+    IPDDP_LAUNCH((k_forward<M>), (n_upper + th - 1) / th, th, 0, s, v, list_fwd, list_next, counters);
+  }
+  static int prepare() {
+#ifndef IPDDP_SIMT_EMU
+    if (BwLayout<M>::BYTES > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_backward<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           BwLayout<M>::BYTES);
+      if (e != cudaSuccess) return -1;
+    }
+#endif
+    return 0;
+  }
+};
+
+template <class M> const ModelVTable* make_vtable() {
+  static const ModelVTable vt = {
+      M::NAME, M::NX, M::NU, M::NC, M::NP, M::D_NSLOT, M::DN_NSLOT, M::VF_NSLOT, BwLayout<M>::BYTES,
+      &Launch<M>::init, &Launch<M>::derivs, &Launch<M>::backward, &Launch<M>::check, &Launch<M>::forward,
+      &Launch<M>::prepare};
+  return &vt;
+}
+
+}  // namespace ipk
+
+#define IPDDP_REGISTER_MODEL(M, sym) \
+  extern "C" const ModelVTable* sym() { return ipk::make_vtable<M>(); }

@@ -1,0 +1,102 @@
+// TEST INFRASTRUCTURE ONLY -- runtime of the SIMT emulator (see cpu_simt.h).
+#include "cpu_simt.h"
+
+#include <omp.h>
+
+namespace emu {
+thread_local BlockState* tls_block = nullptr;
+thread_local dim3 tls_threadIdx, tls_blockIdx, tls_blockDim, tls_gridDim;
+}
+
+extern "C" void emu_switch(void** save_sp, void* new_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+
+namespace emu {
+
+static const size_t kStack = 512 * 1024;
+
+static void trampoline() {
+  BlockState* b = tls_block;
+  (*b->body)();
+  Fiber& f = b->fibers[b->current];
+  f.done = true;
+  void* dummy;
+  emu_switch(&dummy, b->sched_sp);
+  abort();
+}
+
+void yield_barrier() {
+  BlockState* b = tls_block;
+  Fiber& f = b->fibers[b->current];
+  emu_switch(&f.sp, b->sched_sp);
+}
+
+static void run_block(BlockState& bs, dim3 grid, dim3 block, unsigned bx, size_t smem, const std::function<void()>& body) {
+  const int T = block.x;
+  bs.body = &body;
+  if ((int)bs.fibers.size() < T) {
+    bs.fibers.resize(T);
+    bs.stacks.resize((size_t)T * kStack);
+  }
+  if (bs.smem.size() < smem + 64) bs.smem.resize(smem + 64);
+  for (int t = 0; t < T; ++t) {
+    Fiber& f = bs.fibers[t];
+    f.done = false;
+    f.stack = bs.stacks.data() + (size_t)t * kStack;
+    uintptr_t top = ((uintptr_t)(f.stack + kStack)) & ~(uintptr_t)15;
+    void** A = (void**)(top - 16);
+    *A = (void*)&trampoline;
+    void** sp = A - 6;
+    for (int q = 0; q < 6; ++q) sp[q] = nullptr;
+    f.sp = (void*)sp;
+  }
+  tls_block = &bs;
+  tls_blockIdx = dim3(bx, 0, 0);
+  tls_blockDim = block;
+  tls_gridDim = grid;
+  int alive = T;
+  while (alive > 0) {
+    alive = 0;
+    for (int t = 0; t < T; ++t) {
+      Fiber& f = bs.fibers[t];
+      if (f.done) continue;
+      bs.current = t;
+      tls_threadIdx = dim3(t, 0, 0);
+      emu_switch(&bs.sched_sp, f.sp);
+      if (!f.done) alive++;
+    }
+  }
+}
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+  const int G = (int)grid.x;
+#pragma omp parallel
+  {
+    static thread_local BlockState bs;
+#pragma omp for schedule(dynamic, 1)
+    for (int bx = 0; bx < G; ++bx) run_block(bs, grid, block, (unsigned)bx, smem, body);
+  }
+}
+
+}  // namespace emu
