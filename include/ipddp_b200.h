@@ -160,6 +160,17 @@ void* ipddp_stream(ipddp_problem* h);
 double ipddp_measure_fp64_tflops(int device);
 double ipddp_measure_hbm_gbs(int device);
 
+/* Kernel-level test hooks (used by tests/ only).
+ *   ipddp_test_detmath: elementwise device evaluation of the deterministic math layer;
+ *       fn 0 sin, 1 cos, 2 tan, 3 log, 4 exp, 5 pow(x[i], y[i]).
+ *   ipddp_test_ldlt: one warp per matrix runs the device dsytf2_rook('U') / inertia / dsytrs_rook path on
+ *       nmat dense column-major n x n matrices (upper triangle read) with 5 right-hand sides each.
+ *       Outputs: Aout [nmat][n*n] (upper triangle = factors), ipiv [nmat][n] (LAPACK 1-based convention),
+ *       info [nmat], npos [nmat] (positive eigenvalues of D, tol 1e-12), X [nmat][n*5] (solution). */
+int ipddp_test_detmath(int fn, int n, const double* x, const double* y, double* out, int device);
+int ipddp_test_ldlt(int n, int nmat, const double* A, const double* Bm, double* Aout, int* ipiv, int* info,
+                    int* npos, double* X, int device);
+
 #ifdef __cplusplus
 }
 #endif

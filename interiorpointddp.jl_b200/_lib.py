@@ -23,6 +23,7 @@ EXPORTS = [
     "ipddp_eval_derivatives", "ipddp_backward_pass", "ipddp_check", "ipddp_forward_pass", "ipddp_get_results",
     "ipddp_get_trajectory", "ipddp_get_duals", "ipddp_get_counters", "ipddp_get_array", "ipddp_get_trace",
     "ipddp_get_stats", "ipddp_stream", "ipddp_measure_fp64_tflops", "ipddp_measure_hbm_gbs",
+    "ipddp_test_detmath", "ipddp_test_ldlt",
 ]
 
 
@@ -96,6 +97,8 @@ class Lib:
         L.ipddp_measure_fp64_tflops.argtypes = [C.c_int]
         L.ipddp_measure_hbm_gbs.restype = C.c_double
         L.ipddp_measure_hbm_gbs.argtypes = [C.c_int]
+        L.ipddp_test_detmath.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_int]
+        L.ipddp_test_ldlt.argtypes = [C.c_int, C.c_int, dp, dp, dp, ip, ip, ip, dp, C.c_int]
 
     def check(self, rc, what=""):
         if rc != 0:

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "kernels_common.cuh"
+#include "ldlt_warp.cuh"
 #include "vtable.h"
 
 extern "C" {
@@ -74,6 +75,51 @@ __global__ void k_fp64_peak(double* out, int iters) {
 __global__ void k_copy(const double4* __restrict__ a, double4* __restrict__ b, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     b[i] = a[i];
+}
+
+__global__ void k_test_detmath(int fn, int n, const double* x, const double* y, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r;
+  switch (fn) {
+    case 0: r = dm::sin(x[i]); break;
+    case 1: r = dm::cos(x[i]); break;
+    case 2: r = dm::tan(x[i]); break;
+    case 3: r = dm::log(x[i]); break;
+    case 4: r = dm::exp(x[i]); break;
+    default: r = dm::pow(x[i], y[i]); break;
+  }
+  out[i] = r;
+}
+
+// one warp per matrix: dense -> packed smem, factor, inertia, solve 5 rhs, packed -> dense
+__global__ void k_test_ldlt(int n, int nmat, const double* A, const double* Bm, double* Aout, int* ipiv_out,
+                            int* info_out, int* np_out, double* X) {
+  IPDDP_DYN_SMEM(double, sm);
+  const int lane = threadIdx.x, m = blockIdx.x;
+  if (m >= nmat) return;
+  const int kp = n * (n + 1) / 2;
+  double* lhs = sm;
+  double* rhs = lhs + kp;
+  double* ws = rhs + n * 5;
+  int* ipiv = reinterpret_cast<int*>(ws + 4 * n);
+  unsigned short* ij = reinterpret_cast<unsigned short*>(ipiv + n);
+  for (int j = 0; j < n; ++j)
+    for (int i = lane; i <= j; i += 32) {
+      ij[ipk::pk(i, j)] = (unsigned short)(i | (j << 8));
+      lhs[ipk::pk(i, j)] = A[(size_t)m * n * n + i + (size_t)j * n];
+    }
+  for (int e = lane; e < n * 5; e += 32) rhs[e] = Bm[(size_t)m * n * 5 + e];
+  __syncwarp();
+  const int info = ipk::warp_sytf2_rook(n, lhs, ipiv, ij, ws, lane);
+  const int np = ipk::warp_inertia_np(n, lhs, ipiv, 1e-12);
+  if (info == 0) ipk::warp_sytrs_rook<5>(n, lhs, ipiv, rhs, lane);
+  __syncwarp();
+  for (int j = 0; j < n; ++j)
+    for (int i = lane; i <= j; i += 32) Aout[(size_t)m * n * n + i + (size_t)j * n] = lhs[ipk::pk(i, j)];
+  for (int e = lane; e < n * 5; e += 32) X[(size_t)m * n * 5 + e] = rhs[e];
+  for (int e = lane; e < n; e += 32) ipiv_out[(size_t)m * n + e] = ipiv[e];
+  if (lane == 0) { info_out[m] = info; np_out[m] = np; }
 }
 
 }  // namespace
@@ -544,6 +590,44 @@ double ipddp_measure_hbm_gbs(int device) {
   cudaEventDestroy(a); cudaEventDestroy(b);
   cudaFree(x); cudaFree(y);
   return best;
+}
+
+int ipddp_test_detmath(int fn, int n, const double* x, const double* y, double* out, int device) {
+  CK(cudaSetDevice(device));
+  double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  CK(cudaMalloc((void**)&dx, (size_t)n * 8)); CK(cudaMalloc((void**)&dy, (size_t)n * 8)); CK(cudaMalloc((void**)&dout, (size_t)n * 8));
+  CK(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dy, y, (size_t)n * 8, cudaMemcpyHostToDevice));
+  IPDDP_LAUNCH(k_test_detmath, (n + 255) / 256, 256, 0, 0, fn, n, dx, dy, dout);
+  CK(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaGetLastError());
+  cudaFree(dx); cudaFree(dy); cudaFree(dout);
+  return 0;
+}
+
+int ipddp_test_ldlt(int n, int nmat, const double* A, const double* Bm, double* Aout, int* ipiv, int* info,
+                    int* npos, double* X, int device) {
+  if (n < 1 || n > 64) return fail("n out of range");
+  CK(cudaSetDevice(device));
+  const size_t sa = (size_t)nmat * n * n * 8, sb = (size_t)nmat * n * 5 * 8;
+  double *dA = nullptr, *dB = nullptr, *dAo = nullptr, *dX = nullptr;
+  int *dip = nullptr, *dinfo = nullptr, *dnp = nullptr;
+  CK(cudaMalloc((void**)&dA, sa)); CK(cudaMalloc((void**)&dAo, sa)); CK(cudaMalloc((void**)&dB, sb)); CK(cudaMalloc((void**)&dX, sb));
+  CK(cudaMalloc((void**)&dip, (size_t)nmat * n * 4)); CK(cudaMalloc((void**)&dinfo, (size_t)nmat * 4)); CK(cudaMalloc((void**)&dnp, (size_t)nmat * 4));
+  CK(cudaMemcpy(dA, A, sa, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, Bm, sb, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dAo, 0, sa));
+  const int kp = n * (n + 1) / 2;
+  const size_t smem = ((size_t)(kp + n * 5 + 4 * n) * 8 + (size_t)n * 4 + (size_t)kp * 2 + 15) / 16 * 16;
+  IPDDP_LAUNCH(k_test_ldlt, nmat, 32, smem, 0, n, nmat, dA, dB, dAo, dip, dinfo, dnp, dX);
+  CK(cudaMemcpy(Aout, dAo, sa, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(X, dX, sb, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ipiv, dip, (size_t)nmat * n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(info, dinfo, (size_t)nmat * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(npos, dnp, (size_t)nmat * 4, cudaMemcpyDeviceToHost));
+  CK(cudaGetLastError());
+  cudaFree(dA); cudaFree(dB); cudaFree(dAo); cudaFree(dX); cudaFree(dip); cudaFree(dinfo); cudaFree(dnp);
+  return 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,236 @@
+"""Parity checks shared by the GPU tests (-m gpu, through libipddp_b200.so on a B200) and the CPU-side
+emulator tests (same C ABI, kernels compiled against tests/emu/cpu_simt.h).  The checker is always the
+oracle (oracle/); the bar is BIT equality for every compared quantity (see DESIGN.md "Parity")."""
+import ctypes as C
+
+import numpy as np
+
+import ipddp_b200  # noqa: F401
+from ipddp_b200 import instances
+from ipddp_b200.batch import BatchSolver
+from ipddp_b200.codegen import generate, workloads
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.int64)
+
+
+def assert_same_bits(a, b, what):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    # +0.0 and -0.0 are both accepted as zero (structural zeros are skipped on the device)
+    same = (bits(a) == bits(b)) | ((a == 0.0) & (b == 0.0)) | (np.isnan(a) & np.isnan(b))
+    if not same.all():
+        idx = np.argwhere(~same)[0]
+        raise AssertionError(f"{what}: {int((~same).sum())} of {a.size} entries differ, first at {tuple(idx)}: "
+                             f"{a[tuple(idx)]!r} vs {b[tuple(idx)]!r}")
+
+
+def full_solve_parity(lib, oracle, wl, B, N=101, maxit=1000, tol=1e-7, vary_horizon=False, first=0, n_trace=4,
+                      check_traj=True):
+    """Whole-solve parity: status, k, j, l, objective, errors, step sequence (trace) and trajectories."""
+    b = instances.make_batch(wl, B, N, vary_horizon=vary_horizon, first=first)
+    opt = lib.default_options(optimality_tolerance=tol, max_iterations=maxit)
+    s = BatchSolver(wl, B, N, options=opt, trace_capacity=maxit, lib=lib)
+    s.set_batch(b)
+    r = s.solve()
+    oopt = oracle.default_options(optimality_tolerance=tol, max_iterations=maxit)
+    res, xo, uo = oracle.solve_batch(wl, N, b.p, b.lower, b.upper, b.x1, b.ubar, options=oopt,
+                                     horizons=b.horizons, want_traj=True)
+    for i in range(B):
+        o = res[i]
+        got = (int(r.status[i]), int(r.k[i]), int(r.j[i]))
+        assert got == (o.status, o.k, o.j), f"{wl} inst {first+i}: (status,k,j) gpu {got} vs oracle {(o.status, o.k, o.j)}"
+        for name in ("objective", "primal_inf", "dual_inf", "cs_inf", "mu", "reg_last", "step_size"):
+            assert_same_bits(getattr(r, name)[i], getattr(o, name), f"{wl} inst {first+i} {name}")
+        assert int(r.l[i]) == o.l
+    cnt = s.counters()
+    for i in range(B):
+        assert (cnt["n_backward"][i], cnt["n_sweeps"][i], cnt["n_kkt"][i], cnt["n_rollouts"][i]) == \
+            (res[i].n_backward, res[i].n_sweeps, res[i].n_kkt, res[i].n_rollouts), f"{wl} inst {i}: work counters"
+    if check_traj:
+        x, u = s.trajectory()
+        assert_same_bits(x, xo, f"{wl} states")
+        assert_same_bits(u, uo, f"{wl} controls")
+    for i in range(min(n_trace, B)):
+        o = oracle.OracleSolver(wl, int(b.horizons[i]), b.p[i], b.lower[i], b.upper[i], options=oopt)
+        o.solve(b.x1[i], b.ubar[i][:(int(b.horizons[i]) - 1) * s.nu])
+        assert_same_bits(s.trace(i), o.trace(), f"{wl} inst {first+i} accepted-step trace")
+    st = s.stats()
+    s.close()
+    return r, st
+
+
+def _tile_map(wl):
+    md = workloads.get(wl)
+    bd = generate.trace(md)
+    ents, consts, nslot = generate._device_entries(bd["derivs"])
+    entsN, constsN, nslotN = generate._device_entries(bd["derivsN"])
+    rows = {m: r for (m, r, _) in bd["derivs"].outputs}
+    rowsN = {m: r for (m, r, _) in bd["derivsN"].outputs}
+    return ents, nslot, rows, entsN, nslotN, rowsN
+
+
+def phase_parity(lib, oracle, wl, B=3, N=9, rounds=3):
+    """Kernel-level parity after each phase of the first few iterations:
+    initialise -> derivatives (compact tile vs the oracle's dense matrices) -> backward pass (gains, Qu,
+    costate, reg) -> errors/check -> forward pass (trial trajectory, accepted step)."""
+    b = instances.make_batch(wl, B, N)
+    opt = lib.default_options(optimality_tolerance=1e-7)
+    s = BatchSolver(wl, B, N, options=opt, lib=lib)
+    s.set_batch(b)
+    nx, nu, nc = s.nx, s.nu, s.nc
+    K = nu + nc
+    G = (K + 2 * nu) * (nx + 1)
+    oopt = oracle.default_options(optimality_tolerance=1e-7)
+    orc = [oracle.OracleSolver(wl, N, b.p[i], b.lower[i], b.upper[i], options=oopt) for i in range(B)]
+    for i, o in enumerate(orc):
+        o.initialize(b.x1[i], b.ubar[i])
+    s.initialize()
+    ents, nslot, rows, entsN, nslotN, rowsN = _tile_map(wl)
+
+    def cmp_traj(prefix=""):
+        for name, dim, nst in (("x", nx, N), ("u", nu, N - 1), ("c", nc, N - 1), ("il", nu, N - 1), ("iu", nu, N - 1),
+                               ("phi", nc, N - 1), ("zl", nu, N - 1), ("zu", nu, N - 1)):
+            g = s.array(prefix + name).reshape(B, nst, dim)
+            for i, o in enumerate(orc):
+                ref = o.array(prefix + name)
+                assert_same_bits(g[i].reshape(-1), ref[:nst * dim], f"{wl} {prefix}{name} inst {i}")
+
+    cmp_traj()
+    for rnd in range(rounds):
+        s.eval_derivatives()
+        tile = s.array("tile").reshape(B, max(nslot, 0), N) if nslot else None
+        tileN = s.array("tileN").reshape(B, nslotN) if nslotN else None
+        for i, o in enumerate(orc):
+            o.eval_derivatives()
+            dense = {m: o.array(m) for m in rows}
+            sizes = {m: dense[m].size // N if m not in ("fx", "fu") else dense[m].size // (N - 1) for m in rows}
+            for en, slot in ents:
+                if slot < 0:
+                    continue
+                per = {"fx": nx * nx, "fu": nx * nu, "lx": nx, "lu": nu, "lxx": nx * nx, "luu": nu * nu, "lux": nu * nx,
+                       "cx": nc * nx, "cu": nc * nu, "vcxx": nx * nx, "vcux": nu * nx, "vcuu": nu * nu}[en.mat]
+                for t in range(N - 1):
+                    off = t * per
+                    if en.mat in ("lx", "lxx", "vcxx"):
+                        off = t * per      # these exist for all N stages with the same size
+                    ref = dense[en.mat][off + en.i + en.j * rows[en.mat]]
+                    assert_same_bits(tile[i, slot, t], ref, f"{wl} tile {en.mat}[{en.i},{en.j}] t={t} inst {i}")
+            for en, slot in entsN:
+                if slot < 0:
+                    continue
+                per = {"lx": nx, "lxx": nx * nx}[en.mat]
+                ref = o.array(en.mat)[(N - 1) * per + en.i + en.j * rowsN[en.mat]]
+                assert_same_bits(tileN[i, slot], ref, f"{wl} tileN {en.mat}[{en.i},{en.j}] inst {i}")
+        s.backward_pass()
+        gains = s.array("gains").reshape(B, N - 1, G)
+        Qu = s.array("Qu").reshape(B, N - 1, nu)
+        lam = s.array("lam").reshape(B, N, nx)
+        sd = s.array("sd").reshape(-1, B)
+        for i, o in enumerate(orc):
+            st = o.backward_pass()
+            assert st == 0
+            eq = o.array("eq")[:(N - 1) * K * (nx + 1)].reshape(N - 1, K * (nx + 1))
+            iq = o.array("ineq")[:(N - 1) * 2 * nu * (nx + 1)].reshape(N - 1, 2 * nu * (nx + 1))
+            assert_same_bits(gains[i, :, :K * (nx + 1)], eq, f"{wl} eq gains inst {i} round {rnd}")
+            assert_same_bits(gains[i, :, K * (nx + 1):], iq, f"{wl} ineq gains inst {i} round {rnd}")
+            assert_same_bits(Qu[i].reshape(-1), o.array("Qu")[:(N - 1) * nu], f"{wl} Qu inst {i}")
+            assert_same_bits(lam[i].reshape(-1), o.array("lam"), f"{wl} costate inst {i}")
+            assert_same_bits(sd[1, i], o.result().reg_last, f"{wl} reg_last inst {i}")
+        nf = s.check()
+        r = s.results()
+        need_fwd = 0
+        for i, o in enumerate(orc):
+            d, pr, cs0, csm = o.errors()
+            assert_same_bits(r.dual_inf[i], d, f"{wl} dual_inf inst {i}")
+            assert_same_bits(r.primal_inf[i], pr, f"{wl} primal_inf inst {i}")
+            assert_same_bits(r.cs_inf[i], cs0, f"{wl} cs_inf inst {i}")
+            need_fwd += 1
+        # the first rounds never converge nor update the barrier parameter on these workloads with mu = 1
+        if nf != need_fwd:
+            break
+        s.forward_pass()
+        for i, o in enumerate(orc):
+            assert o.forward_pass() == 0
+            o.accept_step()
+        cmp_traj()
+        r = s.results()
+        for i, o in enumerate(orc):
+            ro = o.result()
+            assert (int(r.k[i]), int(r.l[i])) == (ro.k, ro.l)
+            assert_same_bits(r.step_size[i], ro.step_size, f"{wl} step inst {i}")
+            assert_same_bits(r.objective[i], ro.objective, f"{wl} objective inst {i}")
+    s.close()
+
+
+def ldlt_parity(lib, oracle, rng, nmat=200, nmax=35, device=0):
+    """Device dsytf2_rook / inertia / dsytrs_rook vs the oracle's restatement: bit-identical factors, pivots,
+    info, inertia and solutions."""
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    for n in sorted(set([1, 2, 3, 4, 14, 15, 17, nmax])):
+        if n > nmax:
+            continue
+        mats = []
+        for i in range(nmat):
+            kind = i % 4
+            if kind == 0 or n < 4:
+                M = rng.standard_normal((n, n)); M = M + M.T
+            elif kind == 1:
+                m = max(1, (2 * n) // 3); p = n - m
+                H = rng.standard_normal((m, m)); H = H @ H.T + np.diag(rng.uniform(0, 5, m))
+                A = rng.standard_normal((p, m)) * (rng.uniform(size=(p, m)) < 0.4)
+                M = np.zeros((n, n)); M[:m, :m] = H; M[:m, m:] = A.T; M[m:, :m] = A
+            elif kind == 2:
+                M = rng.standard_normal((n, n)) * (rng.uniform(size=(n, n)) < 0.3); M = M + M.T
+                np.fill_diagonal(M, 0.0)
+            else:
+                M = rng.standard_normal((n, n)); M = M + M.T
+                sc = 10.0 ** rng.uniform(-5, 5, n); M = M * sc[:, None] * sc[None, :]
+            mats.append(np.asfortranarray(M))
+        A = np.stack([m.reshape(-1, order="F") for m in mats])
+        Bm = rng.standard_normal((nmat, n * 5))
+        Aout = np.zeros_like(A); X = np.zeros_like(Bm)
+        ipiv = np.zeros((nmat, n), dtype=np.int32); info = np.zeros(nmat, dtype=np.int32); npos = np.zeros(nmat, dtype=np.int32)
+        rc = lib.L.ipddp_test_ldlt(n, nmat, A.ctypes.data_as(dp), Bm.ctypes.data_as(dp), Aout.ctypes.data_as(dp),
+                                   ipiv.ctypes.data_as(ip), info.ctypes.data_as(ip), npos.ctypes.data_as(ip),
+                                   X.ctypes.data_as(dp), device)
+        lib.check(rc, "ipddp_test_ldlt")
+        n2 = 0
+        for i in range(nmat):
+            a = mats[i].copy(order="F")
+            piv = np.zeros(n + 1, dtype=np.int32)
+            inf_o = oracle.lib().oracle_sytf2_rook(n, a.ctypes.data_as(dp), n, piv.ctypes.data_as(ip))
+            assert inf_o == info[i], f"n={n} mat {i}: info {info[i]} vs {inf_o}"
+            assert np.array_equal(piv[:n], ipiv[i]), f"n={n} mat {i}: pivots differ"
+            iu = np.triu_indices(n)
+            got = Aout[i].reshape(n, n, order="F")
+            assert_same_bits(got[iu], a[iu], f"n={n} mat {i} factors")
+            np_o = oracle.lib().oracle_inertia_np(n, a.ctypes.data_as(dp), n, piv.ctypes.data_as(ip), 1e-12)
+            assert np_o == npos[i]
+            n2 += int((piv[:n] < 0).any())
+            if inf_o == 0:
+                bo = np.asfortranarray(Bm[i].reshape(n, 5, order="F").copy())
+                oracle.lib().oracle_sytrs_rook(n, 5, a.ctypes.data_as(dp), n, piv.ctypes.data_as(ip),
+                                               bo.ctypes.data_as(dp), n)
+                assert_same_bits(X[i].reshape(n, 5, order="F"), bo, f"n={n} mat {i} solution")
+        if n >= 4:
+            assert n2 > nmat // 10
+
+
+def detmath_parity(lib, oracle, rng, n=200000, device=0):
+    dp = C.POINTER(C.c_double)
+    cases = {
+        0: np.concatenate([rng.uniform(-10, 10, n), rng.uniform(-1e4, 1e4, n), rng.uniform(-1e-3, 1e-3, 1000), [0.0, np.inf, np.nan]]),
+        3: np.concatenate([rng.uniform(1e-300, 10, n), np.exp(rng.uniform(-700, 700, n)), [0.0, -1.0, np.inf, 5e-324, 1.0]]),
+        4: np.concatenate([rng.uniform(-745, 710, n), rng.uniform(-1, 1, n), [800.0, -800.0, 0.0]]),
+    }
+    cases[1] = cases[0]; cases[2] = cases[0]
+    for fn, x in cases.items():
+        x = np.ascontiguousarray(x); y = np.zeros_like(x); out = np.zeros_like(x)
+        lib.check(lib.L.ipddp_test_detmath(fn, x.size, x.ctypes.data_as(dp), y.ctypes.data_as(dp), out.ctypes.data_as(dp), device), "detmath")
+        ref = oracle.detmath(fn, x)
+        assert np.array_equal(bits(out), bits(ref)) or np.all((bits(out) == bits(ref)) | (np.isnan(out) & np.isnan(ref))), f"detmath fn {fn}"
+    x = np.ascontiguousarray(rng.uniform(1e-9, 3, n)); y = np.ascontiguousarray(rng.uniform(-3, 4, n)); out = np.zeros_like(x)
+    lib.check(lib.L.ipddp_test_detmath(5, n, x.ctypes.data_as(dp), y.ctypes.data_as(dp), out.ctypes.data_as(dp), device), "detmath")
+    assert np.array_equal(bits(out), bits(oracle.detmath(5, x, y)))

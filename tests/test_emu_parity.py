@@ -1,0 +1,43 @@
+"""CPU-side logic checks of the CUDA kernel SOURCES: the product's .cu/.cuh files are compiled with g++ against
+the fiber-based SIMT emulator in tests/emu (test infrastructure, never loaded by the package) and driven
+through the same C ABI.  Small sizes only; the real parity tests run on the GPU (test_gpu_*.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    from ipddp_b200 import _lib
+    return _lib.Lib(build_emu.build())
+
+
+@pytest.mark.parametrize("wl,B,N,maxit", [("double_integrator", 2, 101, 1000), ("cartpole", 2, 9, 25),
+                                          ("acrobot", 2, 9, 30), ("concar", 3, 11, 60), ("concar_quad", 2, 11, 60),
+                                          ("pushing", 2, 9, 30)])
+def test_emulated_full_solve(emu, oracle_mod, wl, B, N, maxit):
+    helpers.full_solve_parity(emu, oracle_mod, wl, B, N, maxit=maxit, n_trace=B)
+
+
+def test_emulated_varying_horizon(emu, oracle_mod):
+    helpers.full_solve_parity(emu, oracle_mod, "concar", 4, 13, maxit=80, vary_horizon=True, first=100, n_trace=4)
+
+
+@pytest.mark.parametrize("wl", ["double_integrator", "cartpole", "concar", "pushing"])
+def test_emulated_phases(emu, oracle_mod, wl):
+    helpers.phase_parity(emu, oracle_mod, wl, B=2, N=7, rounds=2)
+
+
+def test_emulated_ldlt(emu, oracle_mod):
+    helpers.ldlt_parity(emu, oracle_mod, np.random.default_rng(3), nmat=24, nmax=35)
+
+
+def test_emulated_detmath(emu, oracle_mod):
+    helpers.detmath_parity(emu, oracle_mod, np.random.default_rng(4), n=5000)

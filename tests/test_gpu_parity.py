@@ -1,0 +1,132 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI of
+libipddp_b200.so, against the CPU oracle on the same seeded inputs.  Bar: bit equality of status, iteration
+counts, accepted-step trace, objective, infeasibilities and trajectories (DESIGN.md "Parity").  Golden
+known-answer rows of the reference are re-checked on the GPU output directly."""
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "no CUDA device"
+    from ipddp_b200 import _lib
+    return _lib.load()
+
+
+def test_detmath_bit_exact(gpu, oracle_mod):
+    helpers.detmath_parity(gpu, oracle_mod, np.random.default_rng(4), n=200000)
+
+
+def test_ldlt_bit_exact(gpu, oracle_mod):
+    helpers.ldlt_parity(gpu, oracle_mod, np.random.default_rng(3), nmat=400, nmax=35)
+
+
+@pytest.mark.parametrize("wl", ["double_integrator", "cartpole", "acrobot", "concar", "concar_quad", "pushing"])
+def test_phase_parity(gpu, oracle_mod, wl):
+    helpers.phase_parity(gpu, oracle_mod, wl, B=4, N=21, rounds=3)
+
+
+@pytest.mark.parametrize("wl,B", [("double_integrator", 1), ("cartpole", 32), ("acrobot", 16), ("concar", 16),
+                                  ("concar_quad", 16), ("pushing", 8)])
+def test_full_solve_parity(gpu, oracle_mod, wl, B):
+    helpers.full_solve_parity(gpu, oracle_mod, wl, B, 101, n_trace=3)
+
+
+def test_varying_horizon_parity(gpu, oracle_mod):
+    """config 5: per-instance horizons (offset tables / horizon vector), synthetic instances."""
+    helpers.full_solve_parity(gpu, oracle_mod, "pushing", 8, 101, vary_horizon=True, first=100, n_trace=2)
+    helpers.full_solve_parity(gpu, oracle_mod, "concar", 12, 61, vary_horizon=True, first=200, n_trace=2)
+
+
+def test_max_iterations_and_short_horizon(gpu, oracle_mod):
+    helpers.full_solve_parity(gpu, oracle_mod, "cartpole", 4, 101, maxit=7)          # status 8
+    helpers.full_solve_parity(gpu, oracle_mod, "double_integrator", 1, 2)           # single running stage
+    helpers.full_solve_parity(gpu, oracle_mod, "acrobot", 3, 3, maxit=50)
+
+
+def test_golden_table_on_gpu(gpu):
+    """The reference's own known answers (experiments/ipddp2/results/cartpole_friction.txt), straight from the GPU."""
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver
+    for wl, frac in (("cartpole", 0.90), ("concar_quad", 0.95), ("double_integrator", 1.0)):
+        g = instances.load_golden_results(wl)
+        n = len(g["seed"])
+        b = instances.make_batch(wl, n, 101)
+        s = BatchSolver(wl, n, 101, options=gpu.default_options(optimality_tolerance=1e-7), lib=gpu)
+        s.set_batch(b)
+        r = s.solve()
+        ok = (r.k == g["iterations"]) & (np.abs(r.objective - g["objective"]) <= 1e-8 * np.maximum(1.0, np.abs(g["objective"])))
+        assert ok.sum() >= frac * n, f"{wl}: {ok.sum()}/{n}"
+        assert np.array_equal(r.status[ok] == 0, g["converged"][ok])
+        s.close()
+
+
+def test_batch_consistency_and_permutation(gpu):
+    """instance i inside a batch == instance i alone; results do not depend on the position in the batch
+    (size-independent property, run at a few thousand instances)."""
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver
+    B = 2048
+    opt = gpu.default_options(optimality_tolerance=1e-7)
+    b = instances.make_batch("cartpole", B, 101)
+    s = BatchSolver("cartpole", B, 101, options=opt, lib=gpu)
+    s.set_batch(b)
+    r = s.solve()
+    x, u = s.trajectory()
+    s.close()
+    assert (r.status == 0).mean() > 0.97
+    perm = np.random.default_rng(0).permutation(B)
+    s2 = BatchSolver("cartpole", B, 101, options=opt, lib=gpu)
+    s2.set_inputs(b.x1[perm], b.ubar[perm], b.p[perm], b.lower[perm], b.upper[perm], b.horizons[perm])
+    r2 = s2.solve()
+    x2, u2 = s2.trajectory()
+    s2.close()
+    assert np.array_equal(r2.k, r.k[perm]) and np.array_equal(r2.status, r.status[perm])
+    helpers.assert_same_bits(r2.objective, r.objective[perm], "objective under permutation")
+    helpers.assert_same_bits(x2, x[perm], "states under permutation")
+    for i in (0, 777, 2047):
+        s1 = BatchSolver("cartpole", 1, 101, options=opt, lib=gpu)
+        s1.set_inputs(b.x1[i:i + 1], b.ubar[i:i + 1], b.p[i:i + 1], b.lower[i:i + 1], b.upper[i:i + 1])
+        r1 = s1.solve()
+        x1_, u1_ = s1.trajectory()
+        s1.close()
+        assert int(r1.k[0]) == int(r.k[i]) and int(r1.status[0]) == int(r.status[i])
+        helpers.assert_same_bits(u1_[0], u[i], f"controls of instance {i} alone vs in batch")
+
+
+def test_full_size_batch_properties(gpu, oracle_mod):
+    """BASELINE config 2 at full size (16384 cartpole instances): every instance terminates with a valid
+    status, >= 99 % converge with primal infeasibility below tolerance, the first 100 reproduce the small-batch
+    answers bit-for-bit, and a random sample of 8 instances matches the oracle exactly."""
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver
+    B = 16384
+    opt = gpu.default_options(optimality_tolerance=1e-7)
+    b = instances.make_batch("cartpole", B, 101)
+    s = BatchSolver("cartpole", B, 101, options=opt, lib=gpu)
+    s.set_batch(b)
+    r = s.solve()
+    st = s.stats()
+    s.close()
+    assert np.isin(r.status, [0, 1, 7, 8]).all()
+    assert (r.status == 0).mean() >= 0.99
+    conv = r.status == 0
+    assert (r.primal_inf[conv] < 1e-7).all() and np.isfinite(r.objective[conv]).all()
+    assert st.sum_kkt > 0 and st.n_converged == conv.sum()
+    s100 = BatchSolver("cartpole", 100, 101, options=opt, lib=gpu)
+    s100.set_batch(b.slice(0, 100))
+    r100 = s100.solve()
+    s100.close()
+    assert np.array_equal(r100.k, r.k[:100])
+    helpers.assert_same_bits(r100.objective, r.objective[:100], "first 100 of the full batch")
+    idx = np.random.default_rng(1).choice(B, 8, replace=False)
+    oopt = oracle_mod.default_options(optimality_tolerance=1e-7)
+    res, _, _ = oracle_mod.solve_batch("cartpole", 101, b.p[idx], b.lower[idx], b.upper[idx], b.x1[idx], b.ubar[idx], options=oopt)
+    for q, i in enumerate(idx):
+        assert (int(r.status[i]), int(r.k[i])) == (res[q].status, res[q].k)
+        helpers.assert_same_bits(r.objective[i], res[q].objective, f"instance {i} objective vs oracle")
