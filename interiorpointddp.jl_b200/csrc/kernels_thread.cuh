@@ -1,5 +1,5 @@
-// Thread-per-instance kernels: initialisation, convergence check / barrier update, forward pass
-// (rollout + filter line search), and the thread-per-(instance, knot) derivative kernel.
+// Thread-per-instance kernels: initialisation, convergence check / barrier update, and the
+// thread-per-(instance, knot) derivative kernel.  (The forward pass lives in kernel_forward.cuh.)
 //
 // These phases are short, sequential-in-time per instance and dominated by streaming each instance's
 // own contiguous records, so one thread walks one instance; instance records are contiguous, the
@@ -256,191 +256,6 @@ __global__ void k_check(DevView v, const int* list, int n_list, int* list_next, 
     return;
   }
   list_fwd[atomicAdd(&counters[CNT_FWD], 1)] = b;
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_forward: forward_pass! (reference src/forward_pass.jl:1-57) = backtracking line search over
-// rollout! (:98-153) with the fraction-to-boundary test (:59-85, fused into the rollout with early
-// exit: same accept/reject decision), filter test, switching / Armijo / sufficient-decrease tests;
-// then update_nominal_trajectory! (src/data/methods.jl:78-91, here: flip nomsel), filter augmentation
-// (src/solve.jl:81,95-99, Q5) and the iteration bookkeeping of src/solve.jl:82-85.
-// ---------------------------------------------------------------------------------------------
-template <class M>
-IPDDP_D int rollout(const DevView& v, int b, int Nb, int nom, int cur, double step, double one_m_tau) {
-  typedef Rec<M> R;
-  constexpr int K = M::NU + M::NC, NR = M::NX + 1;
-  const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
-  const double* lo = v.lower + (size_t)b * M::NU;
-  const double* up = v.upper + (size_t)b * M::NU;
-  double x[M::NX], xn[M::NXN], dx[M::NX], u[M::NU > 0 ? M::NU : 1];
-  {
-    const double* r0 = v.rec(nom, b, 0);
-#pragma unroll
-    for (int i = 0; i < M::NX; ++i) x[i] = r0[R::X + i];
-  }
-  for (int t = 0; t < Nb; ++t) {
-    const double* rn = v.rec(nom, b, t);
-    double* rc = v.rec(cur, b, t);
-#pragma unroll
-    for (int i = 0; i < M::NX; ++i) { dx[i] = x[i] - rn[R::X + i]; rc[R::X + i] = x[i]; }
-    if (t == Nb - 1) break;
-    const double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
-    const double* gi = g + K * NR;
-    bool viol = false, bad = false;
-#pragma unroll
-    for (int i = 0; i < M::NU; ++i) {
-      double w = g[i];
-      w *= step;
-      w += rn[R::U + i];
-      w = dot4c<M::NX>(g + i + K, K, dx, 1) + w;
-      u[i] = w;
-      rc[R::U + i] = w;
-      const double il = w - lo[i], iu = up[i] - w;
-      rc[R::IL + i] = il;
-      rc[R::IU + i] = iu;
-      viol = viol || (rn[R::IL + i] * one_m_tau > il) || (rn[R::IU + i] * one_m_tau > iu);
-      bad = bad || !finite(w);
-    }
-#pragma unroll
-    for (int q = 0; q < M::NC; ++q) {
-      double w = g[M::NU + q];
-      w *= step;
-      w += rn[R::PHI + q];
-      rc[R::PHI + q] = dot4c<M::NX>(g + M::NU + q + K, K, dx, 1) + w;
-    }
-#pragma unroll
-    for (int i = 0; i < M::NU; ++i) {
-      double w = gi[i];
-      w *= step;
-      w += rn[R::ZL + i];
-      w = dot4c<M::NX>(gi + i + 2 * M::NU, 2 * M::NU, dx, 1) + w;
-      rc[R::ZL + i] = w;
-      viol = viol || (rn[R::ZL + i] * one_m_tau > w);
-    }
-#pragma unroll
-    for (int i = 0; i < M::NU; ++i) {
-      double w = gi[M::NU + i];
-      w *= step;
-      w += rn[R::ZU + i];
-      w = dot4c<M::NX>(gi + M::NU + i + 2 * M::NU, 2 * M::NU, dx, 1) + w;
-      rc[R::ZU + i] = w;
-      viol = viol || (rn[R::ZU + i] * one_m_tau > w);
-    }
-    M::dyn(x, u, p, xn);
-#pragma unroll
-    for (int i = 0; i < M::NX; ++i) { x[i] = xn[i]; bad = bad || !finite(xn[i]); }
-    if (bad) return 1;    // DomainError analogue: reject, halve (src/forward_pass.jl:18-24)
-    if (viol) return 2;   // fraction-to-boundary violated somewhere: reject, halve
-  }
-  return 0;
-}
-
-template <class M>
-__global__ void k_forward(DevView v, const int* list_fwd, int* list_next, int* counters) {
-  constexpr int K = M::NU + M::NC;
-  typedef Rec<M> R;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= counters[CNT_FWD]) return;
-  const int b = list_fwd[i];
-  const int Nb = v.horizon[b];
-  const int nom = v.nomsel[b], cur = 1 - nom;
-  const double mu = v.sdv(SD_MU, b);
-  const double tau = jmax(v.opt.tau_min, 1.0 - mu);
-  const double one_m_tau = 1.0 - tau;
-  const double theta_prev = v.sdv(SD_THETA_CURR, b), L_prev = v.sdv(SD_L_CURR, b);
-  const double theta_min = v.sdv(SD_THETA_MIN, b);
-  int l = 0, status = 0, nroll = 0;
-  double step = 1.0;
-  bool switching = false, armijo = false;
-  double L_next = 0.0, theta_next = 0.0, J = v.sdv(SD_OBJECTIVE, b);
-
-  // expected_change_lagrangian (src/forward_pass.jl:87-96), t descending
-  double dL = 0.0;
-  for (int t = Nb - 2; t >= 0; --t) {
-    const double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
-    const double* q = v.Qu + ((size_t)b * (v.N - 1) + t) * M::NU;
-    const double* rn = v.rec(nom, b, t);
-    dL += dot4c<M::NU>(q, 1, g, 1);
-    dL += dot4c<M::NC>(rn + R::C, 1, g + M::NU, 1);
-  }
-  (void)K;
-  const int fn = v.siv(SI_FILTER_N, b);
-  while (step >= IPDDP_EPS) {
-    const double gamma = step;
-    nroll++;
-    const int rc = rollout<M>(v, b, Nb, nom, cur, gamma, one_m_tau);
-    if (rc == 1) { step *= 0.5; continue; }
-    if (rc == 2) { status = 2; step *= 0.5; continue; }
-    double theta, L;
-    eval_metrics<M>(v, cur, b, Nb, mu, &J, &theta, &L);
-    bool blocked = false;
-    for (int f = 0; f < fn; ++f) {
-      const double ft = v.filter[(size_t)(0 * IPDDP_FILTER_CAPACITY + f) * v.B + b];
-      const double fL = v.filter[(size_t)(1 * IPDDP_FILTER_CAPACITY + f) * v.B + b];
-      if (theta >= ft && L >= fL) { blocked = true; break; }
-    }
-    status = blocked ? 3 : 0;
-    if (status != 0) { step *= 0.5; l += 1; continue; }
-    switching = (dL < 0.0) && (dm::pow(-gamma * dL, v.opt.s_L) * dm::pow(gamma, 1.0 - v.opt.s_L) >
-                               v.opt.delta * dm::pow(theta_prev, v.opt.s_theta));
-    armijo = L - L_prev - 10.0 * IPDDP_EPS * fabs(L_prev) <= v.opt.eta_L * gamma * dL;
-    if (theta <= theta_min && switching) {
-      status = armijo ? 0 : 4;
-    } else {
-      const bool suff = (theta <= (1.0 - v.opt.gamma_theta) * theta_prev) || (L <= L_prev - v.opt.gamma_L * theta_prev);
-      status = suff ? 0 : 5;
-    }
-    if (status != 0) { step *= 0.5; l += 1; continue; }
-    L_next = L;
-    theta_next = theta;
-    break;
-  }
-  if (step < IPDDP_EPS) status = 7;
-  v.siv(SI_L, b) = l;
-  v.siv(SI_NROLL, b) += nroll;
-  v.sdv(SD_STEP, b) = step;
-  v.sdv(SD_OBJECTIVE, b) = J;
-  v.siv(SI_SWITCHING, b) = switching;
-  v.siv(SI_ARMIJO, b) = armijo;
-  v.siv(SI_STATUS, b) = status;
-  if (status != 0) {  // line search failed: break
-    v.siv(SI_DONE, b) = 1;
-    return;
-  }
-  // accept: update_nominal_trajectory! (pointer flip), filter, bookkeeping
-  v.nomsel[b] = cur;
-  if (!armijo && !switching) {
-    if (fn >= IPDDP_FILTER_CAPACITY) {
-      v.siv(SI_STATUS, b) = 9;
-      v.siv(SI_DONE, b) = 1;
-      return;
-    }
-    v.filter[(size_t)(0 * IPDDP_FILTER_CAPACITY + fn) * v.B + b] = (1.0 - v.opt.gamma_theta) * theta_prev;
-    v.filter[(size_t)(1 * IPDDP_FILTER_CAPACITY + fn) * v.B + b] = L_prev - v.opt.gamma_L * theta_prev;
-    v.siv(SI_FILTER_N, b) = fn + 1;
-  }
-  v.sdv(SD_L_CURR, b) = L_next;
-  v.sdv(SD_THETA_CURR, b) = theta_next;
-  v.sdv(SD_L_NEXT, b) = L_next;
-  v.sdv(SD_THETA_NEXT, b) = theta_next;
-  const int k = v.siv(SI_K, b) + 1;
-  v.siv(SI_K, b) = k;
-  if (v.trace_cap > 0) {
-    const int row = v.siv(SI_TRACE_N, b);
-    if (row < v.trace_cap) {
-      double* tr = v.trace + ((size_t)b * v.trace_cap + row) * IPDDP_TRACE_COLS;
-      tr[0] = (double)k; tr[1] = (double)v.siv(SI_J, b); tr[2] = J; tr[3] = v.sdv(SD_PRIMAL_INF, b);
-      tr[4] = v.sdv(SD_DUAL_INF, b); tr[5] = v.sdv(SD_CS_INF, b); tr[6] = mu; tr[7] = v.sdv(SD_REG_LAST, b);
-      tr[8] = step; tr[9] = (double)l; tr[10] = theta_next; tr[11] = L_next;
-      v.siv(SI_TRACE_N, b) = row + 1;
-    }
-  }
-  if (k >= v.opt.max_iterations) {  // src/solve.jl:90
-    v.siv(SI_STATUS, b) = 8;
-    v.siv(SI_DONE, b) = 1;
-    return;
-  }
-  list_next[atomicAdd(&counters[CNT_NEXT], 1)] = b;
 }
 
 }  // namespace ipk

@@ -3,6 +3,7 @@
 #pragma once
 #include "kernels_thread.cuh"
 #include "kernel_backward.cuh"
+#include "kernel_forward.cuh"
 #include "vtable.h"
 
 namespace ipk {
@@ -31,8 +32,8 @@ template <class M> struct Launch {
   static void forward(const DevView& v, const int* list_fwd, int n_upper, int* list_next, int* counters,
                       cudaStream_t s) {
     if (n_upper <= 0) return;
-    const int th = 32;
-    IPDDP_LAUNCH((k_forward<M>), (n_upper + th - 1) / th, th, 0, s, v, list_fwd, list_next, counters);
+    IPDDP_LAUNCH((k_forward<M>), (n_upper + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, FwLayout<M>::bytes(v.N), s, v,
+                 list_fwd, list_next, counters);
   }
   static int prepare() {
 #ifndef IPDDP_SIMT_EMU

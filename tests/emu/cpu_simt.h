@@ -83,6 +83,60 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lanemask) 
   memcpy(&r, &raw, sizeof(T));
   return r;
 }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  emu::BlockState* b = emu::tls_block;
+  const int me = emu::tls_threadIdx.x;
+  unsigned long long raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  b->xchg[me] = raw;
+  emu::yield_barrier();
+  raw = b->xchg[(me & ~31) | (src & 31)];
+  emu::yield_barrier();
+  T r;
+  memcpy(&r, &raw, sizeof(T));
+  return r;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  emu::BlockState* b = emu::tls_block;
+  const int me = emu::tls_threadIdx.x;
+  b->xchg[me] = pred ? 1ull : 0ull;
+  emu::yield_barrier();
+  unsigned r = 0;
+  const int w0 = me & ~31;
+  const int nthr = (int)emu::tls_blockDim.x;
+  for (int q = 0; q < 32 && w0 + q < nthr; ++q) if (!b->fibers[w0 + q].done && b->xchg[w0 + q]) r |= (1u << q);
+  emu::yield_barrier();
+  return r;
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  emu::BlockState* b = emu::tls_block;
+  const int me = emu::tls_threadIdx.x;
+  b->xchg[me] = v;
+  emu::yield_barrier();
+  unsigned r = 0;
+  const int w0 = me & ~31;
+  for (int q = 0; q < 32; ++q) { unsigned x = (unsigned)b->xchg[w0 + q]; if (x > r) r = x; }
+  emu::yield_barrier();
+  return r;
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  emu::BlockState* b = emu::tls_block;
+  const int me = emu::tls_threadIdx.x;
+  b->xchg[me] = v;
+  emu::yield_barrier();
+  unsigned r = 0xffffffffu;
+  const int w0 = me & ~31;
+  for (int q = 0; q < 32; ++q) { unsigned x = (unsigned)b->xchg[w0 + q]; if (x < r) r = x; }
+  emu::yield_barrier();
+  return r;
+}
+static inline int __ffs(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __double2hiint(double x) { return (int)(emu_d2ll(x) >> 32); }
+static inline int __double2loint(double x) { return (int)(emu_d2ll(x) & 0xffffffffll); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
 // ---- CUDA runtime shims (host memory stands in for device memory)
