@@ -225,6 +225,10 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   if (opt) v.opt = *opt; else ipddp_default_options(&v.opt);
   v.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
   v.n_compl = (indices_compl && n_compl > 0) ? n_compl : 0;
+  for (int q = 0; q < v.n_compl; ++q) {
+    if (indices_compl[q] < 0 || indices_compl[q] >= vt->nc) { delete h; return fail("indices_compl out of range"); }
+    v.compl_mask |= 1ull << indices_compl[q];
+  }
   const size_t np1 = vt->np > 0 ? vt->np : 1;
   int rc = 0;
   rc |= h->alloc(&h->d_compl, (size_t)v.n_compl);

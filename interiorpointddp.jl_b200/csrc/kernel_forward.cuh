@@ -25,7 +25,7 @@ template <class M> struct FwLayout {
   static constexpr int NUP = M::NU > 0 ? M::NU : 1;
   // per warp: u[NU] | chunk[32] | idx bytes (2*NU, padded to 8 doubles) | per-knot partials 4 x N (runtime)
   static constexpr int FIXED = NUP + 32 + ((2 * NUP + 7) / 8);
-  static int per_warp_doubles(int N) { return FIXED + 4 * N; }
+  static IPDDP_BOTH int per_warp_doubles(int N) { return FIXED + 4 * N; }
   static size_t bytes(int N) { return (size_t)FW_WARPS * per_warp_doubles(N) * sizeof(double); }
 };
 
@@ -133,18 +133,15 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_forward(DevView v, const int*
       if (Nb > 1) prefetch(0);
       for (int t = 0; t < Nb; ++t) {
         double* rcur = v.rec(cur, b, t);
-        if (t == Nb - 1) {
-          if (lane < NX) rcur[R::X + lane] = x[lane < NX ? lane : 0];
-          break;
-        }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) dx[i] = x[i] - xbar[i];
         if (lane < NX) {
           double xv = x[0];
 #pragma unroll
           for (int i = 1; i < NX; ++i) xv = (lane == i) ? x[i] : xv;
           rcur[R::X + lane] = xv;
         }
+        if (t == Nb - 1) break;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) dx[i] = x[i] - xbar[i];
         bool viol = false, bad = false;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
@@ -202,7 +199,10 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_forward(DevView v, const int*
         double n1 = 0.0;
         if (NC > 0) {
           M::con(x, u, p, c);
-          for (int q = 0; q < v.n_compl; ++q) c[v.compl_idx[q]] -= mu;
+          if (v.compl_mask) {
+#pragma unroll
+            for (int i = 0; i < M::NC; ++i) if ((v.compl_mask >> i) & 1ull) c[i] -= mu;
+          }
 #pragma unroll
           for (int i = 0; i < NC; ++i) { r[R::C + i] = c[i]; n1 += fabs(c[i]); }
         }

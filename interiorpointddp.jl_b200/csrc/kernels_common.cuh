@@ -63,7 +63,10 @@ IPDDP_D void eval_metrics(const DevView& v, int set, int b, int Nb, double mu, d
       M::cost(x, u, p, &Jp);
       if (M::NC > 0) {
         M::con(x, u, p, c);
-        for (int q = 0; q < v.n_compl; ++q) c[v.compl_idx[q]] -= mu;
+        if (v.compl_mask) {
+#pragma unroll
+            for (int i = 0; i < M::NC; ++i) if ((v.compl_mask >> i) & 1ull) c[i] -= mu;
+          }
         double n1 = 0.0;
 #pragma unroll
         for (int i = 0; i < M::NC; ++i) { r[R::C + i] = c[i]; n1 += fabs(c[i]); }

@@ -39,6 +39,7 @@ struct DevView {
   int TR, G;                 // record sizes (doubles)
   int n_compl;
   const int* compl_idx;
+  unsigned long long compl_mask;   // bit i set <=> constraint i is in indices_compl
   // inputs
   const double* p;           // [B][np]
   const double* lower;       // [B][nu]

@@ -11,6 +11,7 @@
 #define IPDDP_HD __device__ __forceinline__
 #define IPDDP_TABLE static __device__ const
 #define IPDDP_D __device__ __forceinline__
+#define IPDDP_BOTH __host__ __device__
 #define IPDDP_D2LL(x) __double_as_longlong(x)
 #define IPDDP_LL2D(x) __longlong_as_double(x)
 #define IPDDP_FMA(a, b, c) __fma_rn((a), (b), (c))

@@ -57,6 +57,7 @@ inline void* cur_smem() { return tls_block->smem.data(); }
 
 #define IPDDP_HD inline
 #define IPDDP_D inline
+#define IPDDP_BOTH
 #define IPDDP_TABLE static const
 static inline long long emu_d2ll(double x) { long long u; memcpy(&u, &x, 8); return u; }
 static inline double emu_ll2d(long long u) { double x; memcpy(&x, &u, 8); return x; }
