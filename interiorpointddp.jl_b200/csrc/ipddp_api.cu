@@ -92,28 +92,26 @@ __global__ void k_test_detmath(int fn, int n, const double* x, const double* y, 
   out[i] = r;
 }
 
-// one warp per matrix: dense -> packed smem, factor, inertia, solve 5 rhs, packed -> dense
-__global__ void k_test_ldlt(int n, int nmat, const double* A, const double* Bm, double* Aout, int* ipiv_out,
+// one warp per matrix: dense -> packed smem, factor (+ inertia), solve 5 rhs, packed -> dense
+template <int N>
+__global__ void k_test_ldlt(int nmat, const double* A, const double* Bm, double* Aout, int* ipiv_out,
                             int* info_out, int* np_out, double* X) {
   IPDDP_DYN_SMEM(double, sm);
   const int lane = threadIdx.x, m = blockIdx.x;
   if (m >= nmat) return;
-  const int kp = n * (n + 1) / 2;
+  constexpr int n = N, kp = N * (N + 1) / 2;
   double* lhs = sm;
   double* rhs = lhs + kp;
   double* ws = rhs + n * 5;
   int* ipiv = reinterpret_cast<int*>(ws + 4 * n);
-  unsigned short* ij = reinterpret_cast<unsigned short*>(ipiv + n);
+  unsigned char* list = reinterpret_cast<unsigned char*>(ipiv + n);
   for (int j = 0; j < n; ++j)
-    for (int i = lane; i <= j; i += 32) {
-      ij[ipk::pk(i, j)] = (unsigned short)(i | (j << 8));
-      lhs[ipk::pk(i, j)] = A[(size_t)m * n * n + i + (size_t)j * n];
-    }
+    for (int i = lane; i <= j; i += 32) lhs[ipk::pk(i, j)] = A[(size_t)m * n * n + i + (size_t)j * n];
   for (int e = lane; e < n * 5; e += 32) rhs[e] = Bm[(size_t)m * n * 5 + e];
   __syncwarp();
-  const int info = ipk::warp_sytf2_rook(n, lhs, ipiv, ij, ws, lane);
-  const int np = ipk::warp_inertia_np(n, lhs, ipiv, 1e-12);
-  if (info == 0) ipk::warp_sytrs_rook<5>(n, lhs, ipiv, rhs, lane);
+  int np = 0;
+  const int info = ipk::warp_sytf2_rook<N>(lhs, ipiv, ws, list, lane, 1e-12, np);
+  if (info == 0) ipk::warp_sytrs_rook<N, 5>(lhs, ipiv, rhs, lane);
   __syncwarp();
   for (int j = 0; j < n; ++j)
     for (int i = lane; i <= j; i += 32) Aout[(size_t)m * n * n + i + (size_t)j * n] = lhs[ipk::pk(i, j)];
@@ -622,8 +620,15 @@ int ipddp_test_ldlt(int n, int nmat, const double* A, const double* Bm, double* 
   CK(cudaMemcpy(dB, Bm, sb, cudaMemcpyHostToDevice));
   CK(cudaMemset(dAo, 0, sa));
   const int kp = n * (n + 1) / 2;
-  const size_t smem = ((size_t)(kp + n * 5 + 4 * n) * 8 + (size_t)n * 4 + (size_t)kp * 2 + 15) / 16 * 16;
-  IPDDP_LAUNCH(k_test_ldlt, nmat, 32, smem, 0, n, nmat, dA, dB, dAo, dip, dinfo, dnp, dX);
+  const size_t smem = ((size_t)(kp + n * 5 + 4 * n) * 8 + (size_t)n * 4 + 64 + 15) / 16 * 16;
+#define IPDDP_LDLT_CASE(NN) case NN: IPDDP_LAUNCH((k_test_ldlt<NN>), nmat, 32, smem, 0, nmat, dA, dB, dAo, dip, dinfo, dnp, dX); break;
+  switch (n) {
+    IPDDP_LDLT_CASE(1) IPDDP_LDLT_CASE(2) IPDDP_LDLT_CASE(3) IPDDP_LDLT_CASE(4) IPDDP_LDLT_CASE(5) IPDDP_LDLT_CASE(8)
+    IPDDP_LDLT_CASE(14) IPDDP_LDLT_CASE(15) IPDDP_LDLT_CASE(16) IPDDP_LDLT_CASE(17) IPDDP_LDLT_CASE(31) IPDDP_LDLT_CASE(32)
+    IPDDP_LDLT_CASE(33) IPDDP_LDLT_CASE(35) IPDDP_LDLT_CASE(48) IPDDP_LDLT_CASE(64)
+    default: return fail("ipddp_test_ldlt: n must be one of 1,2,3,4,5,8,14,15,16,17,31,32,33,35,48,64");
+  }
+#undef IPDDP_LDLT_CASE
   CK(cudaMemcpy(Aout, dAo, sa, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(X, dX, sb, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(ipiv, dip, (size_t)nmat * n * 4, cudaMemcpyDeviceToHost));

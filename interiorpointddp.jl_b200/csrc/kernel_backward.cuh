@@ -48,8 +48,8 @@ template <class M> struct BwLayout {
   // ints (4 bytes) after the doubles
   static constexpr int IPIV_B = DBL_END * 8;
   static constexpr int TBL_B = IPIV_B + pad(K) * 4;
-  static constexpr int IJ_B = TBL_B + pad(M::NTBL) * 4;
-  static constexpr int BYTES = ((IJ_B + pad(KP) * 2 + 15) / 16) * 16;
+  static constexpr int LIST_B = TBL_B + pad(M::NTBL) * 4;
+  static constexpr int BYTES = ((LIST_B + 64 + 15) / 16) * 16;
 };
 
 template <class M>
@@ -76,13 +76,11 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
   unsigned char* smb = reinterpret_cast<unsigned char*>(sm);
   int* ipiv = reinterpret_cast<int*>(smb + L::IPIV_B);
   MEntry* tbl = reinterpret_cast<MEntry*>(smb + L::TBL_B);
-  unsigned short* ij = reinterpret_cast<unsigned short*>(smb + L::IJ_B);
+  unsigned char* nzlist = smb + L::LIST_B;
 
   // ---- one-time setup: scatter tables, constants, packed-index table, constant parts of fx / fu
   for (int e = lane; e < M::NTBL; e += 32) tbl[e] = M::tbl()[e];
   for (int e = lane; e < M::NCONST; e += 32) cst[e] = M::consts()[e];
-  for (int j = 0; j < K; ++j)
-    for (int i = lane; i <= j; i += 32) ij[pk(i, j)] = (unsigned short)(i | (j << 8));
   for (int e = lane; e < NX * NX; e += 32) fx[e] = 0.0;
   for (int e = lane; e < NX * NU; e += 32) fu[e] = 0.0;
   __syncwarp();
@@ -218,7 +216,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
         Cm[e] = dot4c<NX>(xxt + i, NX, fx + j * NX, 1) + Cm[e];
       }
       for (int e = lane; e < NU * (NU + 1) / 2; e += 32) {
-        const unsigned short q = ij[e];
+        const unsigned q = tri_decode(e);
         const int i = q & 0xff, j = q >> 8;
         const double h0 = (i == j) ? (t1[i] + t2[i]) : 0.0;
         lhs[e] = dot4c<NX>(uxt + i, NU, fu + j * NX, 1) + h0;
@@ -257,17 +255,17 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
       for (int e = lane; e < K * NR; e += 32) rhs[e] = rhs0[e] * -1.0;
       __syncwarp();
       // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
-      const int info = warp_sytf2_rook(K, lhs, ipiv, ij, ws, lane);
+      int np = 0;
+      const int info = warp_sytf2_rook<K>(lhs, ipiv, ws, nzlist, lane, 1e-12, np);
       delta_c = 0.0;
       if (info > 0) delta_c = v.opt.delta_c * dm::pow(mu, v.opt.kappa_c);
-      const int np = warp_inertia_np(K, lhs, ipiv, 1e-12);
       if (np != NU || info != 0) {
         if (reg == 0.0) reg = (reg_last == 0.0) ? v.opt.reg_1 : jmax(v.opt.reg_min, v.opt.kappa_w_m * reg_last);
         else reg = (reg_last == 0.0) ? v.opt.kappa_bar_w_p * reg : v.opt.kappa_w_p * reg;
         status = 1;
         break;
       }
-      warp_sytrs_rook<NR>(K, lhs, ipiv, rhs, lane);
+      warp_sytrs_rook<K, NR>(lhs, ipiv, rhs, lane);
       // ---- gains to HBM: eq block, then ineq block                      (:159-172)
       double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
       for (int e = lane; e < K * NR; e += 32) g[e] = rhs[e];

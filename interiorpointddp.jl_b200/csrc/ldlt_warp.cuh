@@ -4,98 +4,130 @@
 // Replaces LAPACK dsytrf_rook('U') (reached by the reference at src/inertia_correction.jl:261 through
 // FastLapackInterface), dsytrs_rook (`ldiv!(bk, eq[t])`, src/backward_pass.jl:148) and `inertia!`
 // (src/inertia_correction.jl:54-205) for n <= 64, i.e. the unblocked dsytf2_rook path.  One warp works
-// on one matrix: pivot searches are warp arg-max reductions that keep IDAMAX's first-maximum
-// tie-break, the symmetric interchanges and the rank-1 / rank-2 trailing updates are spread over the
-// lanes element-wise.  Every matrix element sees exactly the operation sequence of the unblocked
-// LAPACK algorithm (rank-1 update as fma(x_i, -d*x_j, a_ij) like OpenBLAS' dsyr; everything else
-// plain IEEE ops), so the factors, the pivot sequence and `info` do not depend on the lane mapping.
+// on one matrix; every matrix element sees exactly the operation sequence of the unblocked LAPACK
+// algorithm (rank-1 update as fma(x_i, -d*x_j, a_ij) like OpenBLAS' dsyr; everything else plain IEEE
+// ops), so factors, pivot sequence and `info` do not depend on the lane mapping.
+//
+// How the work is mapped (the kernel is instruction-issue bound):
+//   * pivot searches: |a| is an order-preserving 64-bit key; two REDUX.MAX (high / low word) + ballots give
+//     the maximum and the set of ties, from which IDAMAX's first-maximum rule and dsytf2_rook's
+//     "row segment first, column segment only if strictly larger" rule are applied on a 64-bit tie mask;
+//   * trailing updates are SPARSE: pivot columns of IPDDP2 KKT matrices are mostly zero (measured: 23 %
+//     non-zero entries, 7 % of the rank-1 element updates do arithmetic), so the non-zero row indices are
+//     compacted with a ballot and only the nnz(nnz+1)/2 affected elements are touched.  Skipped
+//     elements would receive fma(0, t, a) = a, i.e. the skip is exact for finite data (only the sign of
+//     an exact zero can differ);
+//   * the inertia of D is counted while the pivots are produced (a D block is final when it is chosen);
+//   * triangular solves: one lane per row for the rank-1 downdates, 4 lanes per right-hand side for the
+//     dgemv('T') dot products (partial sums i mod 4 + 2-step butterfly = the dot4 summation order).
 #pragma once
 #include "kernels_common.cuh"
 
 namespace ipk {
 
-IPDDP_D int pk(int i, int j) { return i + ((j * (j + 1)) >> 1); }   // requires i <= j
+IPDDP_D int coff(int j) { return (j * (j + 1)) >> 1; }
+IPDDP_D int pk(int i, int j) { return i + coff(j); }   // requires i <= j
 
-// first-maximum arg-max over the warp: larger value wins, ties go to the smaller index
-IPDDP_D void warp_argmax(double& val, int& idx) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const double ov = __shfl_xor_sync(IPDDP_FULL_MASK, val, off);
-    const int oi = __shfl_xor_sync(IPDDP_FULL_MASK, idx, off);
-    if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
-  }
+// (a, b) with a <= b for the p-th element of a packed upper triangle, as a | b << 8
+IPDDP_D unsigned tri_decode(int p) {
+  int b = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+  while (coff(b) > p) --b;
+  while (coff(b + 1) <= p) ++b;
+  return (unsigned)(p - coff(b)) | ((unsigned)b << 8);
+}
+
+// Maximum of the non-negative candidates (v0 at index lane, v1 at index lane+32; vld* = candidate present)
+// and the 64-bit mask of the indices that attain it.
+template <bool TWO>
+IPDDP_D double warp_max_ties(double v0, bool vld0, double v1, bool vld1, unsigned long long& ties) {
+  const unsigned h0 = vld0 ? (unsigned)__double2hiint(v0) : 0u, l0 = vld0 ? (unsigned)__double2loint(v0) : 0u;
+  const unsigned h1 = (TWO && vld1) ? (unsigned)__double2hiint(v1) : 0u, l1 = (TWO && vld1) ? (unsigned)__double2loint(v1) : 0u;
+  const unsigned mh = __reduce_max_sync(IPDDP_FULL_MASK, TWO ? (h0 > h1 ? h0 : h1) : h0);
+  unsigned lc = (h0 == mh) ? l0 : 0u;
+  if (TWO) { const unsigned lc1 = (h1 == mh) ? l1 : 0u; lc = lc > lc1 ? lc : lc1; }
+  const unsigned ml = __reduce_max_sync(IPDDP_FULL_MASK, lc);
+  const unsigned m0 = __ballot_sync(IPDDP_FULL_MASK, vld0 && h0 == mh && l0 == ml);
+  unsigned long long t = m0;
+  if (TWO) t |= (unsigned long long)__ballot_sync(IPDDP_FULL_MASK, vld1 && h1 == mh && l1 == ml) << 32;
+  ties = t;
+  return __hiloint2double((int)mh, (int)ml);
 }
 
 // symmetric interchange of rows/columns a < b inside the leading (b+1)x(b+1) block (dsytf2_rook style:
 // trailing columns are NOT touched)
+template <bool TWO>
 IPDDP_D void warp_sym_swap(double* A, int a, int b, int lane) {
-  for (int i = lane; i < b; i += 32) {
-    if (i < a) {
-      const int pa = pk(i, a), pb = pk(i, b);
-      const double t = A[pa]; A[pa] = A[pb]; A[pb] = t;
-    } else if (i > a) {
-      const int pa = pk(a, i), pb = pk(i, b);
+  const int ca = coff(a), cb = coff(b);
+#pragma unroll
+  for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+    const int i = lane + 32 * s;
+    if (i < b && i != a) {
+      const int pa = (i < a) ? ca + i : coff(i) + a, pb = cb + i;
       const double t = A[pa]; A[pa] = A[pb]; A[pb] = t;
     }
   }
   if (lane == 0) {
-    const int pa = pk(a, a), pb = pk(b, b);
-    const double t = A[pa]; A[pa] = A[pb]; A[pb] = t;
+    const double t = A[ca + a]; A[ca + a] = A[cb + b]; A[cb + b] = t;
   }
 }
 
-// dsytf2_rook('U').  A: packed upper (n(n+1)/2), ipiv: n ints (LAPACK 1-based convention),
-// ij: table of (i | j<<8) for every packed index, w: scratch of 4n doubles.  Returns info.
-IPDDP_D int warp_sytf2_rook(int n, double* A, int* ipiv, const unsigned short* ij, double* w, int lane) {
+// compacts the indices i (< 64) flagged by (f0 at lane, f1 at lane+32) into list[] ascending; returns count
+template <bool TWO>
+IPDDP_D int warp_compact(bool f0, bool f1, unsigned char* list, int lane) {
+  const unsigned m0 = __ballot_sync(IPDDP_FULL_MASK, f0);
+  const unsigned lt = (1u << lane) - 1u;
+  if (f0) list[__popc(m0 & lt)] = (unsigned char)lane;
+  int n = __popc(m0);
+  if (TWO) {
+    const unsigned m1 = __ballot_sync(IPDDP_FULL_MASK, f1);
+    if (f1) list[n + __popc(m1 & lt)] = (unsigned char)(lane + 32);
+    n += __popc(m1);
+  }
+  return n;
+}
+
+// dsytf2_rook('U') on the packed matrix A of order K.  ipiv: K ints (LAPACK 1-based convention),
+// w: scratch of 4K doubles, list: K bytes.  Returns info; np_out = number of positive eigenvalues of D
+// (reference inertia! with atol = tol).
+template <int K>
+IPDDP_D int warp_sytf2_rook(double* A, int* ipiv, double* w, unsigned char* list, int lane, double tol, int& np_out) {
+  constexpr bool TWO = K > 32;
   const double alpha = 0.6403882032022076;   // (1 + sqrt(17)) / 8
   const double sfmin = 2.2250738585072014e-308;
-  int info = 0;
-  int k = n - 1;   // 0-based pivot column
+  int info = 0, np = 0;
+  int k = K - 1;   // 0-based pivot column
+  const int i0 = lane, i1 = lane + 32;
   while (k >= 0) {
     int kstep = 1, p = k, kp = k;
-    const double absakk = fabs(A[pk(k, k)]);
+    const int ck = coff(k);
+    const double absakk = fabs(A[ck + k]);
     double colmax = 0.0;
     int imax = 0;
     if (k > 0) {
-      double v = -1.0; int vi = 0x7fffffff;
-      for (int i = lane; i < k; i += 32) {
-        const double a = fabs(A[pk(i, k)]);
-        if (a > v) { v = a; vi = i; }
-      }
-      warp_argmax(v, vi);
-      colmax = v; imax = vi;
+      unsigned long long ties;
+      const bool v0 = i0 < k, v1 = TWO && i1 < k;
+      colmax = warp_max_ties<TWO>(v0 ? fabs(A[ck + i0]) : 0.0, v0, v1 ? fabs(A[ck + i1]) : 0.0, v1, ties);
+      imax = __ffsll((long long)ties) - 1;
     }
-    bool singular = false;
     if (fmax(absakk, colmax) == 0.0) {
       if (info == 0) info = k + 1;
       kp = k;
-      singular = true;
     } else {
       if (!(absakk < alpha * colmax)) {
         kp = k;
       } else {
         for (;;) {
-          // rowmax: largest off-diagonal magnitude in row/column imax of the leading block;
-          // row segment (imax, j), j = imax+1..k, is searched first, the column segment replaces it
-          // only if strictly larger
-          double rv = -1.0; int rj = 0x7fffffff;
-          for (int j = imax + 1 + lane; j <= k; j += 32) {
-            const double a = fabs(A[pk(imax, j)]);
-            if (a > rv) { rv = a; rj = j; }
-          }
-          warp_argmax(rv, rj);
-          double rowmax = 0.0; int jmax = 0;
-          if (imax != k) { rowmax = rv; jmax = rj; }
-          if (imax > 0) {
-            double cv = -1.0; int ci = 0x7fffffff;
-            for (int i = lane; i < imax; i += 32) {
-              const double a = fabs(A[pk(i, imax)]);
-              if (a > cv) { cv = a; ci = i; }
-            }
-            warp_argmax(cv, ci);
-            if (cv > rowmax) { rowmax = cv; jmax = ci; }
-          }
-          if (!(fabs(A[pk(imax, imax)]) < alpha * rowmax)) {
+          // largest off-diagonal magnitude in row/column imax of the leading block; ties: the row segment
+          // (c > imax) is searched first and wins, lowest index inside a segment
+          const int ci = coff(imax);
+          const bool v0 = i0 <= k && i0 != imax, v1 = TWO && i1 <= k && i1 != imax;
+          const double a0 = v0 ? fabs(i0 < imax ? A[ci + i0] : A[coff(i0) + imax]) : 0.0;
+          const double a1 = v1 ? fabs(i1 < imax ? A[ci + i1] : A[coff(i1) + imax]) : 0.0;
+          unsigned long long ties;
+          const double rowmax = warp_max_ties<TWO>(a0, v0, a1, v1, ties);
+          const unsigned long long rowpart = ties & ~((2ull << imax) - 1ull);
+          const int jmax = __ffsll((long long)(rowpart ? rowpart : ties)) - 1;
+          if (!(fabs(A[ci + imax]) < alpha * rowmax)) {
             kp = imax;
             break;
           } else if (p == jmax || rowmax <= colmax) {
@@ -111,12 +143,12 @@ IPDDP_D int warp_sytf2_rook(int n, double* A, int* ipiv, const unsigned short* i
       }
       __syncwarp();
       if (kstep == 2 && p != k) {   // first interchange: k <-> p
-        warp_sym_swap(A, p, k, lane);
+        warp_sym_swap<TWO>(A, p, k, lane);
         __syncwarp();
       }
       const int kk = k - kstep + 1;
       if (kp != kk) {               // second interchange: kk <-> kp
-        warp_sym_swap(A, kp, kk, lane);
+        warp_sym_swap<TWO>(A, kp, kk, lane);
         if (kstep == 2 && lane == 0) {
           const int pa = pk(k - 1, k), pb = pk(kp, k);
           const double t = A[pa]; A[pa] = A[pb]; A[pb] = t;
@@ -125,25 +157,31 @@ IPDDP_D int warp_sytf2_rook(int n, double* A, int* ipiv, const unsigned short* i
       }
       if (kstep == 1) {
         if (k > 0) {
-          double* x = A + pk(0, k);
-          const double akk = A[pk(k, k)];
-          const int ne = (k * (k + 1)) >> 1;
-          if (fabs(akk) >= sfmin) {
-            const double d11 = 1.0 / akk;
-            for (int e = lane; e < ne; e += 32) {
-              const unsigned short q = ij[e];
-              const double xj = x[q >> 8];
-              if (xj != 0.0) A[e] = IPDDP_FMA(x[q & 0xff], -d11 * xj, A[e]);
+          double* x = A + ck;
+          const double akk = A[ck + k];
+          const double x0 = (i0 < k) ? x[i0] : 0.0;
+          const double x1 = (TWO && i1 < k) ? x[i1] : 0.0;
+          const int nnz = warp_compact<TWO>(x0 != 0.0, x1 != 0.0, list, lane);
+          if (nnz > 0) {
+            __syncwarp();
+            const bool big = fabs(akk) >= sfmin;
+            const double d11 = big ? 1.0 / akk : akk;
+            if (!big) {   // tiny pivot: LAPACK divides the column first, then updates with -akk
+              if (x0 != 0.0) x[i0] = x0 / akk;
+              if (TWO && x1 != 0.0) x[i1] = x1 / akk;
+              __syncwarp();
             }
-            __syncwarp();
-            for (int i = lane; i < k; i += 32) x[i] = x[i] * d11;
-          } else {
-            for (int i = lane; i < k; i += 32) x[i] = x[i] / akk;
-            __syncwarp();
-            for (int e = lane; e < ne; e += 32) {
-              const unsigned short q = ij[e];
-              const double xj = x[q >> 8];
-              if (xj != 0.0) A[e] = IPDDP_FMA(x[q & 0xff], -akk * xj, A[e]);
+            const int P = (nnz * (nnz + 1)) >> 1;
+            for (int pp = lane; pp < P; pp += 32) {
+              const unsigned q = tri_decode(pp);
+              const int i = list[q & 0xff], j = list[q >> 8];
+              const int e = coff(j) + i;
+              A[e] = IPDDP_FMA(x[i], -d11 * x[j], A[e]);
+            }
+            if (big) {
+              __syncwarp();
+              if (x0 != 0.0) x[i0] = x0 * d11;
+              if (TWO && x1 != 0.0) x[i1] = x1 * d11;
             }
           }
           __syncwarp();
@@ -151,201 +189,207 @@ IPDDP_D int warp_sytf2_rook(int n, double* A, int* ipiv, const unsigned short* i
       } else {
         if (k > 1) {
           const int m = k - 1;   // rows/columns 0..m-1 get updated
-          double* xk = A + pk(0, k);
-          double* xkm1 = A + pk(0, k - 1);
-          const double d12 = A[pk(k - 1, k)];
-          const double d22 = A[pk(k - 1, k - 1)] / d12;
-          const double d11 = A[pk(k, k)] / d12;
+          double* xk = A + ck;
+          double* xkm1 = A + coff(k - 1);
+          const double d12 = xk[k - 1];
+          const double d22 = xkm1[k - 1] / d12;
+          const double d11 = xk[k] / d12;
           const double t = 1.0 / (d11 * d22 - 1.0);
-          double* wk = w; double* wkm1 = w + n; double* rk = w + 2 * n; double* rkm1 = w + 3 * n;
-          for (int j = lane; j < m; j += 32) {
-            const double ak = xk[j], akm1 = xkm1[j];
-            wkm1[j] = t * (d11 * akm1 - ak);
-            wk[j] = t * (d22 * ak - akm1);
-            rk[j] = ak / d12;
-            rkm1[j] = akm1 / d12;
+          double* wk = w; double* wkm1 = w + K; double* rk = w + 2 * K; double* rkm1 = w + 3 * K;
+          bool f[2] = {false, false};
+#pragma unroll
+          for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+            const int j = lane + 32 * s;
+            if (j < m) {
+              const double ak = xk[j], akm1 = xkm1[j];
+              f[s] = (ak != 0.0) || (akm1 != 0.0);
+              if (f[s]) {
+                wkm1[j] = t * (d11 * akm1 - ak);
+                wk[j] = t * (d22 * ak - akm1);
+                rk[j] = ak / d12;
+                rkm1[j] = akm1 / d12;
+              }
+            }
           }
+          const int nnz = warp_compact<TWO>(f[0], f[1], list, lane);
           __syncwarp();
-          const int ne = (m * (m + 1)) >> 1;
-          for (int e = lane; e < ne; e += 32) {
-            const unsigned short q = ij[e];
-            const int i = q & 0xff, j = q >> 8;
+          const int P = (nnz * (nnz + 1)) >> 1;
+          for (int pp = lane; pp < P; pp += 32) {
+            const unsigned q = tri_decode(pp);
+            const int i = list[q & 0xff], j = list[q >> 8];
+            const int e = coff(j) + i;
             A[e] = A[e] - rk[i] * wk[j] - rkm1[i] * wkm1[j];
           }
-          for (int j = lane; j < m; j += 32) {
-            xk[j] = wk[j] / d12;
-            xkm1[j] = wkm1[j] / d12;
+#pragma unroll
+          for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+            const int j = lane + 32 * s;
+            if (f[s]) {
+              xk[j] = wk[j] / d12;
+              xkm1[j] = wkm1[j] / d12;
+            }
           }
           __syncwarp();
         }
       }
     }
-    (void)singular;
-    if (lane == 0) {
-      if (kstep == 1) {
-        ipiv[k] = kp + 1;
-      } else {
-        ipiv[k] = -(p + 1);
-        ipiv[k - 1] = -(kp + 1);
+    // pivot record + inertia of the finished D block
+    if (kstep == 1) {
+      if (lane == 0) ipiv[k] = kp + 1;
+      if (A[ck + k] > tol) np += 1;
+    } else {
+      if (lane == 0) { ipiv[k] = -(p + 1); ipiv[k - 1] = -(kp + 1); }
+      const double d11 = A[pk(k - 1, k - 1)], d12 = A[ck + k - 1], d22 = A[ck + k];
+      if (d12 != 0.0) {
+        const double a11 = fabs(d11), a22 = fabs(d22);
+        const double s1 = 2.0 * fmax(fmax(a11, fabs(d12)), a22);
+        double smin;
+        if (a11 >= a22) smin = fabs((d11 / s1) * d22 - (d12 / s1) * d12);
+        else            smin = fabs(d11 * (d22 / s1) - (d12 / s1) * d12);
+        const double trace = d11 + d22;
+        if (0.5 * s1 <= tol) {
+        } else if (smin > tol || trace == 0.0) {
+          np += 1;
+        } else if (trace >= 0.0) {
+          np += 1;
+        }
+      } else {   // reference: zero super-diagonal => two 1x1 blocks
+        if (d11 > tol) np += 1;
+        if (d22 > tol) np += 1;
       }
     }
     k -= kstep;
   }
   __syncwarp();
+  np_out = np;
   return info;
 }
 
-// number of positive eigenvalues of D with absolute tolerance tol (reference `inertia!`, atol = 1e-12);
-// executed redundantly by every lane (uniform, broadcast reads)
-IPDDP_D int warp_inertia_np(int n, const double* A, const int* ipiv, double tol) {
-  int np = 0;
-  int i = 0;
-  // blocks are parsed from the bottom as get_D! does; 2x2 blocks are (i, i+1) with both ipiv < 0.
-  // Walk upwards from the top using the pairing implied by the bottom-up parse: count the negative
-  // entries below to know the parity.
-  // A bottom-up parse pairs negatives from the end; runs of negatives always have even length
-  // (LAPACK marks both rows of a 2x2 block), so a top-down pairing is identical.
-  while (i < n) {
-    bool two = false;
-    double d12 = 0.0;
-    if (i + 1 < n && ipiv[i] < 0 && ipiv[i + 1] < 0) {
-      d12 = A[pk(i, i + 1)];
-      two = (d12 != 0.0);
-    }
-    if (two) {
-      const double d11 = A[pk(i, i)], d22 = A[pk(i + 1, i + 1)];
-      const double a11 = fabs(d11), a22 = fabs(d22);
-      const double s1 = 2.0 * fmax(fmax(a11, fabs(d12)), a22);
-      double smin;
-      if (a11 >= a22) smin = fabs((d11 / s1) * d22 - (d12 / s1) * d12);
-      else            smin = fabs(d11 * (d22 / s1) - (d12 / s1) * d12);
-      const double trace = d11 + d22;
-      if (0.5 * s1 <= tol) {
-      } else if (smin > tol || trace == 0.0) {
-        np += 1;
-      } else if (trace >= 0.0) {
-        np += 1;
-      }
-      i += 2;
-    } else {
-      if (i + 1 < n && ipiv[i] < 0 && ipiv[i + 1] < 0) {
-        // 2x2 block whose off-diagonal is exactly zero: reference treats both rows as 1x1 blocks
-        if (A[pk(i, i)] > tol) np += 1;
-        if (A[pk(i + 1, i + 1)] > tol) np += 1;
-        i += 2;
-      } else {
-        if (A[pk(i, i)] > tol) np += 1;
-        i += 1;
-      }
-    }
-  }
-  return np;
-}
-
-// dsytrs_rook('U') on NR right-hand sides held column-major in Bm (leading dimension n).
-// Backward substitution spreads each column update over the lanes; the forward substitution's
-// dgemv('T') dot products use 4 lanes per right-hand side (partial sums i mod 4, then a 2-step
-// butterfly) -- the dot4 order.
-template <int NR>
-IPDDP_D void warp_sytrs_rook(int n, const double* A, const int* ipiv, double* Bm, int lane) {
-  int k = n - 1;
+// dsytrs_rook('U') on NR right-hand sides held column-major in Bm (leading dimension K).
+template <int K, int NR>
+IPDDP_D void warp_sytrs_rook(const double* A, const int* ipiv, double* Bm, int lane) {
+  constexpr bool TWO = K > 32;
+  const int i0 = lane, i1 = lane + 32;
+  int k = K - 1;
   while (k >= 0) {
+    const int ck = coff(k);
     if (ipiv[k] > 0) {
       const int kp = ipiv[k] - 1;
-      if (kp != k && lane < NR) {
-        const double t = Bm[k + lane * n]; Bm[k + lane * n] = Bm[kp + lane * n]; Bm[kp + lane * n] = t;
+      if (kp != k) {
+        if (lane < NR) { const double t = Bm[k + lane * K]; Bm[k + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
+        __syncwarp();
       }
-      __syncwarp();
-      const double* x = A + pk(0, k);
+      const double x0 = (i0 < k) ? A[ck + i0] : 0.0;
+      const double x1 = (TWO && i1 < k) ? A[ck + i1] : 0.0;
+      if (x0 != 0.0) {
 #pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        const double t = -Bm[k + j * n];
-        for (int i = lane; i < k; i += 32) Bm[i + j * n] = IPDDP_FMA(x[i], t, Bm[i + j * n]);
+        for (int j = 0; j < NR; ++j) Bm[i0 + j * K] = IPDDP_FMA(x0, -Bm[k + j * K], Bm[i0 + j * K]);
+      }
+      if (TWO && x1 != 0.0) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) Bm[i1 + j * K] = IPDDP_FMA(x1, -Bm[k + j * K], Bm[i1 + j * K]);
       }
       __syncwarp();
-      if (lane < NR) Bm[k + lane * n] = Bm[k + lane * n] * (1.0 / A[pk(k, k)]);
+      if (lane < NR) Bm[k + lane * K] = Bm[k + lane * K] * (1.0 / A[ck + k]);
       __syncwarp();
       k -= 1;
     } else {
       int kp = -ipiv[k] - 1;
-      if (kp != k && lane < NR) {
-        const double t = Bm[k + lane * n]; Bm[k + lane * n] = Bm[kp + lane * n]; Bm[kp + lane * n] = t;
+      if (kp != k) {
+        if (lane < NR) { const double t = Bm[k + lane * K]; Bm[k + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
+        __syncwarp();
       }
-      __syncwarp();
       kp = -ipiv[k - 1] - 1;
-      if (kp != k - 1 && lane < NR) {
-        const double t = Bm[k - 1 + lane * n]; Bm[k - 1 + lane * n] = Bm[kp + lane * n]; Bm[kp + lane * n] = t;
+      if (kp != k - 1) {
+        if (lane < NR) { const double t = Bm[k - 1 + lane * K]; Bm[k - 1 + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
+        __syncwarp();
       }
-      __syncwarp();
+      const int ckm1 = coff(k - 1);
       if (k > 1) {
-        const double* xk = A + pk(0, k);
-        const double* xkm1 = A + pk(0, k - 1);
 #pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          const double tk = -Bm[k + j * n];
-          const double tkm1 = -Bm[k - 1 + j * n];
-          for (int i = lane; i < k - 1; i += 32) {
-            double bv = IPDDP_FMA(xk[i], tk, Bm[i + j * n]);
-            Bm[i + j * n] = IPDDP_FMA(xkm1[i], tkm1, bv);
+        for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+          const int i = lane + 32 * s;
+          if (i < k - 1) {
+            const double xa = A[ck + i], xb = A[ckm1 + i];
+            if (xa != 0.0 || xb != 0.0) {
+#pragma unroll
+              for (int j = 0; j < NR; ++j) {
+                const double bv = IPDDP_FMA(xa, -Bm[k + j * K], Bm[i + j * K]);
+                Bm[i + j * K] = IPDDP_FMA(xb, -Bm[k - 1 + j * K], bv);
+              }
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
       if (lane < NR) {
-        const double akm1k = A[pk(k - 1, k)];
-        const double akm1 = A[pk(k - 1, k - 1)] / akm1k;
-        const double ak = A[pk(k, k)] / akm1k;
+        const double akm1k = A[ck + k - 1];
+        const double akm1 = A[ckm1 + k - 1] / akm1k;
+        const double ak = A[ck + k] / akm1k;
         const double denom = akm1 * ak - 1.0;
-        const double bkm1 = Bm[k - 1 + lane * n] / akm1k;
-        const double bk = Bm[k + lane * n] / akm1k;
-        Bm[k - 1 + lane * n] = (ak * bkm1 - bk) / denom;
-        Bm[k + lane * n] = (akm1 * bk - bkm1) / denom;
+        const double bkm1 = Bm[k - 1 + lane * K] / akm1k;
+        const double bk = Bm[k + lane * K] / akm1k;
+        Bm[k - 1 + lane * K] = (ak * bkm1 - bk) / denom;
+        Bm[k + lane * K] = (akm1 * bk - bkm1) / denom;
       }
       __syncwarp();
       k -= 2;
     }
   }
-  // forward: U' X = B
+  // forward: U' X = B;  lane = (rhs column j, partial g)
   const int g = lane & 3;
+  constexpr int NPASS = (NR + 7) / 8;
   k = 0;
-  while (k < n) {
+  while (k < K) {
     const bool one = ipiv[k] > 0;
-    const int ncol = one ? 1 : 2;   // pivot columns handled in this step
-    for (int c = 0; c < ncol; ++c) {
-      const int kc = k + c;
-      if (k > 0) {
-        const double* x = A + pk(0, kc);
-        for (int j0 = 0; j0 < NR; j0 += 8) {
-          const int j = j0 + (lane >> 2);
-          double s = 0.0;
-          if (j < NR)
-            for (int i = g; i < k; i += 4) s = IPDDP_FMA(x[i], Bm[i + j * n], s);
-          s = s + __shfl_xor_sync(IPDDP_FULL_MASK, s, 1);
-          s = s + __shfl_xor_sync(IPDDP_FULL_MASK, s, 2);
-          if (j < NR && g == 0) Bm[kc + j * n] = Bm[kc + j * n] - s;
+    if (k > 0) {
+      const double* xa = A + coff(k);
+      const double* xb = A + coff(k + (one ? 0 : 1));
+#pragma unroll
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int j = ps * 8 + (lane >> 2);
+        const bool act = j < NR;
+        const double* bj = Bm + (act ? j : 0) * K;
+        double sa = 0.0, sb = 0.0;
+        if (act) {
+          if (one) {
+            for (int i = g; i < k; i += 4) sa = IPDDP_FMA(xa[i], bj[i], sa);
+          } else {
+            for (int i = g; i < k; i += 4) { const double bv = bj[i]; sa = IPDDP_FMA(xa[i], bv, sa); sb = IPDDP_FMA(xb[i], bv, sb); }
+          }
+        }
+        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
+        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
+        if (!one) {
+          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
+          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
+        }
+        if (act && g == 0) {
+          Bm[k + j * K] = Bm[k + j * K] - sa;
+          if (!one) Bm[k + 1 + j * K] = Bm[k + 1 + j * K] - sb;
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
     if (one) {
       const int kp = ipiv[k] - 1;
-      if (kp != k && lane < NR) {
-        const double t = Bm[k + lane * n]; Bm[k + lane * n] = Bm[kp + lane * n]; Bm[kp + lane * n] = t;
+      if (kp != k) {
+        if (lane < NR) { const double t = Bm[k + lane * K]; Bm[k + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
+        __syncwarp();
       }
       k += 1;
     } else {
       int kp = -ipiv[k] - 1;
-      if (kp != k && lane < NR) {
-        const double t = Bm[k + lane * n]; Bm[k + lane * n] = Bm[kp + lane * n]; Bm[kp + lane * n] = t;
+      if (kp != k) {
+        if (lane < NR) { const double t = Bm[k + lane * K]; Bm[k + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
+        __syncwarp();
       }
-      __syncwarp();
       kp = -ipiv[k + 1] - 1;
-      if (kp != k + 1 && lane < NR) {
-        const double t = Bm[k + 1 + lane * n]; Bm[k + 1 + lane * n] = Bm[kp + lane * n]; Bm[kp + lane * n] = t;
+      if (kp != k + 1) {
+        if (lane < NR) { const double t = Bm[k + 1 + lane * K]; Bm[k + 1 + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
+        __syncwarp();
       }
       k += 2;
     }
-    __syncwarp();
   }
 }
 

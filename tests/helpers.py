@@ -168,7 +168,7 @@ def ldlt_parity(lib, oracle, rng, nmat=200, nmax=35, device=0):
     """Device dsytf2_rook / inertia / dsytrs_rook vs the oracle's restatement: bit-identical factors, pivots,
     info, inertia and solutions."""
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
-    for n in sorted(set([1, 2, 3, 4, 14, 15, 17, nmax])):
+    for n in sorted(set([1, 2, 3, 4, 8, 14, 15, 17, 32, 33, 35, 48, 64])):
         if n > nmax:
             continue
         mats = []
