@@ -49,7 +49,7 @@ template <class M> struct BwLayout {
   static constexpr int IPIV_B = DBL_END * 8;
   static constexpr int TBL_B = IPIV_B + pad(K) * 4;
   static constexpr int LIST_B = TBL_B + pad(M::NTBL) * 4;
-  static constexpr int BYTES = ((LIST_B + 64 + 15) / 16) * 16;
+  static constexpr int BYTES = ((LIST_B + LdltScratch<(K > 0 ? K : 1)>::BYTES + 15) / 16) * 16;
 };
 
 template <class M>
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
       __syncwarp();
       // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
       int np = 0;
-      const int info = warp_sytf2_rook<K>(lhs, ipiv, ws, nzlist, lane, 1e-12, np);
+      const int info = warp_ldlt_factor<K, NR>(lhs, ipiv, rhs, ws, nzlist, lane, 1e-12, np);
       delta_c = 0.0;
       if (info > 0) delta_c = v.opt.delta_c * dm::pow(mu, v.opt.kappa_c);
       if (np != NU || info != 0) {
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
         status = 1;
         break;
       }
-      warp_sytrs_rook<K, NR>(lhs, ipiv, rhs, lane);
+      warp_ldlt_solve_forward<K, NR>(lhs, ipiv, rhs, nzlist, lane);
       // ---- gains to HBM: eq block, then ineq block                      (:159-172)
       double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
       for (int e = lane; e < K * NR; e += 32) g[e] = rhs[e];

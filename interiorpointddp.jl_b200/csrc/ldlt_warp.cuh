@@ -4,26 +4,31 @@
 // Replaces LAPACK dsytrf_rook('U') (reached by the reference at src/inertia_correction.jl:261 through
 // FastLapackInterface), dsytrs_rook (`ldiv!(bk, eq[t])`, src/backward_pass.jl:148) and `inertia!`
 // (src/inertia_correction.jl:54-205) for n <= 64, i.e. the unblocked dsytf2_rook path.  One warp works
-// on one matrix; every matrix element sees exactly the operation sequence of the unblocked LAPACK
-// algorithm (rank-1 update as fma(x_i, -d*x_j, a_ij) like OpenBLAS' dsyr; everything else plain IEEE
-// ops), so factors, pivot sequence and `info` do not depend on the lane mapping.
+// on one matrix; every matrix / right-hand-side element sees exactly the operation sequence of the
+// unblocked LAPACK algorithms (rank-1 update as fma(x_i, -d*x_j, a_ij) like OpenBLAS' dsyr; everything
+// else plain IEEE ops), so factors, pivot sequence, `info` and the solution do not depend on the lane mapping.
 //
 // How the work is mapped (the kernel is instruction-issue bound):
 //   * pivot searches: |a| is an order-preserving 64-bit key; two REDUX.MAX (high / low word) + ballots give
 //     the maximum and the set of ties, from which IDAMAX's first-maximum rule and dsytf2_rook's
-//     "row segment first, column segment only if strictly larger" rule are applied on a 64-bit tie mask;
+//     "row segment first, column segment only if strictly larger" rule are applied on the tie mask;
 //   * trailing updates are SPARSE: pivot columns of IPDDP2 KKT matrices are mostly zero (measured: 23 %
 //     non-zero entries, 7 % of the rank-1 element updates do arithmetic), so the non-zero row indices are
 //     compacted with a ballot and only the nnz(nnz+1)/2 affected elements are touched.  Skipped
 //     elements would receive fma(0, t, a) = a, i.e. the skip is exact for finite data (only the sign of
-//     an exact zero can differ);
+//     an exact zero can differ).  The row lists are kept per pivot column and reused by both triangular
+//     solves (their skipped terms are fma(0, b, s) = s as well);
+//   * dsytrs_rook's first loop (interchange, rank-1 downdate of B, scaling) runs in the same k-descending
+//     pivot order as the factorisation, so it is fused into it: the multipliers are still in registers and
+//     1/a_kk is not recomputed.  Only the U' solve is a separate pass;
 //   * the inertia of D is counted while the pivots are produced (a D block is final when it is chosen);
-//   * triangular solves: one lane per row for the rank-1 downdates, 4 lanes per right-hand side for the
-//     dgemv('T') dot products (partial sums i mod 4 + 2-step butterfly = the dot4 summation order).
+//   * rows >= 32 (second slot per lane) are only touched while the pivot index is >= 32.
 #pragma once
 #include "kernels_common.cuh"
 
 namespace ipk {
+
+constexpr int NZCAP = 8;          // non-zero rows remembered per pivot column; more => dense fallback (count 255)
 
 IPDDP_D int coff(int j) { return (j * (j + 1)) >> 1; }
 IPDDP_D int pk(int i, int j) { return i + coff(j); }   // requires i <= j
@@ -86,166 +91,136 @@ IPDDP_D int warp_compact(bool f0, bool f1, unsigned char* list, int lane) {
   return n;
 }
 
-// dsytf2_rook('U') on the packed matrix A of order K.  ipiv: K ints (LAPACK 1-based convention),
-// w: scratch of 4K doubles, list: K bytes.  Returns info; np_out = number of positive eigenvalues of D
-// (reference inertia! with atol = tol).
-template <int K>
-IPDDP_D int warp_sytf2_rook(double* A, int* ipiv, double* w, unsigned char* list, int lane, double tol, int& np_out) {
-  constexpr bool TWO = K > 32;
+template <int NR> IPDDP_D void warp_swap_rows(double* Bm, int ld, int a, int b, int lane) {
+  if (lane < NR) { const double t = Bm[a + lane * ld]; Bm[a + lane * ld] = Bm[b + lane * ld]; Bm[b + lane * ld] = t; }
+}
+
+// Scratch layout used by the factorisation: w: 4K doubles; list: K bytes (current compaction);
+// nzc: K bytes (count per pivot column, 255 = dense), nzl: K*NZCAP bytes (row lists per pivot column).
+template <int K> struct LdltScratch {
+  static constexpr int BYTES = ((K + K + K * NZCAP + 15) / 16) * 16;
+};
+
+// One pivot step (column k) of dsytf2_rook('U') fused with dsytrs_rook's first loop on Bm.
+// Returns kstep (1 or 2).  TWO = rows >= 32 may be involved (k >= 32).
+template <int K, int NR, bool TWO>
+IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsigned char* list, unsigned char* nzc,
+                      unsigned char* nzl, int lane, unsigned tri_lane, double tol, int& info, int& np) {
   const double alpha = 0.6403882032022076;   // (1 + sqrt(17)) / 8
   const double sfmin = 2.2250738585072014e-308;
-  int info = 0, np = 0;
-  int k = K - 1;   // 0-based pivot column
   const int i0 = lane, i1 = lane + 32;
-  while (k >= 0) {
-    int kstep = 1, p = k, kp = k;
-    const int ck = coff(k);
-    const double absakk = fabs(A[ck + k]);
-    double colmax = 0.0;
-    int imax = 0;
-    if (k > 0) {
+  int kstep = 1, p = k, kp = k;
+  const int ck = coff(k);
+  const double absakk = fabs(A[ck + k]);
+  double colmax = 0.0;
+  int imax = 0;
+  if (k > 0) {
+    unsigned long long ties;
+    const bool v0 = i0 < k, v1 = TWO && i1 < k;
+    colmax = warp_max_ties<TWO>(v0 ? fabs(A[ck + i0]) : 0.0, v0, v1 ? fabs(A[ck + i1]) : 0.0, v1, ties);
+    imax = __ffsll((long long)ties) - 1;
+  }
+  if (fmax(absakk, colmax) == 0.0) {
+    // exactly singular column: no elimination (LAPACK sets info and moves on); dsytrs would divide by zero
+    if (info == 0) info = k + 1;
+    if (lane == 0) { ipiv[k] = k + 1; nzc[k] = 0; }
+    return 1;
+  }
+  if (absakk < alpha * colmax) {
+    for (;;) {
+      // largest off-diagonal magnitude in row/column imax of the leading block; ties: the row segment
+      // (c > imax) is searched first and wins, lowest index inside a segment
+      const int ci = coff(imax);
+      const bool v0 = i0 <= k && i0 != imax, v1 = TWO && i1 <= k && i1 != imax;
+      const double a0 = v0 ? fabs(i0 < imax ? A[ci + i0] : A[coff(i0) + imax]) : 0.0;
+      const double a1 = v1 ? fabs(i1 < imax ? A[ci + i1] : A[coff(i1) + imax]) : 0.0;
       unsigned long long ties;
-      const bool v0 = i0 < k, v1 = TWO && i1 < k;
-      colmax = warp_max_ties<TWO>(v0 ? fabs(A[ck + i0]) : 0.0, v0, v1 ? fabs(A[ck + i1]) : 0.0, v1, ties);
-      imax = __ffsll((long long)ties) - 1;
+      const double rowmax = warp_max_ties<TWO>(a0, v0, a1, v1, ties);
+      const unsigned long long rowpart = ties & ~((2ull << imax) - 1ull);
+      const int jmax = __ffsll((long long)(rowpart ? rowpart : ties)) - 1;
+      if (!(fabs(A[ci + imax]) < alpha * rowmax)) { kp = imax; break; }
+      else if (p == jmax || rowmax <= colmax) { kp = imax; kstep = 2; break; }
+      else { p = imax; colmax = rowmax; imax = jmax; }
     }
-    if (fmax(absakk, colmax) == 0.0) {
-      if (info == 0) info = k + 1;
-      kp = k;
-    } else {
-      if (!(absakk < alpha * colmax)) {
-        kp = k;
-      } else {
-        for (;;) {
-          // largest off-diagonal magnitude in row/column imax of the leading block; ties: the row segment
-          // (c > imax) is searched first and wins, lowest index inside a segment
-          const int ci = coff(imax);
-          const bool v0 = i0 <= k && i0 != imax, v1 = TWO && i1 <= k && i1 != imax;
-          const double a0 = v0 ? fabs(i0 < imax ? A[ci + i0] : A[coff(i0) + imax]) : 0.0;
-          const double a1 = v1 ? fabs(i1 < imax ? A[ci + i1] : A[coff(i1) + imax]) : 0.0;
-          unsigned long long ties;
-          const double rowmax = warp_max_ties<TWO>(a0, v0, a1, v1, ties);
-          const unsigned long long rowpart = ties & ~((2ull << imax) - 1ull);
-          const int jmax = __ffsll((long long)(rowpart ? rowpart : ties)) - 1;
-          if (!(fabs(A[ci + imax]) < alpha * rowmax)) {
-            kp = imax;
-            break;
-          } else if (p == jmax || rowmax <= colmax) {
-            kp = imax;
-            kstep = 2;
-            break;
-          } else {
-            p = imax;
-            colmax = rowmax;
-            imax = jmax;
-          }
-        }
-      }
-      __syncwarp();
-      if (kstep == 2 && p != k) {   // first interchange: k <-> p
-        warp_sym_swap<TWO>(A, p, k, lane);
+  }
+  __syncwarp();
+  if (kstep == 2 && p != k) {   // first interchange: k <-> p  (matrix and right-hand sides)
+    warp_sym_swap<TWO>(A, p, k, lane);
+    warp_swap_rows<NR>(Bm, K, k, p, lane);
+    __syncwarp();
+  }
+  const int kk = k - kstep + 1;
+  if (kp != kk) {               // second interchange: kk <-> kp
+    warp_sym_swap<TWO>(A, kp, kk, lane);
+    if (kstep == 2 && lane == 0) {
+      const int pa = pk(k - 1, k), pb = pk(kp, k);
+      const double t = A[pa]; A[pa] = A[pb]; A[pb] = t;
+    }
+    warp_swap_rows<NR>(Bm, K, kk, kp, lane);
+    __syncwarp();
+  }
+  if (kstep == 1) {
+    const double akk = A[ck + k];
+    if (lane == 0) ipiv[k] = kp + 1;
+    if (akk > tol) np += 1;
+    int nnz = 0;
+    double x0 = 0.0, x1 = 0.0, d11 = 0.0;
+    const bool big = fabs(akk) >= sfmin;
+    if (k > 0) {
+      double* x = A + ck;
+      x0 = (i0 < k) ? x[i0] : 0.0;
+      x1 = (TWO && i1 < k) ? x[i1] : 0.0;
+      nnz = warp_compact<TWO>(x0 != 0.0, x1 != 0.0, list, lane);
+      d11 = big ? 1.0 / akk : akk;
+      if (nnz > 0) {
         __syncwarp();
-      }
-      const int kk = k - kstep + 1;
-      if (kp != kk) {               // second interchange: kk <-> kp
-        warp_sym_swap<TWO>(A, kp, kk, lane);
-        if (kstep == 2 && lane == 0) {
-          const int pa = pk(k - 1, k), pb = pk(kp, k);
-          const double t = A[pa]; A[pa] = A[pb]; A[pb] = t;
-        }
-        __syncwarp();
-      }
-      if (kstep == 1) {
-        if (k > 0) {
-          double* x = A + ck;
-          const double akk = A[ck + k];
-          const double x0 = (i0 < k) ? x[i0] : 0.0;
-          const double x1 = (TWO && i1 < k) ? x[i1] : 0.0;
-          const int nnz = warp_compact<TWO>(x0 != 0.0, x1 != 0.0, list, lane);
-          if (nnz > 0) {
-            __syncwarp();
-            const bool big = fabs(akk) >= sfmin;
-            const double d11 = big ? 1.0 / akk : akk;
-            if (!big) {   // tiny pivot: LAPACK divides the column first, then updates with -akk
-              if (x0 != 0.0) x[i0] = x0 / akk;
-              if (TWO && x1 != 0.0) x[i1] = x1 / akk;
-              __syncwarp();
-            }
-            const int P = (nnz * (nnz + 1)) >> 1;
-            for (int pp = lane; pp < P; pp += 32) {
-              const unsigned q = tri_decode(pp);
-              const int i = list[q & 0xff], j = list[q >> 8];
-              const int e = coff(j) + i;
-              A[e] = IPDDP_FMA(x[i], -d11 * x[j], A[e]);
-            }
-            if (big) {
-              __syncwarp();
-              if (x0 != 0.0) x[i0] = x0 * d11;
-              if (TWO && x1 != 0.0) x[i1] = x1 * d11;
-            }
-          }
+        if (!big) {   // tiny pivot: LAPACK divides the column first, then updates with -akk
+          if (x0 != 0.0) { x0 = x0 / akk; x[i0] = x0; }
+          if (TWO && x1 != 0.0) { x1 = x1 / akk; x[i1] = x1; }
           __syncwarp();
         }
-      } else {
-        if (k > 1) {
-          const int m = k - 1;   // rows/columns 0..m-1 get updated
-          double* xk = A + ck;
-          double* xkm1 = A + coff(k - 1);
-          const double d12 = xk[k - 1];
-          const double d22 = xkm1[k - 1] / d12;
-          const double d11 = xk[k] / d12;
-          const double t = 1.0 / (d11 * d22 - 1.0);
-          double* wk = w; double* wkm1 = w + K; double* rk = w + 2 * K; double* rkm1 = w + 3 * K;
-          bool f[2] = {false, false};
-#pragma unroll
-          for (int s = 0; s < (TWO ? 2 : 1); ++s) {
-            const int j = lane + 32 * s;
-            if (j < m) {
-              const double ak = xk[j], akm1 = xkm1[j];
-              f[s] = (ak != 0.0) || (akm1 != 0.0);
-              if (f[s]) {
-                wkm1[j] = t * (d11 * akm1 - ak);
-                wk[j] = t * (d22 * ak - akm1);
-                rk[j] = ak / d12;
-                rkm1[j] = akm1 / d12;
-              }
-            }
-          }
-          const int nnz = warp_compact<TWO>(f[0], f[1], list, lane);
-          __syncwarp();
-          const int P = (nnz * (nnz + 1)) >> 1;
-          for (int pp = lane; pp < P; pp += 32) {
-            const unsigned q = tri_decode(pp);
-            const int i = list[q & 0xff], j = list[q >> 8];
-            const int e = coff(j) + i;
-            A[e] = A[e] - rk[i] * wk[j] - rkm1[i] * wkm1[j];
-          }
-#pragma unroll
-          for (int s = 0; s < (TWO ? 2 : 1); ++s) {
-            const int j = lane + 32 * s;
-            if (f[s]) {
-              xk[j] = wk[j] / d12;
-              xkm1[j] = wkm1[j] / d12;
-            }
-          }
-          __syncwarp();
+        const int P = (nnz * (nnz + 1)) >> 1;
+        for (int pp = lane; pp < P; pp += 32) {
+          const unsigned q = (pp < 32) ? tri_lane : tri_decode(pp);
+          const int i = list[q & 0xff], j = list[q >> 8];
+          const int e = coff(j) + i;
+          A[e] = IPDDP_FMA(x[i], -d11 * x[j], A[e]);
         }
+        if (big) {    // scale the multipliers (registers keep the scaled values for the B downdate)
+          __syncwarp();
+          if (x0 != 0.0) { x0 = x0 * d11; x[i0] = x0; }
+          if (TWO && x1 != 0.0) { x1 = x1 * d11; x[i1] = x1; }
+        }
+        if (lane < nnz && lane < NZCAP) nzl[k * NZCAP + lane] = list[lane];
       }
     }
-    // pivot record + inertia of the finished D block
-    if (kstep == 1) {
-      if (lane == 0) ipiv[k] = kp + 1;
-      if (A[ck + k] > tol) np += 1;
-    } else {
-      if (lane == 0) { ipiv[k] = -(p + 1); ipiv[k - 1] = -(kp + 1); }
-      const double d11 = A[pk(k - 1, k - 1)], d12 = A[ck + k - 1], d22 = A[ck + k];
+    if (lane == 0) nzc[k] = (unsigned char)(nnz <= NZCAP ? nnz : 255);
+    // dsytrs first loop for this pivot: B(0:k-1,:) -= x * B(k,:), then B(k,:) *= 1/akk
+    if (x0 != 0.0) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) Bm[i0 + j * K] = IPDDP_FMA(x0, -Bm[k + j * K], Bm[i0 + j * K]);
+    }
+    if (TWO && x1 != 0.0) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) Bm[i1 + j * K] = IPDDP_FMA(x1, -Bm[k + j * K], Bm[i1 + j * K]);
+    }
+    __syncwarp();
+    if (lane < NR) Bm[k + lane * K] = Bm[k + lane * K] * (k > 0 && big ? d11 : 1.0 / akk);
+    __syncwarp();
+  } else {
+    double* xk = A + ck;
+    double* xkm1 = A + coff(k - 1);
+    const double d12 = xk[k - 1];
+    if (lane == 0) { ipiv[k] = -(p + 1); ipiv[k - 1] = -(kp + 1); }
+    {   // inertia of the 2x2 block (reference inertia!, atol = tol)
+      const double e11 = xkm1[k - 1], e22 = xk[k];
       if (d12 != 0.0) {
-        const double a11 = fabs(d11), a22 = fabs(d22);
+        const double a11 = fabs(e11), a22 = fabs(e22);
         const double s1 = 2.0 * fmax(fmax(a11, fabs(d12)), a22);
         double smin;
-        if (a11 >= a22) smin = fabs((d11 / s1) * d22 - (d12 / s1) * d12);
-        else            smin = fabs(d11 * (d22 / s1) - (d12 / s1) * d12);
-        const double trace = d11 + d22;
+        if (a11 >= a22) smin = fabs((e11 / s1) * e22 - (d12 / s1) * d12);
+        else            smin = fabs(e11 * (e22 / s1) - (d12 / s1) * d12);
+        const double trace = e11 + e22;
         if (0.5 * s1 <= tol) {
         } else if (smin > tol || trace == 0.0) {
           np += 1;
@@ -253,109 +228,135 @@ IPDDP_D int warp_sytf2_rook(double* A, int* ipiv, double* w, unsigned char* list
           np += 1;
         }
       } else {   // reference: zero super-diagonal => two 1x1 blocks
-        if (d11 > tol) np += 1;
-        if (d22 > tol) np += 1;
+        if (e11 > tol) np += 1;
+        if (e22 > tol) np += 1;
       }
     }
-    k -= kstep;
+    int nnz = 0;
+    bool f[2] = {false, false};
+    if (k > 1) {
+      const int m = k - 1;   // rows/columns 0..m-1 get updated
+      const double d22 = xkm1[k - 1] / d12;
+      const double d11 = xk[k] / d12;
+      const double t = 1.0 / (d11 * d22 - 1.0);
+      double* wk = w; double* wkm1 = w + K; double* rk = w + 2 * K; double* rkm1 = w + 3 * K;
+#pragma unroll
+      for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+        const int j = lane + 32 * s;
+        if (j < m) {
+          const double ak = xk[j], akm1 = xkm1[j];
+          f[s] = (ak != 0.0) || (akm1 != 0.0);
+          if (f[s]) {
+            wkm1[j] = t * (d11 * akm1 - ak);
+            wk[j] = t * (d22 * ak - akm1);
+            rk[j] = ak / d12;
+            rkm1[j] = akm1 / d12;
+          }
+        }
+      }
+      nnz = warp_compact<TWO>(f[0], f[1], list, lane);
+      __syncwarp();
+      const int P = (nnz * (nnz + 1)) >> 1;
+      for (int pp = lane; pp < P; pp += 32) {
+        const unsigned q = (pp < 32) ? tri_lane : tri_decode(pp);
+        const int i = list[q & 0xff], j = list[q >> 8];
+        const int e = coff(j) + i;
+        A[e] = A[e] - rk[i] * wk[j] - rkm1[i] * wkm1[j];
+      }
+#pragma unroll
+      for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+        const int j = lane + 32 * s;
+        if (f[s]) {
+          xk[j] = wk[j] / d12;
+          xkm1[j] = wkm1[j] / d12;
+        }
+      }
+      if (lane < nnz && lane < NZCAP) { nzl[k * NZCAP + lane] = list[lane]; nzl[(k - 1) * NZCAP + lane] = list[lane]; }
+      __syncwarp();
+    }
+    if (lane == 0) { const unsigned char c = (unsigned char)(nnz <= NZCAP ? nnz : 255); nzc[k] = c; nzc[k - 1] = c; }
+    // dsytrs first loop for the 2x2 block: two rank-1 downdates of B, then the 2x2 solve
+#pragma unroll
+    for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+      const int i = lane + 32 * s;
+      if (f[s]) {
+        const double xa = xk[i], xb = xkm1[i];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          const double bv = IPDDP_FMA(xa, -Bm[k + j * K], Bm[i + j * K]);
+          Bm[i + j * K] = IPDDP_FMA(xb, -Bm[k - 1 + j * K], bv);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane < NR) {
+      const double akm1k = d12;
+      const double akm1 = xkm1[k - 1] / akm1k;
+      const double ak = xk[k] / akm1k;
+      const double denom = akm1 * ak - 1.0;
+      const double bkm1 = Bm[k - 1 + lane * K] / akm1k;
+      const double bk = Bm[k + lane * K] / akm1k;
+      Bm[k - 1 + lane * K] = (ak * bkm1 - bk) / denom;
+      Bm[k + lane * K] = (akm1 * bk - bkm1) / denom;
+    }
+    __syncwarp();
   }
+  return kstep;
+}
+
+// dsytf2_rook('U') on the packed matrix A of order K, fused with the first (U D) loop of dsytrs_rook on
+// the NR right-hand sides in Bm (column-major, leading dimension K).  Returns info; np_out = number of
+// positive eigenvalues of D.  If info != 0 the contents of Bm are meaningless (the caller restarts).
+template <int K, int NR>
+IPDDP_D int warp_ldlt_factor(double* A, int* ipiv, double* Bm, double* w, unsigned char* scratch, int lane, double tol,
+                             int& np_out) {
+  unsigned char* list = scratch;
+  unsigned char* nzc = scratch + K;
+  unsigned char* nzl = scratch + 2 * K;
+  const unsigned tri_lane = tri_decode(lane);
+  int info = 0, np = 0;
+  int k = K - 1;
+  if (K > 32) {
+    while (k >= 32) k -= ldlt_step<K, NR, true>(k, A, ipiv, Bm, w, list, nzc, nzl, lane, tri_lane, tol, info, np);
+  }
+  while (k >= 0) k -= ldlt_step<K, NR, false>(k, A, ipiv, Bm, w, list, nzc, nzl, lane, tri_lane, tol, info, np);
   __syncwarp();
   np_out = np;
   return info;
 }
 
-// dsytrs_rook('U') on NR right-hand sides held column-major in Bm (leading dimension K).
+// second loop of dsytrs_rook('U'): U' X = B, k ascending.  4 lanes per right-hand side accumulate the
+// dgemv('T') dot product in the dot4 order (partial sums by i mod 4, ascending i, 2-step butterfly);
+// zero multipliers are skipped through the per-column row lists.
 template <int K, int NR>
-IPDDP_D void warp_sytrs_rook(const double* A, const int* ipiv, double* Bm, int lane) {
-  constexpr bool TWO = K > 32;
-  const int i0 = lane, i1 = lane + 32;
-  int k = K - 1;
-  while (k >= 0) {
-    const int ck = coff(k);
-    if (ipiv[k] > 0) {
-      const int kp = ipiv[k] - 1;
-      if (kp != k) {
-        if (lane < NR) { const double t = Bm[k + lane * K]; Bm[k + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
-        __syncwarp();
-      }
-      const double x0 = (i0 < k) ? A[ck + i0] : 0.0;
-      const double x1 = (TWO && i1 < k) ? A[ck + i1] : 0.0;
-      if (x0 != 0.0) {
-#pragma unroll
-        for (int j = 0; j < NR; ++j) Bm[i0 + j * K] = IPDDP_FMA(x0, -Bm[k + j * K], Bm[i0 + j * K]);
-      }
-      if (TWO && x1 != 0.0) {
-#pragma unroll
-        for (int j = 0; j < NR; ++j) Bm[i1 + j * K] = IPDDP_FMA(x1, -Bm[k + j * K], Bm[i1 + j * K]);
-      }
-      __syncwarp();
-      if (lane < NR) Bm[k + lane * K] = Bm[k + lane * K] * (1.0 / A[ck + k]);
-      __syncwarp();
-      k -= 1;
-    } else {
-      int kp = -ipiv[k] - 1;
-      if (kp != k) {
-        if (lane < NR) { const double t = Bm[k + lane * K]; Bm[k + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
-        __syncwarp();
-      }
-      kp = -ipiv[k - 1] - 1;
-      if (kp != k - 1) {
-        if (lane < NR) { const double t = Bm[k - 1 + lane * K]; Bm[k - 1 + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
-        __syncwarp();
-      }
-      const int ckm1 = coff(k - 1);
-      if (k > 1) {
-#pragma unroll
-        for (int s = 0; s < (TWO ? 2 : 1); ++s) {
-          const int i = lane + 32 * s;
-          if (i < k - 1) {
-            const double xa = A[ck + i], xb = A[ckm1 + i];
-            if (xa != 0.0 || xb != 0.0) {
-#pragma unroll
-              for (int j = 0; j < NR; ++j) {
-                const double bv = IPDDP_FMA(xa, -Bm[k + j * K], Bm[i + j * K]);
-                Bm[i + j * K] = IPDDP_FMA(xb, -Bm[k - 1 + j * K], bv);
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
-      if (lane < NR) {
-        const double akm1k = A[ck + k - 1];
-        const double akm1 = A[ckm1 + k - 1] / akm1k;
-        const double ak = A[ck + k] / akm1k;
-        const double denom = akm1 * ak - 1.0;
-        const double bkm1 = Bm[k - 1 + lane * K] / akm1k;
-        const double bk = Bm[k + lane * K] / akm1k;
-        Bm[k - 1 + lane * K] = (ak * bkm1 - bk) / denom;
-        Bm[k + lane * K] = (akm1 * bk - bkm1) / denom;
-      }
-      __syncwarp();
-      k -= 2;
-    }
-  }
-  // forward: U' X = B;  lane = (rhs column j, partial g)
+IPDDP_D void warp_ldlt_solve_forward(const double* A, const int* ipiv, double* Bm, const unsigned char* scratch, int lane) {
+  const unsigned char* nzc = scratch + K;
+  const unsigned char* nzl = scratch + 2 * K;
   const int g = lane & 3;
-  constexpr int NPASS = (NR + 7) / 8;
-  k = 0;
+  static_assert(NR <= 8, "at most 8 right-hand sides");
+  const int j = lane >> 2;
+  const bool act = j < NR;
+  double* bj = Bm + (act ? j : 0) * K;
+  int k = 0;
   while (k < K) {
     const bool one = ipiv[k] > 0;
     if (k > 0) {
-      const double* xa = A + coff(k);
-      const double* xb = A + coff(k + (one ? 0 : 1));
-#pragma unroll
-      for (int ps = 0; ps < NPASS; ++ps) {
-        const int j = ps * 8 + (lane >> 2);
-        const bool act = j < NR;
-        const double* bj = Bm + (act ? j : 0) * K;
+      const int cnt = nzc[k];
+      if (cnt != 0) {
+        const double* xa = A + coff(k);
+        const double* xb = A + coff(k + (one ? 0 : 1));
         double sa = 0.0, sb = 0.0;
-        if (act) {
-          if (one) {
-            for (int i = g; i < k; i += 4) sa = IPDDP_FMA(xa[i], bj[i], sa);
-          } else {
-            for (int i = g; i < k; i += 4) { const double bv = bj[i]; sa = IPDDP_FMA(xa[i], bv, sa); sb = IPDDP_FMA(xb[i], bv, sb); }
+        if (cnt != 255) {
+          for (int r = 0; r < cnt; ++r) {
+            const int i = nzl[k * NZCAP + r];
+            if (act && (i & 3) == g) {
+              const double bv = bj[i];
+              sa = IPDDP_FMA(xa[i], bv, sa);
+              if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
+            }
           }
+        } else if (act) {
+          for (int i = g; i < k; i += 4) { const double bv = bj[i]; sa = IPDDP_FMA(xa[i], bv, sa); if (!one) sb = IPDDP_FMA(xb[i], bv, sb); }
         }
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
@@ -364,30 +365,21 @@ IPDDP_D void warp_sytrs_rook(const double* A, const int* ipiv, double* Bm, int l
           sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
         }
         if (act && g == 0) {
-          Bm[k + j * K] = Bm[k + j * K] - sa;
-          if (!one) Bm[k + 1 + j * K] = Bm[k + 1 + j * K] - sb;
+          bj[k] = bj[k] - sa;
+          if (!one) bj[k + 1] = bj[k + 1] - sb;
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
     if (one) {
       const int kp = ipiv[k] - 1;
-      if (kp != k) {
-        if (lane < NR) { const double t = Bm[k + lane * K]; Bm[k + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
-        __syncwarp();
-      }
+      if (kp != k) { warp_swap_rows<NR>(Bm, K, k, kp, lane); __syncwarp(); }
       k += 1;
     } else {
       int kp = -ipiv[k] - 1;
-      if (kp != k) {
-        if (lane < NR) { const double t = Bm[k + lane * K]; Bm[k + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
-        __syncwarp();
-      }
+      if (kp != k) { warp_swap_rows<NR>(Bm, K, k, kp, lane); __syncwarp(); }
       kp = -ipiv[k + 1] - 1;
-      if (kp != k + 1) {
-        if (lane < NR) { const double t = Bm[k + 1 + lane * K]; Bm[k + 1 + lane * K] = Bm[kp + lane * K]; Bm[kp + lane * K] = t; }
-        __syncwarp();
-      }
+      if (kp != k + 1) { warp_swap_rows<NR>(Bm, K, k + 1, kp, lane); __syncwarp(); }
       k += 2;
     }
   }
