@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference's exported Julia API (reference src/InteriorPointDDP.jl:29-45):
+
+    Dynamics, Objective, Constraint, Bound, Options, Solver, solve (= solve!), get_trajectory
+
+Same names, argument meaning and result fields as the reference, extended additively for batching
+(per-instance x1, controls, parameter vector p, horizon).  Where the reference traces user closures with
+Symbolics.jl and `eval`s generated Julia (src/dynamics.jl:15-47, src/objectives.jl:12-33,
+src/constraints.jl:16-50), this traces them with SymPy, emits CUDA device functions (codegen/generate.py),
+compiles them with nvcc into a model plugin and registers it through `ipddp_model_load`.  The solve itself
+always runs on the GPU through the C ABI (no CPU fallback).
+
+Example (reference experiments/ipddp2/double_integrator.jl:27-63):
+
+    f = lambda x, u: [x[0] + dt * x[1], x[1] + dt * u[0]]
+    dynamics = [Dynamics(f, 2, 3) for k in range(N - 1)]
+    objective = [Objective(lambda x, u: dt * (u[1] + u[2]), 2, 3)] * (N - 1) + [Objective(term, 2, 0)]
+    constraints = [Constraint(lambda x, u: [u[1] - u[2] - u[0] * x[1]], 2, 3)] * (N - 1) + [Constraint(2, 0)]
+    bounds = [Bound([-10, 0, 0], [10, inf, inf])] * (N - 1) + [Bound(float, 0)]
+    solver = Solver(float, dynamics, objective, constraints, bounds, options=Options(optimality_tolerance=1e-7))
+    solve(solver, x1, ubar)
+    x_sol, u_sol = get_trajectory(solver)
+    solver.data.k, solver.data.status, solver.data.objective
+"""
+from __future__ import annotations
+
+import hashlib
+import inspect
+import os
+import subprocess
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .batch import BatchSolver
+from .codegen import generate, workloads
+
+INF = float("inf")
+HERE = os.path.dirname(os.path.abspath(__file__))
+PLUGIN_DIR = os.path.join(HERE, "_plugins")
+
+
+def _arity(fn) -> int:
+    return len([p for p in inspect.signature(fn).parameters.values()
+                if p.default is inspect.Parameter.empty and p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)])
+
+
+def _with_p(fn, nargs_without_p):
+    """Accept closures written without the runtime parameter vector (the reference's signature)."""
+    if fn is None:
+        return None
+    return fn if _arity(fn) > nargs_without_p else (lambda *a: fn(*a[:nargs_without_p]))
+
+
+# ------------------------------------------------------------------------------------------------
+# constructors (reference src/dynamics.jl:15, src/objectives.jl:12, src/constraints.jl:16,52, src/bounds.jl:12-26)
+# ------------------------------------------------------------------------------------------------
+class Dynamics:
+    """Dynamics(f, num_state, num_control; quasi_newton=false): x+ = f(x, u[, p])."""
+
+    def __init__(self, f: Callable, num_state: int, num_control: int, quasi_newton: bool = False):
+        self.f = _with_p(f, 2)
+        self.num_state, self.num_control, self.quasi_newton = int(num_state), int(num_control), bool(quasi_newton)
+        self._src = f
+
+
+class Objective:
+    """Objective(f, num_state, num_control): stage cost l(x, u[, p]); num_control = 0 for the terminal stage."""
+
+    def __init__(self, f: Callable, num_state: int, num_control: int):
+        self.f = _with_p(f, 2)
+        self.num_state, self.num_control = int(num_state), int(num_control)
+        self._src = f
+
+
+class Constraint:
+    """Constraint(c, num_state, num_control; quasi_newton=false, indices_compl=nothing) or the empty
+    Constraint(num_state, num_control)."""
+
+    def __init__(self, *args, quasi_newton: bool = False, indices_compl: Optional[Sequence[int]] = None):
+        if callable(args[0]):
+            c, nx, nu = args
+            self.c = _with_p(c, 2)
+            self._src = c
+        else:
+            nx, nu = args
+            self.c = None
+            self._src = None
+        self.num_state, self.num_control = int(nx), int(nu)
+        self.quasi_newton = bool(quasi_newton)
+        # reference indices are 1-based (Julia); here 0-based
+        self.indices_compl = list(indices_compl) if indices_compl is not None else []
+
+
+class Bound:
+    """Bound(lower, upper) | Bound(T, num_control) (unbounded) | Bound(num_control, lower, upper)."""
+
+    def __init__(self, *args):
+        if len(args) == 2 and isinstance(args[0], type):
+            n = int(args[1])
+            self.lower, self.upper = np.full(n, -INF), np.full(n, INF)
+        elif len(args) == 3:
+            n, lo, up = args
+            self.lower, self.upper = np.full(int(n), float(lo)), np.full(int(n), float(up))
+        else:
+            lo, up = args
+            self.lower = np.asarray(lo, dtype=np.float64).reshape(-1)
+            self.upper = np.asarray(up, dtype=np.float64).reshape(-1)
+        assert self.lower.shape == self.upper.shape
+        self.indices_lower = [i for i, v in enumerate(self.lower) if not np.isinf(v)]
+        self.indices_upper = [i for i, v in enumerate(self.upper) if not np.isinf(v)]
+        self.num_lower, self.num_upper = len(self.indices_lower), len(self.indices_upper)
+
+
+def Options(**kw) -> _lib.Options:
+    """Options{T}(; kwargs...) (reference src/options.jl:1-38).  Greek field names map to ASCII:
+    mu_init, kappa_1, kappa_2, kappa_bar_w_p, kappa_w_p, kappa_w_m, kappa_c, delta_c, kappa_eps, kappa_mu,
+    theta_mu, tau_min, eta_L, s_L, delta, s_theta, gamma_alpha, gamma_theta, gamma_L, kappa_Sigma."""
+    return _lib.load().default_options(**kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# model plugin cache: closures -> CUDA -> nvcc -> .so -> ipddp_model_load
+# ------------------------------------------------------------------------------------------------
+def _closure_fingerprint(fns) -> str:
+    h = hashlib.sha256()
+    for f in fns:
+        if f is None:
+            h.update(b"none")
+            continue
+        try:
+            h.update(inspect.getsource(f).encode())
+        except (OSError, TypeError):
+            h.update(repr(f).encode())
+        for cell in (getattr(f, "__closure__", None) or ()):
+            try:
+                h.update(repr(cell.cell_contents).encode())
+            except Exception:
+                pass
+    return h.hexdigest()[:12]
+
+
+def build_model_plugin(md: workloads.ModelDef, force: bool = False) -> str:
+    """Generates csrc for `md` and compiles it for sm_100a into a plugin exporting `ipddp_plugin_vtable`."""
+    os.makedirs(PLUGIN_DIR, exist_ok=True)
+    bundles = generate.trace(md)
+    src = generate.emit_device(md, bundles).replace('#include "../model_common.cuh"',
+                                                    f'#include "{os.path.join(HERE, "csrc", "model_common.cuh")}"')
+    tag = hashlib.sha256(src.encode()).hexdigest()[:12]
+    so = os.path.join(PLUGIN_DIR, f"{md.name}_{tag}.so")
+    if os.path.exists(so) and not force:
+        return so
+    cuh = os.path.join(PLUGIN_DIR, f"{md.name}_{tag}.cuh")
+    cu = os.path.join(PLUGIN_DIR, f"{md.name}_{tag}.cu")
+    with open(cuh, "w") as fh:
+        fh.write(src)
+    with open(cu, "w") as fh:
+        fh.write(f'#include "{cuh}"\n#include "{os.path.join(HERE, "csrc", "model_register.cuh")}"\n'
+                 f'IPDDP_REGISTER_MODEL(Model_{md.name}, ipddp_plugin_vtable)\n')
+    from . import build as _b
+    cmd = [_b.NVCC] + _b.FLAGS + ["-shared", cu, "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for model plugin:\n" + r.stdout + r.stderr)
+    return so
+
+
+@dataclass
+class SolverData:
+    """Mirror of reference SolverData (src/data/solver.jl:8-33) after a solve; arrays of length B
+    (scalars when the solver was built for a single instance)."""
+    status: object = 0
+    k: object = 0
+    j: object = 0
+    l: object = 0
+    objective: object = 0.0
+    primal_inf: object = 0.0
+    dual_inf: object = 0.0
+    cs_inf: object = 0.0
+    mu: object = 0.0
+    reg_last: object = 0.0
+    step_size: object = 0.0
+    wall_time: float = 0.0       # seconds (device time of the whole batch solve)
+    solver_time: float = 0.0     # wall_time minus derivative-evaluation time
+    fn_eval_time: float = 0.0
+
+
+class Solver:
+    """Solver(T, dynamics, objectives, constraints, bounds=nothing; options=nothing)  (reference src/solver.jl:11-26)
+
+    Batched extension: `batch` instances share the model; `num_parameter` runtime parameters per instance are
+    the trailing argument `p` of the closures.  This round supports horizons whose running stages 1..N-1 share one
+    Dynamics / Objective / Constraint / Bound object (as every reference experiment does) plus a terminal stage with
+    num_control = 0 and no constraints; per-instance horizons <= N are allowed."""
+
+    def __init__(self, T, dynamics: List[Dynamics], objectives: List[Objective], constraints: List[Constraint],
+                 bounds: Optional[List[Bound]] = None, options: Optional[_lib.Options] = None, batch: int = 1,
+                 num_parameter: int = 0, device: int = 0, name: Optional[str] = None, trace_capacity: int = 0):
+        assert T in (float, np.float64), "FP64 only (the reference experiments are all Float64)"
+        N = len(objectives)
+        assert len(dynamics) + 1 == N == len(constraints), "need N-1 dynamics, N objectives, N constraints"
+        d0, o0, c0 = dynamics[0], objectives[0], constraints[0]
+        if any(d._src is not d0._src for d in dynamics) or any(o._src is not o0._src for o in objectives[:-1]) \
+                or any(c._src is not c0._src for c in constraints[:-1]):
+            raise NotImplementedError("running stages must share one Dynamics/Objective/Constraint (see class docstring)")
+        oN, cN = objectives[-1], constraints[-1]
+        assert oN.num_control == 0 and cN.c is None, "terminal stage must have num_control = 0 and no constraints"
+        nx, nu = d0.num_state, d0.num_control
+        if bounds is None:
+            bounds = [Bound(float, nu)] * (N - 1) + [Bound(float, 0)]
+        b0 = bounds[0]
+        if any(not (np.array_equal(b.lower, b0.lower) and np.array_equal(b.upper, b0.upper)) for b in bounds[:-1]):
+            raise NotImplementedError("running stages must share one Bound (per-instance bounds go through solve(..., lower=, upper=))")
+        self.N, self.nx, self.nu, self.batch, self.num_parameter = N, nx, nu, int(batch), int(num_parameter)
+        self.bound = b0
+        self.quasi_newton = d0.quasi_newton or c0.quasi_newton
+        stage_f = o0.f
+        term_f = _with_p(oN._src, 2)
+        cfun = c0.c if c0.c is not None else (lambda x, u, p: [])
+        tag = name or ("user_" + _closure_fingerprint([d0._src, o0._src, oN._src, c0._src]))
+        md = workloads.ModelDef(
+            name=tag, nx=nx, nu=nu, np_=self.num_parameter, f=d0.f, stage_cost=stage_f,
+            term_cost=lambda x, p: term_f(x, [], p), c=cfun, lower=lambda p: list(b0.lower), upper=lambda p: list(b0.upper),
+            u_init=[0.0] * nu, dt=0.0, indices_compl=list(c0.indices_compl))
+        self.model_def = md
+        self.lib = _lib.load()
+        if tag not in self.lib.models():
+            so = build_model_plugin(md)
+            self.lib.check(self.lib.L.ipddp_model_load(so.encode()), "ipddp_model_load")
+        self.options = options if options is not None else self.lib.default_options()
+        if self.quasi_newton:
+            self.options.quasi_newton = 1
+        self._bs = BatchSolver(tag, self.batch, N, options=self.options, device=device, trace_capacity=trace_capacity,
+                               indices_compl=c0.indices_compl, lib=self.lib)
+        self.nc = self._bs.nc
+        self.data = SolverData()
+
+    @classmethod
+    def from_workload(cls, workload: str, batch: int, N: int = 101, options=None, device: int = 0, trace_capacity: int = 0):
+        """One of the reference's six benchmark classes (built into the library)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        md = workloads.get(workload)
+        self.model_def = md
+        self.N, self.nx, self.nu, self.batch, self.num_parameter = N, md.nx, md.nu, int(batch), md.np_
+        self.options = options if options is not None else self.lib.default_options()
+        self._bs = BatchSolver(workload, self.batch, N, options=self.options, device=device, trace_capacity=trace_capacity,
+                               lib=self.lib)
+        self.nc = self._bs.nc
+        self.bound = None
+        self.quasi_newton = False
+        self.data = SolverData()
+        return self
+
+    # --------------------------------------------------------------------------------------------
+    def _fill_data(self, r):
+        st = self._bs.stats()
+        one = self.batch == 1
+        g = (lambda a: a[0].item()) if one else (lambda a: a)
+        self.data = SolverData(status=g(r.status), k=g(r.k), j=g(r.j), l=g(r.l), objective=g(r.objective),
+                               primal_inf=g(r.primal_inf), dual_inf=g(r.dual_inf), cs_inf=g(r.cs_inf), mu=g(r.mu),
+                               reg_last=g(r.reg_last), step_size=g(r.step_size), wall_time=st.ms_total * 1e-3,
+                               solver_time=(st.ms_total - st.ms_derivs) * 1e-3, fn_eval_time=st.ms_derivs * 1e-3)
+        return self.data
+
+
+def solve(solver: Solver, x1=None, controls=None, params=None, lower=None, upper=None, horizons=None):
+    """solve!(solver, x1, controls) (reference src/solve.jl:1-4); without x1/controls: solve!(solver)
+    (warm start from the stored nominal trajectory, src/solve.jl:6-17).
+
+    x1: [nx] or [B, nx]; controls: list of N per-stage vectors (last one empty), or [N-1, nu], or [B, N-1, nu];
+    params: [np] or [B, np]; lower/upper: per-instance bounds [B, nu] (default: the Solver's Bound)."""
+    B, N, nx, nu = solver.batch, solver.N, solver.nx, solver.nu
+    if x1 is None and controls is None:
+        r = solver._bs.solve(warm_start=True)
+        return solver._fill_data(r)
+    x1 = np.asarray(x1, dtype=np.float64)
+    x1 = np.broadcast_to(x1.reshape(-1, nx), (B, nx))
+    if isinstance(controls, (list, tuple)) and len(controls) == N and np.size(controls[-1]) == 0:
+        controls = np.stack([np.asarray(c, dtype=np.float64) for c in controls[:-1]])
+    controls = np.asarray(controls, dtype=np.float64)
+    controls = np.broadcast_to(controls.reshape(-1, (N - 1) * nu), (B, (N - 1) * nu))
+    p = None
+    if solver.num_parameter > 0:
+        p = np.broadcast_to(np.asarray(params, dtype=np.float64).reshape(-1, solver.num_parameter), (B, solver.num_parameter))
+    if lower is None and solver.bound is not None:
+        lower = solver.bound.lower
+    if upper is None and solver.bound is not None:
+        upper = solver.bound.upper
+    solver._bs.set_inputs(x1, controls, p, lower, upper, horizons)
+    r = solver._bs.solve()
+    return solver._fill_data(r)
+
+
+def get_trajectory(solver: Solver):
+    """get_trajectory(solver) -> (nominal_states, nominal_controls) (reference src/solver.jl:46-48).
+    Single instance: lists of per-stage vectors like the reference; batched: arrays [B,N,nx], [B,N-1,nu]."""
+    x, u = solver._bs.trajectory()
+    if solver.batch == 1:
+        return [x[0, t] for t in range(solver.N)], [u[0, t] for t in range(solver.N - 1)] + [np.zeros(0)]
+    return x, u

@@ -164,14 +164,15 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
     if (lane == 0) ipiv[k] = kp + 1;
     if (akk > tol) np += 1;
     int nnz = 0;
-    double x0 = 0.0, x1 = 0.0, d11 = 0.0;
+    double x0 = 0.0, x1 = 0.0;
     const bool big = fabs(akk) >= sfmin;
+    const double rinv = 1.0 / akk;            // used by the column scaling (big) and by dsytrs' B(k,:) scaling
+    const double d11 = big ? rinv : akk;
     if (k > 0) {
       double* x = A + ck;
       x0 = (i0 < k) ? x[i0] : 0.0;
       x1 = (TWO && i1 < k) ? x[i1] : 0.0;
       nnz = warp_compact<TWO>(x0 != 0.0, x1 != 0.0, list, lane);
-      d11 = big ? 1.0 / akk : akk;
       if (nnz > 0) {
         __syncwarp();
         if (!big) {   // tiny pivot: LAPACK divides the column first, then updates with -akk
@@ -205,7 +206,7 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
       for (int j = 0; j < NR; ++j) Bm[i1 + j * K] = IPDDP_FMA(x1, -Bm[k + j * K], Bm[i1 + j * K]);
     }
     __syncwarp();
-    if (lane < NR) Bm[k + lane * K] = Bm[k + lane * K] * (k > 0 && big ? d11 : 1.0 / akk);
+    if (lane < NR) Bm[k + lane * K] = Bm[k + lane * K] * rinv;
     __syncwarp();
   } else {
     double* xk = A + ck;
