@@ -113,7 +113,7 @@ def run_reference(args, rank, world):
     import ipddp_b200  # noqa: F401
     from ipddp_b200 import instances
     cores = os.cpu_count() or 1
-    sample = max(cores, min(args.batch, args.cpu_sample if args.cpu_sample > 0 else cores * 8))
+    sample = max(cores, min(args.batch, args.cpu_sample if args.cpu_sample > 0 else cores * 48))
     b = instances.make_batch(args.workload, sample, args.knots)
     opt = oracle.default_options(optimality_tolerance=args.tol)
     conv = 0
@@ -154,8 +154,9 @@ def main():
     ap.add_argument("--workload", default="cartpole")
     ap.add_argument("--knots", type=int, default=101)
     ap.add_argument("--tol", type=float, default=1e-7)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="instances per step of the CPU baseline (0 = 8 x cores)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU baseline sample (0 = 128 x cores for cpu_baseline, 48 x cores per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=4, help="independent batches in flight during the timed steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -171,7 +172,7 @@ def main():
     import torch.distributed as dist
     import ipddp_b200  # noqa: F401
     from ipddp_b200 import _lib, instances
-    from ipddp_b200.batch import BatchSolver
+    from ipddp_b200.batch import BatchSolver, solve_many
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -186,12 +187,13 @@ def main():
     # every rank takes its own contiguous range of the workload's canonical instance stream
     batch = instances.make_batch(args.workload, B, N, first=rank * B)
     opt = lib.default_options(optimality_tolerance=args.tol)
-    solver = BatchSolver(args.workload, B, N, options=opt, device=local_rank, lib=lib)
+    F = max(1, min(args.inflight, args.steps))
+    solvers = [BatchSolver(args.workload, B, N, options=opt, device=local_rank, lib=lib) for _ in range(F)]
+    solver = solvers[0]
 
     # pinned host copies (e2e path) and device-resident copies (value path)
     def pin(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h = {k: pin(v) for k, v in dict(x1=batch.x1, ubar=batch.ubar, p=batch.p if npar > 0 else np.zeros((B, 1)),
                                      lower=batch.lower, upper=batch.upper).items()}
     h_hz = torch.from_numpy(batch.horizons.astype(np.int32)).pin_memory()
@@ -199,63 +201,75 @@ def main():
     d_hz = h_hz.to(dev)
     torch.cuda.synchronize()
 
-    def set_device_inputs():
-        solver.set_inputs_device(d["x1"].data_ptr(), d["ubar"].data_ptr(), d["p"].data_ptr() if npar > 0 else None,
-                                 d["lower"].data_ptr(), d["upper"].data_ptr(), d_hz.data_ptr())
+    def set_device_inputs(sv):
+        sv.set_inputs_device(d["x1"].data_ptr(), d["ubar"].data_ptr(), d["p"].data_ptr() if npar > 0 else None,
+                             d["lower"].data_ptr(), d["upper"].data_ptr(), d_hz.data_ptr())
+
+    def set_host_inputs(sv):
+        sv.lib.check(sv.lib.L.ipddp_set_inputs(
+            sv.h, _lib.dptr(h["x1"].numpy()), _lib.dptr(h["ubar"].numpy()),
+            _lib.dptr(h["p"].numpy()) if npar > 0 else None, _lib.dptr(h["lower"].numpy()), _lib.dptr(h["upper"].numpy()),
+            _lib.iptr(h_hz.numpy())), "ipddp_set_inputs")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    set_device_inputs()
+    for sv in solvers:
+        set_device_inputs(sv)
     for _ in range(args.warmup):
         solver.solve()
 
-    # ------------------------------------------------------------------ timed: device-resident
+    # ---------------------------------------------------- timed region A: K steps one after another (kernels timed alone)
     agg = dict(ms_total=0.0, ms_derivs=0.0, ms_backward=0.0, ms_check=0.0, ms_forward=0.0, ms_init=0.0, kkt=0, sweeps=0,
                rollouts=0, deriv=0, conv=0, launches=0, rounds=0, active_rounds=0, backward_calls=0)
     barrier()
-    with ClockSampler(local_rank) as clk:
-        t_wall0 = time.perf_counter()
-        for _ in range(args.steps):
-            set_device_inputs()
-            solver.solve()
-            st = solver.stats()
-            agg["ms_total"] += st.ms_total; agg["ms_derivs"] += st.ms_derivs; agg["ms_backward"] += st.ms_backward
-            agg["ms_check"] += st.ms_check; agg["ms_forward"] += st.ms_forward; agg["ms_init"] += st.ms_init
-            agg["kkt"] += st.sum_kkt; agg["sweeps"] += st.sum_sweeps; agg["rollouts"] += st.sum_rollouts
-            agg["deriv"] += st.sum_deriv_stages; agg["conv"] += st.n_converged; agg["launches"] += st.launches
-            agg["rounds"] += st.iterations; agg["active_rounds"] += st.n_active_rounds; agg["backward_calls"] += st.sum_backward
-        barrier()
-        wall_dev = time.perf_counter() - t_wall0
-    clocks = clk.summary()
+    for _ in range(args.steps):
+        set_device_inputs(solver)
+        solver.solve()
+        st = solver.stats()
+        agg["ms_total"] += st.ms_total; agg["ms_derivs"] += st.ms_derivs; agg["ms_backward"] += st.ms_backward
+        agg["ms_check"] += st.ms_check; agg["ms_forward"] += st.ms_forward; agg["ms_init"] += st.ms_init
+        agg["kkt"] += st.sum_kkt; agg["sweeps"] += st.sum_sweeps; agg["rollouts"] += st.sum_rollouts
+        agg["deriv"] += st.sum_deriv_stages; agg["conv"] += st.n_converged; agg["launches"] += st.launches
+        agg["rounds"] += st.iterations; agg["active_rounds"] += st.n_active_rounds; agg["backward_calls"] += st.sum_backward
+    barrier()
     res = solver.results()
 
-    # ------------------------------------------------------------------ timed: end to end through host buffers
-    hx = np.zeros((B, N, nx)); hu = np.zeros((B, N - 1, nu))
-    hx_t = torch.from_numpy(hx).pin_memory(); hu_t = torch.from_numpy(hu).pin_memory()
-    hxn, hun = hx_t.numpy(), hu_t.numpy()
-    import ctypes as C
+    # ---------------------------------------------------- timed region B: the same K steps, up to F batches in flight
+    # (independent problem handles on their own streams, ipddp_solve_many): whole-job throughput, inputs resident in HBM
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        ms_pipe, st_pipe = solve_many(solvers, total_solves=args.steps)
+        barrier()
+    clocks = clk.summary()
+
+    # ---------------------------------------------------- timed region C: end to end through host buffers, F in flight
+    hxs = [torch.from_numpy(np.zeros((B, N, nx))).pin_memory() for _ in range(F)]
+    hus = [torch.from_numpy(np.zeros((B, N - 1, nu))).pin_memory() for _ in range(F)]
     barrier()
     t0 = time.perf_counter()
     conv_e2e = 0
-    for _ in range(args.steps):
-        solver.lib.check(solver.lib.L.ipddp_set_inputs(
-            solver.h, _lib.dptr(h["x1"].numpy()), _lib.dptr(h["ubar"].numpy()),
-            _lib.dptr(h["p"].numpy()) if npar > 0 else None, _lib.dptr(h["lower"].numpy()), _lib.dptr(h["upper"].numpy()),
-            _lib.iptr(h_hz.numpy())), "ipddp_set_inputs")
-        r = solver.solve()
-        solver.lib.check(solver.lib.L.ipddp_get_trajectory(solver.h, _lib.dptr(hxn), _lib.dptr(hun)), "get_trajectory")
-        conv_e2e += int((r.status == 0).sum())
+    done = 0
+    while done < args.steps:
+        nb = min(F, args.steps - done)
+        for sv in solvers[:nb]:
+            set_host_inputs(sv)
+        solve_many(solvers[:nb], total_solves=nb)
+        for q, sv in enumerate(solvers[:nb]):
+            r = sv.results()
+            sv.lib.check(sv.lib.L.ipddp_get_trajectory(sv.h, _lib.dptr(hxs[q].numpy()), _lib.dptr(hus[q].numpy())), "get_trajectory")
+            conv_e2e += int((r.status == 0).sum())
+        done += nb
     barrier()
     wall_e2e = time.perf_counter() - t0
-    h2d = sum(int(t.numel() * t.element_size()) for t in h.values() if not (npar == 0 and t is h["p"])) + int(h_hz.numel() * 4)
-    d2h = B * (4 * 4 + 7 * 8) + hx.nbytes + hu.nbytes
+    h2d = sum(int(t.numel() * t.element_size()) for k_, t in h.items() if not (npar == 0 and k_ == "p")) + int(h_hz.numel() * 4)
+    d2h = B * (4 * 4 + 7 * 8) + int(hxs[0].numel() * 8) + int(hus[0].numel() * 8)
 
     # ------------------------------------------------------------------ reduce over ranks
-    vals = torch.tensor([agg["ms_total"], wall_e2e, wall_dev], dtype=torch.float64, device=dev)
-    sums = torch.tensor([agg["conv"], conv_e2e, agg["kkt"], agg["sweeps"], agg["rollouts"], agg["launches"],
+    vals = torch.tensor([agg["ms_total"], wall_e2e, ms_pipe], dtype=torch.float64, device=dev)
+    sums = torch.tensor([agg["conv"], conv_e2e, st_pipe.sum_kkt, float(st_pipe.n_converged), agg["rollouts"], st_pipe.launches,
                          int((res.status == 0).sum()), float(res.k.sum()), float(res.primal_inf[res.status == 0].max(initial=0.0))],
                         dtype=torch.float64, device=dev)
     if world > 1:
@@ -264,11 +278,12 @@ def main():
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)      # the single NCCL reduction of convergence statistics
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sums[-1] = mx[0]
-    ms_total, wall_e2e_max, _ = [float(x) for x in vals.tolist()]
-    conv_all, conv_e2e_all, kkt_all, sweeps_all, roll_all, launches_all, conv_last, ksum, pr_max = [float(x) for x in sums.tolist()]
+    ms_total, wall_e2e_max, ms_pipe_max = [float(x) for x in vals.tolist()]
+    conv_all, conv_e2e_all, kkt_pipe_all, conv_pipe_all, roll_all, launches_all, conv_last, ksum, pr_max = [float(x) for x in sums.tolist()]
 
     if rank == 0:
-        value = conv_all / (ms_total * 1e-3)
+        value = conv_pipe_all / (ms_pipe_max * 1e-3)
+        value_sequential = conv_all / (ms_total * 1e-3)
         e2e_val = conv_e2e_all / wall_e2e_max
         # roofline of the dominant kernel (backward sweep) on rank 0
         peaks = {}
@@ -285,8 +300,18 @@ def main():
         gb_dense = kkt_bytes_dense(nx, nu, nc) * kkt_rank / tb / 1e9
         gb_compact = kkt_bytes_compact(nx, nu, nc, slots) * kkt_rank / tb / 1e9
         tf = F * kkt_rank / tb / 1e12
+        # dram__bytes_read+write of one k_backward launch from the committed ncu --set full capture
+        # (profiles/r1_backward_summary.md): bytes per KKT step x the KKT steps of an average launch here
+        ncu_bytes_per_kkt = None
+        try:
+            ncu_bytes_per_kkt = float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload]["dram_bytes_per_kkt_step"])
+        except Exception:
+            pass
+        launches_bw = max(1, agg["rounds"])
+        traffic = ncu_bytes_per_kkt * kkt_rank / launches_bw if ncu_bytes_per_kkt else None
         roof_hbm = {"bound": "hbm", "kernel": "k_backward", "achieved": gb_dense, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": gb_dense / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "frac": gb_dense / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_launch": kkt_bytes_dense(nx, nu, nc) * kkt_rank / launches_bw,
                     "note": "achieved = SURVEY 8(d) dense-tile bytes per timestep-KKT x KKT steps / backward-kernel time; "
                             f"this layout moves {kkt_bytes_compact(nx, nu, nc, slots)} B per KKT step (compact tile), i.e. "
                             f"{gb_compact:.1f} GB/s actual"}
@@ -312,7 +337,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             cores = os.cpu_count() or 1
-            sample = max(cores, min(B, args.cpu_sample if args.cpu_sample > 0 else cores * 8))
+            sample = max(cores, min(B, args.cpu_sample if args.cpu_sample > 0 else cores * 128))
             sb = instances.make_batch(args.workload, sample, N)
             t0 = time.perf_counter()
             ores, _, _ = oracle.solve_batch(args.workload, N, sb.p, sb.lower, sb.upper, sb.x1, sb.ubar,
@@ -325,13 +350,18 @@ def main():
                    "kkt_steps_per_s": sum(r.n_kkt for r in ores) / dt}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_pipe_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload} swing-up batch of {B} random initial states per GPU, N={N} knots, tol {args.tol:g}",
                        "batch_per_gpu": B, "knots": N, "l2": "working set (trajectories+gains > 8 GB) far exceeds the 126 MB L2",
-                       "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
+                       "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
+                       "steps_in_flight": F,
+                       "timing": "value/e2e: the K steps run with up to steps_in_flight independent batches in flight on their own "
+                                 "streams (ipddp_solve_many), device time by CUDA events from first enqueue to last completion; "
+                                 "roofline/kernels/sequential: the same K steps one after another, per-kernel CUDA events"},
+            "sequential": {"value": value_sequential, "ms_per_step": ms_total / args.steps},
             "converged_fraction": conv_last / (B * world), "mean_iterations": ksum / (B * world), "max_primal_inf": pr_max,
-            "backward_kkt_steps_per_s": kkt_all / (ms_total * 1e-3),
+            "backward_kkt_steps_per_s": kkt_pipe_all / (ms_pipe_max * 1e-3),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
@@ -341,7 +371,8 @@ def main():
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
-    solver.close()
+    for sv in solvers:
+        sv.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -121,6 +121,14 @@ int ipddp_set_inputs_device(ipddp_problem* h, const double* x1, const double* ub
  * all instances terminated.  warm_start != 0 skips initialize_trajectory! (src/solve.jl:6 semantics). */
 int ipddp_solve(ipddp_problem* h, int warm_start);
 
+/* Throughput driver: n independent problems (same device) progress concurrently, each on its own stream; one host
+ * thread polls completion events and immediately enqueues the next round of whichever problem is ready, so the
+ * lock-step tail of one batch overlaps the bulk rounds of the others.  Handles that finish start another solve of
+ * their inputs until total_solves (>= n) solves are complete.  elapsed_ms: device time from the first enqueue to the
+ * last completion (CUDA events); agg: counters summed over all solves (per-kernel times are not split here). */
+int ipddp_solve_many(ipddp_problem** problems, int n, int total_solves, int warm_start, double* elapsed_ms,
+                     ipddp_stats* agg);
+
 /* Phase-level entry points (for kernel parity tests and profiling), all instances:
  *   initialize       initialize_trajectory! + the prologue of solve! (src/solve.jl:14-38)
  *   eval_derivatives evaluate_derivatives!(problem) (src/derivatives.jl:31-35)

@@ -165,3 +165,16 @@ class BatchSolver:
         st = Stats()
         self.lib.check(self.lib.L.ipddp_get_stats(self.h, C.byref(st)), "ipddp_get_stats")
         return st
+
+
+def solve_many(solvers, total_solves=None, warm_start=False):
+    """Concurrent solve of several BatchSolvers (one device, one stream each), see ipddp_solve_many.
+    Returns (elapsed_ms, Stats summed over all solves)."""
+    lib = solvers[0].lib
+    n = len(solvers)
+    arr = (C.c_void_p * n)(*[s.h for s in solvers])
+    ms = C.c_double()
+    st = Stats()
+    lib.check(lib.L.ipddp_solve_many(arr, n, int(total_solves or n), int(warm_start), C.byref(ms), C.byref(st)),
+              "ipddp_solve_many")
+    return ms.value, st

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels_common.cuh"
@@ -135,6 +136,7 @@ struct ipddp_problem {
   int* d_list_fwd = nullptr;
   int* d_counters = nullptr;
   int* h_counters = nullptr;
+  int* h_si = nullptr;            // pinned snapshot of the per-instance int scalars (ipddp_solve_many)
   int cur = 0, n_active = 0;
   bool inputs_set = false;
   cudaEvent_t ev[8];
@@ -271,6 +273,7 @@ int ipddp_problem_destroy(ipddp_problem* h) {
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->h_si) cudaFreeHost(h->h_si);
   if (h->stream) {
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
@@ -430,6 +433,116 @@ int ipddp_solve(ipddp_problem* h, int warm_start) {
     st.sum_deriv_stages += (long long)si[(size_t)SI_NDERIV * v.B + b];
     st.n_converged += (si[(size_t)SI_STATUS * v.B + b] == 0);
   }
+  return 0;
+}
+
+// Several independent problems progress concurrently, each on its own stream, driven by one host thread that
+// polls completion events and immediately enqueues the next round of whichever handle became ready.  Hides the
+// lock-step tail of one batch (a few straggler instances at <1% occupancy) behind the bulk rounds of the others.
+// total_solves >= n: handles that finish early start another solve of their inputs until total_solves are done.
+int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start, double* elapsed_ms,
+                     ipddp_stats* agg) {
+  if (n < 1 || total_solves < n) return fail("need n >= 1 handles and total_solves >= n");
+  for (int i = 0; i < n; ++i) {
+    if (!hs[i]->inputs_set) return fail("ipddp_set_inputs not called on every handle");
+    if (hs[i]->device != hs[0]->device) return fail("all handles must live on one device");
+    if (!hs[i]->h_si) CK(cudaMallocHost((void**)&hs[i]->h_si, (size_t)SI_COUNT * hs[i]->v.B * sizeof(int)));
+  }
+  CK(cudaSetDevice(hs[0]->device));
+  ipddp_stats tot;
+  memset(&tot, 0, sizeof(tot));
+  enum { IDLE = 0, INIT = 1, ROUND = 2, STATS = 3, FINISHED = 4 };
+  std::vector<int> state(n, IDLE);
+  int started = 0, finished = 0;
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(hs[0]->ev[6], hs[0]->stream));
+  auto enqueue_init = [&](ipddp_problem* h) -> int {
+    memset(&h->st, 0, sizeof(h->st));
+    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
+    h->cur = 0;
+    h->vt->init(h->v, warm_start, h->d_list[0], h->d_counters, h->stream);
+    h->st.launches += 1;
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    return 0;
+  };
+  auto enqueue_round = [&](ipddp_problem* h) -> int {
+    const int nn = h->n_active, cur = h->cur;
+    cudaStream_t s = h->stream;
+    h->st.iterations += 1;
+    h->st.n_active_rounds += nn;
+    h->vt->derivs(h->v, h->d_list[cur], nn, s);
+    h->vt->backward(h->v, h->d_list[cur], nn, s);
+    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
+    h->vt->check(h->v, h->d_list[cur], nn, h->d_list[1 - cur], h->d_list_fwd, h->d_counters, s);
+    h->vt->forward(h->v, h->d_list_fwd, nn, h->d_list[1 - cur], h->d_counters, s);
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(h->ev[5], s));
+    h->st.launches += 4;
+    return 0;
+  };
+  for (int i = 0; i < n; ++i) {
+    if (enqueue_init(hs[i]) != 0) return -1;
+    state[i] = INIT;
+    started++;
+  }
+  while (finished < total_solves) {
+    bool progressed = false;
+    for (int i = 0; i < n; ++i) {
+      ipddp_problem* h = hs[i];
+      if (state[i] == IDLE || state[i] == FINISHED) continue;
+      cudaError_t q = cudaEventQuery(h->ev[5]);
+      if (q == cudaErrorNotReady) continue;
+      if (q != cudaSuccess) return fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+      progressed = true;
+      if (state[i] == INIT || state[i] == ROUND) {
+        if (state[i] == ROUND) h->cur = 1 - h->cur;
+        h->n_active = h->h_counters[CNT_NEXT];
+        if (h->n_active > 0) {
+          if (enqueue_round(h) != 0) return -1;
+          state[i] = ROUND;
+        } else {
+          CK(cudaMemcpyAsync(h->h_si, h->v.si, (size_t)SI_COUNT * h->v.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+          CK(cudaEventRecord(h->ev[5], h->stream));
+          state[i] = STATS;
+        }
+      } else {  // STATS arrived: this solve is complete
+        const int B = h->v.B;
+        tot.iterations += h->st.iterations;
+        tot.launches += h->st.launches;
+        tot.n_active_rounds += h->st.n_active_rounds;
+        for (int b = 0; b < B; ++b) {
+          tot.sum_backward += h->h_si[(size_t)SI_NBACK * B + b];
+          tot.sum_sweeps += h->h_si[(size_t)SI_NSWEEP * B + b];
+          tot.sum_kkt += h->h_si[(size_t)SI_NKKT * B + b];
+          tot.sum_rollouts += h->h_si[(size_t)SI_NROLL * B + b];
+          tot.sum_deriv_stages += h->h_si[(size_t)SI_NDERIV * B + b];
+          tot.n_converged += (h->h_si[(size_t)SI_STATUS * B + b] == 0);
+        }
+        finished++;
+        if (started < total_solves) {
+          if (enqueue_init(h) != 0) return -1;
+          state[i] = INIT;
+          started++;
+        } else {
+          CK(cudaEventRecord(h->ev[7], h->stream));
+          state[i] = FINISHED;
+        }
+      }
+    }
+    if (!progressed) std::this_thread::yield();
+  }
+  float best = 0.f;
+  for (int i = 0; i < n; ++i) {
+    CK(cudaEventSynchronize(hs[i]->ev[7]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, hs[0]->ev[6], hs[i]->ev[7]));
+    if (ms > best) best = ms;
+  }
+  CK(cudaGetLastError());
+  tot.ms_total = best;
+  if (elapsed_ms) *elapsed_ms = best;
+  if (agg) *agg = tot;
   return 0;
 }
 

@@ -168,5 +168,8 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (void*)1; retur
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+enum { cudaErrorNotReady = 600 };
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 1; return 0; }

@@ -41,3 +41,31 @@ def test_emulated_ldlt(emu, oracle_mod):
 
 def test_emulated_detmath(emu, oracle_mod):
     helpers.detmath_parity(emu, oracle_mod, np.random.default_rng(4), n=5000)
+
+
+def test_emulated_solve_many(emu, oracle_mod):
+    """ipddp_solve_many (several problems in flight, event-polled) gives the same per-instance answers as
+    sequential solves, and its aggregated counters add up."""
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver, solve_many
+    opt = emu.default_options(optimality_tolerance=1e-7)
+    solvers, batches = [], []
+    for q, (B, N) in enumerate([(2, 21), (3, 11), (1, 31)]):
+        b = instances.make_batch("double_integrator" if q != 1 else "concar", B, N, first=10 * q)
+        s = BatchSolver(b.workload, B, N, options=opt, lib=emu)
+        s.set_batch(b)
+        solvers.append(s); batches.append(b)
+    ms, st = solve_many(solvers, total_solves=5)
+    got = [s.results() for s in solvers]
+    cnt = [s.counters() for s in solvers]
+    conv = 0
+    for s, r in zip(solvers, got):
+        r2 = s.solve()      # sequential re-solve of the same inputs
+        assert np.array_equal(r.k, r2.k) and np.array_equal(r.status, r2.status)
+        helpers.assert_same_bits(r.objective, r2.objective, "objective")
+    # 5 solves: handles 0,1,2 once, then the first two that finished once more
+    assert st.n_converged >= sum(int((r.status == 0).sum()) for r in got)
+    assert st.sum_kkt >= sum(int(c["n_kkt"].sum()) for c in cnt)
+    assert st.launches > 0 and st.iterations > 0
+    for s in solvers:
+        s.close()
