@@ -22,33 +22,36 @@ template <class M> struct BwLayout {
   static constexpr int NX = M::NX, NU = M::NU, NC = M::NC, K = NU + NC, NR = NX + 1;
   static constexpr int KP = K * (K + 1) / 2;
   static constexpr int pad(int n) { return n > 0 ? n : 1; }
+  static constexpr int mx(int a, int b) { return a > b ? a : b; }
   // offsets in doubles
   static constexpr int LHS = 0;
-  static constexpr int RHS = LHS + pad(KP);          // K x NR, becomes [alpha beta; psi omega]
-  static constexpr int RHS0 = RHS + pad(K * NR);     // un-negated copy: [Qu B; c cx]
-  static constexpr int FX = RHS0 + pad(K * NR);      // NX x NX (row index = next-state component)
+  static constexpr int RHS = LHS + pad(KP);          // K x NR: assembled as [Qu B; c cx], negated, solved -> [alpha beta; psi omega]
+  static constexpr int FX = RHS + pad(K * NR);       // NX x NX (row index = next-state component)
   static constexpr int FU = FX + NX * NX;            // NX x NU
   static constexpr int VXX = FU + pad(NX * NU);      // value Hessian of knot t+1
   static constexpr int VX = VXX + NX * NX;
   static constexpr int LAM = VX + NX;
   static constexpr int CM = LAM + NX;                // C (NX x NX)
-  static constexpr int XXT = CM + NX * NX;           // fx' Vxx+  (NX x NX)
-  static constexpr int UXT = XXT + NX * NX;          // fu' Vxx+  (NU x NX)
-  static constexpr int VEC = UXT + pad(NU * NX);     // il iu zl zu t1 t2 chil chiu  (8 x NU)
-  static constexpr int PHI = VEC + pad(8 * NU);
-  static constexpr int XS = PHI + pad(NC);
-  static constexpr int US = XS + NX;
-  static constexpr int LX = US + pad(NU);
-  static constexpr int TILE = LX + NX;
-  static constexpr int VFS = TILE + pad(M::D_NSLOT > M::DN_NSLOT ? M::D_NSLOT : M::DN_NSLOT);
-  static constexpr int WS = VFS + pad(M::VF_NSLOT);  // 4K scratch for the 2x2 update
-  static constexpr int CST = WS + pad(4 * K);
-  static constexpr int NEWV = CST + pad(M::NCONST);  // new Vxx (NX*NX), Vx (NX), lam (NX)
-  static constexpr int DBL_END = NEWV + NX * NX + 2 * NX;
+  static constexpr int VEC = CM + NX * NX;           // zl zu t1 t2 chil chiu  (6 x NU)
+  static constexpr int PHI = VEC + pad(6 * NU);
+  static constexpr int LX = PHI + pad(NC);
+  static constexpr int NEWV = LX + NX;               // new Vxx (NX*NX), Vx (NX), lam (NX)
+  // PRE: buffers that are dead once the factorisation starts; the 4K-double scratch of the 2x2 pivot update
+  // (WS) is aliased on top of them
+  static constexpr int PRE = NEWV + NX * NX + 2 * NX;
+  static constexpr int UXT = PRE;                    // fu' Vxx+  (NU x NX)
+  static constexpr int XXT = UXT + pad(NU * NX);     // fx' Vxx+  (NX x NX)
+  static constexpr int TILE = XXT + NX * NX;
+  static constexpr int DSC = TILE + pad(mx(M::D_NSLOT, M::DN_NSLOT));   // |dual residual| per control
+  static constexpr int VFS = DSC + pad(NU);
+  static constexpr int XS = VFS + pad(M::VF_NSLOT);  // x, u copies for the dynamics Hessian contraction
+  static constexpr int US = XS + (M::VF_NSLOT > 0 ? NX : 0);
+  static constexpr int PRE_END = US + (M::VF_NSLOT > 0 ? NU : 0);
+  static constexpr int WS = PRE;
+  static constexpr int DBL_END = mx(PRE_END, WS + 4 * K);
   // ints (4 bytes) after the doubles
   static constexpr int IPIV_B = DBL_END * 8;
-  static constexpr int TBL_B = IPIV_B + pad(K) * 4;
-  static constexpr int LIST_B = TBL_B + pad(M::NTBL) * 4;
+  static constexpr int LIST_B = IPIV_B + pad(K) * 4;
   static constexpr int BYTES = ((LIST_B + LdltScratch<(K > 0 ? K : 1)>::BYTES + 15) / 16) * 16;
 };
 
@@ -65,32 +68,33 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
   const int Nb = v.horizon[b];
   const int set = v.nomsel[b];
 
-  double* lhs = sm + L::LHS; double* rhs = sm + L::RHS; double* rhs0 = sm + L::RHS0;
+  double* lhs = sm + L::LHS; double* rhs = sm + L::RHS;
   double* fx = sm + L::FX; double* fu = sm + L::FU; double* Vxx = sm + L::VXX; double* Vx = sm + L::VX;
   double* lamn = sm + L::LAM; double* Cm = sm + L::CM; double* xxt = sm + L::XXT; double* uxt = sm + L::UXT;
-  double* il = sm + L::VEC; double* iu = il + NU; double* zl = iu + NU; double* zu = zl + NU;
+  double* zl = sm + L::VEC; double* zu = zl + NU;
   double* t1 = zu + NU; double* t2 = t1 + NU; double* chil = t2 + NU; double* chiu = chil + NU;
   double* phi = sm + L::PHI; double* xs = sm + L::XS; double* us = sm + L::US; double* lx = sm + L::LX;
-  double* tile = sm + L::TILE; double* vfs = sm + L::VFS; double* ws = sm + L::WS; double* cst = sm + L::CST;
+  double* tile = sm + L::TILE; double* vfs = sm + L::VFS; double* ws = sm + L::WS; double* dsc = sm + L::DSC;
   double* nVxx = sm + L::NEWV; double* nVx = nVxx + NX * NX; double* nlam = nVx + NX;
   unsigned char* smb = reinterpret_cast<unsigned char*>(sm);
   int* ipiv = reinterpret_cast<int*>(smb + L::IPIV_B);
-  MEntry* tbl = reinterpret_cast<MEntry*>(smb + L::TBL_B);
   unsigned char* nzlist = smb + L::LIST_B;
+  // scatter tables and constants stay in global memory (read-only path, shared by every warp of the grid)
+  const MEntry* tbl = M::tbl();
+  const double* cst = M::consts();
+  (void)xs; (void)us; (void)vfs;
 
-  // ---- one-time setup: scatter tables, constants, packed-index table, constant parts of fx / fu
-  for (int e = lane; e < M::NTBL; e += 32) tbl[e] = M::tbl()[e];
-  for (int e = lane; e < M::NCONST; e += 32) cst[e] = M::consts()[e];
+  // ---- one-time setup: constant parts of fx / fu
   for (int e = lane; e < NX * NX; e += 32) fx[e] = 0.0;
   for (int e = lane; e < NX * NU; e += 32) fu[e] = 0.0;
   __syncwarp();
   for (int e = lane; e < M::D_fx_N; e += 32) {
-    const MEntry q = tbl[M::D_fx_OFF + e];
-    if (q.slot < 0) fx[q.i + q.j * NX] = cst[-1 - q.slot];
+    const MEntry q = ld_entry(tbl + M::D_fx_OFF + e);
+    if (q.slot < 0) fx[q.i + q.j * NX] = IPDDP_LDG(cst - 1 - q.slot);
   }
   for (int e = lane; e < M::D_fu_N; e += 32) {
-    const MEntry q = tbl[M::D_fu_OFF + e];
-    if (q.slot < 0) fu[q.i + q.j * NX] = cst[-1 - q.slot];
+    const MEntry q = ld_entry(tbl + M::D_fu_OFF + e);
+    if (q.slot < 0) fu[q.i + q.j * NX] = IPDDP_LDG(cst - 1 - q.slot);
   }
   __syncwarp();
 
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
   int status = 0, nsweep = 0, nkkt = 0;
   double dual_num = 0.0;
 
-  auto val = [&](const MEntry& q) -> double { return q.slot >= 0 ? tile[q.slot] : cst[-1 - q.slot]; };
+  auto val = [&](const MEntry& q) -> double { return q.slot >= 0 ? tile[q.slot] : IPDDP_LDG(cst - 1 - q.slot); };
 
   while (reg <= v.opt.reg_max) {
     status = 0;
@@ -116,8 +120,8 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
       for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
       for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
       __syncwarp();
-      for (int e = lane; e < M::DN_lxx_N; e += 32) { const MEntry q = tbl[M::DN_lxx_OFF + e]; Cm[q.i + q.j * NX] = val(q); }
-      for (int e = lane; e < M::DN_lx_N; e += 32) { const MEntry q = tbl[M::DN_lx_OFF + e]; lx[q.i] = val(q); }
+      for (int e = lane; e < M::DN_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::DN_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
+      for (int e = lane; e < M::DN_lx_N; e += 32) { const MEntry q = ld_entry(tbl + M::DN_lx_OFF + e); lx[q.i] = val(q); }
       __syncwarp();
       // C = lxx (+ vcxx = 0 unless quasi_newton);  Vxx = (0 + 0) + C ;  Vx = lambda = 0 + lx
       // inertia_correction! on the empty KKT matrix resets delta_c (Q4: the value set by a failed knot
@@ -138,34 +142,35 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
       const double* r = v.rec(set, b, t);
       // ---- stage inputs
       for (int e = lane; e < M::D_NSLOT; e += 32) tile[e] = v.tile[((size_t)b * M::D_NSLOT + e) * v.N + t];
-      for (int e = lane; e < NU; e += 32) {
-        us[e] = r[R::U + e]; il[e] = r[R::IL + e]; iu[e] = r[R::IU + e]; zl[e] = r[R::ZL + e]; zu[e] = r[R::ZU + e];
+      for (int e = lane; e < NU; e += 32) { zl[e] = r[R::ZL + e]; zu[e] = r[R::ZU + e]; }
+      if constexpr (M::VF_NSLOT > 0) {
+        for (int e = lane; e < NU; e += 32) us[e] = r[R::U + e];
+        for (int e = lane; e < NX; e += 32) xs[e] = r[R::X + e];
       }
       for (int e = lane; e < NC; e += 32) phi[e] = r[R::PHI + e];
-      for (int e = lane; e < NX; e += 32) xs[e] = r[R::X + e];
       for (int e = lane; e < L::KP; e += 32) lhs[e] = 0.0;
-      for (int e = lane; e < K * NR; e += 32) rhs0[e] = 0.0;
+      for (int e = lane; e < K * NR; e += 32) rhs[e] = 0.0;
       for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
       for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
       __syncwarp();
-      // ---- scatter pass 1: fx, fu (non-constant part), cu -> lhs top-right, cx -> rhs0, lu -> rhs0 col 0,
-      //      lux -> rhs0 B block, lxx -> C, lx, c -> rhs0
-      for (int e = lane; e < M::D_fx_N; e += 32) { const MEntry q = tbl[M::D_fx_OFF + e]; if (q.slot >= 0) fx[q.i + q.j * NX] = tile[q.slot]; }
-      for (int e = lane; e < M::D_fu_N; e += 32) { const MEntry q = tbl[M::D_fu_OFF + e]; if (q.slot >= 0) fu[q.i + q.j * NX] = tile[q.slot]; }
-      for (int e = lane; e < M::D_cu_N; e += 32) { const MEntry q = tbl[M::D_cu_OFF + e]; lhs[pk(q.j, NU + q.i)] = val(q); }
-      for (int e = lane; e < M::D_cx_N; e += 32) { const MEntry q = tbl[M::D_cx_OFF + e]; rhs0[NU + q.i + (1 + q.j) * K] = val(q); }
-      for (int e = lane; e < M::D_lu_N; e += 32) { const MEntry q = tbl[M::D_lu_OFF + e]; rhs0[q.i] = val(q); }
-      for (int e = lane; e < M::D_lux_N; e += 32) { const MEntry q = tbl[M::D_lux_OFF + e]; rhs0[q.i + (1 + q.j) * K] = val(q); }
-      for (int e = lane; e < M::D_lxx_N; e += 32) { const MEntry q = tbl[M::D_lxx_OFF + e]; Cm[q.i + q.j * NX] = val(q); }
-      for (int e = lane; e < M::D_lx_N; e += 32) { const MEntry q = tbl[M::D_lx_OFF + e]; lx[q.i] = val(q); }
-      for (int e = lane; e < NC; e += 32) rhs0[NU + e] = r[R::C + e];
+      // ---- scatter pass 1: fx, fu (non-constant part), cu -> lhs top-right, cx -> rhs, lu -> rhs col 0,
+      //      lux -> rhs B block, lxx -> C, lx, c -> rhs   (rhs holds the un-negated [Qu B; c cx] until the solve)
+      for (int e = lane; e < M::D_fx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fx_OFF + e); if (q.slot >= 0) fx[q.i + q.j * NX] = tile[q.slot]; }
+      for (int e = lane; e < M::D_fu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fu_OFF + e); if (q.slot >= 0) fu[q.i + q.j * NX] = tile[q.slot]; }
+      for (int e = lane; e < M::D_cu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cu_OFF + e); lhs[pk(q.j, NU + q.i)] = val(q); }
+      for (int e = lane; e < M::D_cx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cx_OFF + e); rhs[NU + q.i + (1 + q.j) * K] = val(q); }
+      for (int e = lane; e < M::D_lu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lu_OFF + e); rhs[q.i] = val(q); }
+      for (int e = lane; e < M::D_lux_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lux_OFF + e); rhs[q.i + (1 + q.j) * K] = val(q); }
+      for (int e = lane; e < M::D_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
+      for (int e = lane; e < M::D_lx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lx_OFF + e); lx[q.i] = val(q); }
+      for (int e = lane; e < NC; e += 32) rhs[NU + e] = r[R::C + e];
       __syncwarp();
       // ---- barrier terms, Qu, dual-infeasibility numerator            (src/backward_pass.jl:62-75)
       for (int i = lane; i < NU; i += 32) {
-        double a1 = 1.0 / il[i], a2 = 1.0 / iu[i];
+        double a1 = 1.0 / r[R::IL + i], a2 = 1.0 / r[R::IU + i];
         const double cl = a1 * mu, cu_ = a2 * mu;
         chil[i] = cl; chiu[i] = cu_;
-        const double lu_i = rhs0[i];
+        const double lu_i = rhs[i];
         double dq = 0.0;   // cu' phi
         {
           double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
         q = dot4c<NX>(fu + i * NX, 1, Vx, 1) + q;
         q -= cl;
         q += cu_;
-        rhs0[i] = q;   // Qu
+        rhs[i] = q;   // Qu
         // dual error numerator: lu + cu'phi - zl + zu + fu'lambda+      (src/solve.jl:127-132)
         double d = dq + lu_i;
         d -= zl[i];
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
         d = dot4c<NX>(fu + i * NX, 1, lamn, 1) + d;
         t1[i] = a1 * zl[i];   // Sigma^L
         t2[i] = a2 * zu[i];   // Sigma^U
-        ws[i] = fabs(d);
+        dsc[i] = fabs(d);
       }
       // ---- xx_tmp = fx' Vxx+ ; ux_tmp = fu' Vxx+                        (:80, :91)
       for (int e = lane; e < NX * NX; e += 32) {
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
       __syncwarp();
       {  // dual_num = max(dual_num, |.|_inf) -- uniform scan, NaN propagating like Julia's max
         double m = 0.0;
-        for (int i = 0; i < NU; ++i) m = jmax(m, ws[i]);
+        for (int i = 0; i < NU; ++i) m = jmax(m, dsc[i]);
         dual_num = jmax(dual_num, m);
       }
       // ---- C += xx_tmp fx ;  H = Sigma + ux_tmp fu (upper) ; B += ux_tmp fx    (:81, :86-99)
@@ -223,11 +228,11 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
       }
       for (int e = lane; e < NU * NX; e += 32) {
         const int i = e % NU, j = e / NU;
-        rhs0[i + (1 + j) * K] = dot4c<NX>(uxt + i, NU, fx + j * NX, 1) + rhs0[i + (1 + j) * K];
+        rhs[i + (1 + j) * K] = dot4c<NX>(uxt + i, NU, fx + j * NX, 1) + rhs[i + (1 + j) * K];
       }
       __syncwarp();
       // ---- H += luu
-      for (int e = lane; e < M::D_luu_N; e += 32) { const MEntry q = tbl[M::D_luu_OFF + e]; lhs[pk(q.i, q.j)] += val(q); }
+      for (int e = lane; e < M::D_luu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_luu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
       __syncwarp();
       if (second_order) {
         if constexpr (M::VF_NSLOT > 0) {   // dynamics Hessian contraction with lambda+ (:102-110), evaluated redundantly per lane
@@ -237,22 +242,25 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
           if (lane == 0)
             for (int s = 0; s < M::VF_NSLOT; ++s) vfs[s] = vfl[s];
           __syncwarp();
-          for (int e = lane; e < M::VF_vfxx_N; e += 32) { const MEntry q = tbl[M::VF_vfxx_OFF + e]; Cm[q.i + q.j * NX] += (q.slot >= 0 ? vfs[q.slot] : cst[-1 - q.slot]); }
-          for (int e = lane; e < M::VF_vfux_N; e += 32) { const MEntry q = tbl[M::VF_vfux_OFF + e]; rhs0[q.i + (1 + q.j) * K] += (q.slot >= 0 ? vfs[q.slot] : cst[-1 - q.slot]); }
-          for (int e = lane; e < M::VF_vfuu_N; e += 32) { const MEntry q = tbl[M::VF_vfuu_OFF + e]; lhs[pk(q.i, q.j)] += (q.slot >= 0 ? vfs[q.slot] : cst[-1 - q.slot]); }
+          for (int e = lane; e < M::VF_vfxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfxx_OFF + e); Cm[q.i + q.j * NX] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
+          for (int e = lane; e < M::VF_vfux_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfux_OFF + e); rhs[q.i + (1 + q.j) * K] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
+          for (int e = lane; e < M::VF_vfuu_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfuu_OFF + e); lhs[pk(q.i, q.j)] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
           __syncwarp();
         }
-        for (int e = lane; e < M::D_vcuu_N; e += 32) { const MEntry q = tbl[M::D_vcuu_OFF + e]; lhs[pk(q.i, q.j)] += val(q); }
-        for (int e = lane; e < M::D_vcux_N; e += 32) { const MEntry q = tbl[M::D_vcux_OFF + e]; rhs0[q.i + (1 + q.j) * K] += val(q); }
-        for (int e = lane; e < M::D_vcxx_N; e += 32) { const MEntry q = tbl[M::D_vcxx_OFF + e]; Cm[q.i + q.j * NX] += val(q); }
+        for (int e = lane; e < M::D_vcuu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcuu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
+        for (int e = lane; e < M::D_vcux_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcux_OFF + e); rhs[q.i + (1 + q.j) * K] += val(q); }
+        for (int e = lane; e < M::D_vcxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcxx_OFF + e); Cm[q.i + q.j * NX] += val(q); }
         __syncwarp();
       }
       if (reg > 0.0)
         for (int i = lane; i < NU; i += 32) lhs[pk(i, i)] += reg;
       if (delta_c > 0.0)
         for (int i = lane; i < NC; i += 32) lhs[pk(NU + i, NU + i)] -= delta_c;
-      // ---- rhs = -rhs0                                                  (:129-136)
-      for (int e = lane; e < K * NR; e += 32) rhs[e] = rhs0[e] * -1.0;
+      // ---- park the un-negated [Qu B; c cx] in this knot's gains slot (HBM, read back after the solve), write Qu,
+      //      and negate in place: rhs = -[Qu B; c cx]                    (:129-136)
+      double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
+      double* qo = v.Qu + ((size_t)b * (v.N - 1) + t) * NU;
+      for (int e = lane; e < K * NR; e += 32) { const double w = rhs[e]; g[e] = w; rhs[e] = w * -1.0; if (e < NU) qo[e] = w; }
       __syncwarp();
       // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
       int np = 0;
@@ -266,9 +274,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
         break;
       }
       warp_ldlt_solve_forward<K, NR>(lhs, ipiv, rhs, nzlist, lane);
-      // ---- gains to HBM: eq block, then ineq block                      (:159-172)
-      double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
-      for (int e = lane; e < K * NR; e += 32) g[e] = rhs[e];
+      // ---- ineq gains to HBM                                            (:159-172)
       double* gi = g + K * NR;
       for (int e = lane; e < NU * NR; e += 32) {
         const int i = e % NU, j = e / NU;
@@ -288,8 +294,6 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
           gi[NU + i + j * 2 * NU] = be * t2[i];
         }
       }
-      double* qo = v.Qu + ((size_t)b * (v.N - 1) + t) * NU;
-      for (int e = lane; e < NU; e += 32) qo[e] = rhs0[e];
       // ---- Vxx = beta' B + omega' cx + C ; Vx ; lambda                  (:176-189)
       // 4 lanes per output element: partial sums over i mod 4, butterfly combine = dot4 order
       {
@@ -299,8 +303,8 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
           const int i = e % NX, j = e / NX;
           double sa = 0.0, sb = 0.0;
           if (e < NX * NX) {
-            for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], rhs0[q + (1 + j) * K], sa);
-            for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], rhs0[NU + q + (1 + j) * K], sb);
+            for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], IPDDP_LDCG(g + q + (1 + j) * K), sa);
+            for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], IPDDP_LDCG(g + NU + q + (1 + j) * K), sb);
           }
           sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
           sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
@@ -317,9 +321,9 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
           const int i = e0 + (lane >> 2);
           double sa = 0.0, sb = 0.0, sc = 0.0;
           if (i < NX) {
-            for (int q = g4; q < NC; q += 4) sc = IPDDP_FMA(rhs0[NU + q + (1 + i) * K], phi[q], sc);        // cx' phi
-            for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], rhs0[q], sa);             // beta' Qu
-            for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], rhs0[NU + q], sb);   // omega' c
+            for (int q = g4; q < NC; q += 4) sc = IPDDP_FMA(IPDDP_LDCG(g + NU + q + (1 + i) * K), phi[q], sc);        // cx' phi
+            for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], IPDDP_LDCG(g + q), sa);             // beta' Qu
+            for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], IPDDP_LDCG(g + NU + q), sb);   // omega' c
           }
           sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
           sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
@@ -341,6 +345,7 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
         }
       }
       __syncwarp();
+      for (int e = lane; e < K * NR; e += 32) g[e] = rhs[e];   // eq gains replace the parked copy
       for (int e = lane; e < NX * NX; e += 32) Vxx[e] = nVxx[e];
       for (int e = lane; e < NX; e += 32) {
         Vx[e] = nVx[e];

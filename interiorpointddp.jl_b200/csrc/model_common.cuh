@@ -10,3 +10,13 @@ struct MEntry {
   short slot;
   unsigned char i, j;
 };
+
+// read-only load of one table entry (4 bytes: slot | i << 16 | j << 24)
+IPDDP_D MEntry ld_entry(const MEntry* p) {
+  const unsigned w = IPDDP_LDG(reinterpret_cast<const unsigned*>(p));
+  MEntry q;
+  q.slot = (short)(w & 0xffffu);
+  q.i = (unsigned char)((w >> 16) & 0xffu);
+  q.j = (unsigned char)(w >> 24);
+  return q;
+}
