@@ -294,12 +294,12 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         fp64_peak = float(lib.L.ipddp_measure_fp64_tflops(local_rank))
-        F = kkt_flops(nx, nu, nc)
+        flops_kkt = kkt_flops(nx, nu, nc)
         tb = agg["ms_backward"] * 1e-3
         kkt_rank = agg["kkt"]
         gb_dense = kkt_bytes_dense(nx, nu, nc) * kkt_rank / tb / 1e9
         gb_compact = kkt_bytes_compact(nx, nu, nc, slots) * kkt_rank / tb / 1e9
-        tf = F * kkt_rank / tb / 1e12
+        tf = flops_kkt * kkt_rank / tb / 1e12
         # dram__bytes_read+write of one k_backward launch from the committed ncu --set full capture
         # (profiles/r1_backward_summary.md): bytes per KKT step x the KKT steps of an average launch here
         ncu_bytes_per_kkt = None
@@ -317,7 +317,7 @@ def main():
                             f"{gb_compact:.1f} GB/s actual"}
         roof_fp64 = {"bound": "fp64", "kernel": "k_backward", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": tf / fp64_peak if fp64_peak > 0 else None, "peak_source": "DFMA microbenchmark, measured live",
-                     "flops_per_kkt_step": F}
+                     "flops_per_kkt_step": flops_kkt}
         nst = agg["deriv"] * (N - 1) if agg["deriv"] else 0
         td = agg["ms_derivs"] * 1e-3
         tfw = agg["ms_forward"] * 1e-3

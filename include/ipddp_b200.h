@@ -121,6 +121,11 @@ int ipddp_set_inputs_device(ipddp_problem* h, const double* x1, const double* ub
  * all instances terminated.  warm_start != 0 skips initialize_trajectory! (src/solve.jl:6 semantics). */
 int ipddp_solve(ipddp_problem* h, int warm_start);
 
+/* Splits the problem's instances into S contiguous cohorts with their own active lists, counters and streams; cohorts
+ * then progress through their rounds independently inside ipddp_solve / ipddp_solve_many (default S = 1: one lock-step
+ * loop with per-kernel timing in ipddp_stats).  Results are identical for every S. */
+int ipddp_set_cohorts(ipddp_problem* h, int S);
+
 /* Throughput driver: n independent problems (same device) progress concurrently, each on its own stream; one host
  * thread polls completion events and immediately enqueues the next round of whichever problem is ready, so the
  * lock-step tail of one batch overlaps the bulk rounds of the others.  Handles that finish start another solve of

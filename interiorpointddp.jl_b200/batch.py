@@ -93,6 +93,10 @@ class BatchSolver:
         self.set_inputs(batch.x1, batch.ubar, batch.p if self.np > 0 else None, batch.lower, batch.upper,
                         batch.horizons)
 
+    def set_cohorts(self, S: int):
+        """Split the batch into S independently progressing slices (see ipddp_set_cohorts)."""
+        self.lib.check(self.lib.L.ipddp_set_cohorts(self.h, int(S)), "ipddp_set_cohorts")
+
     # ------------------------------------------------------------------ solve and phases
     def solve(self, warm_start: bool = False) -> BatchResult:
         self.lib.check(self.lib.L.ipddp_solve(self.h, int(warm_start)), "ipddp_solve")

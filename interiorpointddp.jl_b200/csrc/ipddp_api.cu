@@ -123,6 +123,20 @@ __global__ void k_test_ldlt(int nmat, const double* A, const double* Bm, double*
 
 }  // namespace
 
+// A cohort is a contiguous slice of a problem's instances with its own active lists, counters and stream, so that
+// slices progress through their rounds independently (ipddp_set_cohorts, ipddp_solve_many).
+struct Cohort {
+  int b0 = 0, nb = 0;
+  int* d_list[2] = {nullptr, nullptr};
+  int* d_list_fwd = nullptr;
+  int* d_counters = nullptr;
+  int* h_counters = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool own_stream = false;
+  int cur = 0, n_active = 0, state = 0;
+};
+
 struct ipddp_problem {
   const ModelVTable* vt = nullptr;
   DevView v;
@@ -137,6 +151,10 @@ struct ipddp_problem {
   int* d_counters = nullptr;
   int* h_counters = nullptr;
   int* h_si = nullptr;            // pinned snapshot of the per-instance int scalars (ipddp_solve_many)
+  std::vector<Cohort> cohorts;    // >= 1 after ipddp_problem_create
+  int* d_ccount = nullptr;        // [S][CNT_COUNT]
+  int* h_ccount = nullptr;        // pinned
+  int cohorts_done = 0, hstate = 0;
   int cur = 0, n_active = 0;
   bool inputs_set = false;
   cudaEvent_t ev[8];
@@ -157,7 +175,7 @@ namespace {
 int run_init(ipddp_problem* h, int warm) {
   CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
   h->cur = 0;
-  h->vt->init(h->v, warm, h->d_list[0], h->d_counters, h->stream);
+  h->vt->init(h->v, warm, 0, h->v.B, h->d_list[0], h->d_counters, h->stream);
   h->st.launches += 1;
   CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -169,6 +187,8 @@ int run_init(ipddp_problem* h, int warm) {
 }  // namespace
 
 extern "C" {
+
+int ipddp_set_cohorts(ipddp_problem* h, int S);
 
 int ipddp_abi_version(void) { return IPDDP_ABI_VERSION; }
 const char* ipddp_last_error(void) { return g_err.c_str(); }
@@ -264,7 +284,33 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   CK(cudaStreamCreate(&h->stream));
   CK(cudaMallocHost((void**)&h->h_counters, CNT_COUNT * sizeof(int)));
   for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->ev[i]));
+  if (ipddp_set_cohorts(h, 1) != 0) return -1;
   *out = h;
+  return 0;
+}
+
+int ipddp_set_cohorts(ipddp_problem* h, int S) {
+  if (S < 1) S = 1;
+  if (S > h->v.B) S = h->v.B;
+  CK(cudaSetDevice(h->device));
+  for (auto& c : h->cohorts) { if (c.ev) cudaEventDestroy(c.ev); if (c.own_stream && c.stream) cudaStreamDestroy(c.stream); }
+  h->cohorts.clear();
+  if (h->d_ccount) { cudaFree(h->d_ccount); h->d_ccount = nullptr; }
+  if (h->h_ccount) { cudaFreeHost(h->h_ccount); h->h_ccount = nullptr; }
+  CK(cudaMalloc((void**)&h->d_ccount, (size_t)S * CNT_COUNT * sizeof(int)));
+  CK(cudaMallocHost((void**)&h->h_ccount, (size_t)S * CNT_COUNT * sizeof(int)));
+  h->cohorts.resize(S);
+  const int B = h->v.B, base = B / S, rem = B % S;
+  int b0 = 0;
+  for (int c = 0; c < S; ++c) {
+    Cohort& co = h->cohorts[c];
+    co.b0 = b0; co.nb = base + (c < rem ? 1 : 0); b0 += co.nb;
+    co.d_list[0] = h->d_list[0] + co.b0; co.d_list[1] = h->d_list[1] + co.b0; co.d_list_fwd = h->d_list_fwd + co.b0;
+    co.d_counters = h->d_ccount + (size_t)c * CNT_COUNT; co.h_counters = h->h_ccount + (size_t)c * CNT_COUNT;
+    if (c == 0) { co.stream = h->stream; co.own_stream = false; }
+    else { CK(cudaStreamCreate(&co.stream)); co.own_stream = true; }
+    CK(cudaEventCreate(&co.ev));
+  }
   return 0;
 }
 
@@ -274,6 +320,9 @@ int ipddp_problem_destroy(ipddp_problem* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_si) cudaFreeHost(h->h_si);
+  for (auto& c : h->cohorts) { if (c.ev) cudaEventDestroy(c.ev); if (c.own_stream && c.stream) cudaStreamDestroy(c.stream); }
+  if (h->d_ccount) cudaFree(h->d_ccount);
+  if (h->h_ccount) cudaFreeHost(h->h_ccount);
   if (h->stream) {
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
@@ -379,6 +428,13 @@ int ipddp_forward_pass(ipddp_problem* h) {
 int ipddp_solve(ipddp_problem* h, int warm_start) {
   if (!h->inputs_set) return fail("ipddp_set_inputs not called");
   CK(cudaSetDevice(h->device));
+  if (h->cohorts.size() > 1) {   // cohorts progress independently: no per-kernel time split
+    ipddp_stats agg;
+    double ms = 0.0;
+    if (ipddp_solve_many(&h, 1, 1, warm_start, &ms, &agg) != 0) return -1;
+    h->st = agg;
+    return 0;
+  }
   const DevView& v = h->v;
   ipddp_stats& st = h->st;
   memset(&st, 0, sizeof(st));
@@ -436,10 +492,11 @@ int ipddp_solve(ipddp_problem* h, int warm_start) {
   return 0;
 }
 
-// Several independent problems progress concurrently, each on its own stream, driven by one host thread that
-// polls completion events and immediately enqueues the next round of whichever handle became ready.  Hides the
-// lock-step tail of one batch (a few straggler instances at <1% occupancy) behind the bulk rounds of the others.
-// total_solves >= n: handles that finish early start another solve of their inputs until total_solves are done.
+// Several independent problems -- and the cohorts inside each problem -- progress concurrently, each cohort on its
+// own stream, driven by one host thread that polls completion events and immediately enqueues the next round of
+// whichever cohort became ready.  This hides the lock-step tail of one batch (a few straggler instances at <1 %
+// occupancy) behind the bulk rounds of the others, and the straggler warps of one kernel behind other cohorts' kernels.
+// total_solves >= n: problems that finish early start another solve of their inputs until total_solves are done.
 int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start, double* elapsed_ms,
                      ipddp_stats* agg) {
   if (n < 1 || total_solves < n) return fail("need n >= 1 handles and total_solves >= n");
@@ -451,62 +508,55 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
   CK(cudaSetDevice(hs[0]->device));
   ipddp_stats tot;
   memset(&tot, 0, sizeof(tot));
-  enum { IDLE = 0, INIT = 1, ROUND = 2, STATS = 3, FINISHED = 4 };
-  std::vector<int> state(n, IDLE);
+  enum { IDLE = 0, INIT = 1, ROUND = 2, CDONE = 3 };           // cohort states
+  enum { H_RUNNING = 0, H_STATS = 1, H_FINISHED = 2 };          // handle states
   int started = 0, finished = 0;
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(hs[0]->ev[6], hs[0]->stream));
   auto enqueue_init = [&](ipddp_problem* h) -> int {
     memset(&h->st, 0, sizeof(h->st));
-    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
-    h->cur = 0;
-    h->vt->init(h->v, warm_start, h->d_list[0], h->d_counters, h->stream);
-    h->st.launches += 1;
-    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaEventRecord(h->ev[5], h->stream));
+    h->cohorts_done = 0;
+    h->hstate = H_RUNNING;
+    for (auto& c : h->cohorts) {
+      CK(cudaMemsetAsync(c.d_counters, 0, CNT_COUNT * sizeof(int), c.stream));
+      c.cur = 0;
+      h->vt->init(h->v, warm_start, c.b0, c.nb, c.d_list[0], c.d_counters, c.stream);
+      h->st.launches += 1;
+      CK(cudaMemcpyAsync(c.h_counters, c.d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      CK(cudaEventRecord(c.ev, c.stream));
+      c.state = INIT;
+    }
     return 0;
   };
-  auto enqueue_round = [&](ipddp_problem* h) -> int {
-    const int nn = h->n_active, cur = h->cur;
-    cudaStream_t s = h->stream;
+  auto enqueue_round = [&](ipddp_problem* h, Cohort& c) -> int {
+    const int nn = c.n_active, cur = c.cur;
+    cudaStream_t s = c.stream;
     h->st.iterations += 1;
     h->st.n_active_rounds += nn;
-    h->vt->derivs(h->v, h->d_list[cur], nn, s);
-    h->vt->backward(h->v, h->d_list[cur], nn, s);
-    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
-    h->vt->check(h->v, h->d_list[cur], nn, h->d_list[1 - cur], h->d_list_fwd, h->d_counters, s);
-    h->vt->forward(h->v, h->d_list_fwd, nn, h->d_list[1 - cur], h->d_counters, s);
-    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(h->ev[5], s));
+    h->vt->derivs(h->v, c.d_list[cur], nn, s);
+    h->vt->backward(h->v, c.d_list[cur], nn, s);
+    CK(cudaMemsetAsync(c.d_counters, 0, CNT_COUNT * sizeof(int), s));
+    h->vt->check(h->v, c.d_list[cur], nn, c.d_list[1 - cur], c.d_list_fwd, c.d_counters, s);
+    h->vt->forward(h->v, c.d_list_fwd, nn, c.d_list[1 - cur], c.d_counters, s);
+    CK(cudaMemcpyAsync(c.h_counters, c.d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(c.ev, s));
     h->st.launches += 4;
     return 0;
   };
   for (int i = 0; i < n; ++i) {
     if (enqueue_init(hs[i]) != 0) return -1;
-    state[i] = INIT;
     started++;
   }
   while (finished < total_solves) {
     bool progressed = false;
     for (int i = 0; i < n; ++i) {
       ipddp_problem* h = hs[i];
-      if (state[i] == IDLE || state[i] == FINISHED) continue;
-      cudaError_t q = cudaEventQuery(h->ev[5]);
-      if (q == cudaErrorNotReady) continue;
-      if (q != cudaSuccess) return fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
-      progressed = true;
-      if (state[i] == INIT || state[i] == ROUND) {
-        if (state[i] == ROUND) h->cur = 1 - h->cur;
-        h->n_active = h->h_counters[CNT_NEXT];
-        if (h->n_active > 0) {
-          if (enqueue_round(h) != 0) return -1;
-          state[i] = ROUND;
-        } else {
-          CK(cudaMemcpyAsync(h->h_si, h->v.si, (size_t)SI_COUNT * h->v.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-          CK(cudaEventRecord(h->ev[5], h->stream));
-          state[i] = STATS;
-        }
-      } else {  // STATS arrived: this solve is complete
+      if (h->hstate == H_FINISHED) continue;
+      if (h->hstate == H_STATS) {
+        cudaError_t q = cudaEventQuery(h->ev[5]);
+        if (q == cudaErrorNotReady) continue;
+        if (q != cudaSuccess) return fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+        progressed = true;
         const int B = h->v.B;
         tot.iterations += h->st.iterations;
         tot.launches += h->st.launches;
@@ -522,12 +572,34 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
         finished++;
         if (started < total_solves) {
           if (enqueue_init(h) != 0) return -1;
-          state[i] = INIT;
           started++;
         } else {
           CK(cudaEventRecord(h->ev[7], h->stream));
-          state[i] = FINISHED;
+          h->hstate = H_FINISHED;
         }
+        continue;
+      }
+      for (auto& c : h->cohorts) {
+        if (c.state != INIT && c.state != ROUND) continue;
+        cudaError_t q = cudaEventQuery(c.ev);
+        if (q == cudaErrorNotReady) continue;
+        if (q != cudaSuccess) return fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+        progressed = true;
+        if (c.state == ROUND) c.cur = 1 - c.cur;
+        c.n_active = c.h_counters[CNT_NEXT];
+        if (c.n_active > 0) {
+          if (enqueue_round(h, c) != 0) return -1;
+          c.state = ROUND;
+        } else {
+          c.state = CDONE;
+          h->cohorts_done++;
+        }
+      }
+      if (h->hstate == H_RUNNING && h->cohorts_done == (int)h->cohorts.size()) {
+        // every cohort stream is idle (their last events were observed): snapshot the per-instance scalars
+        CK(cudaMemcpyAsync(h->h_si, h->v.si, (size_t)SI_COUNT * h->v.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev[5], h->stream));
+        h->hstate = H_STATS;
       }
     }
     if (!progressed) std::this_thread::yield();

@@ -16,10 +16,11 @@ namespace ipk {
 // warm != 0: keep the stored nominal primal trajectory (solve!(solver), src/solve.jl:6-17).
 // ---------------------------------------------------------------------------------------------
 template <class M>
-__global__ void k_init(DevView v, int warm, int* list_next, int* counters) {
+__global__ void k_init(DevView v, int warm, int b0, int nb, int* list_next, int* counters) {
   typedef Rec<M> R;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= v.B) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= nb) return;
+  const int b = b0 + tid;
   const int Nb = v.horizon[b];
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
   const double* lo = v.lower + (size_t)b * M::NU;

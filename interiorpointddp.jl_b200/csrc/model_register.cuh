@@ -9,9 +9,9 @@
 namespace ipk {
 
 template <class M> struct Launch {
-  static void init(const DevView& v, int warm, int* list_next, int* counters, cudaStream_t s) {
+  static void init(const DevView& v, int warm, int b0, int nb, int* list_next, int* counters, cudaStream_t s) {
     const int th = 64;
-    IPDDP_LAUNCH((k_init<M>), (v.B + th - 1) / th, th, 0, s, v, warm, list_next, counters);
+    IPDDP_LAUNCH((k_init<M>), (nb + th - 1) / th, th, 0, s, v, warm, b0, nb, list_next, counters);
   }
   static void derivs(const DevView& v, const int* list, int n, cudaStream_t s) {
     if (n <= 0) return;

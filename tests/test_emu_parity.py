@@ -54,12 +54,15 @@ def test_emulated_solve_many(emu, oracle_mod):
         b = instances.make_batch("double_integrator" if q != 1 else "concar", B, N, first=10 * q)
         s = BatchSolver(b.workload, B, N, options=opt, lib=emu)
         s.set_batch(b)
+        if q == 1:
+            s.set_cohorts(2)     # instances of this problem progress in two independent slices
         solvers.append(s); batches.append(b)
     ms, st = solve_many(solvers, total_solves=5)
     got = [s.results() for s in solvers]
     cnt = [s.counters() for s in solvers]
     conv = 0
     for s, r in zip(solvers, got):
+        s.set_cohorts(1)
         r2 = s.solve()      # sequential re-solve of the same inputs
         assert np.array_equal(r.k, r2.k) and np.array_equal(r.status, r2.status)
         helpers.assert_same_bits(r.objective, r2.objective, "objective")
@@ -69,3 +72,22 @@ def test_emulated_solve_many(emu, oracle_mod):
     assert st.launches > 0 and st.iterations > 0
     for s in solvers:
         s.close()
+
+
+def test_emulated_cohorts_single_solve(emu, oracle_mod):
+    """ipddp_solve on a problem split into cohorts == the oracle (and therefore == the single-cohort solve)."""
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver
+    b = instances.make_batch("concar", 5, 11)
+    s = BatchSolver("concar", 5, 11, options=emu.default_options(optimality_tolerance=1e-7), lib=emu)
+    s.set_batch(b)
+    s.set_cohorts(3)
+    r = s.solve()
+    res, xo, uo = oracle_mod.solve_batch("concar", 11, b.p, b.lower, b.upper, b.x1, b.ubar,
+                                         options=oracle_mod.default_options(optimality_tolerance=1e-7), want_traj=True)
+    assert [int(k) for k in r.k] == [q.k for q in res] and [int(x) for x in r.status] == [q.status for q in res]
+    x, u = s.trajectory()
+    helpers.assert_same_bits(x, xo, "states")
+    st = s.stats()
+    assert st.sum_kkt == sum(q.n_kkt for q in res) and st.n_converged == sum(1 for q in res if q.status == 0)
+    s.close()
