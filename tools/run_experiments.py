@@ -1,0 +1,61 @@
+"""Regenerates the reference's results tables (experiments/ipddp2/results/*.txt, written by e.g.
+experiments/ipddp2/cartpole_friction.jl:151-161) on the GPU: the 100 seeded instances of each class are solved as ONE
+batch per class, and the table is written in the reference's column format.  With --compare the tables are diffed
+against the committed golden copies (tests/golden/results): iteration-count and 9-digit-objective agreement per class.
+
+    python tools/run_experiments.py [--out gpurun_out/results] [--compare]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import ipddp_b200  # noqa: F401,E402
+from ipddp_b200 import _lib, instances  # noqa: E402
+from ipddp_b200.batch import BatchSolver  # noqa: E402
+
+CLASSES = [("cartpole", "cartpole_friction"), ("acrobot", "acrobot_contact"), ("concar", "concar"),
+           ("concar_quad", "concar_quad"), ("pushing", "pushing_1_obs"), ("double_integrator", "double_integrator")]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "results"))
+    ap.add_argument("--compare", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+    lib = _lib.load()
+    summary = {}
+    for wl, fname in CLASSES:
+        g = instances.load_golden_results(wl)
+        n = len(g["seed"])
+        b = instances.make_batch(wl, n, 101)
+        s = BatchSolver(wl, n, 101, options=lib.default_options(optimality_tolerance=1e-7), lib=lib)
+        s.set_batch(b)
+        r = s.solve()
+        st = s.stats()
+        s.close()
+        wall_ms = st.ms_total / n      # batch device time amortised per instance
+        solver_ms = (st.ms_total - st.ms_derivs) / n
+        with open(os.path.join(args.out, fname + ".txt"), "w") as fh:
+            fh.write(" seed  iterations  status     objective           primal        wall (ms)   solver(ms)  \n")
+            for i in range(n):
+                fh.write(" %2s     %5s      %5s    %.8e    %.8e     %5.1f        %5.1f  \n" % (
+                    i + 1, int(r.k[i]), "true" if r.status[i] == 0 else "false", r.objective[i], r.primal_inf[i],
+                    wall_ms, solver_ms))
+        same_it = int((r.k == g["iterations"]).sum())
+        same_obj = int((np.abs(r.objective - g["objective"]) <= 1e-8 * np.maximum(1.0, np.abs(g["objective"]))).sum())
+        both = int(((r.k == g["iterations"]) & (np.abs(r.objective - g["objective"]) <= 1e-8 * np.maximum(1.0, np.abs(g["objective"])))).sum())
+        summary[fname] = dict(instances=n, converged_gpu=int((r.status == 0).sum()), converged_reference=int(g["converged"].sum()),
+                              same_iterations=same_it, same_objective_1e8=same_obj, same_both=both,
+                              mean_iterations_gpu=float(r.k.mean()), mean_iterations_reference=float(g["iterations"].mean()),
+                              batch_ms=round(st.ms_total, 1), ms_per_instance=round(wall_ms, 3))
+        print(fname, json.dumps(summary[fname]), flush=True)
+    json.dump(summary, open(os.path.join(args.out, "summary.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
