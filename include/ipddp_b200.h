@@ -101,6 +101,10 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
                          const ipddp_options* opt, int device, int trace_capacity, ipddp_problem** out);
 int ipddp_problem_destroy(ipddp_problem* h);
 int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt);
+/* Execution tuning that never changes results (no reference counterpart).  h == NULL sets the default for problems
+ * created afterwards.  Keys: "fw_spec_max" -- rounds with at most this many active instances run the forward pass with
+ * one CTA per instance that tries 8 step sizes of the backtracking sequence at once (0 = never). */
+int ipddp_set_tuning(ipddp_problem* h, const char* key, int value);
 
 /* Per-timestep offset tables of the instance records (doubles from the start of one instance's
  * block): traj_off[t], gain_off[t] for t = 0..N-1, and the strides.  Any pointer may be NULL. */

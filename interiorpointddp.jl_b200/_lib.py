@@ -19,7 +19,7 @@ TRACE_NAMES = ["k", "j", "objective", "primal_inf", "dual_inf", "cs_inf", "mu", 
 EXPORTS = [
     "ipddp_abi_version", "ipddp_last_error", "ipddp_default_options", "ipddp_num_models", "ipddp_model_name",
     "ipddp_model_dims", "ipddp_model_load", "ipddp_problem_create", "ipddp_problem_destroy", "ipddp_set_options",
-    "ipddp_layout", "ipddp_set_inputs", "ipddp_set_inputs_device", "ipddp_solve", "ipddp_solve_many", "ipddp_set_cohorts", "ipddp_initialize",
+    "ipddp_set_tuning", "ipddp_layout", "ipddp_set_inputs", "ipddp_set_inputs_device", "ipddp_solve", "ipddp_solve_many", "ipddp_set_cohorts", "ipddp_initialize",
     "ipddp_eval_derivatives", "ipddp_backward_pass", "ipddp_check", "ipddp_forward_pass", "ipddp_get_results",
     "ipddp_get_trajectory", "ipddp_get_duals", "ipddp_get_counters", "ipddp_get_array", "ipddp_get_trace",
     "ipddp_get_stats", "ipddp_stream", "ipddp_measure_fp64_tflops", "ipddp_measure_hbm_gbs",
@@ -75,6 +75,7 @@ class Lib:
                                            C.c_int, C.POINTER(vp)]
         L.ipddp_problem_destroy.argtypes = [vp]
         L.ipddp_set_options.argtypes = [vp, C.POINTER(Options)]
+        L.ipddp_set_tuning.argtypes = [vp, C.c_char_p, C.c_int]
         L.ipddp_layout.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                    C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.ipddp_set_inputs.argtypes = [vp, dp, dp, dp, dp, dp, ip]

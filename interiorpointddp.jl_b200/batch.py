@@ -93,6 +93,10 @@ class BatchSolver:
         self.set_inputs(batch.x1, batch.ubar, batch.p if self.np > 0 else None, batch.lower, batch.upper,
                         batch.horizons)
 
+    def set_tuning(self, key: str, value: int):
+        """Execution tuning that never changes results (see ipddp_set_tuning)."""
+        self.lib.check(self.lib.L.ipddp_set_tuning(self.h, key.encode(), int(value)), "ipddp_set_tuning")
+
     def set_cohorts(self, S: int):
         """Split the batch into S independently progressing slices (see ipddp_set_cohorts)."""
         self.lib.check(self.lib.L.ipddp_set_cohorts(self.h, int(S)), "ipddp_set_cohorts")

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import concurrent.futures as cf
 import glob
+import hashlib
 import os
 import subprocess
 import sys
@@ -27,10 +28,19 @@ def sources():
     return [os.path.join(CSRC, "ipddp_api.cu")] + sorted(glob.glob(os.path.join(CSRC, "models", "*.cu")))
 
 
-def _deps_mtime():
-    files = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
-        glob.glob(os.path.join(CSRC, "models_gen", "*.cuh")) + [os.path.join(HERE, "..", "include", "ipddp_b200.h")]
-    return max(os.path.getmtime(f) for f in files)
+def _headers():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                  glob.glob(os.path.join(CSRC, "models_gen", "*.cuh")) + [os.path.join(HERE, "..", "include", "ipddp_b200.h")])
+
+
+def content_hash(files, extra=""):
+    """sha256 over file contents (not mtimes: checkouts and container moves reset those)."""
+    h = hashlib.sha256(extra.encode())
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 def _compile(src, verbose):
@@ -43,11 +53,13 @@ def _compile(src, verbose):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     srcs = sources()
-    dep = _deps_mtime()
-    todo = []
+    hdrs = _headers()
+    todo, stamps = [], {}
     for s in srcs:
         o = os.path.join(OBJ, os.path.basename(s).replace(".cu", ".o"))
-        if force or not os.path.exists(o) or os.path.getmtime(o) < max(dep, os.path.getmtime(s)):
+        stamps[s] = content_hash([s] + hdrs, " ".join(FLAGS))
+        old = open(o + ".hash").read() if os.path.exists(o + ".hash") else ""
+        if force or not os.path.exists(o) or old != stamps[s]:
             todo.append(s)
     if todo:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
@@ -56,6 +68,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     sys.stderr.write(out)
                 if rc != 0:
                     raise RuntimeError(f"nvcc failed on {src}")
+                with open(obj + ".hash", "w") as fh:
+                    fh.write(stamps[src])
     objs = [os.path.join(OBJ, os.path.basename(s).replace(".cu", ".o")) for s in srcs]
     if todo or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",

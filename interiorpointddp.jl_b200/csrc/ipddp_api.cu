@@ -32,6 +32,7 @@ const ModelVTable* ipddp_vtable_double_integrator();
 namespace {
 
 thread_local std::string g_err;
+int g_fw_spec_max = 148;   // default for new problems: speculative line search when <= one CTA per SM is active
 int fail(const std::string& m) { g_err = m; return -1; }
 #define CK(call)                                                                                    \
   do {                                                                                              \
@@ -157,6 +158,7 @@ struct ipddp_problem {
   int cohorts_done = 0, hstate = 0;
   int cur = 0, n_active = 0;
   bool inputs_set = false;
+  int spec_cap = 0;              // instances the speculative-forward record pool (DevView::spec_traj) was sized for
   cudaEvent_t ev[8];
   ipddp_stats st;
 
@@ -244,6 +246,7 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   v.G = (vt->nu + vt->nc + 2 * vt->nu) * (vt->nx + 1);
   if (opt) v.opt = *opt; else ipddp_default_options(&v.opt);
   v.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
+  v.fw_spec_max = g_fw_spec_max;
   v.n_compl = (indices_compl && n_compl > 0) ? n_compl : 0;
   for (int q = 0; q < v.n_compl; ++q) {
     if (indices_compl[q] < 0 || indices_compl[q] >= vt->nc) { delete h; return fail("indices_compl out of range"); }
@@ -269,6 +272,8 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   rc |= h->alloc(&v.si, (size_t)SI_COUNT * B);
   rc |= h->alloc(&v.filter, (size_t)2 * IPDDP_FILTER_CAPACITY * B);
   rc |= h->alloc(&v.trace, (size_t)B * v.trace_cap * IPDDP_TRACE_COLS);
+  rc |= h->alloc(&v.spec_traj, (size_t)(v.fw_spec_max > 0 ? v.fw_spec_max : 0) * 8 * N * v.TR);   // 8 = ipk::FWS_WARPS
+  h->spec_cap = v.fw_spec_max;
   rc |= h->alloc(&h->d_list[0], (size_t)B);
   rc |= h->alloc(&h->d_list[1], (size_t)B);
   rc |= h->alloc(&h->d_list_fwd, (size_t)B);
@@ -332,6 +337,25 @@ int ipddp_problem_destroy(ipddp_problem* h) {
 }
 
 int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt) { h->v.opt = *opt; return 0; }
+
+int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
+  const std::string k = key ? key : "";
+  if (k == "fw_spec_max") {   // h == NULL: default for problems created afterwards
+    if (value < 0) value = 0;
+    if (!h) { g_fw_spec_max = value; return 0; }
+    if (value > h->spec_cap) {   // grow the private trial-record pool
+      CK(cudaSetDevice(h->device));
+      double* q = nullptr;
+      CK(cudaMalloc((void**)&q, (size_t)value * 8 * h->v.N * h->v.TR * sizeof(double)));
+      h->allocs.push_back(q);    // the old pool is released with the handle
+      h->v.spec_traj = q;
+      h->spec_cap = value;
+    }
+    h->v.fw_spec_max = value;
+    return 0;
+  }
+  return fail("unknown tuning key " + k);
+}
 
 int ipddp_layout(ipddp_problem* h, long long* traj_off, long long* gain_off, long long* traj_stride,
                  long long* gain_stride, long long* tile_stride) {

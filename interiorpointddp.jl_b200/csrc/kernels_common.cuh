@@ -95,6 +95,103 @@ IPDDP_D void eval_metrics(const DevView& v, int set, int b, int Nb, double mu, d
   *Lout = bl;
 }
 
+// Per-warp scratch shared by the warp-per-instance kernels that evaluate merit terms (k_forward, k_check):
+// u[NU] | chunk[32] | finite-bound index bytes (2*NU, padded to 8 doubles) | 4 per-knot arrays of N doubles.
+template <class M> struct MeritLayout {
+  static constexpr int NUP = M::NU > 0 ? M::NU : 1;
+  static constexpr int FIXED = NUP + 32 + ((2 * NUP + 7) / 8);
+  static IPDDP_BOTH int per_warp_doubles(int N) { return FIXED + 4 * N; }
+};
+
+// finite-bound index list in the reference's accumulation order (lower indices, then upper indices;
+// src/data/methods.jl:45-53); built by lane 0, counts broadcast
+template <class M>
+IPDDP_D void warp_bound_list(const double* lo, const double* up, unsigned char* bidx, int lane, int& nlo, int& nbd) {
+  int a = 0, q = 0;
+  if (lane == 0) {
+    for (int i = 0; i < M::NU; ++i) if (!is_inf(lo[i])) bidx[q++] = (unsigned char)i;
+    a = q;
+    for (int i = 0; i < M::NU; ++i) if (!is_inf(up[i])) bidx[q++] = (unsigned char)i;
+  }
+  nlo = __shfl_sync(IPDDP_FULL_MASK, a, 0);
+  nbd = __shfl_sync(IPDDP_FULL_MASK, q, 0);
+  __syncwarp();
+}
+
+// Warp-parallel eval_metrics: the per-knot terms (l_t, c_t written to the record, |c_t|_1, c_t'phi_t) are evaluated
+// with lane = knot, the barrier logs 32 at a time, and every sum is then accumulated sequentially in exactly the
+// order eval_metrics uses -- bit-identical results.  All lanes return the same J, theta, L.
+// recs: the instance's knot records of the trajectory set to evaluate (record t at recs + t * TR).
+template <class M>
+IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu, const double* p, int nlo, int nbd,
+                               const unsigned char* bidx, double* chunk, double* p_l, double* p_th, double* p_d,
+                               int lane, double* Jout, double* theta_out, double* Lout) {
+  typedef Rec<M> R;
+  constexpr int NX = M::NX, NU = M::NU, NC = M::NC;
+  for (int t = lane; t < Nb; t += 32) {
+    double* r = recs + (size_t)t * R::SIZE;
+    double x[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = r[R::X + i];
+    double Jp;
+    if (t < Nb - 1) {
+      double u[NU > 0 ? NU : 1], c[NC > 0 ? NC : 1];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) u[i] = r[R::U + i];
+      M::cost(x, u, p, &Jp);
+      double n1 = 0.0;
+      if (NC > 0) {
+        M::con(x, u, p, c);
+        if (v.compl_mask) {
+#pragma unroll
+          for (int i = 0; i < M::NC; ++i) if ((v.compl_mask >> i) & 1ull) c[i] -= mu;
+        }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { r[R::C + i] = c[i]; n1 += fabs(c[i]); }
+      }
+      p_th[t] = n1;
+      double ph[NC > 0 ? NC : 1];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) ph[i] = r[R::PHI + i];
+      p_d[t] = dot4c<NC>(c, 1, ph, 1);
+    } else {
+      M::costN(x, p, &Jp);
+      p_th[t] = 0.0;
+      p_d[t] = 0.0;
+    }
+    p_l[t] = Jp;
+  }
+  __syncwarp();
+  double Jn = 0.0, theta = 0.0;
+  for (int t = 0; t < Nb; ++t) { Jn += p_l[t]; if (t < Nb - 1 && NC > 0) theta += p_th[t]; }
+  // barrier term: bl -= log(slack) over (t, lower idx..., upper idx...), one running accumulator
+  double bl = 0.0;
+  {
+    const int total = (Nb - 1) * nbd;
+    for (int base = 0; base < total; base += 32) {
+      const int q = base + lane;
+      double lg = 0.0;
+      if (q < total) {
+        const int t = q / nbd, s = q - t * nbd;
+        const double* r = recs + (size_t)t * R::SIZE;
+        const int i = bidx[s];
+        lg = dm::log(s < nlo ? r[R::IL + i] : r[R::IU + i]);
+      }
+      chunk[lane] = lg;
+      __syncwarp();
+      const int cnt = (total - base) < 32 ? (total - base) : 32;
+      for (int e = 0; e < cnt; ++e) bl -= chunk[e];
+      __syncwarp();
+    }
+  }
+  bl *= mu;
+  bl += Jn;
+  for (int t = 0; t < Nb; ++t) bl += p_d[t];
+  *Jout = Jn;
+  *theta_out = theta;
+  *Lout = bl;
+}
+
 IPDDP_D void reset_filter(const DevView& v, int b) {
   v.filter[(size_t)(0 * IPDDP_FILTER_CAPACITY + 0) * v.B + b] = v.sdv(SD_THETA_MAX, b);
   v.filter[(size_t)(1 * IPDDP_FILTER_CAPACITY + 0) * v.B + b] = -dm::inf();

@@ -156,31 +156,45 @@ __global__ void k_derivs(DevView v, const int* list, int n_list) {
 
 // ---------------------------------------------------------------------------------------------
 // k_check: optimality errors (reference src/solve.jl:107-180), convergence test and barrier update
-// (src/solve.jl:49-73).  Appends the instance to the forward list, to the next-round list (barrier
-// update: `continue` without forward pass, Q6) or marks it done.
+// (src/solve.jl:49-73), one warp per instance.  Appends the instance to the forward list, to the next-round list
+// (barrier update: `continue` without forward pass, Q6) or marks it done.
+// Per-knot terms are evaluated with lane = knot; the max-norms are order independent (NaN-propagating max), the
+// sums are then accumulated sequentially in the reference's order (t descending) from shared memory.
 // ---------------------------------------------------------------------------------------------
+constexpr int CHK_WARPS = 4;
+
 template <class M>
-__global__ void k_check(DevView v, const int* list, int n_list, int* list_next, int* list_fwd, int* counters) {
+__global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, const int* list, int n_list, int* list_next,
+                                                         int* list_fwd, int* counters) {
   typedef Rec<M> R;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  IPDDP_DYN_SMEM(double, sm_all);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * CHK_WARPS + warp;
   if (i >= n_list) return;
   const int b = list[i];
   if (v.siv(SI_STATUS, b) != 0) {  // backward pass failed (status 1): break
-    v.siv(SI_DONE, b) = 1;
+    __syncwarp();
+    if (lane == 0) v.siv(SI_DONE, b) = 1;
     return;
   }
+  double* us = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
+  double* chunk = us + MeritLayout<M>::NUP;
+  unsigned char* bidx = reinterpret_cast<unsigned char*>(chunk + 32);
+  double* part = chunk + 32 + ((2 * MeritLayout<M>::NUP + 7) / 8);
+  double* p_a = part; double* p_b = part + v.N; double* p_c = part + 2 * v.N;
   const int Nb = v.horizon[b];
   const int set = v.nomsel[b];
   const double* lo = v.lower + (size_t)b * M::NU;
   const double* up = v.upper + (size_t)b * M::NU;
+  const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
   const double mu = v.sdv(SD_MU, b);
-  int nb_stage = 0;
-  for (int q = 0; q < M::NU; ++q) nb_stage += (!is_inf(lo[q])) + (!is_inf(up[q]));
+  int nlo = 0, nbd = 0;
+  warp_bound_list<M>(lo, up, bidx, lane, nlo, nbd);
+  const int nb_stage = nbd;
 
-  double num_ineq = 0.0, z_norm = 0.0, phi_norm = 0.0, primal_inf = 0.0;
-  double cs0 = 0.0, csm = 0.0, z_norm_cs = 0.0;
+  double primal_inf = 0.0, cs0 = 0.0, csm = 0.0;
   // terminal stage contributes nothing (nu = nc = 0)
-  for (int t = Nb - 2; t >= 0; --t) {
+  for (int t = lane; t < Nb - 1; t += 32) {
     const double* r = v.rec(set, b, t);
     double m = 0.0;
 #pragma unroll
@@ -193,10 +207,7 @@ __global__ void k_check(DevView v, const int* list, int n_list, int* list_next, 
     for (int q = 0; q < M::NU; ++q) szu += r[R::ZU + q];
 #pragma unroll
     for (int q = 0; q < M::NC; ++q) sphi += fabs(r[R::PHI + q]);
-    z_norm += szl;
-    z_norm += szu;
-    phi_norm += sphi;
-    num_ineq += (double)nb_stage;
+    p_a[t] = szl; p_b[t] = szu; p_c[t] = sphi;
     if (nb_stage > 0) {
       double a0 = 0.0, am = 0.0, b0 = 0.0, bm = 0.0;
 #pragma unroll
@@ -221,10 +232,24 @@ __global__ void k_check(DevView v, const int* list, int n_list, int* list_next, 
       }
       cs0 = jmax(cs0, a0); cs0 = jmax(cs0, b0);
       csm = jmax(csm, am); csm = jmax(csm, bm);
-      z_norm_cs += szl;
-      z_norm_cs += szu;
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    primal_inf = jmax(primal_inf, __shfl_xor_sync(IPDDP_FULL_MASK, primal_inf, o));
+    cs0 = jmax(cs0, __shfl_xor_sync(IPDDP_FULL_MASK, cs0, o));
+    csm = jmax(csm, __shfl_xor_sync(IPDDP_FULL_MASK, csm, o));
+  }
+  __syncwarp();
+  double z_norm = 0.0, phi_norm = 0.0;
+  for (int t = Nb - 2; t >= 0; --t) {
+    z_norm += p_a[t];
+    z_norm += p_b[t];
+    phi_norm += p_c[t];
+  }
+  __syncwarp();
+  const double num_ineq = (double)nb_stage * (double)(Nb - 1);   // sum of Nb-1 copies of a small integer: exact
+  const double z_norm_cs = nb_stage > 0 ? z_norm : 0.0;          // same additions in the same order
   const double s_max = v.opt.s_max;
   const double num_constr = (double)(M::NC * (Nb - 1));
   const double sd_ = jmax(s_max, (phi_norm + z_norm) / jmax(num_ineq + num_constr, 1.0)) / s_max;
@@ -232,31 +257,35 @@ __global__ void k_check(DevView v, const int* list, int n_list, int* list_next, 
   const double dual_inf = v.sdv(SD_DUAL_NUM, b) / sd_;
   const double cs_inf = cs0 / sc_;
   const double cs_mu = csm / sc_;
-  v.sdv(SD_DUAL_INF, b) = dual_inf;
-  v.sdv(SD_PRIMAL_INF, b) = primal_inf;
-  v.sdv(SD_CS_INF, b) = cs_inf;
   const double err_mu = jmax(jmax(dual_inf, cs_mu), primal_inf);
   const double err_0 = jmax(jmax(dual_inf, cs_inf), primal_inf);
   const double tol = v.opt.optimality_tolerance;
+  if (lane == 0) {
+    v.sdv(SD_DUAL_INF, b) = dual_inf;
+    v.sdv(SD_PRIMAL_INF, b) = primal_inf;
+    v.sdv(SD_CS_INF, b) = cs_inf;
+  }
   if (err_0 < tol) {  // converged
-    v.siv(SI_DONE, b) = 1;
+    if (lane == 0) v.siv(SI_DONE, b) = 1;
     return;
   }
   const int num_bounds = nb_stage * (Nb - 1);
   if (err_mu <= v.opt.kappa_eps * mu && num_bounds > 0 && mu > tol / 10.0) {
     const double mu_new = jmax(tol / 10.0, jmin(v.opt.kappa_mu * mu, dm::pow(mu, v.opt.theta_mu)));
-    v.sdv(SD_MU, b) = mu_new;
-    reset_filter(v, b);
     double J, theta, L;
-    eval_metrics<M>(v, set, b, Nb, mu_new, &J, &theta, &L);
-    v.sdv(SD_OBJECTIVE, b) = J;
-    v.sdv(SD_L_CURR, b) = L;
-    v.sdv(SD_THETA_CURR, b) = theta;
-    v.siv(SI_J, b) += 1;
-    list_next[atomicAdd(&counters[CNT_NEXT], 1)] = b;
+    warp_eval_metrics<M>(v, v.rec(set, b, 0), Nb, mu_new, p, nlo, nbd, bidx, chunk, p_a, p_b, p_c, lane, &J, &theta, &L);
+    if (lane == 0) {
+      v.sdv(SD_MU, b) = mu_new;
+      reset_filter(v, b);
+      v.sdv(SD_OBJECTIVE, b) = J;
+      v.sdv(SD_L_CURR, b) = L;
+      v.sdv(SD_THETA_CURR, b) = theta;
+      v.siv(SI_J, b) += 1;
+      list_next[atomicAdd(&counters[CNT_NEXT], 1)] = b;
+    }
     return;
   }
-  list_fwd[atomicAdd(&counters[CNT_FWD], 1)] = b;
+  if (lane == 0) list_fwd[atomicAdd(&counters[CNT_FWD], 1)] = b;
 }
 
 }  // namespace ipk

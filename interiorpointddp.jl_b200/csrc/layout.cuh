@@ -60,6 +60,8 @@ struct DevView {
   double* filter;            // [2][FCAP][B]
   double* trace;             // [B][trace_cap][IPDDP_TRACE_COLS]
   int trace_cap;
+  int fw_spec_max;           // rounds with at most this many active instances use k_forward_spec
+  double* spec_traj;         // [fw_spec_max][FWS_WARPS][N][TR] private trial records of the speculative line search
   ipddp_options opt;
 
   IPDDP_D double* rec(int set, int b, int t) const { return traj + (((size_t)set * B + b) * N + t) * TR; }

@@ -26,17 +26,28 @@ template <class M> struct Launch {
   static void check(const DevView& v, const int* list, int n, int* list_next, int* list_fwd, int* counters,
                     cudaStream_t s) {
     if (n <= 0) return;
-    const int th = 64;
-    IPDDP_LAUNCH((k_check<M>), (n + th - 1) / th, th, 0, s, v, list, n, list_next, list_fwd, counters);
+    const size_t smem = (size_t)CHK_WARPS * MeritLayout<M>::per_warp_doubles(v.N) * sizeof(double);
+    IPDDP_LAUNCH((k_check<M>), (n + CHK_WARPS - 1) / CHK_WARPS, CHK_WARPS * 32, smem, s, v, list, n, list_next, list_fwd,
+                 counters);
   }
   static void forward(const DevView& v, const int* list_fwd, int n_upper, int* list_next, int* counters,
                       cudaStream_t s) {
     if (n_upper <= 0) return;
+    if (n_upper <= v.fw_spec_max) {
+      IPDDP_LAUNCH((k_forward_spec<M>), n_upper, FWS_WARPS * 32, FwLayout<M>::spec_bytes(v.N), s, v, list_fwd, list_next,
+                   counters);
+      return;
+    }
     IPDDP_LAUNCH((k_forward<M>), (n_upper + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, FwLayout<M>::bytes(v.N), s, v,
                  list_fwd, list_next, counters);
   }
   static int prepare() {
 #ifndef IPDDP_SIMT_EMU
+    // long horizons: the per-knot scratch of the merit evaluation may exceed the 48 KB default
+    const int big = 160 * 1024;
+    if (cudaFuncSetAttribute(k_forward<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_forward_spec<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_check<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
     if (BwLayout<M>::BYTES > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k_backward<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            BwLayout<M>::BYTES);

@@ -47,8 +47,19 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (idempotent)."""
-    if force or not os.path.exists(LIB_PATH):
-        subprocess.check_call(["make", "-C", HERE, "-s"] + (["-B"] if force else []))
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(HERE, "*.h")) + glob.glob(os.path.join(HERE, "*.cpp")) +
+                    glob.glob(os.path.join(HERE, "models_gen", "*.h")) + [os.path.join(HERE, "Makefile")]):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    stamp, stamp_file = h.hexdigest(), LIB_PATH + ".hash"
+    stale = not os.path.exists(LIB_PATH) or not os.path.exists(stamp_file) or open(stamp_file).read() != stamp
+    if force or stale:   # content hash, not mtime: checkouts reset mtimes
+        subprocess.check_call(["make", "-C", HERE, "-s", "-B"])
+        with open(stamp_file, "w") as fh:
+            fh.write(stamp)
     return LIB_PATH
 
 

@@ -2,6 +2,7 @@
 g++ against the fiber-based SIMT emulator (cpu_simt.h).  Used by tests/test_emu_*.py to check kernel
 logic bit-for-bit against the oracle in a container without a GPU.  Never loaded by the package."""
 import glob
+import hashlib
 import os
 import subprocess
 import sys
@@ -20,10 +21,16 @@ def build(force=False):
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         glob.glob(os.path.join(CSRC, "models_gen", "*.cuh")) + glob.glob(os.path.join(HERE, "cpu_simt.*")) + \
         [os.path.join(ROOT, "include", "ipddp_b200.h")]
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
-        return LIB
     objdir = os.path.join(HERE, "_build")
     os.makedirs(objdir, exist_ok=True)
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for d in sorted(deps):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    stamp, stamp_file = h.hexdigest(), os.path.join(objdir, "lib.hash")
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB
     procs = []
     objs = []
     for s in srcs:
@@ -38,6 +45,8 @@ def build(force=False):
         if p.wait() != 0:
             raise RuntimeError("emulator build failed")
     subprocess.check_call([CXX, "-shared", "-fopenmp", "-o", LIB] + objs + ["-ldl", "-lm"])
+    with open(stamp_file, "w") as fh:
+        fh.write(stamp)
     return LIB
 
 

@@ -52,6 +52,13 @@ void yield_barrier() {
   emu_switch(&f.sp, b->sched_sp);
 }
 
+void yield_block_barrier() {
+  BlockState* b = tls_block;
+  Fiber& f = b->fibers[b->current];
+  f.at_block_barrier = true;
+  emu_switch(&f.sp, b->sched_sp);
+}
+
 static void run_block(BlockState& bs, dim3 grid, dim3 block, unsigned bx, size_t smem, const std::function<void()>& body) {
   const int T = block.x;
   bs.body = &body;
@@ -63,6 +70,7 @@ static void run_block(BlockState& bs, dim3 grid, dim3 block, unsigned bx, size_t
   for (int t = 0; t < T; ++t) {
     Fiber& f = bs.fibers[t];
     f.done = false;
+    f.at_block_barrier = false;
     f.stack = bs.stacks.data() + (size_t)t * kStack;
     uintptr_t top = ((uintptr_t)(f.stack + kStack)) & ~(uintptr_t)15;
     void** A = (void**)(top - 16);
@@ -78,14 +86,18 @@ static void run_block(BlockState& bs, dim3 grid, dim3 block, unsigned bx, size_t
   int alive = T;
   while (alive > 0) {
     alive = 0;
+    int parked = 0;
     for (int t = 0; t < T; ++t) {
       Fiber& f = bs.fibers[t];
       if (f.done) continue;
+      if (f.at_block_barrier) { alive++; parked++; continue; }
       bs.current = t;
       tls_threadIdx = dim3(t, 0, 0);
       emu_switch(&bs.sched_sp, f.sp);
-      if (!f.done) alive++;
+      if (!f.done) { alive++; if (f.at_block_barrier) parked++; }
     }
+    if (alive > 0 && parked == alive)
+      for (int t = 0; t < T; ++t) bs.fibers[t].at_block_barrier = false;
   }
 }
 

@@ -6,7 +6,8 @@
 //
 // Model: every thread of a block is a fiber (own stack, hand-rolled x86-64 context switch); fibers of
 // a block run round-robin on one OS thread, __syncwarp/__syncthreads/shuffles yield to the scheduler,
-// which releases the barrier once every live fiber has arrived.  Blocks are distributed over OpenMP
+// which releases the barrier once every live fiber has arrived (warp-level barriers: one step per scheduler
+// round; __syncthreads: a fiber stays parked until every live fiber of the block is parked at __syncthreads).  Blocks are distributed over OpenMP
 // threads.  Floating point: fma() is a hardware FMA (-mfma), everything else uncontracted
 // (-ffp-contract=off), matching nvcc -fmad=false + explicit __fma_rn.
 #pragma once
@@ -24,7 +25,7 @@ struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c 
 struct double4 { double x, y, z, w; };
 
 namespace emu {
-struct Fiber { void* sp; char* stack; bool done; };
+struct Fiber { void* sp; char* stack; bool done; bool at_block_barrier; };
 struct BlockState {
   std::vector<Fiber> fibers;
   std::vector<char> stacks;
@@ -37,6 +38,7 @@ struct BlockState {
 extern thread_local BlockState* tls_block;
 extern thread_local dim3 tls_threadIdx, tls_blockIdx, tls_blockDim, tls_gridDim;
 void yield_barrier();
+void yield_block_barrier();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 inline void* cur_smem() { return tls_block->smem.data(); }
 }  // namespace emu
@@ -71,7 +73,7 @@ static inline double emu_ll2d(long long u) { double x; memcpy(&x, &u, 8); return
   emu::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })
 
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::yield_barrier(); }
-static inline void __syncthreads() { emu::yield_barrier(); }
+static inline void __syncthreads() { emu::yield_block_barrier(); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lanemask) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
   emu::BlockState* b = emu::tls_block;

@@ -26,6 +26,17 @@ def test_emulated_full_solve(emu, oracle_mod, wl, B, N, maxit):
     helpers.full_solve_parity(emu, oracle_mod, wl, B, N, maxit=maxit, n_trace=B)
 
 
+@pytest.mark.parametrize("wl,B,N,maxit", [("cartpole", 2, 9, 25), ("concar", 3, 11, 60), ("pushing", 2, 9, 30)])
+def test_emulated_forward_one_warp_per_instance(emu, oracle_mod, wl, B, N, maxit):
+    """The small batches above all take the speculative forward kernel (k_forward_spec, <= 148 active instances);
+    this forces the bulk kernel (k_forward) on the same problems."""
+    emu.L.ipddp_set_tuning(None, b"fw_spec_max", 0)
+    try:
+        helpers.full_solve_parity(emu, oracle_mod, wl, B, N, maxit=maxit, n_trace=B)
+    finally:
+        emu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
+
+
 def test_emulated_varying_horizon(emu, oracle_mod):
     helpers.full_solve_parity(emu, oracle_mod, "concar", 4, 13, maxit=80, vary_horizon=True, first=100, n_trace=4)
 
