@@ -103,7 +103,9 @@ int ipddp_problem_destroy(ipddp_problem* h);
 int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt);
 /* Execution tuning that never changes results (no reference counterpart).  h == NULL sets the default for problems
  * created afterwards.  Keys: "fw_spec_max" -- rounds with at most this many active instances run the forward pass with
- * one CTA per instance that tries 8 step sizes of the backtracking sequence at once (0 = never). */
+ * one CTA per instance that tries 8 step sizes of the backtracking sequence at once (0 = never);
+ * "bw_spec_max" -- rounds with at most this many active instances run the backward pass with one CTA per instance
+ * that tries 4 values of the regularisation schedule at once (0 = never). */
 int ipddp_set_tuning(ipddp_problem* h, const char* key, int value);
 
 /* Per-timestep offset tables of the instance records (doubles from the start of one instance's

@@ -18,6 +18,8 @@
 
 #include "kernels_common.cuh"
 #include "ldlt_warp.cuh"
+#include "kernel_backward.cuh"
+#include "kernel_forward.cuh"
 #include "vtable.h"
 
 extern "C" {
@@ -33,6 +35,7 @@ namespace {
 
 thread_local std::string g_err;
 int g_fw_spec_max = 148;   // default for new problems: speculative line search when <= one CTA per SM is active
+int g_bw_spec_max = 592;   // speculative restarts when <= 4 CTAs (16 warps) per SM are active
 int fail(const std::string& m) { g_err = m; return -1; }
 #define CK(call)                                                                                    \
   do {                                                                                              \
@@ -105,14 +108,14 @@ __global__ void k_test_ldlt(int nmat, const double* A, const double* Bm, double*
   double* lhs = sm;
   double* rhs = lhs + kp;
   double* ws = rhs + n * 5;
-  int* ipiv = reinterpret_cast<int*>(ws + 4 * n);
-  unsigned char* scratch = reinterpret_cast<unsigned char*>(ipiv + n);
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(ws + 4 * n);
+  int* ipiv = reinterpret_cast<int*>(scratch + ipk::LdltScratch<N>::BYTES);
   for (int j = 0; j < n; ++j)
     for (int i = lane; i <= j; i += 32) lhs[ipk::pk(i, j)] = A[(size_t)m * n * n + i + (size_t)j * n];
   for (int e = lane; e < n * 5; e += 32) rhs[e] = Bm[(size_t)m * n * 5 + e];
   __syncwarp();
   int np = 0;
-  const int info = ipk::warp_ldlt_factor<N, 5>(lhs, ipiv, rhs, ws, scratch, lane, 1e-12, np);
+  const int info = ipk::warp_ldlt_factor<N, 5>(lhs, ipiv, rhs, ws, scratch, lane, 1e-12, np, ipk::ldlt_tri_lane(lane));
   if (info == 0) ipk::warp_ldlt_solve_forward<N, 5>(lhs, ipiv, rhs, scratch, lane);
   __syncwarp();
   for (int j = 0; j < n; ++j)
@@ -159,6 +162,8 @@ struct ipddp_problem {
   int cur = 0, n_active = 0;
   bool inputs_set = false;
   int spec_cap = 0;              // instances the speculative-forward record pool (DevView::spec_traj) was sized for
+  int bw_spec_cap = 0;           // instances the speculative-backward output pool (DevView::spec_bw) was sized for
+  size_t bw_pool_doubles() const { return (size_t)(v.N - 1) * (v.G + v.nu) + (size_t)v.N * v.nx; }
   cudaEvent_t ev[8];
   ipddp_stats st;
 
@@ -247,6 +252,7 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   if (opt) v.opt = *opt; else ipddp_default_options(&v.opt);
   v.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
   v.fw_spec_max = g_fw_spec_max;
+  v.bw_spec_max = g_bw_spec_max;
   v.n_compl = (indices_compl && n_compl > 0) ? n_compl : 0;
   for (int q = 0; q < v.n_compl; ++q) {
     if (indices_compl[q] < 0 || indices_compl[q] >= vt->nc) { delete h; return fail("indices_compl out of range"); }
@@ -272,8 +278,11 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   rc |= h->alloc(&v.si, (size_t)SI_COUNT * B);
   rc |= h->alloc(&v.filter, (size_t)2 * IPDDP_FILTER_CAPACITY * B);
   rc |= h->alloc(&v.trace, (size_t)B * v.trace_cap * IPDDP_TRACE_COLS);
-  rc |= h->alloc(&v.spec_traj, (size_t)(v.fw_spec_max > 0 ? v.fw_spec_max : 0) * 8 * N * v.TR);   // 8 = ipk::FWS_WARPS
+  rc |= h->alloc(&v.spec_traj, (size_t)(v.fw_spec_max > 0 ? v.fw_spec_max : 0) * ipk::FWS_WARPS * N * v.TR);
   h->spec_cap = v.fw_spec_max;
+  if (v.bw_spec_max > B) v.bw_spec_max = B;
+  rc |= h->alloc(&v.spec_bw, (size_t)(v.bw_spec_max > 0 ? v.bw_spec_max : 0) * (ipk::BWS_WARPS - 1) * h->bw_pool_doubles());
+  h->bw_spec_cap = v.bw_spec_max;
   rc |= h->alloc(&h->d_list[0], (size_t)B);
   rc |= h->alloc(&h->d_list[1], (size_t)B);
   rc |= h->alloc(&h->d_list_fwd, (size_t)B);
@@ -346,12 +355,27 @@ int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
     if (value > h->spec_cap) {   // grow the private trial-record pool
       CK(cudaSetDevice(h->device));
       double* q = nullptr;
-      CK(cudaMalloc((void**)&q, (size_t)value * 8 * h->v.N * h->v.TR * sizeof(double)));
+      CK(cudaMalloc((void**)&q, (size_t)value * ipk::FWS_WARPS * h->v.N * h->v.TR * sizeof(double)));
       h->allocs.push_back(q);    // the old pool is released with the handle
       h->v.spec_traj = q;
       h->spec_cap = value;
     }
     h->v.fw_spec_max = value;
+    return 0;
+  }
+  if (k == "bw_spec_max") {
+    if (value < 0) value = 0;
+    if (!h) { g_bw_spec_max = value; return 0; }
+    if (value > h->v.B) value = h->v.B;
+    if (value > h->bw_spec_cap) {
+      CK(cudaSetDevice(h->device));
+      double* q = nullptr;
+      CK(cudaMalloc((void**)&q, (size_t)value * (ipk::BWS_WARPS - 1) * h->bw_pool_doubles() * sizeof(double)));
+      h->allocs.push_back(q);
+      h->v.spec_bw = q;
+      h->bw_spec_cap = value;
+    }
+    h->v.bw_spec_max = value;
     return 0;
   }
   return fail("unknown tuning key " + k);
@@ -829,7 +853,7 @@ int ipddp_test_ldlt(int n, int nmat, const double* A, const double* Bm, double* 
   CK(cudaMemcpy(dB, Bm, sb, cudaMemcpyHostToDevice));
   CK(cudaMemset(dAo, 0, sa));
   const int kp = n * (n + 1) / 2;
-  const size_t smem = ((size_t)(kp + n * 5 + 4 * n) * 8 + (size_t)n * 4 + (size_t)n * (2 + ipk::NZCAP) + 31) / 16 * 16;
+  const size_t smem = ((size_t)(kp + n * 5 + 4 * n) * 8 + (size_t)n * 4 + ((size_t)n * 17 + 15) / 16 * 16 + 31) / 16 * 16;
 #define IPDDP_LDLT_CASE(NN) case NN: IPDDP_LAUNCH((k_test_ldlt<NN>), nmat, 32, smem, 0, nmat, dA, dB, dAo, dip, dinfo, dnp, dX); break;
   switch (n) {
     IPDDP_LDLT_CASE(1) IPDDP_LDLT_CASE(2) IPDDP_LDLT_CASE(3) IPDDP_LDLT_CASE(4) IPDDP_LDLT_CASE(5) IPDDP_LDLT_CASE(8)

@@ -32,8 +32,8 @@ template <class M> struct BwLayout {
   static constexpr int VX = VXX + NX * NX;
   static constexpr int LAM = VX + NX;
   static constexpr int CM = LAM + NX;                // C (NX x NX)
-  static constexpr int VEC = CM + NX * NX;           // zl zu t1 t2 chil chiu  (6 x NU)
-  static constexpr int PHI = VEC + pad(6 * NU);
+  static constexpr int VEC = CM + NX * NX;           // 1/il 1/iu Sigma^L Sigma^U  (4 x NU)
+  static constexpr int PHI = VEC + pad(4 * NU);
   static constexpr int LX = PHI + pad(NC);
   static constexpr int NEWV = LX + NX;               // new Vxx (NX*NX), Vx (NX), lam (NX)
   // PRE: buffers that are dead once the factorisation starts; the 4K-double scratch of the 2x2 pivot update
@@ -50,41 +50,49 @@ template <class M> struct BwLayout {
   static constexpr int WS = PRE;
   static constexpr int DBL_END = mx(PRE_END, WS + 4 * K);
   // ints (4 bytes) after the doubles
-  static constexpr int IPIV_B = DBL_END * 8;
-  static constexpr int LIST_B = IPIV_B + pad(K) * 4;
-  static constexpr int BYTES = ((LIST_B + LdltScratch<(K > 0 ? K : 1)>::BYTES + 15) / 16) * 16;
+  // LDLT scratch (8-byte aligned: it starts with doubles), then ipiv (ints)
+  static constexpr int LIST_B = DBL_END * 8;
+  static constexpr int IPIV_B = LIST_B + LdltScratch<(K > 0 ? K : 1)>::BYTES;
+  static constexpr int BYTES = ((IPIV_B + pad(K) * 4 + 15) / 16) * 16;
 };
 
-template <class M>
-__global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int n_list) {
-  typedef BwLayout<M> L;
-  typedef Rec<M> R;
-  constexpr int NX = L::NX, NU = L::NU, NC = L::NC, K = L::K, NR = L::NR;
-  IPDDP_DYN_SMEM(double, sm);
-  const int lane = threadIdx.x;
-  const int inst = blockIdx.x;
-  if (inst >= n_list) return;
-  const int b = list[inst];
-  const int Nb = v.horizon[b];
-  const int set = v.nomsel[b];
+// where one sweep writes its outputs (per-instance base pointers: gains + t*G, Qu + t*NU, lam + t*NX)
+struct BwOut {
+  double* gains;
+  double* Qu;
+  double* lam;
+};
 
-  double* lhs = sm + L::LHS; double* rhs = sm + L::RHS;
-  double* fx = sm + L::FX; double* fu = sm + L::FU; double* Vxx = sm + L::VXX; double* Vx = sm + L::VX;
-  double* lamn = sm + L::LAM; double* Cm = sm + L::CM; double* xxt = sm + L::XXT; double* uxt = sm + L::UXT;
-  double* zl = sm + L::VEC; double* zu = zl + NU;
-  double* t1 = zu + NU; double* t2 = t1 + NU; double* chil = t2 + NU; double* chiu = chil + NU;
-  double* phi = sm + L::PHI; double* xs = sm + L::XS; double* us = sm + L::US; double* lx = sm + L::LX;
-  double* tile = sm + L::TILE; double* vfs = sm + L::VFS; double* ws = sm + L::WS; double* dsc = sm + L::DSC;
-  double* nVxx = sm + L::NEWV; double* nVx = nVxx + NX * NX; double* nlam = nVx + NX;
-  unsigned char* smb = reinterpret_cast<unsigned char*>(sm);
-  int* ipiv = reinterpret_cast<int*>(smb + L::IPIV_B);
-  unsigned char* nzlist = smb + L::LIST_B;
-  // scatter tables and constants stay in global memory (read-only path, shared by every warp of the grid)
-  const MEntry* tbl = M::tbl();
-  const double* cst = M::consts();
+// regularisation schedule on inertia failure (src/inertia_correction.jl:267-274); reg_last is the value the previous
+// backward pass ended with
+IPDDP_D double bw_next_reg(const DevView& v, double reg, double reg_last) {
+  if (reg == 0.0) return (reg_last == 0.0) ? v.opt.reg_1 : jmax(v.opt.reg_min, v.opt.kappa_w_m * reg_last);
+  return (reg_last == 0.0) ? v.opt.kappa_bar_w_p * reg : v.opt.kappa_w_p * reg;
+}
+
+#define IPDDP_BW_POINTERS \
+  double* lhs = sm + L::LHS; double* rhs = sm + L::RHS; \
+  double* fx = sm + L::FX; double* fu = sm + L::FU; double* Vxx = sm + L::VXX; double* Vx = sm + L::VX; \
+  double* lamn = sm + L::LAM; double* Cm = sm + L::CM; double* xxt = sm + L::XXT; double* uxt = sm + L::UXT; \
+  double* ra1 = sm + L::VEC; double* ra2 = ra1 + NU; double* t1 = ra2 + NU; double* t2 = t1 + NU; \
+  double* phi = sm + L::PHI; double* xs = sm + L::XS; double* us = sm + L::US; double* lx = sm + L::LX; \
+  double* tile = sm + L::TILE; double* vfs = sm + L::VFS; double* ws = sm + L::WS; double* dsc = sm + L::DSC; \
+  double* nVxx = sm + L::NEWV; double* nVx = nVxx + NX * NX; double* nlam = nVx + NX; \
+  unsigned char* smb = reinterpret_cast<unsigned char*>(sm); \
+  int* ipiv = reinterpret_cast<int*>(smb + L::IPIV_B); \
+  unsigned char* nzlist = smb + L::LIST_B; \
+  const MEntry* tbl = M::tbl(); \
+  const double* cst = M::consts(); \
   (void)xs; (void)us; (void)vfs;
 
-  // ---- one-time setup: constant parts of fx / fu
+// one-time setup of a warp's shared memory: constant parts of fx / fu
+template <class M>
+IPDDP_D void bw_setup(double* sm, int lane) {
+  typedef BwLayout<M> L;
+  constexpr int NX = L::NX, NU = L::NU;
+  double* fx = sm + L::FX; double* fu = sm + L::FU;
+  const MEntry* tbl = M::tbl();
+  const double* cst = M::consts();
   for (int e = lane; e < NX * NX; e += 32) fx[e] = 0.0;
   for (int e = lane; e < NX * NU; e += 32) fu[e] = 0.0;
   __syncwarp();
@@ -97,266 +105,367 @@ __global__ void __launch_bounds__(32) k_backward(DevView v, const int* list, int
     if (q.slot < 0) fu[q.i + q.j * NX] = IPDDP_LDG(cst - 1 - q.slot);
   }
   __syncwarp();
+}
 
-  const double mu = v.sdv(SD_MU, b);
-  const double reg_last = v.sdv(SD_REG_LAST, b);
+// One sweep t = Nb-1 .. 0 of backward_pass! with regularisation `reg` by one warp.  Returns 0 on success, 1 if the
+// inertia test failed at some knot (the caller restarts with a larger reg).  nkkt += knots visited;
+// dual_num = numerator of the dual infeasibility of this sweep.
+template <class M>
+IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, double mu, double* sm, const BwOut& out,
+                     int lane, int& nkkt, double& dual_num) {
+  typedef BwLayout<M> L;
+  typedef Rec<M> R;
+  constexpr int NX = L::NX, NU = L::NU, NC = L::NC, K = L::K, NR = L::NR;
+  IPDDP_BW_POINTERS
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
   const bool second_order = (v.opt.quasi_newton == 0);
-  double reg = 0.0, delta_c = 0.0;
-  int status = 0, nsweep = 0, nkkt = 0;
-  double dual_num = 0.0;
-
+  double delta_c = 0.0;
+  const unsigned tri_lane = ldlt_tri_lane(lane);
   auto val = [&](const MEntry& q) -> double { return q.slot >= 0 ? tile[q.slot] : IPDDP_LDG(cst - 1 - q.slot); };
-
-  while (reg <= v.opt.reg_max) {
-    status = 0;
-    nsweep++;
-    dual_num = 0.0;
-    // ================= terminal knot (K = 0): Vxx = lxx_N, Vx = lx_N, lambda = lx_N =================
-    {
-      const int t = Nb - 1;
-      nkkt++;
-      for (int e = lane; e < M::DN_NSLOT; e += 32) tile[e] = v.tileN[(size_t)b * (M::DN_NSLOT > 0 ? M::DN_NSLOT : 1) + e];
-      for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
-      for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
-      __syncwarp();
-      for (int e = lane; e < M::DN_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::DN_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
-      for (int e = lane; e < M::DN_lx_N; e += 32) { const MEntry q = ld_entry(tbl + M::DN_lx_OFF + e); lx[q.i] = val(q); }
-      __syncwarp();
-      // C = lxx (+ vcxx = 0 unless quasi_newton);  Vxx = (0 + 0) + C ;  Vx = lambda = 0 + lx
-      // inertia_correction! on the empty KKT matrix resets delta_c (Q4: the value set by a failed knot
-      // never reaches a non-empty KKT matrix)
-      delta_c = 0.0;
-      for (int e = lane; e < NX * NX; e += 32) Vxx[e] = (0.0 + 0.0) + (second_order ? (Cm[e] + 0.0) : Cm[e]);
-      for (int e = lane; e < NX; e += 32) {
-        const double l0 = 0.0 + lx[e];
-        lamn[e] = l0;
-        Vx[e] = (l0 + 0.0) + 0.0;
-        v.lam[((size_t)b * v.N + t) * NX + e] = l0;
-      }
-      __syncwarp();
+  dual_num = 0.0;
+  // ================= terminal knot (K = 0): Vxx = lxx_N, Vx = lx_N, lambda = lx_N =================
+  {
+    const int t = Nb - 1;
+    nkkt++;
+    for (int e = lane; e < M::DN_NSLOT; e += 32) tile[e] = v.tileN[(size_t)b * (M::DN_NSLOT > 0 ? M::DN_NSLOT : 1) + e];
+    for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
+    for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
+    __syncwarp();
+    for (int e = lane; e < M::DN_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::DN_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
+    for (int e = lane; e < M::DN_lx_N; e += 32) { const MEntry q = ld_entry(tbl + M::DN_lx_OFF + e); lx[q.i] = val(q); }
+    __syncwarp();
+    // C = lxx (+ vcxx = 0 unless quasi_newton);  Vxx = (0 + 0) + C ;  Vx = lambda = 0 + lx
+    // inertia_correction! on the empty KKT matrix resets delta_c (Q4: the value set by a failed knot
+    // never reaches a non-empty KKT matrix)
+    delta_c = 0.0;
+    for (int e = lane; e < NX * NX; e += 32) Vxx[e] = (0.0 + 0.0) + (second_order ? (Cm[e] + 0.0) : Cm[e]);
+    for (int e = lane; e < NX; e += 32) {
+      const double l0 = 0.0 + lx[e];
+      lamn[e] = l0;
+      Vx[e] = (l0 + 0.0) + 0.0;
+      out.lam[(size_t)t * NX + e] = l0;
     }
-    // ================= running knots =================
-    for (int t = Nb - 2; t >= 0; --t) {
-      nkkt++;
-      const double* r = v.rec(set, b, t);
-      // ---- stage inputs
-      for (int e = lane; e < M::D_NSLOT; e += 32) tile[e] = v.tile[((size_t)b * M::D_NSLOT + e) * v.N + t];
-      for (int e = lane; e < NU; e += 32) { zl[e] = r[R::ZL + e]; zu[e] = r[R::ZU + e]; }
-      if constexpr (M::VF_NSLOT > 0) {
-        for (int e = lane; e < NU; e += 32) us[e] = r[R::U + e];
-        for (int e = lane; e < NX; e += 32) xs[e] = r[R::X + e];
-      }
-      for (int e = lane; e < NC; e += 32) phi[e] = r[R::PHI + e];
-      for (int e = lane; e < L::KP; e += 32) lhs[e] = 0.0;
-      for (int e = lane; e < K * NR; e += 32) rhs[e] = 0.0;
-      for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
-      for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
-      __syncwarp();
-      // ---- scatter pass 1: fx, fu (non-constant part), cu -> lhs top-right, cx -> rhs, lu -> rhs col 0,
-      //      lux -> rhs B block, lxx -> C, lx, c -> rhs   (rhs holds the un-negated [Qu B; c cx] until the solve)
-      for (int e = lane; e < M::D_fx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fx_OFF + e); if (q.slot >= 0) fx[q.i + q.j * NX] = tile[q.slot]; }
-      for (int e = lane; e < M::D_fu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fu_OFF + e); if (q.slot >= 0) fu[q.i + q.j * NX] = tile[q.slot]; }
-      for (int e = lane; e < M::D_cu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cu_OFF + e); lhs[pk(q.j, NU + q.i)] = val(q); }
-      for (int e = lane; e < M::D_cx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cx_OFF + e); rhs[NU + q.i + (1 + q.j) * K] = val(q); }
-      for (int e = lane; e < M::D_lu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lu_OFF + e); rhs[q.i] = val(q); }
-      for (int e = lane; e < M::D_lux_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lux_OFF + e); rhs[q.i + (1 + q.j) * K] = val(q); }
-      for (int e = lane; e < M::D_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
-      for (int e = lane; e < M::D_lx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lx_OFF + e); lx[q.i] = val(q); }
-      for (int e = lane; e < NC; e += 32) rhs[NU + e] = r[R::C + e];
-      __syncwarp();
-      // ---- barrier terms, Qu, dual-infeasibility numerator            (src/backward_pass.jl:62-75)
-      for (int i = lane; i < NU; i += 32) {
-        double a1 = 1.0 / r[R::IL + i], a2 = 1.0 / r[R::IU + i];
-        const double cl = a1 * mu, cu_ = a2 * mu;
-        chil[i] = cl; chiu[i] = cu_;
-        const double lu_i = rhs[i];
-        double dq = 0.0;   // cu' phi
-        {
-          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-          int rr = 0;
-          for (; rr + 3 < NC; rr += 4) {
-            s0 = IPDDP_FMA(lhs[pk(i, NU + rr + 0)], phi[rr + 0], s0);
-            s1 = IPDDP_FMA(lhs[pk(i, NU + rr + 1)], phi[rr + 1], s1);
-            s2 = IPDDP_FMA(lhs[pk(i, NU + rr + 2)], phi[rr + 2], s2);
-            s3 = IPDDP_FMA(lhs[pk(i, NU + rr + 3)], phi[rr + 3], s3);
-          }
-          if (rr < NC) s0 = IPDDP_FMA(lhs[pk(i, NU + rr)], phi[rr], s0);
-          if (rr + 1 < NC) s1 = IPDDP_FMA(lhs[pk(i, NU + rr + 1)], phi[rr + 1], s1);
-          if (rr + 2 < NC) s2 = IPDDP_FMA(lhs[pk(i, NU + rr + 2)], phi[rr + 2], s2);
-          dq = (s0 + s1) + (s2 + s3);
+    __syncwarp();
+  }
+  // ================= running knots =================
+  for (int t = Nb - 2; t >= 0; --t) {
+    nkkt++;
+    const double* r = v.rec(set, b, t);
+    // ---- stage inputs
+    for (int e = lane; e < M::D_NSLOT; e += 32) tile[e] = v.tile[((size_t)b * M::D_NSLOT + e) * v.N + t];
+    if constexpr (M::VF_NSLOT > 0) {
+      for (int e = lane; e < NU; e += 32) us[e] = r[R::U + e];
+      for (int e = lane; e < NX; e += 32) xs[e] = r[R::X + e];
+    }
+    for (int e = lane; e < NC; e += 32) phi[e] = r[R::PHI + e];
+    for (int e = lane; e < L::KP; e += 32) lhs[e] = 0.0;
+    for (int e = lane; e < K * NR; e += 32) rhs[e] = 0.0;
+    for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
+    for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
+    __syncwarp();
+    // ---- scatter pass 1: fx, fu (non-constant part), cu -> lhs top-right, cx -> rhs, lu -> rhs col 0,
+    //      lux -> rhs B block, lxx -> C, lx, c -> rhs   (rhs holds the un-negated [Qu B; c cx] until the solve)
+    for (int e = lane; e < M::D_fx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fx_OFF + e); if (q.slot >= 0) fx[q.i + q.j * NX] = tile[q.slot]; }
+    for (int e = lane; e < M::D_fu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fu_OFF + e); if (q.slot >= 0) fu[q.i + q.j * NX] = tile[q.slot]; }
+    for (int e = lane; e < M::D_cu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cu_OFF + e); lhs[pk(q.j, NU + q.i)] = val(q); }
+    for (int e = lane; e < M::D_cx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cx_OFF + e); rhs[NU + q.i + (1 + q.j) * K] = val(q); }
+    for (int e = lane; e < M::D_lu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lu_OFF + e); rhs[q.i] = val(q); }
+    for (int e = lane; e < M::D_lux_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lux_OFF + e); rhs[q.i + (1 + q.j) * K] = val(q); }
+    for (int e = lane; e < M::D_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
+    for (int e = lane; e < M::D_lx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lx_OFF + e); lx[q.i] = val(q); }
+    for (int e = lane; e < NC; e += 32) rhs[NU + e] = r[R::C + e];
+    __syncwarp();
+    // ---- barrier terms, Qu, dual-infeasibility numerator            (src/backward_pass.jl:62-75)
+    for (int i = lane; i < NU; i += 32) {
+      const double a1 = 1.0 / r[R::IL + i], a2 = 1.0 / r[R::IU + i];
+      const double zl_i = r[R::ZL + i], zu_i = r[R::ZU + i];
+      const double cl = a1 * mu, cu_ = a2 * mu;
+      ra1[i] = a1; ra2[i] = a2;
+      const double lu_i = rhs[i];
+      double dq = 0.0;   // cu' phi
+      {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int rr = 0;
+        for (; rr + 3 < NC; rr += 4) {
+          s0 = IPDDP_FMA(lhs[pk(i, NU + rr + 0)], phi[rr + 0], s0);
+          s1 = IPDDP_FMA(lhs[pk(i, NU + rr + 1)], phi[rr + 1], s1);
+          s2 = IPDDP_FMA(lhs[pk(i, NU + rr + 2)], phi[rr + 2], s2);
+          s3 = IPDDP_FMA(lhs[pk(i, NU + rr + 3)], phi[rr + 3], s3);
         }
-        double q = dq + lu_i;
-        q = dot4c<NX>(fu + i * NX, 1, Vx, 1) + q;
-        q -= cl;
-        q += cu_;
-        rhs[i] = q;   // Qu
-        // dual error numerator: lu + cu'phi - zl + zu + fu'lambda+      (src/solve.jl:127-132)
-        double d = dq + lu_i;
-        d -= zl[i];
-        d += zu[i];
-        d = dot4c<NX>(fu + i * NX, 1, lamn, 1) + d;
-        t1[i] = a1 * zl[i];   // Sigma^L
-        t2[i] = a2 * zu[i];   // Sigma^U
-        dsc[i] = fabs(d);
+        if (rr < NC) s0 = IPDDP_FMA(lhs[pk(i, NU + rr)], phi[rr], s0);
+        if (rr + 1 < NC) s1 = IPDDP_FMA(lhs[pk(i, NU + rr + 1)], phi[rr + 1], s1);
+        if (rr + 2 < NC) s2 = IPDDP_FMA(lhs[pk(i, NU + rr + 2)], phi[rr + 2], s2);
+        dq = (s0 + s1) + (s2 + s3);
       }
-      // ---- xx_tmp = fx' Vxx+ ; ux_tmp = fu' Vxx+                        (:80, :91)
-      for (int e = lane; e < NX * NX; e += 32) {
-        const int i = e % NX, j = e / NX;
-        xxt[e] = dot4c<NX>(fx + i * NX, 1, Vxx + j * NX, 1);
-      }
-      for (int e = lane; e < NU * NX; e += 32) {
-        const int i = e % NU, j = e / NU;
-        uxt[e] = dot4c<NX>(fu + i * NX, 1, Vxx + j * NX, 1);
-      }
-      __syncwarp();
-      {  // dual_num = max(dual_num, |.|_inf) -- uniform scan, NaN propagating like Julia's max
-        double m = 0.0;
-        for (int i = 0; i < NU; ++i) m = jmax(m, dsc[i]);
-        dual_num = jmax(dual_num, m);
-      }
-      // ---- C += xx_tmp fx ;  H = Sigma + ux_tmp fu (upper) ; B += ux_tmp fx    (:81, :86-99)
-      for (int e = lane; e < NX * NX; e += 32) {
-        const int i = e % NX, j = e / NX;
-        Cm[e] = dot4c<NX>(xxt + i, NX, fx + j * NX, 1) + Cm[e];
-      }
-      for (int e = lane; e < NU * (NU + 1) / 2; e += 32) {
-        const unsigned q = tri_decode(e);
-        const int i = q & 0xff, j = q >> 8;
-        const double h0 = (i == j) ? (t1[i] + t2[i]) : 0.0;
-        lhs[e] = dot4c<NX>(uxt + i, NU, fu + j * NX, 1) + h0;
-      }
-      for (int e = lane; e < NU * NX; e += 32) {
-        const int i = e % NU, j = e / NU;
-        rhs[i + (1 + j) * K] = dot4c<NX>(uxt + i, NU, fx + j * NX, 1) + rhs[i + (1 + j) * K];
-      }
-      __syncwarp();
-      // ---- H += luu
-      for (int e = lane; e < M::D_luu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_luu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
-      __syncwarp();
-      if (second_order) {
-        if constexpr (M::VF_NSLOT > 0) {   // dynamics Hessian contraction with lambda+ (:102-110), evaluated redundantly per lane
-          double vfl[M::VF_NSLOT > 0 ? M::VF_NSLOT : 1];
-          auto st = [&](int s, double x_) { vfl[s] = x_; };
-          M::vf(xs, us, lamn, p, st);
-          if (lane == 0)
-            for (int s = 0; s < M::VF_NSLOT; ++s) vfs[s] = vfl[s];
-          __syncwarp();
-          for (int e = lane; e < M::VF_vfxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfxx_OFF + e); Cm[q.i + q.j * NX] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
-          for (int e = lane; e < M::VF_vfux_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfux_OFF + e); rhs[q.i + (1 + q.j) * K] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
-          for (int e = lane; e < M::VF_vfuu_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfuu_OFF + e); lhs[pk(q.i, q.j)] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
-          __syncwarp();
-        }
-        for (int e = lane; e < M::D_vcuu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcuu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
-        for (int e = lane; e < M::D_vcux_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcux_OFF + e); rhs[q.i + (1 + q.j) * K] += val(q); }
-        for (int e = lane; e < M::D_vcxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcxx_OFF + e); Cm[q.i + q.j * NX] += val(q); }
+      double q = dq + lu_i;
+      q = dot4c<NX>(fu + i * NX, 1, Vx, 1) + q;
+      q -= cl;
+      q += cu_;
+      rhs[i] = q;   // Qu
+      // dual error numerator: lu + cu'phi - zl + zu + fu'lambda+      (src/solve.jl:127-132)
+      double d = dq + lu_i;
+      d -= zl_i;
+      d += zu_i;
+      d = dot4c<NX>(fu + i * NX, 1, lamn, 1) + d;
+      t1[i] = a1 * zl_i;    // Sigma^L
+      t2[i] = a2 * zu_i;    // Sigma^U
+      dsc[i] = fabs(d);
+    }
+    // ---- xx_tmp = fx' Vxx+ ; ux_tmp = fu' Vxx+                        (:80, :91)
+    for (int e = lane; e < NX * NX; e += 32) {
+      const int i = e % NX, j = e / NX;
+      xxt[e] = dot4c<NX>(fx + i * NX, 1, Vxx + j * NX, 1);
+    }
+    for (int e = lane; e < NU * NX; e += 32) {
+      const int i = e % NU, j = e / NU;
+      uxt[e] = dot4c<NX>(fu + i * NX, 1, Vxx + j * NX, 1);
+    }
+    __syncwarp();
+    {  // dual_num = max(dual_num, |.|_inf) -- uniform scan, NaN propagating like Julia's max
+      double m = 0.0;
+      for (int i = 0; i < NU; ++i) m = jmax(m, dsc[i]);
+      dual_num = jmax(dual_num, m);
+    }
+    // ---- C += xx_tmp fx ;  H = Sigma + ux_tmp fu (upper) ; B += ux_tmp fx    (:81, :86-99)
+    for (int e = lane; e < NX * NX; e += 32) {
+      const int i = e % NX, j = e / NX;
+      Cm[e] = dot4c<NX>(xxt + i, NX, fx + j * NX, 1) + Cm[e];
+    }
+    for (int e = lane; e < NU * (NU + 1) / 2; e += 32) {
+      const unsigned q = tri_decode(e);
+      const int i = q & 0xff, j = q >> 8;
+      const double h0 = (i == j) ? (t1[i] + t2[i]) : 0.0;
+      lhs[e] = dot4c<NX>(uxt + i, NU, fu + j * NX, 1) + h0;
+    }
+    for (int e = lane; e < NU * NX; e += 32) {
+      const int i = e % NU, j = e / NU;
+      rhs[i + (1 + j) * K] = dot4c<NX>(uxt + i, NU, fx + j * NX, 1) + rhs[i + (1 + j) * K];
+    }
+    __syncwarp();
+    // ---- H += luu
+    for (int e = lane; e < M::D_luu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_luu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
+    __syncwarp();
+    if (second_order) {
+      if constexpr (M::VF_NSLOT > 0) {   // dynamics Hessian contraction with lambda+ (:102-110), evaluated redundantly per lane
+        double vfl[M::VF_NSLOT > 0 ? M::VF_NSLOT : 1];
+        auto st = [&](int s, double x_) { vfl[s] = x_; };
+        M::vf(xs, us, lamn, p, st);
+        if (lane == 0)
+          for (int s = 0; s < M::VF_NSLOT; ++s) vfs[s] = vfl[s];
+        __syncwarp();
+        for (int e = lane; e < M::VF_vfxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfxx_OFF + e); Cm[q.i + q.j * NX] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
+        for (int e = lane; e < M::VF_vfux_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfux_OFF + e); rhs[q.i + (1 + q.j) * K] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
+        for (int e = lane; e < M::VF_vfuu_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfuu_OFF + e); lhs[pk(q.i, q.j)] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
         __syncwarp();
       }
-      if (reg > 0.0)
-        for (int i = lane; i < NU; i += 32) lhs[pk(i, i)] += reg;
-      if (delta_c > 0.0)
-        for (int i = lane; i < NC; i += 32) lhs[pk(NU + i, NU + i)] -= delta_c;
-      // ---- park the un-negated [Qu B; c cx] in this knot's gains slot (HBM, read back after the solve), write Qu,
-      //      and negate in place: rhs = -[Qu B; c cx]                    (:129-136)
-      double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
-      double* qo = v.Qu + ((size_t)b * (v.N - 1) + t) * NU;
-      for (int e = lane; e < K * NR; e += 32) { const double w = rhs[e]; g[e] = w; rhs[e] = w * -1.0; if (e < NU) qo[e] = w; }
-      __syncwarp();
-      // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
-      int np = 0;
-      const int info = warp_ldlt_factor<K, NR>(lhs, ipiv, rhs, ws, nzlist, lane, 1e-12, np);
-      delta_c = 0.0;
-      if (info > 0) delta_c = v.opt.delta_c * dm::pow(mu, v.opt.kappa_c);
-      if (np != NU || info != 0) {
-        if (reg == 0.0) reg = (reg_last == 0.0) ? v.opt.reg_1 : jmax(v.opt.reg_min, v.opt.kappa_w_m * reg_last);
-        else reg = (reg_last == 0.0) ? v.opt.kappa_bar_w_p * reg : v.opt.kappa_w_p * reg;
-        status = 1;
-        break;
-      }
-      warp_ldlt_solve_forward<K, NR>(lhs, ipiv, rhs, nzlist, lane);
-      // ---- ineq gains to HBM                                            (:159-172)
-      double* gi = g + K * NR;
-      for (int e = lane; e < NU * NR; e += 32) {
-        const int i = e % NU, j = e / NU;
-        if (j == 0) {
-          const double al = rhs[i];
-          double cl = chil[i];
-          cl -= zl[i];
-          cl -= t1[i] * al;
-          double cu_ = chiu[i];
-          cu_ -= zu[i];
-          cu_ += t2[i] * al;
-          gi[i] = cl;
-          gi[NU + i] = cu_;
-        } else {
-          const double be = rhs[i + j * K];
-          gi[i + j * 2 * NU] = (be * t1[i]) * -1.0;
-          gi[NU + i + j * 2 * NU] = be * t2[i];
-        }
-      }
-      // ---- Vxx = beta' B + omega' cx + C ; Vx ; lambda                  (:176-189)
-      // 4 lanes per output element: partial sums over i mod 4, butterfly combine = dot4 order
-      {
-        const int g4 = lane & 3;
-        for (int e0 = 0; e0 < NX * NX; e0 += 8) {
-          const int e = e0 + (lane >> 2);
-          const int i = e % NX, j = e / NX;
-          double sa = 0.0, sb = 0.0;
-          if (e < NX * NX) {
-            for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], IPDDP_LDCG(g + q + (1 + j) * K), sa);
-            for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], IPDDP_LDCG(g + NU + q + (1 + j) * K), sb);
-          }
-          sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
-          sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
-          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
-          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
-          if (e < NX * NX && g4 == 0) {
-            double w = sa;
-            w = sb + w;
-            w += Cm[e];
-            nVxx[e] = w;
-          }
-        }
-        for (int e0 = 0; e0 < NX; e0 += 8) {
-          const int i = e0 + (lane >> 2);
-          double sa = 0.0, sb = 0.0, sc = 0.0;
-          if (i < NX) {
-            for (int q = g4; q < NC; q += 4) sc = IPDDP_FMA(IPDDP_LDCG(g + NU + q + (1 + i) * K), phi[q], sc);        // cx' phi
-            for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], IPDDP_LDCG(g + q), sa);             // beta' Qu
-            for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], IPDDP_LDCG(g + NU + q), sb);   // omega' c
-          }
-          sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
-          sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
-          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
-          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
-          sc = sc + __shfl_xor_sync(IPDDP_FULL_MASK, sc, 1);
-          sc = sc + __shfl_xor_sync(IPDDP_FULL_MASK, sc, 2);
-          if (i < NX && g4 == 0) {
-            double w = lx[i];
-            w = sc + w;
-            double lv = w;
-            w = sa + w;
-            w = sb + w;
-            w = dot4c<NX>(fx + i * NX, 1, Vx, 1) + w;
-            lv = dot4c<NX>(fx + i * NX, 1, lamn, 1) + lv;
-            nVx[i] = w;
-            nlam[i] = lv;
-          }
-        }
-      }
-      __syncwarp();
-      for (int e = lane; e < K * NR; e += 32) g[e] = rhs[e];   // eq gains replace the parked copy
-      for (int e = lane; e < NX * NX; e += 32) Vxx[e] = nVxx[e];
-      for (int e = lane; e < NX; e += 32) {
-        Vx[e] = nVx[e];
-        lamn[e] = nlam[e];
-        v.lam[((size_t)b * v.N + t) * NX + e] = nlam[e];
-      }
+      for (int e = lane; e < M::D_vcuu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcuu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
+      for (int e = lane; e < M::D_vcux_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcux_OFF + e); rhs[q.i + (1 + q.j) * K] += val(q); }
+      for (int e = lane; e < M::D_vcxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcxx_OFF + e); Cm[q.i + q.j * NX] += val(q); }
       __syncwarp();
     }
+    if (reg > 0.0)
+      for (int i = lane; i < NU; i += 32) lhs[pk(i, i)] += reg;
+    if (delta_c > 0.0)
+      for (int i = lane; i < NC; i += 32) lhs[pk(NU + i, NU + i)] -= delta_c;
+    // ---- park the un-negated [Qu B; c cx] in this knot's gains slot (HBM, read back after the solve), write Qu,
+    //      and negate in place: rhs = -[Qu B; c cx]                    (:129-136)
+    double* g = out.gains + (size_t)t * v.G;
+    double* qo = out.Qu + (size_t)t * NU;
+    for (int e = lane; e < K * NR; e += 32) { const double w = rhs[e]; g[e] = w; rhs[e] = w * -1.0; if (e < NU) qo[e] = w; }
+    __syncwarp();
+    // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
+    int np = 0;
+    const int info = warp_ldlt_factor<K, NR>(lhs, ipiv, rhs, ws, nzlist, lane, 1e-12, np, tri_lane);
+    delta_c = 0.0;
+    if (info > 0) delta_c = v.opt.delta_c * dm::pow(mu, v.opt.kappa_c);
+    if (np != NU || info != 0) return 1;   // inertia failure: the caller restarts the sweep with a larger reg
+    warp_ldlt_solve_forward<K, NR>(lhs, ipiv, rhs, nzlist, lane);
+    // ---- ineq gains to HBM                                            (:159-172)
+    double* gi = g + K * NR;
+    for (int e = lane; e < NU * NR; e += 32) {
+      const int i = e % NU, j = e / NU;
+      if (j == 0) {
+        const double al = rhs[i];
+        double cl = ra1[i] * mu;      // chi^L = mu / il, recomputed from the stored reciprocal (same operands, same bits)
+        cl -= r[R::ZL + i];
+        cl -= t1[i] * al;
+        double cu_ = ra2[i] * mu;
+        cu_ -= r[R::ZU + i];
+        cu_ += t2[i] * al;
+        gi[i] = cl;
+        gi[NU + i] = cu_;
+      } else {
+        const double be = rhs[i + j * K];
+        gi[i + j * 2 * NU] = (be * t1[i]) * -1.0;
+        gi[NU + i + j * 2 * NU] = be * t2[i];
+      }
+    }
+    // ---- Vxx = beta' B + omega' cx + C ; Vx ; lambda                  (:176-189)
+    // 4 lanes per output element: partial sums over i mod 4, butterfly combine = dot4 order
+    {
+      const int g4 = lane & 3;
+      for (int e0 = 0; e0 < NX * NX; e0 += 8) {
+        const int e = e0 + (lane >> 2);
+        const int i = e % NX, j = e / NX;
+        double sa = 0.0, sb = 0.0;
+        if (e < NX * NX) {
+          for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], IPDDP_LDCG(g + q + (1 + j) * K), sa);
+          for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], IPDDP_LDCG(g + NU + q + (1 + j) * K), sb);
+        }
+        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
+        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
+        sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
+        sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
+        if (e < NX * NX && g4 == 0) {
+          double w = sa;
+          w = sb + w;
+          w += Cm[e];
+          nVxx[e] = w;
+        }
+      }
+      for (int e0 = 0; e0 < NX; e0 += 8) {
+        const int i = e0 + (lane >> 2);
+        double sa = 0.0, sb = 0.0, sc = 0.0;
+        if (i < NX) {
+          for (int q = g4; q < NC; q += 4) sc = IPDDP_FMA(IPDDP_LDCG(g + NU + q + (1 + i) * K), phi[q], sc);        // cx' phi
+          for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], IPDDP_LDCG(g + q), sa);             // beta' Qu
+          for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], IPDDP_LDCG(g + NU + q), sb);   // omega' c
+        }
+        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
+        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
+        sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
+        sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
+        sc = sc + __shfl_xor_sync(IPDDP_FULL_MASK, sc, 1);
+        sc = sc + __shfl_xor_sync(IPDDP_FULL_MASK, sc, 2);
+        if (i < NX && g4 == 0) {
+          double w = lx[i];
+          w = sc + w;
+          double lv = w;
+          w = sa + w;
+          w = sb + w;
+          w = dot4c<NX>(fx + i * NX, 1, Vx, 1) + w;
+          lv = dot4c<NX>(fx + i * NX, 1, lamn, 1) + lv;
+          nVx[i] = w;
+          nlam[i] = lv;
+        }
+      }
+    }
+    __syncwarp();
+    for (int e = lane; e < K * NR; e += 32) g[e] = rhs[e];   // eq gains replace the parked copy
+    for (int e = lane; e < NX * NX; e += 32) Vxx[e] = nVxx[e];
+    for (int e = lane; e < NX; e += 32) {
+      Vx[e] = nVx[e];
+      lamn[e] = nlam[e];
+      out.lam[(size_t)t * NX + e] = nlam[e];
+    }
+    __syncwarp();
+  }
+  return 0;
+}
+
+template <class M>
+__global__ void __launch_bounds__(32, 20) k_backward(DevView v, const int* list, int n_list) {
+  IPDDP_DYN_SMEM(double, sm);
+  const int lane = threadIdx.x;
+  const int inst = blockIdx.x;
+  if (inst >= n_list) return;
+  const int b = list[inst];
+  const int Nb = v.horizon[b];
+  const int set = v.nomsel[b];
+  bw_setup<M>(sm, lane);
+  const double mu = v.sdv(SD_MU, b);
+  const double reg_last = v.sdv(SD_REG_LAST, b);
+  const BwOut out = {v.gains + (size_t)b * (v.N - 1) * v.G, v.Qu + (size_t)b * (v.N - 1) * M::NU,
+                     v.lam + (size_t)b * v.N * M::NX};
+  double reg = 0.0, dual_num = 0.0;
+  int status = 0, nsweep = 0, nkkt = 0;
+  while (reg <= v.opt.reg_max) {
+    nsweep++;
+    status = bw_sweep<M>(v, b, Nb, set, reg, mu, sm, out, lane, nkkt, dual_num);
     if (status == 0) break;
+    reg = bw_next_reg(v, reg, reg_last);
   }
   if (lane == 0) {
+    v.sdv(SD_REG_LAST, b) = reg;
+    v.sdv(SD_DUAL_NUM, b) = dual_num;
+    v.siv(SI_STATUS, b) = status;
+    v.siv(SI_NBACK, b) += 1;
+    v.siv(SI_NSWEEP, b) += nsweep;
+    v.siv(SI_NKKT, b) += nkkt;
+  }
+}
+
+// Speculative restarts for rounds with few active instances (the lock-step tail): one CTA of BWS_WARPS warps per
+// instance, warp w runs the sweep with the w-th value of the regularisation schedule (the schedule only depends on
+// reg_last, so it is known in advance); the first sweep IN SCHEDULE ORDER that passes every inertia test is the one the
+// sequential loop would have ended with, and the counters add up the sweeps the sequential loop would have run.
+// Warp 0 writes the instance's gains / Qu / lambda in place, the others into a private pool (DevView::spec_bw) that
+// is copied over if one of them wins.
+constexpr int BWS_WARPS = 4;
+
+template <class M>
+__global__ void __launch_bounds__(BWS_WARPS * 32) k_backward_spec(DevView v, const int* list, int n_list) {
+  IPDDP_DYN_SMEM(double, sm_all);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inst = blockIdx.x;
+  if (inst >= n_list) return;
+  const int b = list[inst];
+  const int Nb = v.horizon[b];
+  const int set = v.nomsel[b];
+  constexpr int WD = BwLayout<M>::BYTES / 8;
+  double* sm = sm_all + (size_t)warp * WD;
+  double* res_dn = sm_all + (size_t)BWS_WARPS * WD;                 // [BWS_WARPS] dual_num
+  int* res_i = reinterpret_cast<int*>(res_dn + BWS_WARPS);          // [BWS_WARPS][2]: verdict (0 ok, 1 failed, 3 not run), nkkt
+  bw_setup<M>(sm, lane);
+  const double mu = v.sdv(SD_MU, b);
+  const double reg_last = v.sdv(SD_REG_LAST, b);
+  const size_t G1 = (size_t)(v.N - 1) * v.G, Q1 = (size_t)(v.N - 1) * M::NU, L1 = (size_t)v.N * M::NX;
+  BwOut out = {v.gains + (size_t)b * G1, v.Qu + (size_t)b * Q1, v.lam + (size_t)b * L1};
+  const BwOut main_out = out;
+  if (warp > 0) {
+    double* pool = v.spec_bw + ((size_t)inst * (BWS_WARPS - 1) + (warp - 1)) * (G1 + Q1 + L1);
+    out.gains = pool; out.Qu = pool + G1; out.lam = pool + G1 + Q1;
+  }
+  double reg = 0.0, dual_num = 0.0;     // every thread tracks the schedule identically
+  int status = 0, nsweep = 0, nkkt = 0;
+  for (;;) {
+    double mine = reg;
+    for (int q = 0; q < warp; ++q) mine = bw_next_reg(v, mine, reg_last);
+    // candidates after the first one that exceeds reg_max are never reached by the sequential loop
+    bool reachable = true;
+    {
+      double r = reg;
+      for (int q = 0; q < warp; ++q) { if (!(r <= v.opt.reg_max)) reachable = false; r = bw_next_reg(v, r, reg_last); }
+    }
+    int verdict = 3, kk = 0;
+    double dn = 0.0;
+    if (reachable && mine <= v.opt.reg_max) verdict = bw_sweep<M>(v, b, Nb, set, mine, mu, sm, out, lane, kk, dn);
+    if (lane == 0) { res_i[2 * warp] = verdict; res_i[2 * warp + 1] = kk; res_dn[warp] = dn; }
+    __syncthreads();
+    int winner = -1;
+    bool ended = false;
+    for (int q = 0; q < BWS_WARPS; ++q) {
+      const int r = res_i[2 * q];
+      if (r == 3) { ended = true; status = 1; break; }     // reg > reg_max: the while condition of the sequential loop
+      nsweep++;
+      nkkt += res_i[2 * q + 1];
+      dual_num = res_dn[q];
+      if (r == 0) { winner = q; status = 0; break; }
+      status = 1;
+      reg = bw_next_reg(v, reg, reg_last);
+    }
+    if (winner > 0) {     // copy the winning sweep's outputs over the instance's arrays
+      const double* pool = v.spec_bw + ((size_t)inst * (BWS_WARPS - 1) + (winner - 1)) * (G1 + Q1 + L1);
+      const int ng = (Nb - 1) * v.G, nq = (Nb - 1) * M::NU, nl = Nb * M::NX;
+      for (int e = threadIdx.x; e < ng; e += BWS_WARPS * 32) main_out.gains[e] = pool[e];
+      for (int e = threadIdx.x; e < nq; e += BWS_WARPS * 32) main_out.Qu[e] = pool[G1 + e];
+      for (int e = threadIdx.x; e < nl; e += BWS_WARPS * 32) main_out.lam[e] = pool[G1 + Q1 + e];
+    }
+    __syncthreads();
+    if (winner >= 0 || ended) break;
+    if (!(reg <= v.opt.reg_max)) { status = 1; break; }
+  }
+  if (threadIdx.x == 0) {
     v.sdv(SD_REG_LAST, b) = reg;
     v.sdv(SD_DUAL_NUM, b) = dual_num;
     v.siv(SI_STATUS, b) = status;

@@ -61,6 +61,8 @@ struct DevView {
   double* trace;             // [B][trace_cap][IPDDP_TRACE_COLS]
   int trace_cap;
   int fw_spec_max;           // rounds with at most this many active instances use k_forward_spec
+  int bw_spec_max;           // rounds with at most this many active instances use k_backward_spec
+  double* spec_bw;           // [bw_spec_max][BWS_WARPS-1][(N-1)(G+nu) + N nx] private gains / Qu / lambda of speculative sweeps
   double* spec_traj;         // [fw_spec_max][FWS_WARPS][N][TR] private trial records of the speculative line search
   ipddp_options opt;
 

@@ -8,27 +8,41 @@
 // unblocked LAPACK algorithms (rank-1 update as fma(x_i, -d*x_j, a_ij) like OpenBLAS' dsyr; everything
 // else plain IEEE ops), so factors, pivot sequence, `info` and the solution do not depend on the lane mapping.
 //
-// How the work is mapped (the kernel is instruction-issue bound):
-//   * pivot searches: |a| is an order-preserving 64-bit key; two REDUX.MAX (high / low word) + ballots give
-//     the maximum and the set of ties, from which IDAMAX's first-maximum rule and dsytf2_rook's
-//     "row segment first, column segment only if strictly larger" rule are applied on the tie mask;
+// The kernel that calls this is bound by instruction issue and dependent-instruction latency, not by
+// FLOPs or bytes, so the code is organised around the pivot steps that IPDDP2's KKT matrices
+// actually take:
+//   * ldlt_step_fast handles a pivot column k < 32 that ends in a 1x1 pivot either without interchange or with
+//     the single interchange dsytf2_rook finds in its first rook iteration (> 90 % of the steps).  It keeps the
+//     pivot column in registers from the search to the elimination, decides "no interchange" with one warp vote
+//     (|a_kk| >= alpha*|a_ik| for all i  <=>  |a_kk| >= alpha*colmax, since rounding is monotone) and the rook
+//     acceptance |a_pp| >= alpha*rowmax the same way, finds imax with one REDUX.MAX on the high words (a second
+//     one only on ties), and performs the symmetric interchange as stores of register values.  Anything else
+//     (2x2 pivots, longer rook searches, NaNs, tiny pivots, singular columns, k >= 32) falls through -- before
+//     any memory is modified -- to ldlt_step, the general implementation;
 //   * trailing updates are SPARSE: pivot columns of IPDDP2 KKT matrices are mostly zero (measured: 23 %
 //     non-zero entries, 7 % of the rank-1 element updates do arithmetic), so the non-zero row indices are
 //     compacted with a ballot and only the nnz(nnz+1)/2 affected elements are touched.  Skipped
 //     elements would receive fma(0, t, a) = a, i.e. the skip is exact for finite data (only the sign of
-//     an exact zero can differ).  The row lists are kept per pivot column and reused by both triangular
-//     solves (their skipped terms are fma(0, b, s) = s as well);
+//     an exact zero can differ).  The non-zero row MASK of every pivot column is kept and reused by the second
+//     triangular solve (its skipped terms are fma(0, b, s) = s as well);
 //   * dsytrs_rook's first loop (interchange, rank-1 downdate of B, scaling) runs in the same k-descending
-//     pivot order as the factorisation, so it is fused into it: the multipliers are still in registers and
-//     1/a_kk is not recomputed.  Only the U' solve is a separate pass;
+//     pivot order as the factorisation, so it is fused into it: the multipliers are still in registers.
+//     The scaling B(k,:) *= 1/a_kk of a 1x1 pivot row is deferred (row k is not touched again by the first loop)
+//     and applied to all rows at once before the second loop; only the U' solve is a separate pass;
 //   * the inertia of D is counted while the pivots are produced (a D block is final when it is chosen);
 //   * rows >= 32 (second slot per lane) are only touched while the pivot index is >= 32.
 #pragma once
 #include "kernels_common.cuh"
 
-namespace ipk {
+// test-only instrumentation (emulator builds with -DIPDDP_LDLT_STATS): how many pivot steps take which path
+#if defined(IPDDP_SIMT_EMU) && defined(IPDDP_LDLT_STATS)
+extern "C" long long g_ipddp_ldlt_steps[3];
+#define IPDDP_LDLT_COUNT(w) do { if (lane == 0) __atomic_fetch_add(&g_ipddp_ldlt_steps[w], 1, __ATOMIC_RELAXED); } while (0)
+#else
+#define IPDDP_LDLT_COUNT(w) do { } while (0)
+#endif
 
-constexpr int NZCAP = 8;          // non-zero rows remembered per pivot column; more => dense fallback (count 255)
+namespace ipk {
 
 IPDDP_D int coff(int j) { return (j * (j + 1)) >> 1; }
 IPDDP_D int pk(int i, int j) { return i + coff(j); }   // requires i <= j
@@ -76,15 +90,17 @@ IPDDP_D void warp_sym_swap(double* A, int a, int b, int lane) {
   }
 }
 
-// compacts the indices i (< 64) flagged by (f0 at lane, f1 at lane+32) into list[] ascending; returns count
+// compacts the indices i (< 64) flagged by (f0 at lane, f1 at lane+32) into list[] ascending; returns count,
+// m0 / m1 = the flag masks
 template <bool TWO>
-IPDDP_D int warp_compact(bool f0, bool f1, unsigned char* list, int lane) {
-  const unsigned m0 = __ballot_sync(IPDDP_FULL_MASK, f0);
+IPDDP_D int warp_compact(bool f0, bool f1, unsigned char* list, int lane, unsigned& m0, unsigned& m1) {
+  m0 = __ballot_sync(IPDDP_FULL_MASK, f0);
+  m1 = 0u;
   const unsigned lt = (1u << lane) - 1u;
   if (f0) list[__popc(m0 & lt)] = (unsigned char)lane;
   int n = __popc(m0);
   if (TWO) {
-    const unsigned m1 = __ballot_sync(IPDDP_FULL_MASK, f1);
+    m1 = __ballot_sync(IPDDP_FULL_MASK, f1);
     if (f1) list[n + __popc(m1 & lt)] = (unsigned char)(lane + 32);
     n += __popc(m1);
   }
@@ -95,17 +111,35 @@ template <int NR> IPDDP_D void warp_swap_rows(double* Bm, int ld, int a, int b, 
   if (lane < NR) { const double t = Bm[a + lane * ld]; Bm[a + lane * ld] = Bm[b + lane * ld]; Bm[b + lane * ld] = t; }
 }
 
-// Scratch layout used by the factorisation: w: 4K doubles; list: K bytes (current compaction);
-// nzc: K bytes (count per pivot column, 255 = dense), nzl: K*NZCAP bytes (row lists per pivot column).
+// Scratch used by the factorisation and kept for the second solve (base must be 8-byte aligned):
+// dinv: K doubles (deferred 1/a_kk row scalings, 1.0 where the step scaled in place), nzlo / nzhi: K uint32 each
+// (non-zero multiplier rows 0..31 / 32..63 of every pivot column), list: K bytes (current compaction).
+// The 2x2 pivot update additionally needs w: 4K doubles, passed separately.
 template <int K> struct LdltScratch {
-  static constexpr int BYTES = ((K + K + K * NZCAP + 15) / 16) * 16;
+  static constexpr int DINV = 0;
+  static constexpr int NZLO = DINV + K * 8;
+  static constexpr int NZHI = NZLO + K * 4;
+  static constexpr int LIST = NZHI + K * 4;
+  static constexpr int BYTES = ((LIST + K + 15) / 16) * 16;
+  static IPDDP_D double* dinv(unsigned char* s) { return reinterpret_cast<double*>(s + DINV); }
+  static IPDDP_D unsigned* nzlo(unsigned char* s) { return reinterpret_cast<unsigned*>(s + NZLO); }
+  static IPDDP_D unsigned* nzhi(unsigned char* s) { return reinterpret_cast<unsigned*>(s + NZHI); }
+  static IPDDP_D unsigned char* list(unsigned char* s) { return s + LIST; }
+  static IPDDP_D const double* dinv(const unsigned char* s) { return reinterpret_cast<const double*>(s + DINV); }
+  static IPDDP_D const unsigned* nzlo(const unsigned char* s) { return reinterpret_cast<const unsigned*>(s + NZLO); }
+  static IPDDP_D const unsigned* nzhi(const unsigned char* s) { return reinterpret_cast<const unsigned*>(s + NZHI); }
 };
 
-// One pivot step (column k) of dsytf2_rook('U') fused with dsytrs_rook's first loop on Bm.
+// General pivot step (column k) of dsytf2_rook('U') fused with dsytrs_rook's first loop on Bm.
 // Returns kstep (1 or 2).  TWO = rows >= 32 may be involved (k >= 32).
 template <int K, int NR, bool TWO>
-IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsigned char* list, unsigned char* nzc,
-                      unsigned char* nzl, int lane, unsigned tri_lane, double tol, int& info, int& np) {
+IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsigned char* scratch, int lane,
+                      unsigned tri_lane, double tol, int& info, int& np) {
+  typedef LdltScratch<K> S;
+  double* dinv = S::dinv(scratch);
+  unsigned* nzlo = S::nzlo(scratch);
+  unsigned* nzhi = S::nzhi(scratch);
+  unsigned char* list = S::list(scratch);
   const double alpha = 0.6403882032022076;   // (1 + sqrt(17)) / 8
   const double sfmin = 2.2250738585072014e-308;
   const int i0 = lane, i1 = lane + 32;
@@ -123,7 +157,7 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
   if (fmax(absakk, colmax) == 0.0) {
     // exactly singular column: no elimination (LAPACK sets info and moves on); dsytrs would divide by zero
     if (info == 0) info = k + 1;
-    if (lane == 0) { ipiv[k] = k + 1; nzc[k] = 0; }
+    if (lane == 0) { ipiv[k] = k + 1; nzlo[k] = 0u; nzhi[k] = 0u; dinv[k] = 1.0; }
     return 1;
   }
   if (absakk < alpha * colmax) {
@@ -164,6 +198,7 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
     if (lane == 0) ipiv[k] = kp + 1;
     if (akk > tol) np += 1;
     int nnz = 0;
+    unsigned m0 = 0u, m1 = 0u;
     double x0 = 0.0, x1 = 0.0;
     const bool big = fabs(akk) >= sfmin;
     const double rinv = 1.0 / akk;            // used by the column scaling (big) and by dsytrs' B(k,:) scaling
@@ -172,7 +207,7 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
       double* x = A + ck;
       x0 = (i0 < k) ? x[i0] : 0.0;
       x1 = (TWO && i1 < k) ? x[i1] : 0.0;
-      nnz = warp_compact<TWO>(x0 != 0.0, x1 != 0.0, list, lane);
+      nnz = warp_compact<TWO>(x0 != 0.0, x1 != 0.0, list, lane, m0, m1);
       if (nnz > 0) {
         __syncwarp();
         if (!big) {   // tiny pivot: LAPACK divides the column first, then updates with -akk
@@ -182,7 +217,7 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
         }
         const int P = (nnz * (nnz + 1)) >> 1;
         for (int pp = lane; pp < P; pp += 32) {
-          const unsigned q = (pp < 32) ? tri_lane : tri_decode(pp);
+          const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode(pp);
           const int i = list[q & 0xff], j = list[q >> 8];
           const int e = coff(j) + i;
           A[e] = IPDDP_FMA(x[i], -d11 * x[j], A[e]);
@@ -192,10 +227,9 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
           if (x0 != 0.0) { x0 = x0 * d11; x[i0] = x0; }
           if (TWO && x1 != 0.0) { x1 = x1 * d11; x[i1] = x1; }
         }
-        if (lane < nnz && lane < NZCAP) nzl[k * NZCAP + lane] = list[lane];
       }
     }
-    if (lane == 0) nzc[k] = (unsigned char)(nnz <= NZCAP ? nnz : 255);
+    if (lane == 0) { nzlo[k] = m0; nzhi[k] = m1; dinv[k] = 1.0; }
     // dsytrs first loop for this pivot: B(0:k-1,:) -= x * B(k,:), then B(k,:) *= 1/akk
     if (x0 != 0.0) {
 #pragma unroll
@@ -234,6 +268,7 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
       }
     }
     int nnz = 0;
+    unsigned m0 = 0u, m1 = 0u;
     bool f[2] = {false, false};
     if (k > 1) {
       const int m = k - 1;   // rows/columns 0..m-1 get updated
@@ -255,11 +290,11 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
           }
         }
       }
-      nnz = warp_compact<TWO>(f[0], f[1], list, lane);
+      nnz = warp_compact<TWO>(f[0], f[1], list, lane, m0, m1);
       __syncwarp();
       const int P = (nnz * (nnz + 1)) >> 1;
       for (int pp = lane; pp < P; pp += 32) {
-        const unsigned q = (pp < 32) ? tri_lane : tri_decode(pp);
+        const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode(pp);
         const int i = list[q & 0xff], j = list[q >> 8];
         const int e = coff(j) + i;
         A[e] = A[e] - rk[i] * wk[j] - rkm1[i] * wkm1[j];
@@ -272,10 +307,9 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
           xkm1[j] = wkm1[j] / d12;
         }
       }
-      if (lane < nnz && lane < NZCAP) { nzl[k * NZCAP + lane] = list[lane]; nzl[(k - 1) * NZCAP + lane] = list[lane]; }
       __syncwarp();
     }
-    if (lane == 0) { const unsigned char c = (unsigned char)(nnz <= NZCAP ? nnz : 255); nzc[k] = c; nzc[k - 1] = c; }
+    if (lane == 0) { nzlo[k] = m0; nzhi[k] = m1; nzlo[k - 1] = m0; nzhi[k - 1] = m1; dinv[k] = 1.0; dinv[k - 1] = 1.0; }
     // dsytrs first loop for the 2x2 block: two rank-1 downdates of B, then the 2x2 solve
 #pragma unroll
     for (int s = 0; s < (TWO ? 2 : 1); ++s) {
@@ -305,60 +339,175 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
   return kstep;
 }
 
+// Fast pivot step for 0 <= k < 32 (see the header).  Returns false -- with nothing modified -- if the step is not a
+// 1x1 pivot reached with at most one interchange, or if NaNs / tiny pivots / singular columns are involved.
+template <int K, int NR>
+IPDDP_D bool ldlt_step_fast(int k, double* A, int* ipiv, double* Bm, unsigned char* scratch, int lane, unsigned tri_lane,
+                            double tol, int& np) {
+  typedef LdltScratch<K> S;
+  const double alpha = 0.6403882032022076;   // (1 + sqrt(17)) / 8
+  const double sfmin = 2.2250738585072014e-308;
+  const int ck = coff(k);
+  const bool in = lane < k;
+  double x = in ? A[ck + lane] : 0.0;        // pivot column, rows 0..k-1
+  double piv = A[ck + k];
+  int kp = k;
+  const bool keep = __all_sync(IPDDP_FULL_MASK, fabs(piv) >= alpha * fabs(x));   // false on any NaN
+  double xold = 0.0, pold = 0.0;
+  int ci = 0;
+  if (!keep) {
+    if (__any_sync(IPDDP_FULL_MASK, x != x) || piv != piv) return false;
+    // imax: first row attaining max |x|
+    const double ax = fabs(x);
+    const unsigned hi = in ? (unsigned)__double2hiint(ax) : 0u;
+    const unsigned mh = __reduce_max_sync(IPDDP_FULL_MASK, hi);
+    unsigned cand = __ballot_sync(IPDDP_FULL_MASK, in && hi == mh);
+    if (cand & (cand - 1u)) {   // several rows share the high word: compare the low words among them
+      const unsigned lo = (in && hi == mh) ? (unsigned)__double2loint(ax) : 0u;
+      const unsigned ml = __reduce_max_sync(IPDDP_FULL_MASK, lo);
+      cand = __ballot_sync(IPDDP_FULL_MASK, in && hi == mh && lo == ml);
+    }
+    const int imax = __ffs(cand) - 1;
+    ci = coff(imax);
+    // row / column imax of the leading (k+1) x (k+1) block, signed: it becomes the pivot column after the interchange
+    const bool vr = lane <= k && lane != imax;
+    const double a = vr ? (lane < imax ? A[ci + lane] : A[coff(lane) + imax]) : 0.0;
+    const double aii = A[ci + imax];
+    // rook acceptance of the first candidate: |a_ii| >= alpha * rowmax  (false on any NaN)
+    if (!__all_sync(IPDDP_FULL_MASK, fabs(aii) >= alpha * fabs(a))) return false;
+    xold = x; pold = piv;
+    x = (lane == imax) ? x : (in ? a : 0.0);
+    piv = aii;
+    kp = imax;
+  }
+  const unsigned nzm = __ballot_sync(IPDDP_FULL_MASK, x != 0.0);
+  if (!(fabs(piv) >= sfmin)) return false;   // singular column (piv == 0, nzm == 0), tiny pivot
+  // ---- committed: 1x1 pivot piv, interchange k <-> kp
+  const double rinv = 1.0 / piv;
+  if (piv > tol) np += 1;
+  if (lane == 0) { ipiv[k] = kp + 1; S::nzlo(scratch)[k] = nzm; S::nzhi(scratch)[k] = 0u; S::dinv(scratch)[k] = rinv; }
+  if (kp != k) {
+    // symmetric interchange as stores of register values: row / column kp receives the old column k
+    if (in && lane != kp) A[(lane < kp) ? ci + lane : coff(lane) + kp] = xold;
+    if (lane == 0) { A[ci + kp] = pold; A[ck + k] = piv; }
+    warp_swap_rows<NR>(Bm, K, k, kp, lane);
+  }
+  if (nzm == 0u) return true;                // nothing to eliminate; B(k,:) scaling is deferred
+  unsigned char* list = S::list(scratch);
+  if (x != 0.0) list[__popc(nzm & ((1u << lane) - 1u))] = (unsigned char)lane;
+  __syncwarp();
+  const int nnz = __popc(nzm);
+  const int P = (nnz * (nnz + 1)) >> 1;
+  for (int p0 = 0; p0 < P; p0 += 32) {
+    const int pp = p0 + lane;
+    const bool act = pp < P;
+    const unsigned q = (p0 == 0) ? (tri_lane & 0xffffu) : (p0 == 32) ? (tri_lane >> 16) : tri_decode(act ? pp : 0);
+    const int i = act ? list[q & 0xff] : 0, j = act ? list[q >> 8] : 0;
+    const double xi = __shfl_sync(IPDDP_FULL_MASK, x, i), xj = __shfl_sync(IPDDP_FULL_MASK, x, j);
+    if (act) {
+      const int e = coff(j) + i;
+      A[e] = IPDDP_FMA(xi, -rinv * xj, A[e]);
+    }
+  }
+  if (x != 0.0) {
+    const double xs = x * rinv;                // multiplier
+    A[ck + lane] = xs;
+    // dsytrs first loop for this pivot: B(0:k-1,:) -= xs * B(k,:)   (B(k,:) *= 1/piv is deferred: dinv[k])
+#pragma unroll
+    for (int j = 0; j < NR; ++j) Bm[lane + j * K] = IPDDP_FMA(xs, -Bm[k + j * K], Bm[lane + j * K]);
+  } else if (kp != k && in) {
+    A[ck + lane] = 0.0;                        // the interchanged column's zeros
+  }
+  __syncwarp();
+  return true;
+}
+
 // dsytf2_rook('U') on the packed matrix A of order K, fused with the first (U D) loop of dsytrs_rook on
 // the NR right-hand sides in Bm (column-major, leading dimension K).  Returns info; np_out = number of
 // positive eigenvalues of D.  If info != 0 the contents of Bm are meaningless (the caller restarts).
+// scratch: LdltScratch<K>::BYTES, 8-byte aligned.
+// (row, column) pairs of the packed triangle elements `lane` and `lane + 32`: one register serves trailing updates of
+// up to 10 non-zero rows (55 pairs) without decoding.  Loop invariant: compute once per kernel.
+IPDDP_D unsigned ldlt_tri_lane(int lane) { return tri_decode(lane) | (tri_decode(lane + 32) << 16); }
+
 template <int K, int NR>
 IPDDP_D int warp_ldlt_factor(double* A, int* ipiv, double* Bm, double* w, unsigned char* scratch, int lane, double tol,
-                             int& np_out) {
-  unsigned char* list = scratch;
-  unsigned char* nzc = scratch + K;
-  unsigned char* nzl = scratch + 2 * K;
-  const unsigned tri_lane = tri_decode(lane);
+                             int& np_out, unsigned tri_lane) {
   int info = 0, np = 0;
   int k = K - 1;
   if (K > 32) {
-    while (k >= 32) k -= ldlt_step<K, NR, true>(k, A, ipiv, Bm, w, list, nzc, nzl, lane, tri_lane, tol, info, np);
+    while (k >= 32) k -= ldlt_step<K, NR, true>(k, A, ipiv, Bm, w, scratch, lane, tri_lane, tol, info, np);
   }
-  while (k >= 0) k -= ldlt_step<K, NR, false>(k, A, ipiv, Bm, w, list, nzc, nzl, lane, tri_lane, tol, info, np);
+  while (k >= 0) {
+    if (ldlt_step_fast<K, NR>(k, A, ipiv, Bm, scratch, lane, tri_lane, tol, np)) {
+      IPDDP_LDLT_COUNT(0);
+      k -= 1;
+      continue;
+    }
+    const int ks = ldlt_step<K, NR, false>(k, A, ipiv, Bm, w, scratch, lane, tri_lane, tol, info, np);
+    IPDDP_LDLT_COUNT(ks);
+    k -= ks;
+  }
   __syncwarp();
   np_out = np;
   return info;
 }
 
-// second loop of dsytrs_rook('U'): U' X = B, k ascending.  4 lanes per right-hand side accumulate the
-// dgemv('T') dot product in the dot4 order (partial sums by i mod 4, ascending i, 2-step butterfly);
-// zero multipliers are skipped through the per-column row lists.
+// second loop of dsytrs_rook('U'): U' X = B, k ascending, preceded by the deferred row scalings of the first loop.
+// 4 lanes per right-hand side accumulate the dgemv('T') dot product in the dot4 order (partial sums by i mod 4,
+// ascending i, 2-step butterfly); zero multipliers are skipped through the per-column row masks.
 template <int K, int NR>
 IPDDP_D void warp_ldlt_solve_forward(const double* A, const int* ipiv, double* Bm, const unsigned char* scratch, int lane) {
-  const unsigned char* nzc = scratch + K;
-  const unsigned char* nzl = scratch + 2 * K;
-  const int g = lane & 3;
+  typedef LdltScratch<K> S;
+  const double* dinv = S::dinv(scratch);
+  const unsigned* nzlo = S::nzlo(scratch);
+  const unsigned* nzhi = S::nzhi(scratch);
   static_assert(NR <= 8, "at most 8 right-hand sides");
+#pragma unroll
+  for (int s = 0; s < (K > 32 ? 2 : 1); ++s) {
+    const int r = lane + 32 * s;
+    if (r < K) {
+      const double d = dinv[r];
+#pragma unroll
+      for (int j = 0; j < NR; ++j) Bm[r + j * K] = Bm[r + j * K] * d;
+    }
+  }
+  __syncwarp();
+  const int g = lane & 3;
   const int j = lane >> 2;
   const bool act = j < NR;
+  const unsigned gm = 0x11111111u << g;
   double* bj = Bm + (act ? j : 0) * K;
   int k = 0;
   while (k < K) {
     const bool one = ipiv[k] > 0;
     if (k > 0) {
-      const int cnt = nzc[k];
-      if (cnt != 0) {
+      const unsigned mlo = nzlo[k], mhi = (K > 32) ? nzhi[k] : 0u;
+      if ((mlo | mhi) != 0u) {
         const double* xa = A + coff(k);
         const double* xb = A + coff(k + (one ? 0 : 1));
         double sa = 0.0, sb = 0.0;
-        if (cnt != 255) {
-          for (int r = 0; r < cnt; ++r) {
-            const int i = nzl[k * NZCAP + r];
-            if (act && (i & 3) == g) {
+        if (act) {
+          unsigned m = mlo & gm;
+          while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1u;
+            const double bv = bj[i];
+            sa = IPDDP_FMA(xa[i], bv, sa);
+            if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
+          }
+          if (K > 32) {
+            m = mhi & gm;
+            while (m) {
+              const int i = 32 + __ffs(m) - 1;
+              m &= m - 1u;
               const double bv = bj[i];
               sa = IPDDP_FMA(xa[i], bv, sa);
               if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
             }
           }
-        } else if (act) {
-          for (int i = g; i < k; i += 4) { const double bv = bj[i]; sa = IPDDP_FMA(xa[i], bv, sa); if (!one) sb = IPDDP_FMA(xb[i], bv, sb); }
         }
+        __syncwarp();
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
         if (!one) {

@@ -21,6 +21,11 @@ template <class M> struct Launch {
   }
   static void backward(const DevView& v, const int* list, int n, cudaStream_t s) {
     if (n <= 0) return;
+    if (n <= v.bw_spec_max) {
+      const size_t smem = (size_t)BWS_WARPS * BwLayout<M>::BYTES + BWS_WARPS * 8 + BWS_WARPS * 2 * 4;
+      IPDDP_LAUNCH((k_backward_spec<M>), n, BWS_WARPS * 32, smem, s, v, list, n);
+      return;
+    }
     IPDDP_LAUNCH((k_backward<M>), n, 32, BwLayout<M>::BYTES, s, v, list, n);
   }
   static void check(const DevView& v, const int* list, int n, int* list_next, int* list_fwd, int* counters,
@@ -48,6 +53,10 @@ template <class M> struct Launch {
     if (cudaFuncSetAttribute(k_forward<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_forward_spec<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_check<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
+    // the sweep is occupancy bound through shared memory: ask for the largest shared-memory carveout
+    if (cudaFuncSetAttribute(k_backward<M>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_backward_spec<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             BWS_WARPS * BwLayout<M>::BYTES + 256) != cudaSuccess) return -1;
     if (BwLayout<M>::BYTES > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k_backward<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            BwLayout<M>::BYTES);

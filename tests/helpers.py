@@ -173,8 +173,17 @@ def ldlt_parity(lib, oracle, rng, nmat=200, nmax=35, device=0):
             continue
         mats = []
         for i in range(nmat):
-            kind = i % 4
-            if kind == 0 or n < 4:
+            kind = i % 6
+            if kind == 4:     # small integers: many equal magnitudes (first-index tie rules), exact zeros, singular columns
+                M = rng.integers(-2, 3, size=(n, n)).astype(np.float64) * (rng.uniform(size=(n, n)) < 0.5)
+                M = np.triu(M) + np.triu(M, 1).T
+            elif kind == 5 and n >= 4:   # IPDDP-like KKT: diagonal H (wide dynamic range) + sparse constraint rows, zero block
+                m = max(1, (3 * n) // 5); p = n - m
+                H = np.diag(10.0 ** rng.uniform(-8, 8, m))
+                H[0, 1] = H[1, 0] = rng.standard_normal()
+                A = rng.integers(-1, 2, size=(p, m)).astype(np.float64) * (rng.uniform(size=(p, m)) < 0.2) * rng.uniform(0.5, 2.0, (p, m))
+                M = np.zeros((n, n)); M[:m, :m] = H; M[:m, m:] = A.T; M[m:, :m] = A
+            elif kind == 0 or n < 4:
                 M = rng.standard_normal((n, n)); M = M + M.T
             elif kind == 1:
                 m = max(1, (2 * n) // 3); p = n - m

@@ -27,14 +27,16 @@ def test_emulated_full_solve(emu, oracle_mod, wl, B, N, maxit):
 
 
 @pytest.mark.parametrize("wl,B,N,maxit", [("cartpole", 2, 9, 25), ("concar", 3, 11, 60), ("pushing", 2, 9, 30)])
-def test_emulated_forward_one_warp_per_instance(emu, oracle_mod, wl, B, N, maxit):
-    """The small batches above all take the speculative forward kernel (k_forward_spec, <= 148 active instances);
-    this forces the bulk kernel (k_forward) on the same problems."""
+def test_emulated_bulk_kernels(emu, oracle_mod, wl, B, N, maxit):
+    """The small batches above all take the speculative kernels (k_forward_spec, k_backward_spec: few active
+    instances); this forces the bulk kernels (k_forward, k_backward) on the same problems."""
     emu.L.ipddp_set_tuning(None, b"fw_spec_max", 0)
+    emu.L.ipddp_set_tuning(None, b"bw_spec_max", 0)
     try:
         helpers.full_solve_parity(emu, oracle_mod, wl, B, N, maxit=maxit, n_trace=B)
     finally:
         emu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
+        emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
 
 
 def test_emulated_varying_horizon(emu, oracle_mod):
