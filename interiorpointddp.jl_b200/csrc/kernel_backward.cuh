@@ -151,6 +151,11 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
   for (int t = Nb - 2; t >= 0; --t) {
     nkkt++;
     const double* r = v.rec(set, b, t);
+    if (t > 0) {   // the next knot's record and tile sectors: pull them towards L2 while this knot is factorised
+      const double* rn = v.rec(set, b, t - 1);
+      if (lane * 16 < R::SIZE) IPDDP_PREFETCH_L2(rn + lane * 16);
+      for (int e = lane; e < M::D_NSLOT; e += 32) IPDDP_PREFETCH_L2(v.tile + ((size_t)b * M::D_NSLOT + e) * v.N + (t - 1));
+    }
     // ---- stage inputs
     for (int e = lane; e < M::D_NSLOT; e += 32) tile[e] = v.tile[((size_t)b * M::D_NSLOT + e) * v.N + t];
     if constexpr (M::VF_NSLOT > 0) {
@@ -309,8 +314,16 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
         const int i = e % NX, j = e / NX;
         double sa = 0.0, sb = 0.0;
         if (e < NX * NX) {
-          for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], IPDDP_LDCG(g + q + (1 + j) * K), sa);
-          for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], IPDDP_LDCG(g + NU + q + (1 + j) * K), sb);
+          // fully unrolled with the loads of the parked copy (L2 hits) issued ahead of the FMA chains
+          double pu[(NU + 3) / 4 > 0 ? (NU + 3) / 4 : 1], pc[(NC + 3) / 4 > 0 ? (NC + 3) / 4 : 1];
+#pragma unroll
+          for (int qq = 0; qq < (NU + 3) / 4; ++qq) { const int q = g4 + 4 * qq; pu[qq] = (q < NU) ? IPDDP_LDCG(g + q + (1 + j) * K) : 0.0; }
+#pragma unroll
+          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; pc[qq] = (q < NC) ? IPDDP_LDCG(g + NU + q + (1 + j) * K) : 0.0; }
+#pragma unroll
+          for (int qq = 0; qq < (NU + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NU) sa = IPDDP_FMA(rhs[q + (1 + i) * K], pu[qq], sa); }
+#pragma unroll
+          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NC) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], pc[qq], sb); }
         }
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
@@ -327,9 +340,19 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
         const int i = e0 + (lane >> 2);
         double sa = 0.0, sb = 0.0, sc = 0.0;
         if (i < NX) {
-          for (int q = g4; q < NC; q += 4) sc = IPDDP_FMA(IPDDP_LDCG(g + NU + q + (1 + i) * K), phi[q], sc);        // cx' phi
-          for (int q = g4; q < NU; q += 4) sa = IPDDP_FMA(rhs[q + (1 + i) * K], IPDDP_LDCG(g + q), sa);             // beta' Qu
-          for (int q = g4; q < NC; q += 4) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], IPDDP_LDCG(g + NU + q), sb);   // omega' c
+          double px[(NC + 3) / 4 > 0 ? (NC + 3) / 4 : 1], pq[(NU + 3) / 4 > 0 ? (NU + 3) / 4 : 1], pc[(NC + 3) / 4 > 0 ? (NC + 3) / 4 : 1];
+#pragma unroll
+          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; px[qq] = (q < NC) ? IPDDP_LDCG(g + NU + q + (1 + i) * K) : 0.0; }
+#pragma unroll
+          for (int qq = 0; qq < (NU + 3) / 4; ++qq) { const int q = g4 + 4 * qq; pq[qq] = (q < NU) ? IPDDP_LDCG(g + q) : 0.0; }
+#pragma unroll
+          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; pc[qq] = (q < NC) ? IPDDP_LDCG(g + NU + q) : 0.0; }
+#pragma unroll
+          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NC) sc = IPDDP_FMA(px[qq], phi[q], sc); }               // cx' phi
+#pragma unroll
+          for (int qq = 0; qq < (NU + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NU) sa = IPDDP_FMA(rhs[q + (1 + i) * K], pq[qq], sa); }   // beta' Qu
+#pragma unroll
+          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NC) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], pc[qq], sb); }   // omega' c
         }
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);

@@ -17,6 +17,7 @@
 #define IPDDP_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define IPDDP_LDG(p) __ldg(p)
 #define IPDDP_LDCG(p) __ldcg(p)
+#define IPDDP_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define IPDDP_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; type* name = reinterpret_cast<type*>(name##_raw)
 #define IPDDP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif

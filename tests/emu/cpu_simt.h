@@ -68,6 +68,7 @@ static inline double emu_ll2d(long long u) { double x; memcpy(&x, &u, 8); return
 #define IPDDP_FMA(a, b, c) fma((a), (b), (c))
 #define IPDDP_LDG(p) (*(p))
 #define IPDDP_LDCG(p) (*(p))
+#define IPDDP_PREFETCH_L2(p) ((void)(p))
 #define IPDDP_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::cur_smem())
 #define IPDDP_LAUNCH(kernel, grid, block, smem, stream, ...) \
   emu::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })
