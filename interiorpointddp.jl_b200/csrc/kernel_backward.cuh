@@ -70,14 +70,20 @@ IPDDP_D double bw_next_reg(const DevView& v, double reg, double reg_last) {
   return (reg_last == 0.0) ? v.opt.kappa_bar_w_p * reg : v.opt.kappa_w_p * reg;
 }
 
+// (the buffers of the PRE group -- xxt, uxt, tile, dsc, vfs, xs, us -- share memory with ws: no __restrict__ there)
 #define IPDDP_BW_POINTERS \
-  double* lhs = sm + L::LHS; double* rhs = sm + L::RHS; \
-  double* fx = sm + L::FX; double* fu = sm + L::FU; double* Vxx = sm + L::VXX; double* Vx = sm + L::VX; \
-  double* lamn = sm + L::LAM; double* Cm = sm + L::CM; double* xxt = sm + L::XXT; double* uxt = sm + L::UXT; \
-  double* ra1 = sm + L::VEC; double* ra2 = ra1 + NU; double* t1 = ra2 + NU; double* t2 = t1 + NU; \
-  double* phi = sm + L::PHI; double* xs = sm + L::XS; double* us = sm + L::US; double* lx = sm + L::LX; \
+  double* __restrict__ lhs = sm + L::LHS; double* __restrict__ rhs = sm + L::RHS; \
+  double* __restrict__ fx = sm + L::FX; double* __restrict__ fu = sm + L::FU; \
+  double* __restrict__ Vxx = sm + L::VXX; double* __restrict__ Vx = sm + L::VX; \
+  double* __restrict__ lamn = sm + L::LAM; double* __restrict__ Cm = sm + L::CM; \
+  double* xxt = sm + L::XXT; double* uxt = sm + L::UXT; \
+  double* __restrict__ ra1 = sm + L::VEC; double* __restrict__ ra2 = sm + L::VEC + NU; \
+  double* __restrict__ t1 = sm + L::VEC + 2 * NU; double* __restrict__ t2 = sm + L::VEC + 3 * NU; \
+  double* __restrict__ phi = sm + L::PHI; double* xs = sm + L::XS; double* us = sm + L::US; \
+  double* __restrict__ lx = sm + L::LX; \
   double* tile = sm + L::TILE; double* vfs = sm + L::VFS; double* ws = sm + L::WS; double* dsc = sm + L::DSC; \
-  double* nVxx = sm + L::NEWV; double* nVx = nVxx + NX * NX; double* nlam = nVx + NX; \
+  double* __restrict__ nVxx = sm + L::NEWV; double* __restrict__ nVx = sm + L::NEWV + NX * NX; \
+  double* __restrict__ nlam = sm + L::NEWV + NX * NX + NX; \
   unsigned char* smb = reinterpret_cast<unsigned char*>(sm); \
   int* ipiv = reinterpret_cast<int*>(smb + L::IPIV_B); \
   unsigned char* nzlist = smb + L::LIST_B; \

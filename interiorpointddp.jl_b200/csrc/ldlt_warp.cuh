@@ -133,7 +133,8 @@ template <int K> struct LdltScratch {
 // General pivot step (column k) of dsytf2_rook('U') fused with dsytrs_rook's first loop on Bm.
 // Returns kstep (1 or 2).  TWO = rows >= 32 may be involved (k >= 32).
 template <int K, int NR, bool TWO>
-IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsigned char* scratch, int lane,
+IPDDP_D int ldlt_step(int k, double* __restrict__ A, int* __restrict__ ipiv, double* __restrict__ Bm, double* __restrict__ w,
+                      unsigned char* __restrict__ scratch, int lane,
                       unsigned tri_lane, double tol, int& info, int& np) {
   typedef LdltScratch<K> S;
   double* dinv = S::dinv(scratch);
@@ -342,7 +343,8 @@ IPDDP_D int ldlt_step(int k, double* A, int* ipiv, double* Bm, double* w, unsign
 // Fast pivot step for 0 <= k < 32 (see the header).  Returns false -- with nothing modified -- if the step is not a
 // 1x1 pivot reached with at most one interchange, or if NaNs / tiny pivots / singular columns are involved.
 template <int K, int NR>
-IPDDP_D bool ldlt_step_fast(int k, double* A, int* ipiv, double* Bm, unsigned char* scratch, int lane, unsigned tri_lane,
+IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, int* __restrict__ ipiv, double* __restrict__ Bm,
+                            unsigned char* __restrict__ scratch, int lane, unsigned tri_lane,
                             double tol, int& np) {
   typedef LdltScratch<K> S;
   const double alpha = 0.6403882032022076;   // (1 + sqrt(17)) / 8
@@ -353,8 +355,6 @@ IPDDP_D bool ldlt_step_fast(int k, double* A, int* ipiv, double* Bm, unsigned ch
   double piv = A[ck + k];
   int kp = k;
   const bool keep = __all_sync(IPDDP_FULL_MASK, fabs(piv) >= alpha * fabs(x));   // false on any NaN
-  double xold = 0.0, pold = 0.0;
-  int ci = 0;
   if (!keep) {
     if (__any_sync(IPDDP_FULL_MASK, x != x) || piv != piv) return false;
     // imax: first row attaining max |x|
@@ -368,30 +368,31 @@ IPDDP_D bool ldlt_step_fast(int k, double* A, int* ipiv, double* Bm, unsigned ch
       cand = __ballot_sync(IPDDP_FULL_MASK, in && hi == mh && lo == ml);
     }
     const int imax = __ffs(cand) - 1;
-    ci = coff(imax);
+    const int ci = coff(imax);
     // row / column imax of the leading (k+1) x (k+1) block, signed: it becomes the pivot column after the interchange
     const bool vr = lane <= k && lane != imax;
-    const double a = vr ? (lane < imax ? A[ci + lane] : A[coff(lane) + imax]) : 0.0;
+    const int pa = (lane < imax) ? ci + lane : coff(lane) + imax;
+    const double a = vr ? A[pa] : 0.0;
     const double aii = A[ci + imax];
     // rook acceptance of the first candidate: |a_ii| >= alpha * rowmax  (false on any NaN)
     if (!__all_sync(IPDDP_FULL_MASK, fabs(aii) >= alpha * fabs(a))) return false;
-    xold = x; pold = piv;
+    if (!(fabs(aii) >= sfmin)) return false;   // tiny pivot: general path
+    // ---- committed: symmetric interchange k <-> imax as stores of register values (row / column imax receives the
+    //      old column k) and the row interchange of the right-hand sides
+    if (in && lane != imax) A[pa] = x;
+    if (lane == 0) { A[ci + imax] = piv; A[ck + k] = aii; }
+    if (lane < NR) { double* bl = Bm + lane * K; const double t = bl[k]; bl[k] = bl[imax]; bl[imax] = t; }
     x = (lane == imax) ? x : (in ? a : 0.0);
     piv = aii;
     kp = imax;
+  } else if (!(fabs(piv) >= sfmin)) {
+    return false;                              // singular column (piv == 0 => column all zero), tiny pivot
   }
+  // ---- committed: 1x1 pivot piv at (k,k)
   const unsigned nzm = __ballot_sync(IPDDP_FULL_MASK, x != 0.0);
-  if (!(fabs(piv) >= sfmin)) return false;   // singular column (piv == 0, nzm == 0), tiny pivot
-  // ---- committed: 1x1 pivot piv, interchange k <-> kp
   const double rinv = 1.0 / piv;
   if (piv > tol) np += 1;
   if (lane == 0) { ipiv[k] = kp + 1; S::nzlo(scratch)[k] = nzm; S::nzhi(scratch)[k] = 0u; S::dinv(scratch)[k] = rinv; }
-  if (kp != k) {
-    // symmetric interchange as stores of register values: row / column kp receives the old column k
-    if (in && lane != kp) A[(lane < kp) ? ci + lane : coff(lane) + kp] = xold;
-    if (lane == 0) { A[ci + kp] = pold; A[ck + k] = piv; }
-    warp_swap_rows<NR>(Bm, K, k, kp, lane);
-  }
   if (nzm == 0u) return true;                // nothing to eliminate; B(k,:) scaling is deferred
   unsigned char* list = S::list(scratch);
   if (x != 0.0) list[__popc(nzm & ((1u << lane) - 1u))] = (unsigned char)lane;
@@ -431,7 +432,8 @@ IPDDP_D bool ldlt_step_fast(int k, double* A, int* ipiv, double* Bm, unsigned ch
 IPDDP_D unsigned ldlt_tri_lane(int lane) { return tri_decode(lane) | (tri_decode(lane + 32) << 16); }
 
 template <int K, int NR>
-IPDDP_D int warp_ldlt_factor(double* A, int* ipiv, double* Bm, double* w, unsigned char* scratch, int lane, double tol,
+IPDDP_D int warp_ldlt_factor(double* __restrict__ A, int* __restrict__ ipiv, double* __restrict__ Bm, double* __restrict__ w,
+                             unsigned char* __restrict__ scratch, int lane, double tol,
                              int& np_out, unsigned tri_lane) {
   int info = 0, np = 0;
   int k = K - 1;
@@ -457,7 +459,8 @@ IPDDP_D int warp_ldlt_factor(double* A, int* ipiv, double* Bm, double* w, unsign
 // 4 lanes per right-hand side accumulate the dgemv('T') dot product in the dot4 order (partial sums by i mod 4,
 // ascending i, 2-step butterfly); zero multipliers are skipped through the per-column row masks.
 template <int K, int NR>
-IPDDP_D void warp_ldlt_solve_forward(const double* A, const int* ipiv, double* Bm, const unsigned char* scratch, int lane) {
+IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, const int* __restrict__ ipiv, double* __restrict__ Bm,
+                                     const unsigned char* __restrict__ scratch, int lane) {
   typedef LdltScratch<K> S;
   const double* dinv = S::dinv(scratch);
   const unsigned* nzlo = S::nzlo(scratch);
