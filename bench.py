@@ -147,7 +147,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="instances per GPU")
@@ -156,7 +156,9 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-7)
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU baseline sample (0 = 128 x cores for cpu_baseline, 48 x cores per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=4, help="independent batches in flight during the timed steps")
+    ap.add_argument("--inflight", type=int, default=8, help="independent batches in flight during the timed steps")
+    ap.add_argument("--seq-steps", type=int, default=2,
+                    help="steps of the sequential region (one batch at a time, per-kernel CUDA events: rooflines)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -218,14 +220,17 @@ def main():
 
     for sv in solvers:
         set_device_inputs(sv)
-    for _ in range(args.warmup):
+    # warm-up: W untimed steps through the same pipelined path as the timed region, plus one sequential solve
+    if args.warmup > 0:
+        solve_many(solvers[:min(F, args.warmup)], total_solves=args.warmup)
         solver.solve()
 
     # ---------------------------------------------------- timed region A: K steps one after another (kernels timed alone)
     agg = dict(ms_total=0.0, ms_derivs=0.0, ms_backward=0.0, ms_check=0.0, ms_forward=0.0, ms_init=0.0, kkt=0, sweeps=0,
                rollouts=0, deriv=0, conv=0, launches=0, rounds=0, active_rounds=0, backward_calls=0)
+    seq_steps = max(1, min(args.steps, args.seq_steps))
     barrier()
-    for _ in range(args.steps):
+    for _ in range(seq_steps):
         set_device_inputs(solver)
         solver.solve()
         st = solver.stats()
@@ -283,7 +288,7 @@ def main():
 
     if rank == 0:
         value = conv_pipe_all / (ms_pipe_max * 1e-3)
-        value_sequential = conv_all / (ms_total * 1e-3)
+        value_sequential = conv_all / (ms_total * 1e-3)   # over the seq_steps sequential steps
         e2e_val = conv_e2e_all / wall_e2e_max
         # roofline of the dominant kernel (backward sweep) on rank 0
         peaks = {}
@@ -358,15 +363,16 @@ def main():
                        "steps_in_flight": F,
                        "timing": "value/e2e: the K steps run with up to steps_in_flight independent batches in flight on their own "
                                  "streams (ipddp_solve_many), device time by CUDA events from first enqueue to last completion; "
-                                 "roofline/kernels/sequential: the same K steps one after another, per-kernel CUDA events"},
-            "sequential": {"value": value_sequential, "ms_per_step": ms_total / args.steps},
+                                 "roofline/kernels/sequential: sequential.steps of the same steps one after another, per-kernel "
+                                 "CUDA events on the launching stream"},
+            "sequential": {"value": value_sequential, "ms_per_step": ms_total / seq_steps, "steps": seq_steps},
             "converged_fraction": conv_last / (B * world), "mean_iterations": ksum / (B * world), "max_primal_inf": pr_max,
             "backward_kkt_steps_per_s": kkt_pipe_all / (ms_pipe_max * 1e-3),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": roof_hbm, "roofline_fp64": roof_fp64, "kernels": kernels,
-            "lockstep": {"rounds_per_step": agg["rounds"] / args.steps,
+            "lockstep": {"rounds_per_step": agg["rounds"] / seq_steps,
                          "mean_active_fraction": agg["active_rounds"] / max(1, agg["rounds"]) / B},
             "cpu_baseline": cpu,
         }

@@ -50,10 +50,9 @@ template <class M> struct BwLayout {
   static constexpr int WS = PRE;
   static constexpr int DBL_END = mx(PRE_END, WS + 4 * K);
   // ints (4 bytes) after the doubles
-  // LDLT scratch (8-byte aligned: it starts with doubles), then ipiv (ints)
+  // LDLT scratch (8-byte aligned: it starts with doubles)
   static constexpr int LIST_B = DBL_END * 8;
-  static constexpr int IPIV_B = LIST_B + LdltScratch<(K > 0 ? K : 1)>::BYTES;
-  static constexpr int BYTES = ((IPIV_B + pad(K) * 4 + 15) / 16) * 16;
+  static constexpr int BYTES = ((LIST_B + LdltScratch<(K > 0 ? K : 1)>::BYTES + 15) / 16) * 16;
 };
 
 // where one sweep writes its outputs (per-instance base pointers: gains + t*G, Qu + t*NU, lam + t*NX)
@@ -85,7 +84,6 @@ IPDDP_D double bw_next_reg(const DevView& v, double reg, double reg_last) {
   double* __restrict__ nVxx = sm + L::NEWV; double* __restrict__ nVx = sm + L::NEWV + NX * NX; \
   double* __restrict__ nlam = sm + L::NEWV + NX * NX + NX; \
   unsigned char* smb = reinterpret_cast<unsigned char*>(sm); \
-  int* ipiv = reinterpret_cast<int*>(smb + L::IPIV_B); \
   unsigned char* nzlist = smb + L::LIST_B; \
   const MEntry* tbl = M::tbl(); \
   const double* cst = M::consts(); \
@@ -286,11 +284,11 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
     __syncwarp();
     // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
     int np = 0;
-    const int info = warp_ldlt_factor<K, NR>(lhs, ipiv, rhs, ws, nzlist, lane, 1e-12, np, tri_lane);
+    const int info = warp_ldlt_factor<K, NR>(lhs, rhs, ws, nzlist, lane, 1e-12, np, tri_lane);
     delta_c = 0.0;
     if (info > 0) delta_c = v.opt.delta_c * dm::pow(mu, v.opt.kappa_c);
     if (np != NU || info != 0) return 1;   // inertia failure: the caller restarts the sweep with a larger reg
-    warp_ldlt_solve_forward<K, NR>(lhs, ipiv, rhs, nzlist, lane);
+    warp_ldlt_solve_forward<K, NR>(lhs, rhs, nzlist, lane);
     // ---- ineq gains to HBM                                            (:159-172)
     double* gi = g + K * NR;
     for (int e = lane; e < NU * NR; e += 32) {

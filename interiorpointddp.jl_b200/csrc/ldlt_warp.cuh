@@ -112,33 +112,36 @@ template <int NR> IPDDP_D void warp_swap_rows(double* Bm, int ld, int a, int b, 
 }
 
 // Scratch used by the factorisation and kept for the second solve (base must be 8-byte aligned):
-// dinv: K doubles (deferred 1/a_kk row scalings, 1.0 where the step scaled in place), nzlo / nzhi: K uint32 each
-// (non-zero multiplier rows 0..31 / 32..63 of every pivot column), list: K bytes (current compaction).
-// The 2x2 pivot update additionally needs w: 4K doubles, passed separately.
+// dinv: K doubles (deferred 1/a_kk row scalings, 1.0 where the step scaled in place); info: K 64-bit words, low half =
+// non-zero multiplier rows 0..31 of the pivot column, high half = LAPACK's ipiv entry (1-based, negative for 2x2
+// blocks) -- one shared-memory access per column in the second solve; nzhi: K uint32 (rows 32..63, K > 32 only);
+// list: K bytes (current compaction).  The 2x2 pivot update additionally needs w: 4K doubles, passed separately.
 template <int K> struct LdltScratch {
   static constexpr int DINV = 0;
-  static constexpr int NZLO = DINV + K * 8;
-  static constexpr int NZHI = NZLO + K * 4;
+  static constexpr int INFO = DINV + K * 8;
+  static constexpr int NZHI = INFO + K * 8;
   static constexpr int LIST = NZHI + K * 4;
   static constexpr int BYTES = ((LIST + K + 15) / 16) * 16;
   static IPDDP_D double* dinv(unsigned char* s) { return reinterpret_cast<double*>(s + DINV); }
-  static IPDDP_D unsigned* nzlo(unsigned char* s) { return reinterpret_cast<unsigned*>(s + NZLO); }
+  static IPDDP_D unsigned long long* info(unsigned char* s) { return reinterpret_cast<unsigned long long*>(s + INFO); }
   static IPDDP_D unsigned* nzhi(unsigned char* s) { return reinterpret_cast<unsigned*>(s + NZHI); }
   static IPDDP_D unsigned char* list(unsigned char* s) { return s + LIST; }
   static IPDDP_D const double* dinv(const unsigned char* s) { return reinterpret_cast<const double*>(s + DINV); }
-  static IPDDP_D const unsigned* nzlo(const unsigned char* s) { return reinterpret_cast<const unsigned*>(s + NZLO); }
+  static IPDDP_D const unsigned long long* info(const unsigned char* s) { return reinterpret_cast<const unsigned long long*>(s + INFO); }
   static IPDDP_D const unsigned* nzhi(const unsigned char* s) { return reinterpret_cast<const unsigned*>(s + NZHI); }
+  static IPDDP_D unsigned long long pack(unsigned nzlo, int ipiv) { return (unsigned long long)nzlo | ((unsigned long long)(unsigned)ipiv << 32); }
+  static IPDDP_D int ipiv_of(unsigned long long w) { return (int)(unsigned)(w >> 32); }
 };
 
 // General pivot step (column k) of dsytf2_rook('U') fused with dsytrs_rook's first loop on Bm.
 // Returns kstep (1 or 2).  TWO = rows >= 32 may be involved (k >= 32).
 template <int K, int NR, bool TWO>
-IPDDP_D int ldlt_step(int k, double* __restrict__ A, int* __restrict__ ipiv, double* __restrict__ Bm, double* __restrict__ w,
+IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, double* __restrict__ w,
                       unsigned char* __restrict__ scratch, int lane,
                       unsigned tri_lane, double tol, int& info, int& np) {
   typedef LdltScratch<K> S;
   double* dinv = S::dinv(scratch);
-  unsigned* nzlo = S::nzlo(scratch);
+  unsigned long long* cinfo = S::info(scratch);
   unsigned* nzhi = S::nzhi(scratch);
   unsigned char* list = S::list(scratch);
   const double alpha = 0.6403882032022076;   // (1 + sqrt(17)) / 8
@@ -158,7 +161,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, int* __restrict__ ipiv, dou
   if (fmax(absakk, colmax) == 0.0) {
     // exactly singular column: no elimination (LAPACK sets info and moves on); dsytrs would divide by zero
     if (info == 0) info = k + 1;
-    if (lane == 0) { ipiv[k] = k + 1; nzlo[k] = 0u; nzhi[k] = 0u; dinv[k] = 1.0; }
+    if (lane == 0) { cinfo[k] = S::pack(0u, k + 1); nzhi[k] = 0u; dinv[k] = 1.0; }
     return 1;
   }
   if (absakk < alpha * colmax) {
@@ -196,7 +199,6 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, int* __restrict__ ipiv, dou
   }
   if (kstep == 1) {
     const double akk = A[ck + k];
-    if (lane == 0) ipiv[k] = kp + 1;
     if (akk > tol) np += 1;
     int nnz = 0;
     unsigned m0 = 0u, m1 = 0u;
@@ -230,7 +232,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, int* __restrict__ ipiv, dou
         }
       }
     }
-    if (lane == 0) { nzlo[k] = m0; nzhi[k] = m1; dinv[k] = 1.0; }
+    if (lane == 0) { cinfo[k] = S::pack(m0, kp + 1); nzhi[k] = m1; dinv[k] = 1.0; }
     // dsytrs first loop for this pivot: B(0:k-1,:) -= x * B(k,:), then B(k,:) *= 1/akk
     if (x0 != 0.0) {
 #pragma unroll
@@ -247,7 +249,6 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, int* __restrict__ ipiv, dou
     double* xk = A + ck;
     double* xkm1 = A + coff(k - 1);
     const double d12 = xk[k - 1];
-    if (lane == 0) { ipiv[k] = -(p + 1); ipiv[k - 1] = -(kp + 1); }
     {   // inertia of the 2x2 block (reference inertia!, atol = tol)
       const double e11 = xkm1[k - 1], e22 = xk[k];
       if (d12 != 0.0) {
@@ -310,7 +311,10 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, int* __restrict__ ipiv, dou
       }
       __syncwarp();
     }
-    if (lane == 0) { nzlo[k] = m0; nzhi[k] = m1; nzlo[k - 1] = m0; nzhi[k - 1] = m1; dinv[k] = 1.0; dinv[k - 1] = 1.0; }
+    if (lane == 0) {
+      cinfo[k] = S::pack(m0, -(p + 1)); cinfo[k - 1] = S::pack(m0, -(kp + 1));
+      nzhi[k] = m1; nzhi[k - 1] = m1; dinv[k] = 1.0; dinv[k - 1] = 1.0;
+    }
     // dsytrs first loop for the 2x2 block: two rank-1 downdates of B, then the 2x2 solve
 #pragma unroll
     for (int s = 0; s < (TWO ? 2 : 1); ++s) {
@@ -343,7 +347,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, int* __restrict__ ipiv, dou
 // Fast pivot step for 0 <= k < 32 (see the header).  Returns false -- with nothing modified -- if the step is not a
 // 1x1 pivot reached with at most one interchange, or if NaNs / tiny pivots / singular columns are involved.
 template <int K, int NR>
-IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, int* __restrict__ ipiv, double* __restrict__ Bm,
+IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ Bm,
                             unsigned char* __restrict__ scratch, int lane, unsigned tri_lane,
                             double tol, int& np) {
   typedef LdltScratch<K> S;
@@ -392,7 +396,11 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, int* __restrict__ ipi
   const unsigned nzm = __ballot_sync(IPDDP_FULL_MASK, x != 0.0);
   const double rinv = 1.0 / piv;
   if (piv > tol) np += 1;
-  if (lane == 0) { ipiv[k] = kp + 1; S::nzlo(scratch)[k] = nzm; S::nzhi(scratch)[k] = 0u; S::dinv(scratch)[k] = rinv; }
+  if (lane == 0) {
+    S::info(scratch)[k] = S::pack(nzm, kp + 1);
+    S::dinv(scratch)[k] = rinv;
+    if (K > 32) S::nzhi(scratch)[k] = 0u;
+  }
   if (nzm == 0u) return true;                // nothing to eliminate; B(k,:) scaling is deferred
   unsigned char* list = S::list(scratch);
   if (x != 0.0) list[__popc(nzm & ((1u << lane) - 1u))] = (unsigned char)lane;
@@ -432,21 +440,21 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, int* __restrict__ ipi
 IPDDP_D unsigned ldlt_tri_lane(int lane) { return tri_decode(lane) | (tri_decode(lane + 32) << 16); }
 
 template <int K, int NR>
-IPDDP_D int warp_ldlt_factor(double* __restrict__ A, int* __restrict__ ipiv, double* __restrict__ Bm, double* __restrict__ w,
+IPDDP_D int warp_ldlt_factor(double* __restrict__ A, double* __restrict__ Bm, double* __restrict__ w,
                              unsigned char* __restrict__ scratch, int lane, double tol,
                              int& np_out, unsigned tri_lane) {
   int info = 0, np = 0;
   int k = K - 1;
   if (K > 32) {
-    while (k >= 32) k -= ldlt_step<K, NR, true>(k, A, ipiv, Bm, w, scratch, lane, tri_lane, tol, info, np);
+    while (k >= 32) k -= ldlt_step<K, NR, true>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
   }
   while (k >= 0) {
-    if (ldlt_step_fast<K, NR>(k, A, ipiv, Bm, scratch, lane, tri_lane, tol, np)) {
+    if (ldlt_step_fast<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) {
       IPDDP_LDLT_COUNT(0);
       k -= 1;
       continue;
     }
-    const int ks = ldlt_step<K, NR, false>(k, A, ipiv, Bm, w, scratch, lane, tri_lane, tol, info, np);
+    const int ks = ldlt_step<K, NR, false>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
     IPDDP_LDLT_COUNT(ks);
     k -= ks;
   }
@@ -459,11 +467,11 @@ IPDDP_D int warp_ldlt_factor(double* __restrict__ A, int* __restrict__ ipiv, dou
 // 4 lanes per right-hand side accumulate the dgemv('T') dot product in the dot4 order (partial sums by i mod 4,
 // ascending i, 2-step butterfly); zero multipliers are skipped through the per-column row masks.
 template <int K, int NR>
-IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, const int* __restrict__ ipiv, double* __restrict__ Bm,
+IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __restrict__ Bm,
                                      const unsigned char* __restrict__ scratch, int lane) {
   typedef LdltScratch<K> S;
   const double* dinv = S::dinv(scratch);
-  const unsigned* nzlo = S::nzlo(scratch);
+  const unsigned long long* cinfo = S::info(scratch);
   const unsigned* nzhi = S::nzhi(scratch);
   static_assert(NR <= 8, "at most 8 right-hand sides");
 #pragma unroll
@@ -483,55 +491,64 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, const int* __
   double* bj = Bm + (act ? j : 0) * K;
   int k = 0;
   while (k < K) {
-    const bool one = ipiv[k] > 0;
-    if (k > 0) {
-      const unsigned mlo = nzlo[k], mhi = (K > 32) ? nzhi[k] : 0u;
-      if ((mlo | mhi) != 0u) {
-        const double* xa = A + coff(k);
-        const double* xb = A + coff(k + (one ? 0 : 1));
-        double sa = 0.0, sb = 0.0;
-        if (act) {
-          unsigned m = mlo & gm;
+    const unsigned long long cw = cinfo[k];
+    const int pv = S::ipiv_of(cw);
+    const bool one = pv > 0;
+    const unsigned mlo = (k > 0) ? (unsigned)cw : 0u, mhi = (K > 32 && k > 0) ? nzhi[k] : 0u;
+    const bool any = (mlo | mhi) != 0u;
+    double sa = 0.0, sb = 0.0;
+    if (any) {
+      const double* xa = A + coff(k);
+      const double* xb = A + coff(k + (one ? 0 : 1));
+      if (act) {
+        unsigned m = mlo & gm;
+        while (m) {
+          const int i = __ffs(m) - 1;
+          m &= m - 1u;
+          const double bv = bj[i];
+          sa = IPDDP_FMA(xa[i], bv, sa);
+          if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
+        }
+        if (K > 32) {
+          m = mhi & gm;
           while (m) {
-            const int i = __ffs(m) - 1;
+            const int i = 32 + __ffs(m) - 1;
             m &= m - 1u;
             const double bv = bj[i];
             sa = IPDDP_FMA(xa[i], bv, sa);
             if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
           }
-          if (K > 32) {
-            m = mhi & gm;
-            while (m) {
-              const int i = 32 + __ffs(m) - 1;
-              m &= m - 1u;
-              const double bv = bj[i];
-              sa = IPDDP_FMA(xa[i], bv, sa);
-              if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
-            }
-          }
         }
-        __syncwarp();
-        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
-        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
-        if (!one) {
-          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
-          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
-        }
-        if (act && g == 0) {
-          bj[k] = bj[k] - sa;
-          if (!one) bj[k + 1] = bj[k + 1] - sb;
-        }
-        __syncwarp();
+      }
+      __syncwarp();
+      sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
+      sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
+      if (!one) {
+        sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
+        sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
       }
     }
     if (one) {
-      const int kp = ipiv[k] - 1;
-      if (kp != k) { warp_swap_rows<NR>(Bm, K, k, kp, lane); __syncwarp(); }
+      // B(k,:) -= sa, then the interchange k <-> kp, done by the lane that owns column j in one read-modify-write
+      const int kp = pv - 1;
+      if (any || kp != k) {
+        if (act && g == 0) {
+          double v = bj[k];
+          if (any) v = v - sa;
+          if (kp != k) { const double t = bj[kp]; bj[kp] = v; v = t; }
+          bj[k] = v;
+        }
+        __syncwarp();
+      }
       k += 1;
     } else {
-      int kp = -ipiv[k] - 1;
+      if (any) {
+        if (act && g == 0) { bj[k] = bj[k] - sa; bj[k + 1] = bj[k + 1] - sb; }
+        __syncwarp();
+      }
+      int kp = -pv - 1;
       if (kp != k) { warp_swap_rows<NR>(Bm, K, k, kp, lane); __syncwarp(); }
-      kp = -ipiv[k + 1] - 1;
+      kp = -S::ipiv_of(cinfo[k + 1]) - 1;
       if (kp != k + 1) { warp_swap_rows<NR>(Bm, K, k + 1, kp, lane); __syncwarp(); }
       k += 2;
     }
