@@ -21,7 +21,7 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libipddp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique", "-ccbin", "/usr/bin/g++"]
 
 
 def sources():

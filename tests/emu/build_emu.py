@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "interiorpointddp.jl_b200", "csrc")
 LIB = os.path.join(HERE, "libipddp_emu.so")
 CXX = "/usr/bin/g++"
-FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-mfma", "-fno-fast-math", "-x", "c++",
+FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-mfma", "-fno-fast-math", "-fno-gnu-unique", "-fvisibility-inlines-hidden", "-x", "c++",
          "-include", os.path.join(HERE, "cpu_simt.h"), "-w"]
 
 

@@ -37,6 +37,50 @@ def test_full_solve_parity(gpu, oracle_mod, wl, B):
     helpers.full_solve_parity(gpu, oracle_mod, wl, B, 101, n_trace=3)
 
 
+@pytest.mark.parametrize("wl,B", [("cartpole", 24), ("acrobot", 12), ("pushing", 8)])
+def test_bulk_kernels_parity(gpu, oracle_mod, wl, B):
+    """Batches this small normally take the speculative tail kernels (k_forward_spec: 8 step sizes at once,
+    k_backward_spec: 4 regularisation values at once); forcing the thresholds to 0 runs the bulk kernels
+    (k_forward, k_backward) on the same instances.  Both shapes must reproduce the oracle bit for bit."""
+    gpu.L.ipddp_set_tuning(None, b"fw_spec_max", 0)
+    gpu.L.ipddp_set_tuning(None, b"bw_spec_max", 0)
+    try:
+        helpers.full_solve_parity(gpu, oracle_mod, wl, B, 101, n_trace=2)
+    finally:
+        gpu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
+        gpu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+
+
+def test_tail_kernels_equal_bulk_kernels_mid_size(gpu):
+    """Size-independent property at a few hundred instances: the speculative tail kernels and the bulk kernels give
+    identical per-instance answers and identical work counters (sweeps, KKT steps, rollouts)."""
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver
+    B = 320
+    opt = gpu.default_options(optimality_tolerance=1e-7)
+    b = instances.make_batch("cartpole", B, 101, first=500)
+    out = []
+    for fw, bw in ((0, 0), (B, B)):
+        s = BatchSolver("cartpole", B, 101, options=opt, lib=gpu)
+        s.set_tuning("fw_spec_max", fw)
+        s.set_tuning("bw_spec_max", bw)
+        s.set_batch(b)
+        r = s.solve()
+        x, u = s.trajectory()
+        c = s.counters()
+        out.append((r, x, u, c))
+        s.close()
+    (r0, x0, u0, c0), (r1, x1, u1, c1) = out
+    assert np.array_equal(r0.k, r1.k) and np.array_equal(r0.status, r1.status) and np.array_equal(r0.l, r1.l)
+    helpers.assert_same_bits(r0.objective, r1.objective, "objective")
+    helpers.assert_same_bits(r0.reg_last, r1.reg_last, "reg_last")
+    helpers.assert_same_bits(r0.step_size, r1.step_size, "step size")
+    helpers.assert_same_bits(x0, x1, "states")
+    helpers.assert_same_bits(u0, u1, "controls")
+    for key in ("n_backward", "n_sweeps", "n_kkt", "n_rollouts"):
+        assert np.array_equal(c0[key], c1[key]), key
+
+
 def test_varying_horizon_parity(gpu, oracle_mod):
     """config 5: per-instance horizons (offset tables / horizon vector), synthetic instances."""
     helpers.full_solve_parity(gpu, oracle_mod, "pushing", 8, 101, vary_horizon=True, first=100, n_trace=2)
