@@ -147,7 +147,9 @@ def build_model_plugin(md: workloads.ModelDef, force: bool = False) -> str:
     bundles = generate.trace(md)
     src = generate.emit_device(md, bundles).replace('#include "../model_common.cuh"',
                                                     f'#include "{os.path.join(HERE, "csrc", "model_common.cuh")}"')
-    tag = hashlib.sha256(src.encode()).hexdigest()[:12]
+    from . import build as _b
+    # the plugin embeds the kernel templates and the DevView layout: key the cache on them too
+    tag = hashlib.sha256((src + _b.content_hash(_b._headers(), " ".join(_b.FLAGS))).encode()).hexdigest()[:12]
     so = os.path.join(PLUGIN_DIR, f"{md.name}_{tag}.so")
     if os.path.exists(so) and not force:
         return so
@@ -158,7 +160,6 @@ def build_model_plugin(md: workloads.ModelDef, force: bool = False) -> str:
     with open(cu, "w") as fh:
         fh.write(f'#include "{cuh}"\n#include "{os.path.join(HERE, "csrc", "model_register.cuh")}"\n'
                  f'IPDDP_REGISTER_MODEL(Model_{md.name}, ipddp_plugin_vtable)\n')
-    from . import build as _b
     cmd = [_b.NVCC] + _b.FLAGS + ["-shared", cu, "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

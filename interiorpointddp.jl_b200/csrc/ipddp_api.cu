@@ -277,6 +277,7 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   rc |= h->alloc(&v.si, (size_t)SI_COUNT * B);
   rc |= h->alloc(&v.filter, (size_t)2 * IPDDP_FILTER_CAPACITY * B);
   rc |= h->alloc(&v.trace, (size_t)B * v.trace_cap * IPDDP_TRACE_COLS);
+  if (v.fw_spec_max > B) v.fw_spec_max = B;
   rc |= h->alloc(&v.spec_traj, (size_t)(v.fw_spec_max > 0 ? v.fw_spec_max : 0) * ipk::FWS_WARPS * N * v.TR);
   h->spec_cap = v.fw_spec_max;
   if (v.bw_spec_max > B) v.bw_spec_max = B;
@@ -351,6 +352,7 @@ int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
   if (k == "fw_spec_max") {   // h == NULL: default for problems created afterwards
     if (value < 0) value = 0;
     if (!h) { g_fw_spec_max = value; return 0; }
+    if (value > h->v.B) value = h->v.B;
     if (value > h->spec_cap) {   // grow the private trial-record pool
       CK(cudaSetDevice(h->device));
       double* q = nullptr;

@@ -35,15 +35,15 @@ template <class M> struct BwLayout {
   static constexpr int VEC = CM + NX * NX;           // 1/il 1/iu Sigma^L Sigma^U  (4 x NU)
   static constexpr int PHI = VEC + pad(4 * NU);
   static constexpr int LX = PHI + pad(NC);
-  static constexpr int NEWV = LX + NX;               // new Vxx (NX*NX), Vx (NX), lam (NX)
+  static constexpr int NEWV = LX + NX;               // new Vxx (NX*NX), Vx (NX), lam (NX); before the solve: |dual residual| (NU)
   // PRE: buffers that are dead once the factorisation starts; the 4K-double scratch of the 2x2 pivot update
   // (WS) is aliased on top of them
-  static constexpr int PRE = NEWV + NX * NX + 2 * NX;
+  static constexpr int PRE = NEWV + mx(NX * NX + 2 * NX, NU);
+  static constexpr int DSC = NEWV;
   static constexpr int UXT = PRE;                    // fu' Vxx+  (NU x NX)
   static constexpr int XXT = UXT + pad(NU * NX);     // fx' Vxx+  (NX x NX)
   static constexpr int TILE = XXT + NX * NX;
-  static constexpr int DSC = TILE + pad(mx(M::D_NSLOT, M::DN_NSLOT));   // |dual residual| per control
-  static constexpr int VFS = DSC + pad(NU);
+  static constexpr int VFS = TILE + pad(mx(M::D_NSLOT, M::DN_NSLOT));
   static constexpr int XS = VFS + pad(M::VF_NSLOT);  // x, u copies for the dynamics Hessian contraction
   static constexpr int US = XS + (M::VF_NSLOT > 0 ? NX : 0);
   static constexpr int PRE_END = US + (M::VF_NSLOT > 0 ? NU : 0);
@@ -69,7 +69,8 @@ IPDDP_D double bw_next_reg(const DevView& v, double reg, double reg_last) {
   return (reg_last == 0.0) ? v.opt.kappa_bar_w_p * reg : v.opt.kappa_w_p * reg;
 }
 
-// (the buffers of the PRE group -- xxt, uxt, tile, dsc, vfs, xs, us -- share memory with ws: no __restrict__ there)
+// (the buffers of the PRE group -- xxt, uxt, tile, vfs, xs, us -- share memory with ws, and dsc with nVxx / nVx / nlam:
+// no __restrict__ there)
 #define IPDDP_BW_POINTERS \
   double* __restrict__ lhs = sm + L::LHS; double* __restrict__ rhs = sm + L::RHS; \
   double* __restrict__ fx = sm + L::FX; double* __restrict__ fu = sm + L::FU; \
@@ -81,8 +82,7 @@ IPDDP_D double bw_next_reg(const DevView& v, double reg, double reg_last) {
   double* __restrict__ phi = sm + L::PHI; double* xs = sm + L::XS; double* us = sm + L::US; \
   double* __restrict__ lx = sm + L::LX; \
   double* tile = sm + L::TILE; double* vfs = sm + L::VFS; double* ws = sm + L::WS; double* dsc = sm + L::DSC; \
-  double* __restrict__ nVxx = sm + L::NEWV; double* __restrict__ nVx = sm + L::NEWV + NX * NX; \
-  double* __restrict__ nlam = sm + L::NEWV + NX * NX + NX; \
+  double* nVxx = sm + L::NEWV; double* nVx = sm + L::NEWV + NX * NX; double* nlam = sm + L::NEWV + NX * NX + NX; \
   unsigned char* smb = reinterpret_cast<unsigned char*>(sm); \
   unsigned char* nzlist = smb + L::LIST_B; \
   const MEntry* tbl = M::tbl(); \

@@ -491,10 +491,12 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
   double* bj = Bm + (act ? j : 0) * K;
   int k = 0;
   while (k < K) {
-    const unsigned long long cw = cinfo[k];
+    const unsigned long long cw = cinfo[k];      // column 0 carries an empty mask
     const int pv = S::ipiv_of(cw);
     const bool one = pv > 0;
-    const unsigned mlo = (k > 0) ? (unsigned)cw : 0u, mhi = (K > 32 && k > 0) ? nzhi[k] : 0u;
+    const unsigned mlo = (unsigned)cw;
+    unsigned mhi = 0u;
+    if (K > 32) mhi = nzhi[k];
     const bool any = (mlo | mhi) != 0u;
     double sa = 0.0, sb = 0.0;
     if (any) {
@@ -509,7 +511,7 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
           sa = IPDDP_FMA(xa[i], bv, sa);
           if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
         }
-        if (K > 32) {
+        if (K > 32 && mhi != 0u) {
           m = mhi & gm;
           while (m) {
             const int i = 32 + __ffs(m) - 1;
