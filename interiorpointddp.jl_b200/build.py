@@ -50,6 +50,27 @@ def _compile(src, verbose):
     return src, obj, r.returncode, r.stdout + r.stderr
 
 
+def build_variant(name: str, extra_flags, verbose: bool = False) -> str:
+    """A/B experiments: libipddp_b200_<name>.so compiled with extra nvcc flags (e.g. -DIPDDP_FW_MINBLOCKS=3).
+    Never loaded by the package; pass its path to tools/phase_bench.py."""
+    objdir = os.path.join(OBJ, name)
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for s in sources():
+        o = os.path.join(objdir, os.path.basename(s).replace(".cu", ".o"))
+        cmd = [NVCC] + FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}")
+        objs.append(o)
+    lib = os.path.join(HERE, f"libipddp_b200_{name}.so")
+    subprocess.check_call([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin",
+                                                                 "/usr/bin/g++", "-Xcompiler", "-fPIC", "-ldl"])
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     srcs = sources()

@@ -577,16 +577,26 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
     }
     return 0;
   };
+  // Speculative restarts spend 3 of 4 warps on sweeps that are usually discarded: worth it when the GPU is otherwise
+  // idle (the tail of a lone batch), not while another cohort still runs bulk rounds that could use those SM slots.
+  auto bulk_elsewhere = [&](const Cohort* self) -> bool {
+    for (int i = 0; i < n; ++i)
+      for (auto& c : hs[i]->cohorts)
+        if (&c != self && (c.state == INIT || (c.state == ROUND && c.n_active > 4096))) return true;
+    return false;
+  };
   auto enqueue_round = [&](ipddp_problem* h, Cohort& c) -> int {
     const int nn = c.n_active, cur = c.cur;
     cudaStream_t s = c.stream;
     h->st.iterations += 1;
     h->st.n_active_rounds += nn;
-    h->vt->derivs(h->v, c.d_list[cur], nn, s);
-    h->vt->backward(h->v, c.d_list[cur], nn, s);
+    DevView v = h->v;
+    if (nn > 32 && nn <= v.bw_spec_max && bulk_elsewhere(&c)) v.bw_spec_max = 32;
+    h->vt->derivs(v, c.d_list[cur], nn, s);
+    h->vt->backward(v, c.d_list[cur], nn, s);
     CK(cudaMemsetAsync(c.d_counters, 0, CNT_COUNT * sizeof(int), s));
-    h->vt->check(h->v, c.d_list[cur], nn, c.d_list[1 - cur], c.d_list_fwd, c.d_counters, s);
-    h->vt->forward(h->v, c.d_list_fwd, nn, c.d_list[1 - cur], c.d_counters, s);
+    h->vt->check(v, c.d_list[cur], nn, c.d_list[1 - cur], c.d_list_fwd, c.d_counters, s);
+    h->vt->forward(v, c.d_list_fwd, nn, c.d_list[1 - cur], c.d_counters, s);
     CK(cudaMemcpyAsync(c.h_counters, c.d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(c.ev, s));
     h->st.launches += 4;

@@ -31,6 +31,9 @@ namespace ipk {
 
 constexpr int FW_WARPS = 4;
 constexpr int FWS_WARPS = 8;
+#ifndef IPDDP_FW_MINBLOCKS
+#define IPDDP_FW_MINBLOCKS 3      // resident CTAs per SM the register allocation of k_forward is held to (168 registers; measured: 2 -> 65 ms, 3 -> 53 ms, 4 -> 77 ms per 12 bulk rounds)
+#endif
 
 template <class M> struct FwLayout : MeritLayout<M> {
   static size_t bytes(int N) { return (size_t)FW_WARPS * MeritLayout<M>::per_warp_doubles(N) * sizeof(double); }
@@ -269,7 +272,7 @@ IPDDP_D void fw_finish(const DevView& v, const FwState<M>& s, int* list_next, in
 }
 
 template <class M>
-__global__ void __launch_bounds__(FW_WARPS * 32) k_forward(DevView v, const int* list_fwd, int* list_next, int* counters) {
+__global__ void __launch_bounds__(FW_WARPS * 32, IPDDP_FW_MINBLOCKS) k_forward(DevView v, const int* list_fwd, int* list_next, int* counters) {
   IPDDP_DYN_SMEM(double, sm_all);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * FW_WARPS + warp;
