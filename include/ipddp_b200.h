@@ -105,7 +105,9 @@ int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt);
  * created afterwards.  Keys: "fw_spec_max" -- rounds with at most this many active instances run the forward pass with
  * one CTA per instance that tries 8 step sizes of the backtracking sequence at once (0 = never);
  * "bw_spec_max" -- rounds with at most this many active instances run the backward pass with one CTA per instance
- * that tries 4 values of the regularisation schedule at once (0 = never). */
+ * that tries 4 values of the regularisation schedule at once (0 = never);
+ * "bulk_slots" (global) -- ipddp_solve_many admits at most this many batches into their bulk rounds at the same time
+ * (default 2), so that the low-occupancy tail of one batch overlaps the bulk rounds of the next. */
 int ipddp_set_tuning(ipddp_problem* h, const char* key, int value);
 
 /* Per-timestep offset tables of the instance records (doubles from the start of one instance's

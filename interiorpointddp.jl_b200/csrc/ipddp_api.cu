@@ -36,6 +36,7 @@ namespace {
 thread_local std::string g_err;
 int g_fw_spec_max = 148;   // default for new problems: speculative line search when <= one CTA per SM is active
 int g_bw_spec_max = 592;   // speculative restarts when <= 4 CTAs (16 warps) per SM are active
+int g_bulk_slots = 2;      // ipddp_solve_many: batches admitted into their bulk rounds at the same time
 int fail(const std::string& m) { g_err = m; return -1; }
 #define CK(call)                                                                                    \
   do {                                                                                              \
@@ -364,6 +365,10 @@ int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
     h->v.fw_spec_max = value;
     return 0;
   }
+  if (k == "bulk_slots") {
+    g_bulk_slots = value < 1 ? 1 : value;
+    return 0;
+  }
   if (k == "bw_spec_max") {
     if (value < 0) value = 0;
     if (!h) { g_bw_spec_max = value; return 0; }
@@ -558,7 +563,7 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
   ipddp_stats tot;
   memset(&tot, 0, sizeof(tot));
   enum { IDLE = 0, INIT = 1, ROUND = 2, CDONE = 3 };           // cohort states
-  enum { H_RUNNING = 0, H_STATS = 1, H_FINISHED = 2 };          // handle states
+  enum { H_RUNNING = 0, H_STATS = 1, H_FINISHED = 2, H_WAITING = 3 };   // handle states
   int started = 0, finished = 0;
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(hs[0]->ev[6], hs[0]->stream));
@@ -602,15 +607,41 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
     h->st.launches += 4;
     return 0;
   };
-  for (int i = 0; i < n; ++i) {
-    if (enqueue_init(hs[i]) != 0) return -1;
-    started++;
-  }
+  // Admission: batches are started staggered, at most g_bulk_slots of them in their bulk rounds at a time.  Batches
+  // that start together run their low-occupancy middle and tail rounds together, which is exactly what overlapping
+  // batches is meant to avoid; a batch is admitted when an earlier one has dropped below B/8 active instances.
+  for (int i = 0; i < n; ++i) hs[i]->hstate = H_WAITING;
+  std::vector<int> runs(n, 0);
+  auto in_bulk = [&](ipddp_problem* h) -> bool {
+    if (h->hstate != H_RUNNING) return false;
+    long long act = 0;
+    for (auto& c : h->cohorts) {
+      if (c.state == INIT) return true;
+      if (c.state == ROUND) act += c.n_active;
+    }
+    return act * 8 > h->v.B;
+  };
+  auto admit = [&]() -> int {
+    int bulk = 0;
+    for (int i = 0; i < n; ++i) bulk += in_bulk(hs[i]) ? 1 : 0;
+    while (bulk < g_bulk_slots && started < total_solves) {
+      int pick = -1;     // the waiting handle that has run least often in this call (every handle runs at least once)
+      for (int i = 0; i < n; ++i)
+        if (hs[i]->hstate == H_WAITING && (pick < 0 || runs[i] < runs[pick])) pick = i;
+      if (pick < 0) break;
+      if (enqueue_init(hs[pick]) != 0) return -1;
+      runs[pick]++;
+      started++;
+      bulk++;
+    }
+    return 0;
+  };
   while (finished < total_solves) {
     bool progressed = false;
+    if (admit() != 0) return -1;
     for (int i = 0; i < n; ++i) {
       ipddp_problem* h = hs[i];
-      if (h->hstate == H_FINISHED) continue;
+      if (h->hstate == H_FINISHED || h->hstate == H_WAITING) continue;
       if (h->hstate == H_STATS) {
         cudaError_t q = cudaEventQuery(h->ev[5]);
         if (q == cudaErrorNotReady) continue;
@@ -629,13 +660,8 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
           tot.n_converged += (h->h_si[(size_t)SI_STATUS * B + b] == 0);
         }
         finished++;
-        if (started < total_solves) {
-          if (enqueue_init(h) != 0) return -1;
-          started++;
-        } else {
-          CK(cudaEventRecord(h->ev[7], h->stream));
-          h->hstate = H_FINISHED;
-        }
+        CK(cudaEventRecord(h->ev[7], h->stream));        // end of this handle's latest solve
+        h->hstate = (started < total_solves) ? H_WAITING : H_FINISHED;
         continue;
       }
       for (auto& c : h->cohorts) {

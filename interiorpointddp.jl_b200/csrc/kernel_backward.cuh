@@ -186,7 +186,13 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
     __syncwarp();
     // ---- barrier terms, Qu, dual-infeasibility numerator            (src/backward_pass.jl:62-75)
     for (int i = lane; i < NU; i += 32) {
-      const double a1 = 1.0 / r[R::IL + i], a2 = 1.0 / r[R::IU + i];
+      // 1/il, 1/iu.  Unbounded controls have il / iu = +Inf (Q1): 1/Inf = 0 exactly, but the FP64 reciprocal would take
+      // its slow path for it, so those lanes divide 1 by 1 and select the zero afterwards
+      const double il_ = r[R::IL + i], iu_ = r[R::IU + i];
+      const bool il_inf = il_ > 1.7976931348623157e308, iu_inf = iu_ > 1.7976931348623157e308;
+      double a1 = 1.0 / (il_inf ? 1.0 : il_), a2 = 1.0 / (iu_inf ? 1.0 : iu_);
+      a1 = il_inf ? 0.0 : a1;
+      a2 = iu_inf ? 0.0 : a2;
       const double zl_i = r[R::ZL + i], zu_i = r[R::ZU + i];
       const double cl = a1 * mu, cu_ = a2 * mu;
       ra1[i] = a1; ra2[i] = a2;

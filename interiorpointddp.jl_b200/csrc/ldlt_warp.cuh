@@ -55,6 +55,30 @@ IPDDP_D unsigned tri_decode(int p) {
   return (unsigned)(p - coff(b)) | ((unsigned)b << 8);
 }
 
+// x / d for many numerators x and one divisor d.  With rd = RN(1/d) (one real division), q = RN(x*rd),
+// r = x - d*q (exact in one FMA) and RN(q + r*rd) is the correctly rounded quotient (Markstein's theorem) as long as
+// nothing under- or overflows; operands outside [2^-400, 2^400] (zeros, infinities, NaNs, denormals) take the plain
+// division, except +-0 / d which is x*rd exactly.  3 instructions instead of ~25 -- and the plain FP64 division falls
+// into a ~60-instruction slow path for zero numerators, which KKT matrices with a zero block produce all the time.
+struct DivBy {
+  double d, rd;
+  bool ok;
+  IPDDP_D explicit DivBy(double d_) : d(d_), rd(1.0 / d_) {
+    const double a = fabs(d_);
+    ok = a >= 0x1p-400 && a <= 0x1p400;
+  }
+  IPDDP_D double operator()(double x) const {
+    const double ax = fabs(x);
+    if (ok && ax >= 0x1p-400 && ax <= 0x1p400) {
+      const double q = x * rd;
+      const double r = IPDDP_FMA(-d, q, x);
+      return IPDDP_FMA(r, rd, q);
+    }
+    if (ok && x == 0.0) return x * rd;
+    return x / d;
+  }
+};
+
 // Maximum of the non-negative candidates (v0 at index lane, v1 at index lane+32; vld* = candidate present)
 // and the 64-bit mask of the indices that attain it.
 template <bool TWO>
@@ -249,14 +273,20 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
     double* xk = A + ck;
     double* xkm1 = A + coff(k - 1);
     const double d12 = xk[k - 1];
+    const DivBy by12(d12);
+    // D^-1 scaled by d12 (dsytf2_rook / dsytrs_rook): d22 = a(k-1,k-1)/d12, d11 = a(k,k)/d12, denom = d11*d22 - 1
+    const double d22 = by12(xkm1[k - 1]);
+    const double d11 = by12(xk[k]);
+    const DivBy bydn(d11 * d22 - 1.0);
     {   // inertia of the 2x2 block (reference inertia!, atol = tol)
       const double e11 = xkm1[k - 1], e22 = xk[k];
       if (d12 != 0.0) {
         const double a11 = fabs(e11), a22 = fabs(e22);
         const double s1 = 2.0 * fmax(fmax(a11, fabs(d12)), a22);
+        const DivBy bys(s1);
         double smin;
-        if (a11 >= a22) smin = fabs((e11 / s1) * e22 - (d12 / s1) * d12);
-        else            smin = fabs(e11 * (e22 / s1) - (d12 / s1) * d12);
+        if (a11 >= a22) smin = fabs(bys(e11) * e22 - bys(d12) * d12);
+        else            smin = fabs(e11 * bys(e22) - bys(d12) * d12);
         const double trace = e11 + e22;
         if (0.5 * s1 <= tol) {
         } else if (smin > tol || trace == 0.0) {
@@ -274,9 +304,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
     bool f[2] = {false, false};
     if (k > 1) {
       const int m = k - 1;   // rows/columns 0..m-1 get updated
-      const double d22 = xkm1[k - 1] / d12;
-      const double d11 = xk[k] / d12;
-      const double t = 1.0 / (d11 * d22 - 1.0);
+      const double t = bydn.rd;   // 1.0 / (d11 * d22 - 1.0)
       double* wk = w; double* wkm1 = w + K; double* rk = w + 2 * K; double* rkm1 = w + 3 * K;
 #pragma unroll
       for (int s = 0; s < (TWO ? 2 : 1); ++s) {
@@ -287,8 +315,8 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
           if (f[s]) {
             wkm1[j] = t * (d11 * akm1 - ak);
             wk[j] = t * (d22 * ak - akm1);
-            rk[j] = ak / d12;
-            rkm1[j] = akm1 / d12;
+            rk[j] = by12(ak);
+            rkm1[j] = by12(akm1);
           }
         }
       }
@@ -305,8 +333,8 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       for (int s = 0; s < (TWO ? 2 : 1); ++s) {
         const int j = lane + 32 * s;
         if (f[s]) {
-          xk[j] = wk[j] / d12;
-          xkm1[j] = wkm1[j] / d12;
+          xk[j] = by12(wk[j]);
+          xkm1[j] = by12(wkm1[j]);
         }
       }
       __syncwarp();
@@ -330,14 +358,11 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
     }
     __syncwarp();
     if (lane < NR) {
-      const double akm1k = d12;
-      const double akm1 = xkm1[k - 1] / akm1k;
-      const double ak = xk[k] / akm1k;
-      const double denom = akm1 * ak - 1.0;
-      const double bkm1 = Bm[k - 1 + lane * K] / akm1k;
-      const double bk = Bm[k + lane * K] / akm1k;
-      Bm[k - 1 + lane * K] = (ak * bkm1 - bk) / denom;
-      Bm[k + lane * K] = (akm1 * bk - bkm1) / denom;
+      // akm1 = a(k-1,k-1)/d12 = d22, ak = a(k,k)/d12 = d11, denom = akm1*ak - 1 = d11*d22 - 1 (same product)
+      const double bkm1 = by12(Bm[k - 1 + lane * K]);
+      const double bk = by12(Bm[k + lane * K]);
+      Bm[k - 1 + lane * K] = bydn(d11 * bkm1 - bk);
+      Bm[k + lane * K] = bydn(d22 * bk - bkm1);
     }
     __syncwarp();
   }

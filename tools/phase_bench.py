@@ -25,6 +25,8 @@ def run(lib, wl, B, N, rounds):
     s.set_batch(b)
     s.initialize()
     rows = []
+    series = os.environ.get("IPDDP_SERIES", "") != ""
+    prev = None
     for r in range(rounds):
         t0 = time.perf_counter(); s.eval_derivatives()
         t1 = time.perf_counter(); s.backward_pass()
@@ -32,6 +34,18 @@ def run(lib, wl, B, N, rounds):
         t3 = time.perf_counter(); s.forward_pass()
         t4 = time.perf_counter()
         rows.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3, nf))
+        if series:
+            c = s.counters()
+            if prev is not None or True:
+                p0 = prev or {k: np.zeros_like(v) for k, v in c.items()}
+                dk = int((c["n_kkt"] - p0["n_kkt"]).sum()); ds = int((c["n_sweeps"] - p0["n_sweeps"]).sum())
+                db = int((c["n_backward"] - p0["n_backward"]).sum()); dr = int((c["n_rollouts"] - p0["n_rollouts"]).sum())
+                mx = int((c["n_sweeps"] - p0["n_sweeps"]).max())
+                print(json.dumps(dict(round=r, active=db, sweeps=ds, max_sweeps=mx, kkt=dk, bw_ms=round(rows[-1][1], 2),
+                                      Mkkt_per_s=round(dk / rows[-1][1] / 1e3, 2), fw_ms=round(rows[-1][3], 2), rollouts=dr)), flush=True)
+            prev = {k: v.copy() for k, v in c.items()}
+            if db == 0:
+                break
     cnt = s.counters()
     s.close()
     a = np.array([r[:4] for r in rows])
