@@ -15,6 +15,10 @@
 #pragma once
 #include "ldlt_warp.cuh"
 
+#ifndef IPDDP_BW_MINBLOCKS
+#define IPDDP_BW_MINBLOCKS 20     // resident warps per SM the register allocation of k_backward is held to (96 registers)
+#endif
+
 namespace ipk {
 
 template <class M> struct BwLayout {
@@ -397,7 +401,7 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
 }
 
 template <class M>
-__global__ void __launch_bounds__(32, 20) k_backward(DevView v, const int* list, int n_list) {
+__global__ void __launch_bounds__(32, IPDDP_BW_MINBLOCKS) k_backward(DevView v, const int* list, int n_list) {
   IPDDP_DYN_SMEM(double, sm);
   const int lane = threadIdx.x;
   const int inst = blockIdx.x;

@@ -42,6 +42,10 @@ extern "C" long long g_ipddp_ldlt_steps[3];
 #define IPDDP_LDLT_COUNT(w) do { } while (0)
 #endif
 
+#ifndef IPDDP_ONE_GENERIC
+#define IPDDP_ONE_GENERIC 0
+#endif
+
 namespace ipk {
 
 IPDDP_D int coff(int j) { return (j * (j + 1)) >> 1; }
@@ -479,7 +483,11 @@ IPDDP_D int warp_ldlt_factor(double* __restrict__ A, double* __restrict__ Bm, do
       k -= 1;
       continue;
     }
+#if IPDDP_ONE_GENERIC
+    const int ks = ldlt_step<K, NR, (K > 32)>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);   // one instance of the general step
+#else
     const int ks = ldlt_step<K, NR, false>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
+#endif
     IPDDP_LDLT_COUNT(ks);
     k -= ks;
   }
