@@ -107,7 +107,7 @@ int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt);
  * "bw_spec_max" -- rounds with at most this many active instances run the backward pass with one CTA per instance
  * that tries 4 values of the regularisation schedule at once (0 = never);
  * "bulk_slots" (global) -- ipddp_solve_many admits at most this many batches into their bulk rounds at the same time
- * (default 2), so that the low-occupancy tail of one batch overlaps the bulk rounds of the next. */
+ * (default 3), so that the low-occupancy tail of one batch overlaps the bulk rounds of the next. */
 int ipddp_set_tuning(ipddp_problem* h, const char* key, int value);
 
 /* Per-timestep offset tables of the instance records (doubles from the start of one instance's
@@ -182,7 +182,8 @@ double ipddp_measure_fp64_tflops(int device);
 double ipddp_measure_hbm_gbs(int device);
 
 /* Kernel-level test hooks (used by tests/ only).
- *   ipddp_test_detmath: elementwise device evaluation of the deterministic math layer;
+ *   ipddp_test_detmath: elementwise device evaluation of the deterministic math layer (fn 0..5) and of the
+ *       reciprocal-based exact division x / y used inside the LDLT (fn 6);
  *       fn 0 sin, 1 cos, 2 tan, 3 log, 4 exp, 5 pow(x[i], y[i]).
  *   ipddp_test_ldlt: one warp per matrix runs the device dsytf2_rook('U') / inertia / dsytrs_rook path on
  *       nmat dense column-major n x n matrices (upper triangle read) with 5 right-hand sides each.

@@ -36,7 +36,7 @@ namespace {
 thread_local std::string g_err;
 int g_fw_spec_max = 148;   // default for new problems: speculative line search when <= one CTA per SM is active
 int g_bw_spec_max = 592;   // speculative restarts when <= 4 CTAs (16 warps) per SM are active
-int g_bulk_slots = 2;      // ipddp_solve_many: batches admitted into their bulk rounds at the same time
+int g_bulk_slots = 3;      // ipddp_solve_many: batches admitted into their bulk rounds at the same time
 int fail(const std::string& m) { g_err = m; return -1; }
 #define CK(call)                                                                                    \
   do {                                                                                              \
@@ -93,6 +93,7 @@ __global__ void k_test_detmath(int fn, int n, const double* x, const double* y, 
     case 2: r = dm::tan(x[i]); break;
     case 3: r = dm::log(x[i]); break;
     case 4: r = dm::exp(x[i]); break;
+    case 6: r = ipk::DivBy(y[i])(x[i]); break;     // x / y through the reciprocal-based exact division of the LDLT
     default: r = dm::pow(x[i], y[i]); break;
   }
   out[i] = r;

@@ -243,3 +243,28 @@ def detmath_parity(lib, oracle, rng, n=200000, device=0):
     x = np.ascontiguousarray(rng.uniform(1e-9, 3, n)); y = np.ascontiguousarray(rng.uniform(-3, 4, n)); out = np.zeros_like(x)
     lib.check(lib.L.ipddp_test_detmath(5, n, x.ctypes.data_as(dp), y.ctypes.data_as(dp), out.ctypes.data_as(dp), device), "detmath")
     assert np.array_equal(bits(out), bits(oracle.detmath(5, x, y)))
+
+
+def division_parity(lib, rng, n=400000, device=0):
+    """The reciprocal-based division used in the 2x2 pivot path (csrc/ldlt_warp.cuh: DivBy, Markstein's sequence with a
+    plain-division fallback for out-of-range operands) returns the correctly rounded quotient, i.e. the bits of x / y."""
+    dp = C.POINTER(C.c_double)
+
+    def rnd(lo, hi, m):   # random sign, random mantissa, exponent uniform in [lo, hi]
+        return rng.choice([-1.0, 1.0], m) * rng.uniform(1.0, 2.0, m) * np.exp2(rng.integers(lo, hi + 1, m).astype(np.float64))
+    xs = [rnd(-60, 60, n), rnd(-390, 390, n), rnd(-1020, 1020, n // 4), rnd(-10, 10, n // 4)]
+    ys = [rnd(-60, 60, n), rnd(-390, 390, n), rnd(-1020, 1020, n // 4), rnd(-10, 10, n // 4)]
+    # divisors / numerators with extreme mantissas (all ones, all zeros), zeros, infinities, NaN, denormals
+    edge = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+                     np.nextafter(2.0, 1.0), np.nextafter(1.0, 2.0), 3.0, 1.0 / 3.0, 2.0 ** -400, 2.0 ** 400, 2.0 ** -401, 2.0 ** 401])
+    ex, ey = np.meshgrid(edge, edge)
+    xs.append(ex.ravel()); ys.append(ey.ravel())
+    ones = np.nextafter(np.exp2(rng.integers(-50, 50, n // 4).astype(np.float64)) * 2.0, 0.0)   # mantissa all ones
+    xs.append(rnd(-50, 50, n // 4)); ys.append(ones)
+    xs.append(ones); ys.append(rnd(-50, 50, n // 4))
+    x = np.ascontiguousarray(np.concatenate(xs)); y = np.ascontiguousarray(np.concatenate(ys)); out = np.zeros_like(x)
+    lib.check(lib.L.ipddp_test_detmath(6, x.size, x.ctypes.data_as(dp), y.ctypes.data_as(dp), out.ctypes.data_as(dp), device), "division")
+    with np.errstate(all="ignore"):
+        ref = x / y
+    same = (bits(out) == bits(ref)) | (np.isnan(out) & np.isnan(ref))
+    assert same.all(), f"{int((~same).sum())} quotients differ, first: {x[~same][0]!r} / {y[~same][0]!r} -> {out[~same][0]!r} vs {ref[~same][0]!r}"

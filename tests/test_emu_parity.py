@@ -52,6 +52,10 @@ def test_emulated_ldlt(emu, oracle_mod):
     helpers.ldlt_parity(emu, oracle_mod, np.random.default_rng(3), nmat=24, nmax=35)
 
 
+def test_emulated_exact_division(emu):
+    helpers.division_parity(emu, np.random.default_rng(6), n=100000)
+
+
 def test_emulated_detmath(emu, oracle_mod):
     helpers.detmath_parity(emu, oracle_mod, np.random.default_rng(4), n=5000)
 

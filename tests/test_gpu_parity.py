@@ -22,6 +22,10 @@ def test_detmath_bit_exact(gpu, oracle_mod):
     helpers.detmath_parity(gpu, oracle_mod, np.random.default_rng(4), n=200000)
 
 
+def test_exact_division_bit_exact(gpu):
+    helpers.division_parity(gpu, np.random.default_rng(5))
+
+
 def test_ldlt_bit_exact(gpu, oracle_mod):
     helpers.ldlt_parity(gpu, oracle_mod, np.random.default_rng(3), nmat=400, nmax=35)
 

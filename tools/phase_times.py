@@ -7,9 +7,9 @@ import ipddp_b200
 from ipddp_b200 import _lib, instances
 from ipddp_b200.batch import BatchSolver
 
-def run(wl, B, N=101, reps=1):
+def run(wl, B, N=int(os.environ.get('IPDDP_KNOTS', '101')), reps=1):
     lib = _lib.load()
-    b = instances.make_batch(wl, B, N)
+    b = instances.make_batch(wl, B, N, vary_horizon=os.environ.get('IPDDP_VARY_HORIZON', '') != '')
     s = BatchSolver(wl, B, N, options=lib.default_options(optimality_tolerance=1e-7), lib=lib)
     s.set_batch(b)
     out = None

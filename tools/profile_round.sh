@@ -18,4 +18,11 @@ ncu --set full --import-source on --clock-control none -k regex:k_backward --lau
     -o $O/bw_lone_$TAG python tools/phase_bench.py cartpole 8 8 > $O/ncu_bw_lone_$TAG.log 2>&1
 ncu --set full --clock-control none -k regex:k_derivs --launch-skip 1 --launch-count 1 -f \
     -o $O/derivs_$TAG python tools/phase_bench.py cartpole 16384 3 > $O/ncu_derivs_$TAG.log 2>&1
-tail -2 $O/ncu_bw_bulk_$TAG.log; ls -la $O/*_$TAG.ncu-rep
+ncu --set full --import-source on --clock-control none -k regex:k_backward --launch-skip 36 --launch-count 1 -f \
+    -o $O/bw_mid_$TAG python tools/phase_bench.py cartpole 16384 38 > $O/ncu_bw_mid_$TAG.log 2>&1
+# per-round series of the headline batch and the other BASELINE configs (one sequential solve each)
+IPDDP_SERIES=1 python tools/phase_bench.py cartpole 16384 100 > $O/series_$TAG.log 2>&1
+python tools/phase_bench.py cartpole 8 12 > $O/lone_$TAG.log 2>&1
+{ IPDDP_KNOTS=201 python tools/phase_times.py acrobot 8192; python tools/phase_times.py acrobot 8192; python tools/phase_times.py concar 4096;
+  python tools/phase_times.py concar_quad 4096; IPDDP_KNOTS=141 IPDDP_VARY_HORIZON=1 python tools/phase_times.py pushing 2048; } > $O/configs_$TAG.log 2>&1
+tail -2 $O/ncu_bw_bulk_$TAG.log; cat $O/configs_$TAG.log; tail -1 $O/lone_$TAG.log; ls -la $O/*_$TAG.ncu-rep
