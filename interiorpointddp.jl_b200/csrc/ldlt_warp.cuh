@@ -43,7 +43,10 @@ extern "C" long long g_ipddp_ldlt_steps[3];
 #endif
 
 #ifndef IPDDP_ONE_GENERIC
-#define IPDDP_ONE_GENERIC 0
+#define IPDDP_ONE_GENERIC 1       // one instance of the general pivot step for all k (measured: -3.4 % sweep time vs two)
+#endif
+#ifndef IPDDP_DIV_NOINLINE
+#define IPDDP_DIV_NOINLINE 0
 #endif
 
 namespace ipk {
@@ -64,6 +67,14 @@ IPDDP_D unsigned tri_decode(int p) {
 // nothing under- or overflows; operands outside [2^-400, 2^400] (zeros, infinities, NaNs, denormals) take the plain
 // division, except +-0 / d which is x*rd exactly.  3 instructions instead of ~25 -- and the plain FP64 division falls
 // into a ~60-instruction slow path for zero numerators, which KKT matrices with a zero block produce all the time.
+#if IPDDP_DIV_NOINLINE
+// out-of-range operands (rare): one shared copy of the plain division instead of one per call site
+static __device__ __noinline__ double ldlt_div_rare(double x, double d, double rd, bool ok) {
+  if (ok && x == 0.0) return x * rd;
+  return x / d;
+}
+#endif
+
 struct DivBy {
   double d, rd;
   bool ok;
@@ -78,24 +89,28 @@ struct DivBy {
       const double r = IPDDP_FMA(-d, q, x);
       return IPDDP_FMA(r, rd, q);
     }
+#if IPDDP_DIV_NOINLINE
+    return ldlt_div_rare(x, d, rd, ok);
+#else
     if (ok && x == 0.0) return x * rd;
     return x / d;
+#endif
   }
 };
 
 // Maximum of the non-negative candidates (v0 at index lane, v1 at index lane+32; vld* = candidate present)
 // and the 64-bit mask of the indices that attain it.
 template <bool TWO>
-IPDDP_D double warp_max_ties(double v0, bool vld0, double v1, bool vld1, unsigned long long& ties) {
+IPDDP_D double warp_max_ties(double v0, bool vld0, double v1, bool vld1, unsigned long long& ties, bool two = TWO) {
   const unsigned h0 = vld0 ? (unsigned)__double2hiint(v0) : 0u, l0 = vld0 ? (unsigned)__double2loint(v0) : 0u;
-  const unsigned h1 = (TWO && vld1) ? (unsigned)__double2hiint(v1) : 0u, l1 = (TWO && vld1) ? (unsigned)__double2loint(v1) : 0u;
-  const unsigned mh = __reduce_max_sync(IPDDP_FULL_MASK, TWO ? (h0 > h1 ? h0 : h1) : h0);
+  const unsigned h1 = (two && vld1) ? (unsigned)__double2hiint(v1) : 0u, l1 = (two && vld1) ? (unsigned)__double2loint(v1) : 0u;
+  const unsigned mh = __reduce_max_sync(IPDDP_FULL_MASK, two ? (h0 > h1 ? h0 : h1) : h0);
   unsigned lc = (h0 == mh) ? l0 : 0u;
-  if (TWO) { const unsigned lc1 = (h1 == mh) ? l1 : 0u; lc = lc > lc1 ? lc : lc1; }
+  if (two) { const unsigned lc1 = (h1 == mh) ? l1 : 0u; lc = lc > lc1 ? lc : lc1; }
   const unsigned ml = __reduce_max_sync(IPDDP_FULL_MASK, lc);
   const unsigned m0 = __ballot_sync(IPDDP_FULL_MASK, vld0 && h0 == mh && l0 == ml);
   unsigned long long t = m0;
-  if (TWO) t |= (unsigned long long)__ballot_sync(IPDDP_FULL_MASK, vld1 && h1 == mh && l1 == ml) << 32;
+  if (two) t |= (unsigned long long)__ballot_sync(IPDDP_FULL_MASK, vld1 && h1 == mh && l1 == ml) << 32;
   ties = t;
   return __hiloint2double((int)mh, (int)ml);
 }
@@ -103,10 +118,11 @@ IPDDP_D double warp_max_ties(double v0, bool vld0, double v1, bool vld1, unsigne
 // symmetric interchange of rows/columns a < b inside the leading (b+1)x(b+1) block (dsytf2_rook style:
 // trailing columns are NOT touched)
 template <bool TWO>
-IPDDP_D void warp_sym_swap(double* A, int a, int b, int lane) {
+IPDDP_D void warp_sym_swap(double* A, int a, int b, int lane, bool two = TWO) {
   const int ca = coff(a), cb = coff(b);
 #pragma unroll
   for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+    if (s == 1 && !two) continue;
     const int i = lane + 32 * s;
     if (i < b && i != a) {
       const int pa = (i < a) ? ca + i : coff(i) + a, pb = cb + i;
@@ -121,13 +137,13 @@ IPDDP_D void warp_sym_swap(double* A, int a, int b, int lane) {
 // compacts the indices i (< 64) flagged by (f0 at lane, f1 at lane+32) into list[] ascending; returns count,
 // m0 / m1 = the flag masks
 template <bool TWO>
-IPDDP_D int warp_compact(bool f0, bool f1, unsigned char* list, int lane, unsigned& m0, unsigned& m1) {
+IPDDP_D int warp_compact(bool f0, bool f1, unsigned char* list, int lane, unsigned& m0, unsigned& m1, bool two = TWO) {
   m0 = __ballot_sync(IPDDP_FULL_MASK, f0);
   m1 = 0u;
   const unsigned lt = (1u << lane) - 1u;
   if (f0) list[__popc(m0 & lt)] = (unsigned char)lane;
   int n = __popc(m0);
-  if (TWO) {
+  if (two) {
     m1 = __ballot_sync(IPDDP_FULL_MASK, f1);
     if (f1) list[n + __popc(m1 & lt)] = (unsigned char)(lane + 32);
     n += __popc(m1);
@@ -175,6 +191,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
   const double alpha = 0.6403882032022076;   // (1 + sqrt(17)) / 8
   const double sfmin = 2.2250738585072014e-308;
   const int i0 = lane, i1 = lane + 32;
+  const bool two = TWO && k >= 32;     // rows >= 32 exist in the leading block: uniform, so one instance serves every k
   int kstep = 1, p = k, kp = k;
   const int ck = coff(k);
   const double absakk = fabs(A[ck + k]);
@@ -182,8 +199,8 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
   int imax = 0;
   if (k > 0) {
     unsigned long long ties;
-    const bool v0 = i0 < k, v1 = TWO && i1 < k;
-    colmax = warp_max_ties<TWO>(v0 ? fabs(A[ck + i0]) : 0.0, v0, v1 ? fabs(A[ck + i1]) : 0.0, v1, ties);
+    const bool v0 = i0 < k, v1 = two && i1 < k;
+    colmax = warp_max_ties<TWO>(v0 ? fabs(A[ck + i0]) : 0.0, v0, v1 ? fabs(A[ck + i1]) : 0.0, v1, ties, two);
     imax = __ffsll((long long)ties) - 1;
   }
   if (fmax(absakk, colmax) == 0.0) {
@@ -197,11 +214,11 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       // largest off-diagonal magnitude in row/column imax of the leading block; ties: the row segment
       // (c > imax) is searched first and wins, lowest index inside a segment
       const int ci = coff(imax);
-      const bool v0 = i0 <= k && i0 != imax, v1 = TWO && i1 <= k && i1 != imax;
+      const bool v0 = i0 <= k && i0 != imax, v1 = two && i1 <= k && i1 != imax;
       const double a0 = v0 ? fabs(i0 < imax ? A[ci + i0] : A[coff(i0) + imax]) : 0.0;
       const double a1 = v1 ? fabs(i1 < imax ? A[ci + i1] : A[coff(i1) + imax]) : 0.0;
       unsigned long long ties;
-      const double rowmax = warp_max_ties<TWO>(a0, v0, a1, v1, ties);
+      const double rowmax = warp_max_ties<TWO>(a0, v0, a1, v1, ties, two);
       const unsigned long long rowpart = ties & ~((2ull << imax) - 1ull);
       const int jmax = __ffsll((long long)(rowpart ? rowpart : ties)) - 1;
       if (!(fabs(A[ci + imax]) < alpha * rowmax)) { kp = imax; break; }
@@ -211,13 +228,13 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
   }
   __syncwarp();
   if (kstep == 2 && p != k) {   // first interchange: k <-> p  (matrix and right-hand sides)
-    warp_sym_swap<TWO>(A, p, k, lane);
+    warp_sym_swap<TWO>(A, p, k, lane, two);
     warp_swap_rows<NR>(Bm, K, k, p, lane);
     __syncwarp();
   }
   const int kk = k - kstep + 1;
   if (kp != kk) {               // second interchange: kk <-> kp
-    warp_sym_swap<TWO>(A, kp, kk, lane);
+    warp_sym_swap<TWO>(A, kp, kk, lane, two);
     if (kstep == 2 && lane == 0) {
       const int pa = pk(k - 1, k), pb = pk(kp, k);
       const double t = A[pa]; A[pa] = A[pb]; A[pb] = t;
@@ -237,13 +254,13 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
     if (k > 0) {
       double* x = A + ck;
       x0 = (i0 < k) ? x[i0] : 0.0;
-      x1 = (TWO && i1 < k) ? x[i1] : 0.0;
-      nnz = warp_compact<TWO>(x0 != 0.0, x1 != 0.0, list, lane, m0, m1);
+      x1 = (two && i1 < k) ? x[i1] : 0.0;
+      nnz = warp_compact<TWO>(x0 != 0.0, x1 != 0.0, list, lane, m0, m1, two);
       if (nnz > 0) {
         __syncwarp();
         if (!big) {   // tiny pivot: LAPACK divides the column first, then updates with -akk
           if (x0 != 0.0) { x0 = x0 / akk; x[i0] = x0; }
-          if (TWO && x1 != 0.0) { x1 = x1 / akk; x[i1] = x1; }
+          if (two && x1 != 0.0) { x1 = x1 / akk; x[i1] = x1; }
           __syncwarp();
         }
         const int P = (nnz * (nnz + 1)) >> 1;
@@ -256,7 +273,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
         if (big) {    // scale the multipliers (registers keep the scaled values for the B downdate)
           __syncwarp();
           if (x0 != 0.0) { x0 = x0 * d11; x[i0] = x0; }
-          if (TWO && x1 != 0.0) { x1 = x1 * d11; x[i1] = x1; }
+          if (two && x1 != 0.0) { x1 = x1 * d11; x[i1] = x1; }
         }
       }
     }
@@ -266,7 +283,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
 #pragma unroll
       for (int j = 0; j < NR; ++j) Bm[i0 + j * K] = IPDDP_FMA(x0, -Bm[k + j * K], Bm[i0 + j * K]);
     }
-    if (TWO && x1 != 0.0) {
+    if (two && x1 != 0.0) {
 #pragma unroll
       for (int j = 0; j < NR; ++j) Bm[i1 + j * K] = IPDDP_FMA(x1, -Bm[k + j * K], Bm[i1 + j * K]);
     }
@@ -312,6 +329,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       double* wk = w; double* wkm1 = w + K; double* rk = w + 2 * K; double* rkm1 = w + 3 * K;
 #pragma unroll
       for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+        if (s == 1 && !two) continue;
         const int j = lane + 32 * s;
         if (j < m) {
           const double ak = xk[j], akm1 = xkm1[j];
@@ -324,7 +342,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
           }
         }
       }
-      nnz = warp_compact<TWO>(f[0], f[1], list, lane, m0, m1);
+      nnz = warp_compact<TWO>(f[0], f[1], list, lane, m0, m1, two);
       __syncwarp();
       const int P = (nnz * (nnz + 1)) >> 1;
       for (int pp = lane; pp < P; pp += 32) {
@@ -335,6 +353,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       }
 #pragma unroll
       for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+        if (s == 1 && !two) continue;
         const int j = lane + 32 * s;
         if (f[s]) {
           xk[j] = by12(wk[j]);
@@ -350,6 +369,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
     // dsytrs first loop for the 2x2 block: two rank-1 downdates of B, then the 2x2 solve
 #pragma unroll
     for (int s = 0; s < (TWO ? 2 : 1); ++s) {
+      if (s == 1 && !two) continue;
       const int i = lane + 32 * s;
       if (f[s]) {
         const double xa = xk[i], xb = xkm1[i];
@@ -484,7 +504,8 @@ IPDDP_D int warp_ldlt_factor(double* __restrict__ A, double* __restrict__ Bm, do
       continue;
     }
 #if IPDDP_ONE_GENERIC
-    const int ks = ldlt_step<K, NR, (K > 32)>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);   // one instance of the general step
+    // one instance of the general step for every k (rows >= 32 are gated by a uniform run-time flag): half the code
+    const int ks = ldlt_step<K, NR, (K > 32)>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
 #else
     const int ks = ldlt_step<K, NR, false>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
 #endif
