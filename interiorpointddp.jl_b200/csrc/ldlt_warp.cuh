@@ -98,6 +98,16 @@ struct DivBy {
   }
 };
 
+#ifndef IPDDP_TRI_NOINLINE
+#define IPDDP_TRI_NOINLINE 0
+#endif
+#if IPDDP_TRI_NOINLINE
+// pairs beyond the two cached per lane (more than 10 non-zero rows in a pivot column: rare): one out-of-line copy
+static __device__ __noinline__ unsigned tri_decode_rare(int p) { return tri_decode(p); }
+#else
+IPDDP_D unsigned tri_decode_rare(int p) { return tri_decode(p); }
+#endif
+
 // Maximum of the non-negative candidates (v0 at index lane, v1 at index lane+32; vld* = candidate present)
 // and the 64-bit mask of the indices that attain it.
 template <bool TWO>
@@ -265,7 +275,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
         }
         const int P = (nnz * (nnz + 1)) >> 1;
         for (int pp = lane; pp < P; pp += 32) {
-          const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode(pp);
+          const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode_rare(pp);
           const int i = list[q & 0xff], j = list[q >> 8];
           const int e = coff(j) + i;
           A[e] = IPDDP_FMA(x[i], -d11 * x[j], A[e]);
@@ -346,7 +356,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       __syncwarp();
       const int P = (nnz * (nnz + 1)) >> 1;
       for (int pp = lane; pp < P; pp += 32) {
-        const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode(pp);
+        const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode_rare(pp);
         const int i = list[q & 0xff], j = list[q >> 8];
         const int e = coff(j) + i;
         A[e] = A[e] - rk[i] * wk[j] - rkm1[i] * wkm1[j];
@@ -459,7 +469,7 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
   for (int p0 = 0; p0 < P; p0 += 32) {
     const int pp = p0 + lane;
     const bool act = pp < P;
-    const unsigned q = (p0 == 0) ? (tri_lane & 0xffffu) : (p0 == 32) ? (tri_lane >> 16) : tri_decode(act ? pp : 0);
+    const unsigned q = (p0 == 0) ? (tri_lane & 0xffffu) : (p0 == 32) ? (tri_lane >> 16) : tri_decode_rare(act ? pp : 0);
     const int i = act ? list[q & 0xff] : 0, j = act ? list[q >> 8] : 0;
     const double xi = __shfl_sync(IPDDP_FULL_MASK, x, i), xj = __shfl_sync(IPDDP_FULL_MASK, x, j);
     if (act) {

@@ -268,3 +268,31 @@ def division_parity(lib, rng, n=400000, device=0):
         ref = x / y
     same = (bits(out) == bits(ref)) | (np.isnan(out) & np.isnan(ref))
     assert same.all(), f"{int((~same).sum())} quotients differ, first: {x[~same][0]!r} / {y[~same][0]!r} -> {out[~same][0]!r} vs {ref[~same][0]!r}"
+
+
+def sampled_parity(lib, oracle, wl, B, N, sample=6, vary_horizon=False, first=0, seed=0, tol=1e-7):
+    """A batch at BASELINE-config scale on the device, a random sample of its instances on the oracle: same status,
+    iteration counts, work counters, objective bits and trajectories for the sampled instances; every instance ends
+    with a valid status."""
+    b = instances.make_batch(wl, B, N, vary_horizon=vary_horizon, first=first)
+    s = BatchSolver(wl, B, N, options=lib.default_options(optimality_tolerance=tol), lib=lib)
+    s.set_batch(b)
+    r = s.solve()
+    x, u = s.trajectory()
+    cnt = s.counters()
+    s.close()
+    assert np.isin(r.status, [0, 1, 7, 8]).all()
+    idx = np.sort(np.random.default_rng(seed).choice(B, sample, replace=False))
+    oopt = oracle.default_options(optimality_tolerance=tol)
+    res, xo, uo = oracle.solve_batch(wl, N, b.p[idx], b.lower[idx], b.upper[idx], b.x1[idx], b.ubar[idx], options=oopt,
+                                     horizons=b.horizons[idx], want_traj=True)
+    for q, i in enumerate(idx):
+        o = res[q]
+        assert (int(r.status[i]), int(r.k[i]), int(r.j[i]), int(r.l[i])) == (o.status, o.k, o.j, o.l), f"{wl} inst {i}"
+        assert (cnt["n_backward"][i], cnt["n_sweeps"][i], cnt["n_kkt"][i], cnt["n_rollouts"][i]) == \
+            (o.n_backward, o.n_sweeps, o.n_kkt, o.n_rollouts), f"{wl} inst {i}: work counters"
+        for name in ("objective", "primal_inf", "dual_inf", "cs_inf", "mu", "reg_last", "step_size"):
+            assert_same_bits(getattr(r, name)[i], getattr(o, name), f"{wl} inst {i} {name}")
+        assert_same_bits(x[i], xo[q], f"{wl} inst {i} states")
+        assert_same_bits(u[i], uo[q], f"{wl} inst {i} controls")
+    return r

@@ -97,6 +97,15 @@ def test_max_iterations_and_short_horizon(gpu, oracle_mod):
     helpers.full_solve_parity(gpu, oracle_mod, "acrobot", 3, 3, maxit=50)
 
 
+@pytest.mark.parametrize("wl,B,N,vary", [("acrobot", 2048, 201, False), ("concar", 1024, 101, False),
+                                         ("concar_quad", 1024, 101, False), ("pushing", 512, 141, True)])
+def test_baseline_configs_sampled_vs_oracle(gpu, oracle_mod, wl, B, N, vary):
+    """BASELINE configs 3-5 at a scale where the bulk kernels run (thousands of instances, N = 201 for acrobot,
+    per-instance horizons for pushing): a random sample of instances is re-solved on the oracle and must agree bit
+    for bit, including the work counters."""
+    helpers.sampled_parity(gpu, oracle_mod, wl, B, N, sample=5, vary_horizon=vary, first=100, seed=7)
+
+
 def test_golden_table_on_gpu(gpu):
     """The reference's own known answers (experiments/ipddp2/results/cartpole_friction.txt), straight from the GPU."""
     from ipddp_b200 import instances
