@@ -259,6 +259,12 @@ def emit_device(md, bundles) -> str:
     o.append("};\n")
     o.append(f"IPDDP_TABLE double CONSTS[{max(len(all_consts), 1)}] = {{"
              + (", ".join(repr(float(c)) for c in all_consts) if all_consts else "0.0") + "};\n")
+    # controls the dynamics depend on: the columns of fu that are not structurally zero (ascending) and the inverse map
+    d_ents, _, _ = _device_entries(bundles["derivs"])
+    fu_cols = sorted({en.j for (en, _s) in d_ents if en.mat == "fu"})
+    fu_idx = [fu_cols.index(j) if j in fu_cols else 255 for j in range(nu)]
+    o.append(f"IPDDP_TABLE unsigned char FUCOL[{max(len(fu_cols), 1)}] = {{" + (", ".join(str(c) for c in fu_cols) or "0") + "};\n")
+    o.append(f"IPDDP_TABLE unsigned char FUIDX[{max(nu, 1)}] = {{" + (", ".join(str(c) for c in fu_idx) or "255") + "};\n")
     o.append("}\n")
 
     o.append(f"struct Model_{n} {{\n")
@@ -268,6 +274,9 @@ def emit_device(md, bundles) -> str:
     o.append(f"  static constexpr int D_NSLOT = {nslots['D']}, VF_NSLOT = {nslots['VF']}, DN_NSLOT = {nslots['DN']};\n")
     for (prefix, m, off, cnt) in tbl_defs:
         o.append(f"  static constexpr int {prefix}_{m}_OFF = {off}, {prefix}_{m}_N = {cnt};\n")
+    o.append(f"  static constexpr int FU_NC = {len(fu_cols)};   // controls with a structurally non-zero column in fu\n")
+    o.append(f"  static IPDDP_D int fu_col(int c) {{ return gen_{n}::FUCOL[c]; }}\n")
+    o.append(f"  static IPDDP_D int fu_idx(int u) {{ return gen_{n}::FUIDX[u]; }}   // compact column of control u, 255 = none\n")
     o.append(f"  static IPDDP_D const MEntry* tbl() {{ return gen_{n}::TBL; }}\n")
     o.append(f"  static IPDDP_D const double* consts() {{ return gen_{n}::CONSTS; }}\n")
 

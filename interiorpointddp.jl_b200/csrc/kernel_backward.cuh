@@ -31,8 +31,9 @@ template <class M> struct BwLayout {
   static constexpr int LHS = 0;
   static constexpr int RHS = LHS + pad(KP);          // K x NR: assembled as [Qu B; c cx], negated, solved -> [alpha beta; psi omega]
   static constexpr int FX = RHS + pad(K * NR);       // NX x NX (row index = next-state component)
-  static constexpr int FU = FX + NX * NX;            // NX x NU
-  static constexpr int VXX = FU + pad(NX * NU);      // value Hessian of knot t+1
+  static constexpr int NFU = M::FU_NC;               // controls the dynamics depend on (non-zero columns of fu)
+  static constexpr int FU = FX + NX * NX;            // NX x NFU, compact: column c belongs to control M::fu_col(c)
+  static constexpr int VXX = FU + pad(NX * NFU);     // value Hessian of knot t+1
   static constexpr int VX = VXX + NX * NX;
   static constexpr int LAM = VX + NX;
   static constexpr int CM = LAM + NX;                // C (NX x NX)
@@ -44,8 +45,8 @@ template <class M> struct BwLayout {
   // (WS) is aliased on top of them
   static constexpr int PRE = NEWV + mx(NX * NX + 2 * NX, NU);
   static constexpr int DSC = NEWV;
-  static constexpr int UXT = PRE;                    // fu' Vxx+  (NU x NX)
-  static constexpr int XXT = UXT + pad(NU * NX);     // fx' Vxx+  (NX x NX)
+  static constexpr int UXT = PRE;                    // fu' Vxx+  (NFU x NX)
+  static constexpr int XXT = UXT + pad(NFU * NX);    // fx' Vxx+  (NX x NX)
   static constexpr int TILE = XXT + NX * NX;
   static constexpr int VFS = TILE + pad(mx(M::D_NSLOT, M::DN_NSLOT));
   static constexpr int XS = VFS + pad(M::VF_NSLOT);  // x, u copies for the dynamics Hessian contraction
@@ -97,12 +98,12 @@ IPDDP_D double bw_next_reg(const DevView& v, double reg, double reg_last) {
 template <class M>
 IPDDP_D void bw_setup(double* sm, int lane) {
   typedef BwLayout<M> L;
-  constexpr int NX = L::NX, NU = L::NU;
+  constexpr int NX = L::NX, NFU = L::NFU;
   double* fx = sm + L::FX; double* fu = sm + L::FU;
   const MEntry* tbl = M::tbl();
   const double* cst = M::consts();
   for (int e = lane; e < NX * NX; e += 32) fx[e] = 0.0;
-  for (int e = lane; e < NX * NU; e += 32) fu[e] = 0.0;
+  for (int e = lane; e < NX * NFU; e += 32) fu[e] = 0.0;
   __syncwarp();
   for (int e = lane; e < M::D_fx_N; e += 32) {
     const MEntry q = ld_entry(tbl + M::D_fx_OFF + e);
@@ -110,7 +111,7 @@ IPDDP_D void bw_setup(double* sm, int lane) {
   }
   for (int e = lane; e < M::D_fu_N; e += 32) {
     const MEntry q = ld_entry(tbl + M::D_fu_OFF + e);
-    if (q.slot < 0) fu[q.i + q.j * NX] = IPDDP_LDG(cst - 1 - q.slot);
+    if (q.slot < 0) fu[q.i + M::fu_idx(q.j) * NX] = IPDDP_LDG(cst - 1 - q.slot);
   }
   __syncwarp();
 }
@@ -123,7 +124,7 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
                      int lane, int& nkkt, double& dual_num) {
   typedef BwLayout<M> L;
   typedef Rec<M> R;
-  constexpr int NX = L::NX, NU = L::NU, NC = L::NC, K = L::K, NR = L::NR;
+  constexpr int NX = L::NX, NU = L::NU, NC = L::NC, K = L::K, NR = L::NR, NFU = L::NFU;
   IPDDP_BW_POINTERS
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
   const bool second_order = (v.opt.quasi_newton == 0);
@@ -179,7 +180,7 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
     // ---- scatter pass 1: fx, fu (non-constant part), cu -> lhs top-right, cx -> rhs, lu -> rhs col 0,
     //      lux -> rhs B block, lxx -> C, lx, c -> rhs   (rhs holds the un-negated [Qu B; c cx] until the solve)
     for (int e = lane; e < M::D_fx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fx_OFF + e); if (q.slot >= 0) fx[q.i + q.j * NX] = tile[q.slot]; }
-    for (int e = lane; e < M::D_fu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fu_OFF + e); if (q.slot >= 0) fu[q.i + q.j * NX] = tile[q.slot]; }
+    for (int e = lane; e < M::D_fu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fu_OFF + e); if (q.slot >= 0) fu[q.i + M::fu_idx(q.j) * NX] = tile[q.slot]; }
     for (int e = lane; e < M::D_cu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cu_OFF + e); lhs[pk(q.j, NU + q.i)] = val(q); }
     for (int e = lane; e < M::D_cx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cx_OFF + e); rhs[NU + q.i + (1 + q.j) * K] = val(q); }
     for (int e = lane; e < M::D_lu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lu_OFF + e); rhs[q.i] = val(q); }
@@ -217,7 +218,9 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
         dq = (s0 + s1) + (s2 + s3);
       }
       double q = dq + lu_i;
-      q = dot4c<NX>(fu + i * NX, 1, Vx, 1) + q;
+      // fu' Vx: controls outside the fu columns contribute (0 + 0) + (0 + 0) = +0
+      const int ci = M::fu_idx(i);
+      q = (ci != 255 ? dot4c<NX>(fu + ci * NX, 1, Vx, 1) : 0.0) + q;
       q -= cl;
       q += cu_;
       rhs[i] = q;   // Qu
@@ -225,7 +228,7 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
       double d = dq + lu_i;
       d -= zl_i;
       d += zu_i;
-      d = dot4c<NX>(fu + i * NX, 1, lamn, 1) + d;
+      d = (ci != 255 ? dot4c<NX>(fu + ci * NX, 1, lamn, 1) : 0.0) + d;
       t1[i] = a1 * zl_i;    // Sigma^L
       t2[i] = a2 * zu_i;    // Sigma^U
       dsc[i] = fabs(d);
@@ -235,9 +238,9 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
       const int i = e % NX, j = e / NX;
       xxt[e] = dot4c<NX>(fx + i * NX, 1, Vxx + j * NX, 1);
     }
-    for (int e = lane; e < NU * NX; e += 32) {
-      const int i = e % NU, j = e / NU;
-      uxt[e] = dot4c<NX>(fu + i * NX, 1, Vxx + j * NX, 1);
+    for (int e = lane; e < NFU * NX; e += 32) {     // rows of fu' Vxx+ outside the fu columns are exactly zero: not stored
+      const int a = e % NFU, j = e / NFU;
+      uxt[e] = dot4c<NX>(fu + a * NX, 1, Vxx + j * NX, 1);
     }
     __syncwarp();
     {  // dual_num = max(dual_num, |.|_inf) -- uniform scan, NaN propagating like Julia's max
@@ -250,15 +253,21 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
       const int i = e % NX, j = e / NX;
       Cm[e] = dot4c<NX>(xxt + i, NX, fx + j * NX, 1) + Cm[e];
     }
-    for (int e = lane; e < NU * (NU + 1) / 2; e += 32) {
+    // H = (fu' Vxx+ fu) + Sigma: outside the fu columns the product is (0 + 0) + (0 + 0) = +0, i.e. H = +0 + Sigma on the
+    // diagonal and +0 (the cleared matrix) elsewhere; the fu columns get the dense formula
+    for (int i = lane; i < NU; i += 32)
+      if (M::fu_idx(i) == 255) lhs[pk(i, i)] = 0.0 + (t1[i] + t2[i]);
+    for (int e = lane; e < NFU * (NFU + 1) / 2; e += 32) {
       const unsigned q = tri_decode(e);
-      const int i = q & 0xff, j = q >> 8;
-      const double h0 = (i == j) ? (t1[i] + t2[i]) : 0.0;
-      lhs[e] = dot4c<NX>(uxt + i, NU, fu + j * NX, 1) + h0;
+      const int a = q & 0xff, b2 = q >> 8;                 // compact columns a <= b2
+      const int i = M::fu_col(a), j = M::fu_col(b2);       // controls i <= j
+      const double h0 = (a == b2) ? (t1[i] + t2[i]) : 0.0;
+      lhs[pk(i, j)] = dot4c<NX>(uxt + a, NFU, fu + b2 * NX, 1) + h0;
     }
-    for (int e = lane; e < NU * NX; e += 32) {
-      const int i = e % NU, j = e / NU;
-      rhs[i + (1 + j) * K] = dot4c<NX>(uxt + i, NU, fx + j * NX, 1) + rhs[i + (1 + j) * K];
+    for (int e = lane; e < NFU * NX; e += 32) {             // B += (fu' Vxx+) fx: rows outside the fu columns get +0
+      const int a = e % NFU, j = e / NFU;
+      const int i = M::fu_col(a);
+      rhs[i + (1 + j) * K] = dot4c<NX>(uxt + a, NFU, fx + j * NX, 1) + rhs[i + (1 + j) * K];
     }
     __syncwarp();
     // ---- H += luu
