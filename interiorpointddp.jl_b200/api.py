@@ -57,12 +57,30 @@ def _with_p(fn, nargs_without_p):
 # constructors (reference src/dynamics.jl:15, src/objectives.jl:12, src/constraints.jl:16,52, src/bounds.jl:12-26)
 # ------------------------------------------------------------------------------------------------
 class Dynamics:
-    """Dynamics(f, num_state, num_control; quasi_newton=false): x+ = f(x, u[, p])."""
+    """Dynamics(f, num_state, num_control; quasi_newton=false): x+ = f(x, u[, p])   (reference src/dynamics.jl:15)
 
-    def __init__(self, f: Callable, num_state: int, num_control: int, quasi_newton: bool = False):
+    User-provided derivatives (reference src/dynamics.jl:58-61):
+    Dynamics(f, fx, fu, num_next_state, num_state, num_control; vfxx=None, vfux=None, vfuu=None) -- fx, fu are closures
+    (x, u[, p]) -> matrix; the contractions (x, u, v[, p]) -> matrix are optional and stay zero when omitted, as in the
+    reference.  (The reference's closures are in-place `f!(out, x, u)`; here they return the value, because they are
+    traced symbolically into CUDA device functions.)"""
+
+    def __init__(self, f: Callable, *args, quasi_newton: bool = False, vfxx=None, vfux=None, vfuu=None):
         self.f = _with_p(f, 2)
-        self.num_state, self.num_control, self.quasi_newton = int(num_state), int(num_control), bool(quasi_newton)
         self._src = f
+        self.user_derivs = {}
+        if len(args) == 5 and callable(args[0]) and callable(args[1]):
+            fx, fu, num_next_state, num_state, num_control = args
+            assert int(num_next_state) == int(num_state), "state dimension must be constant along the horizon"
+            self.user_derivs = {"fx": _with_p(fx, 2), "fu": _with_p(fu, 2)}
+            for k, fn in (("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu)):
+                if fn is not None:
+                    self.user_derivs[k] = _with_p(fn, 3)
+            self._extra_src = [fx, fu, vfxx, vfux, vfuu]
+        else:
+            num_state, num_control = args
+            self._extra_src = []
+        self.num_state, self.num_control, self.quasi_newton = int(num_state), int(num_control), bool(quasi_newton)
 
 
 class Objective:
@@ -78,8 +96,22 @@ class Constraint:
     """Constraint(c, num_state, num_control; quasi_newton=false, indices_compl=nothing) or the empty
     Constraint(num_state, num_control)."""
 
-    def __init__(self, *args, quasi_newton: bool = False, indices_compl: Optional[Sequence[int]] = None):
-        if callable(args[0]):
+    def __init__(self, *args, quasi_newton: bool = False, indices_compl: Optional[Sequence[int]] = None,
+                 vcxx=None, vcux=None, vcuu=None):
+        self.user_derivs = {}
+        self._extra_src = []
+        if len(args) == 6 and callable(args[0]) and callable(args[1]):
+            # user-provided derivatives (reference src/constraints.jl:60-64):
+            # Constraint(c, cx, cu, num_constraint, num_state, num_control; indices_compl, vcxx, vcux, vcuu)
+            c, cx, cu, _num_constraint, nx, nu = args
+            self.c = _with_p(c, 2)
+            self._src = c
+            self.user_derivs = {"cx": _with_p(cx, 2), "cu": _with_p(cu, 2)}
+            for k, fn in (("vcxx", vcxx), ("vcux", vcux), ("vcuu", vcuu)):
+                if fn is not None:
+                    self.user_derivs[k] = _with_p(fn, 3)
+            self._extra_src = [cx, cu, vcxx, vcux, vcuu]
+        elif callable(args[0]):
             c, nx, nu = args
             self.c = _with_p(c, 2)
             self._src = c
@@ -219,11 +251,14 @@ class Solver:
         stage_f = o0.f
         term_f = _with_p(oN._src, 2)
         cfun = c0.c if c0.c is not None else (lambda x, u, p: [])
-        tag = name or ("user_" + _closure_fingerprint([d0._src, o0._src, oN._src, c0._src]))
+        extra = [f_ for f_ in (d0._extra_src + c0._extra_src) if f_ is not None]
+        tag = name or ("user_" + _closure_fingerprint([d0._src, o0._src, oN._src, c0._src] + extra))
         md = workloads.ModelDef(
             name=tag, nx=nx, nu=nu, np_=self.num_parameter, f=d0.f, stage_cost=stage_f,
             term_cost=lambda x, p: term_f(x, [], p), c=cfun, lower=lambda p: list(b0.lower), upper=lambda p: list(b0.upper),
-            u_init=[0.0] * nu, dt=0.0, indices_compl=list(c0.indices_compl))
+            u_init=[0.0] * nu, dt=0.0, indices_compl=list(c0.indices_compl),
+            user_derivs={**d0.user_derivs, **c0.user_derivs}, user_dynamics=bool(d0.user_derivs),
+            user_constraint=bool(c0.user_derivs))
         self.model_def = md
         self.lib = _lib.load()
         if tag not in self.lib.models():

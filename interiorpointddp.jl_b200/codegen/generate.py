@@ -146,23 +146,49 @@ def trace(md: workloads.ModelDef) -> Dict[str, Bundle]:
     b["costN"] = _make_bundle("costN", ["x", "p"], [("l", sp.Matrix([lN_]))])
     b["con"] = _make_bundle("con", ["x", "u", "p"], [("c", c_)])
 
-    Jfx, Jfu = fx_.jacobian(X), fx_.jacobian(U)
+    ud = getattr(md, "user_derivs", None) or {}
+
+    def user(name, rows, cols, *args):
+        """matrix from a user-provided derivative closure (shape checked), or None"""
+        fn = ud.get(name)
+        if fn is None:
+            return None
+        M = sp.Matrix(fn(*args))
+        if M.shape != (rows, cols):
+            if rows * cols == len(M):
+                M = M.reshape(rows, cols)
+            else:
+                raise ValueError(f"user-provided {name}: expected {rows}x{cols}, got {M.shape}")
+        return M
+
+    def pick(name, rows, cols, args, auto, group_is_user):
+        M = user(name, rows, cols, *args)
+        if M is not None:
+            return M
+        if group_is_user and name.startswith("v"):   # contraction not provided: stays zero (reference semantics)
+            return sp.zeros(rows, cols)
+        return auto()
+
+    udyn, ucon = bool(getattr(md, "user_dynamics", False)), bool(getattr(md, "user_constraint", False))
+    Jfx = pick("fx", nxn, nx, (x, u, p), lambda: fx_.jacobian(X), udyn)
+    Jfu = pick("fu", nxn, nu, (x, u, p), lambda: fx_.jacobian(U), udyn)
     lx = sp.Matrix([l_]).jacobian(X).T
     lu = sp.Matrix([l_]).jacobian(U).T
     lxx, luu, lux = lx.jacobian(X), lu.jacobian(U), lu.jacobian(X)
-    cx, cu = c_.jacobian(X), c_.jacobian(U)
+    cx = pick("cx", nc, nx, (x, u, p), lambda: c_.jacobian(X), ucon)
+    cu = pick("cu", nc, nu, (x, u, p), lambda: c_.jacobian(U), ucon)
     vv = sp.Matrix(v[:nc])
-    vcxx = (cx.T * vv).jacobian(X)
-    vcux = (cu.T * vv).jacobian(X)
-    vcuu = (cu.T * vv).jacobian(U)
+    vcxx = pick("vcxx", nx, nx, (x, u, v[:nc], p), lambda: (cx.T * vv).jacobian(X), ucon)
+    vcux = pick("vcux", nu, nx, (x, u, v[:nc], p), lambda: (cu.T * vv).jacobian(X), ucon)
+    vcuu = pick("vcuu", nu, nu, (x, u, v[:nc], p), lambda: (cu.T * vv).jacobian(U), ucon)
     b["derivs"] = _make_bundle("derivs", ["x", "u", "v", "p"], [
         ("fx", Jfx), ("fu", Jfu), ("lx", lx), ("lu", lu), ("lxx", lxx), ("luu", luu), ("lux", lux),
         ("cx", cx), ("cu", cu), ("vcxx", vcxx), ("vcux", vcux), ("vcuu", vcuu)])
 
     lv = sp.Matrix(lam)
-    vfxx = (Jfx.T * lv).jacobian(X)
-    vfux = (Jfu.T * lv).jacobian(X)
-    vfuu = (Jfu.T * lv).jacobian(U)
+    vfxx = pick("vfxx", nx, nx, (x, u, lam, p), lambda: (Jfx.T * lv).jacobian(X), udyn)
+    vfux = pick("vfux", nu, nx, (x, u, lam, p), lambda: (Jfu.T * lv).jacobian(X), udyn)
+    vfuu = pick("vfuu", nu, nu, (x, u, lam, p), lambda: (Jfu.T * lv).jacobian(U), udyn)
     b["vf"] = _make_bundle("vf", ["x", "u", "v", "p"], [("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu)])
 
     lNx = sp.Matrix([lN_]).jacobian(X).T

@@ -41,6 +41,13 @@ class ModelDef:
     dt: float
     indices_compl: List[int] = field(default_factory=list)   # 0-based
     doc: str = ""
+    # User-provided derivatives (reference src/dynamics.jl:58-61, src/constraints.jl:60-64): name -> callable returning
+    # the matrix, (x, u, p) for fx, fu, cx, cu and (x, u, v, p) for the contractions vfxx, vfux, vfuu, vcxx, vcux, vcuu.
+    # A key that is present replaces symbolic differentiation; in a user-provided group the missing contractions are
+    # zero, as in the reference (`tensor_contraction!` is skipped when they are `nothing`).
+    user_derivs: dict = field(default_factory=dict)
+    user_dynamics: bool = False       # the Dynamics was built from user-provided derivatives
+    user_constraint: bool = False     # the Constraint was built from user-provided derivatives
 
     @property
     def nc(self) -> int:

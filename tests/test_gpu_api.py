@@ -133,3 +133,38 @@ def test_quasi_newton_option(oracle_mod):
         assert (int(r.status[i]), int(r.k[i])) == (res[i].status, res[i].k)
         helpers.assert_same_bits(r.objective[i], res[i].objective, f"objective inst {i}")
     s.close()
+
+
+def test_user_provided_derivative_constructors(oracle_mod):
+    """Dynamics(f, fx, fu, nx', nx, nu; vfxx, vfux, vfuu) and Constraint(c, cx, cu, nc, nx, nu; vcxx, vcux, vcuu)
+    (reference src/dynamics.jl:58-61, src/constraints.jl:60-64) with hand-written derivatives of the double integrator:
+    same iterates as the symbolically differentiated model (= the oracle's built-in restatement)."""
+    from ipddp_b200 import Dynamics, Objective, Constraint, Bound, Options, Solver, solve, get_trajectory
+    dt, N = 0.01, 101
+    f = lambda x, u: [x[0] + dt * x[1], x[1] + dt * u[0]]
+    fx = lambda x, u: [[1.0, dt], [0.0, 1.0]]
+    fu = lambda x, u: [[0.0, 0.0, 0.0], [dt, 0.0, 0.0]]
+    zero = lambda r, c: [[0.0] * c for _ in range(r)]
+    dyn = Dynamics(f, fx, fu, 2, 2, 3, vfxx=lambda x, u, v: zero(2, 2), vfux=lambda x, u, v: zero(3, 2),
+                   vfuu=lambda x, u, v: zero(3, 3))
+    c = lambda x, u: [u[1] - u[2] - u[0] * x[1]]
+    cx = lambda x, u: [[0.0, -u[0]]]
+    cu = lambda x, u: [[-x[1], 1.0, -1.0]]
+    path = Constraint(c, cx, cu, 1, 2, 3, vcxx=lambda x, u, v: zero(2, 2),
+                      vcux=lambda x, u, v: [[0.0, -v[0]], [0.0, 0.0], [0.0, 0.0]], vcuu=lambda x, u, v: zero(3, 3))
+    stage = Objective(lambda x, u: dt * (u[1] + u[2]), 2, 3)
+    term = Objective(lambda x, u: 500.0 * ((x[0] - 1.0) * (x[0] - 1.0) + (x[1] - 0.0) * (x[1] - 0.0)), 2, 0)
+    bound = Bound([-10.0, 0.0, 0.0], [10.0, math.inf, math.inf])
+    solver = Solver(float, [dyn] * (N - 1), [stage] * (N - 1) + [term], [path] * (N - 1) + [Constraint(2, 0)],
+                    [bound] * (N - 1) + [Bound(float, 0)], options=Options(optimality_tolerance=1e-7))
+    ubar = [np.array([0.01, 0.01, 0.01]) for _ in range(N - 1)] + [np.zeros(0)]
+    solve(solver, np.zeros(2), ubar)
+    d = solver.data
+    assert d.status == 0 and d.k == 31 and abs(d.objective - 1.26574863e+00) < 5e-9
+    o = oracle_mod.OracleSolver("double_integrator", N, [], bound.lower, bound.upper,
+                                options=oracle_mod.default_options(optimality_tolerance=1e-7))
+    ro = o.solve(np.zeros(2), np.tile([0.01, 0.01, 0.01], N - 1))
+    assert ro.k == d.k
+    helpers.assert_same_bits(d.objective, ro.objective, "objective")
+    x_sol, _ = get_trajectory(solver)
+    helpers.assert_same_bits(np.concatenate(x_sol), o.array("x"), "states")
