@@ -458,8 +458,7 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
   if (lane == 0) {
     S::info(scratch)[k] = S::pack(nzm, kp + 1);
     S::dinv(scratch)[k] = rinv;
-    if (K > 32) S::nzhi(scratch)[k] = 0u;
-  }
+  }                                              // (nzhi[k] is only read for k > 32: nothing to clear here)
   if (nzm == 0u) return true;                // nothing to eliminate; B(k,:) scaling is deferred
   unsigned char* list = S::list(scratch);
   if (x != 0.0) list[__popc(nzm & ((1u << lane) - 1u))] = (unsigned char)lane;
@@ -560,7 +559,7 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
     const bool one = pv > 0;
     const unsigned mlo = (unsigned)cw;
     unsigned mhi = 0u;
-    if (K > 32) mhi = nzhi[k];
+    if (K > 32 && k > 32) mhi = nzhi[k];        // rows >= 32 can only be non-zero in columns k > 32
     const bool any = (mlo | mhi) != 0u;
     double sa = 0.0, sb = 0.0;
     if (any) {
