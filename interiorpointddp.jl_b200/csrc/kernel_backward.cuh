@@ -1,5 +1,7 @@
-// k_backward: backward_pass! + inertia_correction! (reference src/backward_pass.jl:1-195,
-// src/inertia_correction.jl:257-276), one warp per active instance.
+// k_backward / k_backward_spec: backward_pass! + inertia_correction! (reference src/backward_pass.jl:1-195,
+// src/inertia_correction.jl:257-276).  bw_sweep is one sweep by one warp; k_backward runs the regularisation-restart
+// loop with one warp per active instance (bulk rounds), k_backward_spec tries four values of the regularisation schedule
+// at once with one CTA per instance (rounds with few active instances), see the comment above that kernel.
 //
 // The sweep is sequential in time (t = N-1 .. 0) with a restart-from-the-end loop on inertia failure;
 // per knot the warp assembles the (nu+nc)^2 KKT matrix in shared memory from the compact derivative
@@ -54,7 +56,6 @@ template <class M> struct BwLayout {
   static constexpr int PRE_END = US + (M::VF_NSLOT > 0 ? NU : 0);
   static constexpr int WS = PRE;
   static constexpr int DBL_END = mx(PRE_END, WS + 4 * K);
-  // ints (4 bytes) after the doubles
   // LDLT scratch (8-byte aligned: it starts with doubles)
   static constexpr int LIST_B = DBL_END * 8;
   static constexpr int BYTES = ((LIST_B + LdltScratch<(K > 0 ? K : 1)>::BYTES + 15) / 16) * 16;
