@@ -45,6 +45,9 @@ extern "C" long long g_ipddp_ldlt_steps[3];
 #ifndef IPDDP_ONE_GENERIC
 #define IPDDP_ONE_GENERIC 1       // one instance of the general pivot step for all k (measured: -3.4 % sweep time vs two)
 #endif
+#ifndef IPDDP_FAST2
+#define IPDDP_FAST2 1             // fast pivot step for columns k >= 32 as well (two lane slots)
+#endif
 #ifndef IPDDP_DIV_NOINLINE
 #define IPDDP_DIV_NOINLINE 0
 #endif
@@ -489,6 +492,103 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
   return true;
 }
 
+// The same fast step for a pivot column 32 <= k < 64: rows 0..31 sit in lane slot 0, rows 32..k-1 in slot 1 (the first
+// k - 32 lanes).  The multipliers of the trailing update are read from the column in shared memory (not shuffled, two
+// slots), which costs one more __syncwarp than the single-slot step; everything else is the same sequence.
+template <int K, int NR>
+IPDDP_D bool ldlt_step_fast2(int k, double* __restrict__ A, double* __restrict__ Bm,
+                             unsigned char* __restrict__ scratch, int lane, unsigned tri_lane,
+                             double tol, int& np) {
+  typedef LdltScratch<K> S;
+  const double alpha = 0.6403882032022076;   // (1 + sqrt(17)) / 8
+  const double sfmin = 2.2250738585072014e-308;
+  const int ck = coff(k);
+  const int i1 = lane + 32;
+  const bool in1 = i1 < k;
+  double* xc = A + ck;
+  double x0 = xc[lane];                       // rows 0..31 (k >= 32: all present)
+  double x1 = in1 ? xc[i1] : 0.0;             // rows 32..k-1
+  double piv = xc[k];
+  int kp = k;
+  const bool keep = __all_sync(IPDDP_FULL_MASK, fabs(piv) >= alpha * fabs(x0) && fabs(piv) >= alpha * fabs(x1));
+  if (!keep) {
+    if (__any_sync(IPDDP_FULL_MASK, x0 != x0 || x1 != x1) || piv != piv) return false;
+    // imax: first row attaining max |x| over both slots
+    const double ax0 = fabs(x0), ax1 = fabs(x1);
+    const unsigned h0 = (unsigned)__double2hiint(ax0), h1 = in1 ? (unsigned)__double2hiint(ax1) : 0u;
+    const unsigned mh = __reduce_max_sync(IPDDP_FULL_MASK, h0 > h1 ? h0 : h1);
+    unsigned c0 = __ballot_sync(IPDDP_FULL_MASK, h0 == mh), c1 = __ballot_sync(IPDDP_FULL_MASK, in1 && h1 == mh);
+    if (__popc(c0) + __popc(c1) > 1) {        // several rows share the high word: compare the low words among them
+      const unsigned l0 = (h0 == mh) ? (unsigned)__double2loint(ax0) : 0u;
+      const unsigned l1 = (in1 && h1 == mh) ? (unsigned)__double2loint(ax1) : 0u;
+      const unsigned ml = __reduce_max_sync(IPDDP_FULL_MASK, l0 > l1 ? l0 : l1);
+      c0 = __ballot_sync(IPDDP_FULL_MASK, h0 == mh && l0 == ml);
+      c1 = __ballot_sync(IPDDP_FULL_MASK, in1 && h1 == mh && l1 == ml);
+    }
+    const int imax = c0 ? __ffs(c0) - 1 : 32 + __ffs(c1) - 1;
+    const int ci = coff(imax);
+    // row / column imax of the leading (k+1) x (k+1) block (signed): rows lane (slot 0) and lane + 32 <= k (slot 1)
+    const bool v0 = lane != imax, v1 = i1 <= k && i1 != imax;
+    const int pa0 = (lane < imax) ? ci + lane : coff(lane) + imax;
+    const int pa1 = (i1 < imax) ? ci + i1 : coff(i1) + imax;
+    const double a0 = v0 ? A[pa0] : 0.0;
+    const double a1 = v1 ? A[pa1] : 0.0;
+    const double aii = A[ci + imax];
+    if (!__all_sync(IPDDP_FULL_MASK, fabs(aii) >= alpha * fabs(a0) && fabs(aii) >= alpha * fabs(a1))) return false;
+    if (!(fabs(aii) >= sfmin)) return false;
+    // ---- committed: symmetric interchange k <-> imax (row / column imax receives the old column k), right-hand sides,
+    //      and the new (unscaled) pivot column written back for the trailing update
+    if (lane != imax) { A[pa0] = x0; xc[lane] = a0; }
+    if (in1 && i1 != imax) { A[pa1] = x1; xc[i1] = a1; }
+    if (lane == 0) { A[ci + imax] = piv; xc[k] = aii; }
+    if (lane < NR) { double* bl = Bm + lane * K; const double t = bl[k]; bl[k] = bl[imax]; bl[imax] = t; }
+    x0 = (lane == imax) ? x0 : a0;
+    x1 = in1 ? ((i1 == imax) ? x1 : a1) : 0.0;
+    piv = aii;
+    kp = imax;
+  } else if (!(fabs(piv) >= sfmin)) {
+    return false;
+  }
+  const unsigned nz0 = __ballot_sync(IPDDP_FULL_MASK, x0 != 0.0), nz1 = __ballot_sync(IPDDP_FULL_MASK, x1 != 0.0);
+  const double rinv = 1.0 / piv;
+  if (piv > tol) np += 1;
+  if (lane == 0) {
+    S::info(scratch)[k] = S::pack(nz0, kp + 1);
+    S::nzhi(scratch)[k] = nz1;
+    S::dinv(scratch)[k] = rinv;
+  }
+  if ((nz0 | nz1) == 0u) return true;
+  unsigned char* list = S::list(scratch);
+  const unsigned lt = (1u << lane) - 1u;
+  const int n0 = __popc(nz0);
+  if (x0 != 0.0) list[__popc(nz0 & lt)] = (unsigned char)lane;
+  if (x1 != 0.0) list[n0 + __popc(nz1 & lt)] = (unsigned char)i1;
+  __syncwarp();
+  const int nnz = n0 + __popc(nz1);
+  const int P = (nnz * (nnz + 1)) >> 1;
+  for (int pp = lane; pp < P; pp += 32) {
+    const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode_rare(pp);
+    const int i = list[q & 0xff], j = list[q >> 8];
+    const int e = coff(j) + i;
+    A[e] = IPDDP_FMA(xc[i], -rinv * xc[j], A[e]);
+  }
+  __syncwarp();                                // the unscaled column was read by other lanes: now it can be scaled
+  if (x0 != 0.0) {
+    const double xs = x0 * rinv;
+    xc[lane] = xs;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) Bm[lane + j * K] = IPDDP_FMA(xs, -Bm[k + j * K], Bm[lane + j * K]);
+  }
+  if (x1 != 0.0) {
+    const double xs = x1 * rinv;
+    xc[i1] = xs;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) Bm[i1 + j * K] = IPDDP_FMA(xs, -Bm[k + j * K], Bm[i1 + j * K]);
+  }
+  __syncwarp();
+  return true;
+}
+
 // dsytf2_rook('U') on the packed matrix A of order K, fused with the first (U D) loop of dsytrs_rook on
 // the NR right-hand sides in Bm (column-major, leading dimension K).  Returns info; np_out = number of
 // positive eigenvalues of D.  If info != 0 the contents of Bm are meaningless (the caller restarts).
@@ -504,7 +604,12 @@ IPDDP_D int warp_ldlt_factor(double* __restrict__ A, double* __restrict__ Bm, do
   int info = 0, np = 0;
   int k = K - 1;
   if (K > 32) {
-    while (k >= 32) k -= ldlt_step<K, NR, true>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
+    while (k >= 32) {
+#if IPDDP_FAST2
+      if (ldlt_step_fast2<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) { k -= 1; continue; }
+#endif
+      k -= ldlt_step<K, NR, true>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
+    }
   }
   while (k >= 0) {
     if (ldlt_step_fast<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) {

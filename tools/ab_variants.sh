@@ -1,4 +1,4 @@
-for v in _base ""; do
+for v in _nofast2 ""; do
 IPDDP_SERIES=1 python tools/phase_bench.py cartpole 16384 70 interiorpointddp.jl_b200/libipddp_b200$v.so > gpurun_out/ab$v.log 2>&1
 python - "$v" <<PY
 import json,sys
