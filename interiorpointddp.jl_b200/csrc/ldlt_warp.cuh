@@ -48,9 +48,6 @@ extern "C" long long g_ipddp_ldlt_steps[3];
 #ifndef IPDDP_FAST2
 #define IPDDP_FAST2 1             // fast pivot step for columns k >= 32 as well (two lane slots)
 #endif
-#ifndef IPDDP_DIV_NOINLINE
-#define IPDDP_DIV_NOINLINE 0
-#endif
 
 namespace ipk {
 
@@ -70,14 +67,6 @@ IPDDP_D unsigned tri_decode(int p) {
 // nothing under- or overflows; operands outside [2^-400, 2^400] (zeros, infinities, NaNs, denormals) take the plain
 // division, except +-0 / d which is x*rd exactly.  3 instructions instead of ~25 -- and the plain FP64 division falls
 // into a ~60-instruction slow path for zero numerators, which KKT matrices with a zero block produce all the time.
-#if IPDDP_DIV_NOINLINE
-// out-of-range operands (rare): one shared copy of the plain division instead of one per call site
-static __device__ __noinline__ double ldlt_div_rare(double x, double d, double rd, bool ok) {
-  if (ok && x == 0.0) return x * rd;
-  return x / d;
-}
-#endif
-
 struct DivBy {
   double d, rd;
   bool ok;
@@ -92,24 +81,10 @@ struct DivBy {
       const double r = IPDDP_FMA(-d, q, x);
       return IPDDP_FMA(r, rd, q);
     }
-#if IPDDP_DIV_NOINLINE
-    return ldlt_div_rare(x, d, rd, ok);
-#else
     if (ok && x == 0.0) return x * rd;
     return x / d;
-#endif
   }
 };
-
-#ifndef IPDDP_TRI_NOINLINE
-#define IPDDP_TRI_NOINLINE 0
-#endif
-#if IPDDP_TRI_NOINLINE
-// pairs beyond the two cached per lane (more than 10 non-zero rows in a pivot column: rare): one out-of-line copy
-static __device__ __noinline__ unsigned tri_decode_rare(int p) { return tri_decode(p); }
-#else
-IPDDP_D unsigned tri_decode_rare(int p) { return tri_decode(p); }
-#endif
 
 // Maximum of the non-negative candidates (v0 at index lane, v1 at index lane+32; vld* = candidate present)
 // and the 64-bit mask of the indices that attain it.
@@ -278,7 +253,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
         }
         const int P = (nnz * (nnz + 1)) >> 1;
         for (int pp = lane; pp < P; pp += 32) {
-          const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode_rare(pp);
+          const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode(pp);
           const int i = list[q & 0xff], j = list[q >> 8];
           const int e = coff(j) + i;
           A[e] = IPDDP_FMA(x[i], -d11 * x[j], A[e]);
@@ -359,7 +334,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       __syncwarp();
       const int P = (nnz * (nnz + 1)) >> 1;
       for (int pp = lane; pp < P; pp += 32) {
-        const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode_rare(pp);
+        const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode(pp);
         const int i = list[q & 0xff], j = list[q >> 8];
         const int e = coff(j) + i;
         A[e] = A[e] - rk[i] * wk[j] - rkm1[i] * wkm1[j];
@@ -471,7 +446,7 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
   for (int p0 = 0; p0 < P; p0 += 32) {
     const int pp = p0 + lane;
     const bool act = pp < P;
-    const unsigned q = (p0 == 0) ? (tri_lane & 0xffffu) : (p0 == 32) ? (tri_lane >> 16) : tri_decode_rare(act ? pp : 0);
+    const unsigned q = (p0 == 0) ? (tri_lane & 0xffffu) : (p0 == 32) ? (tri_lane >> 16) : tri_decode(act ? pp : 0);
     const int i = act ? list[q & 0xff] : 0, j = act ? list[q >> 8] : 0;
     const double xi = __shfl_sync(IPDDP_FULL_MASK, x, i), xj = __shfl_sync(IPDDP_FULL_MASK, x, j);
     if (act) {
@@ -567,7 +542,7 @@ IPDDP_D bool ldlt_step_fast2(int k, double* __restrict__ A, double* __restrict__
   const int nnz = n0 + __popc(nz1);
   const int P = (nnz * (nnz + 1)) >> 1;
   for (int pp = lane; pp < P; pp += 32) {
-    const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode_rare(pp);
+    const unsigned q = (pp < 32) ? (tri_lane & 0xffffu) : (pp < 64) ? (tri_lane >> 16) : tri_decode(pp);
     const int i = list[q & 0xff], j = list[q >> 8];
     const int e = coff(j) + i;
     A[e] = IPDDP_FMA(xc[i], -rinv * xc[j], A[e]);
