@@ -2,6 +2,9 @@
 #include "cpu_simt.h"
 
 #include <omp.h>
+#include <string.h>
+
+#include <utility>
 
 namespace emu {
 thread_local BlockState* tls_block = nullptr;
@@ -83,11 +86,26 @@ static void run_block(BlockState& bs, dim3 grid, dim3 block, unsigned bx, size_t
   tls_blockIdx = dim3(bx, 0, 0);
   tls_blockDim = block;
   tls_gridDim = grid;
+  // Lane order inside a scheduler round (IPDDP_EMU_ORDER = fwd | rev | rand): a fiber runs from one barrier to the next
+  // before the following fiber starts, so data exchanged through shared memory WITHOUT a barrier in between is seen
+  // "new" by later fibers and "old" by earlier ones.  Race-free kernels give identical results for every order;
+  // tests/test_emu_parity.py::test_emulated_lane_order_independence uses this as its race check.
+  const char* ord_env = getenv("IPDDP_EMU_ORDER");
+  const int ord = !ord_env ? 0 : !strcmp(ord_env, "rev") ? 1 : !strcmp(ord_env, "rand") ? 2 : 0;
+  std::vector<int> order(T);
+  for (int t = 0; t < T; ++t) order[t] = (ord == 1) ? T - 1 - t : t;
+  unsigned long long rng = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)bx * 0xD1B54A32D192ED03ull);
   int alive = T;
   while (alive > 0) {
     alive = 0;
     int parked = 0;
-    for (int t = 0; t < T; ++t) {
+    if (ord == 2)
+      for (int t = T - 1; t > 0; --t) {   // Fisher-Yates with xorshift64
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(order[t], order[(int)(rng % (unsigned long long)(t + 1))]);
+      }
+    for (int q = 0; q < T; ++q) {
+      const int t = order[q];
       Fiber& f = bs.fibers[t];
       if (f.done) continue;
       if (f.at_block_barrier) { alive++; parked++; continue; }

@@ -39,6 +39,27 @@ def test_emulated_bulk_kernels(emu, oracle_mod, wl, B, N, maxit):
         emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
 
 
+@pytest.mark.parametrize("order", ["rev", "rand"])
+def test_emulated_lane_order_independence(emu, oracle_mod, order, monkeypatch):
+    """Race check of the warp-synchronous shared-memory code.  The emulator runs each lane from one barrier to the next
+    before the following lane starts, so a value handed from lane to lane through shared memory without a barrier in
+    between is seen "new" by later lanes and "old" by earlier ones: a missing __syncwarp changes the results for some
+    lane order (checked by hand: dropping the barrier after the row-list compaction in ldlt_step_fast changes the
+    digests).  Default order = ascending (every other test); here descending and shuffled, bulk and tail kernels, against
+    the oracle.  (compute-sanitizer's racecheck is not available on the GPU pool.)"""
+    monkeypatch.setenv("IPDDP_EMU_ORDER", order)
+    for spec in (148, 0):
+        emu.L.ipddp_set_tuning(None, b"fw_spec_max", spec)
+        emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592 if spec else 0)
+        try:
+            helpers.full_solve_parity(emu, oracle_mod, "cartpole", 2, 9, maxit=25, n_trace=2)
+            helpers.full_solve_parity(emu, oracle_mod, "pushing", 2, 9, maxit=20, vary_horizon=True, n_trace=2)
+        finally:
+            emu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
+            emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+    helpers.phase_parity(emu, oracle_mod, "concar", B=2, N=7, rounds=2)
+
+
 def test_emulated_varying_horizon(emu, oracle_mod):
     helpers.full_solve_parity(emu, oracle_mod, "concar", 4, 13, maxit=80, vary_horizon=True, first=100, n_trace=4)
 
