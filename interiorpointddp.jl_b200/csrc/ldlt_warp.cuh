@@ -45,6 +45,9 @@ extern "C" long long g_ipddp_ldlt_steps[3];
 #ifndef IPDDP_ONE_GENERIC
 #define IPDDP_ONE_GENERIC 1       // one instance of the general pivot step for all k (measured: -3.4 % sweep time vs two)
 #endif
+#ifndef IPDDP_DIV_NOINLINE
+#define IPDDP_DIV_NOINLINE 1
+#endif
 #ifndef IPDDP_FAST2
 #define IPDDP_FAST2 1             // fast pivot step for columns k >= 32 as well (two lane slots)
 #endif
@@ -67,6 +70,13 @@ IPDDP_D unsigned tri_decode(int p) {
 // nothing under- or overflows; operands outside [2^-400, 2^400] (zeros, infinities, NaNs, denormals) take the plain
 // division, except +-0 / d which is x*rd exactly.  3 instructions instead of ~25 -- and the plain FP64 division falls
 // into a ~60-instruction slow path for zero numerators, which KKT matrices with a zero block produce all the time.
+// The fallback division of DivBy sits out of line: the ~25 inlined instructions of an FP64 division per call site (18 sites
+// in the 2x2 pivot path) are cold code in the middle of the hot pivot step.  Measured: -2.8 % sweep time.
+#if IPDDP_DIV_NOINLINE && !defined(IPDDP_SIMT_EMU)
+static __device__ __noinline__ double div_rare(double x, double d) { return x / d; }
+#else
+IPDDP_D double div_rare(double x, double d) { return x / d; }
+#endif
 struct DivBy {
   double d, rd;
   bool ok;
@@ -82,7 +92,7 @@ struct DivBy {
       return IPDDP_FMA(r, rd, q);
     }
     if (ok && x == 0.0) return x * rd;
-    return x / d;
+    return div_rare(x, d);
   }
 };
 
@@ -293,9 +303,9 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
         const double a11 = fabs(e11), a22 = fabs(e22);
         const double s1 = 2.0 * fmax(fmax(a11, fabs(d12)), a22);
         const DivBy bys(s1);
-        double smin;
-        if (a11 >= a22) smin = fabs(bys(e11) * e22 - bys(d12) * d12);
-        else            smin = fabs(e11 * bys(e22) - bys(d12) * d12);
+        // (e11/s1)*e22 - (d12/s1)*d12 if |e11| >= |e22|, else e11*(e22/s1) - ...: one expression, the product commutes
+        const bool first = a11 >= a22;
+        const double smin = fabs(bys(first ? e11 : e22) * (first ? e22 : e11) - bys(d12) * d12);
         const double trace = e11 + e22;
         if (0.5 * s1 <= tol) {
         } else if (smin > tol || trace == 0.0) {
@@ -310,19 +320,19 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
     }
     int nnz = 0;
     unsigned m0 = 0u, m1 = 0u;
-    bool f[2] = {false, false};
+    unsigned fm = 0u;                      // bit s: this lane's row lane + 32 s takes part in the update
+    const int ns = (TWO && two) ? 2 : 1;
     if (k > 1) {
       const int m = k - 1;   // rows/columns 0..m-1 get updated
       const double t = bydn.rd;   // 1.0 / (d11 * d22 - 1.0)
       double* wk = w; double* wkm1 = w + K; double* rk = w + 2 * K; double* rkm1 = w + 3 * K;
-#pragma unroll
-      for (int s = 0; s < (TWO ? 2 : 1); ++s) {
-        if (s == 1 && !two) continue;
+#pragma unroll 1
+      for (int s = 0; s < ns; ++s) {
         const int j = lane + 32 * s;
         if (j < m) {
           const double ak = xk[j], akm1 = xkm1[j];
-          f[s] = (ak != 0.0) || (akm1 != 0.0);
-          if (f[s]) {
+          if ((ak != 0.0) || (akm1 != 0.0)) {
+            fm |= 1u << s;
             wkm1[j] = t * (d11 * akm1 - ak);
             wk[j] = t * (d22 * ak - akm1);
             rk[j] = by12(ak);
@@ -330,7 +340,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
           }
         }
       }
-      nnz = warp_compact<TWO>(f[0], f[1], list, lane, m0, m1, two);
+      nnz = warp_compact<TWO>((fm & 1u) != 0u, (fm & 2u) != 0u, list, lane, m0, m1, two);
       __syncwarp();
       const int P = (nnz * (nnz + 1)) >> 1;
       for (int pp = lane; pp < P; pp += 32) {
@@ -339,11 +349,10 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
         const int e = coff(j) + i;
         A[e] = A[e] - rk[i] * wk[j] - rkm1[i] * wkm1[j];
       }
-#pragma unroll
-      for (int s = 0; s < (TWO ? 2 : 1); ++s) {
-        if (s == 1 && !two) continue;
+#pragma unroll 1
+      for (int s = 0; s < ns; ++s) {
         const int j = lane + 32 * s;
-        if (f[s]) {
+        if ((fm >> s) & 1u) {
           xk[j] = by12(wk[j]);
           xkm1[j] = by12(wkm1[j]);
         }
@@ -355,11 +364,10 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       nzhi[k] = m1; nzhi[k - 1] = m1; dinv[k] = 1.0; dinv[k - 1] = 1.0;
     }
     // dsytrs first loop for the 2x2 block: two rank-1 downdates of B, then the 2x2 solve
-#pragma unroll
-    for (int s = 0; s < (TWO ? 2 : 1); ++s) {
-      if (s == 1 && !two) continue;
+#pragma unroll 1
+    for (int s = 0; s < ns; ++s) {
       const int i = lane + 32 * s;
-      if (f[s]) {
+      if ((fm >> s) & 1u) {
         const double xa = xk[i], xb = xkm1[i];
 #pragma unroll
         for (int j = 0; j < NR; ++j) {

@@ -14,6 +14,7 @@ LIB = os.path.join(HERE, "libipddp_emu.so")
 CXX = "/usr/bin/g++"
 FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-mfma", "-fno-fast-math", "-fno-gnu-unique", "-fvisibility-inlines-hidden", "-x", "c++",
          "-include", os.path.join(HERE, "cpu_simt.h"), "-w"]
+FLAGS += os.environ.get("IPDDP_EMU_DEFS", "").split()     # e.g. "-DIPDDP_SWAP_LOOP=1" to check an experiment macro
 
 
 def build(force=False):

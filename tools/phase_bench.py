@@ -47,6 +47,12 @@ def run(lib, wl, B, N, rounds):
             if db == 0:
                 break
     cnt = s.counters()
+    import hashlib
+    x, u = s.trajectory()
+    res = s.results()
+    digest = hashlib.sha256(np.ascontiguousarray(x).tobytes() + np.ascontiguousarray(u).tobytes()
+                            + np.ascontiguousarray(res.objective).tobytes() + np.ascontiguousarray(res.k).tobytes()
+                            + np.ascontiguousarray(cnt["n_kkt"]).tobytes()).hexdigest()[:16]
     s.close()
     a = np.array([r[:4] for r in rows])
     tail = a[max(1, rounds // 2):]
@@ -56,7 +62,7 @@ def run(lib, wl, B, N, rounds):
                                  check=round(tail[:, 2].mean(), 3), forward=round(tail[:, 3].mean(), 3)),
                sum_ms=dict(derivs=round(a[:, 0].sum(), 2), backward=round(a[:, 1].sum(), 2), check=round(a[:, 2].sum(), 2),
                            forward=round(a[:, 3].sum(), 2)),
-               kkt=int(cnt["n_kkt"].sum()), rollouts=int(cnt["n_rollouts"].sum()),
+               digest=digest, kkt=int(cnt["n_kkt"].sum()), rollouts=int(cnt["n_rollouts"].sum()),
                kkt_per_s=round(cnt["n_kkt"].sum() / (a[:, 1].sum() * 1e-3), 0),
                us_per_kkt_per_warp=round(a[:, 1].sum() * 1e3 / max(1, cnt["n_kkt"].max()), 2))
     print(json.dumps(out), flush=True)
