@@ -296,3 +296,67 @@ def sampled_parity(lib, oracle, wl, B, N, sample=6, vary_horizon=False, first=0,
         assert_same_bits(x[i], xo[q], f"{wl} inst {i} states")
         assert_same_bits(u[i], uo[q], f"{wl} inst {i} controls")
     return r
+
+
+def api_error_convention(lib):
+    """The C ABI's error convention (include/ipddp_b200.h): API misuse returns a non-zero code and leaves a message in
+    ipddp_last_error(); nothing throws, nothing is left half-built; algorithmic outcomes are per-instance status codes."""
+    import ctypes as C
+    import pytest
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver
+    L = lib.L
+    err = lambda: L.ipddp_last_error().decode()
+    opt = lib.default_options()
+    h = C.c_void_p()
+    # unknown model, bad sizes
+    assert L.ipddp_problem_create(b"no_such_model", 2, 11, None, 0, C.byref(opt), 0, 0, C.byref(h)) != 0
+    assert "unknown model" in err() and not h.value
+    assert L.ipddp_problem_create(b"concar", 0, 11, None, 0, C.byref(opt), 0, 0, C.byref(h)) != 0
+    assert "B >= 1" in err()
+    assert L.ipddp_problem_create(b"concar", 2, 1, None, 0, C.byref(opt), 0, 0, C.byref(h)) != 0
+    nx, nu, nc, np_, _ = lib.model_dims("concar")
+    bad_ic = np.array([nc], dtype=np.int32)      # complementarity index out of range
+    assert L.ipddp_problem_create(b"concar", 2, 11, bad_ic.ctypes.data_as(C.POINTER(C.c_int)), 1, C.byref(opt), 0, 0,
+                                  C.byref(h)) != 0
+    assert "indices_compl" in err()
+    with pytest.raises(RuntimeError, match="unknown model"):
+        lib.model_dims("no_such_model")
+    assert L.ipddp_model_load(b"/nonexistent/plugin.so") != 0 and "dlopen" in err()
+    # a valid problem: calls in the wrong order / with bad inputs
+    B, N = 2, 11
+    s = BatchSolver("concar", B, N, options=opt, lib=lib)
+    try:
+        assert L.ipddp_solve(s.h, 0) != 0 and "ipddp_set_inputs not called" in err()
+        assert L.ipddp_initialize(s.h) != 0
+        hs = (C.c_void_p * 1)(s.h)
+        ms, st = C.c_double(), type(s.stats())()
+        assert L.ipddp_solve_many(hs, 1, 1, 0, C.byref(ms), C.byref(st)) != 0
+        b = instances.make_batch("concar", B, N)
+        with pytest.raises(RuntimeError, match="required"):      # missing parameter vector (np > 0) / missing arrays
+            s.lib.check(L.ipddp_set_inputs(s.h, None, None, None, None, None, None), "ipddp_set_inputs")
+        hz = np.array([N, N + 1], dtype=np.int32)
+        with pytest.raises(RuntimeError, match="horizon out of range"):
+            s.set_inputs(b.x1, b.ubar, b.p, b.lower, b.upper, hz)
+        hz[1] = 1
+        with pytest.raises(RuntimeError, match="horizon out of range"):
+            s.set_inputs(b.x1, b.ubar, b.p, b.lower, b.upper, hz)
+        with pytest.raises(RuntimeError, match="unknown tuning key"):
+            s.set_tuning("no_such_key", 1)
+        s.set_batch(b)
+        assert L.ipddp_solve_many(hs, 1, 0, 0, C.byref(ms), C.byref(st)) != 0 and "total_solves" in err()
+        # after all that misuse the handle still solves, and the outcome is in the status codes (0 here)
+        r = s.solve()
+        assert r.status.tolist() == [0, 0]
+        # algorithmic failure is NOT an API error: max_iterations = 3 ends with status 8 and return code 0
+        o3 = lib.default_options(max_iterations=3)
+        s3 = BatchSolver("concar", B, N, options=o3, lib=lib)
+        s3.set_batch(b)
+        r3 = s3.solve()
+        assert r3.status.tolist() == [8, 8] and r3.k.tolist() == [3, 3]
+        s3.close()
+        buf = np.zeros(4)
+        assert L.ipddp_get_array(s.h, b"no_such_array", buf.ctypes.data_as(C.POINTER(C.c_double))) < 0
+        assert "unknown array" in err()
+    finally:
+        s.close()

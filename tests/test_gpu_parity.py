@@ -187,3 +187,8 @@ def test_full_size_batch_properties(gpu, oracle_mod):
     for q, i in enumerate(idx):
         assert (int(r.status[i]), int(r.k[i])) == (res[q].status, res[q].k)
         helpers.assert_same_bits(r.objective[i], res[q].objective, f"instance {i} objective vs oracle")
+
+
+def test_error_convention_gpu(gpu):
+    """API misuse -> return code + ipddp_last_error, algorithmic outcome -> per-instance status."""
+    helpers.api_error_convention(gpu)
