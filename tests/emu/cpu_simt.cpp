@@ -2,6 +2,9 @@
 #include "cpu_simt.h"
 
 #include <omp.h>
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
 #include <string.h>
 
 #include <utility>
@@ -67,14 +70,24 @@ static void run_block(BlockState& bs, dim3 grid, dim3 block, unsigned bx, size_t
   bs.body = &body;
   if ((int)bs.fibers.size() < T) {
     bs.fibers.resize(T);
-    bs.stacks.resize((size_t)T * kStack);
+    while ((int)bs.stacks.size() < T) bs.stacks.push_back((char*)malloc(kStack));
   }
+#if defined(__SANITIZE_ADDRESS__)
+  __asan_unpoison_memory_region(bs.smem.data(), bs.smem.size());
+#endif
   if (bs.smem.size() < smem + 64) bs.smem.resize(smem + 64);
+#if defined(__SANITIZE_ADDRESS__)
+  // shared memory beyond what the launch asked for is poisoned: an overrun of the dynamic shared-memory layout is reported
+  __asan_poison_memory_region(bs.smem.data() + smem, bs.smem.size() - smem);
+#endif
   for (int t = 0; t < T; ++t) {
     Fiber& f = bs.fibers[t];
     f.done = false;
     f.at_block_barrier = false;
-    f.stack = bs.stacks.data() + (size_t)t * kStack;
+    f.stack = bs.stacks[t];
+#if defined(__SANITIZE_ADDRESS__)
+    __asan_unpoison_memory_region(f.stack, kStack);   // redzones of the previous fiber's frames (it never returned)
+#endif
     uintptr_t top = ((uintptr_t)(f.stack + kStack)) & ~(uintptr_t)15;
     void** A = (void**)(top - 16);
     *A = (void*)&trampoline;

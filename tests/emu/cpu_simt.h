@@ -28,7 +28,7 @@ namespace emu {
 struct Fiber { void* sp; char* stack; bool done; bool at_block_barrier; };
 struct BlockState {
   std::vector<Fiber> fibers;
-  std::vector<char> stacks;
+  std::vector<char*> stacks;   // one malloc per fiber (never moved: the frames on them are live between switches)
   std::vector<unsigned char> smem;
   unsigned long long xchg[1024];
   void* sched_sp;

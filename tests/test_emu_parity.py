@@ -60,6 +60,31 @@ def test_emulated_lane_order_independence(emu, oracle_mod, order, monkeypatch):
     helpers.phase_parity(emu, oracle_mod, "concar", B=2, N=7, rounds=2)
 
 
+def test_emulated_memcheck_asan():
+    """memcheck substitute (compute-sanitizer is closed on the GPU pool): the kernel sources compiled with
+    -fsanitize=address against the emulator, where "device" memory is heap memory with redzones and the shared memory
+    beyond the launch's request is poisoned, run tiny solves through every kernel (tools/sanitize.py) in a subprocess.
+    No report, and the digests equal the ones the B200 produced (profiles/r1_sanity/gpu_digests.jsonl).  Negative
+    control done by hand: reading v.horizon[v.B] in k_init is reported with file and line."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    env = dict(os.environ, IPDDP_EMU_DEFS="-fsanitize=address -fno-omit-frame-pointer -g",
+               IPDDP_EMU_LDFLAGS="-fsanitize=address", IPDDP_EMU_LIB="libipddp_emu_asan.so")
+    subprocess.run([sys.executable, os.path.join(here, "emu", "build_emu.py")], env=env, check=True, capture_output=True)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0",
+               IPDDP_LIB=os.path.join(here, "emu", "libipddp_emu_asan.so"))
+    env.pop("IPDDP_EMU_ORDER", None)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize.py")], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
+    want = open(os.path.join(root, "profiles", "r1_sanity", "gpu_digests.jsonl")).read().strip().splitlines()
+    assert r.stdout.strip().splitlines() == want
+
+
 def test_emulated_varying_horizon(emu, oracle_mod):
     helpers.full_solve_parity(emu, oracle_mod, "concar", 4, 13, maxit=80, vary_horizon=True, first=100, n_trace=4)
 
