@@ -8,7 +8,8 @@
 # interiorpointddp.jl_b200/csrc/models_gen/*.cuh and compiled with nvcc into a plugin (see INTEGRATION.md).
 module InteriorPointDDPB200
 
-export Options, BatchProblem, solve!, get_trajectory, load_model!
+export Options, BatchProblem, Stats, solve!, solve_many!, get_trajectory, get_duals, get_trace, get_stats,
+       set_tuning!, set_cohorts!, load_model!
 
 const LIB = get(ENV, "IPDDP_B200_LIB", "libipddp_b200.so")
 
@@ -62,10 +63,37 @@ mutable struct BatchProblem
     nu::Int
     nc::Int
     np::Int
+    # per-instance mirror of the reference's SolverData (src/data/solver.jl:8-33), filled by solve!
     status::Vector{Cint}
     k::Vector{Cint}
+    j::Vector{Cint}
+    l::Vector{Cint}
     objective::Vector{Cdouble}
     primal_inf::Vector{Cdouble}
+    dual_inf::Vector{Cdouble}
+    cs_inf::Vector{Cdouble}
+    μ::Vector{Cdouble}
+    reg_last::Vector{Cdouble}
+    step_size::Vector{Cdouble}
+end
+
+# mirror of `ipddp_stats` (timers of src/data/solver.jl:16-18 split per kernel, work counters)
+Base.@kwdef mutable struct Stats
+    iterations::Cint = 0
+    launches::Clonglong = 0
+    ms_total::Cdouble = 0.0
+    ms_init::Cdouble = 0.0
+    ms_derivs::Cdouble = 0.0
+    ms_backward::Cdouble = 0.0
+    ms_check::Cdouble = 0.0
+    ms_forward::Cdouble = 0.0
+    sum_backward::Clonglong = 0
+    sum_sweeps::Clonglong = 0
+    sum_kkt::Clonglong = 0
+    sum_rollouts::Clonglong = 0
+    sum_deriv_stages::Clonglong = 0
+    n_converged::Clonglong = 0
+    n_active_rounds::Clonglong = 0
 end
 
 """
@@ -84,7 +112,7 @@ function BatchProblem(model::String, B::Int, N::Int; options::Options=Options(),
                 model, B, N, isempty(indices_compl) ? C_NULL : pointer(indices_compl), length(indices_compl),
                 Ref(options), device, trace_capacity, h), "ipddp_problem_create")
     p = BatchProblem(h[], model, B, N, dims[1][], dims[2][], dims[3][], dims[4][], zeros(Cint, B), zeros(Cint, B),
-                     zeros(B), zeros(B))
+                     zeros(Cint, B), zeros(Cint, B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B))
     finalizer(q -> ccall((:ipddp_problem_destroy, LIB), Cint, (Ptr{Cvoid},), q.handle), p)
     return p
 end
@@ -102,16 +130,76 @@ function solve!(p::BatchProblem, x1::Matrix{Float64}, controls::Array{Float64,3}
                 p.handle, x1, controls, params === nothing ? C_NULL : params, lower, upper,
                 horizons === nothing ? C_NULL : horizons), "ipddp_set_inputs")
     check(ccall((:ipddp_solve, LIB), Cint, (Ptr{Cvoid}, Cint), p.handle, 0), "ipddp_solve")
+    return fetch_results!(p)
+end
+
+function fetch_results!(p::BatchProblem)
     check(ccall((:ipddp_get_results, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
                  Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
-                p.handle, p.status, p.k, C_NULL, C_NULL, p.objective, p.primal_inf, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL),
-          "ipddp_get_results")
+                p.handle, p.status, p.k, p.j, p.l, p.objective, p.primal_inf, p.dual_inf, p.cs_inf, p.μ, p.reg_last,
+                p.step_size), "ipddp_get_results")
     return p
 end
 
 "solve!(solver) of the reference (src/solve.jl:6-17): warm start from the stored nominal trajectory."
-solve!(p::BatchProblem) = (check(ccall((:ipddp_solve, LIB), Cint, (Ptr{Cvoid}, Cint), p.handle, 1), "ipddp_solve"); p)
+solve!(p::BatchProblem) = (check(ccall((:ipddp_solve, LIB), Cint, (Ptr{Cvoid}, Cint), p.handle, 1), "ipddp_solve");
+                           fetch_results!(p))
+
+"""
+    solve_many!(problems; total_solves=length(problems)) -> (elapsed_ms, Stats)
+
+Several batches in flight on one GPU (`ipddp_solve_many`; no reference counterpart): the lock-step tail of one batch
+overlaps the bulk rounds of the others.  Inputs must have been set with `set_inputs!` / a previous `solve!`.
+"""
+function solve_many!(ps::Vector{BatchProblem}; total_solves::Int=length(ps), warm_start::Bool=false)
+    hs = [p.handle for p in ps]
+    ms = Ref{Cdouble}(0.0)
+    st = Ref(Stats())
+    check(ccall((:ipddp_solve_many, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Ref{Cdouble}, Ref{Stats}),
+                hs, length(hs), total_solves, warm_start ? 1 : 0, ms, st), "ipddp_solve_many")
+    foreach(fetch_results!, ps)
+    return ms[], st[]
+end
+
+"Execution tuning that never changes results (`ipddp_set_tuning`): \"fw_spec_max\", \"bw_spec_max\", \"bulk_slots\"."
+set_tuning!(p::Union{BatchProblem,Nothing}, key::AbstractString, value::Integer) =
+    check(ccall((:ipddp_set_tuning, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint),
+                p === nothing ? C_NULL : p.handle, key, value), "ipddp_set_tuning")
+
+"Independent slices of one batch, each with its own stream (`ipddp_set_cohorts`); results are identical for every S."
+set_cohorts!(p::BatchProblem, S::Integer) =
+    check(ccall((:ipddp_set_cohorts, LIB), Cint, (Ptr{Cvoid}, Cint), p.handle, S), "ipddp_set_cohorts")
+
+function get_stats(p::BatchProblem)
+    st = Ref(Stats())
+    check(ccall((:ipddp_get_stats, LIB), Cint, (Ptr{Cvoid}, Ref{Stats}), p.handle, st), "ipddp_get_stats")
+    return st[]
+end
+
+"nominal duals (ϕ nc x (N-1) x B, zl and zu nu x (N-1) x B, λ nx x N x B): reference problem.nominal_*_duals"
+function get_duals(p::BatchProblem)
+    ϕ = zeros(p.nc, p.N - 1, p.B); zl = zeros(p.nu, p.N - 1, p.B); zu = zeros(p.nu, p.N - 1, p.B)
+    λ = zeros(p.nx, p.N, p.B)
+    check(ccall((:ipddp_get_duals, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                p.handle, ϕ, zl, zu, λ), "ipddp_get_duals")
+    return ϕ, zl, zu, λ
+end
+
+"""
+    get_trace(p, b) -> 12 x nrows matrix
+
+The numeric columns the reference prints per iteration (src/print.jl:13-29) for instance `b` (1-based): k, j, objective,
+primal_inf, dual_inf, cs_inf, μ, reg_last, step_size, l, θ, barrier Lagrangian.  Needs `trace_capacity > 0`.
+"""
+function get_trace(p::BatchProblem, b::Integer)
+    n = Ref{Cint}(0)
+    sig = (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ref{Cint})
+    check(ccall((:ipddp_get_trace, LIB), Cint, sig, p.handle, b - 1, C_NULL, n), "ipddp_get_trace")   # size query
+    rows = zeros(12, n[])
+    check(ccall((:ipddp_get_trace, LIB), Cint, sig, p.handle, b - 1, rows, n), "ipddp_get_trace")
+    return rows
+end
 
 "get_trajectory(solver) -> (states nx x N x B, controls nu x (N-1) x B)  (reference src/solver.jl:46-48)"
 function get_trajectory(p::BatchProblem)
