@@ -165,7 +165,7 @@ struct ipddp_problem {
   int spec_cap = 0;              // instances the speculative-forward record pool (DevView::spec_traj) was sized for
   int bw_spec_cap = 0;           // instances the speculative-backward output pool (DevView::spec_bw) was sized for
   size_t bw_pool_doubles() const { return (size_t)(v.N - 1) * (v.G + v.nu) + (size_t)v.N * v.nx; }
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   ipddp_stats st;
 
   template <class T> int alloc(T** p, size_t n) {
@@ -292,15 +292,18 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   if (rc != 0) { ipddp_problem_destroy(h); return -1; }
   v.compl_idx = h->d_compl; v.p = h->d_p; v.lower = h->d_lower; v.upper = h->d_upper; v.x1 = h->d_x1;
   v.ubar = h->d_ubar; v.horizon = h->d_horizon;
-  if (v.n_compl) CK(cudaMemcpy(h->d_compl, indices_compl, v.n_compl * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemset(v.traj, 0, (size_t)2 * B * N * v.TR * sizeof(double)));
-  CK(cudaMemset(v.si, 0, (size_t)SI_COUNT * B * sizeof(int)));
-  CK(cudaMemset(v.sd, 0, (size_t)SD_COUNT * B * sizeof(double)));
-  CK(cudaMemset(v.nomsel, 0, (size_t)B * sizeof(int)));
-  CK(cudaStreamCreate(&h->stream));
-  CK(cudaMallocHost((void**)&h->h_counters, CNT_COUNT * sizeof(int)));
-  for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->ev[i]));
-  if (ipddp_set_cohorts(h, 1) != 0) return -1;
+  auto finish = [&]() -> int {   // anything failing from here on releases the half-built handle
+    if (v.n_compl) CK(cudaMemcpy(h->d_compl, indices_compl, v.n_compl * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemset(v.traj, 0, (size_t)2 * B * N * v.TR * sizeof(double)));
+    CK(cudaMemset(v.si, 0, (size_t)SI_COUNT * B * sizeof(int)));
+    CK(cudaMemset(v.sd, 0, (size_t)SD_COUNT * B * sizeof(double)));
+    CK(cudaMemset(v.nomsel, 0, (size_t)B * sizeof(int)));
+    CK(cudaStreamCreate(&h->stream));
+    CK(cudaMallocHost((void**)&h->h_counters, CNT_COUNT * sizeof(int)));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->ev[i]));
+    return ipddp_set_cohorts(h, 1);
+  };
+  if (finish() != 0) { ipddp_problem_destroy(h); return -1; }
   *out = h;
   return 0;
 }
@@ -339,10 +342,9 @@ int ipddp_problem_destroy(ipddp_problem* h) {
   for (auto& c : h->cohorts) { if (c.ev) cudaEventDestroy(c.ev); if (c.own_stream && c.stream) cudaStreamDestroy(c.stream); }
   if (h->d_ccount) cudaFree(h->d_ccount);
   if (h->h_ccount) cudaFreeHost(h->h_ccount);
-  if (h->stream) {
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
-    cudaStreamDestroy(h->stream);
-  }
+  for (int i = 0; i < 8; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
 }
