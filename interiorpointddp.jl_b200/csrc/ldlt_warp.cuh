@@ -595,11 +595,19 @@ IPDDP_D int warp_ldlt_factor(double* __restrict__ A, double* __restrict__ Bm, do
     }
   }
   while (k >= 0) {
+#if defined(IPDDP_TIGHT_FAST) && IPDDP_TIGHT_FAST   // experiment awaiting its A/B (DESIGN.md "Next"): fast steps in their own inner loop
+    while (k >= 0 && ldlt_step_fast<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) {
+      IPDDP_LDLT_COUNT(0);
+      k -= 1;
+    }
+    if (k < 0) break;
+#else
     if (ldlt_step_fast<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) {
       IPDDP_LDLT_COUNT(0);
       k -= 1;
       continue;
     }
+#endif
 #if IPDDP_ONE_GENERIC
     // one instance of the general step for every k (rows >= 32 are gated by a uniform run-time flag): half the code
     const int ks = ldlt_step<K, NR, (K > 32)>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
