@@ -405,11 +405,16 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
   int kp = k;
   const bool keep = __all_sync(IPDDP_FULL_MASK, fabs(piv) >= alpha * fabs(x));   // false on any NaN
   if (!keep) {
+#if !(defined(IPDDP_NAN_BY_MAX) && IPDDP_NAN_BY_MAX)
     if (__any_sync(IPDDP_FULL_MASK, x != x) || piv != piv) return false;
+#endif
     // imax: first row attaining max |x|
     const double ax = fabs(x);
     const unsigned hi = in ? (unsigned)__double2hiint(ax) : 0u;
     const unsigned mh = __reduce_max_sync(IPDDP_FULL_MASK, hi);
+#if defined(IPDDP_NAN_BY_MAX) && IPDDP_NAN_BY_MAX   // experiment awaiting its A/B: NaN (and Inf) rows show up in the maximum, no extra vote
+    if (mh >= 0x7ff00000u || piv != piv) return false;
+#endif
     unsigned cand = __ballot_sync(IPDDP_FULL_MASK, in && hi == mh);
     if (cand & (cand - 1u)) {   // several rows share the high word: compare the low words among them
       const unsigned lo = (in && hi == mh) ? (unsigned)__double2loint(ax) : 0u;
@@ -446,6 +451,23 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
     S::dinv(scratch)[k] = rinv;
   }                                              // (nzhi[k] is only read for k > 32: nothing to clear here)
   if (nzm == 0u) return true;                // nothing to eliminate; B(k,:) scaling is deferred
+#if defined(IPDDP_NNZ1) && IPDDP_NNZ1   // experiment awaiting its A/B: 26 % of the 1x1 steps have ONE non-zero row (profiles/r1_ab)
+  if ((nzm & (nzm - 1u)) == 0u) {            // its lane owns the only element of the trailing update: no list, no shuffles
+    __syncwarp();                            // the interchange above stored a diagonal element from lane 0
+    if (x != 0.0) {
+      const int e = coff(lane) + lane;
+      A[e] = IPDDP_FMA(x, -rinv * x, A[e]);
+      const double xs = x * rinv;
+      A[ck + lane] = xs;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) Bm[lane + j * K] = IPDDP_FMA(xs, -Bm[k + j * K], Bm[lane + j * K]);
+    } else if (kp != k && in) {
+      A[ck + lane] = 0.0;
+    }
+    __syncwarp();
+    return true;
+  }
+#endif
   unsigned char* list = S::list(scratch);
   if (x != 0.0) list[__popc(nzm & ((1u << lane) - 1u))] = (unsigned char)lane;
   __syncwarp();
