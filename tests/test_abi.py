@@ -66,3 +66,25 @@ def test_sass_is_sm100a(product_lib):
     from ipddp_b200 import _lib
     out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_julia_stub_struct_layouts_match_the_header():
+    """julia/InteriorPointDDPB200.jl cannot be executed here; at least its Options / Stats mirrors must have the C
+    structs' field count and type sequence (they are passed by reference through ccall), and every function it binds
+    must be declared in include/ipddp_b200.h."""
+    import ctypes as C
+    import re
+    from ipddp_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "julia", "InteriorPointDDPB200.jl"), encoding="utf-8").read()
+
+    def fields(name):
+        body = re.search(r"mutable struct %s\n(.*?)\nend" % name, jl, re.S).group(1)
+        return re.findall(r"::(Cint|Cdouble|Clonglong)\b", body)
+
+    ctype = {C.c_int: "Cint", C.c_double: "Cdouble", C.c_longlong: "Clonglong"}
+    assert fields("Options") == [ctype[t] for _, t in _lib.Options._fields_]
+    assert fields("Stats") == [ctype[t] for _, t in _lib.Stats._fields_]
+    header = open(os.path.join(root, "include", "ipddp_b200.h")).read()
+    bound = set(re.findall(r"\(:(ipddp_[a-z_0-9]+), LIB\)", jl))
+    assert bound and all(re.search(r"\b%s\(" % f, header) for f in bound), sorted(bound)
