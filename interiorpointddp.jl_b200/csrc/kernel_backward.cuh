@@ -312,7 +312,12 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
     // ---- ineq gains to HBM                                            (:159-172)
     double* gi = g + K * NR;
     for (int e = lane; e < NU * NR; e += 32) {
+#if defined(IPDDP_GAINS_UDIV) && IPDDP_GAINS_UDIV   // experiment awaiting its A/B: the signed e / NU compiles to ~20 byte-permute instructions
+      const int j = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)NU + 1u));
+      const int i = e - j * NU;
+#else
       const int i = e % NU, j = e / NU;
+#endif
       if (j == 0) {
         const double al = rhs[i];
         double cl = ra1[i] * mu;      // chi^L = mu / il, recomputed from the stored reciprocal (same operands, same bits)

@@ -143,6 +143,7 @@ static inline int __ffs(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int __ffsll(long long x) { return x ? __builtin_ctzll((unsigned long long)x) + 1 : 0; }
 static inline double __hiloint2double(int hi, int lo) { return emu_ll2d(((long long)(unsigned)hi << 32) | (unsigned)lo); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline int __double2hiint(double x) { return (int)(emu_d2ll(x) >> 32); }
 static inline int __double2loint(double x) { return (int)(emu_d2ll(x) & 0xffffffffll); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

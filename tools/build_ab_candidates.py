@@ -14,8 +14,9 @@ CANDIDATES = [
     ("c_tight", ["-DIPDDP_TIGHT_FAST=1"]),
     ("c_nnz1", ["-DIPDDP_NNZ1=1"]),
     ("c_nanmax", ["-DIPDDP_NAN_BY_MAX=1"]),
+    ("c_udiv", ["-DIPDDP_GAINS_UDIV=1"]),
     ("c_nnz1_nanmax", ["-DIPDDP_NNZ1=1", "-DIPDDP_NAN_BY_MAX=1"]),
-    ("c_all", ["-DIPDDP_TIGHT_FAST=1", "-DIPDDP_NNZ1=1", "-DIPDDP_NAN_BY_MAX=1"]),
+    ("c_all", ["-DIPDDP_TIGHT_FAST=1", "-DIPDDP_NNZ1=1", "-DIPDDP_NAN_BY_MAX=1", "-DIPDDP_GAINS_UDIV=1"]),
 ]
 
 if __name__ == "__main__":
