@@ -5,15 +5,18 @@ metric   : converged OCP solves/sec (batched)            unit: solves/s
 workload : BASELINE configs[1] = cartpole swing-up, batch of 16384 random initial states, N = 101 knots,
            optimality_tolerance 1e-7, on ONE B200 (per GPU; weak scaling over GPUs: every rank solves its
            own 16384 instances, no data-path collective, one NCCL all-reduce of statistics at the end).
-step     : one complete batched solve (initialise + derivative / backward / check / forward rounds until
-           every instance terminated) of one batch of synthetic instances.
+step     : one batch of 16384 synthetic instances solved to termination (initialise + derivative / backward / check /
+           forward rounds).  The K steps of a timed region are queued behind each other on ONE problem handle whose
+           resident slots are refilled instance by instance (ipddp_solve_queue), so the rounds stay full.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--workload W]
 
-`value`  : device-timed (CUDA events on the library's stream), inputs already resident in HBM.
+`value`  : device-timed (CUDA events on the library's stream), inputs and outputs resident in HBM.
 `e2e`    : the same metric through the C ABI with HOST buffers: pinned H2D of the inputs + solve + D2H of
-           the SolverData scalars and the trajectories, inside the timed region.
---impl reference : the CPU restatement of the reference (oracle/, OpenMP over instances on all host cores)
+           the SolverData scalars, work counters and the trajectories, inside the timed region.
+`configs`: short runs of BASELINE configs 3-5 (acrobot 8192 x 201 knots sharded over the GPUs, concar / concar_quad
+           4096, pushing 2048 with horizons 61..141), each with its KKT rate, roofline fractions and the oracle's rate.
+--impl reference : the CPU restatement of the reference (oracle/, -O3, OpenMP over instances on all host cores)
            on a bounded sample of the same workload.  (The reference itself is Julia; no Julia here.)
 """
 import argparse
@@ -105,16 +108,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+# BASELINE.json configs 3-5 (config 2 is the headline workload): short runs reported under "configs".
+# batch = instances of the whole job (sharded over the ranks: strong scaling), knots = max horizon.
+OTHER_CONFIGS = [
+    dict(name="config3", workload="acrobot", batch=8192, knots=201, vary=False, span=0,
+         what="acrobot batch 8192, N=200 stages (201 knots), sharded over the GPUs"),
+    dict(name="config4a", workload="concar", batch=4096, knots=101, vary=False, span=0,
+         what="concar (state+control constraints and bounds) batch 4096"),
+    dict(name="config4b", workload="concar_quad", batch=4096, knots=101, vary=False, span=0, what="concar_quad batch 4096"),
+    dict(name="config5", workload="pushing", batch=2048, knots=141, vary=True, span=80,
+         what="planar pushing (contact complementarity) batch 2048, horizons 61..141 knots"),
+]
+
+
+def reference_sample(args, cores, per_core):
+    """Bounded sample of the headline workload for the CPU arm: instances 1000.. of the canonical stream (past the 100
+    reference rows), not the first ones."""
+    n = args.cpu_sample if args.cpu_sample > 0 else cores * per_core
+    return max(cores, min(args.batch, n)), 1000
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle (literal restatement of the reference, -O2, OpenMP over instances) on all host cores."""
+    """CPU arm: the oracle (literal restatement of the reference, -O3, OpenMP over instances) on all host cores."""
     if rank != 0:
         return
     import oracle
     import ipddp_b200  # noqa: F401
     from ipddp_b200 import instances
     cores = os.cpu_count() or 1
-    sample = max(cores, min(args.batch, args.cpu_sample if args.cpu_sample > 0 else cores * 48))
-    b = instances.make_batch(args.workload, sample, args.knots)
+    sample, first = reference_sample(args, cores, 48)
+    b = instances.make_batch(args.workload, sample, args.knots, first=first)
     opt = oracle.default_options(optimality_tolerance=args.tol)
     conv = 0
     tot = 0.0
@@ -129,7 +153,8 @@ def run_reference(args, rank, world):
             conv += sum(1 for r in res if r.status == 0)
             kkt += sum(r.n_kkt for r in res)
     val = conv / tot
-    sample_txt = f"first {sample} instances of the workload per step, {cores} OpenMP threads"
+    sample_txt = (f"instances {first}..{first + sample - 1} of the workload's stream per step ({sample} of the {args.batch} "
+                  f"a GPU step solves; per-instance rate), {cores} OpenMP threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -150,15 +175,16 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16384, help="instances per GPU")
+    ap.add_argument("--batch", type=int, default=16384, help="instances per GPU and step")
+    ap.add_argument("--slots", type=int, default=0, help="resident instance slots of the handle (0 = --batch)")
     ap.add_argument("--workload", default="cartpole")
     ap.add_argument("--knots", type=int, default=101)
     ap.add_argument("--tol", type=float, default=1e-7)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU baseline sample (0 = 128 x cores for cpu_baseline, 48 x cores per step for --impl reference)")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="instances of the CPU baseline sample (0 = 128 x cores for cpu_baseline, 48 x cores per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=8, help="independent batches in flight during the timed steps")
-    ap.add_argument("--seq-steps", type=int, default=2,
-                    help="steps of the sequential region (one batch at a time, per-kernel CUDA events: rooflines)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE configs 3-5")
+    ap.add_argument("--no-single", action="store_true", help="skip the lone-batch (one step, nothing queued behind it) run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -170,11 +196,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import ipddp_b200  # noqa: F401
     from ipddp_b200 import _lib, instances
-    from ipddp_b200.batch import BatchSolver, solve_many
+    from ipddp_b200.batch import BatchSolver, make_queue
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -184,120 +211,178 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     nx, nu, nc, npar, slots = lib.model_dims(args.workload)
-    B, N = args.batch, args.knots
-
-    # every rank takes its own contiguous range of the workload's canonical instance stream
-    batch = instances.make_batch(args.workload, B, N, first=rank * B)
+    B, N, K = args.batch, args.knots, args.steps
+    S = args.slots if args.slots > 0 else B
     opt = lib.default_options(optimality_tolerance=args.tol)
-    F = max(1, min(args.inflight, args.steps))
-    solvers = [BatchSolver(args.workload, B, N, options=opt, device=local_rank, lib=lib) for _ in range(F)]
-    solver = solvers[0]
-
-    # pinned host copies (e2e path) and device-resident copies (value path)
-    def pin(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h = {k: pin(v) for k, v in dict(x1=batch.x1, ubar=batch.ubar, p=batch.p if npar > 0 else np.zeros((B, 1)),
-                                     lower=batch.lower, upper=batch.upper).items()}
-    h_hz = torch.from_numpy(batch.horizons.astype(np.int32)).pin_memory()
-    d = {k: t.to(dev, non_blocking=True) for k, t in h.items()}
-    d_hz = h_hz.to(dev)
-    torch.cuda.synchronize()
-
-    def set_device_inputs(sv):
-        sv.set_inputs_device(d["x1"].data_ptr(), d["ubar"].data_ptr(), d["p"].data_ptr() if npar > 0 else None,
-                             d["lower"].data_ptr(), d["upper"].data_ptr(), d_hz.data_ptr())
-
-    def set_host_inputs(sv):
-        sv.lib.check(sv.lib.L.ipddp_set_inputs(
-            sv.h, _lib.dptr(h["x1"].numpy()), _lib.dptr(h["ubar"].numpy()),
-            _lib.dptr(h["p"].numpy()) if npar > 0 else None, _lib.dptr(h["lower"].numpy()), _lib.dptr(h["upper"].numpy()),
-            _lib.iptr(h_hz.numpy())), "ipddp_set_inputs")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for sv in solvers:
-        set_device_inputs(sv)
-    # warm-up: W untimed steps through the same pipelined path as the timed region, plus one sequential solve
+    # every rank takes its own contiguous range of the workload's canonical instance stream; a step is one batch of B
+    # instances, the K steps of a timed region are queued behind each other on ONE handle with S resident slots
+    batch = instances.make_batch(args.workload, B, N, first=rank * B)
+    names = ["x1", "ubar", "p", "lower", "upper"]
+    host1 = dict(x1=batch.x1, ubar=batch.ubar, p=batch.p if npar > 0 else np.zeros((B, 1)), lower=batch.lower, upper=batch.upper)
+    solver = BatchSolver(args.workload, S, N, options=opt, device=local_rank, lib=lib)
+
+    class DevQueue:
+        """`steps` copies of the batch as one queue, inputs and outputs resident in HBM."""
+
+        def __init__(self, steps):
+            self.Q = Q = steps * B
+            self.t = {k: torch.from_numpy(np.ascontiguousarray(host1[k])).to(dev).repeat(steps, 1) for k in names}
+            self.hz = torch.from_numpy(batch.horizons.astype(np.int32)).to(dev).repeat(steps)
+            self.oi = [torch.zeros(Q, dtype=torch.int32, device=dev) for _ in range(4)]
+            self.od = [torch.zeros(Q, dtype=torch.float64, device=dev) for _ in range(7)]
+            self.oc = [torch.zeros(Q, dtype=torch.int32, device=dev) for _ in range(4)]
+            self.x = torch.zeros((Q, N, nx), dtype=torch.float64, device=dev)
+            self.u = torch.zeros((Q, N - 1, nu), dtype=torch.float64, device=dev)
+            t = self.t
+            self.q = make_queue(Q, t["x1"].data_ptr(), t["ubar"].data_ptr(), t["p"].data_ptr() if npar > 0 else None,
+                                t["lower"].data_ptr(), t["upper"].data_ptr(), self.hz.data_ptr(),
+                                [a.data_ptr() for a in self.oi + self.od + self.oc], self.x.data_ptr(), self.u.data_ptr(),
+                                inputs_on_device=True, outputs_on_device=True)
+
+        def solve(self):
+            lib.check(lib.L.ipddp_solve_queue(solver.h, C.byref(self.q)), "ipddp_solve_queue")
+            return solver.stats()
+
+    # ---------------------------------------------------- warm-up: W untimed steps through the same path
     if args.warmup > 0:
-        solve_many(solvers[:min(F, args.warmup)], total_solves=args.warmup)
-        solver.solve()
+        DevQueue(args.warmup).solve()
+        torch.cuda.empty_cache()
 
-    # ---------------------------------------------------- timed region A: K steps one after another (kernels timed alone)
-    agg = dict(ms_total=0.0, ms_derivs=0.0, ms_backward=0.0, ms_check=0.0, ms_forward=0.0, ms_init=0.0, kkt=0, sweeps=0,
-               rollouts=0, deriv=0, conv=0, launches=0, rounds=0, active_rounds=0, backward_calls=0)
-    seq_steps = max(1, min(args.steps, args.seq_steps))
-    barrier()
-    for _ in range(seq_steps):
-        set_device_inputs(solver)
-        solver.solve()
-        st = solver.stats()
-        agg["ms_total"] += st.ms_total; agg["ms_derivs"] += st.ms_derivs; agg["ms_backward"] += st.ms_backward
-        agg["ms_check"] += st.ms_check; agg["ms_forward"] += st.ms_forward; agg["ms_init"] += st.ms_init
-        agg["kkt"] += st.sum_kkt; agg["sweeps"] += st.sum_sweeps; agg["rollouts"] += st.sum_rollouts
-        agg["deriv"] += st.sum_deriv_stages; agg["conv"] += st.n_converged; agg["launches"] += st.launches
-        agg["rounds"] += st.iterations; agg["active_rounds"] += st.n_active_rounds; agg["backward_calls"] += st.sum_backward
-    barrier()
-    res = solver.results()
-
-    # ---------------------------------------------------- timed region B: the same K steps, up to F batches in flight
-    # (independent problem handles on their own streams, ipddp_solve_many): whole-job throughput, inputs resident in HBM
+    # ---------------------------------------------------- timed region A (`value`): K steps, inputs resident in HBM.
+    # Device time by CUDA events on the library's stream from the first enqueue to the last completion
+    # (ipddp_stats.ms_total), per-kernel CUDA events of the same region for the rooflines.
+    dq = DevQueue(K)
     barrier()
     with ClockSampler(local_rank) as clk:
-        ms_pipe, st_pipe = solve_many(solvers, total_solves=args.steps)
+        st = dq.solve()
         barrier()
     clocks = clk.summary()
+    agg = dict(ms_total=st.ms_total, ms_derivs=st.ms_derivs, ms_backward=st.ms_backward, ms_check=st.ms_check,
+               ms_forward=st.ms_forward, kkt=st.sum_kkt, sweeps=st.sum_sweeps, rollouts=st.sum_rollouts,
+               backward_calls=st.sum_backward, conv=st.n_converged, launches=st.launches, rounds=st.iterations,
+               active_rounds=st.n_active_rounds)
+    status_d, k_d, prim_d = dq.oi[0], dq.oi[1], dq.od[1]
+    conv_mask = status_d == 0
+    ksum = float(k_d.double().sum().item())
+    pr_max = float(prim_d[conv_mask].max().item()) if bool(conv_mask.any()) else 0.0
+    del dq
+    torch.cuda.empty_cache()
 
-    # ---------------------------------------------------- timed region C: end to end through host buffers, F in flight
-    hxs = [torch.from_numpy(np.zeros((B, N, nx))).pin_memory() for _ in range(F)]
-    hus = [torch.from_numpy(np.zeros((B, N - 1, nu))).pin_memory() for _ in range(F)]
+    # ---------------------------------------------------- lone batch: one step with nothing queued behind it (the
+    # lock-step tail of its slowest instances is exposed)
+    single = None
+    if not args.no_single:
+        d1 = DevQueue(1)
+        barrier()
+        s1 = d1.solve()
+        barrier()
+        single = dict(ms=s1.ms_total, conv=s1.n_converged, rounds=s1.iterations, active_rounds=s1.n_active_rounds)
+        del d1
+        torch.cuda.empty_cache()
+
+    # ---------------------------------------------------- timed region B (`e2e`): the same K steps through HOST buffers:
+    # pinned inputs -> H2D, solve, D2H of the SolverData scalars, counters and trajectories, all inside the timed region
+    Q = K * B
+
+    def pin(a, reps):
+        return torch.from_numpy(np.ascontiguousarray(a)).repeat(reps, *([1] * (a.ndim - 1))).pin_memory()
+    hin = {k: pin(host1[k], K) for k in names}
+    hhz = pin(batch.horizons.astype(np.int32), K)
+    hoi = [torch.zeros(Q, dtype=torch.int32).pin_memory() for _ in range(4)]
+    hod = [torch.zeros(Q, dtype=torch.float64).pin_memory() for _ in range(7)]
+    hoc = [torch.zeros(Q, dtype=torch.int32).pin_memory() for _ in range(4)]
+    hx = torch.zeros((Q, N, nx), dtype=torch.float64).pin_memory()
+    hu = torch.zeros((Q, N - 1, nu), dtype=torch.float64).pin_memory()
+    hq = make_queue(Q, hin["x1"].data_ptr(), hin["ubar"].data_ptr(), hin["p"].data_ptr() if npar > 0 else None,
+                    hin["lower"].data_ptr(), hin["upper"].data_ptr(), hhz.data_ptr(),
+                    [a.data_ptr() for a in hoi + hod + hoc], hx.data_ptr(), hu.data_ptr())
     barrier()
     t0 = time.perf_counter()
-    conv_e2e = 0
-    done = 0
-    while done < args.steps:
-        nb = min(F, args.steps - done)
-        for sv in solvers[:nb]:
-            set_host_inputs(sv)
-        solve_many(solvers[:nb], total_solves=nb)
-        for q, sv in enumerate(solvers[:nb]):
-            r = sv.results()
-            sv.lib.check(sv.lib.L.ipddp_get_trajectory(sv.h, _lib.dptr(hxs[q].numpy()), _lib.dptr(hus[q].numpy())), "get_trajectory")
-            conv_e2e += int((r.status == 0).sum())
-        done += nb
+    lib.check(lib.L.ipddp_solve_queue(solver.h, C.byref(hq)), "ipddp_solve_queue")
+    conv_e2e = int((hoi[0].numpy() == 0).sum())     # the device->host read of the step results
     barrier()
     wall_e2e = time.perf_counter() - t0
-    h2d = sum(int(t.numel() * t.element_size()) for k_, t in h.items() if not (npar == 0 and k_ == "p")) + int(h_hz.numel() * 4)
-    d2h = B * (4 * 4 + 7 * 8) + int(hxs[0].numel() * 8) + int(hus[0].numel() * 8)
+    st_e2e = solver.stats()
+    h2d = sum(int(t.numel() * t.element_size()) for k_, t in hin.items() if not (npar == 0 and k_ == "p")) // K + B * 4
+    d2h = B * (8 * 4 + 7 * 8) + (int(hx.numel()) + int(hu.numel())) * 8 // K
 
     # ------------------------------------------------------------------ reduce over ranks
-    vals = torch.tensor([agg["ms_total"], wall_e2e, ms_pipe], dtype=torch.float64, device=dev)
-    sums = torch.tensor([agg["conv"], conv_e2e, st_pipe.sum_kkt, float(st_pipe.n_converged), agg["rollouts"], st_pipe.launches,
-                         int((res.status == 0).sum()), float(res.k.sum()), float(res.primal_inf[res.status == 0].max(initial=0.0))],
-                        dtype=torch.float64, device=dev)
+    vals = torch.tensor([agg["ms_total"], wall_e2e, single["ms"] if single else 0.0], dtype=torch.float64, device=dev)
+    sums = torch.tensor([agg["conv"], conv_e2e, agg["kkt"], agg["launches"] + st_e2e.launches, ksum,
+                         single["conv"] if single else 0.0, pr_max], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)      # time = max over ranks
         mx = sums[-1:].clone()
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)      # the single NCCL reduction of convergence statistics
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sums[-1] = mx[0]
-    ms_total, wall_e2e_max, ms_pipe_max = [float(x) for x in vals.tolist()]
-    conv_all, conv_e2e_all, kkt_pipe_all, conv_pipe_all, roll_all, launches_all, conv_last, ksum, pr_max = [float(x) for x in sums.tolist()]
+    ms_total, wall_e2e_max, ms_single = [float(x) for x in vals.tolist()]
+    conv_all, conv_e2e_all, kkt_all, launches_all, ksum_all, conv_single, pr_max = [float(x) for x in sums.tolist()]
+
+    # ------------------------------------------------------------------ BASELINE configs 3-5, short runs (every rank its shard)
+    cfg_lines = []
+    if not args.no_configs:
+        fp64_peak_cfg = float(lib.L.ipddp_measure_fp64_tflops(local_rank))
+        for cfg in OTHER_CONFIGS:
+            wl, Bc, Nc = cfg["workload"], cfg["batch"], cfg["knots"]
+            lo, hi = (Bc * rank) // world, (Bc * (rank + 1)) // world
+            cb = instances.make_batch(wl, hi - lo, Nc, vary_horizon=cfg["vary"], first=lo, horizon_span=cfg["span"] or 40)
+            cs = BatchSolver(wl, hi - lo, Nc, options=opt, device=local_rank, lib=lib)
+            cnx, cnu, cnc, cnp, cslots = lib.model_dims(wl)
+            barrier()
+            for rep in range(2):   # first pass = warm-up
+                r_, cnt_, _, _ = cs.solve_queue(cb.x1, cb.ubar, cb.p if cnp > 0 else None, cb.lower, cb.upper, cb.horizons,
+                                                want_traj=False)
+            cst = cs.stats()
+            cs.close()
+            barrier()
+            v = torch.tensor([cst.ms_total, cst.ms_backward], dtype=torch.float64, device=dev)
+            sm_ = torch.tensor([float(cst.n_converged), float(cst.sum_kkt), float(cst.iterations), float(cst.n_active_rounds)],
+                               dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(v, op=dist.ReduceOp.MAX)
+                dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+            ms_c, ms_bw = [float(x) for x in v.tolist()]
+            conv_c, kkt_c, rounds_c, act_c = [float(x) for x in sm_.tolist()]
+            line_c = {"name": cfg["name"], "workload": cfg["what"], "batch": Bc, "knots": Nc, "n_gpus": world,
+                      "scaling": "strong" if world > 1 else None, "instances_per_gpu": hi - lo,
+                      "solves_per_s": conv_c / (ms_c * 1e-3), "ms": ms_c, "converged_fraction": conv_c / Bc,
+                      "rounds": rounds_c / world, "mean_active_fraction": act_c / max(1.0, rounds_c) / (hi - lo),
+                      "backward_kkt_steps_per_s": kkt_c / (ms_bw * 1e-3) if ms_bw > 0 else None,
+                      "roofline_frac_hbm": (kkt_bytes_dense(cnx, cnu, cnc) * kkt_c / world / (ms_bw * 1e-3) / 1e9 / hbm_peak) if ms_bw > 0 else None,
+                      "roofline_frac_fp64": (kkt_flops(cnx, cnu, cnc) * kkt_c / world / (ms_bw * 1e-3) / 1e12 / fp64_peak_cfg)
+                      if ms_bw > 0 and fp64_peak_cfg > 0 else None}
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                import oracle
+                cores = os.cpu_count() or 1
+                ns = min(Bc, 4 * cores)
+                ob = instances.make_batch(wl, ns, Nc, vary_horizon=cfg["vary"], first=1000, horizon_span=cfg["span"] or 40)
+                t1 = time.perf_counter()
+                ores, _, _ = oracle.solve_batch(wl, Nc, ob.p, ob.lower, ob.upper, ob.x1, ob.ubar,
+                                                options=oracle.default_options(optimality_tolerance=args.tol),
+                                                horizons=ob.horizons, nthreads=cores)
+                dt = time.perf_counter() - t1
+                line_c["cpu"] = {"solves_per_s": sum(1 for o in ores if o.status == 0) / dt, "cores": cores, "kind": "port",
+                                 "sample": f"{ns} instances (1000.. of the stream), one pass, {dt:.1f} s"}
+            cfg_lines.append(line_c)
 
     if rank == 0:
-        value = conv_pipe_all / (ms_pipe_max * 1e-3)
-        value_sequential = conv_all / (ms_total * 1e-3)   # over the seq_steps sequential steps
+        value = conv_all / (ms_total * 1e-3)
         e2e_val = conv_e2e_all / wall_e2e_max
-        # roofline of the dominant kernel (backward sweep) on rank 0
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        # rooflines of the dominant kernel (backward sweep) from the per-kernel CUDA events of timed region A, rank 0
         fp64_peak = float(lib.L.ipddp_measure_fp64_tflops(local_rank))
         flops_kkt = kkt_flops(nx, nu, nc)
         tb = agg["ms_backward"] * 1e-3
@@ -305,80 +390,110 @@ def main():
         gb_dense = kkt_bytes_dense(nx, nu, nc) * kkt_rank / tb / 1e9
         gb_compact = kkt_bytes_compact(nx, nu, nc, slots) * kkt_rank / tb / 1e9
         tf = flops_kkt * kkt_rank / tb / 1e12
-        # dram__bytes_read+write of one k_backward launch from the committed ncu --set full capture
-        # (profiles/r1_backward_summary.md): bytes per KKT step x the KKT steps of an average launch here
-        ncu_bytes_per_kkt = None
+        # dram__bytes_read+write of k_backward from the committed ncu --set full capture (profiles/ncu_traffic.json):
+        # bytes per timestep-KKT x the timestep-KKTs of an average launch of this run
+        ncu_bytes_per_kkt, ncu_src = None, None
         try:
-            ncu_bytes_per_kkt = float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload]["dram_bytes_per_kkt_step"])
+            nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload]
+            ncu_bytes_per_kkt, ncu_src = float(nt["dram_bytes_per_kkt_step"]), nt.get("source")
         except Exception:
             pass
         launches_bw = max(1, agg["rounds"])
         traffic = ncu_bytes_per_kkt * kkt_rank / launches_bw if ncu_bytes_per_kkt else None
         roof_hbm = {"bound": "hbm", "kernel": "k_backward", "achieved": gb_dense, "peak": hbm_peak, "unit": "GB/s",
                     "frac": gb_dense / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
+                    "traffic_source": f"ncu capture ({ncu_src}): bytes per timestep-KKT x timestep-KKTs per launch of this run" if traffic else None,
                     "algorithmic_bytes_per_launch": kkt_bytes_dense(nx, nu, nc) * kkt_rank / launches_bw,
+                    "launches": launches_bw, "avg_launch_ms": agg["ms_backward"] / launches_bw,
+                    "region": "the timed region `value` is measured on (per-kernel CUDA events on the launching stream)",
                     "note": "achieved = SURVEY 8(d) dense-tile bytes per timestep-KKT x KKT steps / backward-kernel time; "
                             f"this layout moves {kkt_bytes_compact(nx, nu, nc, slots)} B per KKT step (compact tile), i.e. "
                             f"{gb_compact:.1f} GB/s actual"}
         roof_fp64 = {"bound": "fp64", "kernel": "k_backward", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": tf / fp64_peak if fp64_peak > 0 else None, "peak_source": "DFMA microbenchmark, measured live",
                      "flops_per_kkt_step": flops_kkt}
-        nst = agg["deriv"] * (N - 1) if agg["deriv"] else 0
+        nst = agg["backward_calls"] * (N - 1)
         td = agg["ms_derivs"] * 1e-3
         tfw = agg["ms_forward"] * 1e-3
         d_bytes = 8 * (slots + nx + nu + nc)
         f_bytes = 8 * ((nu + nc + 2 * nu) * (nx + 1) + (nx + 3 * nu + nc) + (nx + 5 * nu + 2 * nc))
+        ktot = agg["ms_derivs"] + agg["ms_backward"] + agg["ms_check"] + agg["ms_forward"]
         kernels = {
-            "k_derivs": {"ms": agg["ms_derivs"], "GBps_compact_layout": d_bytes * nst / td / 1e9 if td > 0 else None,
+            "k_derivs": {"ms": agg["ms_derivs"], "share": agg["ms_derivs"] / ktot,
+                         "GBps_compact_layout": d_bytes * nst / td / 1e9 if td > 0 else None,
                          "frac_hbm": d_bytes * nst / td / 1e9 / hbm_peak if td > 0 else None},
-            "k_backward": {"ms": agg["ms_backward"], "kkt_steps_per_s": kkt_rank / tb},
-            "k_check": {"ms": agg["ms_check"]},
-            "k_forward": {"ms": agg["ms_forward"], "rollouts": agg["rollouts"],
+            "k_backward": {"ms": agg["ms_backward"], "share": agg["ms_backward"] / ktot, "kkt_steps_per_s": kkt_rank / tb},
+            "k_check": {"ms": agg["ms_check"], "share": agg["ms_check"] / ktot},
+            "k_forward": {"ms": agg["ms_forward"], "share": agg["ms_forward"] / ktot, "rollouts": agg["rollouts"],
                           "GBps": f_bytes * (N - 1) * agg["rollouts"] / tfw / 1e9 if tfw > 0 else None,
                           "frac_hbm": f_bytes * (N - 1) * agg["rollouts"] / tfw / 1e9 / hbm_peak if tfw > 0 else None},
-            "k_init": {"ms": agg["ms_init"]},
+            "host_gaps_ms": agg["ms_total"] - ktot,
         }
         cpu = None
+        parity = {"parity_checked": 0, "parity_mismatches": None}
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             cores = os.cpu_count() or 1
             sample = max(cores, min(B, args.cpu_sample if args.cpu_sample > 0 else cores * 128))
-            sb = instances.make_batch(args.workload, sample, N)
+            sb = batch.slice(0, sample)
             t0 = time.perf_counter()
-            ores, _, _ = oracle.solve_batch(args.workload, N, sb.p, sb.lower, sb.upper, sb.x1, sb.ubar,
-                                            options=oracle.default_options(optimality_tolerance=args.tol),
-                                            horizons=sb.horizons, nthreads=cores)
+            ores, oxs, ous = oracle.solve_batch(args.workload, N, sb.p, sb.lower, sb.upper, sb.x1, sb.ubar,
+                                                options=oracle.default_options(optimality_tolerance=args.tol),
+                                                horizons=sb.horizons, nthreads=cores, want_traj=True)
             dt = time.perf_counter() - t0
             oc = sum(1 for r in ores if r.status == 0)
             cpu = {"value": oc / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"first {sample} instances of the workload, one pass, {cores} OpenMP threads, {dt:.1f} s",
+                   "sample": f"first {sample} instances of the step's batch, one pass, {cores} OpenMP threads, {dt:.1f} s "
+                             "(trajectories returned: the same results are the checker of parity_checked)",
                    "kkt_steps_per_s": sum(r.n_kkt for r in ores) / dt}
+            # the GPU results of the e2e region (host buffers), first step, same instances: bitwise against the oracle
+            gs, gk, gobj = hoi[0].numpy()[:sample], hoi[1].numpy()[:sample], hod[0].numpy()[:sample]
+            gkkt = hoc[2].numpy()[:sample]
+            gx, gu = hx.numpy()[:sample], hu.numpy()[:sample]
+            bad = 0
+            for i, o in enumerate(ores):
+                same = (int(gs[i]) == o.status and int(gk[i]) == o.k and int(gkkt[i]) == o.n_kkt
+                        and np.float64(gobj[i]).view(np.int64) == np.float64(o.objective).view(np.int64))
+                if same:
+                    xa, xb = gx[i], np.asarray(oxs[i]).reshape(gx[i].shape)
+                    ua, ub = gu[i], np.asarray(ous[i]).reshape(gu[i].shape)
+                    same = bool((((xa.view(np.int64) == xb.view(np.int64)) | ((xa == 0) & (xb == 0))).all())
+                                and (((ua.view(np.int64) == ub.view(np.int64)) | ((ua == 0) & (ub == 0))).all()))
+                bad += 0 if same else 1
+            parity = {"parity_checked": sample, "parity_mismatches": bad,
+                      "parity_what": "status, k, timestep-KKT count, objective bits, state and control trajectory bits of the GPU "
+                                     "e2e results vs the oracle, instance by instance"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_pipe_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload} swing-up batch of {B} random initial states per GPU, N={N} knots, tol {args.tol:g}",
-                       "batch_per_gpu": B, "knots": N, "l2": "working set (trajectories+gains > 8 GB) far exceeds the 126 MB L2",
+                       "batch_per_gpu": B, "knots": N, "resident_slots": S,
+                       "l2": "working set (trajectories+gains > 8 GB) far exceeds the 126 MB L2",
                        "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
-                       "steps_in_flight": F,
-                       "timing": "value/e2e: the K steps run with up to steps_in_flight independent batches in flight on their own "
-                                 "streams (ipddp_solve_many), device time by CUDA events from first enqueue to last completion; "
-                                 "roofline/kernels/sequential: sequential.steps of the same steps one after another, per-kernel "
-                                 "CUDA events on the launching stream"},
-            "sequential": {"value": value_sequential, "ms_per_step": ms_total / seq_steps, "steps": seq_steps},
-            "converged_fraction": conv_last / (B * world), "mean_iterations": ksum / (B * world), "max_primal_inf": pr_max,
-            "backward_kkt_steps_per_s": kkt_pipe_all / (ms_pipe_max * 1e-3),
+                       "timing": "value/e2e: the K steps (K x batch instances) are queued on ONE handle with resident_slots instance "
+                                 "slots (ipddp_solve_queue: a slot whose instance terminated is refilled before the next round); "
+                                 "value = device time by CUDA events on the library's stream from first enqueue to last completion, "
+                                 "inputs and outputs in HBM; e2e = wall clock around the same call with pinned HOST buffers; "
+                                 "roofline/kernels/lockstep come from the per-kernel CUDA events of the `value` region itself"},
+            "sequential": ({"value": conv_single / (ms_single * 1e-3), "ms_per_step": ms_single, "steps": 1,
+                            "rounds": single["rounds"], "mean_active_fraction": single["active_rounds"] / max(1, single["rounds"]) / S,
+                            "what": "ONE batch with nothing queued behind it: the lock-step tail of its slowest instances is exposed"}
+                           if single else None),
+            "converged_fraction": conv_all / (K * B * world), "mean_iterations": ksum_all / (K * B * world), "max_primal_inf": pr_max,
+            "backward_kkt_steps_per_s": kkt_all / (ms_total * 1e-3),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": roof_hbm, "roofline_fp64": roof_fp64, "kernels": kernels,
-            "lockstep": {"rounds_per_step": agg["rounds"] / seq_steps,
-                         "mean_active_fraction": agg["active_rounds"] / max(1, agg["rounds"]) / B},
+            "lockstep": {"rounds": agg["rounds"], "rounds_per_step": agg["rounds"] / K,
+                         "mean_active_fraction": agg["active_rounds"] / max(1, agg["rounds"]) / S},
             "cpu_baseline": cpu,
+            "configs": cfg_lines,
         }
+        line.update(parity)
         print(json.dumps(line))
-    for sv in solvers:
-        sv.close()
+    solver.close()
     if world > 1:
         dist.destroy_process_group()
 

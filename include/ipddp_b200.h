@@ -15,7 +15,8 @@
  *   - all matrices column-major, all reals FP64.
  *   - a "knot" is a timestep; N knots = N-1 running stages (nx,nu,nc of the model) + 1 terminal stage
  *     (nx, 0, 0), as in every reference experiment.  Per-instance horizons may be shorter than N.
- *   - one handle = one device + one stream; calls on a handle must be serialised by the caller.
+ *   - one handle = one device + one stream (its own, or the caller's: ipddp_set_stream); calls on a handle must be
+ *     serialised by the caller.
  */
 #ifndef IPDDP_B200_H
 #define IPDDP_B200_H
@@ -24,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IPDDP_ABI_VERSION 1
+#define IPDDP_ABI_VERSION 2
 #define IPDDP_TRACE_COLS 12
 #define IPDDP_FILTER_CAPACITY 64
 
@@ -129,14 +130,43 @@ int ipddp_set_inputs_device(ipddp_problem* h, const double* x1, const double* ub
  * all instances terminated.  warm_start != 0 skips initialize_trajectory! (src/solve.jl:6 semantics). */
 int ipddp_solve(ipddp_problem* h, int warm_start);
 
-/* Splits the problem's instances into S contiguous cohorts with their own active lists, counters and streams; cohorts
- * then progress through their rounds independently inside ipddp_solve / ipddp_solve_many (default S = 1: one lock-step
- * loop with per-kernel timing in ipddp_stats).  Results are identical for every S. */
-int ipddp_set_cohorts(ipddp_problem* h, int S);
+/* Streaming solve of a QUEUE of instances through the handle's B resident slots (B from ipddp_problem_create): every
+ * lock-step round works on the instances resident at that moment; when an instance terminates, its results are written to
+ * the output arrays at the instance's queue index and its slot is re-initialised with the next queued instance before the
+ * following round.  The rounds stay full until the queue runs dry and a straggler only holds its own slot, so one handle
+ * with memory for B instances sustains the throughput that otherwise needs several batches in flight (ipddp_solve_many).
+ * Per instance this is solve!(solver, x1, controls) (reference src/solve.jl:1-93) exactly as in ipddp_solve -- the slot
+ * an instance lands in never enters its computations.  Q may be smaller or (much) larger than B.
+ *   inputs  [Q] instances laid out like ipddp_set_inputs' arrays; HOST pointers, or device pointers if inputs_on_device.
+ *   outputs any pointer may be NULL; HOST arrays of Q (x [Q*N*nx], u [Q*(N-1)*nu], zeros beyond an instance's horizon),
+ *           or device arrays if outputs_on_device.  Host copies (H2D of the inputs, D2H of the results) are issued on the
+ *           handle's stream and are part of ipddp_stats.ms_total.
+ * Not kept in this mode: per-iteration traces and duals (they live in the slots; use ipddp_solve). */
+typedef struct ipddp_queue {
+  int Q;
+  const double* x1;        /* [Q*nx] */
+  const double* ubar;      /* [Q*(N-1)*nu] */
+  const double* params;    /* [Q*np], NULL if np == 0 */
+  const double* lower;     /* [Q*nu] */
+  const double* upper;     /* [Q*nu] */
+  const int* horizons;     /* [Q] knots per instance, NULL = all N */
+  int inputs_on_device;
+  int *status, *k, *j, *l;                                       /* SolverData, reference src/data/solver.jl:8-33 */
+  double *objective, *primal_inf, *dual_inf, *cs_inf, *mu, *reg_last, *step_size;
+  int *n_backward, *n_sweeps, *n_kkt, *n_rollouts;               /* work counters (ipddp_get_counters) */
+  double* x;               /* get_trajectory(solver): nominal states */
+  double* u;               /* nominal controls */
+  int outputs_on_device;
+} ipddp_queue;
+int ipddp_solve_queue(ipddp_problem* h, const ipddp_queue* queue);
 
-/* Throughput driver: n independent problems (same device) progress concurrently, each on its own stream; one host
- * thread polls completion events and immediately enqueues the next round of whichever problem is ready, so the
- * lock-step tail of one batch overlaps the bulk rounds of the others.  Handles that finish start another solve of
+/* Launch on the caller's CUDA stream (cudaStream_t as void*) instead of the handle's own; NULL restores the handle's
+ * stream.  Synchronises the previous stream first. */
+int ipddp_set_stream(ipddp_problem* h, void* cuda_stream);
+
+/* Several handles at once: n independent problems (same device, e.g. different models) progress concurrently, each on
+ * its own stream; one host thread polls completion events and immediately enqueues the next round of whichever problem
+ * is ready, so the lock-step tail of one batch overlaps the bulk rounds of the others.  Handles that finish start another solve of
  * their inputs until total_solves (>= n) solves are complete.  elapsed_ms: device time from the first enqueue to the
  * last completion (CUDA events); agg: counters summed over all solves (per-kernel times are not split here). */
 int ipddp_solve_many(ipddp_problem** problems, int n, int total_solves, int warm_start, double* elapsed_ms,

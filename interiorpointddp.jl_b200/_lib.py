@@ -19,7 +19,8 @@ TRACE_NAMES = ["k", "j", "objective", "primal_inf", "dual_inf", "cs_inf", "mu", 
 EXPORTS = [
     "ipddp_abi_version", "ipddp_last_error", "ipddp_default_options", "ipddp_num_models", "ipddp_model_name",
     "ipddp_model_dims", "ipddp_model_load", "ipddp_problem_create", "ipddp_problem_destroy", "ipddp_set_options",
-    "ipddp_set_tuning", "ipddp_layout", "ipddp_set_inputs", "ipddp_set_inputs_device", "ipddp_solve", "ipddp_solve_many", "ipddp_set_cohorts", "ipddp_initialize",
+    "ipddp_set_tuning", "ipddp_layout", "ipddp_set_inputs", "ipddp_set_inputs_device", "ipddp_solve", "ipddp_solve_many", "ipddp_solve_queue", "ipddp_set_stream",
+    "ipddp_initialize",
     "ipddp_eval_derivatives", "ipddp_backward_pass", "ipddp_check", "ipddp_forward_pass", "ipddp_get_results",
     "ipddp_get_trajectory", "ipddp_get_duals", "ipddp_get_counters", "ipddp_get_array", "ipddp_get_trace",
     "ipddp_get_stats", "ipddp_stream", "ipddp_measure_fp64_tflops", "ipddp_measure_hbm_gbs",
@@ -52,6 +53,19 @@ class Stats(C.Structure):
     ]
 
 
+class Queue(C.Structure):
+    """C layout of `ipddp_queue` (ipddp_solve_queue): Q queued instances, input and output arrays (host or device)."""
+    _fields_ = [
+        ("Q", C.c_int), ("x1", C.c_void_p), ("ubar", C.c_void_p), ("params", C.c_void_p), ("lower", C.c_void_p),
+        ("upper", C.c_void_p), ("horizons", C.c_void_p), ("inputs_on_device", C.c_int),
+        ("status", C.c_void_p), ("k", C.c_void_p), ("j", C.c_void_p), ("l", C.c_void_p),
+        ("objective", C.c_void_p), ("primal_inf", C.c_void_p), ("dual_inf", C.c_void_p), ("cs_inf", C.c_void_p),
+        ("mu", C.c_void_p), ("reg_last", C.c_void_p), ("step_size", C.c_void_p),
+        ("n_backward", C.c_void_p), ("n_sweeps", C.c_void_p), ("n_kkt", C.c_void_p), ("n_rollouts", C.c_void_p),
+        ("x", C.c_void_p), ("u", C.c_void_p), ("outputs_on_device", C.c_int),
+    ]
+
+
 class Lib:
     """Typed handle on one shared library exporting the ipddp_* C ABI."""
 
@@ -81,7 +95,8 @@ class Lib:
         L.ipddp_set_inputs.argtypes = [vp, dp, dp, dp, dp, dp, ip]
         L.ipddp_set_inputs_device.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.ipddp_solve.argtypes = [vp, C.c_int]
-        L.ipddp_set_cohorts.argtypes = [vp, C.c_int]
+        L.ipddp_solve_queue.argtypes = [vp, C.POINTER(Queue)]
+        L.ipddp_set_stream.argtypes = [vp, vp]
         L.ipddp_solve_many.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(Stats)]
         for f in ("ipddp_initialize", "ipddp_eval_derivatives", "ipddp_backward_pass", "ipddp_forward_pass"):
             getattr(L, f).argtypes = [vp]

@@ -97,14 +97,36 @@ class BatchSolver:
         """Execution tuning that never changes results (see ipddp_set_tuning)."""
         self.lib.check(self.lib.L.ipddp_set_tuning(self.h, key.encode(), int(value)), "ipddp_set_tuning")
 
-    def set_cohorts(self, S: int):
-        """Split the batch into S independently progressing slices (see ipddp_set_cohorts)."""
-        self.lib.check(self.lib.L.ipddp_set_cohorts(self.h, int(S)), "ipddp_set_cohorts")
+    def set_stream(self, cuda_stream: int):
+        """Launch on the caller's CUDA stream (raw cudaStream_t, e.g. torch.cuda.Stream().cuda_stream); 0 = own stream."""
+        self.lib.check(self.lib.L.ipddp_set_stream(self.h, C.c_void_p(int(cuda_stream) or None)), "ipddp_set_stream")
 
     # ------------------------------------------------------------------ solve and phases
     def solve(self, warm_start: bool = False) -> BatchResult:
         self.lib.check(self.lib.L.ipddp_solve(self.h, int(warm_start)), "ipddp_solve")
         return self.results()
+
+    def solve_queue(self, x1, ubar, params=None, lower=None, upper=None, horizons=None, want_traj=True):
+        """Streaming solve of Q >= 1 queued instances through this solver's B slots (ipddp_solve_queue); host arrays.
+        Returns (BatchResult over the Q instances, counters dict, x [Q,N,nx] or None, u [Q,N-1,nu] or None)."""
+        N = self.N
+        x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(-1, self.nx)
+        Q = x1.shape[0]
+        ubar = np.ascontiguousarray(ubar, dtype=np.float64).reshape(Q, (N - 1) * self.nu)
+        lower = np.full((Q, self.nu), -np.inf) if lower is None else lower
+        upper = np.full((Q, self.nu), np.inf) if upper is None else upper
+        lower = np.ascontiguousarray(np.broadcast_to(np.asarray(lower, dtype=np.float64), (Q, self.nu)))
+        upper = np.ascontiguousarray(np.broadcast_to(np.asarray(upper, dtype=np.float64), (Q, self.nu)))
+        p = np.ascontiguousarray(params, dtype=np.float64).reshape(Q, self.np) if self.np > 0 else None
+        hz = np.ascontiguousarray(horizons, dtype=np.int32).reshape(Q) if horizons is not None else None
+        ints = [np.zeros(Q, dtype=np.int32) for _ in range(4)]
+        dbl = [np.zeros(Q) for _ in range(7)]
+        cnt = [np.zeros(Q, dtype=np.int32) for _ in range(4)]
+        x = np.zeros((Q, N, self.nx)) if want_traj else None
+        u = np.zeros((Q, N - 1, self.nu)) if want_traj else None
+        q = make_queue(Q, x1, ubar, p, lower, upper, hz, ints + dbl + cnt, x, u)
+        self.lib.check(self.lib.L.ipddp_solve_queue(self.h, C.byref(q)), "ipddp_solve_queue")
+        return (BatchResult(*ints, *dbl), dict(n_backward=cnt[0], n_sweeps=cnt[1], n_kkt=cnt[2], n_rollouts=cnt[3]), x, u)
 
     def initialize(self):
         self.lib.check(self.lib.L.ipddp_initialize(self.h), "ipddp_initialize")
@@ -173,6 +195,30 @@ class BatchSolver:
         st = Stats()
         self.lib.check(self.lib.L.ipddp_get_stats(self.h, C.byref(st)), "ipddp_get_stats")
         return st
+
+
+def _addr(a):
+    if a is None:
+        return None
+    return int(a) if isinstance(a, (int, np.integer)) else a.ctypes.data
+
+
+def make_queue(Q, x1, ubar, params, lower, upper, horizons, scalars, x, u, inputs_on_device=False,
+               outputs_on_device=False) -> _lib.Queue:
+    """Fill an `ipddp_queue`: arrays are numpy arrays (host) or raw device addresses (ints); `scalars` is the list of the
+    15 per-instance output arrays in the struct's order (status k j l | objective primal_inf dual_inf cs_inf mu reg_last
+    step_size | n_backward n_sweeps n_kkt n_rollouts), entries may be None."""
+    q = _lib.Queue()
+    q.Q = int(Q)
+    q.x1, q.ubar, q.params, q.lower, q.upper, q.horizons = (_addr(a) for a in (x1, ubar, params, lower, upper, horizons))
+    q.inputs_on_device = int(inputs_on_device)
+    names = ["status", "k", "j", "l", "objective", "primal_inf", "dual_inf", "cs_inf", "mu", "reg_last", "step_size",
+             "n_backward", "n_sweeps", "n_kkt", "n_rollouts"]
+    for nm, a in zip(names, scalars):
+        setattr(q, nm, _addr(a))
+    q.x, q.u = _addr(x), _addr(u)
+    q.outputs_on_device = int(outputs_on_device)
+    return q
 
 
 def solve_many(solvers, total_solves=None, warm_start=False):

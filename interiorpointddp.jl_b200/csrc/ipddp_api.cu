@@ -5,9 +5,11 @@
 // instance ids rebuilt by the kernels with atomics; finished instances cost nothing):
 //   k_derivs   (instance x knot grid)        evaluate_derivatives!
 //   k_backward (one warp per instance)       backward_pass! + inertia_correction!
-//   k_check    (one thread per instance)     errors, convergence, barrier update -> forward list / next list
-//   k_forward  (one thread per instance)     forward_pass! + accept -> next list
-// then one 32-byte D2H of the list counters decides the next round's grid sizes.
+//   k_check    (one warp per instance)       errors, convergence, barrier update -> forward list / next list
+//   k_forward  (one warp per instance)       forward_pass! + accept -> next list
+// then one 32-byte D2H of the list counters decides the next round's grid sizes.  ipddp_solve runs a fixed batch to
+// completion; ipddp_solve_queue streams a queue of instances through the handle's slots (k_admit / k_retire between
+// rounds) so that the rounds stay full; ipddp_solve_many overlaps several handles.
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
@@ -65,7 +67,8 @@ __global__ void k_gather(DevView v, int use_cur, int off, int dim, int nst, doub
   const int t = (int)((idx / dim) % nst);
   const int b = (int)(idx / ((long long)dim * nst));
   const int set = use_cur ? 1 - v.nomsel[b] : v.nomsel[b];
-  out[idx] = (t < v.horizon[b]) ? v.rec(set, b, t)[off + i] : 0.0;
+  const int lim = off == 0 ? v.horizon[b] : v.horizon[b] - 1;   // x on every knot, everything else on the running stages
+  out[idx] = (t < lim) ? v.rec(set, b, t)[off + i] : 0.0;
 }
 
 __global__ void k_fp64_peak(double* out, int iters) {
@@ -126,46 +129,74 @@ __global__ void k_test_ldlt(int nmat, const double* A, const double* Bm, double*
   if (lane == 0) { info_out[m] = info; np_out[m] = np; }
 }
 
-}  // namespace
+// Queue mode: write the results of the instances whose slots are listed in done[0..n) to the queue's output arrays at
+// the instance's queue index: SolverData scalars, work counters and the nominal trajectory (get_trajectory,
+// reference src/solver.jl:46-48).  One CTA per slot.  Knots beyond the instance's horizon are written as zeros.
+__global__ void k_retire(DevView v, QueueView q, const int* done, int n) {
+  if ((int)blockIdx.x >= n) return;
+  const int b = done[blockIdx.x];
+  const size_t i = (size_t)v.inst_of[b];
+  const size_t Q = (size_t)q.Q;
+  if (threadIdx.x == 0) {
+    const int sf[QSI_COUNT] = {SI_STATUS, SI_K, SI_J, SI_L, SI_NBACK, SI_NSWEEP, SI_NKKT, SI_NROLL};
+    const int df[QSD_COUNT] = {SD_OBJECTIVE, SD_PRIMAL_INF, SD_DUAL_INF, SD_CS_INF, SD_MU, SD_REG_LAST, SD_STEP};
+    for (int f = 0; f < QSI_COUNT; ++f) q.si[(size_t)f * Q + i] = v.siv(sf[f], b);
+    for (int f = 0; f < QSD_COUNT; ++f) q.sd[(size_t)f * Q + i] = v.sdv(df[f], b);
+  }
+  const int Nb = v.horizon[b];
+  const double* r0 = v.rec(v.nomsel[b], b, 0);
+  if (q.x) {
+    double* xo = q.x + i * (size_t)v.N * v.nx;
+    for (int e = threadIdx.x; e < v.N * v.nx; e += blockDim.x) {
+      const int t = e / v.nx, c = e - t * v.nx;
+      xo[e] = t < Nb ? r0[(size_t)t * v.TR + c] : 0.0;
+    }
+  }
+  if (q.u) {
+    double* uo = q.u + i * (size_t)(v.N - 1) * v.nu;
+    for (int e = threadIdx.x; e < (v.N - 1) * v.nu; e += blockDim.x) {
+      const int t = e / v.nu, c = e - t * v.nu;
+      uo[e] = t < Nb - 1 ? r0[(size_t)t * v.TR + v.nx + c] : 0.0;
+    }
+  }
+}
 
-// A cohort is a contiguous slice of a problem's instances with its own active lists, counters and stream, so that
-// slices progress through their rounds independently (ipddp_set_cohorts, ipddp_solve_many).
-struct Cohort {
-  int b0 = 0, nb = 0;
-  int* d_list[2] = {nullptr, nullptr};
-  int* d_list_fwd = nullptr;
-  int* d_counters = nullptr;
-  int* h_counters = nullptr;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev = nullptr;
-  bool own_stream = false;
-  int cur = 0, n_active = 0, state = 0;
-};
+// horizons handed over in device memory cannot be validated on the host: count the out-of-range entries
+__global__ void k_count_bad_horizons(const int* hz, int n, int N, int* bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (hz[i] < 2 || hz[i] > N)) atomicAdd(bad, 1);
+}
+
+}  // namespace
 
 struct ipddp_problem {
   const ModelVTable* vt = nullptr;
   DevView v;
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream every launch of this handle goes to
+  cudaStream_t own_stream = nullptr;  // created with the handle; `stream` points here unless ipddp_set_stream replaced it
   std::vector<void*> allocs;
   int* d_compl = nullptr;
   double *d_p = nullptr, *d_lower = nullptr, *d_upper = nullptr, *d_x1 = nullptr, *d_ubar = nullptr;
   int* d_horizon = nullptr;
   int* d_list[2] = {nullptr, nullptr};
   int* d_list_fwd = nullptr;
+  int* d_done[2] = {nullptr, nullptr};   // queue mode: slots freed in the running / the previous round
   int* d_counters = nullptr;
-  int* h_counters = nullptr;
-  int* h_si = nullptr;            // pinned snapshot of the per-instance int scalars (ipddp_solve_many)
-  std::vector<Cohort> cohorts;    // >= 1 after ipddp_problem_create
-  int* d_ccount = nullptr;        // [S][CNT_COUNT]
-  int* h_ccount = nullptr;        // pinned
-  int cohorts_done = 0, hstate = 0;
-  int cur = 0, n_active = 0;
+  int* h_counters = nullptr;             // pinned
+  int* h_si = nullptr;                   // pinned snapshot of the per-instance int scalars
+  double* h_sd = nullptr;                // pinned snapshot of the per-instance double scalars
+  // grow-only scratch: device staging for gathers and for the queue's inputs / outputs, pinned host staging
+  void* d_stage = nullptr; size_t d_stage_cap = 0;
+  void* d_qin = nullptr;   size_t d_qin_cap = 0;
+  void* d_qout = nullptr;  size_t d_qout_cap = 0;
+  void* h_stage = nullptr; size_t h_stage_cap = 0;
+  int cur = 0, n_active = 0, hstate = 0;
   bool inputs_set = false;
   int spec_cap = 0;              // instances the speculative-forward record pool (DevView::spec_traj) was sized for
   int bw_spec_cap = 0;           // instances the speculative-backward output pool (DevView::spec_bw) was sized for
   size_t bw_pool_doubles() const { return (size_t)(v.N - 1) * (v.G + v.nu) + (size_t)v.N * v.nx; }
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   ipddp_stats st;
 
   template <class T> int alloc(T** p, size_t n) {
@@ -180,6 +211,23 @@ struct ipddp_problem {
 
 namespace {
 
+#define NEED_HANDLE(h) do { if (!(h)) return fail("null problem handle"); } while (0)
+
+int grow_device(void** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+  CK(cudaMalloc(p, need));
+  *cap = need;
+  return 0;
+}
+int grow_pinned(void** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) { cudaFreeHost(*p); *p = nullptr; *cap = 0; }
+  CK(cudaMallocHost(p, need));
+  *cap = need;
+  return 0;
+}
+
 int run_init(ipddp_problem* h, int warm) {
   CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
   h->cur = 0;
@@ -192,16 +240,27 @@ int run_init(ipddp_problem* h, int warm) {
   return 0;
 }
 
+// summed per-instance work counters of a snapshot of the SI block
+void add_counters(ipddp_stats& st, const int* si, int B) {
+  for (int b = 0; b < B; ++b) {
+    st.sum_backward += si[(size_t)SI_NBACK * B + b];
+    st.sum_sweeps += si[(size_t)SI_NSWEEP * B + b];
+    st.sum_kkt += si[(size_t)SI_NKKT * B + b];
+    st.sum_rollouts += si[(size_t)SI_NROLL * B + b];
+    st.sum_deriv_stages += (long long)si[(size_t)SI_NDERIV * B + b];
+    st.n_converged += (si[(size_t)SI_STATUS * B + b] == 0);
+  }
+}
+
 }  // namespace
 
 extern "C" {
-
-int ipddp_set_cohorts(ipddp_problem* h, int S);
 
 int ipddp_abi_version(void) { return IPDDP_ABI_VERSION; }
 const char* ipddp_last_error(void) { return g_err.c_str(); }
 
 void ipddp_default_options(ipddp_options* o) {  // reference src/options.jl:1-38
+  if (!o) return;
   o->quasi_newton = 0; o->optimality_tolerance = 1.0e-8; o->max_iterations = 1000; o->reset_cache = 1;
   o->verbose = 0; o->print_frequency = 10; o->mu_init = 1.0; o->ineq_dual_init = 1.0; o->kappa_1 = 0.01;
   o->kappa_2 = 0.01; o->reg_1 = 1e-4; o->reg_min = 1e-20; o->reg_max = 1e40; o->kappa_bar_w_p = 100.0;
@@ -214,19 +273,23 @@ void ipddp_default_options(ipddp_options* o) {  // reference src/options.jl:1-38
 int ipddp_num_models(void) { return (int)registry().size(); }
 const char* ipddp_model_name(int i) { return (i >= 0 && i < (int)registry().size()) ? registry()[i]->name : nullptr; }
 int ipddp_model_dims(const char* model, int* nx, int* nu, int* nc, int* np, int* tile_slots) {
-  const ModelVTable* m = find(model);
-  if (!m) return fail(std::string("unknown model ") + model);
+  const ModelVTable* m = model ? find(model) : nullptr;
+  if (!m) return fail(std::string("unknown model ") + (model ? model : "(null)"));
   if (nx) *nx = m->nx; if (nu) *nu = m->nu; if (nc) *nc = m->nc; if (np) *np = m->np;
   if (tile_slots) *tile_slots = m->d_nslot;
   return 0;
 }
 int ipddp_model_load(const char* path) {
+  if (!path) return fail("null plugin path");
   void* so = dlopen(path, RTLD_NOW | RTLD_LOCAL);
   if (!so) return fail(std::string("dlopen: ") + dlerror());
   typedef const ModelVTable* (*fn_t)();
   fn_t f = (fn_t)dlsym(so, "ipddp_plugin_vtable");
   if (!f) return fail("plugin does not export ipddp_plugin_vtable");
   const ModelVTable* vt = f();
+  if (!vt || !vt->name || !vt->init || !vt->derivs || !vt->backward || !vt->check || !vt->forward || !vt->admit ||
+      !vt->prepare)
+    return fail("plugin returned an incomplete model table");
   for (auto*& m : registry())
     if (strcmp(m->name, vt->name) == 0) { m = vt; return 0; }
   registry().push_back(vt);
@@ -235,12 +298,19 @@ int ipddp_model_load(const char* path) {
 
 int ipddp_problem_create(const char* model, int B, int N, const int* indices_compl, int n_compl,
                          const ipddp_options* opt, int device, int trace_capacity, ipddp_problem** out) {
-  const ModelVTable* vt = find(model);
-  if (!vt) return fail(std::string("unknown model ") + model);
+  if (!out) return fail("null output pointer");
+  const ModelVTable* vt = model ? find(model) : nullptr;
+  if (!vt) return fail(std::string("unknown model ") + (model ? model : "(null)"));
   if (B < 1 || N < 2) return fail("need B >= 1 and N >= 2");
   if (vt->nu + vt->nc > 64) return fail("KKT dimension nu+nc > 64 not supported");
   CK(cudaSetDevice(device));
-  if (vt->prepare() != 0) return fail("cudaFuncSetAttribute failed");
+  int optin = 0;
+  CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  // the merit kernels keep four per-knot arrays per warp in shared memory: the horizon is bounded by the opt-in limit
+  if ((long long)vt->smem_merit(N) > (long long)optin)
+    return fail("N too large: the per-knot scratch of k_forward / k_check (" + std::to_string(vt->smem_merit(N)) +
+                " B) exceeds the device's shared memory per block (" + std::to_string(optin) + " B)");
+  if (vt->prepare(optin) != 0) return fail("cudaFuncSetAttribute failed");
   ipddp_problem* h = new ipddp_problem();
   memset(&h->st, 0, sizeof(h->st));
   h->vt = vt;
@@ -254,6 +324,7 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   v.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
   v.fw_spec_max = g_fw_spec_max;
   v.bw_spec_max = g_bw_spec_max;
+  if ((long long)vt->smem_merit_spec(N) > (long long)optin) v.fw_spec_max = 0;   // long horizons: bulk line search only
   v.n_compl = (indices_compl && n_compl > 0) ? n_compl : 0;
   for (int q = 0; q < v.n_compl; ++q) {
     if (indices_compl[q] < 0 || indices_compl[q] >= vt->nc) { delete h; return fail("indices_compl out of range"); }
@@ -270,6 +341,7 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   rc |= h->alloc(&h->d_horizon, (size_t)B);
   rc |= h->alloc(&v.traj, (size_t)2 * B * N * v.TR);
   rc |= h->alloc(&v.nomsel, (size_t)B);
+  rc |= h->alloc(&v.inst_of, (size_t)B);
   rc |= h->alloc(&v.lam, (size_t)B * N * vt->nx);
   rc |= h->alloc(&v.tile, (size_t)B * (vt->d_nslot > 0 ? vt->d_nslot : 1) * N);
   rc |= h->alloc(&v.tileN, (size_t)B * (vt->dn_nslot > 0 ? vt->dn_nslot : 1));
@@ -288,6 +360,8 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   rc |= h->alloc(&h->d_list[0], (size_t)B);
   rc |= h->alloc(&h->d_list[1], (size_t)B);
   rc |= h->alloc(&h->d_list_fwd, (size_t)B);
+  rc |= h->alloc(&h->d_done[0], (size_t)B);
+  rc |= h->alloc(&h->d_done[1], (size_t)B);
   rc |= h->alloc(&h->d_counters, (size_t)CNT_COUNT);
   if (rc != 0) { ipddp_problem_destroy(h); return -1; }
   v.compl_idx = h->d_compl; v.p = h->d_p; v.lower = h->d_lower; v.upper = h->d_upper; v.x1 = h->d_x1;
@@ -298,58 +372,53 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
     CK(cudaMemset(v.si, 0, (size_t)SI_COUNT * B * sizeof(int)));
     CK(cudaMemset(v.sd, 0, (size_t)SD_COUNT * B * sizeof(double)));
     CK(cudaMemset(v.nomsel, 0, (size_t)B * sizeof(int)));
-    CK(cudaStreamCreate(&h->stream));
+    CK(cudaMemset(v.inst_of, 0, (size_t)B * sizeof(int)));
+    CK(cudaStreamCreate(&h->own_stream));
+    h->stream = h->own_stream;
     CK(cudaMallocHost((void**)&h->h_counters, CNT_COUNT * sizeof(int)));
-    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->ev[i]));
-    return ipddp_set_cohorts(h, 1);
+    CK(cudaMallocHost((void**)&h->h_si, (size_t)SI_COUNT * B * sizeof(int)));
+    CK(cudaMallocHost((void**)&h->h_sd, (size_t)SD_COUNT * B * sizeof(double)));
+    for (int i = 0; i < 9; ++i) CK(cudaEventCreate(&h->ev[i]));
+    return 0;
   };
   if (finish() != 0) { ipddp_problem_destroy(h); return -1; }
   *out = h;
   return 0;
 }
 
-int ipddp_set_cohorts(ipddp_problem* h, int S) {
-  if (S < 1) S = 1;
-  if (S > h->v.B) S = h->v.B;
-  CK(cudaSetDevice(h->device));
-  for (auto& c : h->cohorts) { if (c.ev) cudaEventDestroy(c.ev); if (c.own_stream && c.stream) cudaStreamDestroy(c.stream); }
-  h->cohorts.clear();
-  if (h->d_ccount) { cudaFree(h->d_ccount); h->d_ccount = nullptr; }
-  if (h->h_ccount) { cudaFreeHost(h->h_ccount); h->h_ccount = nullptr; }
-  CK(cudaMalloc((void**)&h->d_ccount, (size_t)S * CNT_COUNT * sizeof(int)));
-  CK(cudaMallocHost((void**)&h->h_ccount, (size_t)S * CNT_COUNT * sizeof(int)));
-  h->cohorts.resize(S);
-  const int B = h->v.B, base = B / S, rem = B % S;
-  int b0 = 0;
-  for (int c = 0; c < S; ++c) {
-    Cohort& co = h->cohorts[c];
-    co.b0 = b0; co.nb = base + (c < rem ? 1 : 0); b0 += co.nb;
-    co.d_list[0] = h->d_list[0] + co.b0; co.d_list[1] = h->d_list[1] + co.b0; co.d_list_fwd = h->d_list_fwd + co.b0;
-    co.d_counters = h->d_ccount + (size_t)c * CNT_COUNT; co.h_counters = h->h_ccount + (size_t)c * CNT_COUNT;
-    if (c == 0) { co.stream = h->stream; co.own_stream = false; }
-    else { CK(cudaStreamCreate(&co.stream)); co.own_stream = true; }
-    CK(cudaEventCreate(&co.ev));
-  }
-  return 0;
-}
-
 int ipddp_problem_destroy(ipddp_problem* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->d_stage) cudaFree(h->d_stage);
+  if (h->d_qin) cudaFree(h->d_qin);
+  if (h->d_qout) cudaFree(h->d_qout);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_si) cudaFreeHost(h->h_si);
-  for (auto& c : h->cohorts) { if (c.ev) cudaEventDestroy(c.ev); if (c.own_stream && c.stream) cudaStreamDestroy(c.stream); }
-  if (h->d_ccount) cudaFree(h->d_ccount);
-  if (h->h_ccount) cudaFreeHost(h->h_ccount);
-  for (int i = 0; i < 8; ++i)
+  if (h->h_sd) cudaFreeHost(h->h_sd);
+  for (int i = 0; i < 9; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return 0;
 }
 
-int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt) { h->v.opt = *opt; return 0; }
+int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt) {
+  NEED_HANDLE(h);
+  if (!opt) return fail("null options");
+  h->v.opt = *opt;
+  return 0;
+}
+
+int ipddp_set_stream(ipddp_problem* h, void* cuda_stream) {
+  NEED_HANDLE(h);
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
 
 int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
   const std::string k = key ? key : "";
@@ -357,6 +426,9 @@ int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
     if (value < 0) value = 0;
     if (!h) { g_fw_spec_max = value; return 0; }
     if (value > h->v.B) value = h->v.B;
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    if ((long long)h->vt->smem_merit_spec(h->v.N) > (long long)optin) value = 0;
     if (value > h->spec_cap) {   // grow the private trial-record pool
       CK(cudaSetDevice(h->device));
       double* q = nullptr;
@@ -392,6 +464,7 @@ int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
 
 int ipddp_layout(ipddp_problem* h, long long* traj_off, long long* gain_off, long long* traj_stride,
                  long long* gain_stride, long long* tile_stride) {
+  NEED_HANDLE(h);
   const DevView& v = h->v;
   for (int t = 0; t < v.N; ++t) {
     if (traj_off) traj_off[t] = (long long)t * v.TR;
@@ -405,30 +478,38 @@ int ipddp_layout(ipddp_problem* h, long long* traj_off, long long* gain_off, lon
 
 static int set_inputs_impl(ipddp_problem* h, const double* x1, const double* ubar, const double* params,
                            const double* lower, const double* upper, const int* horizons, cudaMemcpyKind kind) {
+  NEED_HANDLE(h);
   const DevView& v = h->v;
   CK(cudaSetDevice(h->device));
   if (!x1 || !ubar || !lower || !upper) return fail("x1, ubar, lower, upper are required");
-  CK(cudaMemcpyAsync(h->d_x1, x1, (size_t)v.B * v.nx * sizeof(double), kind, h->stream));
-  CK(cudaMemcpyAsync(h->d_ubar, ubar, (size_t)v.B * (v.N - 1) * v.nu * sizeof(double), kind, h->stream));
-  if (v.np > 0) {
-    if (!params) return fail("params required (np > 0)");
-    CK(cudaMemcpyAsync(h->d_p, params, (size_t)v.B * v.np * sizeof(double), kind, h->stream));
-  } else {
-    CK(cudaMemsetAsync(h->d_p, 0, (size_t)v.B * sizeof(double), h->stream));
-  }
-  CK(cudaMemcpyAsync(h->d_lower, lower, (size_t)v.B * v.nu * sizeof(double), kind, h->stream));
-  CK(cudaMemcpyAsync(h->d_upper, upper, (size_t)v.B * v.nu * sizeof(double), kind, h->stream));
+  if (v.np > 0 && !params) return fail("params required (np > 0)");
+  cudaStream_t s = h->stream;
+  if (horizons && kind == cudaMemcpyHostToDevice)
+    for (int b = 0; b < v.B; ++b)
+      if (horizons[b] < 2 || horizons[b] > v.N) return fail("horizon out of range [2, N]");
+  CK(cudaMemcpyAsync(h->d_x1, x1, (size_t)v.B * v.nx * sizeof(double), kind, s));
+  CK(cudaMemcpyAsync(h->d_ubar, ubar, (size_t)v.B * (v.N - 1) * v.nu * sizeof(double), kind, s));
+  if (v.np > 0) CK(cudaMemcpyAsync(h->d_p, params, (size_t)v.B * v.np * sizeof(double), kind, s));
+  else CK(cudaMemsetAsync(h->d_p, 0, (size_t)v.B * sizeof(double), s));
+  CK(cudaMemcpyAsync(h->d_lower, lower, (size_t)v.B * v.nu * sizeof(double), kind, s));
+  CK(cudaMemcpyAsync(h->d_upper, upper, (size_t)v.B * v.nu * sizeof(double), kind, s));
+  bool check_device_horizons = false;
   if (horizons) {
-    if (kind == cudaMemcpyHostToDevice)
-      for (int b = 0; b < v.B; ++b)
-        if (horizons[b] < 2 || horizons[b] > v.N) return fail("horizon out of range [2, N]");
-    CK(cudaMemcpyAsync(h->d_horizon, horizons, (size_t)v.B * sizeof(int), kind, h->stream));
+    CK(cudaMemcpyAsync(h->d_horizon, horizons, (size_t)v.B * sizeof(int), kind, s));
+    check_device_horizons = (kind != cudaMemcpyHostToDevice);
   } else {
-    std::vector<int> hz(v.B, v.N);
-    CK(cudaMemcpyAsync(h->d_horizon, hz.data(), (size_t)v.B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (grow_pinned(&h->h_stage, &h->h_stage_cap, (size_t)v.B * sizeof(int)) != 0) return -1;
+    int* hz = (int*)h->h_stage;
+    for (int b = 0; b < v.B; ++b) hz[b] = v.N;
+    CK(cudaMemcpyAsync(h->d_horizon, hz, (size_t)v.B * sizeof(int), cudaMemcpyHostToDevice, s));
   }
-  CK(cudaStreamSynchronize(h->stream));
+  if (check_device_horizons) {   // a horizon outside [2, N] would index out of bounds in every kernel
+    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
+    IPDDP_LAUNCH(k_count_bad_horizons, (v.B + 255) / 256, 256, 0, s, h->d_horizon, v.B, v.N, h->d_counters + CNT_BAD);
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  if (check_device_horizons && h->h_counters[CNT_BAD] != 0) { h->inputs_set = false; return fail("horizon out of range [2, N]"); }
   h->inputs_set = true;
   return 0;
 }
@@ -443,11 +524,13 @@ int ipddp_set_inputs_device(ipddp_problem* h, const double* x1, const double* ub
 }
 
 int ipddp_initialize(ipddp_problem* h) {
+  NEED_HANDLE(h);
   if (!h->inputs_set) return fail("ipddp_set_inputs not called");
   CK(cudaSetDevice(h->device));
   return run_init(h, 0);
 }
 int ipddp_eval_derivatives(ipddp_problem* h) {
+  NEED_HANDLE(h);
   CK(cudaSetDevice(h->device));
   h->vt->derivs(h->v, h->d_list[h->cur], h->n_active, h->stream);
   CK(cudaStreamSynchronize(h->stream));
@@ -455,6 +538,7 @@ int ipddp_eval_derivatives(ipddp_problem* h) {
   return 0;
 }
 int ipddp_backward_pass(ipddp_problem* h) {
+  NEED_HANDLE(h);
   CK(cudaSetDevice(h->device));
   h->vt->backward(h->v, h->d_list[h->cur], h->n_active, h->stream);
   CK(cudaStreamSynchronize(h->stream));
@@ -462,6 +546,7 @@ int ipddp_backward_pass(ipddp_problem* h) {
   return 0;
 }
 int ipddp_check(ipddp_problem* h, int* n_forward) {
+  NEED_HANDLE(h);
   CK(cudaSetDevice(h->device));
   CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
   h->vt->check(h->v, h->d_list[h->cur], h->n_active, h->d_list[1 - h->cur], h->d_list_fwd, h->d_counters, h->stream);
@@ -472,6 +557,7 @@ int ipddp_check(ipddp_problem* h, int* n_forward) {
   return 0;
 }
 int ipddp_forward_pass(ipddp_problem* h) {
+  NEED_HANDLE(h);
   CK(cudaSetDevice(h->device));
   h->vt->forward(h->v, h->d_list_fwd, h->n_active, h->d_list[1 - h->cur], h->d_counters, h->stream);
   CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -482,16 +568,41 @@ int ipddp_forward_pass(ipddp_problem* h) {
   return 0;
 }
 
+// One lock-step round on the handle's stream over the n instances of list[cur]: the four phase kernels, timed with CUDA
+// events (ev[0..4]) on the launching stream; ends with the asynchronous D2H copy of the list counters.
+static int enqueue_round(ipddp_problem* h, const DevView& v, int n, int cur, bool clear_counters) {
+  cudaStream_t s = h->stream;
+  cudaEvent_t* ev = h->ev;
+  CK(cudaEventRecord(ev[0], s));
+  h->vt->derivs(v, h->d_list[cur], n, s);
+  CK(cudaEventRecord(ev[1], s));
+  h->vt->backward(v, h->d_list[cur], n, s);
+  CK(cudaEventRecord(ev[2], s));
+  if (clear_counters) CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
+  h->vt->check(v, h->d_list[cur], n, h->d_list[1 - cur], h->d_list_fwd, h->d_counters, s);
+  CK(cudaEventRecord(ev[3], s));
+  h->vt->forward(v, h->d_list_fwd, n, h->d_list[1 - cur], h->d_counters, s);
+  CK(cudaEventRecord(ev[4], s));
+  CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+  h->st.launches += 4;
+  h->st.iterations += 1;
+  h->st.n_active_rounds += n;
+  return 0;
+}
+static int add_round_times(ipddp_problem* h) {
+  float ms = 0.f;
+  cudaEvent_t* ev = h->ev;
+  CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); h->st.ms_derivs += ms;
+  CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); h->st.ms_backward += ms;
+  CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); h->st.ms_check += ms;
+  CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); h->st.ms_forward += ms;
+  return 0;
+}
+
 int ipddp_solve(ipddp_problem* h, int warm_start) {
+  NEED_HANDLE(h);
   if (!h->inputs_set) return fail("ipddp_set_inputs not called");
   CK(cudaSetDevice(h->device));
-  if (h->cohorts.size() > 1) {   // cohorts progress independently: no per-kernel time split
-    ipddp_stats agg;
-    double ms = 0.0;
-    if (ipddp_solve_many(&h, 1, 1, warm_start, &ms, &agg) != 0) return -1;
-    h->st = agg;
-    return 0;
-  }
   const DevView& v = h->v;
   ipddp_stats& st = h->st;
   memset(&st, 0, sizeof(st));
@@ -506,109 +617,204 @@ int ipddp_solve(ipddp_problem* h, int warm_start) {
   CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
   st.ms_init = ms;
   while (h->n_active > 0) {
-    const int n = h->n_active;
-    const int cur = h->cur;
-    st.iterations += 1;
-    st.n_active_rounds += n;
-    CK(cudaEventRecord(ev[0], s));
-    h->vt->derivs(v, h->d_list[cur], n, s);
-    CK(cudaEventRecord(ev[1], s));
-    h->vt->backward(v, h->d_list[cur], n, s);
-    CK(cudaEventRecord(ev[2], s));
-    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
-    h->vt->check(v, h->d_list[cur], n, h->d_list[1 - cur], h->d_list_fwd, h->d_counters, s);
-    CK(cudaEventRecord(ev[3], s));
-    h->vt->forward(v, h->d_list_fwd, n, h->d_list[1 - cur], h->d_counters, s);
-    CK(cudaEventRecord(ev[4], s));
-    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (enqueue_round(h, v, h->n_active, h->cur, true) != 0) return -1;
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
-    st.launches += 4;
-    CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); st.ms_derivs += ms;
-    CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); st.ms_backward += ms;
-    CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); st.ms_check += ms;
-    CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); st.ms_forward += ms;
+    if (add_round_times(h) != 0) return -1;
     h->n_active = h->h_counters[CNT_NEXT];
-    h->cur = 1 - cur;
+    h->cur = 1 - h->cur;
   }
+  CK(cudaMemcpyAsync(h->h_si, v.si, (size_t)SI_COUNT * v.B * sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ev[7], s));
   CK(cudaEventSynchronize(ev[7]));
   CK(cudaEventElapsedTime(&ms, ev[6], ev[7]));
   st.ms_total = ms;
-  // summed counters
-  std::vector<int> si((size_t)SI_COUNT * v.B);
-  CK(cudaMemcpy(si.data(), v.si, si.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  for (int b = 0; b < v.B; ++b) {
-    st.sum_backward += si[(size_t)SI_NBACK * v.B + b];
-    st.sum_sweeps += si[(size_t)SI_NSWEEP * v.B + b];
-    st.sum_kkt += si[(size_t)SI_NKKT * v.B + b];
-    st.sum_rollouts += si[(size_t)SI_NROLL * v.B + b];
-    st.sum_deriv_stages += (long long)si[(size_t)SI_NDERIV * v.B + b];
-    st.n_converged += (si[(size_t)SI_STATUS * v.B + b] == 0);
-  }
+  add_counters(st, h->h_si, v.B);
   return 0;
 }
 
-// Several independent problems -- and the cohorts inside each problem -- progress concurrently, each cohort on its
-// own stream, driven by one host thread that polls completion events and immediately enqueues the next round of
-// whichever cohort became ready.  This hides the lock-step tail of one batch (a few straggler instances at <1 %
-// occupancy) behind the bulk rounds of the others, and the straggler warps of one kernel behind other cohorts' kernels.
+// Streaming solve: the Q queued instances flow through the handle's B resident slots.  Every lock-step round works
+// on the instances resident at that moment; a slot whose instance terminated in round r is written out (k_retire) and
+// re-initialised with the next queued instance (k_admit) before round r+1, so the rounds stay full until the queue is
+// empty and a straggler instance only ever holds its own slot.  Per instance this is exactly ipddp_solve's sequence
+// (reference src/solve.jl:40-90): which slot an instance lands in does not enter any of its computations.
+int ipddp_solve_queue(ipddp_problem* h, const ipddp_queue* io) {
+  NEED_HANDLE(h);
+  if (!io) return fail("null queue description");
+  const DevView& hv = h->v;
+  const int Q = io->Q, B = hv.B, N = hv.N;
+  if (Q < 1) return fail("need Q >= 1 queued instances");
+  if (!io->x1 || !io->ubar || !io->lower || !io->upper) return fail("x1, ubar, lower, upper are required");
+  if (hv.np > 0 && !io->params) return fail("params required (np > 0)");
+  if (hv.trace_cap > 0) return fail("per-iteration traces are kept per slot: use ipddp_solve for traced solves");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  ipddp_stats& st = h->st;
+  memset(&st, 0, sizeof(st));
+  const size_t np1 = hv.np > 0 ? hv.np : 1;
+  const size_t n_x1 = (size_t)Q * hv.nx, n_ub = (size_t)Q * (N - 1) * hv.nu, n_p = (size_t)Q * np1, n_b = (size_t)Q * hv.nu;
+  const size_t n_xo = (size_t)Q * N * hv.nx, n_uo = (size_t)Q * (N - 1) * hv.nu;
+  CK(cudaEventRecord(h->ev[6], s));
+  QueueView q;
+  memset(&q, 0, sizeof(q));
+  q.Q = Q;
+  // ---- inputs: device pointers are used in place, host pointers are staged (one H2D copy each, on the stream)
+  if (io->inputs_on_device) {
+    q.x1 = io->x1; q.ubar = io->ubar; q.p = io->params; q.lower = io->lower; q.upper = io->upper; q.horizon = io->horizons;
+  } else {
+    if (io->horizons)
+      for (int i = 0; i < Q; ++i)
+        if (io->horizons[i] < 2 || io->horizons[i] > N) return fail("horizon out of range [2, N]");
+    const size_t bytes = (n_x1 + n_ub + n_p + 2 * n_b) * sizeof(double) + (size_t)Q * sizeof(int);
+    if (grow_device(&h->d_qin, &h->d_qin_cap, bytes) != 0) return -1;
+    double* d = (double*)h->d_qin;
+    double* dx1 = d; double* dub = dx1 + n_x1; double* dp = dub + n_ub; double* dlo = dp + n_p; double* dup = dlo + n_b;
+    int* dhz = (int*)(dup + n_b);
+    CK(cudaMemcpyAsync(dx1, io->x1, n_x1 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dub, io->ubar, n_ub * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (hv.np > 0) CK(cudaMemcpyAsync(dp, io->params, n_p * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dlo, io->lower, n_b * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dup, io->upper, n_b * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (io->horizons) CK(cudaMemcpyAsync(dhz, io->horizons, (size_t)Q * sizeof(int), cudaMemcpyHostToDevice, s));
+    q.x1 = dx1; q.ubar = dub; q.p = dp; q.lower = dlo; q.upper = dup; q.horizon = io->horizons ? dhz : nullptr;
+  }
+  // ---- outputs: scalars always go through the handle's buffers (the statistics need them on the host); trajectories
+  //      are written in place when the caller's arrays live on the device
+  const bool want_x = io->x != nullptr, want_u = io->u != nullptr;
+  const bool dev_out = io->outputs_on_device != 0;
+  {
+    size_t bytes = (size_t)QSD_COUNT * Q * sizeof(double) + (size_t)QSI_COUNT * Q * sizeof(int);
+    if (!dev_out) bytes += ((want_x ? n_xo : 0) + (want_u ? n_uo : 0)) * sizeof(double);
+    if (grow_device(&h->d_qout, &h->d_qout_cap, bytes) != 0) return -1;
+    double* d = (double*)h->d_qout;
+    q.sd = d; d += (size_t)QSD_COUNT * Q;
+    if (!dev_out) {
+      if (want_x) { q.x = d; d += n_xo; }
+      if (want_u) { q.u = d; d += n_uo; }
+    } else {
+      q.x = io->x; q.u = io->u;
+    }
+    q.si = (int*)d;
+  }
+  // ---- the rounds
+  int next_inst = 0, retired = 0, n_active = 0, cur = 0, n_free = B, r = 0;
+  const bool runs = hv.opt.max_iterations > 0;   // otherwise every instance terminates inside k_admit (status 8)
+  while (retired < Q) {
+    DevView v = hv;
+    v.done_list = h->d_done[r & 1];
+    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
+    const int n_admit = n_free < Q - next_inst ? n_free : Q - next_inst;
+    if (n_admit > 0) {
+      h->vt->admit(v, q, r == 0 ? nullptr : h->d_done[(r - 1) & 1], n_admit, next_inst, h->d_list[cur] + n_active,
+                   h->d_counters, s);
+      st.launches += 1;
+      next_inst += n_admit;
+      if (runs) n_active += n_admit;
+    }
+    if (n_active > 0) {
+      if (enqueue_round(h, v, n_active, cur, false) != 0) { cudaStreamSynchronize(s); return -1; }
+    } else {
+      CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (h->h_counters[CNT_BAD] != 0) return fail("horizon out of range [2, N] in the queue");
+    if (n_active > 0 && add_round_times(h) != 0) return -1;
+    const int n_done = h->h_counters[CNT_DONE];
+    if (n_done > 0) {
+      IPDDP_LAUNCH(k_retire, n_done, 128, 0, s, v, q, h->d_done[r & 1], n_done);
+      st.launches += 1;
+    }
+    if (n_done == 0 && n_admit == 0 && n_active == 0) return fail("queue stalled");   // cannot happen
+    retired += n_done;
+    n_free = n_done;
+    n_active = n_active > 0 ? h->h_counters[CNT_NEXT] : 0;
+    cur = 1 - cur;
+    r += 1;
+  }
+  // ---- results to the caller
+  {
+    const size_t sd_b = (size_t)QSD_COUNT * Q * sizeof(double), si_b = (size_t)QSI_COUNT * Q * sizeof(int);
+    if (grow_pinned(&h->h_stage, &h->h_stage_cap, sd_b + si_b) != 0) return -1;
+    double* hsd = (double*)h->h_stage;
+    int* hsi = (int*)((char*)h->h_stage + sd_b);
+    CK(cudaMemcpyAsync(hsd, q.sd, sd_b, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hsi, q.si, si_b, cudaMemcpyDeviceToHost, s));
+    int* io_i[QSI_COUNT] = {io->status, io->k, io->j, io->l, io->n_backward, io->n_sweeps, io->n_kkt, io->n_rollouts};
+    double* io_d[QSD_COUNT] = {io->objective, io->primal_inf, io->dual_inf, io->cs_inf, io->mu, io->reg_last, io->step_size};
+    if (dev_out) {
+      for (int f = 0; f < QSI_COUNT; ++f)
+        if (io_i[f]) CK(cudaMemcpyAsync(io_i[f], q.si + (size_t)f * Q, (size_t)Q * sizeof(int), cudaMemcpyDeviceToDevice, s));
+      for (int f = 0; f < QSD_COUNT; ++f)
+        if (io_d[f]) CK(cudaMemcpyAsync(io_d[f], q.sd + (size_t)f * Q, (size_t)Q * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    } else {
+      if (want_x) CK(cudaMemcpyAsync(io->x, q.x, n_xo * sizeof(double), cudaMemcpyDeviceToHost, s));
+      if (want_u) CK(cudaMemcpyAsync(io->u, q.u, n_uo * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaEventRecord(h->ev[7], s));
+    CK(cudaEventSynchronize(h->ev[7]));
+    CK(cudaGetLastError());
+    if (!dev_out) {
+      for (int f = 0; f < QSI_COUNT; ++f)
+        if (io_i[f]) memcpy(io_i[f], hsi + (size_t)f * Q, (size_t)Q * sizeof(int));
+      for (int f = 0; f < QSD_COUNT; ++f)
+        if (io_d[f]) memcpy(io_d[f], hsd + (size_t)f * Q, (size_t)Q * sizeof(double));
+    }
+    for (int i = 0; i < Q; ++i) {
+      st.sum_backward += hsi[(size_t)QSI_NBACK * Q + i];
+      st.sum_sweeps += hsi[(size_t)QSI_NSWEEP * Q + i];
+      st.sum_kkt += hsi[(size_t)QSI_NKKT * Q + i];
+      st.sum_rollouts += hsi[(size_t)QSI_NROLL * Q + i];
+      st.n_converged += (hsi[(size_t)QSI_STATUS * Q + i] == 0);
+    }
+    st.sum_deriv_stages = st.sum_backward;   // one derivative evaluation per backward pass
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]));
+    st.ms_total = ms;
+  }
+  h->inputs_set = false;   // the slots hold whatever instances came last: ipddp_solve needs fresh inputs
+  return 0;
+}
+
+// Several independent problems progress concurrently, each on its own stream, driven by one host thread that polls
+// completion events and immediately enqueues the next round of whichever problem became ready.  This hides the
+// lock-step tail of one batch (a few straggler instances at <1 % occupancy) behind the bulk rounds of the others.
 // total_solves >= n: problems that finish early start another solve of their inputs until total_solves are done.
+// (One problem with more queued instances than slots: ipddp_solve_queue does the same with one handle's memory.)
 int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start, double* elapsed_ms,
                      ipddp_stats* agg) {
-  if (n < 1 || total_solves < n) return fail("need n >= 1 handles and total_solves >= n");
+  if (!hs || n < 1 || total_solves < n) return fail("need n >= 1 handles and total_solves >= n");
   for (int i = 0; i < n; ++i) {
+    if (!hs[i]) return fail("null problem handle");
     if (!hs[i]->inputs_set) return fail("ipddp_set_inputs not called on every handle");
     if (hs[i]->device != hs[0]->device) return fail("all handles must live on one device");
-    if (!hs[i]->h_si) CK(cudaMallocHost((void**)&hs[i]->h_si, (size_t)SI_COUNT * hs[i]->v.B * sizeof(int)));
   }
   CK(cudaSetDevice(hs[0]->device));
   ipddp_stats tot;
   memset(&tot, 0, sizeof(tot));
-  enum { IDLE = 0, INIT = 1, ROUND = 2, CDONE = 3 };           // cohort states
-  enum { H_RUNNING = 0, H_STATS = 1, H_FINISHED = 2, H_WAITING = 3 };   // handle states
+  enum { H_WAITING = 0, H_INIT = 1, H_ROUND = 2, H_STATS = 3, H_FINISHED = 4 };
   int started = 0, finished = 0;
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(hs[0]->ev[6], hs[0]->stream));
+  // any error below leaves other handles' streams busy: drain the device before handing the error to the caller
+  auto bail = [&]() -> int { cudaDeviceSynchronize(); return -1; };
   auto enqueue_init = [&](ipddp_problem* h) -> int {
     memset(&h->st, 0, sizeof(h->st));
-    h->cohorts_done = 0;
-    h->hstate = H_RUNNING;
-    for (auto& c : h->cohorts) {
-      CK(cudaMemsetAsync(c.d_counters, 0, CNT_COUNT * sizeof(int), c.stream));
-      c.cur = 0;
-      h->vt->init(h->v, warm_start, c.b0, c.nb, c.d_list[0], c.d_counters, c.stream);
-      h->st.launches += 1;
-      CK(cudaMemcpyAsync(c.h_counters, c.d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-      CK(cudaEventRecord(c.ev, c.stream));
-      c.state = INIT;
-    }
+    CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
+    h->cur = 0;
+    h->vt->init(h->v, warm_start, 0, h->v.B, h->d_list[0], h->d_counters, h->stream);
+    h->st.launches += 1;
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev[8], h->stream));
+    h->hstate = H_INIT;
     return 0;
   };
   // Speculative restarts spend 3 of 4 warps on sweeps that are usually discarded: worth it when the GPU is otherwise
-  // idle (the tail of a lone batch), not while another cohort still runs bulk rounds that could use those SM slots.
-  auto bulk_elsewhere = [&](const Cohort* self) -> bool {
+  // idle (the tail of a lone batch), not while another problem still runs bulk rounds that could use those SM slots.
+  auto bulk_elsewhere = [&](const ipddp_problem* self) -> bool {
     for (int i = 0; i < n; ++i)
-      for (auto& c : hs[i]->cohorts)
-        if (&c != self && (c.state == INIT || (c.state == ROUND && c.n_active > 4096))) return true;
+      if (hs[i] != self && (hs[i]->hstate == H_INIT || (hs[i]->hstate == H_ROUND && hs[i]->n_active > 4096))) return true;
     return false;
-  };
-  auto enqueue_round = [&](ipddp_problem* h, Cohort& c) -> int {
-    const int nn = c.n_active, cur = c.cur;
-    cudaStream_t s = c.stream;
-    h->st.iterations += 1;
-    h->st.n_active_rounds += nn;
-    DevView v = h->v;
-    if (nn > 32 && nn <= v.bw_spec_max && bulk_elsewhere(&c)) v.bw_spec_max = 32;
-    h->vt->derivs(v, c.d_list[cur], nn, s);
-    h->vt->backward(v, c.d_list[cur], nn, s);
-    CK(cudaMemsetAsync(c.d_counters, 0, CNT_COUNT * sizeof(int), s));
-    h->vt->check(v, c.d_list[cur], nn, c.d_list[1 - cur], c.d_list_fwd, c.d_counters, s);
-    h->vt->forward(v, c.d_list_fwd, nn, c.d_list[1 - cur], c.d_counters, s);
-    CK(cudaMemcpyAsync(c.h_counters, c.d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(c.ev, s));
-    h->st.launches += 4;
-    return 0;
   };
   // Admission: batches are started staggered, at most g_bulk_slots of them in their bulk rounds at a time.  Batches
   // that start together run their low-occupancy middle and tail rounds together, which is exactly what overlapping
@@ -616,13 +822,8 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
   for (int i = 0; i < n; ++i) hs[i]->hstate = H_WAITING;
   std::vector<int> runs(n, 0);
   auto in_bulk = [&](ipddp_problem* h) -> bool {
-    if (h->hstate != H_RUNNING) return false;
-    long long act = 0;
-    for (auto& c : h->cohorts) {
-      if (c.state == INIT) return true;
-      if (c.state == ROUND) act += c.n_active;
-    }
-    return act * 8 > h->v.B;
+    if (h->hstate == H_INIT) return true;
+    return h->hstate == H_ROUND && (long long)h->n_active * 8 > h->v.B;
   };
   auto admit = [&]() -> int {
     int bulk = 0;
@@ -641,52 +842,36 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
   };
   while (finished < total_solves) {
     bool progressed = false;
-    if (admit() != 0) return -1;
+    if (admit() != 0) return bail();
     for (int i = 0; i < n; ++i) {
       ipddp_problem* h = hs[i];
       if (h->hstate == H_FINISHED || h->hstate == H_WAITING) continue;
+      cudaError_t qe = cudaEventQuery(h->ev[8]);
+      if (qe == cudaErrorNotReady) continue;
+      if (qe != cudaSuccess) { fail(std::string("cudaEventQuery: ") + cudaGetErrorString(qe)); return bail(); }
+      progressed = true;
       if (h->hstate == H_STATS) {
-        cudaError_t q = cudaEventQuery(h->ev[5]);
-        if (q == cudaErrorNotReady) continue;
-        if (q != cudaSuccess) return fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
-        progressed = true;
-        const int B = h->v.B;
         tot.iterations += h->st.iterations;
         tot.launches += h->st.launches;
         tot.n_active_rounds += h->st.n_active_rounds;
-        for (int b = 0; b < B; ++b) {
-          tot.sum_backward += h->h_si[(size_t)SI_NBACK * B + b];
-          tot.sum_sweeps += h->h_si[(size_t)SI_NSWEEP * B + b];
-          tot.sum_kkt += h->h_si[(size_t)SI_NKKT * B + b];
-          tot.sum_rollouts += h->h_si[(size_t)SI_NROLL * B + b];
-          tot.sum_deriv_stages += h->h_si[(size_t)SI_NDERIV * B + b];
-          tot.n_converged += (h->h_si[(size_t)SI_STATUS * B + b] == 0);
-        }
+        add_counters(tot, h->h_si, h->v.B);
         finished++;
-        CK(cudaEventRecord(h->ev[7], h->stream));        // end of this handle's latest solve
+        if (cudaEventRecord(h->ev[7], h->stream) != cudaSuccess) { fail("cudaEventRecord"); return bail(); }
         h->hstate = (started < total_solves) ? H_WAITING : H_FINISHED;
         continue;
       }
-      for (auto& c : h->cohorts) {
-        if (c.state != INIT && c.state != ROUND) continue;
-        cudaError_t q = cudaEventQuery(c.ev);
-        if (q == cudaErrorNotReady) continue;
-        if (q != cudaSuccess) return fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
-        progressed = true;
-        if (c.state == ROUND) c.cur = 1 - c.cur;
-        c.n_active = c.h_counters[CNT_NEXT];
-        if (c.n_active > 0) {
-          if (enqueue_round(h, c) != 0) return -1;
-          c.state = ROUND;
-        } else {
-          c.state = CDONE;
-          h->cohorts_done++;
-        }
-      }
-      if (h->hstate == H_RUNNING && h->cohorts_done == (int)h->cohorts.size()) {
-        // every cohort stream is idle (their last events were observed): snapshot the per-instance scalars
-        CK(cudaMemcpyAsync(h->h_si, h->v.si, (size_t)SI_COUNT * h->v.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaEventRecord(h->ev[5], h->stream));
+      if (h->hstate == H_ROUND) h->cur = 1 - h->cur;
+      h->n_active = h->h_counters[CNT_NEXT];
+      if (h->n_active > 0) {
+        DevView v = h->v;
+        if (h->n_active > 32 && h->n_active <= v.bw_spec_max && bulk_elsewhere(h)) v.bw_spec_max = 32;
+        if (enqueue_round(h, v, h->n_active, h->cur, true) != 0) return bail();
+        if (cudaEventRecord(h->ev[8], h->stream) != cudaSuccess) { fail("cudaEventRecord"); return bail(); }
+        h->hstate = H_ROUND;
+      } else {
+        // the stream is idle (its last event was observed): snapshot the per-instance scalars
+        if (cudaMemcpyAsync(h->h_si, h->v.si, (size_t)SI_COUNT * h->v.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaEventRecord(h->ev[8], h->stream) != cudaSuccess) { fail("snapshot of the instance scalars failed"); return bail(); }
         h->hstate = H_STATS;
       }
     }
@@ -706,20 +891,22 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
   return 0;
 }
 
+// SolverData scalars: one D2H copy of each scalar block into pinned memory, then plain host copies
 int ipddp_get_results(ipddp_problem* h, int* status, int* k, int* j, int* l, double* objective,
                       double* primal_inf, double* dual_inf, double* cs_inf, double* mu, double* reg_last,
                       double* step_size) {
+  NEED_HANDLE(h);
   const DevView& v = h->v;
+  const size_t B = (size_t)v.B;
   CK(cudaSetDevice(h->device));
-  auto gi = [&](int f, int* dst) -> cudaError_t {
-    return dst ? cudaMemcpy(dst, v.si + (size_t)f * v.B, v.B * sizeof(int), cudaMemcpyDeviceToHost) : cudaSuccess;
-  };
-  auto gd = [&](int f, double* dst) -> cudaError_t {
-    return dst ? cudaMemcpy(dst, v.sd + (size_t)f * v.B, v.B * sizeof(double), cudaMemcpyDeviceToHost) : cudaSuccess;
-  };
-  CK(gi(SI_STATUS, status)); CK(gi(SI_K, k)); CK(gi(SI_J, j)); CK(gi(SI_L, l));
-  CK(gd(SD_OBJECTIVE, objective)); CK(gd(SD_PRIMAL_INF, primal_inf)); CK(gd(SD_DUAL_INF, dual_inf));
-  CK(gd(SD_CS_INF, cs_inf)); CK(gd(SD_MU, mu)); CK(gd(SD_REG_LAST, reg_last)); CK(gd(SD_STEP, step_size));
+  CK(cudaMemcpyAsync(h->h_si, v.si, (size_t)SI_COUNT * B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_sd, v.sd, (size_t)SD_COUNT * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  auto gi = [&](int f, int* dst) { if (dst) memcpy(dst, h->h_si + (size_t)f * B, B * sizeof(int)); };
+  auto gd = [&](int f, double* dst) { if (dst) memcpy(dst, h->h_sd + (size_t)f * B, B * sizeof(double)); };
+  gi(SI_STATUS, status); gi(SI_K, k); gi(SI_J, j); gi(SI_L, l);
+  gd(SD_OBJECTIVE, objective); gd(SD_PRIMAL_INF, primal_inf); gd(SD_DUAL_INF, dual_inf);
+  gd(SD_CS_INF, cs_inf); gd(SD_MU, mu); gd(SD_REG_LAST, reg_last); gd(SD_STEP, step_size);
   return 0;
 }
 
@@ -727,18 +914,17 @@ static int gather(ipddp_problem* h, int use_cur, int off, int dim, int nst, doub
   const DevView& v = h->v;
   const long long total = (long long)v.B * nst * dim;
   if (total == 0) return 0;
-  double* d = nullptr;
-  CK(cudaMalloc((void**)&d, total * sizeof(double)));
+  if (grow_device(&h->d_stage, &h->d_stage_cap, (size_t)total * sizeof(double)) != 0) return -1;
+  double* d = (double*)h->d_stage;
   const int th = 256;
   IPDDP_LAUNCH(k_gather, (unsigned)((total + th - 1) / th), th, 0, h->stream, v, use_cur, off, dim, nst, d);
-  cudaError_t e = cudaMemcpyAsync(out_host, d, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d);
-  if (e != cudaSuccess) return fail(std::string("gather: ") + cudaGetErrorString(e));
+  CK(cudaMemcpyAsync(out_host, d, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
 int ipddp_get_trajectory(ipddp_problem* h, double* x, double* u) {
+  NEED_HANDLE(h);
   const DevView& v = h->v;
   CK(cudaSetDevice(h->device));
   if (x && gather(h, 0, 0, v.nx, v.N, x) != 0) return -1;
@@ -747,6 +933,7 @@ int ipddp_get_trajectory(ipddp_problem* h, double* x, double* u) {
 }
 
 int ipddp_get_duals(ipddp_problem* h, double* phi, double* zl, double* zu, double* lam) {
+  NEED_HANDLE(h);
   const DevView& v = h->v;
   CK(cudaSetDevice(h->device));
   const int oPHI = v.nx + v.nu + v.nc + 2 * v.nu, oZL = oPHI + v.nc, oZU = oZL + v.nu;
@@ -758,16 +945,22 @@ int ipddp_get_duals(ipddp_problem* h, double* phi, double* zl, double* zu, doubl
 }
 
 int ipddp_get_counters(ipddp_problem* h, int* n_backward, int* n_sweeps, int* n_kkt, int* n_rollouts) {
+  NEED_HANDLE(h);
   const DevView& v = h->v;
+  const size_t B = (size_t)v.B;
   CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->h_si, v.si, (size_t)SI_COUNT * B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   int* dst[4] = {n_backward, n_sweeps, n_kkt, n_rollouts};
   const int f[4] = {SI_NBACK, SI_NSWEEP, SI_NKKT, SI_NROLL};
   for (int q = 0; q < 4; ++q)
-    if (dst[q]) CK(cudaMemcpy(dst[q], v.si + (size_t)f[q] * v.B, v.B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (dst[q]) memcpy(dst[q], h->h_si + (size_t)f[q] * B, B * sizeof(int));
   return 0;
 }
 
 long long ipddp_get_array(ipddp_problem* h, const char* name, double* out) {
+  NEED_HANDLE(h);
+  if (!name) return fail("null array name");
   const DevView& v = h->v;
   if (cudaSetDevice(h->device) != cudaSuccess) return fail("cudaSetDevice");
   std::string nm = name;
@@ -801,6 +994,7 @@ long long ipddp_get_array(ipddp_problem* h, const char* name, double* out) {
 }
 
 int ipddp_get_trace(ipddp_problem* h, int b, double* rows, int* nrows) {
+  NEED_HANDLE(h);
   const DevView& v = h->v;
   CK(cudaSetDevice(h->device));
   if (b < 0 || b >= v.B) return fail("instance out of range");
@@ -813,8 +1007,13 @@ int ipddp_get_trace(ipddp_problem* h, int b, double* rows, int* nrows) {
   return 0;
 }
 
-int ipddp_get_stats(ipddp_problem* h, ipddp_stats* st) { *st = h->st; return 0; }
-void* ipddp_stream(ipddp_problem* h) { return (void*)h->stream; }
+int ipddp_get_stats(ipddp_problem* h, ipddp_stats* st) {
+  NEED_HANDLE(h);
+  if (!st) return fail("null stats pointer");
+  *st = h->st;
+  return 0;
+}
+void* ipddp_stream(ipddp_problem* h) { return h ? (void*)h->stream : nullptr; }
 
 double ipddp_measure_fp64_tflops(int device) {
   if (cudaSetDevice(device) != cudaSuccess) return -1.0;

@@ -242,11 +242,11 @@ IPDDP_D void fw_finish(const DevView& v, const FwState<M>& s, int* list_next, in
   v.siv(SI_SWITCHING, b) = s.switching;
   v.siv(SI_ARMIJO, b) = s.armijo;
   v.siv(SI_STATUS, b) = status;
-  if (status != 0) { v.siv(SI_DONE, b) = 1; return; }
+  if (status != 0) { mark_done(v, b, counters); return; }
   v.nomsel[b] = s.cur;
   const int fn = s.fn;
   if (!s.armijo && !s.switching) {
-    if (fn >= IPDDP_FILTER_CAPACITY) { v.siv(SI_STATUS, b) = 9; v.siv(SI_DONE, b) = 1; return; }
+    if (fn >= IPDDP_FILTER_CAPACITY) { v.siv(SI_STATUS, b) = 9; mark_done(v, b, counters); return; }
     v.filter[(size_t)(0 * IPDDP_FILTER_CAPACITY + fn) * v.B + b] = (1.0 - v.opt.gamma_theta) * s.theta_prev;
     v.filter[(size_t)(1 * IPDDP_FILTER_CAPACITY + fn) * v.B + b] = s.L_prev - v.opt.gamma_L * s.theta_prev;
     v.siv(SI_FILTER_N, b) = fn + 1;
@@ -267,7 +267,7 @@ IPDDP_D void fw_finish(const DevView& v, const FwState<M>& s, int* list_next, in
       v.siv(SI_TRACE_N, b) = row + 1;
     }
   }
-  if (k >= v.opt.max_iterations) { v.siv(SI_STATUS, b) = 8; v.siv(SI_DONE, b) = 1; return; }
+  if (k >= v.opt.max_iterations) { v.siv(SI_STATUS, b) = 8; mark_done(v, b, counters); return; }
   list_next[atomicAdd(&counters[CNT_NEXT], 1)] = b;
 }
 

@@ -192,6 +192,12 @@ IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu
   *Lout = bl;
 }
 
+// the instance in slot b has terminated: flag it and, in queue mode, hand the slot to the retire / admit step
+IPDDP_D void mark_done(const DevView& v, int b, int* counters) {
+  v.siv(SI_DONE, b) = 1;
+  if (v.done_list) v.done_list[atomicAdd(&counters[CNT_DONE], 1)] = b;
+}
+
 IPDDP_D void reset_filter(const DevView& v, int b) {
   v.filter[(size_t)(0 * IPDDP_FILTER_CAPACITY + 0) * v.B + b] = v.sdv(SD_THETA_MAX, b);
   v.filter[(size_t)(1 * IPDDP_FILTER_CAPACITY + 0) * v.B + b] = -dm::inf();

@@ -15,12 +15,11 @@ namespace ipk {
 // distances, open-loop rollout, dual reset (src/solve.jl:182-198), J, c, theta, L, theta_max/min, filter.
 // warm != 0: keep the stored nominal primal trajectory (solve!(solver), src/solve.jl:6-17).
 // ---------------------------------------------------------------------------------------------
+// one instance (slot b) by one thread; x1p / ubarp: this instance's initial state and control guess.
+// returns true if the instance takes part in the first round (max_iterations > 0)
 template <class M>
-__global__ void k_init(DevView v, int warm, int b0, int nb, int* list_next, int* counters) {
+IPDDP_D bool init_instance(const DevView& v, int warm, int b, const double* x1p, const double* ubarp) {
   typedef Rec<M> R;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= nb) return;
-  const int b = b0 + tid;
   const int Nb = v.horizon[b];
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
   const double* lo = v.lower + (size_t)b * M::NU;
@@ -32,7 +31,7 @@ __global__ void k_init(DevView v, int warm, int b0, int nb, int* list_next, int*
   double x[M::NX], xn[M::NXN], u[M::NU > 0 ? M::NU : 1];
   if (!warm) {
 #pragma unroll
-    for (int i = 0; i < M::NX; ++i) x[i] = v.x1[(size_t)b * M::NX + i];
+    for (int i = 0; i < M::NX; ++i) x[i] = x1p[i];
   }
   for (int t = 0; t < Nb; ++t) {
     double* r = v.rec(set, b, t);
@@ -42,7 +41,7 @@ __global__ void k_init(DevView v, int warm, int b0, int nb, int* list_next, int*
     }
     if (t < Nb - 1) {
       if (!warm) {
-        const double* u0p = v.ubar + ((size_t)b * (v.N - 1) + t) * M::NU;
+        const double* u0p = ubarp + (size_t)t * M::NU;
 #pragma unroll
         for (int i = 0; i < M::NU; ++i) {
           const double u0 = u0p[i], l = lo[i], h = up[i];
@@ -106,12 +105,45 @@ __global__ void k_init(DevView v, int warm, int b0, int nb, int* list_next, int*
   v.sdv(SD_DUAL_NUM, b) = 0.0;
   for (int f = 0; f < SI_COUNT; ++f) v.siv(f, b) = 0;
   reset_filter(v, b);
-  if (v.opt.max_iterations > 0) {
+  if (v.opt.max_iterations > 0) return true;
+  v.siv(SI_STATUS, b) = 8;
+  return false;
+}
+
+template <class M>
+__global__ void k_init(DevView v, int warm, int b0, int nb, int* list_next, int* counters) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= nb) return;
+  const int b = b0 + tid;
+  if (init_instance<M>(v, warm, b, v.x1 + (size_t)b * M::NX, v.ubar + (size_t)b * (v.N - 1) * M::NU))
     list_next[atomicAdd(&counters[CNT_NEXT], 1)] = b;
-  } else {
-    v.siv(SI_STATUS, b) = 8;
-    v.siv(SI_DONE, b) = 1;
-  }
+  else
+    mark_done(v, b, counters);
+}
+
+// Queue mode: admit n queued instances inst0 .. inst0+n-1 into the slots slots[0..n) (NULL: slots 0..n-1): copy the
+// instance's parameters, bounds and horizon into the slot, initialise its trajectory from the queue's x1 / ubar
+// (k_init's work) and append the slot to the running round's list at list[j] (the host passes list + n_active).
+template <class M>
+__global__ void k_admit(DevView v, QueueView q, const int* slots, int n, int inst0, int* list, int* counters) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int b = slots ? slots[j] : j;
+  const int i = inst0 + j;
+  constexpr int NP1 = M::NP > 0 ? M::NP : 1;
+  double* ps = const_cast<double*>(v.p) + (size_t)b * NP1;
+  double* lo = const_cast<double*>(v.lower) + (size_t)b * M::NU;
+  double* up = const_cast<double*>(v.upper) + (size_t)b * M::NU;
+  for (int e = 0; e < M::NP; ++e) ps[e] = q.p[(size_t)i * NP1 + e];
+  for (int e = 0; e < M::NU; ++e) { lo[e] = q.lower[(size_t)i * M::NU + e]; up[e] = q.upper[(size_t)i * M::NU + e]; }
+  int hz = q.horizon ? q.horizon[i] : v.N;
+  if (hz < 2 || hz > v.N) { atomicAdd(&counters[CNT_BAD], 1); hz = hz < 2 ? 2 : v.N; }
+  const_cast<int*>(v.horizon)[b] = hz;
+  v.inst_of[b] = i;
+  if (init_instance<M>(v, 0, b, q.x1 + (size_t)i * M::NX, q.ubar + (size_t)i * (v.N - 1) * M::NU))
+    list[j] = b;
+  else
+    mark_done(v, b, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -174,7 +206,7 @@ __global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, const int* 
   const int b = list[i];
   if (v.siv(SI_STATUS, b) != 0) {  // backward pass failed (status 1): break
     __syncwarp();
-    if (lane == 0) v.siv(SI_DONE, b) = 1;
+    if (lane == 0) mark_done(v, b, counters);
     return;
   }
   double* us = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
@@ -266,7 +298,7 @@ __global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, const int* 
     v.sdv(SD_CS_INF, b) = cs_inf;
   }
   if (err_0 < tol) {  // converged
-    if (lane == 0) v.siv(SI_DONE, b) = 1;
+    if (lane == 0) mark_done(v, b, counters);
     return;
   }
   const int num_bounds = nb_stage * (Nb - 1);

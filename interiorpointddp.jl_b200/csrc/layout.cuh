@@ -31,7 +31,22 @@ enum SI {  // int scalars
   SI_STATUS = 0, SI_K, SI_J, SI_L, SI_FILTER_N, SI_SWITCHING, SI_ARMIJO, SI_DONE, SI_NBACK, SI_NSWEEP, SI_NKKT,
   SI_NROLL, SI_NDERIV, SI_TRACE_N, SI_COUNT
 };
-enum CNT { CNT_NEXT = 0, CNT_FWD = 1, CNT_DONE = 2, CNT_COUNT = 8 };
+enum CNT { CNT_NEXT = 0, CNT_FWD = 1, CNT_DONE = 2, CNT_BAD = 3, CNT_COUNT = 8 };
+
+// Queue mode (ipddp_solve_queue): Q queued instances flow through the B resident slots of a handle.  Inputs are read
+// from the queue arrays when an instance is admitted into a slot, results are written to the queue's output arrays
+// when it retires (k_admit / k_retire).
+enum QSI { QSI_STATUS = 0, QSI_K, QSI_J, QSI_L, QSI_NBACK, QSI_NSWEEP, QSI_NKKT, QSI_NROLL, QSI_COUNT };
+enum QSD { QSD_OBJECTIVE = 0, QSD_PRIMAL_INF, QSD_DUAL_INF, QSD_CS_INF, QSD_MU, QSD_REG_LAST, QSD_STEP, QSD_COUNT };
+struct QueueView {
+  int Q;
+  const double *x1, *ubar, *p, *lower, *upper;   // [Q][...] like the batch inputs
+  const int* horizon;                            // [Q] or NULL (= N)
+  int* si;                                       // [QSI_COUNT][Q]
+  double* sd;                                    // [QSD_COUNT][Q]
+  double* x;                                     // [Q][N][nx] or NULL
+  double* u;                                     // [Q][N-1][nu] or NULL
+};
 
 struct DevView {
   int B, N;
@@ -64,6 +79,8 @@ struct DevView {
   int bw_spec_max;           // rounds with at most this many active instances use k_backward_spec
   double* spec_bw;           // [bw_spec_max][BWS_WARPS-1][(N-1)(G+nu) + N nx] private gains / Qu / lambda of speculative sweeps
   double* spec_traj;         // [fw_spec_max][FWS_WARPS][N][TR] private trial records of the speculative line search
+  int* done_list;            // queue mode (ipddp_solve_queue): slots whose instance terminated in this round, else NULL
+  int* inst_of;              // queue mode: [B] queue index of the instance resident in slot b
   ipddp_options opt;
 
   IPDDP_D double* rec(int set, int b, int t) const { return traj + (((size_t)set * B + b) * N + t) * TR; }

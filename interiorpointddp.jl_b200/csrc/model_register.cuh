@@ -6,6 +6,10 @@
 #include "kernel_forward.cuh"
 #include "vtable.h"
 
+#ifndef IPDDP_BW_EXTRA_SMEM
+#define IPDDP_BW_EXTRA_SMEM 0   // A/B only: unused dynamic shared memory per warp of k_backward (lowers the resident warps per SM)
+#endif
+
 namespace ipk {
 
 template <class M> struct Launch {
@@ -13,6 +17,17 @@ template <class M> struct Launch {
     const int th = 64;
     IPDDP_LAUNCH((k_init<M>), (nb + th - 1) / th, th, 0, s, v, warm, b0, nb, list_next, counters);
   }
+  static void admit(const DevView& v, const QueueView& q, const int* slots, int n, int inst0, int* list, int* counters,
+                    cudaStream_t s) {
+    if (n <= 0) return;
+    const int th = 64;
+    IPDDP_LAUNCH((k_admit<M>), (n + th - 1) / th, th, 0, s, v, q, slots, n, inst0, list, counters);
+  }
+  static long long smem_merit(int N) {
+    const size_t a = FwLayout<M>::bytes(N), b = (size_t)CHK_WARPS * MeritLayout<M>::per_warp_doubles(N) * sizeof(double);
+    return (long long)(a > b ? a : b);
+  }
+  static long long smem_merit_spec(int N) { return (long long)FwLayout<M>::spec_bytes(N); }
   static void derivs(const DevView& v, const int* list, int n, cudaStream_t s) {
     if (n <= 0) return;
     const int th = 128;
@@ -26,7 +41,7 @@ template <class M> struct Launch {
       IPDDP_LAUNCH((k_backward_spec<M>), n, BWS_WARPS * 32, smem, s, v, list, n);
       return;
     }
-    IPDDP_LAUNCH((k_backward<M>), n, 32, BwLayout<M>::BYTES, s, v, list, n);
+    IPDDP_LAUNCH((k_backward<M>), n, 32, BwLayout<M>::BYTES + IPDDP_BW_EXTRA_SMEM, s, v, list, n);
   }
   static void check(const DevView& v, const int* list, int n, int* list_next, int* list_fwd, int* counters,
                     cudaStream_t s) {
@@ -46,10 +61,12 @@ template <class M> struct Launch {
     IPDDP_LAUNCH((k_forward<M>), (n_upper + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, FwLayout<M>::bytes(v.N), s, v,
                  list_fwd, list_next, counters);
   }
-  static int prepare() {
+  static int prepare(int max_optin_smem) {
+    (void)max_optin_smem;
 #ifndef IPDDP_SIMT_EMU
-    // long horizons: the per-knot scratch of the merit evaluation may exceed the 48 KB default
-    const int big = 160 * 1024;
+    // long horizons: the per-knot scratch of the merit evaluation may exceed the 48 KB default; ipddp_problem_create
+    // checks the actual need of a horizon against the same limit
+    const int big = max_optin_smem;
     if (cudaFuncSetAttribute(k_forward<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_forward_spec<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_check<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
@@ -71,7 +88,7 @@ template <class M> const ModelVTable* make_vtable() {
   static const ModelVTable vt = {
       M::NAME, M::NX, M::NU, M::NC, M::NP, M::D_NSLOT, M::DN_NSLOT, M::VF_NSLOT, BwLayout<M>::BYTES,
       &Launch<M>::init, &Launch<M>::derivs, &Launch<M>::backward, &Launch<M>::check, &Launch<M>::forward,
-      &Launch<M>::prepare};
+      &Launch<M>::admit, &Launch<M>::smem_merit, &Launch<M>::smem_merit_spec, &Launch<M>::prepare};
   return &vt;
 }
 

@@ -10,5 +10,10 @@ struct ModelVTable {
   void (*backward)(const DevView&, const int* list, int n, cudaStream_t);
   void (*check)(const DevView&, const int* list, int n, int* list_next, int* list_fwd, int* counters, cudaStream_t);
   void (*forward)(const DevView&, const int* list_fwd, int n_upper, int* list_next, int* counters, cudaStream_t);
-  int (*prepare)();
+  // queue mode: admit `n` queued instances inst0.. into the slots `slots` (NULL: 0..n-1), appending them at list[0..n)
+  void (*admit)(const DevView&, const QueueView&, const int* slots, int n, int inst0, int* list, int* counters, cudaStream_t);
+  // dynamic shared memory of the merit kernels (k_forward / k_check, and the speculative k_forward_spec) for N knots
+  long long (*smem_merit)(int N);
+  long long (*smem_merit_spec)(int N);
+  int (*prepare)(int max_optin_smem);
 };

@@ -4,7 +4,8 @@ ONE generator shared by the GPU harness, the tests and the CPU oracle baseline, 
 bit-identical inputs.  Instance i < 100 reproduces the reference's seed i+1 from the committed params
 tables (tests/golden/params/*.txt; Julia's Xoshiro draws cannot be regenerated without Julia); instance
 i >= 100 draws from the same ranges (reference experiments/ipddp2/*.jl) with a counter-based SplitMix64
-stream keyed by (seed, instance, draw).
+stream keyed by (seed, instance, draw).  The params tables ship with the package (data/params, byte-identical to
+tests/golden/params, which tests/test_oracle_golden.py checks); the results tables are test fixtures and stay under tests/.
 """
 from __future__ import annotations
 
@@ -17,9 +18,10 @@ import numpy as np
 
 from .codegen import workloads
 
-_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PARAMS_DIR = os.path.join(_REPO, "tests", "golden", "params")
-RESULTS_DIR = os.path.join(_REPO, "tests", "golden", "results")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+PARAMS_DIR = os.path.join(_HERE, "data", "params")
+RESULTS_DIR = os.path.join(_REPO, "tests", "golden", "results")   # known answers: only tests and tools read them
 
 _PARAM_FILE = {"cartpole": "cartpole_friction", "acrobot": "acrobot_contact", "concar": "concar",
                "concar_quad": "concar", "pushing": "pushing_1_obs"}
@@ -99,8 +101,9 @@ _PUSH_BLOCKS = np.array([
 
 
 def make_batch(workload: str, B: int, N: int = 101, seed: int = 0, use_reference_rows: bool = True,
-               random_x1: bool = True, vary_horizon: bool = False, first: int = 0) -> Batch:
-    """Instances first..first+B-1 of the workload's canonical stream."""
+               random_x1: bool = True, vary_horizon: bool = False, first: int = 0, horizon_span: int = 40) -> Batch:
+    """Instances first..first+B-1 of the workload's canonical stream.  vary_horizon: per-instance horizons drawn uniformly
+    from N - horizon_span .. N knots (reference rows keep N)."""
     md = workloads.get(workload)
     nx, nu = md.nx, md.nu
     inst = np.arange(first, first + B, dtype=np.int64)
@@ -158,7 +161,7 @@ def make_batch(workload: str, B: int, N: int = 101, seed: int = 0, use_reference
     ubar = np.tile(np.asarray(md.u_init, dtype=np.float64), (B, N - 1))
     horizons = np.full(B, N, dtype=np.int32)
     if vary_horizon:
-        lo_h = max(2, N - 40)
+        lo_h = max(2, N - horizon_span)
         hz = lo_h + np.minimum((uniform(seed, inst, 99) * (N - lo_h + 1)).astype(np.int64), N - lo_h)
         horizons = hz.astype(np.int32)
         if tab is not None:

@@ -9,7 +9,7 @@
 module InteriorPointDDPB200
 
 export Options, BatchProblem, Stats, solve!, solve_many!, get_trajectory, get_duals, get_trace, get_stats,
-       set_tuning!, set_cohorts!, load_model!
+       set_tuning!, load_model!
 
 const LIB = get(ENV, "IPDDP_B200_LIB", "libipddp_b200.so")
 
@@ -166,10 +166,6 @@ end
 set_tuning!(p::Union{BatchProblem,Nothing}, key::AbstractString, value::Integer) =
     check(ccall((:ipddp_set_tuning, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint),
                 p === nothing ? C_NULL : p.handle, key, value), "ipddp_set_tuning")
-
-"Independent slices of one batch, each with its own stream (`ipddp_set_cohorts`); results are identical for every S."
-set_cohorts!(p::BatchProblem, S::Integer) =
-    check(ccall((:ipddp_set_cohorts, LIB), Cint, (Ptr{Cvoid}, Cint), p.handle, S), "ipddp_set_cohorts")
 
 function get_stats(p::BatchProblem)
     st = Ref(Stats())

@@ -66,6 +66,8 @@ inline double sum_seq(const vec& v) {
   return s;
 }
 
+static int g_filter_capacity = 0;   // 0 = unbounded like the reference (oracle_set_filter_capacity)
+
 // one set of trajectories (reference src/data/problem.jl:1-24)
 struct Traj {
   std::vector<vec> x, u, c, il, iu, phi, zl, zu, lam;
@@ -628,8 +630,12 @@ struct Solver {
   void accept_step() {
     nom.x = cur.x; nom.u = cur.u; nom.c = cur.c; nom.il = cur.il; nom.iu = cur.iu;
     nom.phi = cur.phi; nom.zl = cur.zl; nom.zu = cur.zu; nom.lam = cur.lam;
-    if (!armijo_passed && !switching)
+    if (!armijo_passed && !switching) {
+      // the device keeps a fixed-capacity filter (IPDDP_FILTER_CAPACITY) and ends the instance with status 9 when an
+      // accepted step would overflow it; the reference's filter is an unbounded Vector.  Off (0) unless a test asks.
+      if (g_filter_capacity > 0 && (int)filter.size() >= g_filter_capacity) { status = 9; return; }
       filter.push_back({(1.0 - opt.gamma_theta) * theta_curr, L_curr - opt.gamma_L * theta_curr});
+    }
     L_curr = L_next;
     theta_curr = theta_next;
     k += 1;
@@ -666,6 +672,7 @@ struct Solver {
       forward_pass();
       if (status != 0) break;
       accept_step();
+      if (status != 0) break;
     }
     if (k == opt.max_iterations) status = 8;
     return status;
@@ -708,6 +715,8 @@ void fill_result(const Solver& s, OracleResult* r) {
 }  // namespace
 
 extern "C" {
+
+void oracle_set_filter_capacity(int cap) { g_filter_capacity = cap; }
 
 void oracle_default_options(OracleOptions* o) {  // reference src/options.jl:1-38
   o->quasi_newton = 0; o->optimality_tolerance = 1.0e-8; o->max_iterations = 1000; o->reset_cache = 1;

@@ -99,6 +99,11 @@ def lib():
     return _lib
 
 
+def set_filter_capacity(cap: int):
+    """0 (default) = unbounded filter like the reference; n > 0 = the device's fixed capacity (status 9 on overflow)."""
+    lib().oracle_set_filter_capacity(int(cap))
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 

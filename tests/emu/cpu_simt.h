@@ -155,6 +155,8 @@ typedef void* cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 227 * 1024; return 0; }
 struct cudaDeviceProp { int multiProcessorCount; };
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaGetLastError() { return 0; }

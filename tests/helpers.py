@@ -61,6 +61,32 @@ def full_solve_parity(lib, oracle, wl, B, N=101, maxit=1000, tol=1e-7, vary_hori
     return r, st
 
 
+def queue_parity(lib, oracle, wl, Q, B, N=101, maxit=1000, tol=1e-7, vary_horizon=False, first=0):
+    """ipddp_solve_queue (Q queued instances through B slots) vs the oracle: every SolverData scalar, the work counters
+    and the trajectories, bit for bit, per queue index."""
+    b = instances.make_batch(wl, Q, N, vary_horizon=vary_horizon, first=first)
+    opt = lib.default_options(optimality_tolerance=tol, max_iterations=maxit)
+    s = BatchSolver(wl, B, N, options=opt, lib=lib)
+    r, cnt, x, u = s.solve_queue(b.x1, b.ubar, b.p if s.np > 0 else None, b.lower, b.upper, b.horizons)
+    st = s.stats()
+    s.close()
+    oopt = oracle.default_options(optimality_tolerance=tol, max_iterations=maxit)
+    res, xo, uo = oracle.solve_batch(wl, N, b.p, b.lower, b.upper, b.x1, b.ubar, options=oopt, horizons=b.horizons,
+                                     want_traj=True)
+    for i in range(Q):
+        o = res[i]
+        got = (int(r.status[i]), int(r.k[i]), int(r.j[i]), int(r.l[i]))
+        assert got == (o.status, o.k, o.j, o.l), f"{wl} queue index {i}: (status,k,j,l) {got} vs oracle {(o.status, o.k, o.j, o.l)}"
+        for name in ("objective", "primal_inf", "dual_inf", "cs_inf", "mu", "reg_last", "step_size"):
+            assert_same_bits(getattr(r, name)[i], getattr(o, name), f"{wl} queue index {i} {name}")
+        assert (cnt["n_backward"][i], cnt["n_sweeps"][i], cnt["n_kkt"][i], cnt["n_rollouts"][i]) == \
+            (o.n_backward, o.n_sweeps, o.n_kkt, o.n_rollouts), f"{wl} queue index {i}: work counters"
+    assert_same_bits(x, xo, f"{wl} states")
+    assert_same_bits(u, uo, f"{wl} controls")
+    assert st.n_converged == sum(1 for o in res if o.status == 0) and st.sum_kkt == sum(o.n_kkt for o in res)
+    return r, st
+
+
 def _tile_map(wl):
     md = workloads.get(wl)
     bd = generate.trace(md)
@@ -296,6 +322,48 @@ def sampled_parity(lib, oracle, wl, B, N, sample=6, vary_horizon=False, first=0,
         assert_same_bits(x[i], xo[q], f"{wl} inst {i} states")
         assert_same_bits(u[i], uo[q], f"{wl} inst {i} controls")
     return r
+
+
+FORCED_STATUS_OPTIONS = {
+    "status1": dict(reg_max=1e-6),                                   # the first inertia failure asks for reg_1 = 1e-4 > reg_max
+    "status7": dict(gamma_theta=1.0, gamma_L=1e30, delta=1e300),      # no step can pass the sufficient-decrease tests
+    # mu never moves, every accepted step augments the filter, the fraction-to-boundary rule keeps the steps short:
+    "status9": dict(kappa_eps=0.0, delta=1e300, eta_L=1e300, tau_min=1e-3),
+}
+
+
+def forced_status_parity(lib, oracle, case, wl_B, N):
+    """The algorithm's failure exits, forced through the options and compared with the oracle bit for bit:
+    status 1 -- regularisation exceeds reg_max in the backward pass (reference src/backward_pass.jl:55-58,
+    src/inertia_correction.jl:264-275); status 7 -- the line search runs out of step sizes (src/forward_pass.jl:55);
+    status 9 -- the device's fixed-capacity filter overflows (the oracle emulates the capacity on request; the
+    reference's filter is an unbounded Vector)."""
+    wl, B = wl_B
+    kw = FORCED_STATUS_OPTIONS[case]
+    if case == "status9":
+        oracle.set_filter_capacity(64)
+    try:
+        b = instances.make_batch(wl, B, N, first=7)
+        s = BatchSolver(wl, B, N, options=lib.default_options(optimality_tolerance=1e-7, **kw), lib=lib)
+        s.set_batch(b)
+        r = s.solve()
+        x, u = s.trajectory()
+        cnt = s.counters()
+        s.close()
+        res, xo, uo = oracle.solve_batch(wl, N, b.p, b.lower, b.upper, b.x1, b.ubar,
+                                         options=oracle.default_options(optimality_tolerance=1e-7, **kw), want_traj=True)
+    finally:
+        oracle.set_filter_capacity(0)
+    want = {"status1": 1, "status7": 7, "status9": 9}[case]
+    assert (r.status == want).sum() >= (B if case != "status1" else 1), (case, r.status)
+    for i in range(B):
+        o = res[i]
+        assert (int(r.status[i]), int(r.k[i]), int(r.j[i]), int(r.l[i])) == (o.status, o.k, o.j, o.l), (case, i)
+        assert (cnt["n_sweeps"][i], cnt["n_kkt"][i], cnt["n_rollouts"][i]) == (o.n_sweeps, o.n_kkt, o.n_rollouts), (case, i)
+        for name in ("objective", "primal_inf", "dual_inf", "cs_inf", "mu", "reg_last", "step_size"):
+            assert_same_bits(getattr(r, name)[i], getattr(o, name), f"{case} inst {i} {name}")
+    assert_same_bits(x, xo, f"{case} states")
+    assert_same_bits(u, uo, f"{case} controls")
 
 
 def api_error_convention(lib):

@@ -46,7 +46,7 @@ def test_options_layout_and_defaults(product_lib):
                delta=1.0, s_theta=1.1, gamma_alpha=0.05, gamma_theta=1e-5, gamma_L=1e-5, kappa_Sigma=1e10)
     for k, v in ref.items():
         assert getattr(o, k) == v, k
-    assert product_lib.ipddp_abi_version() == 1
+    assert product_lib.ipddp_abi_version() == 2
 
 
 def test_model_registry(product_lib):

@@ -117,15 +117,12 @@ def test_emulated_solve_many(emu, oracle_mod):
         b = instances.make_batch("double_integrator" if q != 1 else "concar", B, N, first=10 * q)
         s = BatchSolver(b.workload, B, N, options=opt, lib=emu)
         s.set_batch(b)
-        if q == 1:
-            s.set_cohorts(2)     # instances of this problem progress in two independent slices
         solvers.append(s); batches.append(b)
     ms, st = solve_many(solvers, total_solves=5)
     got = [s.results() for s in solvers]
     cnt = [s.counters() for s in solvers]
     conv = 0
     for s, r in zip(solvers, got):
-        s.set_cohorts(1)
         r2 = s.solve()      # sequential re-solve of the same inputs
         assert np.array_equal(r.k, r2.k) and np.array_equal(r.status, r2.status)
         helpers.assert_same_bits(r.objective, r2.objective, "objective")
@@ -137,20 +134,25 @@ def test_emulated_solve_many(emu, oracle_mod):
         s.close()
 
 
-def test_emulated_cohorts_single_solve(emu, oracle_mod):
-    """ipddp_solve on a problem split into cohorts == the oracle (and therefore == the single-cohort solve)."""
+@pytest.mark.parametrize("wl,Q,B,N,maxit,vary", [("concar", 7, 3, 11, 60, True), ("double_integrator", 5, 8, 21, 1000, False),
+                                                  ("cartpole", 4, 2, 9, 12, False), ("concar", 3, 2, 11, 0, False)])
+def test_emulated_queue(emu, oracle_mod, wl, Q, B, N, maxit, vary):
+    """ipddp_solve_queue: Q queued instances streamed through B slots (more than, fewer than the slots; max_iterations
+    = 0 terminates inside the admission kernel) == the oracle instance by instance, bit for bit."""
+    helpers.queue_parity(emu, oracle_mod, wl, Q, B, N, maxit=maxit, vary_horizon=vary)
+
+
+@pytest.mark.parametrize("case,wl,B,N", [("status1", "cartpole", 2, 9), ("status7", "concar", 2, 11), ("status9", "concar", 2, 11)])
+def test_emulated_forced_statuses(emu, oracle_mod, case, wl, B, N):
+    helpers.forced_status_parity(emu, oracle_mod, case, (wl, B), N)
+
+
+def test_emulated_queue_bad_horizon(emu):
     from ipddp_b200 import instances
     from ipddp_b200.batch import BatchSolver
-    b = instances.make_batch("concar", 5, 11)
-    s = BatchSolver("concar", 5, 11, options=emu.default_options(optimality_tolerance=1e-7), lib=emu)
-    s.set_batch(b)
-    s.set_cohorts(3)
-    r = s.solve()
-    res, xo, uo = oracle_mod.solve_batch("concar", 11, b.p, b.lower, b.upper, b.x1, b.ubar,
-                                         options=oracle_mod.default_options(optimality_tolerance=1e-7), want_traj=True)
-    assert [int(k) for k in r.k] == [q.k for q in res] and [int(x) for x in r.status] == [q.status for q in res]
-    x, u = s.trajectory()
-    helpers.assert_same_bits(x, xo, "states")
-    st = s.stats()
-    assert st.sum_kkt == sum(q.n_kkt for q in res) and st.n_converged == sum(1 for q in res if q.status == 0)
+    b = instances.make_batch("double_integrator", 3, 11)
+    s = BatchSolver("double_integrator", 2, 11, lib=emu)
+    hz = b.horizons.copy(); hz[2] = 12
+    with pytest.raises(RuntimeError, match="horizon out of range"):
+        s.solve_queue(b.x1, b.ubar, None, b.lower, b.upper, hz)
     s.close()

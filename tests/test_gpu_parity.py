@@ -103,7 +103,7 @@ def test_baseline_configs_sampled_vs_oracle(gpu, oracle_mod, wl, B, N, vary):
     """BASELINE configs 3-5 at a scale where the bulk kernels run (thousands of instances, N = 201 for acrobot,
     per-instance horizons for pushing): a random sample of instances is re-solved on the oracle and must agree bit
     for bit, including the work counters."""
-    helpers.sampled_parity(gpu, oracle_mod, wl, B, N, sample=5, vary_horizon=vary, first=100, seed=7)
+    helpers.sampled_parity(gpu, oracle_mod, wl, B, N, sample=256 if wl != "pushing" else 96, vary_horizon=vary, first=100, seed=7)
 
 
 def test_golden_table_on_gpu(gpu):
@@ -159,7 +159,7 @@ def test_batch_consistency_and_permutation(gpu):
 def test_full_size_batch_properties(gpu, oracle_mod):
     """BASELINE config 2 at full size (16384 cartpole instances): every instance terminates with a valid
     status, >= 99 % converge with primal infeasibility below tolerance, the first 100 reproduce the small-batch
-    answers bit-for-bit, and a random sample of 8 instances matches the oracle exactly."""
+    answers bit-for-bit, and a random sample of 256 instances matches the oracle exactly."""
     from ipddp_b200 import instances
     from ipddp_b200.batch import BatchSolver
     B = 16384
@@ -181,12 +181,91 @@ def test_full_size_batch_properties(gpu, oracle_mod):
     s100.close()
     assert np.array_equal(r100.k, r.k[:100])
     helpers.assert_same_bits(r100.objective, r.objective[:100], "first 100 of the full batch")
-    idx = np.random.default_rng(1).choice(B, 8, replace=False)
+    idx = np.random.default_rng(1).choice(B, 256, replace=False)
     oopt = oracle_mod.default_options(optimality_tolerance=1e-7)
     res, _, _ = oracle_mod.solve_batch("cartpole", 101, b.p[idx], b.lower[idx], b.upper[idx], b.x1[idx], b.ubar[idx], options=oopt)
     for q, i in enumerate(idx):
         assert (int(r.status[i]), int(r.k[i])) == (res[q].status, res[q].k)
         helpers.assert_same_bits(r.objective[i], res[q].objective, f"instance {i} objective vs oracle")
+
+
+@pytest.mark.parametrize("wl,Q,B,N,vary", [("cartpole", 3000, 1024, 101, False), ("pushing", 700, 256, 141, True),
+                                             ("acrobot", 300, 512, 201, False)])
+def test_queue_streaming_parity(gpu, oracle_mod, wl, Q, B, N, vary):
+    """ipddp_solve_queue: Q instances streamed through B slots (admission / retirement between rounds) give, per queue
+    index, exactly what one resident batch of the same instances gives (every scalar, counter and trajectory), and a
+    sample agrees with the oracle bit for bit."""
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver
+    b = instances.make_batch(wl, Q, N, vary_horizon=vary, first=50)
+    opt = gpu.default_options(optimality_tolerance=1e-7)
+    s = BatchSolver(wl, B, N, options=opt, lib=gpu)
+    r, cnt, x, u = s.solve_queue(b.x1, b.ubar, b.p if s.np > 0 else None, b.lower, b.upper, b.horizons)
+    stq = s.stats()
+    s.close()
+    s2 = BatchSolver(wl, Q, N, options=opt, lib=gpu)
+    s2.set_batch(b)
+    r2 = s2.solve()
+    x2, u2 = s2.trajectory()
+    c2 = s2.counters()
+    s2.close()
+    for name in ("status", "k", "j", "l"):
+        assert np.array_equal(getattr(r, name), getattr(r2, name)), name
+    for name in ("objective", "primal_inf", "dual_inf", "cs_inf", "mu", "reg_last", "step_size"):
+        helpers.assert_same_bits(getattr(r, name), getattr(r2, name), name)
+    for key in ("n_backward", "n_sweeps", "n_kkt", "n_rollouts"):
+        assert np.array_equal(cnt[key], c2[key]), key
+    helpers.assert_same_bits(x, x2, "states")
+    helpers.assert_same_bits(u, u2, "controls")
+    assert stq.n_converged == int((r2.status == 0).sum()) and stq.sum_kkt == int(c2["n_kkt"].sum())
+    if Q > B:   # the rounds stay (nearly) full until the queue runs dry
+        assert stq.n_active_rounds / stq.iterations > 0.3 * B
+    idx = np.sort(np.random.default_rng(5).choice(Q, 24, replace=False))
+    oopt = oracle_mod.default_options(optimality_tolerance=1e-7)
+    res, xo, uo = oracle_mod.solve_batch(wl, N, b.p[idx], b.lower[idx], b.upper[idx], b.x1[idx], b.ubar[idx], options=oopt,
+                                         horizons=b.horizons[idx], want_traj=True)
+    for q, i in enumerate(idx):
+        assert (int(r.status[i]), int(r.k[i]), int(cnt["n_kkt"][i])) == (res[q].status, res[q].k, res[q].n_kkt)
+        helpers.assert_same_bits(r.objective[i], res[q].objective, f"queue index {i} objective vs oracle")
+        helpers.assert_same_bits(x[i], xo[q], f"queue index {i} states vs oracle")
+
+
+def test_queue_device_buffers(gpu):
+    """inputs and outputs of ipddp_solve_queue resident in device memory (torch tensors) == host buffers."""
+    import torch
+    from ipddp_b200 import instances
+    from ipddp_b200.batch import BatchSolver, make_queue
+    Q, B, N = 600, 256, 61
+    b = instances.make_batch("concar_quad", Q, N)
+    opt = gpu.default_options(optimality_tolerance=1e-7)
+    s = BatchSolver("concar_quad", B, N, options=opt, lib=gpu)
+    r, cnt, x, u = s.solve_queue(b.x1, b.ubar, b.p, b.lower, b.upper, b.horizons)
+    dev = torch.device("cuda", 0)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in dict(x1=b.x1, ubar=b.ubar, p=b.p, lower=b.lower, upper=b.upper).items()}
+    hz = torch.from_numpy(b.horizons.astype(np.int32)).to(dev)
+    oi = [torch.zeros(Q, dtype=torch.int32, device=dev) for _ in range(4)]
+    od = [torch.zeros(Q, dtype=torch.float64, device=dev) for _ in range(7)]
+    oc = [torch.zeros(Q, dtype=torch.int32, device=dev) for _ in range(4)]
+    xd = torch.zeros((Q, N, s.nx), dtype=torch.float64, device=dev)
+    ud = torch.zeros((Q, N - 1, s.nu), dtype=torch.float64, device=dev)
+    q = make_queue(Q, t["x1"].data_ptr(), t["ubar"].data_ptr(), t["p"].data_ptr(), t["lower"].data_ptr(), t["upper"].data_ptr(),
+                   hz.data_ptr(), [a.data_ptr() for a in oi + od + oc], xd.data_ptr(), ud.data_ptr(),
+                   inputs_on_device=True, outputs_on_device=True)
+    import ctypes as C
+    gpu.check(gpu.L.ipddp_solve_queue(s.h, C.byref(q)), "ipddp_solve_queue")
+    torch.cuda.synchronize()
+    s.close()
+    assert np.array_equal(oi[0].cpu().numpy(), r.status) and np.array_equal(oi[1].cpu().numpy(), r.k)
+    helpers.assert_same_bits(od[0].cpu().numpy(), r.objective, "objective")
+    assert np.array_equal(oc[2].cpu().numpy(), cnt["n_kkt"])
+    helpers.assert_same_bits(xd.cpu().numpy(), x, "states")
+    helpers.assert_same_bits(ud.cpu().numpy(), u, "controls")
+
+
+@pytest.mark.parametrize("case", ["status1", "status7", "status9"])
+def test_forced_failure_statuses(gpu, oracle_mod, case):
+    helpers.forced_status_parity(gpu, oracle_mod, case, {"status1": ("cartpole", 48), "status7": ("concar", 16),
+                                                         "status9": ("concar", 16)}[case], 101)
 
 
 def test_error_convention_gpu(gpu):

@@ -61,3 +61,16 @@ def test_pushing_statistical(oracle_mod):
     ks = np.array([r.k for r in res]); objs = np.array([r.objective for r in res])
     assert 0.4 * np.median(g["iterations"]) < np.median(ks) < 2.0 * np.median(g["iterations"])
     assert 0.5 * np.median(g["objective"]) < np.median(objs) < 2.0 * np.median(g["objective"])
+
+
+def test_package_params_tables_are_the_reference_fixtures():
+    """interiorpointddp.jl_b200/data/params (read by the instance generator at run time) == tests/golden/params
+    (byte-identical copies of the reference's experiments/ipddp2/params/*.txt)."""
+    import filecmp
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = os.path.join(here, "golden", "params")
+    names = sorted(os.listdir(gold))
+    assert names == sorted(os.listdir(instances.PARAMS_DIR)) and len(names) == 4
+    for n in names:
+        assert filecmp.cmp(os.path.join(gold, n), os.path.join(instances.PARAMS_DIR, n), shallow=False), n

@@ -17,10 +17,14 @@ CANDIDATES = [
     ("c_udiv", ["-DIPDDP_GAINS_UDIV=1"]),
     ("c_nnz1_nanmax", ["-DIPDDP_NNZ1=1", "-DIPDDP_NAN_BY_MAX=1"]),
     ("c_all", ["-DIPDDP_TIGHT_FAST=1", "-DIPDDP_NNZ1=1", "-DIPDDP_NAN_BY_MAX=1", "-DIPDDP_GAINS_UDIV=1"]),
+    # occupancy curve: unused dynamic shared memory lowers the resident warps per SM of k_backward (21 -> 16 / 12 / 8)
+    ("c_occ16", ["-DIPDDP_BW_EXTRA_SMEM=3700"]),
+    ("c_occ12", ["-DIPDDP_BW_EXTRA_SMEM=8500"]),
+    ("c_occ8", ["-DIPDDP_BW_EXTRA_SMEM=18300"]),
 ]
 
 if __name__ == "__main__":
-    with cf.ThreadPoolExecutor(3) as ex:
+    with cf.ThreadPoolExecutor(4) as ex:
         for lib in ex.map(lambda a: b.build_variant(*a), CANDIDATES):
             print(lib)
     names = " ".join(n for n, _ in CANDIDATES)
