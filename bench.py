@@ -176,7 +176,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="instances per GPU and step")
-    ap.add_argument("--slots", type=int, default=0, help="resident instance slots of the handle (0 = --batch)")
+    ap.add_argument("--slots", type=int, default=0,
+                    help="resident instance slots of the handle (0 = 4 x --batch, capped by the queue length: fewer, fuller rounds)")
     ap.add_argument("--workload", default="cartpole")
     ap.add_argument("--knots", type=int, default=101)
     ap.add_argument("--tol", type=float, default=1e-7)
@@ -212,7 +213,7 @@ def main():
     lib = _lib.load()
     nx, nu, nc, npar, slots = lib.model_dims(args.workload)
     B, N, K = args.batch, args.knots, args.steps
-    S = args.slots if args.slots > 0 else B
+    S = args.slots if args.slots > 0 else min(4 * B, max(B, K * B))
     opt = lib.default_options(optimality_tolerance=args.tol)
     peaks = {}
     try:

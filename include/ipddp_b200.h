@@ -107,6 +107,8 @@ int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt);
  * one CTA per instance that tries 8 step sizes of the backtracking sequence at once (0 = never);
  * "bw_spec_max" -- rounds with at most this many active instances run the backward pass with one CTA per instance
  * that tries 4 values of the regularisation schedule at once (0 = never);
+ * "list_sort" -- 1 (default): the active lists are bucketed by expected work, heaviest instances first, so that a launch
+ * does not end with its longest-running warps; 0: arrival order;
  * "bulk_slots" (global) -- ipddp_solve_many admits at most this many batches into their bulk rounds at the same time
  * (default 3), so that the low-occupancy tail of one batch overlaps the bulk rounds of the next. */
 int ipddp_set_tuning(ipddp_problem* h, const char* key, int value);

@@ -12,6 +12,7 @@
 // rounds) so that the rounds stay full; ipddp_solve_many overlaps several handles.
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -39,6 +40,7 @@ thread_local std::string g_err;
 int g_fw_spec_max = 148;   // default for new problems: speculative line search when <= one CTA per SM is active
 int g_bw_spec_max = 592;   // speculative restarts when <= 4 CTAs (16 warps) per SM are active
 int g_bulk_slots = 3;      // ipddp_solve_many: batches admitted into their bulk rounds at the same time
+int g_list_sort = 1;       // active lists bucketed by expected work, heaviest first (0 = arrival order, for A/B runs)
 int fail(const std::string& m) { g_err = m; return -1; }
 #define CK(call)                                                                                    \
   do {                                                                                              \
@@ -192,6 +194,18 @@ struct ipddp_problem {
   void* d_qout = nullptr;  size_t d_qout_cap = 0;
   void* h_stage = nullptr; size_t h_stage_cap = 0;
   int cur = 0, n_active = 0, hstate = 0;
+  int nb[LIST_BUCKETS] = {0, 0, 0, 0};    // bucket sizes of d_list[cur] (their sum is n_active)
+  ListView view(int which) const {
+    ListView l;
+    l.base = d_list[which]; l.stride = v.B;
+    for (int k = 0; k < LIST_BUCKETS; ++k) l.n[k] = nb[k];
+    return l;
+  }
+  // the bucket sizes of the next round's list as the kernels left them in the (host copy of the) counters
+  void take_next_counts() {
+    n_active = 0;
+    for (int k = 0; k < LIST_BUCKETS; ++k) { nb[k] = h_counters[CNT_NEXT + k]; n_active += nb[k]; }
+  }
   bool inputs_set = false;
   int spec_cap = 0;              // instances the speculative-forward record pool (DevView::spec_traj) was sized for
   int bw_spec_cap = 0;           // instances the speculative-backward output pool (DevView::spec_bw) was sized for
@@ -236,7 +250,7 @@ int run_init(ipddp_problem* h, int warm) {
   CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  h->n_active = h->h_counters[CNT_NEXT];
+  h->take_next_counts();
   return 0;
 }
 
@@ -318,12 +332,13 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   DevView& v = h->v;
   memset(&v, 0, sizeof(v));
   v.B = B; v.N = N; v.nx = vt->nx; v.nu = vt->nu; v.nc = vt->nc; v.np = vt->np;
-  v.TR = vt->nx + 5 * vt->nu + 2 * vt->nc;
-  v.G = (vt->nu + vt->nc + 2 * vt->nu) * (vt->nx + 1);
+  v.TR = (vt->nx + 5 * vt->nu + 2 * vt->nc + 1) & ~1;                  // strides padded to an even number of doubles
+  v.G = ((vt->nu + vt->nc + 2 * vt->nu) * (vt->nx + 1) + 1) & ~1;
   if (opt) v.opt = *opt; else ipddp_default_options(&v.opt);
   v.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
   v.fw_spec_max = g_fw_spec_max;
   v.bw_spec_max = g_bw_spec_max;
+  v.list_sort = g_list_sort;
   if ((long long)vt->smem_merit_spec(N) > (long long)optin) v.fw_spec_max = 0;   // long horizons: bulk line search only
   v.n_compl = (indices_compl && n_compl > 0) ? n_compl : 0;
   for (int q = 0; q < v.n_compl; ++q) {
@@ -357,9 +372,9 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   if (v.bw_spec_max > B) v.bw_spec_max = B;
   rc |= h->alloc(&v.spec_bw, (size_t)(v.bw_spec_max > 0 ? v.bw_spec_max : 0) * (ipk::BWS_WARPS - 1) * h->bw_pool_doubles());
   h->bw_spec_cap = v.bw_spec_max;
-  rc |= h->alloc(&h->d_list[0], (size_t)B);
-  rc |= h->alloc(&h->d_list[1], (size_t)B);
-  rc |= h->alloc(&h->d_list_fwd, (size_t)B);
+  rc |= h->alloc(&h->d_list[0], (size_t)LIST_BUCKETS * B);
+  rc |= h->alloc(&h->d_list[1], (size_t)LIST_BUCKETS * B);
+  rc |= h->alloc(&h->d_list_fwd, (size_t)LIST_BUCKETS * B);
   rc |= h->alloc(&h->d_done[0], (size_t)B);
   rc |= h->alloc(&h->d_done[1], (size_t)B);
   rc |= h->alloc(&h->d_counters, (size_t)CNT_COUNT);
@@ -438,6 +453,10 @@ int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
       h->spec_cap = value;
     }
     h->v.fw_spec_max = value;
+    return 0;
+  }
+  if (k == "list_sort") {
+    if (h) h->v.list_sort = value != 0; else g_list_sort = value != 0;
     return 0;
   }
   if (k == "bulk_slots") {
@@ -532,7 +551,7 @@ int ipddp_initialize(ipddp_problem* h) {
 int ipddp_eval_derivatives(ipddp_problem* h) {
   NEED_HANDLE(h);
   CK(cudaSetDevice(h->device));
-  h->vt->derivs(h->v, h->d_list[h->cur], h->n_active, h->stream);
+  h->vt->derivs(h->v, h->view(h->cur), h->stream);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   return 0;
@@ -540,7 +559,7 @@ int ipddp_eval_derivatives(ipddp_problem* h) {
 int ipddp_backward_pass(ipddp_problem* h) {
   NEED_HANDLE(h);
   CK(cudaSetDevice(h->device));
-  h->vt->backward(h->v, h->d_list[h->cur], h->n_active, h->stream);
+  h->vt->backward(h->v, h->view(h->cur), h->stream);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   return 0;
@@ -549,11 +568,14 @@ int ipddp_check(ipddp_problem* h, int* n_forward) {
   NEED_HANDLE(h);
   CK(cudaSetDevice(h->device));
   CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), h->stream));
-  h->vt->check(h->v, h->d_list[h->cur], h->n_active, h->d_list[1 - h->cur], h->d_list_fwd, h->d_counters, h->stream);
+  h->vt->check(h->v, h->view(h->cur), h->d_list[1 - h->cur], h->d_list_fwd, h->d_counters, h->stream);
   CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  if (n_forward) *n_forward = h->h_counters[CNT_FWD];
+  if (n_forward) {
+    *n_forward = 0;
+    for (int k = 0; k < LIST_BUCKETS; ++k) *n_forward += h->h_counters[CNT_FWD + k];
+  }
   return 0;
 }
 int ipddp_forward_pass(ipddp_problem* h) {
@@ -563,23 +585,24 @@ int ipddp_forward_pass(ipddp_problem* h) {
   CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  h->n_active = h->h_counters[CNT_NEXT];
+  h->take_next_counts();
   h->cur = 1 - h->cur;
   return 0;
 }
 
 // One lock-step round on the handle's stream over the n instances of list[cur]: the four phase kernels, timed with CUDA
 // events (ev[0..4]) on the launching stream; ends with the asynchronous D2H copy of the list counters.
-static int enqueue_round(ipddp_problem* h, const DevView& v, int n, int cur, bool clear_counters) {
+static int enqueue_round(ipddp_problem* h, const DevView& v, const ListView& list, int cur, bool clear_counters) {
   cudaStream_t s = h->stream;
   cudaEvent_t* ev = h->ev;
+  const int n = list.total();
   CK(cudaEventRecord(ev[0], s));
-  h->vt->derivs(v, h->d_list[cur], n, s);
+  h->vt->derivs(v, list, s);
   CK(cudaEventRecord(ev[1], s));
-  h->vt->backward(v, h->d_list[cur], n, s);
+  h->vt->backward(v, list, s);
   CK(cudaEventRecord(ev[2], s));
   if (clear_counters) CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
-  h->vt->check(v, h->d_list[cur], n, h->d_list[1 - cur], h->d_list_fwd, h->d_counters, s);
+  h->vt->check(v, list, h->d_list[1 - cur], h->d_list_fwd, h->d_counters, s);
   CK(cudaEventRecord(ev[3], s));
   h->vt->forward(v, h->d_list_fwd, n, h->d_list[1 - cur], h->d_counters, s);
   CK(cudaEventRecord(ev[4], s));
@@ -617,11 +640,11 @@ int ipddp_solve(ipddp_problem* h, int warm_start) {
   CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
   st.ms_init = ms;
   while (h->n_active > 0) {
-    if (enqueue_round(h, v, h->n_active, h->cur, true) != 0) return -1;
+    if (enqueue_round(h, v, h->view(h->cur), h->cur, true) != 0) return -1;
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (add_round_times(h) != 0) return -1;
-    h->n_active = h->h_counters[CNT_NEXT];
+    h->take_next_counts();
     h->cur = 1 - h->cur;
   }
   CK(cudaMemcpyAsync(h->h_si, v.si, (size_t)SI_COUNT * v.B * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -698,28 +721,41 @@ int ipddp_solve_queue(ipddp_problem* h, const ipddp_queue* io) {
   }
   // ---- the rounds
   int next_inst = 0, retired = 0, n_active = 0, cur = 0, n_free = B, r = 0;
+  FILE* qlog = getenv("IPDDP_QUEUE_LOG") ? fopen(getenv("IPDDP_QUEUE_LOG"), "a") : nullptr;   // per-round series for profiling
+  for (int k = 0; k < LIST_BUCKETS; ++k) h->nb[k] = 0;
+  const int light = LIST_BUCKETS - 1;   // fresh instances join the bucket of the one-sweep instances
   const bool runs = hv.opt.max_iterations > 0;   // otherwise every instance terminates inside k_admit (status 8)
   while (retired < Q) {
     DevView v = hv;
     v.done_list = h->d_done[r & 1];
     CK(cudaMemsetAsync(h->d_counters, 0, CNT_COUNT * sizeof(int), s));
     const int n_admit = n_free < Q - next_inst ? n_free : Q - next_inst;
+    CK(cudaEventRecord(h->ev[5], s));     // ev[5] .. ev[0]: admission (k_admit) of this round, retirement of the previous one
     if (n_admit > 0) {
-      h->vt->admit(v, q, r == 0 ? nullptr : h->d_done[(r - 1) & 1], n_admit, next_inst, h->d_list[cur] + n_active,
-                   h->d_counters, s);
+      h->vt->admit(v, q, r == 0 ? nullptr : h->d_done[(r - 1) & 1], n_admit, next_inst,
+                   h->d_list[cur] + (size_t)light * B + h->nb[light], h->d_counters, s);
       st.launches += 1;
       next_inst += n_admit;
-      if (runs) n_active += n_admit;
+      if (runs) { n_active += n_admit; h->nb[light] += n_admit; }
     }
     if (n_active > 0) {
-      if (enqueue_round(h, v, n_active, cur, false) != 0) { cudaStreamSynchronize(s); return -1; }
+      if (enqueue_round(h, v, h->view(cur), cur, false) != 0) { cudaStreamSynchronize(s); return -1; }
     } else {
       CK(cudaMemcpyAsync(h->h_counters, h->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (h->h_counters[CNT_BAD] != 0) return fail("horizon out of range [2, N] in the queue");
-    if (n_active > 0 && add_round_times(h) != 0) return -1;
+    if (n_active > 0) {
+      const double b0 = st.ms_backward, f0 = st.ms_forward;
+      if (add_round_times(h) != 0) return -1;
+      float ms_a = 0.f;
+      CK(cudaEventElapsedTime(&ms_a, h->ev[5], h->ev[0]));
+      st.ms_init += ms_a;
+      if (qlog) fprintf(qlog, "{\"round\": %d, \"active\": %d, \"buckets\": [%d, %d, %d, %d], \"admitted\": %d, \"admit_ms\": %.3f, "
+                        "\"bw_ms\": %.3f, \"fw_ms\": %.3f, \"done\": %d}\n", r, n_active, h->nb[0], h->nb[1], h->nb[2], h->nb[3],
+                        n_admit, ms_a, st.ms_backward - b0, st.ms_forward - f0, h->h_counters[CNT_DONE]);
+    }
     const int n_done = h->h_counters[CNT_DONE];
     if (n_done > 0) {
       IPDDP_LAUNCH(k_retire, n_done, 128, 0, s, v, q, h->d_done[r & 1], n_done);
@@ -728,10 +764,11 @@ int ipddp_solve_queue(ipddp_problem* h, const ipddp_queue* io) {
     if (n_done == 0 && n_admit == 0 && n_active == 0) return fail("queue stalled");   // cannot happen
     retired += n_done;
     n_free = n_done;
-    n_active = n_active > 0 ? h->h_counters[CNT_NEXT] : 0;
+    if (n_active > 0) { h->take_next_counts(); n_active = h->n_active; }
     cur = 1 - cur;
     r += 1;
   }
+  if (qlog) fclose(qlog);
   // ---- results to the caller
   {
     const size_t sd_b = (size_t)QSD_COUNT * Q * sizeof(double), si_b = (size_t)QSI_COUNT * Q * sizeof(int);
@@ -861,11 +898,11 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
         continue;
       }
       if (h->hstate == H_ROUND) h->cur = 1 - h->cur;
-      h->n_active = h->h_counters[CNT_NEXT];
+      h->take_next_counts();
       if (h->n_active > 0) {
         DevView v = h->v;
         if (h->n_active > 32 && h->n_active <= v.bw_spec_max && bulk_elsewhere(h)) v.bw_spec_max = 32;
-        if (enqueue_round(h, v, h->n_active, h->cur, true) != 0) return bail();
+        if (enqueue_round(h, v, h->view(h->cur), h->cur, true) != 0) return bail();
         if (cudaEventRecord(h->ev[8], h->stream) != cudaSuccess) { fail("cudaEventRecord"); return bail(); }
         h->hstate = H_ROUND;
       } else {
@@ -980,7 +1017,16 @@ long long ipddp_get_array(ipddp_problem* h, const char* name, double* out) {
   const double* src = nullptr;
   long long n = 0;
   if (nm == "lam") { src = v.lam; n = (long long)v.B * v.N * v.nx; }
-  else if (nm == "gains") { src = v.gains; n = (long long)v.B * (v.N - 1) * v.G; }
+  else if (nm == "gains") {      // without the padding double of the device records
+    const long long G = (long long)(v.nu + v.nc + 2 * v.nu) * (v.nx + 1), rows = (long long)v.B * (v.N - 1);
+    if (out && rows > 0) {
+      std::vector<double> tmp((size_t)rows * v.G);
+      cudaError_t e = cudaMemcpy(tmp.data(), v.gains, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+      for (long long r = 0; r < rows; ++r) memcpy(out + r * G, tmp.data() + r * v.G, (size_t)G * sizeof(double));
+    }
+    return rows * G;
+  }
   else if (nm == "Qu") { src = v.Qu; n = (long long)v.B * (v.N - 1) * v.nu; }
   else if (nm == "tile") { src = v.tile; n = (long long)v.B * h->vt->d_nslot * v.N; }
   else if (nm == "tileN") { src = v.tileN; n = (long long)v.B * h->vt->dn_nslot; }

@@ -312,12 +312,8 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
     // ---- ineq gains to HBM                                            (:159-172)
     double* gi = g + K * NR;
     for (int e = lane; e < NU * NR; e += 32) {
-#if defined(IPDDP_GAINS_UDIV) && IPDDP_GAINS_UDIV   // experiment awaiting its A/B: the signed e / NU compiles to ~20 byte-permute instructions
-      const int j = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)NU + 1u));
+      const int j = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)NU + 1u));   // e / NU (the signed division compiles to ~20 instructions)
       const int i = e - j * NU;
-#else
-      const int i = e % NU, j = e / NU;
-#endif
       if (j == 0) {
         const double al = rhs[i];
         double cl = ra1[i] * mu;      // chi^L = mu / il, recomputed from the stored reciprocal (same operands, same bits)
@@ -416,12 +412,12 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
 }
 
 template <class M>
-__global__ void __launch_bounds__(32, IPDDP_BW_MINBLOCKS) k_backward(DevView v, const int* list, int n_list) {
+__global__ void __launch_bounds__(32, IPDDP_BW_MINBLOCKS) k_backward(DevView v, ListView list) {
   IPDDP_DYN_SMEM(double, sm);
   const int lane = threadIdx.x;
   const int inst = blockIdx.x;
-  if (inst >= n_list) return;
-  const int b = list[inst];
+  if (inst >= list.total()) return;
+  const int b = list.at(inst);
   const int Nb = v.horizon[b];
   const int set = v.nomsel[b];
   bw_setup<M>(sm, lane);
@@ -444,6 +440,7 @@ __global__ void __launch_bounds__(32, IPDDP_BW_MINBLOCKS) k_backward(DevView v, 
     v.siv(SI_NBACK, b) += 1;
     v.siv(SI_NSWEEP, b) += nsweep;
     v.siv(SI_NKKT, b) += nkkt;
+    v.siv(SI_LASTSW, b) = nsweep;
   }
 }
 
@@ -456,12 +453,12 @@ __global__ void __launch_bounds__(32, IPDDP_BW_MINBLOCKS) k_backward(DevView v, 
 constexpr int BWS_WARPS = 4;
 
 template <class M>
-__global__ void __launch_bounds__(BWS_WARPS * 32) k_backward_spec(DevView v, const int* list, int n_list) {
+__global__ void __launch_bounds__(BWS_WARPS * 32) k_backward_spec(DevView v, ListView list) {
   IPDDP_DYN_SMEM(double, sm_all);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inst = blockIdx.x;
-  if (inst >= n_list) return;
-  const int b = list[inst];
+  if (inst >= list.total()) return;
+  const int b = list.at(inst);
   const int Nb = v.horizon[b];
   const int set = v.nomsel[b];
   constexpr int WD = BwLayout<M>::BYTES / 8;
@@ -524,6 +521,7 @@ __global__ void __launch_bounds__(BWS_WARPS * 32) k_backward_spec(DevView v, con
     v.siv(SI_NBACK, b) += 1;
     v.siv(SI_NSWEEP, b) += nsweep;
     v.siv(SI_NKKT, b) += nkkt;
+    v.siv(SI_LASTSW, b) = nsweep;
   }
 }
 

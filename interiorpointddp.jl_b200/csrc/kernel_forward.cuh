@@ -26,23 +26,56 @@
 //                   ones.  The accepted candidate's records are copied into the instance's trial set.
 #pragma once
 #include "kernels_common.cuh"
+#include "tma.cuh"
+
+#ifndef IPDDP_FW_TMA
+#define IPDDP_FW_TMA 0            // 1: the rollout's per-knot gains + nominal records are staged in shared memory by TMA bulk copies
+#endif
 
 namespace ipk {
 
 constexpr int FW_WARPS = 4;
 constexpr int FWS_WARPS = 8;
+constexpr int FW_TMA_STAGES = 3;  // per-warp ring of staged knots (two knots in flight ahead of the one being consumed)
 #ifndef IPDDP_FW_MINBLOCKS
 #define IPDDP_FW_MINBLOCKS 3      // resident CTAs per SM the register allocation of k_forward is held to (168 registers; measured: 2 -> 65 ms, 3 -> 53 ms, 4 -> 77 ms per 12 bulk rounds)
 #endif
 
 template <class M> struct FwLayout : MeritLayout<M> {
-  static size_t bytes(int N) { return (size_t)FW_WARPS * MeritLayout<M>::per_warp_doubles(N) * sizeof(double); }
+  // TMA staging ring of one warp: FW_TMA_STAGES x (gains record | nominal record), then the stages' mbarriers
+  static constexpr int K_ = M::NU + M::NC;
+  static constexpr int GP = ((K_ + 2 * M::NU) * (M::NX + 1) + 1) & ~1;     // == DevView::G
+  static constexpr int STAGE = GP + Rec<M>::STRIDE;
+  static constexpr int TMA_DOUBLES = IPDDP_FW_TMA ? FW_TMA_STAGES * STAGE + ((FW_TMA_STAGES + 1) & ~1) : 0;   // even: every warp's ring stays 16-byte aligned
+  static size_t bytes(int N) { return (size_t)FW_WARPS * (MeritLayout<M>::per_warp_doubles(N) + TMA_DOUBLES) * sizeof(double); }
   // spec kernel: per-warp merit scratch, per-warp results (theta, L, J), next base step, rollout verdicts, 2 control ints
-  static IPDDP_BOTH int spec_doubles(int N) {
-    return FWS_WARPS * MeritLayout<M>::per_warp_doubles(N) + 3 * FWS_WARPS + 1 + (FWS_WARPS + 2 + 1) / 2;
+  static IPDDP_BOTH int spec_doubles(int N) {   // rounded up to even: the TMA staging rings follow at a 16-byte boundary
+    return (FWS_WARPS * MeritLayout<M>::per_warp_doubles(N) + 3 * FWS_WARPS + 1 + (FWS_WARPS + 2 + 1) / 2 + 1) & ~1;
   }
-  static size_t spec_bytes(int N) { return (size_t)spec_doubles(N) * sizeof(double); }
+  static size_t spec_bytes(int N) { return (size_t)(spec_doubles(N) + FWS_WARPS * TMA_DOUBLES) * sizeof(double); }
 };
+
+// per-warp handle on the TMA staging ring (empty when IPDDP_FW_TMA is off)
+struct FwStage {
+  double* buf;                 // FW_TMA_STAGES x STAGE doubles, 16-byte aligned
+  unsigned long long* bars;    // FW_TMA_STAGES mbarriers
+  unsigned seq;                // knots staged so far by this warp (stage = seq % STAGES, phase = (seq / STAGES) & 1)
+};
+template <class M>
+IPDDP_D FwStage fw_stage_init(double* base, int lane) {
+  FwStage st;
+  st.buf = base;
+  st.bars = reinterpret_cast<unsigned long long*>(base + FW_TMA_STAGES * FwLayout<M>::STAGE);
+  st.seq = 0;
+#if IPDDP_FW_TMA
+  if (lane == 0) {
+    for (int q = 0; q < FW_TMA_STAGES; ++q) mbar_init(&st.bars[q], 1);
+    mbar_init_fence();
+  }
+  __syncwarp();
+#endif
+  return st;
+}
 
 // per-lane output descriptors of the rollout (loop invariant): which gain row, which nominal field
 template <class M> struct FwDesc {
@@ -70,7 +103,7 @@ template <class M> struct FwDesc {
 //         2 fraction-to-boundary violation (src/forward_pass.jl:26-27)
 template <class M>
 IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int nom, double* trial, double gamma,
-                       double one_m_tau, const double* p, double* us, int lane) {
+                       double one_m_tau, const double* p, double* us, int lane, FwStage& stg) {
   typedef Rec<M> R;
   constexpr int NX = M::NX, NIT = FwDesc<M>::NIT;
   int rc = 0;
@@ -80,9 +113,43 @@ IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int 
   for (int i = 0; i < NX; ++i) x[i] = r0[R::X + i];
   // prefetch registers for knot t
   double ff[NIT], fb[NIT][NX], nv[NIT], nil[NIT], niu[NIT], xbar[NX];
+#if IPDDP_FW_TMA
+  // Knot t's gains record and nominal record are copied into stage (seq0 + t) % STAGES by one bulk copy each, issued by
+  // lane 0 up to STAGES - 1 knots before the warp reads them.  A stage is refilled one knot AFTER its values were loaded
+  // into registers, i.e. after those registers have been consumed by the arithmetic of that knot: no read of the stage can
+  // still be in flight.  Every issued copy is waited for before the function returns (early exits drain the ring), so the
+  // barrier phases stay in step with stg.seq across calls.
+  constexpr int SD = FwLayout<M>::STAGE;
+  const unsigned seq0 = stg.seq;
+  const int nrun = Nb - 1;                 // knots with gains
+  int issued = 0, waited = 0;
+  auto issue = [&](int t) {
+    if (lane == 0) {
+      const int sidx = (int)((seq0 + (unsigned)t) % FW_TMA_STAGES);
+      double* dst = stg.buf + (size_t)sidx * SD;
+      mbar_expect_tx(&stg.bars[sidx], (unsigned)(SD * sizeof(double)));
+      bulk_g2s(dst, v.gains + ((size_t)b * (v.N - 1) + t) * v.G, (unsigned)(FwLayout<M>::GP * sizeof(double)), &stg.bars[sidx]);
+      bulk_g2s(dst + FwLayout<M>::GP, v.rec(nom, b, t), (unsigned)(R::STRIDE * sizeof(double)), &stg.bars[sidx]);
+    }
+    issued = t + 1;
+  };
+  auto wait_knot = [&](int t) {
+    const unsigned q = seq0 + (unsigned)t;
+    mbar_wait(&stg.bars[q % FW_TMA_STAGES], (q / FW_TMA_STAGES) & 1u);
+    waited = t + 1;
+  };
+  for (int t = 0; t < FW_TMA_STAGES && t < nrun; ++t) issue(t);
+#endif
   auto prefetch = [&](int t) {
+#if IPDDP_FW_TMA
+    wait_knot(t);
+    const double* g = stg.buf + (size_t)((seq0 + (unsigned)t) % FW_TMA_STAGES) * SD;
+    const double* rn = g + FwLayout<M>::GP;
+    if (t >= 1 && t - 1 + FW_TMA_STAGES < nrun) issue(t - 1 + FW_TMA_STAGES);   // knot t-1's stage is free (see above)
+#else
     const double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
     const double* rn = v.rec(nom, b, t);
+#endif
 #pragma unroll
     for (int i = 0; i < NX; ++i) xbar[i] = rn[R::X + i];
 #pragma unroll
@@ -98,7 +165,7 @@ IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int 
   };
   if (Nb > 1) prefetch(0);
   for (int t = 0; t < Nb; ++t) {
-    double* rcur = trial + (size_t)t * R::SIZE;
+    double* rcur = trial + (size_t)t * R::STRIDE;
     if (lane < NX) {
       double xv = x[0];
 #pragma unroll
@@ -146,6 +213,11 @@ IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int 
     if (any_bad) { rc = 1; break; }
     if (any_viol) { rc = 2; break; }
   }
+#if IPDDP_FW_TMA
+  while (waited < issued) wait_knot(waited);      // drain the copies an early exit left in flight
+  stg.seq = seq0 + (unsigned)issued;
+  __syncwarp();
+#endif
   return rc;
 }
 
@@ -237,6 +309,7 @@ IPDDP_D void fw_finish(const DevView& v, const FwState<M>& s, int* list_next, in
   if (s.step < IPDDP_EPS) status = 7;
   v.siv(SI_L, b) = s.l;
   v.siv(SI_NROLL, b) += s.nroll;
+  v.siv(SI_LASTROLL, b) = s.nroll;
   v.sdv(SD_STEP, b) = s.step;
   v.sdv(SD_OBJECTIVE, b) = s.J;
   v.siv(SI_SWITCHING, b) = s.switching;
@@ -268,7 +341,7 @@ IPDDP_D void fw_finish(const DevView& v, const FwState<M>& s, int* list_next, in
     }
   }
   if (k >= v.opt.max_iterations) { v.siv(SI_STATUS, b) = 8; mark_done(v, b, counters); return; }
-  list_next[atomicAdd(&counters[CNT_NEXT], 1)] = b;
+  append_next(v, list_next, counters, b);
 }
 
 template <class M>
@@ -276,7 +349,9 @@ __global__ void __launch_bounds__(FW_WARPS * 32, IPDDP_FW_MINBLOCKS) k_forward(D
   IPDDP_DYN_SMEM(double, sm_all);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * FW_WARPS + warp;
-  if (slot >= counters[CNT_FWD]) return;
+  ListView lf = fwd_view(v, list_fwd, counters);
+  if (fwd_heavy_split(v, lf)) lf.n[0] = 0;      // the heaviest bucket is k_forward_spec's (heavy_only launch)
+  if (slot >= lf.total()) return;
   double* us = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
   double* chunk = us + MeritLayout<M>::NUP;
   unsigned char* bidx = reinterpret_cast<unsigned char*>(chunk + 32);
@@ -284,7 +359,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, IPDDP_FW_MINBLOCKS) k_forward(D
   double* p_l = part; double* p_th = part + v.N; double* p_d = part + 2 * v.N;
 
   FwState<M> s;
-  fw_setup<M>(v, s, list_fwd[slot]);
+  fw_setup<M>(v, s, lf.at(slot));
   const double* lo = v.lower + (size_t)s.b * M::NU;
   const double* up = v.upper + (size_t)s.b * M::NU;
   warp_bound_list<M>(lo, up, bidx, lane, s.nlo, s.nbd);
@@ -292,10 +367,11 @@ __global__ void __launch_bounds__(FW_WARPS * 32, IPDDP_FW_MINBLOCKS) k_forward(D
   d.init(lo, up, lane);
   s.dL = fw_expected_change<M>(v, s, p_l, p_th, lane);
 
+  FwStage stg = fw_stage_init<M>(sm_all + (size_t)FW_WARPS * MeritLayout<M>::per_warp_doubles(v.N) + (size_t)warp * FwLayout<M>::TMA_DOUBLES, lane);
   double* trial = v.rec(s.cur, s.b, 0);
   while (s.step >= IPDDP_EPS) {
     s.nroll++;
-    const int rc = fw_rollout<M>(v, d, s.b, s.Nb, s.nom, trial, s.step, s.one_m_tau, s.p, us, lane);
+    const int rc = fw_rollout<M>(v, d, s.b, s.Nb, s.nom, trial, s.step, s.one_m_tau, s.p, us, lane, stg);
     if (rc == 1) { s.step *= 0.5; continue; }
     if (rc == 2) { s.status = 2; s.step *= 0.5; continue; }
     __syncwarp();
@@ -310,12 +386,17 @@ __global__ void __launch_bounds__(FW_WARPS * 32, IPDDP_FW_MINBLOCKS) k_forward(D
 
 template <class M>
 __global__ void __launch_bounds__(FWS_WARPS * 32) k_forward_spec(DevView v, const int* list_fwd, int* list_next,
-                                                                int* counters) {
+                                                                int* counters, int heavy_only) {
   typedef Rec<M> R;
   IPDDP_DYN_SMEM(double, sm_all);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x;
-  if (slot >= counters[CNT_FWD]) return;
+  ListView lf = fwd_view(v, list_fwd, counters);
+  if (heavy_only) {                               // bulk round: only the heaviest bucket, and only if k_forward leaves it to us
+    if (!fwd_heavy_split(v, lf)) return;
+    lf.n[1] = 0; lf.n[2] = 0; lf.n[3] = 0;
+  }
+  if (slot >= lf.total()) return;
   constexpr int NUP = MeritLayout<M>::NUP;
   double* us = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
   double* chunk = us + NUP;
@@ -326,16 +407,18 @@ __global__ void __launch_bounds__(FWS_WARPS * 32) k_forward_spec(DevView v, cons
   double* next_step = res + 3 * FWS_WARPS;
   int* verdict = reinterpret_cast<int*>(next_step + 1);                               // [FWS_WARPS]
   int* ctl = verdict + FWS_WARPS;                                                     // [0] accepted candidate or -1, [1] go on
+  double* tma_base = sm_all + FwLayout<M>::spec_doubles(v.N);
 
   FwState<M> s;
-  fw_setup<M>(v, s, list_fwd[slot]);
+  fw_setup<M>(v, s, lf.at(slot));
   const double* lo = v.lower + (size_t)s.b * M::NU;
   const double* up = v.upper + (size_t)s.b * M::NU;
   FwDesc<M> d;
   d.init(lo, up, lane);
   warp_bound_list<M>(lo, up, bidx, lane, s.nlo, s.nbd);
   if (warp == 0) s.dL = fw_expected_change<M>(v, s, p_l, p_th, lane);   // only thread 0 judges
-  double* trial = v.spec_traj + ((size_t)slot * FWS_WARPS + warp) * v.N * R::SIZE;
+  double* trial = v.spec_traj + ((size_t)slot * FWS_WARPS + warp) * v.N * R::STRIDE;
+  FwStage stg = fw_stage_init<M>(tma_base + (size_t)warp * FwLayout<M>::TMA_DOUBLES, lane);
 
   // thread 0 owns the line-search state; the others only follow s.step
   for (;;) {
@@ -343,7 +426,7 @@ __global__ void __launch_bounds__(FWS_WARPS * 32) k_forward_spec(DevView v, cons
     for (int q = 0; q < warp; ++q) mine *= 0.5;     // the w-th value of the sequential `step *= 0.5` chain
     int rc = 3;                                      // 3: the sequential loop has ended before this step size
     if (mine >= IPDDP_EPS) {
-      rc = fw_rollout<M>(v, d, s.b, s.Nb, s.nom, trial, mine, s.one_m_tau, s.p, us, lane);
+      rc = fw_rollout<M>(v, d, s.b, s.Nb, s.nom, trial, mine, s.one_m_tau, s.p, us, lane, stg);
       if (rc == 0) {
         __syncwarp();
         double Jn, theta, L;
@@ -372,9 +455,9 @@ __global__ void __launch_bounds__(FWS_WARPS * 32) k_forward_spec(DevView v, cons
     __syncthreads();
     const int accepted = ctl[0], go_on = ctl[1];
     if (accepted >= 0) {   // the accepted candidate's records become the instance's trial set (then nomsel flips)
-      const double* src = v.spec_traj + ((size_t)slot * FWS_WARPS + accepted) * v.N * R::SIZE;
+      const double* src = v.spec_traj + ((size_t)slot * FWS_WARPS + accepted) * v.N * R::STRIDE;
       double* dst = v.rec(s.cur, s.b, 0);
-      const int n = (s.Nb - 1) * R::SIZE + M::NX;   // the terminal record only carries x
+      const int n = (s.Nb - 1) * R::STRIDE + M::NX;   // the terminal record only carries x
       for (int e = threadIdx.x; e < n; e += FWS_WARPS * 32) dst[e] = src[e];
     }
     if (!go_on) break;

@@ -6,6 +6,10 @@
 #define IPDDP_FULL_MASK 0xffffffffu
 #define IPDDP_EPS 2.220446049250313e-16
 
+#ifndef IPDDP_FWD_HEAVY_L
+#define IPDDP_FWD_HEAVY_L 16   // trial steps of the last line search that put an instance into the heaviest forward bucket
+#endif
+
 namespace ipk {
 
 // Julia's max/min propagate NaN (the reference relies on max(), norm(.,Inf); src/solve.jl:107-180)
@@ -129,7 +133,7 @@ IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu
   typedef Rec<M> R;
   constexpr int NX = M::NX, NU = M::NU, NC = M::NC;
   for (int t = lane; t < Nb; t += 32) {
-    double* r = recs + (size_t)t * R::SIZE;
+    double* r = recs + (size_t)t * R::STRIDE;
     double x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = r[R::X + i];
@@ -173,7 +177,7 @@ IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu
       double lg = 0.0;
       if (q < total) {
         const int t = q / nbd, s = q - t * nbd;
-        const double* r = recs + (size_t)t * R::SIZE;
+        const double* r = recs + (size_t)t * R::STRIDE;
         const int i = bidx[s];
         lg = dm::log(s < nlo ? r[R::IL + i] : r[R::IU + i]);
       }
@@ -196,6 +200,32 @@ IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu
 IPDDP_D void mark_done(const DevView& v, int b, int* counters) {
   v.siv(SI_DONE, b) = 1;
   if (v.done_list) v.done_list[atomicAdd(&counters[CNT_DONE], 1)] = b;
+}
+
+// append instance b to the next round's list / to this round's forward list (bucket = expected work, see layout.cuh)
+IPDDP_D void append_next(const DevView& v, int* list_next, int* counters, int b) {
+  const int sw = v.siv(SI_LASTSW, b);
+  const int k = !v.list_sort ? 3 : sw >= 4 ? 0 : sw == 3 ? 1 : sw == 2 ? 2 : 3;
+  list_next[(size_t)k * v.B + atomicAdd(&counters[CNT_NEXT + k], 1)] = b;
+}
+IPDDP_D void append_fwd(const DevView& v, int* list_fwd, int* counters, int b) {
+  const int l = v.siv(SI_LASTROLL, b);
+  const int k = !v.list_sort ? 3 : l >= IPDDP_FWD_HEAVY_L ? 0 : l >= 6 ? 1 : l >= 3 ? 2 : 3;
+  list_fwd[(size_t)k * v.B + atomicAdd(&counters[CNT_FWD + k], 1)] = b;
+}
+// the forward list's view, built on the device from the counters k_check left
+IPDDP_D ListView fwd_view(const DevView& v, const int* list_fwd, const int* counters) {
+  ListView l;
+  l.base = list_fwd; l.stride = v.B;
+  for (int k = 0; k < LIST_BUCKETS; ++k) l.n[k] = counters[CNT_FWD + k];
+  return l;
+}
+
+// Rounds too big for the speculative line search as a whole still hand their heaviest forward bucket (instances whose
+// last line search took >= 16 trial steps: the stragglers that reject dozens of step sizes per iteration) to
+// k_forward_spec, 8 step sizes at a time, while k_forward takes the rest; both kernels decide from the same counters.
+IPDDP_D bool fwd_heavy_split(const DevView& v, const ListView& lf) {
+  return v.list_sort && v.fw_spec_max > 0 && lf.n[0] > 0 && lf.n[0] <= v.fw_spec_max;
 }
 
 IPDDP_D void reset_filter(const DevView& v, int b) {

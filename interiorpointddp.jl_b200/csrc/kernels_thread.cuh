@@ -116,14 +116,15 @@ __global__ void k_init(DevView v, int warm, int b0, int nb, int* list_next, int*
   if (tid >= nb) return;
   const int b = b0 + tid;
   if (init_instance<M>(v, warm, b, v.x1 + (size_t)b * M::NX, v.ubar + (size_t)b * (v.N - 1) * M::NU))
-    list_next[atomicAdd(&counters[CNT_NEXT], 1)] = b;
+    append_next(v, list_next, counters, b);
   else
     mark_done(v, b, counters);
 }
 
 // Queue mode: admit n queued instances inst0 .. inst0+n-1 into the slots slots[0..n) (NULL: slots 0..n-1): copy the
 // instance's parameters, bounds and horizon into the slot, initialise its trajectory from the queue's x1 / ubar
-// (k_init's work) and append the slot to the running round's list at list[j] (the host passes list + n_active).
+// (k_init's work) and append the slot to the running round's list at list[j] (the host passes the end of the lightest
+// bucket: a fresh instance's first backward pass is one sweep).
 template <class M>
 __global__ void k_admit(DevView v, QueueView q, const int* slots, int n, int inst0, int* list, int* counters) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,12 +159,12 @@ struct TileStore {
 };
 
 template <class M>
-__global__ void k_derivs(DevView v, const int* list, int n_list) {
+__global__ void k_derivs(DevView v, ListView list) {
   typedef Rec<M> R;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int i = (int)(idx / v.N), t = (int)(idx % v.N);
-  if (i >= n_list) return;
-  const int b = list[i];
+  if (i >= list.total()) return;
+  const int b = list.at(i);
   const int Nb = v.horizon[b];
   if (t >= Nb) return;
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
@@ -196,14 +197,14 @@ __global__ void k_derivs(DevView v, const int* list, int n_list) {
 constexpr int CHK_WARPS = 4;
 
 template <class M>
-__global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, const int* list, int n_list, int* list_next,
-                                                         int* list_fwd, int* counters) {
+__global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, ListView list, int* list_next, int* list_fwd,
+                                                         int* counters) {
   typedef Rec<M> R;
   IPDDP_DYN_SMEM(double, sm_all);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * CHK_WARPS + warp;
-  if (i >= n_list) return;
-  const int b = list[i];
+  if (i >= list.total()) return;
+  const int b = list.at(i);
   if (v.siv(SI_STATUS, b) != 0) {  // backward pass failed (status 1): break
     __syncwarp();
     if (lane == 0) mark_done(v, b, counters);
@@ -313,11 +314,11 @@ __global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, const int* 
       v.sdv(SD_L_CURR, b) = L;
       v.sdv(SD_THETA_CURR, b) = theta;
       v.siv(SI_J, b) += 1;
-      list_next[atomicAdd(&counters[CNT_NEXT], 1)] = b;
+      append_next(v, list_next, counters, b);
     }
     return;
   }
-  if (lane == 0) list_fwd[atomicAdd(&counters[CNT_FWD], 1)] = b;
+  if (lane == 0) append_fwd(v, list_fwd, counters, b);
 }
 
 }  // namespace ipk

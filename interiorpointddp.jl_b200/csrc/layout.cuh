@@ -29,9 +29,28 @@ enum SD {  // double scalars
 };
 enum SI {  // int scalars
   SI_STATUS = 0, SI_K, SI_J, SI_L, SI_FILTER_N, SI_SWITCHING, SI_ARMIJO, SI_DONE, SI_NBACK, SI_NSWEEP, SI_NKKT,
-  SI_NROLL, SI_NDERIV, SI_TRACE_N, SI_COUNT
+  SI_NROLL, SI_NDERIV, SI_TRACE_N, SI_LASTSW, SI_LASTROLL, SI_COUNT
 };
-enum CNT { CNT_NEXT = 0, CNT_FWD = 1, CNT_DONE = 2, CNT_BAD = 3, CNT_COUNT = 8 };
+// Active lists are kept in LIST_BUCKETS buckets, heaviest expected work first (bucket 0), so that a launch hands its
+// longest-running instances to the first wave of warps instead of the last (a launch lasts as long as its slowest warp):
+// the next-round list by the sweeps of the instance's last backward pass, the forward list by the trial steps (rollouts) of
+// its last line search.  list[k * B + i] = i-th instance of bucket k; counters[CNT_NEXT + k] / [CNT_FWD + k] = its size.
+constexpr int LIST_BUCKETS = 4;
+enum CNT { CNT_NEXT = 0, CNT_FWD = 4, CNT_DONE = 8, CNT_BAD = 9, CNT_COUNT = 16 };
+struct ListView {      // kernel argument: a bucketed list with its (host-known) bucket sizes
+  const int* base;
+  int stride;          // B
+  int n[LIST_BUCKETS];
+  IPDDP_BOTH int total() const { return n[0] + n[1] + n[2] + n[3]; }
+  IPDDP_D int at(int i) const {
+    if (i < n[0]) return base[i];
+    i -= n[0];
+    if (i < n[1]) return base[stride + i];
+    i -= n[1];
+    if (i < n[2]) return base[2 * stride + i];
+    return base[3 * stride + (i - n[2])];
+  }
+};
 
 // Queue mode (ipddp_solve_queue): Q queued instances flow through the B resident slots of a handle.  Inputs are read
 // from the queue arrays when an instance is admitted into a slot, results are written to the queue's output arrays
@@ -51,7 +70,7 @@ struct QueueView {
 struct DevView {
   int B, N;
   int nx, nu, nc, np;
-  int TR, G;                 // record sizes (doubles)
+  int TR, G;                 // record strides (doubles), padded to even: x|u|c|il|iu|phi|zl|zu [+pad], eq|ineq gains [+pad]
   int n_compl;
   const int* compl_idx;
   unsigned long long compl_mask;   // bit i set <=> constraint i is in indices_compl
@@ -81,6 +100,7 @@ struct DevView {
   double* spec_traj;         // [fw_spec_max][FWS_WARPS][N][TR] private trial records of the speculative line search
   int* done_list;            // queue mode (ipddp_solve_queue): slots whose instance terminated in this round, else NULL
   int* inst_of;              // queue mode: [B] queue index of the instance resident in slot b
+  int list_sort;             // 1: active lists bucketed by expected work (heaviest first), 0: everything in one bucket (A/B)
   ipddp_options opt;
 
   IPDDP_D double* rec(int set, int b, int t) const { return traj + (((size_t)set * B + b) * N + t) * TR; }
@@ -91,5 +111,6 @@ struct DevView {
 // offsets inside a trajectory record
 template <class M> struct Rec {
   static constexpr int X = 0, U = M::NX, C = U + M::NU, IL = C + M::NC, IU = IL + M::NU, PHI = IU + M::NU,
-                       ZL = PHI + M::NC, ZU = ZL + M::NU, SIZE = ZU + M::NU;
+                       ZL = PHI + M::NC, ZU = ZL + M::NU, SIZE = ZU + M::NU,
+                       STRIDE = (SIZE + 1) & ~1;   // records are padded to an even number of doubles (16-byte multiples: bulk copies)
 };

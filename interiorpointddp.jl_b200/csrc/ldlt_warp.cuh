@@ -42,15 +42,6 @@ extern "C" long long g_ipddp_ldlt_steps[3];
 #define IPDDP_LDLT_COUNT(w) do { } while (0)
 #endif
 
-#ifndef IPDDP_ONE_GENERIC
-#define IPDDP_ONE_GENERIC 1       // one instance of the general pivot step for all k (measured: -3.4 % sweep time vs two)
-#endif
-#ifndef IPDDP_DIV_NOINLINE
-#define IPDDP_DIV_NOINLINE 1
-#endif
-#ifndef IPDDP_FAST2
-#define IPDDP_FAST2 1             // fast pivot step for columns k >= 32 as well (two lane slots)
-#endif
 
 namespace ipk {
 
@@ -72,7 +63,7 @@ IPDDP_D unsigned tri_decode(int p) {
 // into a ~60-instruction slow path for zero numerators, which KKT matrices with a zero block produce all the time.
 // The fallback division of DivBy sits out of line: the ~25 inlined instructions of an FP64 division per call site (18 sites
 // in the 2x2 pivot path) are cold code in the middle of the hot pivot step.  Measured: -2.8 % sweep time.
-#if IPDDP_DIV_NOINLINE && !defined(IPDDP_SIMT_EMU)
+#if !defined(IPDDP_SIMT_EMU)
 static __device__ __noinline__ double div_rare(double x, double d) { return x / d; }
 #else
 IPDDP_D double div_rare(double x, double d) { return x / d; }
@@ -405,16 +396,11 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
   int kp = k;
   const bool keep = __all_sync(IPDDP_FULL_MASK, fabs(piv) >= alpha * fabs(x));   // false on any NaN
   if (!keep) {
-#if !(defined(IPDDP_NAN_BY_MAX) && IPDDP_NAN_BY_MAX)
-    if (__any_sync(IPDDP_FULL_MASK, x != x) || piv != piv) return false;
-#endif
     // imax: first row attaining max |x|
     const double ax = fabs(x);
     const unsigned hi = in ? (unsigned)__double2hiint(ax) : 0u;
     const unsigned mh = __reduce_max_sync(IPDDP_FULL_MASK, hi);
-#if defined(IPDDP_NAN_BY_MAX) && IPDDP_NAN_BY_MAX   // experiment awaiting its A/B: NaN (and Inf) rows show up in the maximum, no extra vote
-    if (mh >= 0x7ff00000u || piv != piv) return false;
-#endif
+    if (mh >= 0x7ff00000u || piv != piv) return false;   // NaN (and Inf) rows show up in the maximum: no extra vote
     unsigned cand = __ballot_sync(IPDDP_FULL_MASK, in && hi == mh);
     if (cand & (cand - 1u)) {   // several rows share the high word: compare the low words among them
       const unsigned lo = (in && hi == mh) ? (unsigned)__double2loint(ax) : 0u;
@@ -451,23 +437,6 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
     S::dinv(scratch)[k] = rinv;
   }                                              // (nzhi[k] is only read for k > 32: nothing to clear here)
   if (nzm == 0u) return true;                // nothing to eliminate; B(k,:) scaling is deferred
-#if defined(IPDDP_NNZ1) && IPDDP_NNZ1   // experiment awaiting its A/B: 26 % of the 1x1 steps have ONE non-zero row (profiles/r1_ab)
-  if ((nzm & (nzm - 1u)) == 0u) {            // its lane owns the only element of the trailing update: no list, no shuffles
-    __syncwarp();                            // the interchange above stored a diagonal element from lane 0
-    if (x != 0.0) {
-      const int e = coff(lane) + lane;
-      A[e] = IPDDP_FMA(x, -rinv * x, A[e]);
-      const double xs = x * rinv;
-      A[ck + lane] = xs;
-#pragma unroll
-      for (int j = 0; j < NR; ++j) Bm[lane + j * K] = IPDDP_FMA(xs, -Bm[k + j * K], Bm[lane + j * K]);
-    } else if (kp != k && in) {
-      A[ck + lane] = 0.0;
-    }
-    __syncwarp();
-    return true;
-  }
-#endif
   unsigned char* list = S::list(scratch);
   if (x != 0.0) list[__popc(nzm & ((1u << lane) - 1u))] = (unsigned char)lane;
   __syncwarp();
@@ -610,32 +579,18 @@ IPDDP_D int warp_ldlt_factor(double* __restrict__ A, double* __restrict__ Bm, do
   int k = K - 1;
   if (K > 32) {
     while (k >= 32) {
-#if IPDDP_FAST2
       if (ldlt_step_fast2<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) { k -= 1; continue; }
-#endif
       k -= ldlt_step<K, NR, true>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
     }
   }
   while (k >= 0) {
-#if defined(IPDDP_TIGHT_FAST) && IPDDP_TIGHT_FAST   // experiment awaiting its A/B (DESIGN.md "Next"): fast steps in their own inner loop
-    while (k >= 0 && ldlt_step_fast<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) {
+    while (k >= 0 && ldlt_step_fast<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) {   // fast steps in their own inner loop
       IPDDP_LDLT_COUNT(0);
       k -= 1;
     }
     if (k < 0) break;
-#else
-    if (ldlt_step_fast<K, NR>(k, A, Bm, scratch, lane, tri_lane, tol, np)) {
-      IPDDP_LDLT_COUNT(0);
-      k -= 1;
-      continue;
-    }
-#endif
-#if IPDDP_ONE_GENERIC
     // one instance of the general step for every k (rows >= 32 are gated by a uniform run-time flag): half the code
     const int ks = ldlt_step<K, NR, (K > 32)>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
-#else
-    const int ks = ldlt_step<K, NR, false>(k, A, Bm, w, scratch, lane, tri_lane, tol, info, np);
-#endif
     IPDDP_LDLT_COUNT(ks);
     k -= ks;
   }

@@ -28,26 +28,29 @@ template <class M> struct Launch {
     return (long long)(a > b ? a : b);
   }
   static long long smem_merit_spec(int N) { return (long long)FwLayout<M>::spec_bytes(N); }
-  static void derivs(const DevView& v, const int* list, int n, cudaStream_t s) {
+  static void derivs(const DevView& v, const ListView& list, cudaStream_t s) {
+    const int n = list.total();
     if (n <= 0) return;
     const int th = 128;
     const long long total = (long long)n * v.N;
-    IPDDP_LAUNCH((k_derivs<M>), (unsigned)((total + th - 1) / th), th, 0, s, v, list, n);
+    IPDDP_LAUNCH((k_derivs<M>), (unsigned)((total + th - 1) / th), th, 0, s, v, list);
   }
-  static void backward(const DevView& v, const int* list, int n, cudaStream_t s) {
+  static void backward(const DevView& v, const ListView& list, cudaStream_t s) {
+    const int n = list.total();
     if (n <= 0) return;
     if (n <= v.bw_spec_max) {
       const size_t smem = (size_t)BWS_WARPS * BwLayout<M>::BYTES + BWS_WARPS * 8 + BWS_WARPS * 2 * 4;
-      IPDDP_LAUNCH((k_backward_spec<M>), n, BWS_WARPS * 32, smem, s, v, list, n);
+      IPDDP_LAUNCH((k_backward_spec<M>), n, BWS_WARPS * 32, smem, s, v, list);
       return;
     }
-    IPDDP_LAUNCH((k_backward<M>), n, 32, BwLayout<M>::BYTES + IPDDP_BW_EXTRA_SMEM, s, v, list, n);
+    IPDDP_LAUNCH((k_backward<M>), n, 32, BwLayout<M>::BYTES + IPDDP_BW_EXTRA_SMEM, s, v, list);
   }
-  static void check(const DevView& v, const int* list, int n, int* list_next, int* list_fwd, int* counters,
+  static void check(const DevView& v, const ListView& list, int* list_next, int* list_fwd, int* counters,
                     cudaStream_t s) {
+    const int n = list.total();
     if (n <= 0) return;
     const size_t smem = (size_t)CHK_WARPS * MeritLayout<M>::per_warp_doubles(v.N) * sizeof(double);
-    IPDDP_LAUNCH((k_check<M>), (n + CHK_WARPS - 1) / CHK_WARPS, CHK_WARPS * 32, smem, s, v, list, n, list_next, list_fwd,
+    IPDDP_LAUNCH((k_check<M>), (n + CHK_WARPS - 1) / CHK_WARPS, CHK_WARPS * 32, smem, s, v, list, list_next, list_fwd,
                  counters);
   }
   static void forward(const DevView& v, const int* list_fwd, int n_upper, int* list_next, int* counters,
@@ -55,9 +58,12 @@ template <class M> struct Launch {
     if (n_upper <= 0) return;
     if (n_upper <= v.fw_spec_max) {
       IPDDP_LAUNCH((k_forward_spec<M>), n_upper, FWS_WARPS * 32, FwLayout<M>::spec_bytes(v.N), s, v, list_fwd, list_next,
-                   counters);
+                   counters, 0);
       return;
     }
+    if (v.list_sort && v.fw_spec_max > 0)   // the heaviest bucket of a bulk round, 8 step sizes at a time (see fwd_heavy_split)
+      IPDDP_LAUNCH((k_forward_spec<M>), v.fw_spec_max, FWS_WARPS * 32, FwLayout<M>::spec_bytes(v.N), s, v, list_fwd,
+                   list_next, counters, 1);
     IPDDP_LAUNCH((k_forward<M>), (n_upper + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, FwLayout<M>::bytes(v.N), s, v,
                  list_fwd, list_next, counters);
   }

@@ -6,9 +6,9 @@ struct ModelVTable {
   const char* name;
   int nx, nu, nc, np, d_nslot, dn_nslot, vf_nslot, smem_backward;
   void (*init)(const DevView&, int warm, int b0, int nb, int* list_next, int* counters, cudaStream_t);
-  void (*derivs)(const DevView&, const int* list, int n, cudaStream_t);
-  void (*backward)(const DevView&, const int* list, int n, cudaStream_t);
-  void (*check)(const DevView&, const int* list, int n, int* list_next, int* list_fwd, int* counters, cudaStream_t);
+  void (*derivs)(const DevView&, const ListView& list, cudaStream_t);
+  void (*backward)(const DevView&, const ListView& list, cudaStream_t);
+  void (*check)(const DevView&, const ListView& list, int* list_next, int* list_fwd, int* counters, cudaStream_t);
   void (*forward)(const DevView&, const int* list_fwd, int n_upper, int* list_next, int* counters, cudaStream_t);
   // queue mode: admit `n` queued instances inst0.. into the slots `slots` (NULL: 0..n-1), appending them at list[0..n)
   void (*admit)(const DevView&, const QueueView&, const int* slots, int n, int inst0, int* list, int* counters, cudaStream_t);

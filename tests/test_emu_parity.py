@@ -85,6 +85,40 @@ def test_emulated_memcheck_asan():
     assert r.stdout.strip().splitlines() == want
 
 
+def test_emulated_forward_heavy_split(oracle_mod):
+    """Bulk rounds hand their heaviest forward bucket to k_forward_spec while k_forward takes the rest.  An emulator
+    build with the bucket threshold lowered to two trial steps (-DIPDDP_FWD_HEAVY_L=2) and a speculative capacity
+    of 1-2 instances makes small batches take exactly that path; results must still equal the oracle bit for bit."""
+    import subprocess
+    from ipddp_b200 import _lib
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, IPDDP_EMU_DEFS="-DIPDDP_FWD_HEAVY_L=2", IPDDP_EMU_LIB="libipddp_emu_heavy2.so")
+    subprocess.run([sys.executable, os.path.join(here, "emu", "build_emu.py")], env=env, check=True, capture_output=True)
+    lib = _lib.Lib(os.path.join(here, "emu", "libipddp_emu_heavy2.so"))
+    for cap, wl, B, N, maxit in ((1, "cartpole", 3, 9, 25), (2, "pushing", 4, 9, 30), (1, "concar", 3, 11, 60)):
+        lib.L.ipddp_set_tuning(None, b"fw_spec_max", cap)
+        lib.L.ipddp_set_tuning(None, b"bw_spec_max", 0)
+        helpers.full_solve_parity(lib, oracle_mod, wl, B, N, maxit=maxit, n_trace=B)
+
+
+def test_emulated_tma_staged_rollout(oracle_mod):
+    """-DIPDDP_FW_TMA=1: the rollout reads its per-knot gains / nominal records from a shared-memory ring filled by TMA
+    bulk copies.  Under the emulator the copies are synchronous, which still checks the ring logic (stage indices across
+    trial steps and early exits, record padding, drain) against the oracle, bulk and speculative kernels."""
+    import subprocess
+    from ipddp_b200 import _lib
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, IPDDP_EMU_DEFS="-DIPDDP_FW_TMA=1", IPDDP_EMU_LIB="libipddp_emu_tma.so")
+    subprocess.run([sys.executable, os.path.join(here, "emu", "build_emu.py")], env=env, check=True, capture_output=True)
+    lib = _lib.Lib(os.path.join(here, "emu", "libipddp_emu_tma.so"))
+    for spec in (148, 0):
+        lib.L.ipddp_set_tuning(None, b"fw_spec_max", spec)
+        helpers.full_solve_parity(lib, oracle_mod, "cartpole", 2, 9, maxit=25, n_trace=2)
+        helpers.full_solve_parity(lib, oracle_mod, "pushing", 3, 9, maxit=30, vary_horizon=True, n_trace=2)
+        helpers.full_solve_parity(lib, oracle_mod, "double_integrator", 2, 2)
+    helpers.phase_parity(lib, oracle_mod, "concar", B=2, N=7, rounds=2)
+
+
 def test_emulated_varying_horizon(emu, oracle_mod):
     helpers.full_solve_parity(emu, oracle_mod, "concar", 4, 13, maxit=80, vary_horizon=True, first=100, n_trace=4)
 

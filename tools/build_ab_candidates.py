@@ -11,16 +11,6 @@ from ipddp_b200 import build as b  # noqa: E402
 
 CANDIDATES = [
     ("c_base", []),
-    ("c_tight", ["-DIPDDP_TIGHT_FAST=1"]),
-    ("c_nnz1", ["-DIPDDP_NNZ1=1"]),
-    ("c_nanmax", ["-DIPDDP_NAN_BY_MAX=1"]),
-    ("c_udiv", ["-DIPDDP_GAINS_UDIV=1"]),
-    ("c_nnz1_nanmax", ["-DIPDDP_NNZ1=1", "-DIPDDP_NAN_BY_MAX=1"]),
-    ("c_all", ["-DIPDDP_TIGHT_FAST=1", "-DIPDDP_NNZ1=1", "-DIPDDP_NAN_BY_MAX=1", "-DIPDDP_GAINS_UDIV=1"]),
-    # occupancy curve: unused dynamic shared memory lowers the resident warps per SM of k_backward (21 -> 16 / 12 / 8)
-    ("c_occ16", ["-DIPDDP_BW_EXTRA_SMEM=3700"]),
-    ("c_occ12", ["-DIPDDP_BW_EXTRA_SMEM=8500"]),
-    ("c_occ8", ["-DIPDDP_BW_EXTRA_SMEM=18300"]),
 ]
 
 if __name__ == "__main__":

@@ -68,11 +68,19 @@ def run(lib, wl, B, N, rounds):
     print(json.dumps(out), flush=True)
 
 
+def apply_tuning(lib):
+    """IPDDP_TUNE="key=value,key=value": global ipddp_set_tuning defaults for the problems created afterwards."""
+    for kv in filter(None, os.environ.get("IPDDP_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        lib.check(lib.L.ipddp_set_tuning(None, k.encode(), int(v)), "ipddp_set_tuning")
+
+
 if __name__ == "__main__":
     wl = sys.argv[1]
     Bs = [int(x) for x in sys.argv[2].split(",")]
     rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 12
     lib = _lib.Lib(sys.argv[4]) if len(sys.argv) > 4 else _lib.load()
     N = int(os.environ.get("IPDDP_KNOTS", "101"))
+    apply_tuning(lib)
     for B in Bs:
         run(lib, wl, B, N, rounds)

@@ -26,7 +26,7 @@ def run(lib, wl, Q, B, N, vary):
     sc = [st_i.data_ptr(), k_i.data_ptr()] + [None] * 13
     q = make_queue(Q, t["x1"].data_ptr(), t["ubar"].data_ptr(), t["p"].data_ptr() if s.np > 0 else None, t["lower"].data_ptr(),
                    t["upper"].data_ptr(), hz.data_ptr(), sc, None, None, inputs_on_device=True, outputs_on_device=True)
-    for rep in range(2):
+    for rep in range(int(os.environ.get("IPDDP_REPS", "1"))):
         lib.check(lib.L.ipddp_solve_queue(s.h, C.byref(q)), "ipddp_solve_queue")
         st = s.stats()
         print(json.dumps(dict(workload=wl, Q=Q, B=B, N=N, rep=rep, ms=round(st.ms_total, 1), converged=int(st.n_converged),
@@ -38,11 +38,19 @@ def run(lib, wl, Q, B, N, vary):
     s.close()
 
 
+def apply_tuning(lib):
+    """IPDDP_TUNE="key=value,key=value": global ipddp_set_tuning defaults for the problems created afterwards."""
+    for kv in filter(None, os.environ.get("IPDDP_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        lib.check(lib.L.ipddp_set_tuning(None, k.encode(), int(v)), "ipddp_set_tuning")
+
+
 if __name__ == "__main__":
     wl = sys.argv[1]
     Q = int(sys.argv[2])
     Bs = [int(x) for x in sys.argv[3].split(",")]
     N = int(sys.argv[4]) if len(sys.argv) > 4 else 101
     lib = _lib.Lib(sys.argv[5]) if len(sys.argv) > 5 else _lib.load()
+    apply_tuning(lib)
     for B in Bs:
         run(lib, wl, Q, B, N, vary=(wl == "pushing"))
