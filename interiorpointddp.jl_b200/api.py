@@ -155,28 +155,32 @@ def Options(**kw) -> _lib.Options:
 # ------------------------------------------------------------------------------------------------
 # model plugin cache: closures -> CUDA -> nvcc -> .so -> ipddp_model_load
 # ------------------------------------------------------------------------------------------------
-def _closure_fingerprint(fns) -> str:
-    h = hashlib.sha256()
-    for f in fns:
-        if f is None:
-            h.update(b"none")
-            continue
-        try:
-            h.update(inspect.getsource(f).encode())
-        except (OSError, TypeError):
-            h.update(repr(f).encode())
-        for cell in (getattr(f, "__closure__", None) or ()):
-            try:
-                h.update(repr(cell.cell_contents).encode())
-            except Exception:
-                pass
-    return h.hexdigest()[:12]
+_loaded_models = {}   # (library id, model name) -> digest of the source the registered model was built from
 
 
-def build_model_plugin(md: workloads.ModelDef, force: bool = False) -> str:
+def _copy_options(o: _lib.Options) -> _lib.Options:
+    c = _lib.Options()
+    for fname, _ in _lib.Options._fields_:
+        setattr(c, fname, getattr(o, fname))
+    return c
+
+
+def model_digest(md: workloads.ModelDef, bundles=None) -> str:
+    """sha256 over the emitted device source with the model name neutralised, the dimensions and indices_compl."""
+    saved = md.name
+    md.name = "M"
+    try:
+        src = generate.emit_device(md, bundles if bundles is not None else generate.trace(md))
+    finally:
+        md.name = saved
+    key = f"{src}|{md.nx}|{md.nu}|{md.np_}|{sorted(md.indices_compl)}"
+    return hashlib.sha256(key.encode()).hexdigest()[:12]
+
+
+def build_model_plugin(md: workloads.ModelDef, force: bool = False, bundles=None) -> str:
     """Generates csrc for `md` and compiles it for sm_100a into a plugin exporting `ipddp_plugin_vtable`."""
     os.makedirs(PLUGIN_DIR, exist_ok=True)
-    bundles = generate.trace(md)
+    bundles = bundles if bundles is not None else generate.trace(md)
     src = generate.emit_device(md, bundles).replace('#include "../model_common.cuh"',
                                                     f'#include "{os.path.join(HERE, "csrc", "model_common.cuh")}"')
     from . import build as _b
@@ -247,26 +251,33 @@ class Solver:
             raise NotImplementedError("running stages must share one Bound (per-instance bounds go through solve(..., lower=, upper=))")
         self.N, self.nx, self.nu, self.batch, self.num_parameter = N, nx, nu, int(batch), int(num_parameter)
         self.bound = b0
-        self.quasi_newton = d0.quasi_newton or c0.quasi_newton
         stage_f = o0.f
         term_f = _with_p(oN._src, 2)
         cfun = c0.c if c0.c is not None else (lambda x, u, p: [])
-        extra = [f_ for f_ in (d0._extra_src + c0._extra_src) if f_ is not None]
-        tag = name or ("user_" + _closure_fingerprint([d0._src, o0._src, oN._src, c0._src] + extra))
         md = workloads.ModelDef(
-            name=tag, nx=nx, nu=nu, np_=self.num_parameter, f=d0.f, stage_cost=stage_f,
+            name="pending", nx=nx, nu=nu, np_=self.num_parameter, f=d0.f, stage_cost=stage_f,
             term_cost=lambda x, p: term_f(x, [], p), c=cfun, lower=lambda p: list(b0.lower), upper=lambda p: list(b0.upper),
             u_init=[0.0] * nu, dt=0.0, indices_compl=list(c0.indices_compl),
             user_derivs={**d0.user_derivs, **c0.user_derivs}, user_dynamics=bool(d0.user_derivs),
-            user_constraint=bool(c0.user_derivs))
+            user_constraint=bool(c0.user_derivs), qn_dynamics=d0.quasi_newton, qn_constraint=c0.quasi_newton)
+        # The model's identity is the device code that was traced from the closures (plus its dimensions): globals and
+        # closure cells the closures read are folded into that code at trace time, so two Solvers share a compiled model
+        # exactly when their emitted sources agree.  A user-chosen `name` is bound to the source it was first built from
+        # in this process; the same name with different code is rebuilt and re-registered (ipddp_model_load replaces it).
+        bundles = generate.trace(md)
+        digest = model_digest(md, bundles)
+        tag = name or ("user_" + digest)
+        md.name = tag
         self.model_def = md
         self.lib = _lib.load()
-        if tag not in self.lib.models():
-            so = build_model_plugin(md)
+        if _loaded_models.get((id(self.lib), tag)) != digest:
+            so = build_model_plugin(md, bundles=bundles)
             self.lib.check(self.lib.L.ipddp_model_load(so.encode()), "ipddp_model_load")
-        self.options = options if options is not None else self.lib.default_options()
-        if self.quasi_newton:
-            self.options.quasi_newton = 1
+            _loaded_models[(id(self.lib), tag)] = digest
+        # per-object quasi_newton only removes that object's contractions (ModelDef.qn_*); Options.quasi_newton is the
+        # user's and is neither forced nor mutated here
+        self.options = _copy_options(options) if options is not None else self.lib.default_options()
+        self.quasi_newton = bool(self.options.quasi_newton)
         self._bs = BatchSolver(tag, self.batch, N, options=self.options, device=device, trace_capacity=trace_capacity,
                                indices_compl=c0.indices_compl, lib=self.lib)
         self.nc = self._bs.nc

@@ -170,6 +170,7 @@ def trace(md: workloads.ModelDef) -> Dict[str, Bundle]:
         return auto()
 
     udyn, ucon = bool(getattr(md, "user_dynamics", False)), bool(getattr(md, "user_constraint", False))
+    qnd, qnc = bool(getattr(md, "qn_dynamics", False)), bool(getattr(md, "qn_constraint", False))
     Jfx = pick("fx", nxn, nx, (x, u, p), lambda: fx_.jacobian(X), udyn)
     Jfu = pick("fu", nxn, nu, (x, u, p), lambda: fx_.jacobian(U), udyn)
     lx = sp.Matrix([l_]).jacobian(X).T
@@ -178,17 +179,23 @@ def trace(md: workloads.ModelDef) -> Dict[str, Bundle]:
     cx = pick("cx", nc, nx, (x, u, p), lambda: c_.jacobian(X), ucon)
     cu = pick("cu", nc, nu, (x, u, p), lambda: c_.jacobian(U), ucon)
     vv = sp.Matrix(v[:nc])
-    vcxx = pick("vcxx", nx, nx, (x, u, v[:nc], p), lambda: (cx.T * vv).jacobian(X), ucon)
-    vcux = pick("vcux", nu, nx, (x, u, v[:nc], p), lambda: (cu.T * vv).jacobian(X), ucon)
-    vcuu = pick("vcuu", nu, nu, (x, u, v[:nc], p), lambda: (cu.T * vv).jacobian(U), ucon)
+    if qnc:   # quasi-Newton constraint object: its contraction caches stay zero
+        vcxx, vcux, vcuu = sp.zeros(nx, nx), sp.zeros(nu, nx), sp.zeros(nu, nu)
+    else:
+        vcxx = pick("vcxx", nx, nx, (x, u, v[:nc], p), lambda: (cx.T * vv).jacobian(X), ucon)
+        vcux = pick("vcux", nu, nx, (x, u, v[:nc], p), lambda: (cu.T * vv).jacobian(X), ucon)
+        vcuu = pick("vcuu", nu, nu, (x, u, v[:nc], p), lambda: (cu.T * vv).jacobian(U), ucon)
     b["derivs"] = _make_bundle("derivs", ["x", "u", "v", "p"], [
         ("fx", Jfx), ("fu", Jfu), ("lx", lx), ("lu", lu), ("lxx", lxx), ("luu", luu), ("lux", lux),
         ("cx", cx), ("cu", cu), ("vcxx", vcxx), ("vcux", vcux), ("vcuu", vcuu)])
 
     lv = sp.Matrix(lam)
-    vfxx = pick("vfxx", nx, nx, (x, u, lam, p), lambda: (Jfx.T * lv).jacobian(X), udyn)
-    vfux = pick("vfux", nu, nx, (x, u, lam, p), lambda: (Jfu.T * lv).jacobian(X), udyn)
-    vfuu = pick("vfuu", nu, nu, (x, u, lam, p), lambda: (Jfu.T * lv).jacobian(U), udyn)
+    if qnd:   # quasi-Newton dynamics object
+        vfxx, vfux, vfuu = sp.zeros(nx, nx), sp.zeros(nu, nx), sp.zeros(nu, nu)
+    else:
+        vfxx = pick("vfxx", nx, nx, (x, u, lam, p), lambda: (Jfx.T * lv).jacobian(X), udyn)
+        vfux = pick("vfux", nu, nx, (x, u, lam, p), lambda: (Jfu.T * lv).jacobian(X), udyn)
+        vfuu = pick("vfuu", nu, nu, (x, u, lam, p), lambda: (Jfu.T * lv).jacobian(U), udyn)
     b["vf"] = _make_bundle("vf", ["x", "u", "v", "p"], [("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu)])
 
     lNx = sp.Matrix([lN_]).jacobian(X).T

@@ -48,6 +48,11 @@ class ModelDef:
     user_derivs: dict = field(default_factory=dict)
     user_dynamics: bool = False       # the Dynamics was built from user-provided derivatives
     user_constraint: bool = False     # the Constraint was built from user-provided derivatives
+    # Dynamics(...; quasi_newton=true) / Constraint(...; quasi_newton=true): that object's second-order contractions are
+    # never evaluated and its caches stay zero (reference src/dynamics.jl:27-37,63-70, src/constraints.jl:76-83); the other
+    # object's terms are still added unless Options.quasi_newton is set (src/backward_pass.jl:101-114)
+    qn_dynamics: bool = False
+    qn_constraint: bool = False
 
     @property
     def nc(self) -> int:

@@ -29,7 +29,7 @@
 #include "tma.cuh"
 
 #ifndef IPDDP_FW_TMA
-#define IPDDP_FW_TMA 0            // 1: the rollout's per-knot gains + nominal records are staged in shared memory by TMA bulk copies
+#define IPDDP_FW_TMA 1            // 1: the rollout's per-knot gains + nominal records are staged in shared memory by TMA bulk copies
 #endif
 
 namespace ipk {

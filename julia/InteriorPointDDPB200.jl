@@ -1,52 +1,98 @@
 # InteriorPointDDPB200.jl -- Julia binding of libipddp_b200.so (C ABI: include/ipddp_b200.h).
 #
-# NOT EXECUTED in the build image (no Julia there); it documents exactly what a maintainer of
-# mingu6/InteriorPointDDP.jl adds to route `solve!` through the B200 library.  It keeps the exported names of
-# reference src/InteriorPointDDP.jl:29-45.  Model code generation: the reference's `Symbolics.build_function`
-# call sites (src/dynamics.jl:26-34, src/objectives.jl:23-28, src/constraints.jl:25-39) are retargeted to
-# `target = Symbolics.CTarget()`; the emitted C bodies are wrapped into the `Model_<name>` struct layout of
+# NOT EXECUTED in the build image (no Julia there; tests/test_abi.py checks every ccall signature and struct mirror of this
+# file against include/ipddp_b200.h).  It keeps the exported names of reference src/InteriorPointDDP.jl:29-45
+# (Dynamics / Objective / Constraint / Bound / Solver / Options / solve! / get_trajectory) on top of a batched layer
+# (BatchProblem, solve_queue!).  Model code generation: the reference's `Symbolics.build_function` call sites
+# (src/dynamics.jl:26-34, src/objectives.jl:23-28, src/constraints.jl:25-39) are retargeted to
+# `target = Symbolics.CTarget()` in codegen.jl; the emitted C bodies are wrapped into the `Model_<name>` struct layout of
 # interiorpointddp.jl_b200/csrc/models_gen/*.cuh and compiled with nvcc into a plugin (see INTEGRATION.md).
 module InteriorPointDDPB200
 
-export Options, BatchProblem, Stats, solve!, solve_many!, get_trajectory, get_duals, get_trace, get_stats,
-       set_tuning!, load_model!
+# the reference's exported names (src/InteriorPointDDP.jl:29-45) ...
+export Objective, Constraint, Dynamics, Bound, Solver, Options, solve!, get_trajectory
+# ... and the batched layer underneath them
+export BatchProblem, Stats, Queue, solve_queue!, solve_many!, get_duals, get_trace, get_stats, set_tuning!, set_stream!,
+       load_model!
 
 const LIB = get(ENV, "IPDDP_B200_LIB", "libipddp_b200.so")
 
-# mirror of `ipddp_options` == reference Options{T} (src/options.jl:1-38), same field order
-Base.@kwdef mutable struct Options
-    quasi_newton::Cint = 0
-    optimality_tolerance::Cdouble = 1.0e-8
-    max_iterations::Cint = 1000
-    reset_cache::Cint = 1
-    verbose::Cint = 0
-    print_frequency::Cint = 10
-    μ_init::Cdouble = 1.0
-    ineq_dual_init::Cdouble = 1.0
-    κ_1::Cdouble = 0.01
-    κ_2::Cdouble = 0.01
-    reg_1::Cdouble = 1e-4
-    reg_min::Cdouble = 1e-20
-    reg_max::Cdouble = 1e40
-    κ_̄w_p::Cdouble = 100.0
-    κ_w_p::Cdouble = 8.0
-    κ_w_m::Cdouble = 1.0 / 3.0
-    κ_c::Cdouble = 0.25
-    δ_c::Cdouble = 1e-8
-    κ_ϵ::Cdouble = 10.0
-    κ_μ::Cdouble = 0.2
-    θ_μ::Cdouble = 1.2
-    τ_min::Cdouble = 0.99
-    s_max::Cdouble = 100.0
-    η_L::Cdouble = 1e-4
-    s_L::Cdouble = 2.3
-    δ::Cdouble = 1.0
-    s_θ::Cdouble = 1.1
-    γ_α::Cdouble = 0.05
-    γ_θ::Cdouble = 1e-5
-    γ_L::Cdouble = 1e-5
-    κ_Σ::Cdouble = 1e10
+include("codegen.jl")
+
+"""
+    Options{T}(; kwargs...)
+
+The reference's `Options{T}` (src/options.jl:1-38): same field names, types and defaults.
+"""
+Base.@kwdef mutable struct Options{T}
+    quasi_newton::Bool = false
+    optimality_tolerance::T = 1.0e-8
+    max_iterations::Int = 1000
+    reset_cache::Bool = true
+    verbose = false
+    print_frequency = 10
+    μ_init::T = 1.0
+    ineq_dual_init::T = 1.0
+    κ_1::T = 0.01
+    κ_2::T = 0.01
+    reg_1::T = 1e-4
+    reg_min::T = 1e-20
+    reg_max::T = 1e40
+    κ_̄w_p::T = 100.0
+    κ_w_p::T = 8.0
+    κ_w_m::T = 1.0 / 3.0
+    κ_c::T = 0.25
+    δ_c::T = 1e-8
+    κ_ϵ::T = 10.0
+    κ_μ::T = 0.2
+    θ_μ::T = 1.2
+    τ_min::T = 0.99
+    s_max::T = 100.0
+    η_L::T = 1e-4
+    s_L::T = 2.3
+    δ::T = 1.0
+    s_θ::T = 1.1
+    γ_α::T = 0.05
+    γ_θ::T = 1e-5
+    γ_L::T = 1e-5
+    κ_Σ::T = 1e10
 end
+
+# C mirror of `ipddp_options` (include/ipddp_b200.h), same field order as Options{T}; passed by reference through ccall
+mutable struct COptions
+    quasi_newton::Cint
+    optimality_tolerance::Cdouble
+    max_iterations::Cint
+    reset_cache::Cint
+    verbose::Cint
+    print_frequency::Cint
+    μ_init::Cdouble
+    ineq_dual_init::Cdouble
+    κ_1::Cdouble
+    κ_2::Cdouble
+    reg_1::Cdouble
+    reg_min::Cdouble
+    reg_max::Cdouble
+    κ_̄w_p::Cdouble
+    κ_w_p::Cdouble
+    κ_w_m::Cdouble
+    κ_c::Cdouble
+    δ_c::Cdouble
+    κ_ϵ::Cdouble
+    κ_μ::Cdouble
+    θ_μ::Cdouble
+    τ_min::Cdouble
+    s_max::Cdouble
+    η_L::Cdouble
+    s_L::Cdouble
+    δ::Cdouble
+    s_θ::Cdouble
+    γ_α::Cdouble
+    γ_θ::Cdouble
+    γ_L::Cdouble
+    κ_Σ::Cdouble
+end
+COptions(o::Options) = COptions((getfield(o, f) for f in fieldnames(Options))...)   # Bool / Int / T convert field by field
 
 last_error() = unsafe_string(ccall((:ipddp_last_error, LIB), Cstring, ()))
 check(rc, what) = rc == 0 || error("$what failed: $(last_error())")
@@ -97,20 +143,20 @@ Base.@kwdef mutable struct Stats
 end
 
 """
-    BatchProblem(model, B, N; options=Options(), device=0, indices_compl=Cint[])
+    BatchProblem(model, B, N; options=Options{Float64}(), device=0, indices_compl=Cint[])
 
 Batched counterpart of `Solver(T, dynamics, objectives, constraints, bounds; options)` (reference src/solver.jl:11-26).
 """
-function BatchProblem(model::String, B::Int, N::Int; options::Options=Options(), device::Int=0,
+function BatchProblem(model::String, B::Int, N::Int; options::Options=Options{Float64}(), device::Int=0,
                       indices_compl::Vector{Cint}=Cint[], trace_capacity::Int=0)
     dims = [Ref{Cint}(0) for _ in 1:5]
     check(ccall((:ipddp_model_dims, LIB), Cint, (Cstring, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}),
                 model, dims...), "ipddp_model_dims")
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ipddp_problem_create, LIB), Cint,
-                (Cstring, Cint, Cint, Ptr{Cint}, Cint, Ref{Options}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                (Cstring, Cint, Cint, Ptr{Cint}, Cint, Ref{COptions}, Cint, Cint, Ref{Ptr{Cvoid}}),
                 model, B, N, isempty(indices_compl) ? C_NULL : pointer(indices_compl), length(indices_compl),
-                Ref(options), device, trace_capacity, h), "ipddp_problem_create")
+                Ref(COptions(options)), device, trace_capacity, h), "ipddp_problem_create")
     p = BatchProblem(h[], model, B, N, dims[1][], dims[2][], dims[3][], dims[4][], zeros(Cint, B), zeros(Cint, B),
                      zeros(Cint, B), zeros(Cint, B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B))
     finalizer(q -> ccall((:ipddp_problem_destroy, LIB), Cint, (Ptr{Cvoid},), q.handle), p)
@@ -162,7 +208,7 @@ function solve_many!(ps::Vector{BatchProblem}; total_solves::Int=length(ps), war
     return ms[], st[]
 end
 
-"Execution tuning that never changes results (`ipddp_set_tuning`): \"fw_spec_max\", \"bw_spec_max\", \"bulk_slots\"."
+"Execution tuning that never changes results (`ipddp_set_tuning`): \"fw_spec_max\", \"bw_spec_max\", \"list_sort\", \"bulk_slots\"."
 set_tuning!(p::Union{BatchProblem,Nothing}, key::AbstractString, value::Integer) =
     check(ccall((:ipddp_set_tuning, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint),
                 p === nothing ? C_NULL : p.handle, key, value), "ipddp_set_tuning")
@@ -204,6 +250,247 @@ function get_trajectory(p::BatchProblem)
     check(ccall((:ipddp_get_trajectory, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), p.handle, x, u),
           "ipddp_get_trajectory")
     return x, u
+end
+
+
+"Launch on the caller's CUDA stream (a `CUstream` / `cudaStream_t` as Ptr{Cvoid}, e.g. from CUDA.jl); C_NULL = own stream."
+set_stream!(p::BatchProblem, stream::Ptr{Cvoid}) =
+    check(ccall((:ipddp_set_stream, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), p.handle, stream), "ipddp_set_stream")
+
+# C mirror of `ipddp_queue` (include/ipddp_b200.h): Q queued instances, input and output arrays
+mutable struct Queue
+    Q::Cint
+    x1::Ptr{Cdouble}
+    ubar::Ptr{Cdouble}
+    params::Ptr{Cdouble}
+    lower::Ptr{Cdouble}
+    upper::Ptr{Cdouble}
+    horizons::Ptr{Cint}
+    inputs_on_device::Cint
+    status::Ptr{Cint}
+    k::Ptr{Cint}
+    j::Ptr{Cint}
+    l::Ptr{Cint}
+    objective::Ptr{Cdouble}
+    primal_inf::Ptr{Cdouble}
+    dual_inf::Ptr{Cdouble}
+    cs_inf::Ptr{Cdouble}
+    mu::Ptr{Cdouble}
+    reg_last::Ptr{Cdouble}
+    step_size::Ptr{Cdouble}
+    n_backward::Ptr{Cint}
+    n_sweeps::Ptr{Cint}
+    n_kkt::Ptr{Cint}
+    n_rollouts::Ptr{Cint}
+    x::Ptr{Cdouble}
+    u::Ptr{Cdouble}
+    outputs_on_device::Cint
+end
+
+"""
+    solve_queue!(prob, x1, controls; params, lower, upper, horizons) -> NamedTuple
+
+Streaming solve (`ipddp_solve_queue`): the Q = size(x1, 2) queued instances flow through the B resident slots of `prob`;
+Q may be much larger than B.  Arrays as in `solve!` with Q in place of B.  Returns the SolverData vectors, the work counters
+and the trajectories (states nx x N x Q, controls nu x (N-1) x Q).
+"""
+function solve_queue!(p::BatchProblem, x1::Matrix{Float64}, controls::Array{Float64,3}; params=nothing,
+                      lower::Matrix{Float64}, upper::Matrix{Float64}, horizons=nothing)
+    Q = size(x1, 2)
+    ints = [zeros(Cint, Q) for _ in 1:8]
+    dbls = [zeros(Cdouble, Q) for _ in 1:7]
+    x = zeros(p.nx, p.N, Q); u = zeros(p.nu, p.N - 1, Q)
+    GC.@preserve x1 controls params lower upper horizons ints dbls x u begin
+        q = Queue(Q, pointer(x1), pointer(controls), params === nothing ? C_NULL : pointer(params), pointer(lower),
+                  pointer(upper), horizons === nothing ? C_NULL : pointer(horizons), 0,
+                  pointer(ints[1]), pointer(ints[2]), pointer(ints[3]), pointer(ints[4]),
+                  pointer(dbls[1]), pointer(dbls[2]), pointer(dbls[3]), pointer(dbls[4]), pointer(dbls[5]), pointer(dbls[6]),
+                  pointer(dbls[7]), pointer(ints[5]), pointer(ints[6]), pointer(ints[7]), pointer(ints[8]),
+                  pointer(x), pointer(u), 0)
+        check(ccall((:ipddp_solve_queue, LIB), Cint, (Ptr{Cvoid}, Ref{Queue}), p.handle, Ref(q)), "ipddp_solve_queue")
+    end
+    return (status=ints[1], k=ints[2], j=ints[3], l=ints[4], objective=dbls[1], primal_inf=dbls[2], dual_inf=dbls[3],
+            cs_inf=dbls[4], μ=dbls[5], reg_last=dbls[6], step_size=dbls[7], n_backward=ints[5], n_sweeps=ints[6],
+            n_kkt=ints[7], n_rollouts=ints[8], states=x, controls=u)
+end
+
+# =====================================================================================================================
+# The reference's exported API (src/InteriorPointDDP.jl:29-45) on top of BatchProblem: same constructors, same call
+# sequence (`Solver(T, dynamics, objectives, constraints, bounds; options)`, `solve!(solver, x1, controls)`,
+# `get_trajectory(solver)`, results in `solver.data`).  The closures are traced symbolically exactly where the reference
+# traces them; instead of `eval`-ing Julia closures the derivatives are emitted through Symbolics' C target (codegen.jl),
+# compiled into a model plugin and registered with the library.  Additive extensions for batching: `batch`,
+# `num_parameter` (closures may take a trailing parameter vector `p`), per-instance `params` / bounds in `solve!`.
+# =====================================================================================================================
+
+"Dynamics(f, num_state, num_control; quasi_newton=false)  (reference src/dynamics.jl:15)"
+struct Dynamics
+    f::Function
+    num_next_state::Int
+    num_state::Int
+    num_control::Int
+    quasi_newton::Bool
+    user::Dict{String,Function}      # user-provided derivative closures (src/dynamics.jl:58-61)
+end
+Dynamics(f::Function, num_state::Int, num_control::Int; quasi_newton::Bool=false) =
+    Dynamics(f, num_state, num_state, num_control, quasi_newton, Dict{String,Function}())
+function Dynamics(f::Function, fx::Function, fu::Function, num_next_state::Int, num_state::Int, num_control::Int;
+                  vfxx=nothing, vfux=nothing, vfuu=nothing)
+    user = Dict{String,Function}("fx" => fx, "fu" => fu)
+    for (k, g) in (("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu))
+        g === nothing || (user[k] = g)
+    end
+    return Dynamics(f, num_next_state, num_state, num_control, false, user)
+end
+
+"Objective(f, num_state, num_control)  (reference src/objectives.jl:12)"
+struct Objective
+    f::Function
+    num_state::Int
+    num_control::Int
+end
+
+"Constraint(c, num_state, num_control; quasi_newton=false, indices_compl=nothing) | Constraint(num_state, num_control)  (reference src/constraints.jl:16,52)"
+struct Constraint
+    c::Union{Function,Nothing}
+    num_state::Int
+    num_control::Int
+    quasi_newton::Bool
+    indices_compl::Vector{Int}       # 1-based, as in the reference
+    user::Dict{String,Function}
+end
+Constraint(c::Function, num_state::Int, num_control::Int; quasi_newton::Bool=false, indices_compl=nothing) =
+    Constraint(c, num_state, num_control, quasi_newton, indices_compl === nothing ? Int[] : collect(Int, indices_compl),
+               Dict{String,Function}())
+Constraint(num_state::Int, num_control::Int) = Constraint(nothing, num_state, num_control, false, Int[], Dict{String,Function}())
+function Constraint(c::Function, cx::Function, cu::Function, num_constraint::Int, num_state::Int, num_control::Int;
+                    indices_compl=nothing, vcxx=nothing, vcux=nothing, vcuu=nothing)
+    user = Dict{String,Function}("cx" => cx, "cu" => cu)
+    for (k, g) in (("vcxx", vcxx), ("vcux", vcux), ("vcuu", vcuu))
+        g === nothing || (user[k] = g)
+    end
+    return Constraint(c, num_state, num_control, false, indices_compl === nothing ? Int[] : collect(Int, indices_compl), user)
+end
+
+"Bound(lower, upper) | Bound(T, num_control) | Bound(num_control, lower, upper)  (reference src/bounds.jl:12-26)"
+struct Bound{T}
+    lower::Vector{T}
+    upper::Vector{T}
+    indices_lower::Vector{Int}
+    indices_upper::Vector{Int}
+    num_lower::Int
+    num_upper::Int
+end
+function Bound(lower::Vector{T}, upper::Vector{T}) where T
+    il = [i for (i, b) in enumerate(lower) if !isinf(b)]
+    iu = [i for (i, b) in enumerate(upper) if !isinf(b)]
+    return Bound{T}(lower, upper, il, iu, length(il), length(iu))
+end
+Bound(T, num_control::Int) = Bound(-T(Inf) .* ones(T, num_control), T(Inf) .* ones(T, num_control))
+Bound(num_control::Int, lower::T, upper::T) where T = Bound(lower .* ones(T, num_control), upper .* ones(T, num_control))
+
+"Mirror of the reference's SolverData fields users read (src/data/solver.jl:8-33); vectors of length `batch` (scalars for batch = 1)."
+Base.@kwdef mutable struct SolverData
+    status = 0
+    k = 0
+    j = 0
+    l = 0
+    objective = 0.0
+    primal_inf = 0.0
+    dual_inf = 0.0
+    cs_inf = 0.0
+    μ = 0.0
+    reg_last = 0.0
+    step_size = 0.0
+    wall_time::Float64 = 0.0        # seconds: device time of the whole (batched) solve
+    solver_time::Float64 = 0.0      # wall_time minus derivative evaluation, as in src/solve.jl:86-87
+    fn_eval_time::Float64 = 0.0
+end
+
+mutable struct Solver{T}
+    problem::BatchProblem
+    data::SolverData
+    options::Options{T}
+    bound::Bound{T}
+    N::Int
+    batch::Int
+    num_parameter::Int
+end
+
+"""
+    Solver(T, dynamics, objectives, constraints, bounds=nothing; options=nothing, batch=1, num_parameter=0, name=nothing)
+
+Reference src/solver.jl:11-26.  The running stages must share one Dynamics / Objective / Constraint / Bound object and the
+terminal stage has num_control = 0 and no constraints (every reference experiment has this shape).
+"""
+function Solver(T, dynamics::Vector{Dynamics}, objectives::Vector{Objective}, constraints::Vector{Constraint},
+                bounds=nothing; options=nothing, batch::Int=1, num_parameter::Int=0, name=nothing, device::Int=0,
+                trace_capacity::Int=0)
+    T === Float64 || error("FP64 only (all reference experiments are Float64)")
+    N = length(objectives)
+    length(dynamics) + 1 == N == length(constraints) || error("need N-1 dynamics, N objectives, N constraints")
+    d, o, c, oN = dynamics[1], objectives[1], constraints[1], objectives[end]
+    all(x -> x === d, dynamics) && all(x -> x === o, objectives[1:end-1]) && all(x -> x === c, constraints[1:end-1]) ||
+        error("running stages must share one Dynamics / Objective / Constraint object")
+    (oN.num_control == 0 && constraints[end].c === nothing) || error("terminal stage: num_control = 0, no constraints")
+    bound = bounds === nothing ? Bound(T, d.num_control) : bounds[1]
+    opts = options === nothing ? Options{T}() : deepcopy(options)
+    user = merge(d.user, c.user)
+    lN = (x, args...) -> oN.f(x, T[], args...)
+    sm = trace(name === nothing ? "pending" : String(name), d.f, o.f, lN, c.c, d.num_state, d.num_control;
+               num_parameter=num_parameter, qn_dynamics=d.quasi_newton, qn_constraint=c.quasi_newton,
+               indices_compl=c.indices_compl, user=user)
+    if name === nothing     # the model's identity is its traced source
+        tag = "user_" * bytes2hex(sha256(emit_device(sm)))[1:12]
+        sm = StageModel(tag, sm.nx, sm.nu, sm.nc, sm.np, sm.f, sm.l, sm.lN, sm.c, sm.mats, sm.x, sm.u, sm.v, sm.lam, sm.p,
+                        sm.indices_compl)
+    end
+    load_model!(build_plugin(sm))
+    prob = BatchProblem(sm.name, batch, N; options=opts, device=device, indices_compl=Cint.(c.indices_compl .- 1),
+                        trace_capacity=trace_capacity)
+    return Solver{T}(prob, SolverData(), opts, bound, N, batch, num_parameter)
+end
+
+unbatch(v, batch) = batch == 1 ? v[1] : v
+
+function fill_data!(s::Solver)
+    p = s.problem
+    st = get_stats(p)
+    s.data = SolverData(status=unbatch(p.status, s.batch), k=unbatch(p.k, s.batch), j=unbatch(p.j, s.batch),
+                        l=unbatch(p.l, s.batch), objective=unbatch(p.objective, s.batch),
+                        primal_inf=unbatch(p.primal_inf, s.batch), dual_inf=unbatch(p.dual_inf, s.batch),
+                        cs_inf=unbatch(p.cs_inf, s.batch), μ=unbatch(p.μ, s.batch), reg_last=unbatch(p.reg_last, s.batch),
+                        step_size=unbatch(p.step_size, s.batch), wall_time=st.ms_total * 1e-3,
+                        solver_time=(st.ms_total - st.ms_derivs) * 1e-3, fn_eval_time=st.ms_derivs * 1e-3)
+    return s.data
+end
+
+"""
+    solve!(solver, x1, controls; params=nothing, lower=nothing, upper=nothing, horizons=nothing)
+
+Reference src/solve.jl:1-4.  Single instance: `x1::Vector{T}`, `controls::Vector{Vector{T}}` (N entries, the last one
+empty), as in the reference.  Batched: `x1` nx x B, `controls` nu x (N-1) x B, `params` np x B, bounds nu x B.
+"""
+function solve!(s::Solver{T}, x1::Vector{T}, controls::Vector{Vector{T}}; params=nothing, kw...) where T
+    u = reduce(hcat, controls[1:s.N-1])
+    return solve!(s, repeat(reshape(x1, :, 1), 1, s.batch), repeat(reshape(u, size(u, 1), size(u, 2), 1), 1, 1, s.batch);
+                  params=params === nothing ? nothing : repeat(reshape(params, :, 1), 1, s.batch), kw...)
+end
+function solve!(s::Solver{T}, x1::Matrix{T}, controls::Array{T,3}; params=nothing, lower=nothing, upper=nothing,
+                horizons=nothing) where T
+    lo = lower === nothing ? repeat(reshape(s.bound.lower, :, 1), 1, s.batch) : lower
+    up = upper === nothing ? repeat(reshape(s.bound.upper, :, 1), 1, s.batch) : upper
+    solve!(s.problem, x1, controls; params=params, lower=lo, upper=up, horizons=horizons)
+    return fill_data!(s)
+end
+"solve!(solver): warm start from the stored nominal trajectory (reference src/solve.jl:6-17)"
+solve!(s::Solver) = (solve!(s.problem); fill_data!(s))
+
+"get_trajectory(solver) -> (nominal_states, nominal_controls)  (reference src/solver.jl:46-48); batch = 1: vectors of per-stage vectors"
+function get_trajectory(s::Solver)
+    x, u = get_trajectory(s.problem)
+    s.batch == 1 || return x, u
+    return [x[:, t, 1] for t in 1:s.N], vcat([u[:, t, 1] for t in 1:s.N-1], [Float64[]])
 end
 
 end # module

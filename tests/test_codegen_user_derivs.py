@@ -51,3 +51,38 @@ def test_shape_check():
         assert "fx" in str(e)
     else:
         raise AssertionError("shape mismatch not detected")
+
+
+def test_per_object_quasi_newton_only_drops_that_objects_contractions():
+    """Dynamics(...; quasi_newton=true) leaves vfxx/vfux/vfuu at zero, Constraint(...; quasi_newton=true) leaves
+    vcxx/vcux/vcuu at zero (reference src/dynamics.jl:27-37,63-70, src/constraints.jl:76-83); the other object's terms
+    stay (src/backward_pass.jl:101-114 only looks at Options.quasi_newton)."""
+    md = workloads.get("concar")
+    full = generate.trace(md)
+    qd = generate.trace(dataclasses.replace(md, qn_dynamics=True))
+    qc = generate.trace(dataclasses.replace(md, qn_constraint=True))
+
+    def nonzero(bundle, names):
+        return {en.mat for (en, _slot) in generate._device_entries(bundle)[0] if en.mat in names}
+    vf, vc = {"vfxx", "vfux", "vfuu"}, {"vcxx", "vcux", "vcuu"}
+    assert nonzero(full["vf"], vf) and nonzero(full["derivs"], vc)
+    assert not nonzero(qd["vf"], vf) and nonzero(qd["derivs"], vc) == nonzero(full["derivs"], vc)
+    assert not nonzero(qc["derivs"], vc) and nonzero(qc["vf"], vf) == nonzero(full["vf"], vf)
+
+
+def test_model_identity_is_the_traced_source():
+    """Two Solvers share a compiled model exactly when their emitted device code agrees: a module-level global that a
+    closure reads is folded into the code at trace time, so changing it changes the model's digest (api.model_digest),
+    while a differently named but identical model has the same digest."""
+    from ipddp_b200 import api
+    md = workloads.get("double_integrator")
+    d0 = api.model_digest(md)
+    assert d0 == api.model_digest(dataclasses.replace(md, name="something_else"))
+    scale = {"dt": 0.01}
+    f1 = lambda x, u, p: [x[0] + scale["dt"] * x[1], x[1] + scale["dt"] * u[0]]
+    m1 = dataclasses.replace(md, f=f1)
+    a = api.model_digest(m1)
+    assert a == d0                                     # same code as the built-in closure
+    scale["dt"] = 0.02
+    assert api.model_digest(m1) != a                   # same closure object, different traced code
+    assert api.model_digest(dataclasses.replace(md, indices_compl=[0])) != d0

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import ipddp_b200  # noqa: F401,E402
-from ipddp_b200 import _lib, instances  # noqa: E402
+from ipddp_b200 import _lib, instances, results_io  # noqa: E402
 from ipddp_b200.batch import BatchSolver  # noqa: E402
 
 CLASSES = [("cartpole", "cartpole_friction"), ("acrobot", "acrobot_contact"), ("concar", "concar"),
@@ -40,12 +40,15 @@ def main():
         s.close()
         wall_ms = st.ms_total / n      # batch device time amortised per instance
         solver_ms = (st.ms_total - st.ms_derivs) / n
-        with open(os.path.join(args.out, fname + ".txt"), "w") as fh:
-            fh.write(" seed  iterations  status     objective           primal        wall (ms)   solver(ms)  \n")
-            for i in range(n):
-                fh.write(" %2s     %5s      %5s    %.8e    %.8e     %5.1f        %5.1f  \n" % (
-                    i + 1, int(r.k[i]), "true" if r.status[i] == 0 else "false", r.objective[i], r.primal_inf[i],
-                    wall_ms, solver_ms))
+        # the reference's writer format (experiments/ipddp2/cartpole_friction.jl:151-168), checked byte for byte against the
+        # reference's own tables by tests/test_results_io.py; the file parses with experiments/utils.jl's read_results
+        results_io.write_results(os.path.join(args.out, fname + ".txt"), np.arange(1, n + 1), r.k, r.status == 0, r.objective,
+                                 r.primal_inf, np.full(n, wall_ms), np.full(n, solver_ms))
+        back = results_io.read_results(os.path.join(args.out, fname + ".txt"))
+        assert back.iters == [int(x) for x in r.k] and back.status == [bool(x) for x in (r.status == 0)]
+        if b.p.shape[1] > 0:
+            os.makedirs(os.path.join(args.out, "params"), exist_ok=True)
+            results_io.write_params(os.path.join(args.out, "params", fname + ".txt"), b.p.tolist())
         same_it = int((r.k == g["iterations"]).sum())
         same_obj = int((np.abs(r.objective - g["objective"]) <= 1e-8 * np.maximum(1.0, np.abs(g["objective"]))).sum())
         both = int(((r.k == g["iterations"]) & (np.abs(r.objective - g["objective"]) <= 1e-8 * np.maximum(1.0, np.abs(g["objective"])))).sum())
