@@ -274,7 +274,7 @@ def main():
     agg = dict(ms_total=st.ms_total, ms_derivs=st.ms_derivs, ms_backward=st.ms_backward, ms_check=st.ms_check,
                ms_forward=st.ms_forward, kkt=st.sum_kkt, sweeps=st.sum_sweeps, rollouts=st.sum_rollouts,
                backward_calls=st.sum_backward, conv=st.n_converged, launches=st.launches, rounds=st.iterations,
-               active_rounds=st.n_active_rounds)
+               active_rounds=st.n_active_rounds, active_sq=st.sum_active_sq)
     status_d, k_d, prim_d = dq.oi[0], dq.oi[1], dq.od[1]
     conv_mask = status_d == 0
     ksum = float(k_d.double().sum().item())
@@ -478,7 +478,7 @@ def main():
                                  "inputs and outputs in HBM; e2e = wall clock around the same call with pinned HOST buffers; "
                                  "roofline/kernels/lockstep come from the per-kernel CUDA events of the `value` region itself"},
             "sequential": ({"value": conv_single / (ms_single * 1e-3), "ms_per_step": ms_single, "steps": 1,
-                            "rounds": single["rounds"], "mean_active_fraction": single["active_rounds"] / max(1, single["rounds"]) / S,
+                            "rounds": single["rounds"], "mean_active_fraction": single["active_rounds"] / max(1, single["rounds"]) / min(S, B),
                             "what": "ONE batch with nothing queued behind it: the lock-step tail of its slowest instances is exposed"}
                            if single else None),
             "converged_fraction": conv_all / (K * B * world), "mean_iterations": ksum_all / (K * B * world), "max_primal_inf": pr_max,
@@ -488,7 +488,10 @@ def main():
             "clocks": clocks,
             "roofline": roof_hbm, "roofline_fp64": roof_fp64, "kernels": kernels,
             "lockstep": {"rounds": agg["rounds"], "rounds_per_step": agg["rounds"] / K,
-                         "mean_active_fraction": agg["active_rounds"] / max(1, agg["rounds"]) / S},
+                         "mean_active_fraction": agg["active_rounds"] / max(1, agg["rounds"]) / S,
+                         "work_weighted_active_fraction": agg["active_sq"] / max(1, agg["active_rounds"]) / S,
+                         "note": "mean_active_fraction averages over rounds (the ~1000 nearly empty rounds of the final tail count "
+                                 "like full ones); work_weighted = the occupancy of the round the average instance-iteration ran in"},
             "cpu_baseline": cpu,
             "configs": cfg_lines,
         }

@@ -75,6 +75,8 @@ typedef struct ipddp_stats {
   long long sum_backward, sum_sweeps, sum_kkt, sum_rollouts, sum_deriv_stages; /* summed over instances */
   long long n_converged;       /* instances with status 0 */
   long long n_active_rounds;   /* sum over rounds of active instances (occupancy of the lock-step loop) */
+  double sum_active_sq;        /* sum over rounds of (active instances)^2: sum_active_sq / n_active_rounds = the round size
+                                  the average instance-iteration ran in (work-weighted occupancy) */
 } ipddp_stats;
 
 typedef struct ipddp_problem ipddp_problem;

@@ -49,7 +49,7 @@ class Stats(C.Structure):
         ("ms_derivs", C.c_double), ("ms_backward", C.c_double), ("ms_check", C.c_double), ("ms_forward", C.c_double),
         ("sum_backward", C.c_longlong), ("sum_sweeps", C.c_longlong), ("sum_kkt", C.c_longlong),
         ("sum_rollouts", C.c_longlong), ("sum_deriv_stages", C.c_longlong), ("n_converged", C.c_longlong),
-        ("n_active_rounds", C.c_longlong),
+        ("n_active_rounds", C.c_longlong), ("sum_active_sq", C.c_double),
     ]
 
 

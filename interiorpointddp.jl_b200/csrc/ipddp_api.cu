@@ -610,6 +610,7 @@ static int enqueue_round(ipddp_problem* h, const DevView& v, const ListView& lis
   h->st.launches += 4;
   h->st.iterations += 1;
   h->st.n_active_rounds += n;
+  h->st.sum_active_sq += (double)n * (double)n;
   return 0;
 }
 static int add_round_times(ipddp_problem* h) {
@@ -891,6 +892,7 @@ int ipddp_solve_many(ipddp_problem** hs, int n, int total_solves, int warm_start
         tot.iterations += h->st.iterations;
         tot.launches += h->st.launches;
         tot.n_active_rounds += h->st.n_active_rounds;
+        tot.sum_active_sq += h->st.sum_active_sq;
         add_counters(tot, h->h_si, h->v.B);
         finished++;
         if (cudaEventRecord(h->ev[7], h->stream) != cudaSuccess) { fail("cudaEventRecord"); return bail(); }

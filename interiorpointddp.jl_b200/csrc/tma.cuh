@@ -2,7 +2,7 @@
 // completion, for staging whole per-knot records ahead of the warp that consumes them.
 // Requirements of the instruction: 16-byte aligned source / destination, size a multiple of 16 bytes -- which is
 // why trajectory and gains records are padded to an even number of doubles (layout.cuh).
-// Under the CPU emulator (tests only) the copy happens synchronously at issue time and the barrier calls are no-ops,
+// Under the CPU emulator (tests only) the copy happens synchronously at issue time and the wait is a warp barrier,
 // so the staging logic (stage indices, phases, drain) is still exercised against the oracle.
 #pragma once
 #include "simt_compat.cuh"
@@ -41,7 +41,9 @@ inline void mbar_init(unsigned long long*, unsigned) {}
 inline void mbar_init_fence() {}
 inline void mbar_expect_tx(unsigned long long*, unsigned) {}
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
-inline void mbar_wait(unsigned long long*, unsigned) {}
+// the wait is a warp-level rendezvous in the emulator: the issuing lane's (synchronous) copy precedes its own wait in
+// program order, so no lane reads a stage before it was filled, whatever order the emulator runs the lanes in
+inline void mbar_wait(unsigned long long*, unsigned) { emu::yield_barrier(); }
 #endif
 
 }  // namespace ipk

@@ -140,6 +140,7 @@ Base.@kwdef mutable struct Stats
     sum_deriv_stages::Clonglong = 0
     n_converged::Clonglong = 0
     n_active_rounds::Clonglong = 0
+    sum_active_sq::Cdouble = 0.0
 end
 
 """
