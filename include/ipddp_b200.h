@@ -90,11 +90,30 @@ void ipddp_default_options(ipddp_options* opt);
 /* Model registry.  A model is the compiled counterpart of the reference's generated closures
  * (Dynamics/Objective/Constraint, src/dynamics.jl:15-47, src/objectives.jl:12-33,
  * src/constraints.jl:16-50).  Built-in: cartpole, acrobot, concar, concar_quad, pushing,
- * double_integrator.  ipddp_model_load registers a plugin .so produced by the code generator. */
+ * double_integrator, and the stage chain `ragged` (a test problem whose state grows from 2 to 3 and whose controls shrink
+ * from 3 to 2 along the horizon).  ipddp_model_load registers a plugin .so produced by the code generator. */
 int ipddp_num_models(void);
 const char* ipddp_model_name(int index);
 int ipddp_model_dims(const char* model, int* nx, int* nu, int* nc, int* np, int* tile_slots);
 int ipddp_model_load(const char* plugin_path);
+
+/* Stage chains -- horizons whose state and control sizes change from stage to stage (reference README.md:18,
+ * src/data/problem.jl:44-62: every buffer is sized per timestep, src/solver.jl:11-26 takes one Dynamics / Objective /
+ * Constraint / Bound per stage).  A chain model is compiled from up to 4 stage TYPES (each with its own nx, nu, nc and next
+ * state size nxn; the last type carries the terminal cost on nxt states); a problem assigns a type to each running stage:
+ *   ipddp_model_stages     the types of a model: arrays of nstage entries (a plain model has one type);
+ *   ipddp_set_stage_types  stage_types[N-1] of a problem (checked: stage t must map onto the state size of knot t+1), to
+ *                          be called before ipddp_set_inputs / ipddp_solve_queue when nstage > 1;
+ *   ipddp_set_stage_compl  indices_compl of one stage type (ipddp_problem_create's list belongs to type 0);
+ *   ipddp_stage_layout     per-knot sizes nx[N], nu[N], nc[N] (the terminal knot: nxt, 0, 0) next to ipddp_layout's offsets.
+ * Array shapes of a chain: every per-stage array is strided by the MAXIMUM over the types (ipddp_model_dims returns the
+ * maxima) and zero-padded: ubar [B][N-1][nu], lower/upper [B][nstage][nu] (one bound vector per stage type), x1 [B][nx],
+ * states [B][N][ns] with ns = max(nx, nxn, nxt) (= nx for a plain model), controls [B][N-1][nu].  Per-instance horizons
+ * are not available for chains. */
+int ipddp_model_stages(const char* model, int* nstage, int* nx, int* nu, int* nc, int* nxn, int* nxt);
+int ipddp_set_stage_types(ipddp_problem* h, const int* stage_types);
+int ipddp_set_stage_compl(ipddp_problem* h, int stage_type, const int* indices_compl, int n_compl);
+int ipddp_stage_layout(ipddp_problem* h, int* nx, int* nu, int* nc);
 
 /* Replaces Solver(T, dynamics, objectives, constraints, bounds; options) (src/solver.jl:11-26) and the
  * workspace constructors behind it (src/data/*.jl) for a batch of B instances with up to N knots.

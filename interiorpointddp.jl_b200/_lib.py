@@ -19,7 +19,8 @@ TRACE_NAMES = ["k", "j", "objective", "primal_inf", "dual_inf", "cs_inf", "mu", 
 EXPORTS = [
     "ipddp_abi_version", "ipddp_last_error", "ipddp_default_options", "ipddp_num_models", "ipddp_model_name",
     "ipddp_model_dims", "ipddp_model_load", "ipddp_problem_create", "ipddp_problem_destroy", "ipddp_set_options",
-    "ipddp_set_tuning", "ipddp_layout", "ipddp_set_inputs", "ipddp_set_inputs_device", "ipddp_solve", "ipddp_solve_many", "ipddp_solve_queue", "ipddp_set_stream",
+    "ipddp_set_tuning", "ipddp_layout", "ipddp_set_inputs", "ipddp_set_inputs_device", "ipddp_solve", "ipddp_solve_many", "ipddp_solve_queue", "ipddp_set_stream", "ipddp_model_stages", "ipddp_set_stage_types",
+    "ipddp_set_stage_compl", "ipddp_stage_layout",
     "ipddp_initialize",
     "ipddp_eval_derivatives", "ipddp_backward_pass", "ipddp_check", "ipddp_forward_pass", "ipddp_get_results",
     "ipddp_get_trajectory", "ipddp_get_duals", "ipddp_get_counters", "ipddp_get_array", "ipddp_get_trace",
@@ -97,6 +98,10 @@ class Lib:
         L.ipddp_solve.argtypes = [vp, C.c_int]
         L.ipddp_solve_queue.argtypes = [vp, C.POINTER(Queue)]
         L.ipddp_set_stream.argtypes = [vp, vp]
+        L.ipddp_model_stages.argtypes = [C.c_char_p, ip, ip, ip, ip, ip, ip]
+        L.ipddp_set_stage_types.argtypes = [vp, ip]
+        L.ipddp_set_stage_compl.argtypes = [vp, C.c_int, ip, C.c_int]
+        L.ipddp_stage_layout.argtypes = [vp, ip, ip, ip]
         L.ipddp_solve_many.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(Stats)]
         for f in ("ipddp_initialize", "ipddp_eval_derivatives", "ipddp_backward_pass", "ipddp_forward_pass"):
             getattr(L, f).argtypes = [vp]
@@ -133,6 +138,13 @@ class Lib:
 
     def models(self):
         return [self.L.ipddp_model_name(i).decode() for i in range(self.L.ipddp_num_models())]
+
+    def model_stages(self, model: str):
+        """(nstage, [(nx, nu, nc, nxn) per stage type], nxt) of a model; a plain model has one stage type."""
+        n, nxt = C.c_int(), C.c_int()
+        a = [(C.c_int * 4)() for _ in range(4)]
+        self.check(self.L.ipddp_model_stages(model.encode(), C.byref(n), a[0], a[1], a[2], a[3], C.byref(nxt)), "ipddp_model_stages")
+        return n.value, [tuple(int(x[k]) for x in a) for k in range(n.value)], nxt.value
 
     def model_dims(self, model: str):
         v = [C.c_int() for _ in range(5)]

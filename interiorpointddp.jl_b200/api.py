@@ -71,7 +71,6 @@ class Dynamics:
         self.user_derivs = {}
         if len(args) == 5 and callable(args[0]) and callable(args[1]):
             fx, fu, num_next_state, num_state, num_control = args
-            assert int(num_next_state) == int(num_state), "state dimension must be constant along the horizon"
             self.user_derivs = {"fx": _with_p(fx, 2), "fu": _with_p(fu, 2)}
             for k, fn in (("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu)):
                 if fn is not None:
@@ -203,6 +202,31 @@ def build_model_plugin(md: workloads.ModelDef, force: bool = False, bundles=None
     return so
 
 
+def build_chain_plugin(chain, all_bundles, force: bool = False) -> str:
+    """Plugin of a stage chain (several stage types, sizes that change along the horizon): one header with the stage
+    structs and the composite model (generate.emit_device_chain)."""
+    os.makedirs(PLUGIN_DIR, exist_ok=True)
+    inc = f'#include "{os.path.join(HERE, "csrc", "model_common.cuh")}"'
+    src = generate.emit_device_chain(chain, [generate.emit_device(md, b) for md, b in zip(chain.stages, all_bundles)])
+    src = src.replace('#include "../model_common.cuh"', inc)
+    from . import build as _b
+    tag = hashlib.sha256((src + _b.content_hash(_b._headers(), " ".join(_b.FLAGS))).encode()).hexdigest()[:12]
+    so = os.path.join(PLUGIN_DIR, f"{chain.name}_{tag}.so")
+    if os.path.exists(so) and not force:
+        return so
+    cuh = os.path.join(PLUGIN_DIR, f"{chain.name}_{tag}.cuh")
+    cu = os.path.join(PLUGIN_DIR, f"{chain.name}_{tag}.cu")
+    with open(cuh, "w") as fh:
+        fh.write(src)
+    with open(cu, "w") as fh:
+        fh.write(f'#include "{cuh}"\n#include "{os.path.join(HERE, "csrc", "model_register.cuh")}"\n'
+                 f'IPDDP_REGISTER_MODEL(Model_{chain.name}, ipddp_plugin_vtable)\n')
+    r = subprocess.run([_b.NVCC] + _b.FLAGS + ["-shared", cu, "-o", so], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for model plugin:\n" + r.stdout + r.stderr)
+    return so
+
+
 @dataclass
 class SolverData:
     """Mirror of reference SolverData (src/data/solver.jl:8-33) after a solve; arrays of length B
@@ -226,10 +250,12 @@ class SolverData:
 class Solver:
     """Solver(T, dynamics, objectives, constraints, bounds=nothing; options=nothing)  (reference src/solver.jl:11-26)
 
-    Batched extension: `batch` instances share the model; `num_parameter` runtime parameters per instance are
-    the trailing argument `p` of the closures.  This round supports horizons whose running stages 1..N-1 share one
-    Dynamics / Objective / Constraint / Bound object (as every reference experiment does) plus a terminal stage with
-    num_control = 0 and no constraints; per-instance horizons <= N are allowed."""
+    One Dynamics / Objective / Constraint / Bound per stage, as in the reference; the state and control sizes may change
+    along the horizon (reference README.md:18, src/data/problem.jl:44-62).  Stages built from the same objects form one
+    stage TYPE (one set of compiled device functions); a horizon may use up to 4 types.  The terminal stage has
+    num_control = 0 and no constraints.  Batched extension: `batch` instances share the model; `num_parameter` runtime
+    parameters per instance are the trailing argument `p` of the closures; per-instance horizons <= N are available when
+    all running stages are of one type."""
 
     def __init__(self, T, dynamics: List[Dynamics], objectives: List[Objective], constraints: List[Constraint],
                  bounds: Optional[List[Bound]] = None, options: Optional[_lib.Options] = None, batch: int = 1,
@@ -237,41 +263,63 @@ class Solver:
         assert T in (float, np.float64), "FP64 only (the reference experiments are all Float64)"
         N = len(objectives)
         assert len(dynamics) + 1 == N == len(constraints), "need N-1 dynamics, N objectives, N constraints"
-        d0, o0, c0 = dynamics[0], objectives[0], constraints[0]
-        if any(d._src is not d0._src for d in dynamics) or any(o._src is not o0._src for o in objectives[:-1]) \
-                or any(c._src is not c0._src for c in constraints[:-1]):
-            raise NotImplementedError("running stages must share one Dynamics/Objective/Constraint (see class docstring)")
         oN, cN = objectives[-1], constraints[-1]
         assert oN.num_control == 0 and cN.c is None, "terminal stage must have num_control = 0 and no constraints"
-        nx, nu = d0.num_state, d0.num_control
         if bounds is None:
-            bounds = [Bound(float, nu)] * (N - 1) + [Bound(float, 0)]
-        b0 = bounds[0]
-        if any(not (np.array_equal(b.lower, b0.lower) and np.array_equal(b.upper, b0.upper)) for b in bounds[:-1]):
-            raise NotImplementedError("running stages must share one Bound (per-instance bounds go through solve(..., lower=, upper=))")
-        self.N, self.nx, self.nu, self.batch, self.num_parameter = N, nx, nu, int(batch), int(num_parameter)
-        self.bound = b0
-        stage_f = o0.f
+            bounds = [Bound(float, d.num_control) for d in dynamics] + [Bound(float, 0)]
+        assert len(bounds) == N
+        # ---- stage types: running stages built from the same closures (and equal bounds) share one type
+        keys, types, stage_type = [], [], []
+        for t in range(N - 1):
+            d, o, c, bd = dynamics[t], objectives[t], constraints[t], bounds[t]
+            key = (id(d._src), id(o._src), id(c._src), d.quasi_newton, c.quasi_newton, tuple(c.indices_compl),
+                   bd.lower.tobytes(), bd.upper.tobytes())
+            if key not in keys:
+                keys.append(key)
+                types.append((d, o, c, bd))
+            stage_type.append(keys.index(key))
+        if len(types) > 4:
+            raise NotImplementedError("at most 4 distinct stage types per horizon")
+        last = stage_type[-1]           # the type of the last running stage carries the terminal cost: it goes last
+        order = [k for k in range(len(types)) if k != last] + [last]
+        types = [types[k] for k in order]
+        stage_type = [order.index(k) for k in stage_type]
+        self.stage_type = stage_type
+        self.N, self.batch, self.num_parameter = N, int(batch), int(num_parameter)
         term_f = _with_p(oN._src, 2)
-        cfun = c0.c if c0.c is not None else (lambda x, u, p: [])
-        md = workloads.ModelDef(
-            name="pending", nx=nx, nu=nu, np_=self.num_parameter, f=d0.f, stage_cost=stage_f,
-            term_cost=lambda x, p: term_f(x, [], p), c=cfun, lower=lambda p: list(b0.lower), upper=lambda p: list(b0.upper),
-            u_init=[0.0] * nu, dt=0.0, indices_compl=list(c0.indices_compl),
-            user_derivs={**d0.user_derivs, **c0.user_derivs}, user_dynamics=bool(d0.user_derivs),
-            user_constraint=bool(c0.user_derivs), qn_dynamics=d0.quasi_newton, qn_constraint=c0.quasi_newton)
+        mds = []
+        for k, (d, o, c, bd) in enumerate(types):
+            cfun = c.c if c.c is not None else (lambda x, u, p: [])
+            is_last = k == len(types) - 1
+            mds.append(workloads.ModelDef(
+                name=f"pending_s{k}", nx=d.num_state, nu=d.num_control, np_=self.num_parameter, f=d.f, stage_cost=o.f,
+                term_cost=(lambda x, p: term_f(x, [], p)) if is_last else (lambda x, p: 0.0 * x[0]), c=cfun,
+                lower=(lambda p, bd=bd: list(bd.lower)), upper=(lambda p, bd=bd: list(bd.upper)),
+                u_init=[0.0] * d.num_control, dt=0.0, indices_compl=list(c.indices_compl),
+                user_derivs={**d.user_derivs, **c.user_derivs}, user_dynamics=bool(d.user_derivs),
+                user_constraint=bool(c.user_derivs), qn_dynamics=d.quasi_newton, qn_constraint=c.quasi_newton,
+                nx_term=oN.num_state if is_last else None))
+        self.stage_defs = mds
+        self.bounds_by_type = [bd for (_, _, _, bd) in types]
+        self.bound = self.bounds_by_type[0]
+        self.lib = _lib.load()
         # The model's identity is the device code that was traced from the closures (plus its dimensions): globals and
         # closure cells the closures read are folded into that code at trace time, so two Solvers share a compiled model
         # exactly when their emitted sources agree.  A user-chosen `name` is bound to the source it was first built from
         # in this process; the same name with different code is rebuilt and re-registered (ipddp_model_load replaces it).
-        bundles = generate.trace(md)
-        digest = model_digest(md, bundles)
+        all_bundles = [generate.trace(md) for md in mds]
+        chain = len(mds) > 1 or all_bundles[0]["dyn"].outputs[0][1] != mds[0].nx or (oN.num_state != mds[0].nx)
+        digest = hashlib.sha256("|".join(model_digest(md, bd) for md, bd in zip(mds, all_bundles)).encode()).hexdigest()[:12]
         tag = name or ("user_" + digest)
-        md.name = tag
-        self.model_def = md
-        self.lib = _lib.load()
+        if chain:
+            for k, md in enumerate(mds):
+                md.name = f"{tag}_s{k}"
+            self.model_def = workloads.ChainDef(tag, mds)
+        else:
+            mds[0].name = tag
+            self.model_def = mds[0]
         if _loaded_models.get((id(self.lib), tag)) != digest:
-            so = build_model_plugin(md, bundles=bundles)
+            so = build_chain_plugin(self.model_def, all_bundles) if chain else build_model_plugin(mds[0], bundles=all_bundles[0])
             self.lib.check(self.lib.L.ipddp_model_load(so.encode()), "ipddp_model_load")
             _loaded_models[(id(self.lib), tag)] = digest
         # per-object quasi_newton only removes that object's contractions (ModelDef.qn_*); Options.quasi_newton is the
@@ -279,8 +327,9 @@ class Solver:
         self.options = _copy_options(options) if options is not None else self.lib.default_options()
         self.quasi_newton = bool(self.options.quasi_newton)
         self._bs = BatchSolver(tag, self.batch, N, options=self.options, device=device, trace_capacity=trace_capacity,
-                               indices_compl=c0.indices_compl, lib=self.lib)
-        self.nc = self._bs.nc
+                               indices_compl=mds[0].indices_compl, lib=self.lib)
+        self._bs.set_stage_types(stage_type, [md.indices_compl for md in mds])
+        self.nx, self.nu, self.nc = self._bs.nx, self._bs.nu, self._bs.nc      # maxima over the stage types
         self.data = SolverData()
 
     @classmethod
@@ -296,6 +345,8 @@ class Solver:
                                lib=self.lib)
         self.nc = self._bs.nc
         self.bound = None
+        self.bounds_by_type = None
+        self.stage_type = [0] * (N - 1)
         self.quasi_newton = False
         self.data = SolverData()
         return self
@@ -323,18 +374,31 @@ def solve(solver: Solver, x1=None, controls=None, params=None, lower=None, upper
         r = solver._bs.solve(warm_start=True)
         return solver._fill_data(r)
     x1 = np.asarray(x1, dtype=np.float64)
+    if x1.ndim == 1 and x1.size < nx:       # stage chain: the first stage may have fewer states than the largest one
+        x1 = np.concatenate([x1, np.zeros(nx - x1.size)])
     x1 = np.broadcast_to(x1.reshape(-1, nx), (B, nx))
     if isinstance(controls, (list, tuple)) and len(controls) == N and np.size(controls[-1]) == 0:
-        controls = np.stack([np.asarray(c, dtype=np.float64) for c in controls[:-1]])
+        # the reference's list of per-stage vectors (possibly of different lengths): padded to the largest control size
+        padded = np.zeros((N - 1, nu))
+        for t in range(N - 1):
+            c = np.asarray(controls[t], dtype=np.float64).reshape(-1)
+            padded[t, :c.size] = c
+        controls = padded
     controls = np.asarray(controls, dtype=np.float64)
     controls = np.broadcast_to(controls.reshape(-1, (N - 1) * nu), (B, (N - 1) * nu))
     p = None
     if solver.num_parameter > 0:
         p = np.broadcast_to(np.asarray(params, dtype=np.float64).reshape(-1, solver.num_parameter), (B, solver.num_parameter))
-    if lower is None and solver.bound is not None:
-        lower = solver.bound.lower
-    if upper is None and solver.bound is not None:
-        upper = solver.bound.upper
+    if solver.bounds_by_type is not None:   # one bound vector per stage type, padded with +-inf
+        def pad(vecs, fill):
+            out = np.full((len(vecs), nu), fill)
+            for k, v in enumerate(vecs):
+                out[k, :v.size] = v
+            return out.reshape(-1)
+        if lower is None:
+            lower = pad([bd.lower for bd in solver.bounds_by_type], -np.inf)
+        if upper is None:
+            upper = pad([bd.upper for bd in solver.bounds_by_type], np.inf)
     solver._bs.set_inputs(x1, controls, p, lower, upper, horizons)
     r = solver._bs.solve()
     return solver._fill_data(r)
@@ -345,5 +409,7 @@ def get_trajectory(solver: Solver):
     Single instance: lists of per-stage vectors like the reference; batched: arrays [B,N,nx], [B,N-1,nu]."""
     x, u = solver._bs.trajectory()
     if solver.batch == 1:
-        return [x[0, t] for t in range(solver.N)], [u[0, t] for t in range(solver.N - 1)] + [np.zeros(0)]
+        nxs, nus, _ = solver._bs.stage_layout()
+        return ([x[0, t, :nxs[t]] for t in range(solver.N)],
+                [u[0, t, :nus[t]] for t in range(solver.N - 1)] + [np.zeros(0)])
     return x, u

@@ -40,6 +40,9 @@ class BatchSolver:
         self.lib = lib or _lib.load()
         self.model, self.B, self.N = model, int(B), int(N)
         self.nx, self.nu, self.nc, self.np, self.tile_slots = self.lib.model_dims(model)
+        # stage chains: nx / nu / nc are the maxima over the stage types (array strides); ns = stride of the state outputs
+        self.nstage, self.stages, self.nxt = self.lib.model_stages(model)
+        self.ns = max([self.nxt] + [max(st[0], st[3]) for st in self.stages])
         self.options = options or self.lib.default_options()
         ic = np.ascontiguousarray(indices_compl if indices_compl is not None else [], dtype=np.int32)
         h = C.c_void_p()
@@ -67,12 +70,13 @@ class BatchSolver:
         B, N = self.B, self.N
         x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(B, self.nx)
         ubar = np.ascontiguousarray(ubar, dtype=np.float64).reshape(B, (N - 1) * self.nu)
+        nb = self.nstage * self.nu          # bounds per instance: one vector per stage type
         if lower is None:
-            lower = np.full((B, self.nu), -np.inf)
+            lower = np.full((B, nb), -np.inf)
         if upper is None:
-            upper = np.full((B, self.nu), np.inf)
-        lower = np.ascontiguousarray(np.broadcast_to(np.asarray(lower, dtype=np.float64), (B, self.nu)))
-        upper = np.ascontiguousarray(np.broadcast_to(np.asarray(upper, dtype=np.float64), (B, self.nu)))
+            upper = np.full((B, nb), np.inf)
+        lower = np.ascontiguousarray(np.broadcast_to(np.asarray(lower, dtype=np.float64).reshape(-1, nb), (B, nb)))
+        upper = np.ascontiguousarray(np.broadcast_to(np.asarray(upper, dtype=np.float64).reshape(-1, nb), (B, nb)))
         p = None
         if self.np > 0:
             p = np.ascontiguousarray(params, dtype=np.float64).reshape(B, self.np)
@@ -92,6 +96,22 @@ class BatchSolver:
     def set_batch(self, batch):
         self.set_inputs(batch.x1, batch.ubar, batch.p if self.np > 0 else None, batch.lower, batch.upper,
                         batch.horizons)
+
+    def set_stage_types(self, stage_types, indices_compl=None):
+        """Stage chains: the stage type of every running stage t = 0..N-2 (ipddp_set_stage_types) and, optionally, the
+        indices_compl of each stage type (list of lists, ipddp_set_stage_compl)."""
+        st = np.ascontiguousarray(stage_types, dtype=np.int32).reshape(self.N - 1)
+        self.lib.check(self.lib.L.ipddp_set_stage_types(self.h, iptr(st)), "ipddp_set_stage_types")
+        for k, ic in enumerate(indices_compl or []):
+            a = np.ascontiguousarray(ic, dtype=np.int32)
+            self.lib.check(self.lib.L.ipddp_set_stage_compl(self.h, k, iptr(a) if a.size else None, int(a.size)),
+                           "ipddp_set_stage_compl")
+
+    def stage_layout(self):
+        """per-knot sizes (nx[N], nu[N], nc[N]) of the problem (ipddp_stage_layout)"""
+        a = [np.zeros(self.N, dtype=np.int32) for _ in range(3)]
+        self.lib.check(self.lib.L.ipddp_stage_layout(self.h, *[iptr(x) for x in a]), "ipddp_stage_layout")
+        return tuple(a)
 
     def set_tuning(self, key: str, value: int):
         """Execution tuning that never changes results (see ipddp_set_tuning)."""
@@ -113,16 +133,17 @@ class BatchSolver:
         x1 = np.ascontiguousarray(x1, dtype=np.float64).reshape(-1, self.nx)
         Q = x1.shape[0]
         ubar = np.ascontiguousarray(ubar, dtype=np.float64).reshape(Q, (N - 1) * self.nu)
-        lower = np.full((Q, self.nu), -np.inf) if lower is None else lower
-        upper = np.full((Q, self.nu), np.inf) if upper is None else upper
-        lower = np.ascontiguousarray(np.broadcast_to(np.asarray(lower, dtype=np.float64), (Q, self.nu)))
-        upper = np.ascontiguousarray(np.broadcast_to(np.asarray(upper, dtype=np.float64), (Q, self.nu)))
+        nb = self.nstage * self.nu
+        lower = np.full((Q, nb), -np.inf) if lower is None else lower
+        upper = np.full((Q, nb), np.inf) if upper is None else upper
+        lower = np.ascontiguousarray(np.broadcast_to(np.asarray(lower, dtype=np.float64).reshape(-1, nb), (Q, nb)))
+        upper = np.ascontiguousarray(np.broadcast_to(np.asarray(upper, dtype=np.float64).reshape(-1, nb), (Q, nb)))
         p = np.ascontiguousarray(params, dtype=np.float64).reshape(Q, self.np) if self.np > 0 else None
         hz = np.ascontiguousarray(horizons, dtype=np.int32).reshape(Q) if horizons is not None else None
         ints = [np.zeros(Q, dtype=np.int32) for _ in range(4)]
         dbl = [np.zeros(Q) for _ in range(7)]
         cnt = [np.zeros(Q, dtype=np.int32) for _ in range(4)]
-        x = np.zeros((Q, N, self.nx)) if want_traj else None
+        x = np.zeros((Q, N, self.ns)) if want_traj else None
         u = np.zeros((Q, N - 1, self.nu)) if want_traj else None
         q = make_queue(Q, x1, ubar, p, lower, upper, hz, ints + dbl + cnt, x, u)
         self.lib.check(self.lib.L.ipddp_solve_queue(self.h, C.byref(q)), "ipddp_solve_queue")
@@ -156,7 +177,7 @@ class BatchSolver:
 
     def trajectory(self):
         """get_trajectory(solver): nominal states [B,N,nx] and controls [B,N-1,nu]."""
-        x = np.zeros((self.B, self.N, self.nx))
+        x = np.zeros((self.B, self.N, self.ns))
         u = np.zeros((self.B, self.N - 1, self.nu))
         self.lib.check(self.lib.L.ipddp_get_trajectory(self.h, dptr(x), dptr(u)), "ipddp_get_trajectory")
         return x, u
@@ -165,7 +186,7 @@ class BatchSolver:
         phi = np.zeros((self.B, self.N - 1, self.nc))
         zl = np.zeros((self.B, self.N - 1, self.nu))
         zu = np.zeros((self.B, self.N - 1, self.nu))
-        lam = np.zeros((self.B, self.N, self.nx))
+        lam = np.zeros((self.B, self.N, self.ns))
         self.lib.check(self.lib.L.ipddp_get_duals(self.h, dptr(phi), dptr(zl), dptr(zu), dptr(lam)), "ipddp_get_duals")
         return phi, zl, zu, lam
 

@@ -135,7 +135,9 @@ def trace(md: workloads.ModelDef) -> Dict[str, Bundle]:
     c_ = sp.Matrix(md.c(x, u, p)) if md.nc > 0 else sp.zeros(0, 1)
     nc = c_.rows
     l_ = sp.sympify(md.stage_cost(x, u, p))
-    lN_ = sp.sympify(md.term_cost(x, p))
+    nxt = int(getattr(md, "nx_term", None) or nx)      # the terminal cost may see a state of another size (stage chains)
+    xt = x if nxt == nx else _sym("x", nxt)
+    lN_ = sp.sympify(md.term_cost(xt, p))
     v = _sym("v", max(nc, 1))
     lam = _sym("v", nxn)
     X, U = sp.Matrix(x), sp.Matrix(u)
@@ -179,7 +181,7 @@ def trace(md: workloads.ModelDef) -> Dict[str, Bundle]:
     cx = pick("cx", nc, nx, (x, u, p), lambda: c_.jacobian(X), ucon)
     cu = pick("cu", nc, nu, (x, u, p), lambda: c_.jacobian(U), ucon)
     vv = sp.Matrix(v[:nc])
-    if qnc:   # quasi-Newton constraint object: its contraction caches stay zero
+    if qnc or nc == 0:   # quasi-Newton constraint object (or no constraints): the contraction caches stay zero
         vcxx, vcux, vcuu = sp.zeros(nx, nx), sp.zeros(nu, nx), sp.zeros(nu, nu)
     else:
         vcxx = pick("vcxx", nx, nx, (x, u, v[:nc], p), lambda: (cx.T * vv).jacobian(X), ucon)
@@ -198,8 +200,9 @@ def trace(md: workloads.ModelDef) -> Dict[str, Bundle]:
         vfuu = pick("vfuu", nu, nu, (x, u, lam, p), lambda: (Jfu.T * lv).jacobian(U), udyn)
     b["vf"] = _make_bundle("vf", ["x", "u", "v", "p"], [("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu)])
 
-    lNx = sp.Matrix([lN_]).jacobian(X).T
-    b["derivsN"] = _make_bundle("derivsN", ["x", "p"], [("lx", lNx), ("lxx", lNx.jacobian(X))])
+    XT = sp.Matrix(xt)
+    lNx = sp.Matrix([lN_]).jacobian(XT).T
+    b["derivsN"] = _make_bundle("derivsN", ["x", "p"], [("lx", lNx), ("lxx", lNx.jacobian(XT))])
     return b
 
 
@@ -228,8 +231,9 @@ def emit_oracle(md, bundles) -> str:
         for en in b.entries:
             o.append(f"  {en.mat}[{en.i + en.j * rows[en.mat]}] = {en.text};\n")
         o.append("}\n")
+    nxt = bundles["derivsN"].outputs[0][1]
     o.append(f"static const OracleModel model = {{\"{n}\", {md.nx}, {md.nu}, {nc}, {nxn}, {md.np_}, "
-             f"dyn, cost, costN, con, derivs, vf, derivsN}};\n")
+             f"dyn, cost, costN, con, derivs, vf, derivsN, {nxt}}};\n")
     o.append("}\n")
     return "".join(o)
 
@@ -302,7 +306,13 @@ def emit_device(md, bundles) -> str:
 
     o.append(f"struct Model_{n} {{\n")
     o.append(f"  static constexpr const char* NAME = \"{n}\";\n")
+    nxt = bundles["derivsN"].outputs[0][1]
     o.append(f"  static constexpr int NX = {nx}, NU = {nu}, NC = {nc}, NXN = {nxn}, NP = {md.np_};\n")
+    o.append(f"  static constexpr int NXT = {nxt};   // state size the terminal cost (costN / derivsN) is evaluated on\n")
+    o.append(f"  // a plain model is a chain of one stage type (see ipk::for_stage, model_common.cuh)\n")
+    o.append(f"  static constexpr int NSTAGE = 1;\n")
+    o.append(f"  template <int I> using Stage = Model_{n};\n")
+    o.append(f"  using Terminal = Model_{n};\n")
     o.append(f"  static constexpr int NTBL = {len(all_entries)}, NCONST = {len(all_consts)};\n")
     o.append(f"  static constexpr int D_NSLOT = {nslots['D']}, VF_NSLOT = {nslots['VF']}, DN_NSLOT = {nslots['DN']};\n")
     for (prefix, m, off, cnt) in tbl_defs:
@@ -361,14 +371,60 @@ def emit_device(md, bundles) -> str:
     return "".join(o)
 
 
+def emit_device_chain(chain, stage_sources) -> str:
+    """One header for a chain of stage types (state / control sizes that change along the horizon): the stage structs
+    `Model_<chain>_s<i>` as emit_device writes them, plus the composite `Model_<chain>` the kernels are instantiated with.
+    The composite carries the MAXIMA over the stage types under the usual names (NX, NU, NC, D_NSLOT, ...): they size every
+    buffer and stride; the per-knot arithmetic is instantiated per stage type (ipk::for_stage)."""
+    n = chain.name
+    o = [f"// GENERATED by interiorpointddp.jl_b200/codegen/generate.py -- do not edit.\n"
+         f"// Stage chain '{n}': {chain.doc}\n#pragma once\n"]
+    for src in stage_sources:
+        o.append(src.replace("#pragma once\n", ""))
+    S = [f"Model_{md.name}" for md in chain.stages]
+    mx = lambda field: "ipk::cmax(" + ", ".join(f"{s}::{field}" for s in S) + ")"
+    o.append(f"struct Model_{n} {{\n")
+    o.append(f"  static constexpr const char* NAME = \"{n}\";\n")
+    o.append(f"  static constexpr int NSTAGE = {len(S)};\n")
+    o.append(f"  template <int I> using Stage = typename ipk::TypeAt<I, {', '.join(S)}>::type;\n")
+    o.append(f"  using Terminal = {S[-1]};\n")
+    for f_ in ("NX", "NU", "NC", "NXN", "NP", "D_NSLOT", "VF_NSLOT", "FU_NC"):
+        o.append(f"  static constexpr int {f_} = {mx(f_)};\n")
+    o.append(f"  static constexpr int NXT = Terminal::NXT, DN_NSLOT = Terminal::DN_NSLOT;\n")
+    o.append("};\n")
+    return "".join(o)
+
+
+def emit_oracle_chain(chain, stage_sources) -> str:
+    n = chain.name
+    o = [f"// GENERATED by interiorpointddp.jl_b200/codegen/generate.py -- do not edit.\n"
+         f"// Oracle models of the stage types of chain '{n}'.\n#pragma once\n"]
+    for src in stage_sources:
+        o.append(src.replace("#pragma once\n", ""))
+    return "".join(o)
+
+
+def generate_chain(chain, oracle_dir, device_dir):
+    bundles = [trace(md) for md in chain.stages]
+    with open(os.path.join(oracle_dir, f"{chain.name}.h"), "w") as fh:
+        fh.write(emit_oracle_chain(chain, [emit_oracle(md, b) for md, b in zip(chain.stages, bundles)]))
+    with open(os.path.join(device_dir, f"{chain.name}.cuh"), "w") as fh:
+        fh.write(emit_device_chain(chain, [emit_device(md, b) for md, b in zip(chain.stages, bundles)]))
+    print(f"chain {chain.name}: " + ", ".join(f"{md.name}(nx={md.nx} nu={md.nu} nc={b['con'].outputs[0][1]} -> {b['dyn'].outputs[0][1]})"
+                                              for md, b in zip(chain.stages, bundles)))
+
+
 def generate_all(names=None, oracle_dir=None, device_dir=None):
     root = os.path.dirname(os.path.dirname(HERE))
     oracle_dir = oracle_dir or os.path.join(root, "oracle", "models_gen")
     device_dir = device_dir or os.path.join(HERE, "..", "csrc", "models_gen")
     os.makedirs(oracle_dir, exist_ok=True)
     os.makedirs(device_dir, exist_ok=True)
-    names = names or list(workloads.WORKLOADS)
+    names = names or (list(workloads.WORKLOADS) + list(workloads.CHAINS))
     for nm in names:
+        if nm in workloads.CHAINS:
+            generate_chain(workloads.get_chain(nm), oracle_dir, device_dir)
+            continue
         md = workloads.get(nm)
         b = trace(md)
         with open(os.path.join(oracle_dir, f"{nm}.h"), "w") as fh:

@@ -53,6 +53,9 @@ class ModelDef:
     # object's terms are still added unless Options.quasi_newton is set (src/backward_pass.jl:101-114)
     qn_dynamics: bool = False
     qn_constraint: bool = False
+    # dimension of the state the terminal cost is evaluated on (None = nx).  In a chain of stage types the terminal cost
+    # lives with the LAST stage type and sees that stage's next state (num_next_state may differ from num_state).
+    nx_term: object = None
 
     @property
     def nc(self) -> int:
@@ -352,6 +355,67 @@ def _double_integrator() -> ModelDef:
         name="double_integrator", nx=nx, nu=nu, np_=0, f=f, stage_cost=stage, term_cost=term, c=c,
         lower=lambda p: [-lim, 0.0, 0.0], upper=lambda p: [lim, INF, INF],
         u_init=[0.01] * nu, dt=dt, doc="no parameters")
+
+
+# --------------------------------------------------------------------------------------
+# A horizon whose state and control sizes change along the way (reference README.md:18, src/data/problem.jl:44-62:
+# every buffer is sized per timestep).  Synthetic test chain of three stage types built around the double integrator:
+#   s0  (nx 2, nu 3, nc 1) -> 2   the double integrator with its absolute-work slacks
+#   s1  (nx 2, nu 3, nc 1) -> 3   same controls, the dynamics adds a third state (running integral of the position)
+#   s2  (nx 3, nu 2, nc 0) -> 3   fewer controls, no constraint, a cost on the integral state; carries the terminal cost
+# --------------------------------------------------------------------------------------
+@dataclass
+class ChainDef:
+    name: str
+    stages: List[ModelDef]            # the stage types; stages[-1] carries the terminal cost (nx_term)
+    doc: str = ""
+
+    def stage_types(self, N: int) -> List[int]:
+        """stage type of the running stages t = 0..N-2 of a horizon with N knots (the canonical test layout)"""
+        n1 = (N - 1) // 2
+        return [0] * n1 + [1] + [2] * (N - 2 - n1)
+
+
+def _ragged_chain() -> ChainDef:
+    dt = 0.01
+    lim = 10.0
+
+    def f0(x, u, p):
+        return [x[0] + dt * x[1], x[1] + dt * u[0]]
+
+    def f1(x, u, p):
+        return [x[0] + dt * x[1], x[1] + dt * u[0], dt * x[0]]
+
+    def f2(x, u, p):
+        return [x[0] + dt * x[1], x[1] + dt * u[0], x[2] + dt * x[0]]
+
+    def stage01(x, u, p):
+        return dt * (u[1] + u[2])
+
+    def stage2(x, u, p):
+        return dt * (0.5 * u[0] * u[0] + u[1]) + 0.1 * dt * x[2] * x[2]
+
+    def c01(x, u, p):
+        return [u[1] - u[2] - u[0] * x[1]]
+
+    def term(x, p):
+        return 500.0 * ((x[0] - 1.0) * (x[0] - 1.0) + x[1] * x[1]) + 5.0 * x[2] * x[2]
+
+    zero_term = lambda x, p: 0.0 * x[0]
+    s0 = ModelDef(name="ragged_s0", nx=2, nu=3, np_=0, f=f0, stage_cost=stage01, term_cost=zero_term, c=c01,
+                  lower=lambda p: [-lim, 0.0, 0.0], upper=lambda p: [lim, INF, INF], u_init=[0.01] * 3, dt=dt)
+    s1 = ModelDef(name="ragged_s1", nx=2, nu=3, np_=0, f=f1, stage_cost=stage01, term_cost=zero_term, c=c01,
+                  lower=lambda p: [-lim, 0.0, 0.0], upper=lambda p: [lim, INF, INF], u_init=[0.01] * 3, dt=dt)
+    s2 = ModelDef(name="ragged_s2", nx=3, nu=2, np_=0, f=f2, stage_cost=stage2, term_cost=term, c=lambda x, u, p: [],
+                  lower=lambda p: [-lim, 0.0], upper=lambda p: [lim, INF], u_init=[0.01] * 2, dt=dt, nx_term=3)
+    return ChainDef("ragged", [s0, s1, s2], doc="double integrator whose state grows from 2 to 3 and whose controls shrink from 3 to 2")
+
+
+CHAINS = {"ragged": _ragged_chain}
+
+
+def get_chain(name: str) -> ChainDef:
+    return CHAINS[name]()
 
 
 WORKLOADS = {

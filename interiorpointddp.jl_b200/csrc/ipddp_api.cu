@@ -32,6 +32,7 @@ const ModelVTable* ipddp_vtable_concar();
 const ModelVTable* ipddp_vtable_concar_quad();
 const ModelVTable* ipddp_vtable_pushing();
 const ModelVTable* ipddp_vtable_double_integrator();
+const ModelVTable* ipddp_vtable_ragged();
 }
 
 namespace {
@@ -51,7 +52,8 @@ int fail(const std::string& m) { g_err = m; return -1; }
 std::vector<const ModelVTable*>& registry() {
   static std::vector<const ModelVTable*> r = {ipddp_vtable_cartpole(),    ipddp_vtable_acrobot(),
                                               ipddp_vtable_concar(),      ipddp_vtable_concar_quad(),
-                                              ipddp_vtable_pushing(),     ipddp_vtable_double_integrator()};
+                                              ipddp_vtable_pushing(),     ipddp_vtable_double_integrator(),
+                                              ipddp_vtable_ragged()};
   return r;
 }
 const ModelVTable* find(const char* name) {
@@ -60,8 +62,31 @@ const ModelVTable* find(const char* name) {
   return nullptr;
 }
 
-// gather one field of the trajectory records into a dense [B][nst][dim] array
-__global__ void k_gather(DevView v, int use_cur, int off, int dim, int nst, double* out) {
+// Field `f` (0 x, 1 u, 2 c, 3 il, 4 iu, 5 phi, 6 zl, 7 zu) of knot t's record of an instance whose knot has nx / nu / nc
+// entries: offset inside the record and number of entries.
+__device__ __forceinline__ void field_of(int f, int nx, int nu, int nc, int* off, int* dim) {
+  const int oU = nx, oC = oU + nu, oIL = oC + nc, oIU = oIL + nu, oPHI = oIU + nu, oZL = oPHI + nc, oZU = oZL + nu;
+  switch (f) {
+    case 0: *off = 0; *dim = nx; break;
+    case 1: *off = oU; *dim = nu; break;
+    case 2: *off = oC; *dim = nc; break;
+    case 3: *off = oIL; *dim = nu; break;
+    case 4: *off = oIU; *dim = nu; break;
+    case 5: *off = oPHI; *dim = nc; break;
+    case 6: *off = oZL; *dim = nu; break;
+    default: *off = oZU; *dim = nu; break;
+  }
+}
+// sizes of knot t of instance b: its stage type's (nx, nu, nc); the terminal knot carries nxt states only
+__device__ __forceinline__ void knot_dims(const DevView& v, int t, int Nb, int* nx, int* nu, int* nc) {
+  if (t >= Nb - 1) { *nx = v.nxt; *nu = 0; *nc = 0; return; }
+  const int k = v.type_of(t);
+  *nx = v.snx[k]; *nu = v.snu[k]; *nc = v.snc[k];
+}
+
+// gather one field of the trajectory records into a dense [B][nst][dim] array (dim = the largest size of the field over
+// the stage types; entries a knot does not have, and knots beyond an instance's horizon, are zero)
+__global__ void k_gather(DevView v, int use_cur, int field, int dim, int nst, double* out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)v.B * nst * dim;
   if (idx >= total) return;
@@ -69,8 +94,15 @@ __global__ void k_gather(DevView v, int use_cur, int off, int dim, int nst, doub
   const int t = (int)((idx / dim) % nst);
   const int b = (int)(idx / ((long long)dim * nst));
   const int set = use_cur ? 1 - v.nomsel[b] : v.nomsel[b];
-  const int lim = off == 0 ? v.horizon[b] : v.horizon[b] - 1;   // x on every knot, everything else on the running stages
-  out[idx] = (t < lim) ? v.rec(set, b, t)[off + i] : 0.0;
+  const int Nb = v.horizon[b];
+  double val = 0.0;
+  if (t < Nb) {
+    int nx, nu, nc, off, n;
+    knot_dims(v, t, Nb, &nx, &nu, &nc);
+    field_of(field, nx, nu, nc, &off, &n);
+    if (i < n) val = v.rec(set, b, t)[off + i];
+  }
+  out[idx] = val;
 }
 
 __global__ void k_fp64_peak(double* out, int iters) {
@@ -148,17 +180,21 @@ __global__ void k_retire(DevView v, QueueView q, const int* done, int n) {
   const int Nb = v.horizon[b];
   const double* r0 = v.rec(v.nomsel[b], b, 0);
   if (q.x) {
-    double* xo = q.x + i * (size_t)v.N * v.nx;
-    for (int e = threadIdx.x; e < v.N * v.nx; e += blockDim.x) {
-      const int t = e / v.nx, c = e - t * v.nx;
-      xo[e] = t < Nb ? r0[(size_t)t * v.TR + c] : 0.0;
+    double* xo = q.x + i * (size_t)v.N * v.ns;
+    for (int e = threadIdx.x; e < v.N * v.ns; e += blockDim.x) {
+      const int t = e / v.ns, c = e - t * v.ns;
+      int nx = 0, nu = 0, nc = 0;
+      if (t < Nb) knot_dims(v, t, Nb, &nx, &nu, &nc);
+      xo[e] = c < nx ? r0[(size_t)t * v.TR + c] : 0.0;
     }
   }
   if (q.u) {
     double* uo = q.u + i * (size_t)(v.N - 1) * v.nu;
     for (int e = threadIdx.x; e < (v.N - 1) * v.nu; e += blockDim.x) {
       const int t = e / v.nu, c = e - t * v.nu;
-      uo[e] = t < Nb - 1 ? r0[(size_t)t * v.TR + v.nx + c] : 0.0;
+      int nx = 0, nu = 0, nc = 0;
+      if (t < Nb - 1) knot_dims(v, t, Nb, &nx, &nu, &nc);
+      uo[e] = c < nu ? r0[(size_t)t * v.TR + nx + c] : 0.0;
     }
   }
 }
@@ -209,7 +245,9 @@ struct ipddp_problem {
   bool inputs_set = false;
   int spec_cap = 0;              // instances the speculative-forward record pool (DevView::spec_traj) was sized for
   int bw_spec_cap = 0;           // instances the speculative-backward output pool (DevView::spec_bw) was sized for
-  size_t bw_pool_doubles() const { return (size_t)(v.N - 1) * (v.G + v.nu) + (size_t)v.N * v.nx; }
+  size_t bw_pool_doubles() const { return (size_t)(v.N - 1) * (v.G + v.nu) + (size_t)v.N * v.ns; }
+  unsigned char* d_stage_type = nullptr;   // stage chains: [N-1] stage type per running stage
+  bool stages_set = false;
   cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   ipddp_stats st;
 
@@ -332,6 +370,8 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   DevView& v = h->v;
   memset(&v, 0, sizeof(v));
   v.B = B; v.N = N; v.nx = vt->nx; v.nu = vt->nu; v.nc = vt->nc; v.np = vt->np;
+  v.nstage = vt->nstage; v.nxt = vt->nxt; v.ns = vt->ns;
+  for (int k = 0; k < MAX_STAGE_TYPES; ++k) { v.snx[k] = vt->snx[k]; v.snu[k] = vt->snu[k]; v.snc[k] = vt->snc[k]; }
   v.TR = (vt->nx + 5 * vt->nu + 2 * vt->nc + 1) & ~1;                  // strides padded to an even number of doubles
   v.G = ((vt->nu + vt->nc + 2 * vt->nu) * (vt->nx + 1) + 1) & ~1;
   if (opt) v.opt = *opt; else ipddp_default_options(&v.opt);
@@ -342,22 +382,23 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   if ((long long)vt->smem_merit_spec(N) > (long long)optin) v.fw_spec_max = 0;   // long horizons: bulk line search only
   v.n_compl = (indices_compl && n_compl > 0) ? n_compl : 0;
   for (int q = 0; q < v.n_compl; ++q) {
-    if (indices_compl[q] < 0 || indices_compl[q] >= vt->nc) { delete h; return fail("indices_compl out of range"); }
-    v.compl_mask |= 1ull << indices_compl[q];
+    if (indices_compl[q] < 0 || indices_compl[q] >= vt->snc[0]) { delete h; return fail("indices_compl out of range"); }
+    v.compl_mask[0] |= 1ull << indices_compl[q];     // stage type 0; the other types of a chain: ipddp_set_stage_compl
   }
   const size_t np1 = vt->np > 0 ? vt->np : 1;
   int rc = 0;
   rc |= h->alloc(&h->d_compl, (size_t)v.n_compl);
   rc |= h->alloc(&h->d_p, (size_t)B * np1);
-  rc |= h->alloc(&h->d_lower, (size_t)B * vt->nu);
-  rc |= h->alloc(&h->d_upper, (size_t)B * vt->nu);
+  rc |= h->alloc(&h->d_lower, (size_t)B * vt->nstage * vt->nu);
+  rc |= h->alloc(&h->d_upper, (size_t)B * vt->nstage * vt->nu);
+  if (vt->nstage > 1) rc |= h->alloc(&h->d_stage_type, (size_t)(N - 1));
   rc |= h->alloc(&h->d_x1, (size_t)B * vt->nx);
   rc |= h->alloc(&h->d_ubar, (size_t)B * (N - 1) * vt->nu);
   rc |= h->alloc(&h->d_horizon, (size_t)B);
   rc |= h->alloc(&v.traj, (size_t)2 * B * N * v.TR);
   rc |= h->alloc(&v.nomsel, (size_t)B);
   rc |= h->alloc(&v.inst_of, (size_t)B);
-  rc |= h->alloc(&v.lam, (size_t)B * N * vt->nx);
+  rc |= h->alloc(&v.lam, (size_t)B * N * vt->ns);
   rc |= h->alloc(&v.tile, (size_t)B * (vt->d_nslot > 0 ? vt->d_nslot : 1) * N);
   rc |= h->alloc(&v.tileN, (size_t)B * (vt->dn_nslot > 0 ? vt->dn_nslot : 1));
   rc |= h->alloc(&v.gains, (size_t)B * (N - 1) * v.G);
@@ -381,6 +422,8 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   if (rc != 0) { ipddp_problem_destroy(h); return -1; }
   v.compl_idx = h->d_compl; v.p = h->d_p; v.lower = h->d_lower; v.upper = h->d_upper; v.x1 = h->d_x1;
   v.ubar = h->d_ubar; v.horizon = h->d_horizon;
+  v.stage_type = h->d_stage_type;      // NULL for a plain model
+  h->stages_set = vt->nstage == 1;
   auto finish = [&]() -> int {   // anything failing from here on releases the half-built handle
     if (v.n_compl) CK(cudaMemcpy(h->d_compl, indices_compl, v.n_compl * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemset(v.traj, 0, (size_t)2 * B * N * v.TR * sizeof(double)));
@@ -432,6 +475,73 @@ int ipddp_set_stream(ipddp_problem* h, void* cuda_stream) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+int ipddp_model_stages(const char* model, int* nstage, int* nx, int* nu, int* nc, int* nxn, int* nxt) {
+  const ModelVTable* m = model ? find(model) : nullptr;
+  if (!m) return fail(std::string("unknown model ") + (model ? model : "(null)"));
+  if (nstage) *nstage = m->nstage;
+  if (nxt) *nxt = m->nxt;
+  for (int k = 0; k < m->nstage; ++k) {
+    if (nx) nx[k] = m->snx[k];
+    if (nu) nu[k] = m->snu[k];
+    if (nc) nc[k] = m->snc[k];
+    if (nxn) nxn[k] = m->snxn[k];
+  }
+  return 0;
+}
+
+int ipddp_set_stage_types(ipddp_problem* h, const int* stage_types) {
+  NEED_HANDLE(h);
+  if (!stage_types) return fail("null stage type table");
+  const DevView& v = h->v;
+  const ModelVTable* vt = h->vt;
+  for (int t = 0; t < v.N - 1; ++t) {
+    const int k = stage_types[t];
+    if (k < 0 || k >= vt->nstage) return fail("stage type out of range");
+    const int next_nx = t + 1 < v.N - 1 ? vt->snx[stage_types[t + 1]] : vt->nxt;
+    if (t + 1 < v.N - 1 && (stage_types[t + 1] < 0 || stage_types[t + 1] >= vt->nstage)) return fail("stage type out of range");
+    if (vt->snxn[k] != next_nx)
+      return fail("stage " + std::to_string(t) + " maps to " + std::to_string(vt->snxn[k]) + " states but the next knot has " +
+                  std::to_string(next_nx));
+  }
+  if (vt->nstage == 1) return 0;
+  CK(cudaSetDevice(h->device));
+  std::vector<unsigned char> tmp(v.N - 1);
+  for (int t = 0; t < v.N - 1; ++t) tmp[t] = (unsigned char)stage_types[t];
+  CK(cudaMemcpy(h->d_stage_type, tmp.data(), tmp.size(), cudaMemcpyHostToDevice));
+  h->stages_set = true;
+  return 0;
+}
+
+int ipddp_set_stage_compl(ipddp_problem* h, int stage_type, const int* indices_compl, int n_compl) {
+  NEED_HANDLE(h);
+  if (stage_type < 0 || stage_type >= h->vt->nstage) return fail("stage type out of range");
+  unsigned long long m = 0ull;
+  for (int q = 0; q < n_compl; ++q) {
+    if (!indices_compl || indices_compl[q] < 0 || indices_compl[q] >= h->vt->snc[stage_type]) return fail("indices_compl out of range");
+    m |= 1ull << indices_compl[q];
+  }
+  h->v.compl_mask[stage_type] = m;
+  return 0;
+}
+
+int ipddp_stage_layout(ipddp_problem* h, int* nx, int* nu, int* nc) {
+  NEED_HANDLE(h);
+  const DevView& v = h->v;
+  std::vector<unsigned char> types(v.N > 1 ? v.N - 1 : 1, 0);
+  if (v.nstage > 1) {
+    if (!h->stages_set) return fail("stage chain: ipddp_set_stage_types not called");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(types.data(), h->d_stage_type, (size_t)(v.N - 1), cudaMemcpyDeviceToHost));
+  }
+  for (int t = 0; t < v.N; ++t) {
+    const bool term = t == v.N - 1;
+    if (nx) nx[t] = term ? v.nxt : v.snx[types[t]];
+    if (nu) nu[t] = term ? 0 : v.snu[types[t]];
+    if (nc) nc[t] = term ? 0 : v.snc[types[t]];
+  }
   return 0;
 }
 
@@ -502,6 +612,8 @@ static int set_inputs_impl(ipddp_problem* h, const double* x1, const double* uba
   CK(cudaSetDevice(h->device));
   if (!x1 || !ubar || !lower || !upper) return fail("x1, ubar, lower, upper are required");
   if (v.np > 0 && !params) return fail("params required (np > 0)");
+  if (!h->stages_set) return fail("stage chain: ipddp_set_stage_types not called");
+  if (v.nstage > 1 && horizons) return fail("stage chains solve the full horizon: per-instance horizons are not supported");
   cudaStream_t s = h->stream;
   if (horizons && kind == cudaMemcpyHostToDevice)
     for (int b = 0; b < v.B; ++b)
@@ -510,8 +622,8 @@ static int set_inputs_impl(ipddp_problem* h, const double* x1, const double* uba
   CK(cudaMemcpyAsync(h->d_ubar, ubar, (size_t)v.B * (v.N - 1) * v.nu * sizeof(double), kind, s));
   if (v.np > 0) CK(cudaMemcpyAsync(h->d_p, params, (size_t)v.B * v.np * sizeof(double), kind, s));
   else CK(cudaMemsetAsync(h->d_p, 0, (size_t)v.B * sizeof(double), s));
-  CK(cudaMemcpyAsync(h->d_lower, lower, (size_t)v.B * v.nu * sizeof(double), kind, s));
-  CK(cudaMemcpyAsync(h->d_upper, upper, (size_t)v.B * v.nu * sizeof(double), kind, s));
+  CK(cudaMemcpyAsync(h->d_lower, lower, (size_t)v.B * v.nstage * v.nu * sizeof(double), kind, s));
+  CK(cudaMemcpyAsync(h->d_upper, upper, (size_t)v.B * v.nstage * v.nu * sizeof(double), kind, s));
   bool check_device_horizons = false;
   if (horizons) {
     CK(cudaMemcpyAsync(h->d_horizon, horizons, (size_t)v.B * sizeof(int), kind, s));
@@ -676,8 +788,11 @@ int ipddp_solve_queue(ipddp_problem* h, const ipddp_queue* io) {
   ipddp_stats& st = h->st;
   memset(&st, 0, sizeof(st));
   const size_t np1 = hv.np > 0 ? hv.np : 1;
-  const size_t n_x1 = (size_t)Q * hv.nx, n_ub = (size_t)Q * (N - 1) * hv.nu, n_p = (size_t)Q * np1, n_b = (size_t)Q * hv.nu;
-  const size_t n_xo = (size_t)Q * N * hv.nx, n_uo = (size_t)Q * (N - 1) * hv.nu;
+  const size_t n_x1 = (size_t)Q * hv.nx, n_ub = (size_t)Q * (N - 1) * hv.nu, n_p = (size_t)Q * np1,
+               n_b = (size_t)Q * hv.nstage * hv.nu;
+  const size_t n_xo = (size_t)Q * N * hv.ns, n_uo = (size_t)Q * (N - 1) * hv.nu;
+  if (!h->stages_set) return fail("stage chain: ipddp_set_stage_types not called");
+  if (hv.nstage > 1 && io->horizons) return fail("stage chains solve the full horizon: per-instance horizons are not supported");
   CK(cudaEventRecord(h->ev[6], s));
   QueueView q;
   memset(&q, 0, sizeof(q));
@@ -949,14 +1064,14 @@ int ipddp_get_results(ipddp_problem* h, int* status, int* k, int* j, int* l, dou
   return 0;
 }
 
-static int gather(ipddp_problem* h, int use_cur, int off, int dim, int nst, double* out_host) {
+static int gather(ipddp_problem* h, int use_cur, int field, int dim, int nst, double* out_host) {
   const DevView& v = h->v;
   const long long total = (long long)v.B * nst * dim;
   if (total == 0) return 0;
   if (grow_device(&h->d_stage, &h->d_stage_cap, (size_t)total * sizeof(double)) != 0) return -1;
   double* d = (double*)h->d_stage;
   const int th = 256;
-  IPDDP_LAUNCH(k_gather, (unsigned)((total + th - 1) / th), th, 0, h->stream, v, use_cur, off, dim, nst, d);
+  IPDDP_LAUNCH(k_gather, (unsigned)((total + th - 1) / th), th, 0, h->stream, v, use_cur, field, dim, nst, d);
   CK(cudaMemcpyAsync(out_host, d, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -966,8 +1081,8 @@ int ipddp_get_trajectory(ipddp_problem* h, double* x, double* u) {
   NEED_HANDLE(h);
   const DevView& v = h->v;
   CK(cudaSetDevice(h->device));
-  if (x && gather(h, 0, 0, v.nx, v.N, x) != 0) return -1;
-  if (u && gather(h, 0, v.nx, v.nu, v.N - 1, u) != 0) return -1;
+  if (x && gather(h, 0, 0, v.ns, v.N, x) != 0) return -1;
+  if (u && gather(h, 0, 1, v.nu, v.N - 1, u) != 0) return -1;
   return 0;
 }
 
@@ -975,11 +1090,10 @@ int ipddp_get_duals(ipddp_problem* h, double* phi, double* zl, double* zu, doubl
   NEED_HANDLE(h);
   const DevView& v = h->v;
   CK(cudaSetDevice(h->device));
-  const int oPHI = v.nx + v.nu + v.nc + 2 * v.nu, oZL = oPHI + v.nc, oZU = oZL + v.nu;
-  if (phi && gather(h, 0, oPHI, v.nc, v.N - 1, phi) != 0) return -1;
-  if (zl && gather(h, 0, oZL, v.nu, v.N - 1, zl) != 0) return -1;
-  if (zu && gather(h, 0, oZU, v.nu, v.N - 1, zu) != 0) return -1;
-  if (lam) CK(cudaMemcpy(lam, v.lam, (size_t)v.B * v.N * v.nx * sizeof(double), cudaMemcpyDeviceToHost));
+  if (phi && gather(h, 0, 5, v.nc, v.N - 1, phi) != 0) return -1;
+  if (zl && gather(h, 0, 6, v.nu, v.N - 1, zl) != 0) return -1;
+  if (zu && gather(h, 0, 7, v.nu, v.N - 1, zu) != 0) return -1;
+  if (lam) CK(cudaMemcpy(lam, v.lam, (size_t)v.B * v.N * v.ns * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1005,20 +1119,18 @@ long long ipddp_get_array(ipddp_problem* h, const char* name, double* out) {
   std::string nm = name;
   int use_cur = 0;
   if (nm.rfind("cur_", 0) == 0) { use_cur = 1; nm = nm.substr(4); }
-  const int oX = 0, oU = v.nx, oC = oU + v.nu, oIL = oC + v.nc, oIU = oIL + v.nu, oPHI = oIU + v.nu,
-            oZL = oPHI + v.nc, oZU = oZL + v.nu;
-  struct F { const char* n; int off, dim, nst; } fields[] = {
-      {"x", oX, v.nx, v.N}, {"u", oU, v.nu, v.N - 1}, {"c", oC, v.nc, v.N - 1}, {"il", oIL, v.nu, v.N - 1},
-      {"iu", oIU, v.nu, v.N - 1}, {"phi", oPHI, v.nc, v.N - 1}, {"zl", oZL, v.nu, v.N - 1}, {"zu", oZU, v.nu, v.N - 1}};
+  struct F { const char* n; int field, dim, nst; } fields[] = {
+      {"x", 0, v.ns, v.N}, {"u", 1, v.nu, v.N - 1}, {"c", 2, v.nc, v.N - 1}, {"il", 3, v.nu, v.N - 1},
+      {"iu", 4, v.nu, v.N - 1}, {"phi", 5, v.nc, v.N - 1}, {"zl", 6, v.nu, v.N - 1}, {"zu", 7, v.nu, v.N - 1}};
   for (auto& f : fields)
     if (nm == f.n) {
       const long long n = (long long)v.B * f.nst * f.dim;
-      if (out && gather(h, use_cur, f.off, f.dim, f.nst, out) != 0) return -1;
+      if (out && gather(h, use_cur, f.field, f.dim, f.nst, out) != 0) return -1;
       return n;
     }
   const double* src = nullptr;
   long long n = 0;
-  if (nm == "lam") { src = v.lam; n = (long long)v.B * v.N * v.nx; }
+  if (nm == "lam") { src = v.lam; n = (long long)v.B * v.N * v.ns; }
   else if (nm == "gains") {      // without the padding double of the device records
     const long long G = (long long)(v.nu + v.nc + 2 * v.nu) * (v.nx + 1), rows = (long long)v.B * (v.N - 1);
     if (out && rows > 0) {

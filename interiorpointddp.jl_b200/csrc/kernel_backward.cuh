@@ -24,32 +24,35 @@
 namespace ipk {
 
 template <class M> struct BwLayout {
-  static_assert(M::NXN == M::NX, "state dimension must be constant along the horizon");
+  // Sizes come from M: for a stage chain M carries the maxima over its stage types, so one layout serves every knot; the
+  // arithmetic of a knot indexes the buffers with its own stage type's dimensions.  NS = largest state size that can sit in
+  // a state-sized buffer (stage states, next states, the terminal state).
   static constexpr int NX = M::NX, NU = M::NU, NC = M::NC, K = NU + NC, NR = NX + 1;
+  static constexpr int NS = cmax(M::NX, M::NXN, M::NXT);
   static constexpr int KP = K * (K + 1) / 2;
   static constexpr int pad(int n) { return n > 0 ? n : 1; }
   static constexpr int mx(int a, int b) { return a > b ? a : b; }
   // offsets in doubles
   static constexpr int LHS = 0;
   static constexpr int RHS = LHS + pad(KP);          // K x NR: assembled as [Qu B; c cx], negated, solved -> [alpha beta; psi omega]
-  static constexpr int FX = RHS + pad(K * NR);       // NX x NX (row index = next-state component)
+  static constexpr int FX = RHS + pad(K * NR);       // NXN x NX (row index = next-state component)
   static constexpr int NFU = M::FU_NC;               // controls the dynamics depend on (non-zero columns of fu)
-  static constexpr int FU = FX + NX * NX;            // NX x NFU, compact: column c belongs to control M::fu_col(c)
-  static constexpr int VXX = FU + pad(NX * NFU);     // value Hessian of knot t+1
-  static constexpr int VX = VXX + NX * NX;
-  static constexpr int LAM = VX + NX;
-  static constexpr int CM = LAM + NX;                // C (NX x NX)
-  static constexpr int VEC = CM + NX * NX;           // 1/il 1/iu Sigma^L Sigma^U  (4 x NU)
+  static constexpr int FU = FX + NS * NS;            // NXN x NFU, compact: column c belongs to control fu_col(c)
+  static constexpr int VXX = FU + pad(NS * NFU);     // value Hessian of knot t+1
+  static constexpr int VX = VXX + NS * NS;
+  static constexpr int LAM = VX + NS;
+  static constexpr int CM = LAM + NS;                // C (NX x NX)
+  static constexpr int VEC = CM + NS * NS;           // 1/il 1/iu Sigma^L Sigma^U  (4 x NU)
   static constexpr int PHI = VEC + pad(4 * NU);
   static constexpr int LX = PHI + pad(NC);
-  static constexpr int NEWV = LX + NX;               // new Vxx (NX*NX), Vx (NX), lam (NX); before the solve: |dual residual| (NU)
+  static constexpr int NEWV = LX + NS;               // new Vxx (NX*NX), Vx (NX), lam (NX); before the solve: |dual residual| (NU)
   // PRE: buffers that are dead once the factorisation starts; the 4K-double scratch of the 2x2 pivot update
   // (WS) is aliased on top of them
-  static constexpr int PRE = NEWV + mx(NX * NX + 2 * NX, NU);
+  static constexpr int PRE = NEWV + mx(NS * NS + 2 * NS, NU);
   static constexpr int DSC = NEWV;
-  static constexpr int UXT = PRE;                    // fu' Vxx+  (NFU x NX)
-  static constexpr int XXT = UXT + pad(NFU * NX);    // fx' Vxx+  (NX x NX)
-  static constexpr int TILE = XXT + NX * NX;
+  static constexpr int UXT = PRE;                    // fu' Vxx+  (NFU x NXN)
+  static constexpr int XXT = UXT + pad(NFU * NS);    // fx' Vxx+  (NX x NXN)
+  static constexpr int TILE = XXT + NS * NS;
   static constexpr int VFS = TILE + pad(mx(M::D_NSLOT, M::DN_NSLOT));
   static constexpr int XS = VFS + pad(M::VF_NSLOT);  // x, u copies for the dynamics Hessian contraction
   static constexpr int US = XS + (M::VF_NSLOT > 0 ? NX : 0);
@@ -76,118 +79,128 @@ IPDDP_D double bw_next_reg(const DevView& v, double reg, double reg_last) {
 }
 
 // (the buffers of the PRE group -- xxt, uxt, tile, vfs, xs, us -- share memory with ws, and dsc with nVxx / nVx / nlam:
-// no __restrict__ there)
-#define IPDDP_BW_POINTERS \
+// no __restrict__ there).  L = the (chain) model's layout, S = the stage type whose tables / constants are used.
+#define IPDDP_BW_POINTERS(S) \
   double* __restrict__ lhs = sm + L::LHS; double* __restrict__ rhs = sm + L::RHS; \
   double* __restrict__ fx = sm + L::FX; double* __restrict__ fu = sm + L::FU; \
   double* __restrict__ Vxx = sm + L::VXX; double* __restrict__ Vx = sm + L::VX; \
   double* __restrict__ lamn = sm + L::LAM; double* __restrict__ Cm = sm + L::CM; \
   double* xxt = sm + L::XXT; double* uxt = sm + L::UXT; \
-  double* __restrict__ ra1 = sm + L::VEC; double* __restrict__ ra2 = sm + L::VEC + NU; \
-  double* __restrict__ t1 = sm + L::VEC + 2 * NU; double* __restrict__ t2 = sm + L::VEC + 3 * NU; \
+  double* __restrict__ ra1 = sm + L::VEC; double* __restrict__ ra2 = sm + L::VEC + S::NU; \
+  double* __restrict__ t1 = sm + L::VEC + 2 * S::NU; double* __restrict__ t2 = sm + L::VEC + 3 * S::NU; \
   double* __restrict__ phi = sm + L::PHI; double* xs = sm + L::XS; double* us = sm + L::US; \
   double* __restrict__ lx = sm + L::LX; \
   double* tile = sm + L::TILE; double* vfs = sm + L::VFS; double* ws = sm + L::WS; double* dsc = sm + L::DSC; \
-  double* nVxx = sm + L::NEWV; double* nVx = sm + L::NEWV + NX * NX; double* nlam = sm + L::NEWV + NX * NX + NX; \
+  double* nVxx = sm + L::NEWV; double* nVx = sm + L::NEWV + S::NX * S::NX; double* nlam = sm + L::NEWV + S::NX * S::NX + S::NX; \
   unsigned char* smb = reinterpret_cast<unsigned char*>(sm); \
   unsigned char* nzlist = smb + L::LIST_B; \
-  const MEntry* tbl = M::tbl(); \
-  const double* cst = M::consts(); \
-  (void)xs; (void)us; (void)vfs;
+  const MEntry* tbl = S::tbl(); \
+  const double* cst = S::consts(); \
+  (void)lhs; (void)rhs; (void)fx; (void)fu; (void)Vxx; (void)Vx; (void)lamn; (void)Cm; (void)xxt; (void)uxt; (void)ra1; (void)ra2; \
+  (void)t1; (void)t2; (void)phi; (void)xs; (void)us; (void)lx; (void)tile; (void)vfs; (void)ws; (void)dsc; (void)nVxx; (void)nVx; \
+  (void)nlam; (void)nzlist; (void)tbl; (void)cst;
 
-// one-time setup of a warp's shared memory: constant parts of fx / fu
-template <class M>
+// constant parts of fx / fu of stage type S in a warp's shared memory (once per warp for a plain model, at every knot of a
+// stage chain, whose constants change with the stage type)
+template <class M, class S>
 IPDDP_D void bw_setup(double* sm, int lane) {
   typedef BwLayout<M> L;
-  constexpr int NX = L::NX, NFU = L::NFU;
+  constexpr int NX = S::NX, NN = S::NXN, NFU = S::FU_NC;
   double* fx = sm + L::FX; double* fu = sm + L::FU;
-  const MEntry* tbl = M::tbl();
-  const double* cst = M::consts();
-  for (int e = lane; e < NX * NX; e += 32) fx[e] = 0.0;
-  for (int e = lane; e < NX * NFU; e += 32) fu[e] = 0.0;
+  const MEntry* tbl = S::tbl();
+  const double* cst = S::consts();
+  for (int e = lane; e < NN * NX; e += 32) fx[e] = 0.0;
+  for (int e = lane; e < NN * NFU; e += 32) fu[e] = 0.0;
   __syncwarp();
-  for (int e = lane; e < M::D_fx_N; e += 32) {
-    const MEntry q = ld_entry(tbl + M::D_fx_OFF + e);
-    if (q.slot < 0) fx[q.i + q.j * NX] = IPDDP_LDG(cst - 1 - q.slot);
+  for (int e = lane; e < S::D_fx_N; e += 32) {
+    const MEntry q = ld_entry(tbl + S::D_fx_OFF + e);
+    if (q.slot < 0) fx[q.i + q.j * NN] = IPDDP_LDG(cst - 1 - q.slot);
   }
-  for (int e = lane; e < M::D_fu_N; e += 32) {
-    const MEntry q = ld_entry(tbl + M::D_fu_OFF + e);
-    if (q.slot < 0) fu[q.i + M::fu_idx(q.j) * NX] = IPDDP_LDG(cst - 1 - q.slot);
+  for (int e = lane; e < S::D_fu_N; e += 32) {
+    const MEntry q = ld_entry(tbl + S::D_fu_OFF + e);
+    if (q.slot < 0) fu[q.i + S::fu_idx(q.j) * NN] = IPDDP_LDG(cst - 1 - q.slot);
   }
   __syncwarp();
 }
 
-// One sweep t = Nb-1 .. 0 of backward_pass! with regularisation `reg` by one warp.  Returns 0 on success, 1 if the
-// inertia test failed at some knot (the caller restarts with a larger reg).  nkkt += knots visited;
-// dual_num = numerator of the dual infeasibility of this sweep.
+// per-sweep state shared by the knots of one sweep
+struct BwSweep {
+  double reg, mu, delta_c, dual_num;
+  bool second_order;
+  unsigned tri_lane;
+};
+
+// terminal knot (K = 0): Vxx = lxx_N, Vx = lx_N, lambda = lx_N, on the terminal stage's NXT states
 template <class M>
-IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, double mu, double* sm, const BwOut& out,
-                     int lane, int& nkkt, double& dual_num) {
+IPDDP_D void bw_terminal(const DevView& v, int b, int t, double* sm, const BwOut& out, int lane, BwSweep& sw) {
   typedef BwLayout<M> L;
-  typedef Rec<M> R;
-  constexpr int NX = L::NX, NU = L::NU, NC = L::NC, K = L::K, NR = L::NR, NFU = L::NFU;
-  IPDDP_BW_POINTERS
-  const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
-  const bool second_order = (v.opt.quasi_newton == 0);
-  double delta_c = 0.0;
-  const unsigned tri_lane = ldlt_tri_lane(lane);
+  typedef typename M::Terminal T;
+  constexpr int NX = T::NXT;
+  IPDDP_BW_POINTERS(T)
   auto val = [&](const MEntry& q) -> double { return q.slot >= 0 ? tile[q.slot] : IPDDP_LDG(cst - 1 - q.slot); };
-  dual_num = 0.0;
-  // ================= terminal knot (K = 0): Vxx = lxx_N, Vx = lx_N, lambda = lx_N =================
-  {
-    const int t = Nb - 1;
-    nkkt++;
-    for (int e = lane; e < M::DN_NSLOT; e += 32) tile[e] = v.tileN[(size_t)b * (M::DN_NSLOT > 0 ? M::DN_NSLOT : 1) + e];
-    for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
-    for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
-    __syncwarp();
-    for (int e = lane; e < M::DN_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::DN_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
-    for (int e = lane; e < M::DN_lx_N; e += 32) { const MEntry q = ld_entry(tbl + M::DN_lx_OFF + e); lx[q.i] = val(q); }
-    __syncwarp();
-    // C = lxx (+ vcxx = 0 unless quasi_newton);  Vxx = (0 + 0) + C ;  Vx = lambda = 0 + lx
-    // inertia_correction! on the empty KKT matrix resets delta_c (Q4: the value set by a failed knot
-    // never reaches a non-empty KKT matrix)
-    delta_c = 0.0;
-    for (int e = lane; e < NX * NX; e += 32) Vxx[e] = (0.0 + 0.0) + (second_order ? (Cm[e] + 0.0) : Cm[e]);
-    for (int e = lane; e < NX; e += 32) {
-      const double l0 = 0.0 + lx[e];
-      lamn[e] = l0;
-      Vx[e] = (l0 + 0.0) + 0.0;
-      out.lam[(size_t)t * NX + e] = l0;
-    }
-    __syncwarp();
+  for (int e = lane; e < T::DN_NSLOT; e += 32) tile[e] = v.tileN[(size_t)b * (M::DN_NSLOT > 0 ? M::DN_NSLOT : 1) + e];
+  for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
+  for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < T::DN_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + T::DN_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
+  for (int e = lane; e < T::DN_lx_N; e += 32) { const MEntry q = ld_entry(tbl + T::DN_lx_OFF + e); lx[q.i] = val(q); }
+  __syncwarp();
+  // C = lxx (+ vcxx = 0 unless quasi_newton);  Vxx = (0 + 0) + C ;  Vx = lambda = 0 + lx
+  // inertia_correction! on the empty KKT matrix resets delta_c (Q4: the value set by a failed knot
+  // never reaches a non-empty KKT matrix)
+  sw.delta_c = 0.0;
+  for (int e = lane; e < NX * NX; e += 32) Vxx[e] = (0.0 + 0.0) + (sw.second_order ? (Cm[e] + 0.0) : Cm[e]);
+  for (int e = lane; e < NX; e += 32) {
+    const double l0 = 0.0 + lx[e];
+    lamn[e] = l0;
+    Vx[e] = (l0 + 0.0) + 0.0;
+    out.lam[(size_t)t * L::NS + e] = l0;
   }
-  // ================= running knots =================
-  for (int t = Nb - 2; t >= 0; --t) {
-    nkkt++;
+  __syncwarp();
+}
+
+// One running knot t of stage type S (NX states, NN = NXN next states).  Returns 0, or 1 if the inertia test failed.
+template <class M, class S>
+IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const BwOut& out, int lane, BwSweep& sw,
+                    const double* p) {
+  typedef BwLayout<M> L;
+  typedef Rec<S> R;
+  constexpr int NX = S::NX, NN = S::NXN, NU = S::NU, NC = S::NC, K = NU + NC, NR = NX + 1, NFU = S::FU_NC;
+  IPDDP_BW_POINTERS(S)
+  const double reg = sw.reg, mu = sw.mu;
+  const bool second_order = sw.second_order;
+  const unsigned tri_lane = sw.tri_lane;
+  auto val = [&](const MEntry& q) -> double { return q.slot >= 0 ? tile[q.slot] : IPDDP_LDG(cst - 1 - q.slot); };
+  if constexpr (M::NSTAGE > 1) bw_setup<M, S>(sm, lane);     // the constants of fx / fu belong to the stage type
+  {
     const double* r = v.rec(set, b, t);
     if (t > 0) {   // the next knot's record and tile sectors: pull them towards L2 while this knot is factorised
       const double* rn = v.rec(set, b, t - 1);
-      if (lane * 16 < R::SIZE) IPDDP_PREFETCH_L2(rn + lane * 16);
+      if (lane * 16 < Rec<M>::SIZE) IPDDP_PREFETCH_L2(rn + lane * 16);
       for (int e = lane; e < M::D_NSLOT; e += 32) IPDDP_PREFETCH_L2(v.tile + ((size_t)b * M::D_NSLOT + e) * v.N + (t - 1));
     }
     // ---- stage inputs
-    for (int e = lane; e < M::D_NSLOT; e += 32) tile[e] = v.tile[((size_t)b * M::D_NSLOT + e) * v.N + t];
-    if constexpr (M::VF_NSLOT > 0) {
+    for (int e = lane; e < S::D_NSLOT; e += 32) tile[e] = v.tile[((size_t)b * M::D_NSLOT + e) * v.N + t];
+    if constexpr (S::VF_NSLOT > 0) {
       for (int e = lane; e < NU; e += 32) us[e] = r[R::U + e];
       for (int e = lane; e < NX; e += 32) xs[e] = r[R::X + e];
     }
     for (int e = lane; e < NC; e += 32) phi[e] = r[R::PHI + e];
-    for (int e = lane; e < L::KP; e += 32) lhs[e] = 0.0;
+    for (int e = lane; e < K * (K + 1) / 2; e += 32) lhs[e] = 0.0;
     for (int e = lane; e < K * NR; e += 32) rhs[e] = 0.0;
     for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
     for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
     __syncwarp();
     // ---- scatter pass 1: fx, fu (non-constant part), cu -> lhs top-right, cx -> rhs, lu -> rhs col 0,
     //      lux -> rhs B block, lxx -> C, lx, c -> rhs   (rhs holds the un-negated [Qu B; c cx] until the solve)
-    for (int e = lane; e < M::D_fx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fx_OFF + e); if (q.slot >= 0) fx[q.i + q.j * NX] = tile[q.slot]; }
-    for (int e = lane; e < M::D_fu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_fu_OFF + e); if (q.slot >= 0) fu[q.i + M::fu_idx(q.j) * NX] = tile[q.slot]; }
-    for (int e = lane; e < M::D_cu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cu_OFF + e); lhs[pk(q.j, NU + q.i)] = val(q); }
-    for (int e = lane; e < M::D_cx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_cx_OFF + e); rhs[NU + q.i + (1 + q.j) * K] = val(q); }
-    for (int e = lane; e < M::D_lu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lu_OFF + e); rhs[q.i] = val(q); }
-    for (int e = lane; e < M::D_lux_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lux_OFF + e); rhs[q.i + (1 + q.j) * K] = val(q); }
-    for (int e = lane; e < M::D_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
-    for (int e = lane; e < M::D_lx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_lx_OFF + e); lx[q.i] = val(q); }
+    for (int e = lane; e < S::D_fx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_fx_OFF + e); if (q.slot >= 0) fx[q.i + q.j * NN] = tile[q.slot]; }
+    for (int e = lane; e < S::D_fu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_fu_OFF + e); if (q.slot >= 0) fu[q.i + S::fu_idx(q.j) * NN] = tile[q.slot]; }
+    for (int e = lane; e < S::D_cu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_cu_OFF + e); lhs[pk(q.j, NU + q.i)] = val(q); }
+    for (int e = lane; e < S::D_cx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_cx_OFF + e); rhs[NU + q.i + (1 + q.j) * K] = val(q); }
+    for (int e = lane; e < S::D_lu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lu_OFF + e); rhs[q.i] = val(q); }
+    for (int e = lane; e < S::D_lux_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lux_OFF + e); rhs[q.i + (1 + q.j) * K] = val(q); }
+    for (int e = lane; e < S::D_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
+    for (int e = lane; e < S::D_lx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lx_OFF + e); lx[q.i] = val(q); }
     for (int e = lane; e < NC; e += 32) rhs[NU + e] = r[R::C + e];
     __syncwarp();
     // ---- barrier terms, Qu, dual-infeasibility numerator            (src/backward_pass.jl:62-75)
@@ -220,8 +233,8 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
       }
       double q = dq + lu_i;
       // fu' Vx: controls outside the fu columns contribute (0 + 0) + (0 + 0) = +0
-      const int ci = M::fu_idx(i);
-      q = (ci != 255 ? dot4c<NX>(fu + ci * NX, 1, Vx, 1) : 0.0) + q;
+      const int ci = S::fu_idx(i);
+      q = (ci != 255 ? dot4c<NN>(fu + ci * NN, 1, Vx, 1) : 0.0) + q;
       q -= cl;
       q += cu_;
       rhs[i] = q;   // Qu
@@ -229,84 +242,84 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
       double d = dq + lu_i;
       d -= zl_i;
       d += zu_i;
-      d = (ci != 255 ? dot4c<NX>(fu + ci * NX, 1, lamn, 1) : 0.0) + d;
+      d = (ci != 255 ? dot4c<NN>(fu + ci * NN, 1, lamn, 1) : 0.0) + d;
       t1[i] = a1 * zl_i;    // Sigma^L
       t2[i] = a2 * zu_i;    // Sigma^U
       dsc[i] = fabs(d);
     }
-    // ---- xx_tmp = fx' Vxx+ ; ux_tmp = fu' Vxx+                        (:80, :91)
-    for (int e = lane; e < NX * NX; e += 32) {
+    // ---- xx_tmp = fx' Vxx+ (NX x NN) ; ux_tmp = fu' Vxx+ (NFU x NN)      (:80, :91)
+    for (int e = lane; e < NX * NN; e += 32) {
       const int i = e % NX, j = e / NX;
-      xxt[e] = dot4c<NX>(fx + i * NX, 1, Vxx + j * NX, 1);
+      xxt[e] = dot4c<NN>(fx + i * NN, 1, Vxx + j * NN, 1);
     }
-    for (int e = lane; e < NFU * NX; e += 32) {     // rows of fu' Vxx+ outside the fu columns are exactly zero: not stored
+    for (int e = lane; e < NFU * NN; e += 32) {     // rows of fu' Vxx+ outside the fu columns are exactly zero: not stored
       const int a = e % NFU, j = e / NFU;
-      uxt[e] = dot4c<NX>(fu + a * NX, 1, Vxx + j * NX, 1);
+      uxt[e] = dot4c<NN>(fu + a * NN, 1, Vxx + j * NN, 1);
     }
     __syncwarp();
     {  // dual_num = max(dual_num, |.|_inf) -- uniform scan, NaN propagating like Julia's max
       double m = 0.0;
       for (int i = 0; i < NU; ++i) m = jmax(m, dsc[i]);
-      dual_num = jmax(dual_num, m);
+      sw.dual_num = jmax(sw.dual_num, m);
     }
     // ---- C += xx_tmp fx ;  H = Sigma + ux_tmp fu (upper) ; B += ux_tmp fx    (:81, :86-99)
     for (int e = lane; e < NX * NX; e += 32) {
       const int i = e % NX, j = e / NX;
-      Cm[e] = dot4c<NX>(xxt + i, NX, fx + j * NX, 1) + Cm[e];
+      Cm[e] = dot4c<NN>(xxt + i, NX, fx + j * NN, 1) + Cm[e];
     }
     // H = (fu' Vxx+ fu) + Sigma: outside the fu columns the product is (0 + 0) + (0 + 0) = +0, i.e. H = +0 + Sigma on the
     // diagonal and +0 (the cleared matrix) elsewhere; the fu columns get the dense formula
     for (int i = lane; i < NU; i += 32)
-      if (M::fu_idx(i) == 255) lhs[pk(i, i)] = 0.0 + (t1[i] + t2[i]);
+      if (S::fu_idx(i) == 255) lhs[pk(i, i)] = 0.0 + (t1[i] + t2[i]);
     for (int e = lane; e < NFU * (NFU + 1) / 2; e += 32) {
       const unsigned q = tri_decode(e);
       const int a = q & 0xff, b2 = q >> 8;                 // compact columns a <= b2
-      const int i = M::fu_col(a), j = M::fu_col(b2);       // controls i <= j
+      const int i = S::fu_col(a), j = S::fu_col(b2);       // controls i <= j
       const double h0 = (a == b2) ? (t1[i] + t2[i]) : 0.0;
-      lhs[pk(i, j)] = dot4c<NX>(uxt + a, NFU, fu + b2 * NX, 1) + h0;
+      lhs[pk(i, j)] = dot4c<NN>(uxt + a, NFU, fu + b2 * NN, 1) + h0;
     }
     for (int e = lane; e < NFU * NX; e += 32) {             // B += (fu' Vxx+) fx: rows outside the fu columns get +0
       const int a = e % NFU, j = e / NFU;
-      const int i = M::fu_col(a);
-      rhs[i + (1 + j) * K] = dot4c<NX>(uxt + a, NFU, fx + j * NX, 1) + rhs[i + (1 + j) * K];
+      const int i = S::fu_col(a);
+      rhs[i + (1 + j) * K] = dot4c<NN>(uxt + a, NFU, fx + j * NN, 1) + rhs[i + (1 + j) * K];
     }
     __syncwarp();
     // ---- H += luu
-    for (int e = lane; e < M::D_luu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_luu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
+    for (int e = lane; e < S::D_luu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_luu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
     __syncwarp();
     if (second_order) {
-      if constexpr (M::VF_NSLOT > 0) {   // dynamics Hessian contraction with lambda+ (:102-110), evaluated redundantly per lane
-        double vfl[M::VF_NSLOT > 0 ? M::VF_NSLOT : 1];
-        auto st = [&](int s, double x_) { vfl[s] = x_; };
-        M::vf(xs, us, lamn, p, st);
+      if constexpr (S::VF_NSLOT > 0) {   // dynamics Hessian contraction with lambda+ (:102-110), evaluated redundantly per lane
+        double vfl[S::VF_NSLOT > 0 ? S::VF_NSLOT : 1];
+        auto st = [&](int s_, double x_) { vfl[s_] = x_; };
+        S::vf(xs, us, lamn, p, st);
         if (lane == 0)
-          for (int s = 0; s < M::VF_NSLOT; ++s) vfs[s] = vfl[s];
+          for (int s_ = 0; s_ < S::VF_NSLOT; ++s_) vfs[s_] = vfl[s_];
         __syncwarp();
-        for (int e = lane; e < M::VF_vfxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfxx_OFF + e); Cm[q.i + q.j * NX] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
-        for (int e = lane; e < M::VF_vfux_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfux_OFF + e); rhs[q.i + (1 + q.j) * K] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
-        for (int e = lane; e < M::VF_vfuu_N; e += 32) { const MEntry q = ld_entry(tbl + M::VF_vfuu_OFF + e); lhs[pk(q.i, q.j)] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
+        for (int e = lane; e < S::VF_vfxx_N; e += 32) { const MEntry q = ld_entry(tbl + S::VF_vfxx_OFF + e); Cm[q.i + q.j * NX] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
+        for (int e = lane; e < S::VF_vfux_N; e += 32) { const MEntry q = ld_entry(tbl + S::VF_vfux_OFF + e); rhs[q.i + (1 + q.j) * K] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
+        for (int e = lane; e < S::VF_vfuu_N; e += 32) { const MEntry q = ld_entry(tbl + S::VF_vfuu_OFF + e); lhs[pk(q.i, q.j)] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
         __syncwarp();
       }
-      for (int e = lane; e < M::D_vcuu_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcuu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
-      for (int e = lane; e < M::D_vcux_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcux_OFF + e); rhs[q.i + (1 + q.j) * K] += val(q); }
-      for (int e = lane; e < M::D_vcxx_N; e += 32) { const MEntry q = ld_entry(tbl + M::D_vcxx_OFF + e); Cm[q.i + q.j * NX] += val(q); }
+      for (int e = lane; e < S::D_vcuu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_vcuu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
+      for (int e = lane; e < S::D_vcux_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_vcux_OFF + e); rhs[q.i + (1 + q.j) * K] += val(q); }
+      for (int e = lane; e < S::D_vcxx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_vcxx_OFF + e); Cm[q.i + q.j * NX] += val(q); }
       __syncwarp();
     }
     if (reg > 0.0)
       for (int i = lane; i < NU; i += 32) lhs[pk(i, i)] += reg;
-    if (delta_c > 0.0)
-      for (int i = lane; i < NC; i += 32) lhs[pk(NU + i, NU + i)] -= delta_c;
+    if (sw.delta_c > 0.0)
+      for (int i = lane; i < NC; i += 32) lhs[pk(NU + i, NU + i)] -= sw.delta_c;
     // ---- park the un-negated [Qu B; c cx] in this knot's gains slot (HBM, read back after the solve), write Qu,
     //      and negate in place: rhs = -[Qu B; c cx]                    (:129-136)
     double* g = out.gains + (size_t)t * v.G;
-    double* qo = out.Qu + (size_t)t * NU;
+    double* qo = out.Qu + (size_t)t * M::NU;
     for (int e = lane; e < K * NR; e += 32) { const double w = rhs[e]; g[e] = w; rhs[e] = w * -1.0; if (e < NU) qo[e] = w; }
     __syncwarp();
     // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
     int np = 0;
     const int info = warp_ldlt_factor<K, NR>(lhs, rhs, ws, nzlist, lane, 1e-12, np, tri_lane);
-    delta_c = 0.0;
-    if (info > 0) delta_c = v.opt.delta_c * dm::pow(mu, v.opt.kappa_c);
+    sw.delta_c = 0.0;
+    if (info > 0) sw.delta_c = v.opt.delta_c * dm::pow(mu, v.opt.kappa_c);
     if (np != NU || info != 0) return 1;   // inertia failure: the caller restarts the sweep with a larger reg
     warp_ldlt_solve_forward<K, NR>(lhs, rhs, nzlist, lane);
     // ---- ineq gains to HBM                                            (:159-172)
@@ -391,8 +404,8 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
           double lv = w;
           w = sa + w;
           w = sb + w;
-          w = dot4c<NX>(fx + i * NX, 1, Vx, 1) + w;
-          lv = dot4c<NX>(fx + i * NX, 1, lamn, 1) + lv;
+          w = dot4c<NN>(fx + i * NN, 1, Vx, 1) + w;
+          lv = dot4c<NN>(fx + i * NN, 1, lamn, 1) + lv;
           nVx[i] = w;
           nlam[i] = lv;
         }
@@ -404,11 +417,34 @@ IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, doubl
     for (int e = lane; e < NX; e += 32) {
       Vx[e] = nVx[e];
       lamn[e] = nlam[e];
-      out.lam[(size_t)t * NX + e] = nlam[e];
+      out.lam[(size_t)t * L::NS + e] = nlam[e];
     }
     __syncwarp();
   }
   return 0;
+}
+
+// One sweep t = Nb-1 .. 0 of backward_pass! with regularisation `reg` by one warp.  Returns 0 on success, 1 if the
+// inertia test failed at some knot (the caller restarts with a larger reg).  nkkt += knots visited;
+// dual_num = numerator of the dual infeasibility of this sweep.
+template <class M>
+IPDDP_D int bw_sweep(const DevView& v, int b, int Nb, int set, double reg, double mu, double* sm, const BwOut& out,
+                     int lane, int& nkkt, double& dual_num) {
+  const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
+  BwSweep sw;
+  sw.reg = reg; sw.mu = mu; sw.delta_c = 0.0; sw.dual_num = 0.0;
+  sw.second_order = (v.opt.quasi_newton == 0);
+  sw.tri_lane = ldlt_tri_lane(lane);
+  nkkt++;
+  bw_terminal<M>(v, b, Nb - 1, sm, out, lane, sw);
+  int status = 0;
+  for (int t = Nb - 2; t >= 0; --t) {
+    nkkt++;
+    for_stage<M>(v.type_of(t), [&](auto tag) { status = bw_knot<M, IPDDP_STAGE(tag)>(v, b, t, set, sm, out, lane, sw, p); });
+    if (status != 0) break;
+  }
+  dual_num = sw.dual_num;
+  return status;
 }
 
 template <class M>
@@ -420,11 +456,11 @@ __global__ void __launch_bounds__(32, IPDDP_BW_MINBLOCKS) k_backward(DevView v, 
   const int b = list.at(inst);
   const int Nb = v.horizon[b];
   const int set = v.nomsel[b];
-  bw_setup<M>(sm, lane);
+  if constexpr (M::NSTAGE == 1) bw_setup<M, M>(sm, lane);
   const double mu = v.sdv(SD_MU, b);
   const double reg_last = v.sdv(SD_REG_LAST, b);
   const BwOut out = {v.gains + (size_t)b * (v.N - 1) * v.G, v.Qu + (size_t)b * (v.N - 1) * M::NU,
-                     v.lam + (size_t)b * v.N * M::NX};
+                     v.lam + (size_t)b * v.N * BwLayout<M>::NS};
   double reg = 0.0, dual_num = 0.0;
   int status = 0, nsweep = 0, nkkt = 0;
   while (reg <= v.opt.reg_max) {
@@ -465,10 +501,10 @@ __global__ void __launch_bounds__(BWS_WARPS * 32) k_backward_spec(DevView v, Lis
   double* sm = sm_all + (size_t)warp * WD;
   double* res_dn = sm_all + (size_t)BWS_WARPS * WD;                 // [BWS_WARPS] dual_num
   int* res_i = reinterpret_cast<int*>(res_dn + BWS_WARPS);          // [BWS_WARPS][2]: verdict (0 ok, 1 failed, 3 not run), nkkt
-  bw_setup<M>(sm, lane);
+  if constexpr (M::NSTAGE == 1) bw_setup<M, M>(sm, lane);
   const double mu = v.sdv(SD_MU, b);
   const double reg_last = v.sdv(SD_REG_LAST, b);
-  const size_t G1 = (size_t)(v.N - 1) * v.G, Q1 = (size_t)(v.N - 1) * M::NU, L1 = (size_t)v.N * M::NX;
+  const size_t G1 = (size_t)(v.N - 1) * v.G, Q1 = (size_t)(v.N - 1) * M::NU, L1 = (size_t)v.N * BwLayout<M>::NS;
   BwOut out = {v.gains + (size_t)b * G1, v.Qu + (size_t)b * Q1, v.lam + (size_t)b * L1};
   const BwOut main_out = out;
   if (warp > 0) {
@@ -505,7 +541,7 @@ __global__ void __launch_bounds__(BWS_WARPS * 32) k_backward_spec(DevView v, Lis
     }
     if (winner > 0) {     // copy the winning sweep's outputs over the instance's arrays
       const double* pool = v.spec_bw + ((size_t)inst * (BWS_WARPS - 1) + (winner - 1)) * (G1 + Q1 + L1);
-      const int ng = (Nb - 1) * v.G, nq = (Nb - 1) * M::NU, nl = Nb * M::NX;
+      const int ng = (Nb - 1) * v.G, nq = (Nb - 1) * M::NU, nl = Nb * BwLayout<M>::NS;
       for (int e = threadIdx.x; e < ng; e += BWS_WARPS * 32) main_out.gains[e] = pool[e];
       for (int e = threadIdx.x; e < nq; e += BWS_WARPS * 32) main_out.Qu[e] = pool[G1 + e];
       for (int e = threadIdx.x; e < nl; e += BWS_WARPS * 32) main_out.lam[e] = pool[G1 + Q1 + e];

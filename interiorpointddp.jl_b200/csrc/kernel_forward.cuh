@@ -77,14 +77,17 @@ IPDDP_D FwStage fw_stage_init(double* base, int lane) {
   return st;
 }
 
-// per-lane output descriptors of the rollout (loop invariant): which gain row, which nominal field
+// per-lane output descriptors of the rollout (invariant along a run of one stage type): which gain row, which nominal
+// field.  Sized for the largest stage type of a chain; init<S> fills them for stage type S.
 template <class M> struct FwDesc {
-  static constexpr int K = M::NU + M::NC, NR = M::NX + 1, NOUT = K + 2 * M::NU, NIT = (NOUT + 31) / 32;
+  static constexpr int NOUT_MAX = M::NU + M::NC + 2 * M::NU, NIT = (NOUT_MAX + 31) / 32;
   int g_off[NIT], g_ld[NIT], n_off[NIT], kind[NIT];   // kind 0 u, 1 phi, 2 zl, 3 zu, -1 none
   double blo[NIT], bup[NIT];
-  IPDDP_D void init(const double* lo, const double* up, int lane) {
-    typedef Rec<M> R;
-    constexpr int NU = M::NU;
+  int type;                                            // stage type the descriptors were filled for (-1: none yet)
+  template <class S> IPDDP_D void init(const double* lo, const double* up, int lane, int type_) {
+    typedef Rec<S> R;
+    constexpr int NU = S::NU, K = S::NU + S::NC, NR = S::NX + 1, NOUT = K + 2 * NU;
+    type = type_;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int o = lane + 32 * it;
@@ -97,22 +100,30 @@ template <class M> struct FwDesc {
     }
   }
 };
+// descriptors for the stage type of knot t (no-op while the type does not change)
+template <class M>
+IPDDP_D void fw_desc_for(const DevView& v, FwDesc<M>& d, int b, int t, int lane) {
+  const int type = v.type_of(t);
+  if (d.type == type) return;
+  for_stage<M>(type, [&](auto tag) { d.template init<IPDDP_STAGE(tag)>(v.lower_of(b, type), v.upper_of(b, type), lane, type); });
+}
 
 // rollout! for step size gamma by one warp into the trial records at `trial` (record t at trial + t * TR).
 // returns 0 pass, 1 non-finite control / state (DomainError analogue, src/forward_pass.jl:18-24),
 //         2 fraction-to-boundary violation (src/forward_pass.jl:26-27)
 template <class M>
-IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int nom, double* trial, double gamma,
+IPDDP_D int fw_rollout(const DevView& v, FwDesc<M>& d, int b, int Nb, int nom, double* trial, double gamma,
                        double one_m_tau, const double* p, double* us, int lane, FwStage& stg) {
-  typedef Rec<M> R;
-  constexpr int NX = M::NX, NIT = FwDesc<M>::NIT;
+  constexpr int STRIDE = Rec<M>::STRIDE;
+  constexpr int NXM = Dims<M>::NS;     // a chain's state size changes with the stage type
+  constexpr int NIT = FwDesc<M>::NIT;
   int rc = 0;
-  double x[NX], xn[NX], dx[NX];
+  double x[NXM], dx[NXM];
   const double* r0 = v.rec(nom, b, 0);
 #pragma unroll
-  for (int i = 0; i < NX; ++i) x[i] = r0[R::X + i];
+  for (int i = 0; i < NXM; ++i) x[i] = (M::NSTAGE == 1 || i < v.snx[v.type_of(0)]) ? r0[i] : 0.0;
   // prefetch registers for knot t
-  double ff[NIT], fb[NIT][NX], nv[NIT], nil[NIT], niu[NIT], xbar[NX];
+  double ff[NIT], fb[NIT][M::NX], nv[NIT], nil[NIT], niu[NIT], xbar[NXM];
 #if IPDDP_FW_TMA
   // Knot t's gains record and nominal record are copied into stage (seq0 + t) % STAGES by one bulk copy each, issued by
   // lane 0 up to STAGES - 1 knots before the warp reads them.  A stage is refilled one knot AFTER its values were loaded
@@ -129,7 +140,7 @@ IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int 
       double* dst = stg.buf + (size_t)sidx * SD;
       mbar_expect_tx(&stg.bars[sidx], (unsigned)(SD * sizeof(double)));
       bulk_g2s(dst, v.gains + ((size_t)b * (v.N - 1) + t) * v.G, (unsigned)(FwLayout<M>::GP * sizeof(double)), &stg.bars[sidx]);
-      bulk_g2s(dst + FwLayout<M>::GP, v.rec(nom, b, t), (unsigned)(R::STRIDE * sizeof(double)), &stg.bars[sidx]);
+      bulk_g2s(dst + FwLayout<M>::GP, v.rec(nom, b, t), (unsigned)(STRIDE * sizeof(double)), &stg.bars[sidx]);
     }
     issued = t + 1;
   };
@@ -140,7 +151,9 @@ IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int 
   };
   for (int t = 0; t < FW_TMA_STAGES && t < nrun; ++t) issue(t);
 #endif
+  // loads knot t's gains rows and nominal values into the prefetch registers (descriptors: the knot's stage type)
   auto prefetch = [&](int t) {
+    fw_desc_for<M>(v, d, b, t, lane);
 #if IPDDP_FW_TMA
     wait_knot(t);
     const double* g = stg.buf + (size_t)((seq0 + (unsigned)t) % FW_TMA_STAGES) * SD;
@@ -150,63 +163,85 @@ IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int 
     const double* g = v.gains + ((size_t)b * (v.N - 1) + t) * v.G;
     const double* rn = v.rec(nom, b, t);
 #endif
+    for_stage<M>(d.type, [&](auto tag) {
+      typedef IPDDP_STAGE(tag) S;
+      typedef Rec<S> R;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) xbar[i] = rn[R::X + i];
+      for (int i = 0; i < S::NX; ++i) xbar[i] = rn[R::X + i];
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      if (d.kind[it] >= 0) {
-        ff[it] = g[d.g_off[it]];
+      for (int it = 0; it < NIT; ++it) {
+        if (d.kind[it] >= 0) {
+          ff[it] = g[d.g_off[it]];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) fb[it][j] = g[d.g_off[it] + (1 + j) * d.g_ld[it]];
-        nv[it] = rn[d.n_off[it]];
-        if (d.kind[it] == 0) { nil[it] = rn[R::IL + (d.n_off[it] - R::U)]; niu[it] = rn[R::IU + (d.n_off[it] - R::U)]; }
+          for (int j = 0; j < S::NX; ++j) fb[it][j] = g[d.g_off[it] + (1 + j) * d.g_ld[it]];
+          nv[it] = rn[d.n_off[it]];
+          if (d.kind[it] == 0) { nil[it] = rn[R::IL + (d.n_off[it] - R::U)]; niu[it] = rn[R::IU + (d.n_off[it] - R::U)]; }
+        }
       }
-    }
+    });
   };
   if (Nb > 1) prefetch(0);
   for (int t = 0; t < Nb; ++t) {
-    double* rcur = trial + (size_t)t * R::STRIDE;
-    if (lane < NX) {
-      double xv = x[0];
+    double* rcur = trial + (size_t)t * STRIDE;
+    if (t == Nb - 1) {        // terminal knot: only the state
+      if (lane < M::Terminal::NXT) {
+        double xv = x[0];
 #pragma unroll
-      for (int i = 1; i < NX; ++i) xv = (lane == i) ? x[i] : xv;
-      rcur[R::X + lane] = xv;
+        for (int i = 1; i < M::Terminal::NXT; ++i) xv = (lane == i) ? x[i] : xv;
+        rcur[lane] = xv;
+      }
+      break;
     }
-    if (t == Nb - 1) break;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) dx[i] = x[i] - xbar[i];
     bool viol = false, bad = false;
+    const int type_t = d.type;            // the prefetch below may move the descriptors on to the next knot's stage type
+    for_stage<M>(type_t, [&](auto tag) {
+      typedef IPDDP_STAGE(tag) S;
+      typedef Rec<S> R;
+      constexpr int NX = S::NX;
+      if (lane < NX) {
+        double xv = x[0];
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      if (d.kind[it] >= 0) {
-        double w = ff[it];
-        w *= gamma;
-        w += nv[it];
-        w = dot4c<NX>(fb[it], 1, dx, 1) + w;
-        rcur[d.n_off[it]] = w;
-        if (d.kind[it] == 0) {
-          const int i = d.n_off[it] - R::U;
-          us[i] = w;
-          const double il = w - d.blo[it], iu = d.bup[it] - w;
-          rcur[R::IL + i] = il;
-          rcur[R::IU + i] = iu;
-          viol = viol || (nil[it] * one_m_tau > il) || (niu[it] * one_m_tau > iu);
-          bad = bad || !finite(w);
-        } else if (d.kind[it] >= 2) {
-          viol = viol || (nv[it] * one_m_tau > w);
+        for (int i = 1; i < NX; ++i) xv = (lane == i) ? x[i] : xv;
+        rcur[R::X + lane] = xv;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) dx[i] = x[i] - xbar[i];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        if (d.kind[it] >= 0) {
+          double w = ff[it];
+          w *= gamma;
+          w += nv[it];
+          w = dot4c<NX>(fb[it], 1, dx, 1) + w;
+          rcur[d.n_off[it]] = w;
+          if (d.kind[it] == 0) {
+            const int i = d.n_off[it] - R::U;
+            us[i] = w;
+            const double il = w - d.blo[it], iu = d.bup[it] - w;
+            rcur[R::IL + i] = il;
+            rcur[R::IU + i] = iu;
+            viol = viol || (nil[it] * one_m_tau > il) || (niu[it] * one_m_tau > iu);
+            bad = bad || !finite(w);
+          } else if (d.kind[it] >= 2) {
+            viol = viol || (nv[it] * one_m_tau > w);
+          }
         }
       }
-    }
+    });
     __syncwarp();
     if (t + 1 < Nb - 1) prefetch(t + 1);
     else {
       const double* rn = v.rec(nom, b, t + 1);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) xbar[i] = rn[R::X + i];
+      for (int i = 0; i < M::Terminal::NXT; ++i) xbar[i] = rn[i];
     }
-    M::dyn(x, us, p, xn);
+    for_stage<M>(type_t, [&](auto tag) {
+      typedef IPDDP_STAGE(tag) S;
+      double xn[S::NXN];
+      S::dyn(x, us, p, xn);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { x[i] = xn[i]; bad = bad || !finite(xn[i]); }
+      for (int i = 0; i < S::NXN; ++i) { x[i] = xn[i]; bad = bad || !finite(xn[i]); }
+    });
     const bool any_bad = __any_sync(IPDDP_FULL_MASK, bad);
     const bool any_viol = __any_sync(IPDDP_FULL_MASK, viol);
     __syncwarp();
@@ -223,7 +258,7 @@ IPDDP_D int fw_rollout(const DevView& v, const FwDesc<M>& d, int b, int Nb, int 
 
 // per-instance invariants of one forward pass + the line-search state
 template <class M> struct FwState {
-  int b, Nb, nom, cur, fn, nlo, nbd;
+  int b, Nb, nom, cur, fn;
   double mu, one_m_tau, theta_prev, L_prev, theta_min, dL;
   const double* p;
   int l, status, nroll;
@@ -245,7 +280,6 @@ IPDDP_D void fw_setup(const DevView& v, FwState<M>& s, int b) {
   s.L_prev = v.sdv(SD_L_CURR, b);
   s.theta_min = v.sdv(SD_THETA_MIN, b);
   s.fn = v.siv(SI_FILTER_N, b);
-  s.nlo = 0; s.nbd = 0;
   s.l = 0; s.status = 0; s.nroll = 0;
   s.step = 1.0;
   s.switching = false; s.armijo = false;
@@ -257,13 +291,16 @@ IPDDP_D void fw_setup(const DevView& v, FwState<M>& s, int b) {
 // expected_change_lagrangian (src/forward_pass.jl:87-96): per-knot terms in parallel, ordered sum t descending
 template <class M>
 IPDDP_D double fw_expected_change(const DevView& v, const FwState<M>& s, double* p_l, double* p_th, int lane) {
-  typedef Rec<M> R;
   for (int t = lane; t < s.Nb - 1; t += 32) {
     const double* g = v.gains + ((size_t)s.b * (v.N - 1) + t) * v.G;
     const double* q = v.Qu + ((size_t)s.b * (v.N - 1) + t) * M::NU;
     const double* rn = v.rec(s.nom, s.b, t);
-    p_l[t] = dot4c<M::NU>(q, 1, g, 1);
-    p_th[t] = dot4c<M::NC>(rn + R::C, 1, g + M::NU, 1);
+    for_stage<M>(v.type_of(t), [&](auto tag) {
+      typedef IPDDP_STAGE(tag) S;
+      typedef Rec<S> R;
+      p_l[t] = dot4c<S::NU>(q, 1, g, 1);
+      p_th[t] = dot4c<S::NC>(rn + R::C, 1, g + S::NU, 1);
+    });
   }
   __syncwarp();
   double dL = 0.0;
@@ -355,16 +392,14 @@ __global__ void __launch_bounds__(FW_WARPS * 32, IPDDP_FW_MINBLOCKS) k_forward(D
   double* us = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
   double* chunk = us + MeritLayout<M>::NUP;
   unsigned char* bidx = reinterpret_cast<unsigned char*>(chunk + 32);
-  double* part = chunk + 32 + ((2 * MeritLayout<M>::NUP + 7) / 8);   // [4][N]: l_t, theta_t, c'phi_t, spare
+  double* part = us + MeritLayout<M>::FIXED;   // [4][N]: l_t, theta_t, c'phi_t, spare
   double* p_l = part; double* p_th = part + v.N; double* p_d = part + 2 * v.N;
 
   FwState<M> s;
   fw_setup<M>(v, s, lf.at(slot));
-  const double* lo = v.lower + (size_t)s.b * M::NU;
-  const double* up = v.upper + (size_t)s.b * M::NU;
-  warp_bound_list<M>(lo, up, bidx, lane, s.nlo, s.nbd);
+  const BoundLists<M> bls = warp_bound_lists<M>(v, s.b, bidx, lane);
   FwDesc<M> d;
-  d.init(lo, up, lane);
+  d.type = -1;
   s.dL = fw_expected_change<M>(v, s, p_l, p_th, lane);
 
   FwStage stg = fw_stage_init<M>(sm_all + (size_t)FW_WARPS * MeritLayout<M>::per_warp_doubles(v.N) + (size_t)warp * FwLayout<M>::TMA_DOUBLES, lane);
@@ -376,7 +411,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, IPDDP_FW_MINBLOCKS) k_forward(D
     if (rc == 2) { s.status = 2; s.step *= 0.5; continue; }
     __syncwarp();
     double Jn, theta, L;
-    warp_eval_metrics<M>(v, trial, s.Nb, s.mu, s.p, s.nlo, s.nbd, bidx, chunk, p_l, p_th, p_d, lane, &Jn, &theta, &L);
+    warp_eval_metrics<M>(v, trial, s.Nb, s.mu, s.p, bls, chunk, p_l, p_th, p_d, lane, &Jn, &theta, &L);
     if (fw_accept<M>(v, s, Jn, theta, L)) break;
     s.step *= 0.5;
     s.l += 1;
@@ -401,7 +436,7 @@ __global__ void __launch_bounds__(FWS_WARPS * 32) k_forward_spec(DevView v, cons
   double* us = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
   double* chunk = us + NUP;
   unsigned char* bidx = reinterpret_cast<unsigned char*>(chunk + 32);
-  double* part = chunk + 32 + ((2 * NUP + 7) / 8);
+  double* part = us + MeritLayout<M>::FIXED;
   double* p_l = part; double* p_th = part + v.N; double* p_d = part + 2 * v.N;
   double* res = sm_all + (size_t)FWS_WARPS * MeritLayout<M>::per_warp_doubles(v.N);   // [FWS_WARPS][3]: theta, L, J
   double* next_step = res + 3 * FWS_WARPS;
@@ -411,11 +446,9 @@ __global__ void __launch_bounds__(FWS_WARPS * 32) k_forward_spec(DevView v, cons
 
   FwState<M> s;
   fw_setup<M>(v, s, lf.at(slot));
-  const double* lo = v.lower + (size_t)s.b * M::NU;
-  const double* up = v.upper + (size_t)s.b * M::NU;
   FwDesc<M> d;
-  d.init(lo, up, lane);
-  warp_bound_list<M>(lo, up, bidx, lane, s.nlo, s.nbd);
+  d.type = -1;
+  const BoundLists<M> bls = warp_bound_lists<M>(v, s.b, bidx, lane);
   if (warp == 0) s.dL = fw_expected_change<M>(v, s, p_l, p_th, lane);   // only thread 0 judges
   double* trial = v.spec_traj + ((size_t)slot * FWS_WARPS + warp) * v.N * R::STRIDE;
   FwStage stg = fw_stage_init<M>(tma_base + (size_t)warp * FwLayout<M>::TMA_DOUBLES, lane);
@@ -430,7 +463,7 @@ __global__ void __launch_bounds__(FWS_WARPS * 32) k_forward_spec(DevView v, cons
       if (rc == 0) {
         __syncwarp();
         double Jn, theta, L;
-        warp_eval_metrics<M>(v, trial, s.Nb, s.mu, s.p, s.nlo, s.nbd, bidx, chunk, p_l, p_th, p_d, lane, &Jn, &theta, &L);
+        warp_eval_metrics<M>(v, trial, s.Nb, s.mu, s.p, bls, chunk, p_l, p_th, p_d, lane, &Jn, &theta, &L);
         if (lane == 0) { res[3 * warp + 0] = theta; res[3 * warp + 1] = L; res[3 * warp + 2] = Jn; }
       }
     }
@@ -457,7 +490,7 @@ __global__ void __launch_bounds__(FWS_WARPS * 32) k_forward_spec(DevView v, cons
     if (accepted >= 0) {   // the accepted candidate's records become the instance's trial set (then nomsel flips)
       const double* src = v.spec_traj + ((size_t)slot * FWS_WARPS + accepted) * v.N * R::STRIDE;
       double* dst = v.rec(s.cur, s.b, 0);
-      const int n = (s.Nb - 1) * R::STRIDE + M::NX;   // the terminal record only carries x
+      const int n = (s.Nb - 1) * R::STRIDE + M::Terminal::NXT;   // the terminal record only carries x
       for (int e = threadIdx.x; e < n; e += FWS_WARPS * 32) dst[e] = src[e];
     }
     if (!go_on) break;

@@ -12,6 +12,32 @@
 
 namespace ipk {
 
+// Stage dispatch: calls f(StageTag<S>{}) with S = stage type `type` of the (chain) model M.  A plain model is a chain of
+// one type: the call is direct, nothing is looked up.
+template <class S> struct StageTag { typedef S type; };
+template <class M, class F>
+IPDDP_D void for_stage(int type, F&& f) {
+  static_assert(M::NSTAGE >= 1 && M::NSTAGE <= MAX_STAGE_TYPES, "1..4 stage types");
+  if constexpr (M::NSTAGE == 1) {
+    (void)type;
+    f(StageTag<typename M::template Stage<0>>{});
+  } else if constexpr (M::NSTAGE == 2) {
+    if (type == 0) f(StageTag<typename M::template Stage<0>>{}); else f(StageTag<typename M::template Stage<1>>{});
+  } else if constexpr (M::NSTAGE == 3) {
+    if (type == 0) f(StageTag<typename M::template Stage<0>>{});
+    else if (type == 1) f(StageTag<typename M::template Stage<1>>{});
+    else f(StageTag<typename M::template Stage<2>>{});
+  } else {
+    if (type == 0) f(StageTag<typename M::template Stage<0>>{});
+    else if (type == 1) f(StageTag<typename M::template Stage<1>>{});
+    else if (type == 2) f(StageTag<typename M::template Stage<2>>{});
+    else f(StageTag<typename M::template Stage<3>>{});
+  }
+}
+#define IPDDP_STAGE(tag) typename decltype(tag)::type
+// stride of state-sized arrays (lambda, the x outputs): the largest state a knot of the (chain) model can carry
+template <class M> struct Dims { static constexpr int NS = cmax(M::NX, M::NXN, M::NXT); };
+
 // Julia's max/min propagate NaN (the reference relies on max(), norm(.,Inf); src/solve.jl:107-180)
 IPDDP_D double jmax(double a, double b) { return (a != a || b != b) ? dm::nan_() : (a > b ? a : b); }
 IPDDP_D double jmin(double a, double b) { return (a != a || b != b) ? dm::nan_() : (a < b ? a : b); }
@@ -49,41 +75,48 @@ template <int NN> IPDDP_D double dot4c(const double* a, int sa, const double* b,
 template <class M>
 IPDDP_D void eval_metrics(const DevView& v, int set, int b, int Nb, double mu, double* Jout, double* theta_out,
                           double* Lout) {
-  typedef Rec<M> R;
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
-  const double* lo = v.lower + (size_t)b * M::NU;
-  const double* up = v.upper + (size_t)b * M::NU;
   double J = 0.0, theta = 0.0, bl = 0.0;
   for (int t = 0; t < Nb; ++t) {
     double* r = v.rec(set, b, t);
-    double x[M::NX];
-#pragma unroll
-    for (int i = 0; i < M::NX; ++i) x[i] = r[R::X + i];
     double Jp;
     if (t < Nb - 1) {
-      double u[M::NU > 0 ? M::NU : 1], c[M::NC > 0 ? M::NC : 1];
+      const int type = v.type_of(t);
+      for_stage<M>(type, [&](auto tag) {
+        typedef IPDDP_STAGE(tag) S;
+        typedef Rec<S> R;
+        const double* lo = v.lower_of(b, type);
+        const double* up = v.upper_of(b, type);
+        double x[S::NX], u[S::NU > 0 ? S::NU : 1], c[S::NC > 0 ? S::NC : 1];
 #pragma unroll
-      for (int i = 0; i < M::NU; ++i) u[i] = r[R::U + i];
-      M::cost(x, u, p, &Jp);
-      if (M::NC > 0) {
-        M::con(x, u, p, c);
-        if (v.compl_mask) {
+        for (int i = 0; i < S::NX; ++i) x[i] = r[R::X + i];
 #pragma unroll
-            for (int i = 0; i < M::NC; ++i) if ((v.compl_mask >> i) & 1ull) c[i] -= mu;
+        for (int i = 0; i < S::NU; ++i) u[i] = r[R::U + i];
+        S::cost(x, u, p, &Jp);
+        if (S::NC > 0) {
+          S::con(x, u, p, c);
+          if (v.compl_mask[type]) {
+#pragma unroll
+            for (int i = 0; i < S::NC; ++i) if ((v.compl_mask[type] >> i) & 1ull) c[i] -= mu;
           }
-        double n1 = 0.0;
+          double n1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < M::NC; ++i) { r[R::C + i] = c[i]; n1 += fabs(c[i]); }
-        theta += n1;
-      }
+          for (int i = 0; i < S::NC; ++i) { r[R::C + i] = c[i]; n1 += fabs(c[i]); }
+          theta += n1;
+        }
 #pragma unroll
-      for (int i = 0; i < M::NU; ++i)
-        if (!is_inf(lo[i])) bl -= dm::log(r[R::IL + i]);
+        for (int i = 0; i < S::NU; ++i)
+          if (!is_inf(lo[i])) bl -= dm::log(r[R::IL + i]);
 #pragma unroll
-      for (int i = 0; i < M::NU; ++i)
-        if (!is_inf(up[i])) bl -= dm::log(r[R::IU + i]);
+        for (int i = 0; i < S::NU; ++i)
+          if (!is_inf(up[i])) bl -= dm::log(r[R::IU + i]);
+      });
     } else {
-      M::costN(x, p, &Jp);
+      typedef typename M::Terminal T;
+      double x[T::NXT];
+#pragma unroll
+      for (int i = 0; i < T::NXT; ++i) x[i] = r[i];
+      T::costN(x, p, &Jp);
     }
     J += Jp;
   }
@@ -91,7 +124,11 @@ IPDDP_D void eval_metrics(const DevView& v, int set, int b, int Nb, double mu, d
   bl += J;
   for (int t = 0; t < Nb - 1; ++t) {
     const double* r = v.rec(set, b, t);
-    bl += dot4c<M::NC>(r + R::C, 1, r + R::PHI, 1);
+    for_stage<M>(v.type_of(t), [&](auto tag) {
+      typedef IPDDP_STAGE(tag) S;
+      typedef Rec<S> R;
+      bl += dot4c<S::NC>(r + R::C, 1, r + R::PHI, 1);
+    });
   }
   bl += 0.0;  // terminal stage: dot of two empty vectors
   *Jout = J;
@@ -100,26 +137,41 @@ IPDDP_D void eval_metrics(const DevView& v, int set, int b, int Nb, double mu, d
 }
 
 // Per-warp scratch shared by the warp-per-instance kernels that evaluate merit terms (k_forward, k_check):
-// u[NU] | chunk[32] | finite-bound index bytes (2*NU, padded to 8 doubles) | 4 per-knot arrays of N doubles.
+// u[NU] | chunk[32] | finite-bound index bytes (2*NU per stage type, padded to 8 doubles) | 4 per-knot arrays of N doubles.
 template <class M> struct MeritLayout {
   static constexpr int NUP = M::NU > 0 ? M::NU : 1;
-  static constexpr int FIXED = NUP + 32 + ((2 * NUP + 7) / 8);
+  static constexpr int BIDX = 2 * NUP;                       // bytes of one stage type's index list
+  static constexpr int FIXED = NUP + 32 + ((BIDX * M::NSTAGE + 7) / 8);
   static IPDDP_BOTH int per_warp_doubles(int N) { return FIXED + 4 * N; }
 };
 
-// finite-bound index list in the reference's accumulation order (lower indices, then upper indices;
-// src/data/methods.jl:45-53); built by lane 0, counts broadcast
+// finite-bound index lists in the reference's accumulation order (lower indices, then upper indices;
+// src/data/methods.jl:45-53), one per stage type; built by lane 0, counts broadcast
+template <class M> struct BoundLists {
+  int nlo[M::NSTAGE], nbd[M::NSTAGE];
+  const unsigned char* bidx;
+  IPDDP_D const unsigned char* list(int type) const { return bidx + type * MeritLayout<M>::BIDX; }
+};
 template <class M>
-IPDDP_D void warp_bound_list(const double* lo, const double* up, unsigned char* bidx, int lane, int& nlo, int& nbd) {
-  int a = 0, q = 0;
-  if (lane == 0) {
-    for (int i = 0; i < M::NU; ++i) if (!is_inf(lo[i])) bidx[q++] = (unsigned char)i;
-    a = q;
-    for (int i = 0; i < M::NU; ++i) if (!is_inf(up[i])) bidx[q++] = (unsigned char)i;
+IPDDP_D BoundLists<M> warp_bound_lists(const DevView& v, int b, unsigned char* bidx, int lane) {
+  BoundLists<M> bl;
+  bl.bidx = bidx;
+  for (int type = 0; type < M::NSTAGE; ++type) {
+    int a = 0, q = 0;
+    if (lane == 0) {
+      const double* lo = v.lower_of(b, type);
+      const double* up = v.upper_of(b, type);
+      unsigned char* dst = bidx + type * MeritLayout<M>::BIDX;
+      const int nu = M::NSTAGE == 1 ? M::NU : v.snu[type];
+      for (int i = 0; i < nu; ++i) if (!is_inf(lo[i])) dst[q++] = (unsigned char)i;
+      a = q;
+      for (int i = 0; i < nu; ++i) if (!is_inf(up[i])) dst[q++] = (unsigned char)i;
+    }
+    bl.nlo[type] = __shfl_sync(IPDDP_FULL_MASK, a, 0);
+    bl.nbd[type] = __shfl_sync(IPDDP_FULL_MASK, q, 0);
   }
-  nlo = __shfl_sync(IPDDP_FULL_MASK, a, 0);
-  nbd = __shfl_sync(IPDDP_FULL_MASK, q, 0);
   __syncwarp();
+  return bl;
 }
 
 // Warp-parallel eval_metrics: the per-knot terms (l_t, c_t written to the record, |c_t|_1, c_t'phi_t) are evaluated
@@ -127,39 +179,48 @@ IPDDP_D void warp_bound_list(const double* lo, const double* up, unsigned char* 
 // order eval_metrics uses -- bit-identical results.  All lanes return the same J, theta, L.
 // recs: the instance's knot records of the trajectory set to evaluate (record t at recs + t * TR).
 template <class M>
-IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu, const double* p, int nlo, int nbd,
-                               const unsigned char* bidx, double* chunk, double* p_l, double* p_th, double* p_d,
+IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu, const double* p, const BoundLists<M>& bls,
+                               double* chunk, double* p_l, double* p_th, double* p_d,
                                int lane, double* Jout, double* theta_out, double* Lout) {
-  typedef Rec<M> R;
-  constexpr int NX = M::NX, NU = M::NU, NC = M::NC;
+  constexpr int STRIDE = Rec<M>::STRIDE;
   for (int t = lane; t < Nb; t += 32) {
-    double* r = recs + (size_t)t * R::STRIDE;
-    double x[NX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = r[R::X + i];
+    double* r = recs + (size_t)t * STRIDE;
     double Jp;
     if (t < Nb - 1) {
-      double u[NU > 0 ? NU : 1], c[NC > 0 ? NC : 1];
+      const int type = v.type_of(t);
+      for_stage<M>(type, [&](auto tag) {
+        typedef IPDDP_STAGE(tag) S;
+        typedef Rec<S> R;
+        constexpr int NX = S::NX, NU = S::NU, NC = S::NC;
+        double x[NX];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) u[i] = r[R::U + i];
-      M::cost(x, u, p, &Jp);
-      double n1 = 0.0;
-      if (NC > 0) {
-        M::con(x, u, p, c);
-        if (v.compl_mask) {
+        for (int i = 0; i < NX; ++i) x[i] = r[R::X + i];
+        double u[NU > 0 ? NU : 1], c[NC > 0 ? NC : 1];
 #pragma unroll
-          for (int i = 0; i < M::NC; ++i) if ((v.compl_mask >> i) & 1ull) c[i] -= mu;
+        for (int i = 0; i < NU; ++i) u[i] = r[R::U + i];
+        S::cost(x, u, p, &Jp);
+        double n1 = 0.0;
+        if (NC > 0) {
+          S::con(x, u, p, c);
+          if (v.compl_mask[type]) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) if ((v.compl_mask[type] >> i) & 1ull) c[i] -= mu;
+          }
+#pragma unroll
+          for (int i = 0; i < NC; ++i) { r[R::C + i] = c[i]; n1 += fabs(c[i]); }
         }
+        p_th[t] = n1;
+        double ph[NC > 0 ? NC : 1];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { r[R::C + i] = c[i]; n1 += fabs(c[i]); }
-      }
-      p_th[t] = n1;
-      double ph[NC > 0 ? NC : 1];
-#pragma unroll
-      for (int i = 0; i < NC; ++i) ph[i] = r[R::PHI + i];
-      p_d[t] = dot4c<NC>(c, 1, ph, 1);
+        for (int i = 0; i < NC; ++i) ph[i] = r[R::PHI + i];
+        p_d[t] = dot4c<NC>(c, 1, ph, 1);
+      });
     } else {
-      M::costN(x, p, &Jp);
+      typedef typename M::Terminal T;
+      double x[T::NXT];
+#pragma unroll
+      for (int i = 0; i < T::NXT; ++i) x[i] = r[i];
+      T::costN(x, p, &Jp);
       p_th[t] = 0.0;
       p_d[t] = 0.0;
     }
@@ -167,17 +228,23 @@ IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu
   }
   __syncwarp();
   double Jn = 0.0, theta = 0.0;
-  for (int t = 0; t < Nb; ++t) { Jn += p_l[t]; if (t < Nb - 1 && NC > 0) theta += p_th[t]; }
+  for (int t = 0; t < Nb; ++t) {
+    Jn += p_l[t];
+    if (t < Nb - 1 && (M::NSTAGE > 1 ? v.snc[v.type_of(t)] > 0 : M::NC > 0)) theta += p_th[t];
+  }
   // barrier term: bl -= log(slack) over (t, lower idx..., upper idx...), one running accumulator
   double bl = 0.0;
-  {
+  if constexpr (M::NSTAGE == 1) {
+    typedef Rec<M> R;
+    const int nlo = bls.nlo[0], nbd = bls.nbd[0];
+    const unsigned char* bidx = bls.list(0);
     const int total = (Nb - 1) * nbd;
     for (int base = 0; base < total; base += 32) {
       const int q = base + lane;
       double lg = 0.0;
       if (q < total) {
         const int t = q / nbd, s = q - t * nbd;
-        const double* r = recs + (size_t)t * R::STRIDE;
+        const double* r = recs + (size_t)t * STRIDE;
         const int i = bidx[s];
         lg = dm::log(s < nlo ? r[R::IL + i] : r[R::IU + i]);
       }
@@ -186,6 +253,25 @@ IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu
       const int cnt = (total - base) < 32 ? (total - base) : 32;
       for (int e = 0; e < cnt; ++e) bl -= chunk[e];
       __syncwarp();
+    }
+  } else {   // stage chain: the number of bounded controls changes with the knot's stage type -- one knot at a time
+    for (int t = 0; t < Nb - 1; ++t) {
+      const int type = v.type_of(t);
+      const int nlo = bls.nlo[type], nbd = bls.nbd[type];
+      const unsigned char* bidx = bls.list(type);
+      const double* r = recs + (size_t)t * STRIDE;
+      const int nx = v.snx[type], nu = v.snu[type], nc = v.snc[type];
+      const int oIL = nx + nu + nc, oIU = oIL + nu;
+      for (int base = 0; base < nbd; base += 32) {
+        const int s = base + lane;
+        double lg = 0.0;
+        if (s < nbd) { const int i = bidx[s]; lg = dm::log(s < nlo ? r[oIL + i] : r[oIU + i]); }
+        chunk[lane] = lg;
+        __syncwarp();
+        const int cnt = (nbd - base) < 32 ? (nbd - base) : 32;
+        for (int e = 0; e < cnt; ++e) bl -= chunk[e];
+        __syncwarp();
+      }
     }
   }
   bl *= mu;

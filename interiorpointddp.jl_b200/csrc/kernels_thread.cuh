@@ -19,31 +19,38 @@ namespace ipk {
 // returns true if the instance takes part in the first round (max_iterations > 0)
 template <class M>
 IPDDP_D bool init_instance(const DevView& v, int warm, int b, const double* x1p, const double* ubarp) {
-  typedef Rec<M> R;
   const int Nb = v.horizon[b];
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
-  const double* lo = v.lower + (size_t)b * M::NU;
-  const double* up = v.upper + (size_t)b * M::NU;
   const double k1 = v.opt.kappa_1, k2 = v.opt.kappa_2;
   int set = 0;
   if (warm) set = v.nomsel[b]; else v.nomsel[b] = 0;
 
-  double x[M::NX], xn[M::NXN], u[M::NU > 0 ? M::NU : 1];
+  double x[Dims<M>::NS];     // a chain's state size changes with the stage type: sized for the largest
   if (!warm) {
-#pragma unroll
-    for (int i = 0; i < M::NX; ++i) x[i] = x1p[i];
+    for (int i = 0; i < M::NX; ++i) x[i] = (M::NSTAGE == 1 || i < v.snx[v.type_of(0)]) ? x1p[i] : 0.0;
   }
   for (int t = 0; t < Nb; ++t) {
     double* r = v.rec(set, b, t);
-    if (!warm) {
-#pragma unroll
-      for (int i = 0; i < M::NX; ++i) r[R::X + i] = x[i];
-    }
-    if (t < Nb - 1) {
+    if (t == Nb - 1) {
       if (!warm) {
+#pragma unroll
+        for (int i = 0; i < M::Terminal::NXT; ++i) r[i] = x[i];
+      }
+      break;
+    }
+    const int type = v.type_of(t);
+    for_stage<M>(type, [&](auto tag) {
+      typedef IPDDP_STAGE(tag) S;
+      typedef Rec<S> R;
+      const double* lo = v.lower_of(b, type);
+      const double* up = v.upper_of(b, type);
+      if (!warm) {
+#pragma unroll
+        for (int i = 0; i < S::NX; ++i) r[R::X + i] = x[i];
+        double u[S::NU > 0 ? S::NU : 1], xn[S::NXN];
         const double* u0p = ubarp + (size_t)t * M::NU;
 #pragma unroll
-        for (int i = 0; i < M::NU; ++i) {
+        for (int i = 0; i < S::NU; ++i) {
           const double u0 = u0p[i], l = lo[i], h = up[i];
           double ub;
           if (!is_inf(l) && is_inf(h)) {
@@ -68,22 +75,22 @@ IPDDP_D bool init_instance(const DevView& v, int warm, int b, const double* x1p,
           r[R::IL + i] = ub - l;
           r[R::IU + i] = h - ub;
         }
-        M::dyn(x, u, p, xn);
+        S::dyn(x, u, p, xn);
 #pragma unroll
-        for (int i = 0; i < M::NX; ++i) x[i] = xn[i];
+        for (int i = 0; i < S::NXN; ++i) x[i] = xn[i];
       }
       // reset_duals!
 #pragma unroll
-      for (int i = 0; i < M::NC; ++i) r[R::PHI + i] = 0.0;
+      for (int i = 0; i < S::NC; ++i) r[R::PHI + i] = 0.0;
 #pragma unroll
-      for (int i = 0; i < M::NU; ++i) {
+      for (int i = 0; i < S::NU; ++i) {
         r[R::ZL + i] = is_inf(lo[i]) ? 0.0 : 1.0;
         r[R::ZU + i] = is_inf(up[i]) ? 0.0 : 1.0;
       }
-    }
+    });
   }
   for (int t = 0; t < Nb; ++t)
-    for (int i = 0; i < M::NX; ++i) v.lam[((size_t)b * v.N + t) * M::NX + i] = 0.0;
+    for (int i = 0; i < Dims<M>::NS; ++i) v.lam[((size_t)b * v.N + t) * Dims<M>::NS + i] = 0.0;
 
   // reset!(data) + prologue
   const double mu = v.opt.mu_init;
@@ -133,10 +140,11 @@ __global__ void k_admit(DevView v, QueueView q, const int* slots, int n, int ins
   const int i = inst0 + j;
   constexpr int NP1 = M::NP > 0 ? M::NP : 1;
   double* ps = const_cast<double*>(v.p) + (size_t)b * NP1;
-  double* lo = const_cast<double*>(v.lower) + (size_t)b * M::NU;
-  double* up = const_cast<double*>(v.upper) + (size_t)b * M::NU;
+  constexpr int NB = M::NSTAGE * M::NU;       // bounds per instance: [stage type][control]
+  double* lo = const_cast<double*>(v.lower) + (size_t)b * NB;
+  double* up = const_cast<double*>(v.upper) + (size_t)b * NB;
   for (int e = 0; e < M::NP; ++e) ps[e] = q.p[(size_t)i * NP1 + e];
-  for (int e = 0; e < M::NU; ++e) { lo[e] = q.lower[(size_t)i * M::NU + e]; up[e] = q.upper[(size_t)i * M::NU + e]; }
+  for (int e = 0; e < NB; ++e) { lo[e] = q.lower[(size_t)i * NB + e]; up[e] = q.upper[(size_t)i * NB + e]; }
   int hz = q.horizon ? q.horizon[i] : v.N;
   if (hz < 2 || hz > v.N) { atomicAdd(&counters[CNT_BAD], 1); hz = hz < 2 ? 2 : v.N; }
   const_cast<int*>(v.horizon)[b] = hz;
@@ -160,7 +168,6 @@ struct TileStore {
 
 template <class M>
 __global__ void k_derivs(DevView v, ListView list) {
-  typedef Rec<M> R;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int i = (int)(idx / v.N), t = (int)(idx % v.N);
   if (i >= list.total()) return;
@@ -169,20 +176,27 @@ __global__ void k_derivs(DevView v, ListView list) {
   if (t >= Nb) return;
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
   const double* r = v.rec(v.nomsel[b], b, t);
-  double x[M::NX];
-#pragma unroll
-  for (int q = 0; q < M::NX; ++q) x[q] = r[R::X + q];
   if (t < Nb - 1) {
-    double u[M::NU > 0 ? M::NU : 1], phi[M::NC > 0 ? M::NC : 1];
+    for_stage<M>(v.type_of(t), [&](auto tag) {
+      typedef IPDDP_STAGE(tag) S;
+      typedef Rec<S> R;
+      double x[S::NX], u[S::NU > 0 ? S::NU : 1], phi[S::NC > 0 ? S::NC : 1];
 #pragma unroll
-    for (int q = 0; q < M::NU; ++q) u[q] = r[R::U + q];
+      for (int q = 0; q < S::NX; ++q) x[q] = r[R::X + q];
 #pragma unroll
-    for (int q = 0; q < M::NC; ++q) phi[q] = r[R::PHI + q];
-    TileStore st{v.tile + (size_t)b * M::D_NSLOT * v.N + t, v.N};
-    M::derivs(x, u, phi, p, st);
+      for (int q = 0; q < S::NU; ++q) u[q] = r[R::U + q];
+#pragma unroll
+      for (int q = 0; q < S::NC; ++q) phi[q] = r[R::PHI + q];
+      TileStore st{v.tile + (size_t)b * M::D_NSLOT * v.N + t, v.N};
+      S::derivs(x, u, phi, p, st);
+    });
   } else {
+    typedef typename M::Terminal T;
+    double x[T::NXT];
+#pragma unroll
+    for (int q = 0; q < T::NXT; ++q) x[q] = r[q];
     TileStore st{v.tileN + (size_t)b * (M::DN_NSLOT > 0 ? M::DN_NSLOT : 1), 1};
-    M::derivsN(x, p, st);
+    T::derivsN(x, p, st);
   }
   if (t == 0) v.siv(SI_NDERIV, b) += 1;
 }
@@ -199,7 +213,6 @@ constexpr int CHK_WARPS = 4;
 template <class M>
 __global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, ListView list, int* list_next, int* list_fwd,
                                                          int* counters) {
-  typedef Rec<M> R;
   IPDDP_DYN_SMEM(double, sm_all);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * CHK_WARPS + warp;
@@ -213,59 +226,60 @@ __global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, ListView li
   double* us = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
   double* chunk = us + MeritLayout<M>::NUP;
   unsigned char* bidx = reinterpret_cast<unsigned char*>(chunk + 32);
-  double* part = chunk + 32 + ((2 * MeritLayout<M>::NUP + 7) / 8);
+  double* part = us + MeritLayout<M>::FIXED;
   double* p_a = part; double* p_b = part + v.N; double* p_c = part + 2 * v.N;
   const int Nb = v.horizon[b];
   const int set = v.nomsel[b];
-  const double* lo = v.lower + (size_t)b * M::NU;
-  const double* up = v.upper + (size_t)b * M::NU;
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
   const double mu = v.sdv(SD_MU, b);
-  int nlo = 0, nbd = 0;
-  warp_bound_list<M>(lo, up, bidx, lane, nlo, nbd);
-  const int nb_stage = nbd;
+  const BoundLists<M> bls = warp_bound_lists<M>(v, b, bidx, lane);
 
   double primal_inf = 0.0, cs0 = 0.0, csm = 0.0;
   // terminal stage contributes nothing (nu = nc = 0)
   for (int t = lane; t < Nb - 1; t += 32) {
     const double* r = v.rec(set, b, t);
-    double m = 0.0;
+    const int type = v.type_of(t);
+    for_stage<M>(type, [&](auto tag) {
+      typedef IPDDP_STAGE(tag) S;
+      typedef Rec<S> R;
+      double m = 0.0;
 #pragma unroll
-    for (int q = 0; q < M::NC; ++q) m = jmax(m, fabs(r[R::C + q]));
-    primal_inf = jmax(primal_inf, m);
-    double szl = 0.0, szu = 0.0, sphi = 0.0;
+      for (int q = 0; q < S::NC; ++q) m = jmax(m, fabs(r[R::C + q]));
+      primal_inf = jmax(primal_inf, m);
+      double szl = 0.0, szu = 0.0, sphi = 0.0;
 #pragma unroll
-    for (int q = 0; q < M::NU; ++q) szl += r[R::ZL + q];
+      for (int q = 0; q < S::NU; ++q) szl += r[R::ZL + q];
 #pragma unroll
-    for (int q = 0; q < M::NU; ++q) szu += r[R::ZU + q];
+      for (int q = 0; q < S::NU; ++q) szu += r[R::ZU + q];
 #pragma unroll
-    for (int q = 0; q < M::NC; ++q) sphi += fabs(r[R::PHI + q]);
-    p_a[t] = szl; p_b[t] = szu; p_c[t] = sphi;
-    if (nb_stage > 0) {
-      double a0 = 0.0, am = 0.0, b0 = 0.0, bm = 0.0;
+      for (int q = 0; q < S::NC; ++q) sphi += fabs(r[R::PHI + q]);
+      p_a[t] = szl; p_b[t] = szu; p_c[t] = sphi;
+      if (bls.nbd[type] > 0) {
+        double a0 = 0.0, am = 0.0, b0 = 0.0, bm = 0.0;
 #pragma unroll
-      for (int q = 0; q < M::NU; ++q) {
-        double w = r[R::IL + q];
-        w *= r[R::ZL + q];
-        double w0 = w - 0.0, wm = w - mu;
-        if (w0 != w0) w0 = 0.0;   // replace!(NaN => 0) after subtracting mu (Q3)
-        if (wm != wm) wm = 0.0;
-        a0 = jmax(a0, fabs(w0));
-        am = jmax(am, fabs(wm));
+        for (int q = 0; q < S::NU; ++q) {
+          double w = r[R::IL + q];
+          w *= r[R::ZL + q];
+          double w0 = w - 0.0, wm = w - mu;
+          if (w0 != w0) w0 = 0.0;   // replace!(NaN => 0) after subtracting mu (Q3)
+          if (wm != wm) wm = 0.0;
+          a0 = jmax(a0, fabs(w0));
+          am = jmax(am, fabs(wm));
+        }
+#pragma unroll
+        for (int q = 0; q < S::NU; ++q) {
+          double w = r[R::IU + q];
+          w *= r[R::ZU + q];
+          double w0 = w - 0.0, wm = w - mu;
+          if (w0 != w0) w0 = 0.0;
+          if (wm != wm) wm = 0.0;
+          b0 = jmax(b0, fabs(w0));
+          bm = jmax(bm, fabs(wm));
+        }
+        cs0 = jmax(cs0, a0); cs0 = jmax(cs0, b0);
+        csm = jmax(csm, am); csm = jmax(csm, bm);
       }
-#pragma unroll
-      for (int q = 0; q < M::NU; ++q) {
-        double w = r[R::IU + q];
-        w *= r[R::ZU + q];
-        double w0 = w - 0.0, wm = w - mu;
-        if (w0 != w0) w0 = 0.0;
-        if (wm != wm) wm = 0.0;
-        b0 = jmax(b0, fabs(w0));
-        bm = jmax(bm, fabs(wm));
-      }
-      cs0 = jmax(cs0, a0); cs0 = jmax(cs0, b0);
-      csm = jmax(csm, am); csm = jmax(csm, bm);
-    }
+    });
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -274,17 +288,30 @@ __global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, ListView li
     csm = jmax(csm, __shfl_xor_sync(IPDDP_FULL_MASK, csm, o));
   }
   __syncwarp();
-  double z_norm = 0.0, phi_norm = 0.0;
+  // sums in the reference's order (t descending); the complementarity error only counts stages that have bounds
+  // (src/solve.jl:160-166), the dual error every stage
+  double z_norm = 0.0, phi_norm = 0.0, z_norm_cs = 0.0;
+  int num_bounds = 0, num_con = 0;
   for (int t = Nb - 2; t >= 0; --t) {
     z_norm += p_a[t];
     z_norm += p_b[t];
     phi_norm += p_c[t];
+    if constexpr (M::NSTAGE > 1) {
+      const int type = v.type_of(t);
+      if (bls.nbd[type] > 0) { z_norm_cs += p_a[t]; z_norm_cs += p_b[t]; }
+      num_bounds += bls.nbd[type];
+      num_con += v.snc[type];
+    }
   }
   __syncwarp();
-  const double num_ineq = (double)nb_stage * (double)(Nb - 1);   // sum of Nb-1 copies of a small integer: exact
-  const double z_norm_cs = nb_stage > 0 ? z_norm : 0.0;          // same additions in the same order
+  if constexpr (M::NSTAGE == 1) {
+    num_bounds = bls.nbd[0] * (Nb - 1);
+    num_con = M::NC * (Nb - 1);
+    z_norm_cs = bls.nbd[0] > 0 ? z_norm : 0.0;      // same additions in the same order
+  }
+  const double num_ineq = (double)num_bounds;        // a sum of small integers: exact
+  const double num_constr = (double)num_con;
   const double s_max = v.opt.s_max;
-  const double num_constr = (double)(M::NC * (Nb - 1));
   const double sd_ = jmax(s_max, (phi_norm + z_norm) / jmax(num_ineq + num_constr, 1.0)) / s_max;
   const double sc_ = jmax(s_max, z_norm_cs / jmax(num_ineq, 1.0)) / s_max;
   const double dual_inf = v.sdv(SD_DUAL_NUM, b) / sd_;
@@ -302,11 +329,10 @@ __global__ void __launch_bounds__(CHK_WARPS * 32) k_check(DevView v, ListView li
     if (lane == 0) mark_done(v, b, counters);
     return;
   }
-  const int num_bounds = nb_stage * (Nb - 1);
   if (err_mu <= v.opt.kappa_eps * mu && num_bounds > 0 && mu > tol / 10.0) {
     const double mu_new = jmax(tol / 10.0, jmin(v.opt.kappa_mu * mu, dm::pow(mu, v.opt.theta_mu)));
     double J, theta, L;
-    warp_eval_metrics<M>(v, v.rec(set, b, 0), Nb, mu_new, p, nlo, nbd, bidx, chunk, p_a, p_b, p_c, lane, &J, &theta, &L);
+    warp_eval_metrics<M>(v, v.rec(set, b, 0), Nb, mu_new, p, bls, chunk, p_a, p_b, p_c, lane, &J, &theta, &L);
     if (lane == 0) {
       v.sdv(SD_MU, b) = mu_new;
       reset_filter(v, b);

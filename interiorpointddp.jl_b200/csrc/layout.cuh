@@ -67,17 +67,26 @@ struct QueueView {
   double* u;                                     // [Q][N-1][nu] or NULL
 };
 
+constexpr int MAX_STAGE_TYPES = 4;
+
 struct DevView {
   int B, N;
-  int nx, nu, nc, np;
+  int nx, nu, nc, np;        // of a plain model; of a stage chain: the maxima over its stage types (they size every stride)
+  // Stage chains (reference src/data/problem.jl:44-62: state / control sizes may change along the horizon): running stage t
+  // is of type stage_type[t] (NULL: one type), with its own sizes snx/snu/snc; the terminal knot carries nxt states.
+  // Storage stays uniform -- every record, gains block, Qu, lambda and tile column is strided by the maxima -- while the
+  // arithmetic of a knot is instantiated for its stage type (ipk::for_stage).
+  int nstage, nxt, ns;       // ns = stride of state-sized arrays (lambda, x outputs) = the largest state of any knot
+  int snx[MAX_STAGE_TYPES], snu[MAX_STAGE_TYPES], snc[MAX_STAGE_TYPES];
+  const unsigned char* stage_type;   // [N-1] or NULL
   int TR, G;                 // record strides (doubles), padded to even: x|u|c|il|iu|phi|zl|zu [+pad], eq|ineq gains [+pad]
   int n_compl;
   const int* compl_idx;
-  unsigned long long compl_mask;   // bit i set <=> constraint i is in indices_compl
+  unsigned long long compl_mask[MAX_STAGE_TYPES];   // per stage type: bit i set <=> constraint i is in indices_compl
   // inputs
   const double* p;           // [B][np]
-  const double* lower;       // [B][nu]
-  const double* upper;       // [B][nu]
+  const double* lower;       // [B][nstage][nu]: bounds per instance and stage type
+  const double* upper;       // [B][nstage][nu]
   const double* x1;          // [B][nx]
   const double* ubar;        // [B][(N-1) nu]
   const int* horizon;        // [B]
@@ -103,6 +112,9 @@ struct DevView {
   int list_sort;             // 1: active lists bucketed by expected work (heaviest first), 0: everything in one bucket (A/B)
   ipddp_options opt;
 
+  IPDDP_D int type_of(int t) const { return stage_type ? (int)stage_type[t] : 0; }
+  IPDDP_D const double* lower_of(int b, int type) const { return lower + ((size_t)b * nstage + type) * nu; }
+  IPDDP_D const double* upper_of(int b, int type) const { return upper + ((size_t)b * nstage + type) * nu; }
   IPDDP_D double* rec(int set, int b, int t) const { return traj + (((size_t)set * B + b) * N + t) * TR; }
   IPDDP_D double& sdv(int f, int b) const { return sd[(size_t)f * B + b]; }
   IPDDP_D int& siv(int f, int b) const { return si[(size_t)f * B + b]; }

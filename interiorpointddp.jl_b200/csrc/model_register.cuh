@@ -90,9 +90,20 @@ template <class M> struct Launch {
   }
 };
 
+template <class M, int I> constexpr int stage_dim(int which) {
+  if constexpr (I < M::NSTAGE) {
+    typedef typename M::template Stage<I> S;
+    return which == 0 ? S::NX : which == 1 ? S::NU : which == 2 ? S::NC : S::NXN;
+  } else {
+    return 0;
+  }
+}
+#define IPDDP_STAGE_DIMS(w) {stage_dim<M, 0>(w), stage_dim<M, 1>(w), stage_dim<M, 2>(w), stage_dim<M, 3>(w)}
+
 template <class M> const ModelVTable* make_vtable() {
   static const ModelVTable vt = {
       M::NAME, M::NX, M::NU, M::NC, M::NP, M::D_NSLOT, M::DN_NSLOT, M::VF_NSLOT, BwLayout<M>::BYTES,
+      M::NSTAGE, M::NXT, Dims<M>::NS, IPDDP_STAGE_DIMS(0), IPDDP_STAGE_DIMS(1), IPDDP_STAGE_DIMS(2), IPDDP_STAGE_DIMS(3),
       &Launch<M>::init, &Launch<M>::derivs, &Launch<M>::backward, &Launch<M>::check, &Launch<M>::forward,
       &Launch<M>::admit, &Launch<M>::smem_merit, &Launch<M>::smem_merit_spec, &Launch<M>::prepare};
   return &vt;

@@ -4,7 +4,11 @@
 
 struct ModelVTable {
   const char* name;
-  int nx, nu, nc, np, d_nslot, dn_nslot, vf_nslot, smem_backward;
+  int nx, nu, nc, np, d_nslot, dn_nslot, vf_nslot, smem_backward;   // nx/nu/nc: maxima over the stage types of a chain
+  // stage chain: number of stage types, their sizes (state, control, constraint, next state), the terminal state size and
+  // the stride of state-sized arrays
+  int nstage, nxt, ns;
+  int snx[MAX_STAGE_TYPES], snu[MAX_STAGE_TYPES], snc[MAX_STAGE_TYPES], snxn[MAX_STAGE_TYPES];
   void (*init)(const DevView&, int warm, int b0, int nb, int* list_next, int* counters, cudaStream_t);
   void (*derivs)(const DevView&, const ListView& list, cudaStream_t);
   void (*backward)(const DevView&, const ListView& list, cudaStream_t);

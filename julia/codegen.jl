@@ -200,6 +200,11 @@ function emit_device(sm::StageModel)
     println(io, "struct Model_$n {")
     println(io, "  static constexpr const char* NAME = \"$n\";")
     println(io, "  static constexpr int NX = $(sm.nx), NU = $(sm.nu), NC = $(sm.nc), NXN = $(sm.nx), NP = $(sm.np);")
+    println(io, "  static constexpr int NXT = $(sm.nx);   // state size the terminal cost is evaluated on")
+    println(io, "  // a plain model is a chain of one stage type (ipk::for_stage); chains of several types: generate.py")
+    println(io, "  static constexpr int NSTAGE = 1;")
+    println(io, "  template <int I> using Stage = Model_$n;")
+    println(io, "  using Terminal = Model_$n;")
     println(io, "  static constexpr int NTBL = $(length(all_entries)), NCONST = $(length(consts));")
     println(io, "  static constexpr int D_NSLOT = $(length(d_dyn)), VF_NSLOT = $(length(vf_dyn)), DN_NSLOT = $(length(dn_dyn));")
     off = 0

@@ -28,6 +28,7 @@
 #include "models_gen/concar_quad.h"
 #include "models_gen/double_integrator.h"
 #include "models_gen/pushing.h"
+#include "models_gen/ragged.h"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -38,7 +39,8 @@ namespace {
 typedef std::vector<double> vec;
 
 const OracleModel* kModels[] = {&gen_cartpole::model,    &gen_acrobot::model, &gen_concar::model,
-                                &gen_concar_quad::model, &gen_pushing::model, &gen_double_integrator::model};
+                                &gen_concar_quad::model, &gen_pushing::model, &gen_double_integrator::model,
+                                &gen_ragged_s0::model,   &gen_ragged_s1::model, &gen_ragged_s2::model};
 const int kNumModels = sizeof(kModels) / sizeof(kModels[0]);
 
 const OracleModel* find_model(const char* name) {
@@ -95,7 +97,9 @@ struct Bound {  // reference src/bounds.jl:1-17
 };
 
 struct Solver {
-  const OracleModel* m = nullptr;
+  const OracleModel* m = nullptr;              // stage 0's model (dimension queries of uniform problems)
+  std::vector<const OracleModel*> mt;          // model of stage t; mt[N-1] carries the terminal cost (costN / derivsN)
+  std::vector<std::vector<int>> compl_t;       // indices_compl of stage t
   int N = 0;
   std::vector<int> nx, nu, nc;
   vec p;
@@ -135,6 +139,7 @@ struct Solver {
   void setup(const OracleModel* model, int N_, const double* p_, const double* lo, const double* up,
              const int* compl_idx, int n_compl, const OracleOptions* o) {
     m = model; N = N_;
+    mt.assign(N, m);
     nx.assign(N, m->nx); nu.assign(N, m->nu); nc.assign(N, m->nc);
     nu[N - 1] = 0; nc[N - 1] = 0;   // terminal stage (every experiment: Objective(term, nx, 0), Constraint(nx, 0))
     p.assign(p_, p_ + m->np);
@@ -144,7 +149,51 @@ struct Solver {
     for (int t = 0; t < N - 1; ++t) bounds[t].set(l, u);
     bounds[N - 1].set(vec(), vec());
     indices_compl.assign(compl_idx, compl_idx + (compl_idx ? n_compl : 0));
+    compl_t.assign(N, indices_compl);
     opt = *o;
+    allocate();
+  }
+
+  // A chain of stage types (reference src/data/problem.jl:44-62: every buffer is sized per timestep): stage t < N-1 uses
+  // types[stage_type[t]], the terminal cost is types[ntypes-1]'s costN on a state of its nxt entries.  lo / up: the types'
+  // bounds one after another; compl_idx / n_compl: the types' indices_compl one after another with their counts.
+  int setup_chain(const OracleModel* const* types, int ntypes, const int* stage_type, int N_, const double* p_,
+                  const double* lo, const double* up, const int* compl_idx, const int* n_compl, const OracleOptions* o) {
+    N = N_;
+    m = types[stage_type[0]];
+    const OracleModel* term = types[ntypes - 1];
+    mt.assign(N, term);
+    nx.assign(N, 0); nu.assign(N, 0); nc.assign(N, 0);
+    int np = 0;
+    std::vector<int> boff(ntypes, 0), coff(ntypes, 0);
+    for (int k = 0, b = 0, c = 0; k < ntypes; ++k) {
+      boff[k] = b; coff[k] = c;
+      b += types[k]->nu; c += n_compl ? n_compl[k] : 0;
+      if (types[k]->np > np) np = types[k]->np;
+    }
+    bounds.resize(N);
+    compl_t.assign(N, std::vector<int>());
+    for (int t = 0; t < N - 1; ++t) {
+      const int k = stage_type[t];
+      if (k < 0 || k >= ntypes) return -1;
+      mt[t] = types[k];
+      nx[t] = mt[t]->nx; nu[t] = mt[t]->nu; nc[t] = mt[t]->nc;
+      bounds[t].set(vec(lo + boff[k], lo + boff[k] + mt[t]->nu), vec(up + boff[k], up + boff[k] + mt[t]->nu));
+      if (compl_idx && n_compl) compl_t[t].assign(compl_idx + coff[k], compl_idx + coff[k] + n_compl[k]);
+      if (t > 0 && mt[t - 1]->nxn != nx[t]) return -2;        // x_{t+1} = f_t(x_t, u_t) must fit the next stage
+    }
+    nx[N - 1] = term->nxt;
+    if (mt[N - 2]->nxn != nx[N - 1]) return -2;
+    bounds[N - 1].set(vec(), vec());
+    p.assign(p_, p_ + np);
+    if (p.empty()) p.push_back(0.0);
+    indices_compl.clear();
+    opt = *o;
+    allocate();
+    return 0;
+  }
+
+  void allocate() {
     nom.alloc(N, nx, nu, nc); cur.alloc(N, nx, nu, nc);
     auto A = [&](std::vector<vec>& v, auto f) { v.resize(N); for (int t = 0; t < N; ++t) v[t].assign(f(t), 0.0); };
     auto nxn = [&](int t) { return t < N - 1 ? nx[t + 1] : 0; };
@@ -171,15 +220,15 @@ struct Solver {
   Traj& tr(bool nominal) { return nominal ? nom : cur; }
 
   // ---------------------------------------------------------------- model evaluation helpers
-  void dynamics(int t, const vec& x, const vec& u, vec& xn) { (void)t; m->dyn(x.data(), u.data(), p.data(), xn.data()); }
+  void dynamics(int t, const vec& x, const vec& u, vec& xn) { mt[t]->dyn(x.data(), u.data(), p.data(), xn.data()); }
 
   // reference src/objectives.jl:37-46
   double eval_objective(bool nominal) {
     Traj& T = tr(nominal);
     double J = 0.0, Jp = 0.0;
     for (int t = 0; t < N; ++t) {
-      if (t < N - 1) m->cost(T.x[t].data(), T.u[t].data(), p.data(), &Jp);
-      else m->costN(T.x[t].data(), p.data(), &Jp);
+      if (t < N - 1) mt[t]->cost(T.x[t].data(), T.u[t].data(), p.data(), &Jp);
+      else mt[t]->costN(T.x[t].data(), p.data(), &Jp);
       J += Jp;
     }
     objective = J;
@@ -191,8 +240,8 @@ struct Solver {
     Traj& T = tr(nominal);
     for (int t = 0; t < N; ++t) {
       if (nc[t] > 0) {
-        m->con(T.x[t].data(), T.u[t].data(), p.data(), T.c[t].data());
-        for (int i : indices_compl) T.c[t][i] -= mu_;
+        mt[t]->con(T.x[t].data(), T.u[t].data(), p.data(), T.c[t].data());
+        for (int i : compl_t[t]) T.c[t][i] -= mu_;
       }
     }
   }
@@ -307,11 +356,11 @@ struct Solver {
     n_deriv++;
     for (int t = 0; t < N; ++t) {
       if (t < N - 1) {
-        m->derivs(nom.x[t].data(), nom.u[t].data(), nom.phi[t].data(), p.data(), fx[t].data(), fu[t].data(),
+        mt[t]->derivs(nom.x[t].data(), nom.u[t].data(), nom.phi[t].data(), p.data(), fx[t].data(), fu[t].data(),
                   lx[t].data(), lu[t].data(), lxx[t].data(), luu[t].data(), lux[t].data(), cx[t].data(),
                   cu[t].data(), vcxx[t].data(), vcux[t].data(), vcuu[t].data());
       } else {
-        m->derivsN(nom.x[t].data(), p.data(), lx[t].data(), lxx[t].data());
+        mt[t]->derivsN(nom.x[t].data(), p.data(), lx[t].data(), lxx[t].data());
       }
     }
   }
@@ -389,7 +438,7 @@ struct Solver {
         // second-order contraction terms                          (:102-115)
         if (!opt.quasi_newton) {
           if (t < N - 1) {
-            m->vf(T.x[t].data(), T.u[t].data(), T.lam[t + 1].data(), p.data(), vfxx[t].data(), vfux[t].data(),
+            mt[t]->vf(T.x[t].data(), T.u[t].data(), T.lam[t + 1].data(), p.data(), vfxx[t].data(), vfux[t].data(),
                   vfuu[t].data());
             for (int e = 0; e < n * n; ++e) C[t][e] += vfxx[t][e];
             for (int e = 0; e < mu_ * n; ++e) Bm[t][e] += vfux[t][e];
@@ -745,6 +794,23 @@ void* oracle_create(const char* model, int N, const double* p, const double* low
   if (opt) o = *opt; else oracle_default_options(&o);
   Solver* s = new Solver();
   s->setup(m, N, p, lower, upper, indices_compl, n_compl, &o);
+  return s;
+}
+// Chain of stage types: type_names[ntypes] (registered models), stage_type[N-1] per running stage; bounds and
+// indices_compl of the types one after another (see Solver::setup_chain).  p: max over the types' np doubles.
+void* oracle_create_chain(const char* const* type_names, int ntypes, const int* stage_type, int N, const double* p,
+                          const double* lower, const double* upper, const int* indices_compl, const int* n_compl,
+                          const OracleOptions* opt) {
+  if (ntypes < 1 || ntypes > 16 || N < 2) return nullptr;
+  const OracleModel* types[16];
+  for (int k = 0; k < ntypes; ++k) {
+    types[k] = find_model(type_names[k]);
+    if (!types[k]) return nullptr;
+  }
+  OracleOptions o;
+  if (opt) o = *opt; else oracle_default_options(&o);
+  Solver* s = new Solver();
+  if (s->setup_chain(types, ntypes, stage_type, N, p, lower, upper, indices_compl, n_compl, &o) != 0) { delete s; return nullptr; }
   return s;
 }
 void oracle_destroy(void* h) { delete (Solver*)h; }

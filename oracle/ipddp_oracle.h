@@ -63,6 +63,12 @@ int oracle_model_dims(const char* model, int* nx, int* nu, int* nc, int* np);
 // lower/upper: nu doubles (+-inf allowed), applied to every running stage.  indices_compl: 0-based, may be NULL.
 void* oracle_create(const char* model, int N, const double* p, const double* lower, const double* upper,
                     const int* indices_compl, int n_compl, const OracleOptions* opt);
+// chain of stage types (state / control sizes may change along the horizon; reference src/data/problem.jl:44-62):
+// type_names[ntypes] registered models, stage_type[N-1]; lower/upper and indices_compl/n_compl: per type, concatenated.
+void* oracle_create_chain(const char* const* type_names, int ntypes, const int* stage_type, int N, const double* p,
+                          const double* lower, const double* upper, const int* indices_compl, const int* n_compl,
+                          const OracleOptions* opt);
+void oracle_set_filter_capacity(int cap);   // 0 = unbounded (reference); n = the device's fixed filter capacity
 void oracle_destroy(void* h);
 
 // reference solve!(solver, x1, controls) (src/solve.jl:1-4); ubar is (N-1)*nu doubles

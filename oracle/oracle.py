@@ -73,6 +73,9 @@ def lib():
         L.oracle_model_dims.argtypes = [C.c_char_p, ip, ip, ip, ip]
         L.oracle_create.restype = C.c_void_p
         L.oracle_create.argtypes = [C.c_char_p, C.c_int, dp, dp, dp, ip, C.c_int, C.POINTER(OracleOptions)]
+        L.oracle_create_chain.restype = C.c_void_p
+        L.oracle_create_chain.argtypes = [C.POINTER(C.c_char_p), C.c_int, ip, C.c_int, dp, dp, dp, ip, ip,
+                                          C.POINTER(OracleOptions)]
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_solve.argtypes = [C.c_void_p, dp, dp]
         L.oracle_resolve.argtypes = [C.c_void_p]
@@ -207,6 +210,43 @@ class OracleSolver:
         if n:
             lib().oracle_get_array(self.h, name.encode(), _dp(out))
         return out
+
+
+class OracleChainSolver(OracleSolver):
+    """One OCP instance whose stage types change along the horizon (oracle_create_chain): `types` = registered model names,
+    `stage_type[t]` for the running stages t = 0..N-2, `lowers` / `uppers` / `indices_compl` one entry per type.  `solve`
+    takes the initial controls as the concatenation of the stages' (differently sized) vectors."""
+
+    def __init__(self, types, stage_type, N, p, lowers, uppers, options=None, indices_compl=None):
+        self.types, self.N = list(types), N
+        self.stage_type = np.ascontiguousarray(stage_type, dtype=np.int32)
+        assert self.stage_type.size == N - 1
+        dims = [model_dims(t) for t in self.types]
+        self.stage_nu = [dims[k][1] for k in self.stage_type]
+        self.stage_nx = [dims[k][0] for k in self.stage_type]
+        p = np.ascontiguousarray(np.atleast_1d(np.asarray(p, dtype=np.float64)))
+        if p.size == 0:
+            p = np.zeros(1)
+        self._p = p
+        self._lo = np.ascontiguousarray(np.concatenate([np.asarray(l, dtype=np.float64).reshape(-1) for l in lowers]))
+        self._up = np.ascontiguousarray(np.concatenate([np.asarray(u, dtype=np.float64).reshape(-1) for u in uppers]))
+        self.options = options or default_options()
+        ic = indices_compl if indices_compl is not None else [[] for _ in self.types]
+        self._ncompl = np.ascontiguousarray([len(c) for c in ic], dtype=np.int32)
+        flat = np.ascontiguousarray([i for c in ic for i in c], dtype=np.int32)
+        self._ic = flat if flat.size else np.zeros(1, dtype=np.int32)
+        names = (C.c_char_p * len(self.types))(*[t.encode() for t in self.types])
+        self.h = lib().oracle_create_chain(names, len(self.types), _ip(self.stage_type), N, _dp(p), _dp(self._lo), _dp(self._up),
+                                           _ip(self._ic), _ip(self._ncompl), C.byref(self.options))
+        if not self.h:
+            raise RuntimeError("oracle_create_chain failed (unknown type, or stage dimensions that do not chain)")
+
+    def solve(self, x1, ubar):
+        x1 = np.ascontiguousarray(x1, dtype=np.float64)
+        ubar = np.ascontiguousarray(ubar, dtype=np.float64).reshape(-1)
+        assert ubar.size == sum(self.stage_nu)
+        lib().oracle_solve(self.h, _dp(x1), _dp(ubar))
+        return self.result()
 
 
 def solve_batch(model, N, p, lower, upper, x1, ubar, options=None, horizons=None, nthreads=0, want_traj=False):

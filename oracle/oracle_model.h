@@ -18,4 +18,5 @@ typedef struct OracleModel {
   void (*vf)(const double* x, const double* u, const double* v, const double* p, double* vfxx, double* vfux,
              double* vfuu);
   void (*derivsN)(const double* x, const double* p, double* lx, double* lxx);
+  int nxt;   // state size costN / derivsN are evaluated on (= nx except for the last stage type of a chain)
 } OracleModel;

@@ -87,6 +87,75 @@ def queue_parity(lib, oracle, wl, Q, B, N=101, maxit=1000, tol=1e-7, vary_horizo
     return r, st
 
 
+def chain_inputs(chain, B, N, seed=0):
+    """Padded batch inputs of a stage chain: (stage_types, x1 [B,nx], ubar [B,(N-1)*nu], lower/upper [B,nstage*nu]) plus
+    the per-instance ragged pieces the oracle takes.  Instances differ in their initial state."""
+    st = chain.stage_types(N)
+    nu_max = max(md.nu for md in chain.stages)
+    nx0 = chain.stages[st[0]].nx
+    nx_max = max(md.nx for md in chain.stages)
+    rng = np.random.default_rng(seed)
+    x1 = np.zeros((B, nx_max))
+    x1[:, :nx0] = 0.2 * rng.standard_normal((B, nx0))
+    x1[0, :] = 0.0
+    ubar = np.zeros((B, N - 1, nu_max))
+    for t, k in enumerate(st):
+        ubar[:, t, :chain.stages[k].nu] = np.asarray(chain.stages[k].u_init)
+    lower = np.full((B, len(chain.stages), nu_max), -np.inf)
+    upper = np.full((B, len(chain.stages), nu_max), np.inf)
+    for k, md in enumerate(chain.stages):
+        lower[:, k, :md.nu] = md.lower([])
+        upper[:, k, :md.nu] = md.upper([])
+    return st, x1, ubar.reshape(B, -1), lower.reshape(B, -1), upper.reshape(B, -1)
+
+
+def chain_parity(lib, oracle, name, B, N, maxit=1000, tol=1e-7, queue_slots=0):
+    """A horizon whose state / control sizes change from stage to stage (reference README.md:18, src/data/problem.jl:44-62):
+    the device's chain model against the oracle's per-stage models -- status, iteration counts, objective and error bits,
+    work counters, accepted-step trace and the (ragged) trajectories."""
+    chain = workloads.get_chain(name)
+    st, x1, ubar, lower, upper = chain_inputs(chain, B, N)
+    opt = lib.default_options(optimality_tolerance=tol, max_iterations=maxit)
+    s = BatchSolver(name, queue_slots or B, N, options=opt, trace_capacity=0 if queue_slots else maxit, lib=lib)
+    assert s.nstage == len(chain.stages)
+    s.set_stage_types(st)
+    nxs, nus, ncs = s.stage_layout()
+    assert list(nus[:-1]) == [chain.stages[k].nu for k in st] and nus[-1] == 0 and nxs[-1] == s.nxt
+    if queue_slots:
+        r, cnt, x, u = s.solve_queue(x1, ubar, None, lower, upper)
+    else:
+        s.set_inputs(x1, ubar, None, lower, upper)
+        r = s.solve()
+        x, u = s.trajectory()
+        cnt = s.counters()
+    nu_max = s.nu
+    oopt = oracle.default_options(optimality_tolerance=tol, max_iterations=maxit)
+    for i in range(B):
+        o = oracle.OracleChainSolver([md.name for md in chain.stages], st, N, [], [md.lower([]) for md in chain.stages],
+                                     [md.upper([]) for md in chain.stages], options=oopt)
+        ub = ubar[i].reshape(N - 1, nu_max)
+        res = o.solve(x1[i, :chain.stages[st[0]].nx], np.concatenate([ub[t, :chain.stages[k].nu] for t, k in enumerate(st)]))
+        got = (int(r.status[i]), int(r.k[i]), int(r.j[i]), int(r.l[i]))
+        assert got == (res.status, res.k, res.j, res.l), f"{name} inst {i}: (status,k,j,l) {got} vs oracle {(res.status, res.k, res.j, res.l)}"
+        for nm in ("objective", "primal_inf", "dual_inf", "cs_inf", "mu", "reg_last", "step_size"):
+            assert_same_bits(getattr(r, nm)[i], getattr(res, nm), f"{name} inst {i} {nm}")
+        assert (cnt["n_backward"][i], cnt["n_sweeps"][i], cnt["n_kkt"][i], cnt["n_rollouts"][i]) == \
+            (res.n_backward, res.n_sweeps, res.n_kkt, res.n_rollouts), f"{name} inst {i}: work counters"
+        xo, uo = o.array("x"), o.array("u")
+        px = pu = 0
+        for t in range(N):
+            assert_same_bits(x[i, t, :nxs[t]], xo[px:px + nxs[t]], f"{name} inst {i} state of knot {t}")
+            assert not x[i, t, nxs[t]:].any()
+            px += nxs[t]
+            if t < N - 1:
+                assert_same_bits(u[i, t, :nus[t]], uo[pu:pu + nus[t]], f"{name} inst {i} control of knot {t}")
+                pu += nus[t]
+        if not queue_slots and i < 2:
+            assert_same_bits(s.trace(i), o.trace(), f"{name} inst {i} accepted-step trace")
+    s.close()
+    return r
+
+
 def _tile_map(wl):
     md = workloads.get(wl)
     bd = generate.trace(md)

@@ -52,7 +52,7 @@ def test_options_layout_and_defaults(product_lib):
 def test_model_registry(product_lib):
     from ipddp_b200 import _lib
     lib = _lib.Lib(_lib.LIB_PATH)
-    assert set(lib.models()) == {"cartpole", "acrobot", "concar", "concar_quad", "pushing", "double_integrator"}
+    assert set(lib.models()) == {"cartpole", "acrobot", "concar", "concar_quad", "pushing", "double_integrator", "ragged"}
     assert lib.model_dims("cartpole")[:4] == (4, 21, 14, 5)
     assert lib.model_dims("acrobot")[:4] == (4, 9, 6, 8)
     assert lib.model_dims("concar")[:4] == (4, 10, 4, 14)
@@ -181,9 +181,11 @@ def test_julia_emitter_writes_the_names_the_kernels_read():
     used = set()
     csrc = os.path.join(ROOT, "interiorpointddp.jl_b200", "csrc")
     for f in os.listdir(csrc):
-        if f.endswith(".cuh"):
-            used |= set(re.findall(r"\bM::([A-Za-z_][A-Za-z_0-9]*)", open(os.path.join(csrc, f)).read()))
+        if f.endswith(".cuh") and f != "ldlt_warp.cuh":     # (there S is the LDLT scratch layout, not a stage type)
+            # M = the (chain) model, S = a stage type, T = the terminal stage type
+            used |= set(re.findall(r"\b[MST]::([A-Za-z_][A-Za-z_0-9]*)", open(os.path.join(csrc, f)).read()))
     assert len(used) > 30
+    used.discard("template")          # `M::template Stage<I>`: a keyword, not a member
     for name in sorted(used):
         if re.fullmatch(r"(D|VF|DN)_[a-z]+_(OFF|N)", name):
             prefix, mat, _ = name.split("_")
@@ -191,3 +193,15 @@ def test_julia_emitter_writes_the_names_the_kernels_read():
             assert "$(prefix)_$(shown)_OFF" in cj and "$(prefix)_$(shown)_N" in cj
         else:
             assert re.search(r"\b%s\b" % name, cj), f"the Julia emitter never writes M::{name}"
+
+
+def test_stage_chain_model_tables(product_lib):
+    """The built-in stage chain `ragged` (state / control sizes that change along the horizon) is registered with its
+    stage types; ipddp_model_dims reports the maxima that stride the arrays."""
+    from ipddp_b200 import _lib
+    lib = _lib.Lib(_lib.LIB_PATH)
+    assert "ragged" in lib.models()
+    nstage, stages, nxt = lib.model_stages("ragged")
+    assert (nstage, nxt) == (3, 3) and stages == [(2, 3, 1, 2), (2, 3, 1, 3), (3, 2, 0, 3)]
+    assert lib.model_dims("ragged")[:3] == (3, 3, 1)
+    assert lib.model_stages("cartpole") == (1, [(4, 21, 14, 4)], 4)

@@ -119,6 +119,33 @@ def test_emulated_tma_staged_rollout(oracle_mod):
     helpers.phase_parity(lib, oracle_mod, "concar", B=2, N=7, rounds=2)
 
 
+@pytest.mark.parametrize("spec", [True, False])
+def test_emulated_stage_chain(emu, oracle_mod, spec):
+    """State and control sizes that change along the horizon (stage chain `ragged`: 2 -> 3 states, 3 -> 2 controls, a
+    constraint that disappears), bulk and speculative kernels, against the oracle's per-stage models."""
+    emu.L.ipddp_set_tuning(None, b"fw_spec_max", 148 if spec else 0)
+    emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592 if spec else 0)
+    try:
+        helpers.chain_parity(emu, oracle_mod, "ragged", 3, 13, maxit=60)
+    finally:
+        emu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
+        emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+
+
+def test_emulated_stage_chain_queue(emu, oracle_mod):
+    helpers.chain_parity(emu, oracle_mod, "ragged", 5, 9, maxit=40, queue_slots=2)
+
+
+def test_emulated_stage_chain_rejects_mismatched_stages(emu):
+    from ipddp_b200.batch import BatchSolver
+    s = BatchSolver("ragged", 2, 11, lib=emu)
+    with pytest.raises(RuntimeError, match="maps to"):
+        s.set_stage_types([0] * 10)            # type 0 keeps 2 states, the terminal cost wants 3
+    with pytest.raises(RuntimeError, match="ipddp_set_stage_types not called"):
+        s.set_inputs(np.zeros((2, 3)), np.zeros((2, 30)))
+    s.close()
+
+
 def test_emulated_varying_horizon(emu, oracle_mod):
     helpers.full_solve_parity(emu, oracle_mod, "concar", 4, 13, maxit=80, vary_horizon=True, first=100, n_trace=4)
 

@@ -168,3 +168,33 @@ def test_user_provided_derivative_constructors(oracle_mod):
     helpers.assert_same_bits(d.objective, ro.objective, "objective")
     x_sol, _ = get_trajectory(solver)
     helpers.assert_same_bits(np.concatenate(x_sol), o.array("x"), "states")
+
+
+def test_solver_with_stage_sizes_that_change_along_the_horizon(oracle_mod):
+    """The reference's constructor call with one Dynamics / Objective / Constraint / Bound per stage whose state and
+    control sizes change mid-way (README.md:18): Solver groups the stages into stage types, compiles a chain model and
+    reproduces the oracle's per-stage solve bit for bit."""
+    from ipddp_b200 import Dynamics, Objective, Constraint, Bound, Solver, solve, get_trajectory
+    from ipddp_b200.codegen import workloads
+    ch = workloads.get_chain("ragged")
+    N = 41
+    st = ch.stage_types(N)
+    dyn = [Dynamics(lambda x, u, md=md: md.f(x, u, []), md.nx, md.nu) for md in ch.stages]
+    obj = [Objective(lambda x, u, md=md: md.stage_cost(x, u, []), md.nx, md.nu) for md in ch.stages]
+    con = [Constraint(lambda x, u, md=md: md.c(x, u, []), md.nx, md.nu) if md.nc > 0 else Constraint(md.nx, md.nu) for md in ch.stages]
+    bnd = [Bound(np.array(md.lower([])), np.array(md.upper([]))) for md in ch.stages]
+    termo = Objective(lambda x, u: ch.stages[-1].term_cost(x, []), 3, 0)
+    solver = Solver(float, [dyn[k] for k in st], [obj[k] for k in st] + [termo], [con[k] for k in st] + [Constraint(3, 0)],
+                    [bnd[k] for k in st] + [Bound(float, 0)], options=None)
+    assert solver._bs.nstage == 3 and solver.stage_type == st
+    ubar = [np.asarray(ch.stages[k].u_init) for k in st] + [np.zeros(0)]
+    data = solve(solver, np.zeros(2), ubar)
+    xs, us = get_trajectory(solver)
+    o = oracle_mod.OracleChainSolver([md.name for md in ch.stages], st, N, [], [md.lower([]) for md in ch.stages],
+                                     [md.upper([]) for md in ch.stages])
+    res = o.solve(np.zeros(2), np.concatenate(ubar))
+    assert (int(data.status), int(data.k), int(data.j)) == (res.status, res.k, res.j)
+    helpers.assert_same_bits(data.objective, res.objective, "objective")
+    assert [len(x) for x in xs] == [ch.stages[k].nx for k in st] + [3] and [len(u) for u in us[:-1]] == [ch.stages[k].nu for k in st]
+    helpers.assert_same_bits(np.concatenate(xs), o.array("x"), "ragged states")
+    helpers.assert_same_bits(np.concatenate(us), o.array("u"), "ragged controls")

@@ -268,6 +268,32 @@ def test_forced_failure_statuses(gpu, oracle_mod, case):
                                                          "status9": ("concar", 16)}[case], 101)
 
 
+def test_stage_chain_parity(gpu, oracle_mod):
+    """SURVEY 8 a13 / reference README.md:18: state and control sizes that change along the horizon.  The chain model
+    `ragged` (2 -> 3 states, 3 -> 2 controls, a constraint that disappears mid-way; three stage types) on the device
+    against the oracle's per-stage models, bit for bit: resident batch (speculative kernels), bulk kernels, and streamed
+    through fewer slots than instances."""
+    helpers.chain_parity(gpu, oracle_mod, "ragged", 48, 101)
+    gpu.L.ipddp_set_tuning(None, b"fw_spec_max", 0)
+    gpu.L.ipddp_set_tuning(None, b"bw_spec_max", 0)
+    try:
+        helpers.chain_parity(gpu, oracle_mod, "ragged", 24, 61)
+    finally:
+        gpu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
+        gpu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+    helpers.chain_parity(gpu, oracle_mod, "ragged", 40, 41, queue_slots=16)
+
+
+def test_stage_chain_rejects_mismatched_stages(gpu):
+    from ipddp_b200.batch import BatchSolver
+    s = BatchSolver("ragged", 2, 11, lib=gpu)
+    with pytest.raises(RuntimeError, match="maps to"):
+        s.set_stage_types([0] * 10)            # type 0 keeps 2 states, the terminal cost wants 3
+    with pytest.raises(RuntimeError, match="ipddp_set_stage_types not called"):
+        s.set_inputs(np.zeros((2, 3)), np.zeros((2, 30)))
+    s.close()
+
+
 def test_error_convention_gpu(gpu):
     """API misuse -> return code + ipddp_last_error, algorithmic outcome -> per-instance status."""
     helpers.api_error_convention(gpu)
