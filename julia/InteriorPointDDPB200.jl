@@ -109,6 +109,8 @@ mutable struct BatchProblem
     nu::Int
     nc::Int
     np::Int
+    ns::Int          # stride of the state outputs: the largest state of any knot (= nx for a plain model)
+    nstage::Int      # stage types of the model (1 for a plain model)
     # per-instance mirror of the reference's SolverData (src/data/solver.jl:8-33), filled by solve!
     status::Vector{Cint}
     k::Vector{Cint}
@@ -153,12 +155,18 @@ function BatchProblem(model::String, B::Int, N::Int; options::Options=Options{Fl
     dims = [Ref{Cint}(0) for _ in 1:5]
     check(ccall((:ipddp_model_dims, LIB), Cint, (Cstring, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}),
                 model, dims...), "ipddp_model_dims")
+    nst = Ref{Cint}(0); nxt = Ref{Cint}(0)
+    snx = zeros(Cint, 4); snu = zeros(Cint, 4); snc = zeros(Cint, 4); snxn = zeros(Cint, 4)
+    check(ccall((:ipddp_model_stages, LIB), Cint,
+                (Cstring, Ref{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ref{Cint}), model, nst, snx, snu, snc, snxn, nxt),
+          "ipddp_model_stages")
+    ns = max(nxt[], maximum(snx[1:nst[]]), maximum(snxn[1:nst[]]))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ipddp_problem_create, LIB), Cint,
                 (Cstring, Cint, Cint, Ptr{Cint}, Cint, Ref{COptions}, Cint, Cint, Ref{Ptr{Cvoid}}),
                 model, B, N, isempty(indices_compl) ? C_NULL : pointer(indices_compl), length(indices_compl),
                 Ref(COptions(options)), device, trace_capacity, h), "ipddp_problem_create")
-    p = BatchProblem(h[], model, B, N, dims[1][], dims[2][], dims[3][], dims[4][], zeros(Cint, B), zeros(Cint, B),
+    p = BatchProblem(h[], model, B, N, dims[1][], dims[2][], dims[3][], dims[4][], Int(ns), Int(nst[]), zeros(Cint, B), zeros(Cint, B),
                      zeros(Cint, B), zeros(Cint, B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B))
     finalizer(q -> ccall((:ipddp_problem_destroy, LIB), Cint, (Ptr{Cvoid},), q.handle), p)
     return p
@@ -223,7 +231,7 @@ end
 "nominal duals (ϕ nc x (N-1) x B, zl and zu nu x (N-1) x B, λ nx x N x B): reference problem.nominal_*_duals"
 function get_duals(p::BatchProblem)
     ϕ = zeros(p.nc, p.N - 1, p.B); zl = zeros(p.nu, p.N - 1, p.B); zu = zeros(p.nu, p.N - 1, p.B)
-    λ = zeros(p.nx, p.N, p.B)
+    λ = zeros(p.ns, p.N, p.B)
     check(ccall((:ipddp_get_duals, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 p.handle, ϕ, zl, zu, λ), "ipddp_get_duals")
     return ϕ, zl, zu, λ
@@ -244,9 +252,9 @@ function get_trace(p::BatchProblem, b::Integer)
     return rows
 end
 
-"get_trajectory(solver) -> (states nx x N x B, controls nu x (N-1) x B)  (reference src/solver.jl:46-48)"
+"get_trajectory(solver) -> (states ns x N x B, controls nu x (N-1) x B)  (reference src/solver.jl:46-48); zero-padded for stage chains"
 function get_trajectory(p::BatchProblem)
-    x = zeros(p.nx, p.N, p.B)
+    x = zeros(p.ns, p.N, p.B)
     u = zeros(p.nu, p.N - 1, p.B)
     check(ccall((:ipddp_get_trajectory, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), p.handle, x, u),
           "ipddp_get_trajectory")
@@ -300,7 +308,7 @@ function solve_queue!(p::BatchProblem, x1::Matrix{Float64}, controls::Array{Floa
     Q = size(x1, 2)
     ints = [zeros(Cint, Q) for _ in 1:8]
     dbls = [zeros(Cdouble, Q) for _ in 1:7]
-    x = zeros(p.nx, p.N, Q); u = zeros(p.nu, p.N - 1, Q)
+    x = zeros(p.ns, p.N, Q); u = zeros(p.nu, p.N - 1, Q)
     GC.@preserve x1 controls params lower upper horizons ints dbls x u begin
         q = Queue(Q, pointer(x1), pointer(controls), params === nothing ? C_NULL : pointer(params), pointer(lower),
                   pointer(upper), horizons === nothing ? C_NULL : pointer(horizons), 0,
@@ -412,7 +420,10 @@ mutable struct Solver{T}
     problem::BatchProblem
     data::SolverData
     options::Options{T}
-    bound::Bound{T}
+    bounds::Vector{Bound{T}}       # one per stage type
+    stage_type::Vector{Int}        # 0-based stage type of every running stage
+    stage_nx::Vector{Int}          # per-knot sizes (ipddp_stage_layout)
+    stage_nu::Vector{Int}
     N::Int
     batch::Int
     num_parameter::Int
@@ -421,8 +432,9 @@ end
 """
     Solver(T, dynamics, objectives, constraints, bounds=nothing; options=nothing, batch=1, num_parameter=0, name=nothing)
 
-Reference src/solver.jl:11-26.  The running stages must share one Dynamics / Objective / Constraint / Bound object and the
-terminal stage has num_control = 0 and no constraints (every reference experiment has this shape).
+Reference src/solver.jl:11-26: one Dynamics / Objective / Constraint / Bound per stage.  Stages built from the same objects
+form one stage TYPE (one set of compiled device functions); a horizon may use up to 4 types, and the state and control
+sizes may change from type to type (reference README.md:18).  The terminal stage has num_control = 0 and no constraints.
 """
 function Solver(T, dynamics::Vector{Dynamics}, objectives::Vector{Objective}, constraints::Vector{Constraint},
                 bounds=nothing; options=nothing, batch::Int=1, num_parameter::Int=0, name=nothing, device::Int=0,
@@ -430,26 +442,58 @@ function Solver(T, dynamics::Vector{Dynamics}, objectives::Vector{Objective}, co
     T === Float64 || error("FP64 only (all reference experiments are Float64)")
     N = length(objectives)
     length(dynamics) + 1 == N == length(constraints) || error("need N-1 dynamics, N objectives, N constraints")
-    d, o, c, oN = dynamics[1], objectives[1], constraints[1], objectives[end]
-    all(x -> x === d, dynamics) && all(x -> x === o, objectives[1:end-1]) && all(x -> x === c, constraints[1:end-1]) ||
-        error("running stages must share one Dynamics / Objective / Constraint object")
+    oN = objectives[end]
     (oN.num_control == 0 && constraints[end].c === nothing) || error("terminal stage: num_control = 0, no constraints")
-    bound = bounds === nothing ? Bound(T, d.num_control) : bounds[1]
-    opts = options === nothing ? Options{T}() : deepcopy(options)
-    user = merge(d.user, c.user)
-    lN = (x, args...) -> oN.f(x, T[], args...)
-    sm = trace(name === nothing ? "pending" : String(name), d.f, o.f, lN, c.c, d.num_state, d.num_control;
-               num_parameter=num_parameter, qn_dynamics=d.quasi_newton, qn_constraint=c.quasi_newton,
-               indices_compl=c.indices_compl, user=user)
-    if name === nothing     # the model's identity is its traced source
-        tag = "user_" * bytes2hex(sha256(emit_device(sm)))[1:12]
-        sm = StageModel(tag, sm.nx, sm.nu, sm.nc, sm.np, sm.f, sm.l, sm.lN, sm.c, sm.mats, sm.x, sm.u, sm.v, sm.lam, sm.p,
-                        sm.indices_compl)
+    bnds = bounds === nothing ? [Bound(T, d.num_control) for d in dynamics] : bounds[1:N-1]
+    # ---- stage types: running stages built from the same objects (and equal bounds) share one type
+    keys = Any[]; stage_type = Int[]
+    for t in 1:N-1
+        key = (objectid(dynamics[t]), objectid(objectives[t]), objectid(constraints[t]), bnds[t].lower, bnds[t].upper)
+        k = findfirst(==(key), keys)
+        k === nothing && (push!(keys, key); k = length(keys))
+        push!(stage_type, k)
     end
-    load_model!(build_plugin(sm))
-    prob = BatchProblem(sm.name, batch, N; options=opts, device=device, indices_compl=Cint.(c.indices_compl .- 1),
+    length(keys) <= 4 || error("at most 4 distinct stage types per horizon")
+    last = stage_type[end]                      # the last running stage's type carries the terminal cost: it goes last
+    order = vcat([k for k in 1:length(keys) if k != last], [last])
+    rep = [findfirst(==(k), stage_type) for k in order]          # a representative stage of each type
+    stage_type = [findfirst(==(k), order) - 1 for k in stage_type]
+    opts = options === nothing ? Options{T}() : deepcopy(options)
+    lN = (x, args...) -> oN.f(x, T[], args...)
+    zeroN = (x, args...) -> 0 * x[1]
+    sms = StageModel[]
+    for (k, t) in enumerate(rep)
+        d, o, c = dynamics[t], objectives[t], constraints[t]
+        islast = k == length(rep)
+        push!(sms, trace("pending_s$(k - 1)", d.f, o.f, islast ? lN : zeroN, c.c, d.num_state, d.num_control;
+                         num_parameter=num_parameter, qn_dynamics=d.quasi_newton, qn_constraint=c.quasi_newton,
+                         indices_compl=c.indices_compl, user=merge(d.user, c.user),
+                         nx_term=islast ? oN.num_state : d.num_state))
+    end
+    chain = length(sms) > 1 || sms[1].nxn != sms[1].nx || sms[1].nxt != sms[1].nx
+    # the model's identity is its traced source
+    tag = name === nothing ? "user_" * bytes2hex(sha256(join(emit_device(sm) for sm in sms)))[1:12] : String(name)
+    if chain
+        sms = [renamed(sm, "$(tag)_s$(k - 1)") for (k, sm) in enumerate(sms)]
+        load_model!(build_plugin(tag, emit_chain(tag, sms)))
+    else
+        sms = [renamed(sms[1], tag)]
+        load_model!(build_plugin(sms[1]))
+    end
+    prob = BatchProblem(tag, batch, N; options=opts, device=device, indices_compl=Cint.(sms[1].indices_compl .- 1),
                         trace_capacity=trace_capacity)
-    return Solver{T}(prob, SolverData(), opts, bound, N, batch, num_parameter)
+    check(ccall((:ipddp_set_stage_types, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}), prob.handle, Cint.(stage_type)),
+          "ipddp_set_stage_types")
+    for (k, sm) in enumerate(sms)
+        ic = Cint.(sm.indices_compl .- 1)
+        check(ccall((:ipddp_set_stage_compl, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Cint), prob.handle, k - 1,
+                    isempty(ic) ? C_NULL : pointer(ic), length(ic)), "ipddp_set_stage_compl")
+    end
+    snx = zeros(Cint, N); snu = zeros(Cint, N); snc = zeros(Cint, N)
+    check(ccall((:ipddp_stage_layout, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), prob.handle, snx, snu, snc),
+          "ipddp_stage_layout")
+    return Solver{T}(prob, SolverData(), opts, [bnds[t] for t in rep], stage_type, Int.(snx), Int.(snu), N, batch,
+                     num_parameter)
 end
 
 unbatch(v, batch) = batch == 1 ? v[1] : v
@@ -473,15 +517,29 @@ Reference src/solve.jl:1-4.  Single instance: `x1::Vector{T}`, `controls::Vector
 empty), as in the reference.  Batched: `x1` nx x B, `controls` nu x (N-1) x B, `params` np x B, bounds nu x B.
 """
 function solve!(s::Solver{T}, x1::Vector{T}, controls::Vector{Vector{T}}; params=nothing, kw...) where T
-    u = reduce(hcat, controls[1:s.N-1])
-    return solve!(s, repeat(reshape(x1, :, 1), 1, s.batch), repeat(reshape(u, size(u, 1), size(u, 2), 1), 1, 1, s.batch);
+    p = s.problem
+    x1p = zeros(T, p.nx); x1p[1:length(x1)] .= x1              # a chain's first stage may have fewer states than the largest
+    u = zeros(T, p.nu, s.N - 1)                                 # per-stage control vectors padded to the largest size
+    for t in 1:s.N-1
+        u[1:length(controls[t]), t] .= controls[t]
+    end
+    return solve!(s, repeat(reshape(x1p, :, 1), 1, s.batch), repeat(reshape(u, size(u, 1), size(u, 2), 1), 1, 1, s.batch);
                   params=params === nothing ? nothing : repeat(reshape(params, :, 1), 1, s.batch), kw...)
 end
 function solve!(s::Solver{T}, x1::Matrix{T}, controls::Array{T,3}; params=nothing, lower=nothing, upper=nothing,
                 horizons=nothing) where T
-    lo = lower === nothing ? repeat(reshape(s.bound.lower, :, 1), 1, s.batch) : lower
-    up = upper === nothing ? repeat(reshape(s.bound.upper, :, 1), 1, s.batch) : upper
-    solve!(s.problem, x1, controls; params=params, lower=lo, upper=up, horizons=horizons)
+    p = s.problem
+    function padded(get, fill)       # one bound vector per stage type, padded to the largest control size: nu*ntypes x B
+        m = fill .* ones(T, p.nu, length(s.bounds))
+        for (k, b) in enumerate(s.bounds)
+            v = get(b)
+            m[1:length(v), k] .= v
+        end
+        return repeat(reshape(m, :, 1), 1, s.batch)
+    end
+    lo = lower === nothing ? padded(b -> b.lower, -T(Inf)) : lower
+    up = upper === nothing ? padded(b -> b.upper, T(Inf)) : upper
+    solve!(p, x1, controls; params=params, lower=lo, upper=up, horizons=horizons)
     return fill_data!(s)
 end
 "solve!(solver): warm start from the stored nominal trajectory (reference src/solve.jl:6-17)"
@@ -491,7 +549,7 @@ solve!(s::Solver) = (solve!(s.problem); fill_data!(s))
 function get_trajectory(s::Solver)
     x, u = get_trajectory(s.problem)
     s.batch == 1 || return x, u
-    return [x[:, t, 1] for t in 1:s.N], vcat([u[:, t, 1] for t in 1:s.N-1], [Float64[]])
+    return [x[1:s.stage_nx[t], t, 1] for t in 1:s.N], vcat([u[1:s.stage_nu[t], t, 1] for t in 1:s.N-1], [Float64[]])
 end
 
 end # module

@@ -34,6 +34,8 @@ struct StageModel
     nu::Int
     nc::Int
     np::Int
+    nxn::Int                  # size of the next state f maps to (may differ from nx inside a stage chain)
+    nxt::Int                  # size of the state the terminal cost is evaluated on
     f::Vector{Num}            # x+ = f(x, u[, p])
     l::Num                    # stage cost
     lN::Num                   # terminal cost (x[, p])
@@ -45,7 +47,12 @@ struct StageModel
     lam::Vector{Num}
     p::Vector{Num}
     indices_compl::Vector{Int}   # 1-based, as in the reference
+    xt::Vector{Num}              # the terminal cost's state symbols
 end
+
+"the same stage under another name (the model's name is derived from its emitted source)"
+renamed(sm::StageModel, name::String) = StageModel(name, sm.nx, sm.nu, sm.nc, sm.np, sm.nxn, sm.nxt, sm.f, sm.l, sm.lN, sm.c,
+                                                   sm.mats, sm.x, sm.u, sm.v, sm.lam, sm.p, sm.indices_compl, sm.xt)
 
 call_with_p(fn, args, p) = applicable(fn, args..., p) ? fn(args..., p) : fn(args...)
 
@@ -58,19 +65,19 @@ stage type.  `user` may hold user-provided derivative closures ("fx", "fu", "vfx
 src/constraints.jl:60-64): they are traced instead of differentiated and missing contractions stay zero.
 """
 function trace(name, f, l, lN, c, nx::Int, nu::Int; num_parameter::Int=0, qn_dynamics::Bool=false,
-               qn_constraint::Bool=false, indices_compl=Int[], user=Dict{String,Function}())
+               qn_constraint::Bool=false, indices_compl=Int[], user=Dict{String,Function}(), nx_term::Int=nx)
     x = Symbolics.variables(:x, 1:nx)
     u = Symbolics.variables(:u, 1:nu)
     p = Symbolics.variables(:p, 1:max(num_parameter, 1))
     y = collect(call_with_p(f, (x, u), p))
-    nxn = length(y)
-    nxn == nx || error("state dimension must be constant along a stage type (got $nx -> $nxn)")
+    nxn = length(y)          # a stage of a chain may map onto a state of another size
     cv = c === nothing ? Num[] : collect(call_with_p(c, (x, u), p))
     nc = length(cv)
     v = Symbolics.variables(:v, 1:max(nc, 1))
     lam = Symbolics.variables(:lam, 1:nxn)
     lval = call_with_p(l, (x, u), p)
-    lNval = call_with_p(lN, (x,), p)
+    xt = nx_term == nx ? x : Symbolics.variables(:x, 1:nx_term)     # the terminal cost may see a state of another size
+    lNval = call_with_p(lN, (xt,), p)
     m = Dict{String,Matrix{Num}}()
     usr(key, args...) = haskey(user, key) ? Matrix{Num}(call_with_p(user[key], args, p)) : nothing
     pick(key, auto, args...; group_user=false, rows=0, cols=0) = begin
@@ -100,10 +107,10 @@ function trace(name, f, l, lN, c, nx::Int, nu::Int; num_parameter::Int=0, qn_dyn
         m["vfux"] = pick("vfux", () -> sum(lam[t] .* Symbolics.jacobian(Symbolics.gradient(y[t], u), x) for t in 1:nxn), x, u, lam; group_user=udyn, rows=nu, cols=nx)
         m["vfuu"] = pick("vfuu", () -> sum(lam[t] .* Symbolics.hessian(y[t], u) for t in 1:nxn), x, u, lam; group_user=udyn, rows=nu, cols=nu)
     end
-    lNx = Symbolics.gradient(lNval, x)
-    m["Nlx"] = reshape(lNx, :, 1); m["Nlxx"] = Symbolics.jacobian(lNx, x)
-    return StageModel(String(name), nx, nu, nc, num_parameter, y, lval, lNval, cv, m, x, u, v, lam, p,
-                      collect(Int, indices_compl))
+    lNx = Symbolics.gradient(lNval, xt)
+    m["Nlx"] = reshape(lNx, :, 1); m["Nlxx"] = Symbolics.jacobian(lNx, xt)
+    return StageModel(String(name), nx, nu, nc, num_parameter, nxn, nx_term, y, lval, lNval, cv, m, x, u, v, lam, p,
+                      collect(Int, indices_compl), xt)
 end
 
 isconst_entry(e::Num) = isempty(Symbolics.get_variables(e))
@@ -175,7 +182,7 @@ function emit_device(sm::StageModel)
     dn_entries, dn_dyn = classify(sm, dn_names, consts)
     all_entries = vcat(d_entries, vf_entries, dn_entries)
     fu = sm.mats["fu"]
-    fucol = [j - 1 for j in 1:sm.nu if any(!iszero(Symbolics.value(fu[i, j])) for i in 1:sm.nx)]
+    fucol = [j - 1 for j in 1:sm.nu if any(!iszero(Symbolics.value(fu[i, j])) for i in 1:sm.nxn)]
     fuidx = fill(255, sm.nu)
     for (c, j) in enumerate(fucol)
         fuidx[j+1] = c - 1
@@ -199,8 +206,8 @@ function emit_device(sm::StageModel)
     println(io, "}")
     println(io, "struct Model_$n {")
     println(io, "  static constexpr const char* NAME = \"$n\";")
-    println(io, "  static constexpr int NX = $(sm.nx), NU = $(sm.nu), NC = $(sm.nc), NXN = $(sm.nx), NP = $(sm.np);")
-    println(io, "  static constexpr int NXT = $(sm.nx);   // state size the terminal cost is evaluated on")
+    println(io, "  static constexpr int NX = $(sm.nx), NU = $(sm.nu), NC = $(sm.nc), NXN = $(sm.nxn), NP = $(sm.np);")
+    println(io, "  static constexpr int NXT = $(sm.nxt);   // state size the terminal cost is evaluated on")
     println(io, "  // a plain model is a chain of one stage type (ipk::for_stage); chains of several types: generate.py")
     println(io, "  static constexpr int NSTAGE = 1;")
     println(io, "  template <int I> using Stage = Model_$n;")
@@ -228,7 +235,7 @@ function emit_device(sm::StageModel)
     println(io, "  static IPDDP_D void cost(const double* __restrict__ x, const double* __restrict__ u, const double* __restrict__ p, double* __restrict__ du) {")
     void_args(io, ("x", "u", "p")); print(io, c_body([sm.l], [xa, ua, pa], [:x, :u, :p])); println(io, "  }")
     println(io, "  static IPDDP_D void costN(const double* __restrict__ x, const double* __restrict__ p, double* __restrict__ du) {")
-    void_args(io, ("x", "p")); print(io, c_body([sm.lN], [xa, pa], [:x, :p])); println(io, "  }")
+    void_args(io, ("x", "p")); print(io, c_body([sm.lN], [sm.xt, pa], [:x, :p])); println(io, "  }")
     println(io, "  static IPDDP_D void con(const double* __restrict__ x, const double* __restrict__ u, const double* __restrict__ p, double* __restrict__ du) {")
     void_args(io, ("x", "u", "p", "du")); print(io, c_body(sm.c, [xa, ua, pa], [:x, :u, :p])); println(io, "  }")
     # tile functions: du[k] = e  ->  st(k, e)
@@ -238,9 +245,38 @@ function emit_device(sm::StageModel)
     println(io, "  template <class Store> static IPDDP_D void vf(const double* __restrict__ x, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ p, Store st) {")
     void_args(io, ("x", "u", "v", "p")); print(io, store_calls(c_body(vf_dyn, [xa, ua, sm.lam, pa], [:x, :u, :v, :p]))); println(io, "  }")
     println(io, "  template <class Store> static IPDDP_D void derivsN(const double* __restrict__ x, const double* __restrict__ p, Store st) {")
-    void_args(io, ("x", "p")); print(io, store_calls(c_body(dn_dyn, [xa, pa], [:x, :p]))); println(io, "  }")
+    void_args(io, ("x", "p")); print(io, store_calls(c_body(dn_dyn, [sm.xt, pa], [:x, :p]))); println(io, "  }")
     println(io, "};")
     println(io, "#undef sin\n#undef cos\n#undef tan\n#undef log\n#undef exp\n#undef pow\n#undef sqrt")
+    return String(take!(io))
+end
+
+"""
+    emit_chain(name, stages::Vector{StageModel}) -> String
+
+Header of a stage chain (state / control sizes that change along the horizon; reference README.md:18): the stage structs
+plus the composite `Model_<name>` the kernels are instantiated with -- NSTAGE, `Stage<I>`, `Terminal` (the last stage type)
+and the maxima over the stage types under the usual names, which size every buffer and stride (the same layout as
+interiorpointddp.jl_b200/codegen/generate.py:emit_device_chain).
+"""
+function emit_chain(name::String, stages::Vector{StageModel})
+    io = IOBuffer()
+    println(io, "// GENERATED by julia/codegen.jl -- stage chain '$name'.\n#pragma once")
+    for sm in stages
+        print(io, replace(emit_device(sm), "#pragma once\n" => ""))
+    end
+    S = ["Model_$(sm.name)" for sm in stages]
+    mx(f) = "ipk::cmax(" * join(("$s::$f" for s in S), ", ") * ")"
+    println(io, "struct Model_$name {")
+    println(io, "  static constexpr const char* NAME = \"$name\";")
+    println(io, "  static constexpr int NSTAGE = $(length(S));")
+    println(io, "  template <int I> using Stage = typename ipk::TypeAt<I, $(join(S, ", "))>::type;")
+    println(io, "  using Terminal = $(S[end]);")
+    for f in ("NX", "NU", "NC", "NXN", "NP", "D_NSLOT", "VF_NSLOT", "FU_NC")
+        println(io, "  static constexpr int $f = $(mx(f));")
+    end
+    println(io, "  static constexpr int NXT = Terminal::NXT, DN_NSLOT = Terminal::DN_NSLOT;")
+    println(io, "};")
     return String(take!(io))
 end
 
@@ -251,18 +287,18 @@ end
 emitted source and of the kernel headers it embeds, so a changed closure or a changed library version never reuses a
 stale plugin.  Flags as in interiorpointddp.jl_b200/build.py (sm_100a, no implicit FMA contraction).
 """
-function build_plugin(sm::StageModel; csrc::AbstractString=get(ENV, "IPDDP_B200_CSRC", ""), outdir::AbstractString=mktempdir(),
-                      nvcc::AbstractString=get(ENV, "NVCC", "nvcc"))
+build_plugin(sm::StageModel; kw...) = build_plugin(sm.name, emit_device(sm); kw...)
+function build_plugin(name::AbstractString, src::AbstractString; csrc::AbstractString=get(ENV, "IPDDP_B200_CSRC", ""),
+                      outdir::AbstractString=mktempdir(), nvcc::AbstractString=get(ENV, "NVCC", "nvcc"))
     isdir(csrc) || error("IPDDP_B200_CSRC must point at interiorpointddp.jl_b200/csrc (kernel templates)")
-    src = emit_device(sm)
     hdrs = join((read(joinpath(csrc, f), String) for f in sort(readdir(csrc)) if endswith(f, ".cuh") || endswith(f, ".h")))
     tag = bytes2hex(sha256(src * hdrs))[1:12]
-    so = joinpath(outdir, "$(sm.name)_$tag.so")
+    so = joinpath(outdir, "$(name)_$tag.so")
     isfile(so) && return so
-    cuh = joinpath(outdir, "$(sm.name)_$tag.cuh")
-    cu = joinpath(outdir, "$(sm.name)_$tag.cu")
+    cuh = joinpath(outdir, "$(name)_$tag.cuh")
+    cu = joinpath(outdir, "$(name)_$tag.cu")
     write(cuh, src)
-    write(cu, "#include \"$cuh\"\n#include \"model_register.cuh\"\nIPDDP_REGISTER_MODEL(Model_$(sm.name), ipddp_plugin_vtable)\n")
+    write(cu, "#include \"$cuh\"\n#include \"model_register.cuh\"\nIPDDP_REGISTER_MODEL(Model_$(name), ipddp_plugin_vtable)\n")
     run(`$nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC
          -Xcompiler -fno-gnu-unique -I$csrc -shared $cu -o $so`)
     return so
