@@ -200,8 +200,8 @@ class BatchSolver:
         if n < 0:
             raise KeyError(f"{name}: {self.lib.L.ipddp_last_error().decode()}")
         out = np.zeros(int(n))
-        if n:
-            self.lib.L.ipddp_get_array(self.h, name.encode(), dptr(out))
+        if n and self.lib.L.ipddp_get_array(self.h, name.encode(), dptr(out)) < 0:
+            raise RuntimeError(f"ipddp_get_array({name}) failed: {self.lib.L.ipddp_last_error().decode()}")
         return out
 
     def trace(self, b: int) -> np.ndarray:

@@ -145,12 +145,15 @@ __global__ void k_test_ldlt(int nmat, const double* A, const double* Bm, double*
   if (m >= nmat) return;
   constexpr int n = N, kp = N * (N + 1) / 2;
   double* lhs = sm;
-  double* rhs = lhs + kp;
-  double* ws = rhs + n * 5;
+  double* rhs = lhs + ((kp + 1) & ~1);
+  double* ws = rhs + ((n * 6 + 1) & ~1);
   unsigned char* scratch = reinterpret_cast<unsigned char*>(ws + 4 * n);
   for (int j = 0; j < n; ++j)
     for (int i = lane; i <= j; i += 32) lhs[ipk::pk(i, j)] = A[(size_t)m * n * n + i + (size_t)j * n];
-  for (int e = lane; e < n * 5; e += 32) rhs[e] = Bm[(size_t)m * n * 5 + e];
+  typedef ipk::RhsL<N, 5> RL;
+  for (int e = lane; e < RL::SIZE; e += 32) rhs[e] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < n * 5; e += 32) rhs[RL::at(e % n, e / n)] = Bm[(size_t)m * n * 5 + e];
   __syncwarp();
   int np = 0;
   const int info = ipk::warp_ldlt_factor<N, 5>(lhs, rhs, ws, scratch, lane, 1e-12, np, ipk::ldlt_tri_lane(lane));
@@ -158,7 +161,7 @@ __global__ void k_test_ldlt(int nmat, const double* A, const double* Bm, double*
   __syncwarp();
   for (int j = 0; j < n; ++j)
     for (int i = lane; i <= j; i += 32) Aout[(size_t)m * n * n + i + (size_t)j * n] = lhs[ipk::pk(i, j)];
-  for (int e = lane; e < n * 5; e += 32) X[(size_t)m * n * 5 + e] = rhs[e];
+  for (int e = lane; e < n * 5; e += 32) X[(size_t)m * n * 5 + e] = rhs[RL::at(e % n, e / n)];
   for (int e = lane; e < n; e += 32) ipiv_out[(size_t)m * n + e] = ipk::LdltScratch<N>::ipiv_of(ipk::LdltScratch<N>::info(scratch)[e]);
   if (lane == 0) { info_out[m] = info; np_out[m] = np; }
 }
@@ -1252,7 +1255,7 @@ int ipddp_test_ldlt(int n, int nmat, const double* A, const double* Bm, double* 
   CK(cudaMemcpy(dB, Bm, sb, cudaMemcpyHostToDevice));
   CK(cudaMemset(dAo, 0, sa));
   const int kp = n * (n + 1) / 2;
-  const size_t smem = ((size_t)(kp + n * 5 + 4 * n) * 8 + ((size_t)n * 21 + 15) / 16 * 16 + 31) / 16 * 16;
+  const size_t smem = ((size_t)(kp + 2 + n * 6 + 2 + 4 * n) * 8 + ((size_t)n * 21 + 15) / 16 * 16 + 31) / 16 * 16;
 #define IPDDP_LDLT_CASE(NN) case NN: IPDDP_LAUNCH((k_test_ldlt<NN>), nmat, 32, smem, 0, nmat, dA, dB, dAo, dip, dinfo, dnp, dX); break;
   switch (n) {
     IPDDP_LDLT_CASE(1) IPDDP_LDLT_CASE(2) IPDDP_LDLT_CASE(3) IPDDP_LDLT_CASE(4) IPDDP_LDLT_CASE(5) IPDDP_LDLT_CASE(8)

@@ -34,8 +34,8 @@ template <class M> struct BwLayout {
   static constexpr int mx(int a, int b) { return a > b ? a : b; }
   // offsets in doubles
   static constexpr int LHS = 0;
-  static constexpr int RHS = LHS + pad(KP);          // K x NR: assembled as [Qu B; c cx], negated, solved -> [alpha beta; psi omega]
-  static constexpr int FX = RHS + pad(K * NR);       // NXN x NX (row index = next-state component)
+  static constexpr int RHS = LHS + ((pad(KP) + 1) & ~1);   // (16-byte aligned) K x NR: assembled as [Qu B; c cx], negated, solved -> [alpha beta; psi omega]
+  static constexpr int FX = RHS + ((pad(RhsL<(K > 0 ? K : 1), NR>::SIZE) + 1) & ~1);   // NXN x NX (row index = next-state component)
   static constexpr int NFU = M::FU_NC;               // controls the dynamics depend on (non-zero columns of fu)
   static constexpr int FU = FX + NS * NS;            // NXN x NFU, compact: column c belongs to control fu_col(c)
   static constexpr int VXX = FU + pad(NS * NFU);     // value Hessian of knot t+1
@@ -166,6 +166,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
   typedef BwLayout<M> L;
   typedef Rec<S> R;
   constexpr int NX = S::NX, NN = S::NXN, NU = S::NU, NC = S::NC, K = NU + NC, NR = NX + 1, NFU = S::FU_NC;
+  typedef RhsL<K, NR> RL;          // layout of the K x NR right-hand sides in shared memory (ldlt_warp.cuh)
   IPDDP_BW_POINTERS(S)
   const double reg = sw.reg, mu = sw.mu;
   const bool second_order = sw.second_order;
@@ -187,7 +188,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
     }
     for (int e = lane; e < NC; e += 32) phi[e] = r[R::PHI + e];
     for (int e = lane; e < K * (K + 1) / 2; e += 32) lhs[e] = 0.0;
-    for (int e = lane; e < K * NR; e += 32) rhs[e] = 0.0;
+    for (int e = lane; e < RL::SIZE; e += 32) rhs[e] = 0.0;
     for (int e = lane; e < NX * NX; e += 32) Cm[e] = 0.0;
     for (int e = lane; e < NX; e += 32) lx[e] = 0.0;
     __syncwarp();
@@ -196,12 +197,12 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
     for (int e = lane; e < S::D_fx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_fx_OFF + e); if (q.slot >= 0) fx[q.i + q.j * NN] = tile[q.slot]; }
     for (int e = lane; e < S::D_fu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_fu_OFF + e); if (q.slot >= 0) fu[q.i + S::fu_idx(q.j) * NN] = tile[q.slot]; }
     for (int e = lane; e < S::D_cu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_cu_OFF + e); lhs[pk(q.j, NU + q.i)] = val(q); }
-    for (int e = lane; e < S::D_cx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_cx_OFF + e); rhs[NU + q.i + (1 + q.j) * K] = val(q); }
-    for (int e = lane; e < S::D_lu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lu_OFF + e); rhs[q.i] = val(q); }
-    for (int e = lane; e < S::D_lux_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lux_OFF + e); rhs[q.i + (1 + q.j) * K] = val(q); }
+    for (int e = lane; e < S::D_cx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_cx_OFF + e); rhs[RL::at(NU + q.i, 1 + q.j)] = val(q); }
+    for (int e = lane; e < S::D_lu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lu_OFF + e); rhs[RL::at(q.i, 0)] = val(q); }
+    for (int e = lane; e < S::D_lux_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lux_OFF + e); rhs[RL::at(q.i, 1 + q.j)] = val(q); }
     for (int e = lane; e < S::D_lxx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lxx_OFF + e); Cm[q.i + q.j * NX] = val(q); }
     for (int e = lane; e < S::D_lx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_lx_OFF + e); lx[q.i] = val(q); }
-    for (int e = lane; e < NC; e += 32) rhs[NU + e] = r[R::C + e];
+    for (int e = lane; e < NC; e += 32) rhs[RL::at(NU + e, 0)] = r[R::C + e];
     __syncwarp();
     // ---- barrier terms, Qu, dual-infeasibility numerator            (src/backward_pass.jl:62-75)
     for (int i = lane; i < NU; i += 32) {
@@ -215,7 +216,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
       const double zl_i = r[R::ZL + i], zu_i = r[R::ZU + i];
       const double cl = a1 * mu, cu_ = a2 * mu;
       ra1[i] = a1; ra2[i] = a2;
-      const double lu_i = rhs[i];
+      const double lu_i = rhs[RL::at(i, 0)];
       double dq = 0.0;   // cu' phi
       {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -237,7 +238,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
       q = (ci != 255 ? dot4c<NN>(fu + ci * NN, 1, Vx, 1) : 0.0) + q;
       q -= cl;
       q += cu_;
-      rhs[i] = q;   // Qu
+      rhs[RL::at(i, 0)] = q;   // Qu
       // dual error numerator: lu + cu'phi - zl + zu + fu'lambda+      (src/solve.jl:127-132)
       double d = dq + lu_i;
       d -= zl_i;
@@ -281,7 +282,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
     for (int e = lane; e < NFU * NX; e += 32) {             // B += (fu' Vxx+) fx: rows outside the fu columns get +0
       const int a = e % NFU, j = e / NFU;
       const int i = S::fu_col(a);
-      rhs[i + (1 + j) * K] = dot4c<NN>(uxt + a, NFU, fx + j * NN, 1) + rhs[i + (1 + j) * K];
+      rhs[RL::at(i, 1 + j)] = dot4c<NN>(uxt + a, NFU, fx + j * NN, 1) + rhs[RL::at(i, 1 + j)];
     }
     __syncwarp();
     // ---- H += luu
@@ -296,12 +297,12 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
           for (int s_ = 0; s_ < S::VF_NSLOT; ++s_) vfs[s_] = vfl[s_];
         __syncwarp();
         for (int e = lane; e < S::VF_vfxx_N; e += 32) { const MEntry q = ld_entry(tbl + S::VF_vfxx_OFF + e); Cm[q.i + q.j * NX] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
-        for (int e = lane; e < S::VF_vfux_N; e += 32) { const MEntry q = ld_entry(tbl + S::VF_vfux_OFF + e); rhs[q.i + (1 + q.j) * K] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
+        for (int e = lane; e < S::VF_vfux_N; e += 32) { const MEntry q = ld_entry(tbl + S::VF_vfux_OFF + e); rhs[RL::at(q.i, 1 + q.j)] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
         for (int e = lane; e < S::VF_vfuu_N; e += 32) { const MEntry q = ld_entry(tbl + S::VF_vfuu_OFF + e); lhs[pk(q.i, q.j)] += (q.slot >= 0 ? vfs[q.slot] : IPDDP_LDG(cst - 1 - q.slot)); }
         __syncwarp();
       }
       for (int e = lane; e < S::D_vcuu_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_vcuu_OFF + e); lhs[pk(q.i, q.j)] += val(q); }
-      for (int e = lane; e < S::D_vcux_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_vcux_OFF + e); rhs[q.i + (1 + q.j) * K] += val(q); }
+      for (int e = lane; e < S::D_vcux_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_vcux_OFF + e); rhs[RL::at(q.i, 1 + q.j)] += val(q); }
       for (int e = lane; e < S::D_vcxx_N; e += 32) { const MEntry q = ld_entry(tbl + S::D_vcxx_OFF + e); Cm[q.i + q.j * NX] += val(q); }
       __syncwarp();
     }
@@ -313,7 +314,10 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
     //      and negate in place: rhs = -[Qu B; c cx]                    (:129-136)
     double* g = out.gains + (size_t)t * v.G;
     double* qo = out.Qu + (size_t)t * M::NU;
-    for (int e = lane; e < K * NR; e += 32) { const double w = rhs[e]; g[e] = w; rhs[e] = w * -1.0; if (e < NU) qo[e] = w; }
+    for (int e = lane; e < K * NR; e += 32) {     // e = position in the column-major gains block (row e % K, column e / K)
+      const int jc = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)K + 1u)), rr = e - jc * K;
+      const double w = rhs[RL::at(rr, jc)]; g[e] = w; rhs[RL::at(rr, jc)] = w * -1.0; if (e < NU) qo[e] = w;
+    }
     __syncwarp();
     // ---- factorise + inertia                                          (src/inertia_correction.jl:257-276)
     int np = 0;
@@ -328,7 +332,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
       const int j = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)NU + 1u));   // e / NU (the signed division compiles to ~20 instructions)
       const int i = e - j * NU;
       if (j == 0) {
-        const double al = rhs[i];
+        const double al = rhs[RL::at(i, 0)];
         double cl = ra1[i] * mu;      // chi^L = mu / il, recomputed from the stored reciprocal (same operands, same bits)
         cl -= r[R::ZL + i];
         cl -= t1[i] * al;
@@ -338,7 +342,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
         gi[i] = cl;
         gi[NU + i] = cu_;
       } else {
-        const double be = rhs[i + j * K];
+        const double be = rhs[RL::at(i, j)];
         gi[i + j * 2 * NU] = (be * t1[i]) * -1.0;
         gi[NU + i + j * 2 * NU] = be * t2[i];
       }
@@ -359,9 +363,9 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
 #pragma unroll
           for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; pc[qq] = (q < NC) ? IPDDP_LDCG(g + NU + q + (1 + j) * K) : 0.0; }
 #pragma unroll
-          for (int qq = 0; qq < (NU + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NU) sa = IPDDP_FMA(rhs[q + (1 + i) * K], pu[qq], sa); }
+          for (int qq = 0; qq < (NU + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NU) sa = IPDDP_FMA(rhs[RL::at(q, 1 + i)], pu[qq], sa); }
 #pragma unroll
-          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NC) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], pc[qq], sb); }
+          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NC) sb = IPDDP_FMA(rhs[RL::at(NU + q, 1 + i)], pc[qq], sb); }
         }
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
@@ -388,9 +392,9 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
 #pragma unroll
           for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NC) sc = IPDDP_FMA(px[qq], phi[q], sc); }               // cx' phi
 #pragma unroll
-          for (int qq = 0; qq < (NU + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NU) sa = IPDDP_FMA(rhs[q + (1 + i) * K], pq[qq], sa); }   // beta' Qu
+          for (int qq = 0; qq < (NU + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NU) sa = IPDDP_FMA(rhs[RL::at(q, 1 + i)], pq[qq], sa); }   // beta' Qu
 #pragma unroll
-          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NC) sb = IPDDP_FMA(rhs[NU + q + (1 + i) * K], pc[qq], sb); }   // omega' c
+          for (int qq = 0; qq < (NC + 3) / 4; ++qq) { const int q = g4 + 4 * qq; if (q < NC) sb = IPDDP_FMA(rhs[RL::at(NU + q, 1 + i)], pc[qq], sb); }   // omega' c
         }
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
         sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
@@ -412,7 +416,10 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
       }
     }
     __syncwarp();
-    for (int e = lane; e < K * NR; e += 32) g[e] = rhs[e];   // eq gains replace the parked copy
+    for (int e = lane; e < K * NR; e += 32) {     // eq gains replace the parked copy
+      const int jc = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)K + 1u)), rr = e - jc * K;
+      g[e] = rhs[RL::at(rr, jc)];
+    }
     for (int e = lane; e < NX * NX; e += 32) Vxx[e] = nVxx[e];
     for (int e = lane; e < NX; e += 32) {
       Vx[e] = nVx[e];

@@ -140,9 +140,36 @@ IPDDP_D int warp_compact(bool f0, bool f1, unsigned char* list, int lane, unsign
   return n;
 }
 
-template <int NR> IPDDP_D void warp_swap_rows(double* Bm, int ld, int a, int b, int lane) {
-  if (lane < NR) { const double t = Bm[a + lane * ld]; Bm[a + lane * ld] = Bm[b + lane * ld]; Bm[b + lane * ld] = t; }
-}
+// Access to the K x NR right-hand sides in shared memory (column-major: element (r, j) at r + j K).  The first solve loop
+// touches whole rows -- row k broadcast, row i updated, row interchanges -- NR = nx + 1 doubles each; all loads of a row
+// update are issued before its FMAs.  (A row-major layout with rows padded to 16 bytes and 128-bit accesses was measured
+// and lost 0.7 %: profiles/r2_ab/summary.md, series 4.)
+template <int K, int NR> struct RhsL {
+  static constexpr int LD = NR;
+  static constexpr int SIZE = K * NR;
+  static IPDDP_D int at(int r, int j) { return r + j * K; }
+  static IPDDP_D void load_row(const double* B, int r, double (&v)[LD]) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) v[j] = B[r + j * K];
+  }
+  static IPDDP_D void store_row(double* B, int r, const double (&v)[LD]) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) B[r + j * K] = v[j];
+  }
+  // B(i,:) = fma(x, -B(k,:), B(i,:)) for one row i by one lane (the dger of dsytrs_rook's first loop)
+  static IPDDP_D void downdate_row(double* B, int i, int k, double x) {
+    double bk[LD], bi[LD];
+    load_row(B, k, bk);
+    load_row(B, i, bi);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) bi[j] = IPDDP_FMA(x, -bk[j], bi[j]);
+    store_row(B, i, bi);
+  }
+  // rows a <-> b
+  static IPDDP_D void swap_rows(double* B, int a, int b, int lane) {
+    if (lane < NR) { const double t = B[a + lane * K]; B[a + lane * K] = B[b + lane * K]; B[b + lane * K] = t; }
+  }
+};
 
 // Scratch used by the factorisation and kept for the second solve (base must be 8-byte aligned):
 // dinv: K doubles (deferred 1/a_kk row scalings, 1.0 where the step scaled in place); info: K 64-bit words, low half =
@@ -218,7 +245,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
   __syncwarp();
   if (kstep == 2 && p != k) {   // first interchange: k <-> p  (matrix and right-hand sides)
     warp_sym_swap<TWO>(A, p, k, lane, two);
-    warp_swap_rows<NR>(Bm, K, k, p, lane);
+    RhsL<K, NR>::swap_rows(Bm, k, p, lane);
     __syncwarp();
   }
   const int kk = k - kstep + 1;
@@ -228,7 +255,7 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       const int pa = pk(k - 1, k), pb = pk(kp, k);
       const double t = A[pa]; A[pa] = A[pb]; A[pb] = t;
     }
-    warp_swap_rows<NR>(Bm, K, kk, kp, lane);
+    RhsL<K, NR>::swap_rows(Bm, kk, kp, lane);
     __syncwarp();
   }
   if (kstep == 1) {
@@ -268,16 +295,10 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
     }
     if (lane == 0) { cinfo[k] = S::pack(m0, kp + 1); nzhi[k] = m1; dinv[k] = 1.0; }
     // dsytrs first loop for this pivot: B(0:k-1,:) -= x * B(k,:), then B(k,:) *= 1/akk
-    if (x0 != 0.0) {
-#pragma unroll
-      for (int j = 0; j < NR; ++j) Bm[i0 + j * K] = IPDDP_FMA(x0, -Bm[k + j * K], Bm[i0 + j * K]);
-    }
-    if (two && x1 != 0.0) {
-#pragma unroll
-      for (int j = 0; j < NR; ++j) Bm[i1 + j * K] = IPDDP_FMA(x1, -Bm[k + j * K], Bm[i1 + j * K]);
-    }
+    if (x0 != 0.0) RhsL<K, NR>::downdate_row(Bm, i0, k, x0);
+    if (two && x1 != 0.0) RhsL<K, NR>::downdate_row(Bm, i1, k, x1);
     __syncwarp();
-    if (lane < NR) Bm[k + lane * K] = Bm[k + lane * K] * rinv;
+    if (lane < NR) Bm[RhsL<K, NR>::at(k, lane)] = Bm[RhsL<K, NR>::at(k, lane)] * rinv;
     __syncwarp();
   } else {
     double* xk = A + ck;
@@ -360,20 +381,24 @@ IPDDP_D int ldlt_step(int k, double* __restrict__ A, double* __restrict__ Bm, do
       const int i = lane + 32 * s;
       if ((fm >> s) & 1u) {
         const double xa = xk[i], xb = xkm1[i];
+        typedef RhsL<K, NR> RL;
+        double bk[RL::LD], bkm[RL::LD], bi[RL::LD];
+        RL::load_row(Bm, k, bk); RL::load_row(Bm, k - 1, bkm); RL::load_row(Bm, i, bi);
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
-          const double bv = IPDDP_FMA(xa, -Bm[k + j * K], Bm[i + j * K]);
-          Bm[i + j * K] = IPDDP_FMA(xb, -Bm[k - 1 + j * K], bv);
+          const double bv = IPDDP_FMA(xa, -bk[j], bi[j]);
+          bi[j] = IPDDP_FMA(xb, -bkm[j], bv);
         }
+        RL::store_row(Bm, i, bi);
       }
     }
     __syncwarp();
     if (lane < NR) {
       // akm1 = a(k-1,k-1)/d12 = d22, ak = a(k,k)/d12 = d11, denom = akm1*ak - 1 = d11*d22 - 1 (same product)
-      const double bkm1 = by12(Bm[k - 1 + lane * K]);
-      const double bk = by12(Bm[k + lane * K]);
-      Bm[k - 1 + lane * K] = bydn(d11 * bkm1 - bk);
-      Bm[k + lane * K] = bydn(d22 * bk - bkm1);
+      const double bkm1 = by12(Bm[RhsL<K, NR>::at(k - 1, lane)]);
+      const double bk = by12(Bm[RhsL<K, NR>::at(k, lane)]);
+      Bm[RhsL<K, NR>::at(k - 1, lane)] = bydn(d11 * bkm1 - bk);
+      Bm[RhsL<K, NR>::at(k, lane)] = bydn(d22 * bk - bkm1);
     }
     __syncwarp();
   }
@@ -421,7 +446,7 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
     //      old column k) and the row interchange of the right-hand sides
     if (in && lane != imax) A[pa] = x;
     if (lane == 0) { A[ci + imax] = piv; A[ck + k] = aii; }
-    if (lane < NR) { double* bl = Bm + lane * K; const double t = bl[k]; bl[k] = bl[imax]; bl[imax] = t; }
+    RhsL<K, NR>::swap_rows(Bm, k, imax, lane);
     x = (lane == imax) ? x : (in ? a : 0.0);
     piv = aii;
     kp = imax;
@@ -457,8 +482,7 @@ IPDDP_D bool ldlt_step_fast(int k, double* __restrict__ A, double* __restrict__ 
     const double xs = x * rinv;                // multiplier
     A[ck + lane] = xs;
     // dsytrs first loop for this pivot: B(0:k-1,:) -= xs * B(k,:)   (B(k,:) *= 1/piv is deferred: dinv[k])
-#pragma unroll
-    for (int j = 0; j < NR; ++j) Bm[lane + j * K] = IPDDP_FMA(xs, -Bm[k + j * K], Bm[lane + j * K]);
+    RhsL<K, NR>::downdate_row(Bm, lane, k, xs);
   } else if (kp != k && in) {
     A[ck + lane] = 0.0;                        // the interchanged column's zeros
   }
@@ -515,7 +539,7 @@ IPDDP_D bool ldlt_step_fast2(int k, double* __restrict__ A, double* __restrict__
     if (lane != imax) { A[pa0] = x0; xc[lane] = a0; }
     if (in1 && i1 != imax) { A[pa1] = x1; xc[i1] = a1; }
     if (lane == 0) { A[ci + imax] = piv; xc[k] = aii; }
-    if (lane < NR) { double* bl = Bm + lane * K; const double t = bl[k]; bl[k] = bl[imax]; bl[imax] = t; }
+    RhsL<K, NR>::swap_rows(Bm, k, imax, lane);
     x0 = (lane == imax) ? x0 : a0;
     x1 = in1 ? ((i1 == imax) ? x1 : a1) : 0.0;
     piv = aii;
@@ -550,14 +574,12 @@ IPDDP_D bool ldlt_step_fast2(int k, double* __restrict__ A, double* __restrict__
   if (x0 != 0.0) {
     const double xs = x0 * rinv;
     xc[lane] = xs;
-#pragma unroll
-    for (int j = 0; j < NR; ++j) Bm[lane + j * K] = IPDDP_FMA(xs, -Bm[k + j * K], Bm[lane + j * K]);
+    RhsL<K, NR>::downdate_row(Bm, lane, k, xs);
   }
   if (x1 != 0.0) {
     const double xs = x1 * rinv;
     xc[i1] = xs;
-#pragma unroll
-    for (int j = 0; j < NR; ++j) Bm[i1 + j * K] = IPDDP_FMA(xs, -Bm[k + j * K], Bm[i1 + j * K]);
+    RhsL<K, NR>::downdate_row(Bm, i1, k, xs);
   }
   __syncwarp();
   return true;
@@ -615,8 +637,12 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
     const int r = lane + 32 * s;
     if (r < K) {
       const double d = dinv[r];
+      typedef RhsL<K, NR> RL;
+      double br[RL::LD];
+      RL::load_row(Bm, r, br);
 #pragma unroll
-      for (int j = 0; j < NR; ++j) Bm[r + j * K] = Bm[r + j * K] * d;
+      for (int j = 0; j < NR; ++j) br[j] = br[j] * d;
+      RL::store_row(Bm, r, br);
     }
   }
   __syncwarp();
@@ -624,7 +650,9 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
   const int j = lane >> 2;
   const bool act = j < NR;
   const unsigned gm = 0x11111111u << g;
-  double* bj = Bm + (act ? j : 0) * K;
+  typedef RhsL<K, NR> RL;
+  const int jc = act ? j : 0;
+  auto bj = [&](int i) -> double& { return Bm[RL::at(i, jc)]; };
   int k = 0;
   while (k < K) {
     const unsigned long long cw = cinfo[k];      // column 0 carries an empty mask
@@ -643,7 +671,7 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
         while (m) {
           const int i = __ffs(m) - 1;
           m &= m - 1u;
-          const double bv = bj[i];
+          const double bv = bj(i);
           sa = IPDDP_FMA(xa[i], bv, sa);
           if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
         }
@@ -652,7 +680,7 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
           while (m) {
             const int i = 32 + __ffs(m) - 1;
             m &= m - 1u;
-            const double bv = bj[i];
+            const double bv = bj(i);
             sa = IPDDP_FMA(xa[i], bv, sa);
             if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
           }
@@ -671,23 +699,23 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
       const int kp = pv - 1;
       if (any || kp != k) {
         if (act && g == 0) {
-          double v = bj[k];
+          double v = bj(k);
           if (any) v = v - sa;
-          if (kp != k) { const double t = bj[kp]; bj[kp] = v; v = t; }
-          bj[k] = v;
+          if (kp != k) { const double t = bj(kp); bj(kp) = v; v = t; }
+          bj(k) = v;
         }
         __syncwarp();
       }
       k += 1;
     } else {
       if (any) {
-        if (act && g == 0) { bj[k] = bj[k] - sa; bj[k + 1] = bj[k + 1] - sb; }
+        if (act && g == 0) { bj(k) = bj(k) - sa; bj(k + 1) = bj(k + 1) - sb; }
         __syncwarp();
       }
       int kp = -pv - 1;
-      if (kp != k) { warp_swap_rows<NR>(Bm, K, k, kp, lane); __syncwarp(); }
+      if (kp != k) { RL::swap_rows(Bm, k, kp, lane); __syncwarp(); }
       kp = -S::ipiv_of(cinfo[k + 1]) - 1;
-      if (kp != k + 1) { warp_swap_rows<NR>(Bm, K, k + 1, kp, lane); __syncwarp(); }
+      if (kp != k + 1) { RL::swap_rows(Bm, k + 1, kp, lane); __syncwarp(); }
       k += 2;
     }
   }

@@ -23,6 +23,7 @@
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct double4 { double x, y, z, w; };
+struct double2 { double x, y; };
 
 namespace emu {
 struct Fiber { void* sp; char* stack; bool done; bool at_block_barrier; };
