@@ -127,7 +127,8 @@ int ipddp_set_options(ipddp_problem* h, const ipddp_options* opt);
  * created afterwards.  Keys: "fw_spec_max" -- rounds with at most this many active instances run the forward pass with
  * one CTA per instance that tries 8 step sizes of the backtracking sequence at once (0 = never);
  * "bw_spec_max" -- rounds with at most this many active instances run the backward pass with one CTA per instance
- * that tries 4 values of the regularisation schedule at once (0 = never);
+ * that tries 4 values of the regularisation schedule at once (0 = never).  The default (-1 as the global default) is the
+ * number of instances whose speculative CTAs are resident at the same time on the device (CTAs per SM x SMs);
  * "list_sort" -- 1 (default): the active lists are bucketed by expected work, heaviest instances first, so that a launch
  * does not end with its longest-running warps; 0: arrival order;
  * "bulk_slots" (global) -- ipddp_solve_many admits at most this many batches into their bulk rounds at the same time

@@ -38,8 +38,10 @@ const ModelVTable* ipddp_vtable_ragged();
 namespace {
 
 thread_local std::string g_err;
-int g_fw_spec_max = 148;   // default for new problems: speculative line search when <= one CTA per SM is active
-int g_bw_spec_max = 592;   // speculative restarts when <= 4 CTAs (16 warps) per SM are active
+// defaults for new problems: -1 = as many instances as the speculative kernels hold in one wave on this device
+// (ModelVTable::spec_caps: e.g. cartpole 148 / 740, acrobot 296 / 2 664), capped by the memory of their private pools
+int g_fw_spec_max = -1;
+int g_bw_spec_max = -1;
 int g_bulk_slots = 3;      // ipddp_solve_many: batches admitted into their bulk rounds at the same time
 int g_list_sort = 1;       // active lists bucketed by expected work, heaviest first (0 = arrival order, for A/B runs)
 int fail(const std::string& m) { g_err = m; return -1; }
@@ -343,7 +345,7 @@ int ipddp_model_load(const char* path) {
   if (!f) return fail("plugin does not export ipddp_plugin_vtable");
   const ModelVTable* vt = f();
   if (!vt || !vt->name || !vt->init || !vt->derivs || !vt->backward || !vt->check || !vt->forward || !vt->admit ||
-      !vt->prepare)
+      !vt->prepare || !vt->spec_caps)
     return fail("plugin returned an incomplete model table");
   for (auto*& m : registry())
     if (strcmp(m->name, vt->name) == 0) { m = vt; return 0; }
@@ -379,8 +381,17 @@ int ipddp_problem_create(const char* model, int B, int N, const int* indices_com
   v.G = ((vt->nu + vt->nc + 2 * vt->nu) * (vt->nx + 1) + 1) & ~1;
   if (opt) v.opt = *opt; else ipddp_default_options(&v.opt);
   v.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
-  v.fw_spec_max = g_fw_spec_max;
-  v.bw_spec_max = g_bw_spec_max;
+  {
+    int cap_bw = 592, cap_fw = 148;
+    vt->spec_caps(N, &cap_bw, &cap_fw);
+    // private pools: at most ~3 GB each
+    const double bw_one = 3.0 * ((double)(N - 1) * (v.G + v.nu) + (double)N * v.ns) * 8.0, fw_one = 8.0 * N * v.TR * 8.0;
+    const int lim_bw = (int)(3.0e9 / bw_one), lim_fw = (int)(3.0e9 / fw_one);
+    if (cap_bw > lim_bw) cap_bw = lim_bw;
+    if (cap_fw > lim_fw) cap_fw = lim_fw;
+    v.fw_spec_max = g_fw_spec_max >= 0 ? g_fw_spec_max : cap_fw;
+    v.bw_spec_max = g_bw_spec_max >= 0 ? g_bw_spec_max : cap_bw;
+  }
   v.list_sort = g_list_sort;
   if ((long long)vt->smem_merit_spec(N) > (long long)optin) v.fw_spec_max = 0;   // long horizons: bulk line search only
   v.n_compl = (indices_compl && n_compl > 0) ? n_compl : 0;
@@ -551,8 +562,8 @@ int ipddp_stage_layout(ipddp_problem* h, int* nx, int* nu, int* nc) {
 int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
   const std::string k = key ? key : "";
   if (k == "fw_spec_max") {   // h == NULL: default for problems created afterwards
+    if (!h) { g_fw_spec_max = value < 0 ? -1 : value; return 0; }     // -1: automatic (one wave of speculative CTAs)
     if (value < 0) value = 0;
-    if (!h) { g_fw_spec_max = value; return 0; }
     if (value > h->v.B) value = h->v.B;
     int optin = 0;
     CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -577,8 +588,8 @@ int ipddp_set_tuning(ipddp_problem* h, const char* key, int value) {
     return 0;
   }
   if (k == "bw_spec_max") {
+    if (!h) { g_bw_spec_max = value < 0 ? -1 : value; return 0; }
     if (value < 0) value = 0;
-    if (!h) { g_bw_spec_max = value; return 0; }
     if (value > h->v.B) value = h->v.B;
     if (value > h->bw_spec_cap) {
       CK(cudaSetDevice(h->device));

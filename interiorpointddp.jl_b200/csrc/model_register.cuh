@@ -67,6 +67,23 @@ template <class M> struct Launch {
     IPDDP_LAUNCH((k_forward<M>), (n_upper + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, FwLayout<M>::bytes(v.N), s, v,
                  list_fwd, list_next, counters);
   }
+  // The speculative tail kernels trade work for latency (4 regularisation values / 8 step sizes at once): worth it exactly
+  // while every active instance's CTA is resident at the same time, i.e. up to (CTAs per SM) x (SMs) instances.
+  static void spec_caps(int N, int* bw_spec, int* fw_spec) {
+    *bw_spec = 592; *fw_spec = 148;
+#ifndef IPDDP_SIMT_EMU
+    int dev = 0, sms = 0, nb = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return;
+    const size_t smem_bw = (size_t)BWS_WARPS * BwLayout<M>::BYTES + BWS_WARPS * 8 + BWS_WARPS * 2 * 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_backward_spec<M>, BWS_WARPS * 32, smem_bw) == cudaSuccess && nb > 0)
+      *bw_spec = nb * sms;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_forward_spec<M>, FWS_WARPS * 32, FwLayout<M>::spec_bytes(N)) == cudaSuccess && nb > 0)
+      *fw_spec = nb * sms;
+#else
+    (void)N;
+#endif
+  }
   static int prepare(int max_optin_smem) {
     (void)max_optin_smem;
 #ifndef IPDDP_SIMT_EMU
@@ -105,7 +122,7 @@ template <class M> const ModelVTable* make_vtable() {
       M::NAME, M::NX, M::NU, M::NC, M::NP, M::D_NSLOT, M::DN_NSLOT, M::VF_NSLOT, BwLayout<M>::BYTES,
       M::NSTAGE, M::NXT, Dims<M>::NS, IPDDP_STAGE_DIMS(0), IPDDP_STAGE_DIMS(1), IPDDP_STAGE_DIMS(2), IPDDP_STAGE_DIMS(3),
       &Launch<M>::init, &Launch<M>::derivs, &Launch<M>::backward, &Launch<M>::check, &Launch<M>::forward,
-      &Launch<M>::admit, &Launch<M>::smem_merit, &Launch<M>::smem_merit_spec, &Launch<M>::prepare};
+      &Launch<M>::admit, &Launch<M>::smem_merit, &Launch<M>::smem_merit_spec, &Launch<M>::prepare, &Launch<M>::spec_caps};
   return &vt;
 }
 

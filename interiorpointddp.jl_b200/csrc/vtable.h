@@ -20,4 +20,6 @@ struct ModelVTable {
   long long (*smem_merit)(int N);
   long long (*smem_merit_spec)(int N);
   int (*prepare)(int max_optin_smem);
+  // how many instances the speculative tail kernels can hold in ONE wave on the current device (CTAs per SM x SMs)
+  void (*spec_caps)(int N, int* bw_spec, int* fw_spec);
 };

@@ -35,8 +35,8 @@ def test_emulated_bulk_kernels(emu, oracle_mod, wl, B, N, maxit):
     try:
         helpers.full_solve_parity(emu, oracle_mod, wl, B, N, maxit=maxit, n_trace=B)
     finally:
-        emu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
-        emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+        emu.L.ipddp_set_tuning(None, b"fw_spec_max", -1)
+        emu.L.ipddp_set_tuning(None, b"bw_spec_max", -1)
 
 
 @pytest.mark.parametrize("order", ["rev", "rand"])
@@ -55,8 +55,8 @@ def test_emulated_lane_order_independence(emu, oracle_mod, order, monkeypatch):
             helpers.full_solve_parity(emu, oracle_mod, "cartpole", 2, 9, maxit=25, n_trace=2)
             helpers.full_solve_parity(emu, oracle_mod, "pushing", 2, 9, maxit=20, vary_horizon=True, n_trace=2)
         finally:
-            emu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
-            emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+            emu.L.ipddp_set_tuning(None, b"fw_spec_max", -1)
+            emu.L.ipddp_set_tuning(None, b"bw_spec_max", -1)
     helpers.phase_parity(emu, oracle_mod, "concar", B=2, N=7, rounds=2)
 
 
@@ -128,8 +128,8 @@ def test_emulated_stage_chain(emu, oracle_mod, spec):
     try:
         helpers.chain_parity(emu, oracle_mod, "ragged", 3, 13, maxit=60)
     finally:
-        emu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
-        emu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+        emu.L.ipddp_set_tuning(None, b"fw_spec_max", -1)
+        emu.L.ipddp_set_tuning(None, b"bw_spec_max", -1)
 
 
 def test_emulated_stage_chain_queue(emu, oracle_mod):

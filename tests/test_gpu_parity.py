@@ -51,8 +51,8 @@ def test_bulk_kernels_parity(gpu, oracle_mod, wl, B):
     try:
         helpers.full_solve_parity(gpu, oracle_mod, wl, B, 101, n_trace=2)
     finally:
-        gpu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
-        gpu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+        gpu.L.ipddp_set_tuning(None, b"fw_spec_max", -1)
+        gpu.L.ipddp_set_tuning(None, b"bw_spec_max", -1)
 
 
 def test_tail_kernels_equal_bulk_kernels_mid_size(gpu):
@@ -279,8 +279,8 @@ def test_stage_chain_parity(gpu, oracle_mod):
     try:
         helpers.chain_parity(gpu, oracle_mod, "ragged", 24, 61)
     finally:
-        gpu.L.ipddp_set_tuning(None, b"fw_spec_max", 148)
-        gpu.L.ipddp_set_tuning(None, b"bw_spec_max", 592)
+        gpu.L.ipddp_set_tuning(None, b"fw_spec_max", -1)
+        gpu.L.ipddp_set_tuning(None, b"bw_spec_max", -1)
     helpers.chain_parity(gpu, oracle_mod, "ragged", 40, 41, queue_slots=16)
 
 
