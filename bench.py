@@ -469,7 +469,8 @@ def main():
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload} swing-up batch of {B} random initial states per GPU, N={N} knots, tol {args.tol:g}",
-                       "batch_per_gpu": B, "knots": N, "resident_slots": S,
+                       "batch_per_gpu": B, "knots": N, "resident_slots": S, "handles": 1,
+                       "device_memory_gb_per_gpu": round(torch.cuda.max_memory_allocated(dev) / 1e9 + S * 0.000635, 1),
                        "l2": "working set (trajectories+gains > 8 GB) far exceeds the 126 MB L2",
                        "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
                        "timing": "value/e2e: the K steps (K x batch instances) are queued on ONE handle with resident_slots instance "
