@@ -271,6 +271,8 @@ def main():
         st = dq.solve()
         barrier()
     clocks = clk.summary()
+    _free, _total = torch.cuda.mem_get_info(dev)
+    mem_used_gb = round((_total - _free) / 1e9, 1)    # slots + this region's queue (inputs and outputs) on the device
     agg = dict(ms_total=st.ms_total, ms_derivs=st.ms_derivs, ms_backward=st.ms_backward, ms_check=st.ms_check,
                ms_forward=st.ms_forward, kkt=st.sum_kkt, sweeps=st.sum_sweeps, rollouts=st.sum_rollouts,
                backward_calls=st.sum_backward, conv=st.n_converged, launches=st.launches, rounds=st.iterations,
@@ -470,7 +472,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload} swing-up batch of {B} random initial states per GPU, N={N} knots, tol {args.tol:g}",
                        "batch_per_gpu": B, "knots": N, "resident_slots": S, "handles": 1,
-                       "device_memory_gb_per_gpu": round(torch.cuda.max_memory_allocated(dev) / 1e9 + S * 0.000635, 1),
+                       "device_memory_gb_per_gpu": mem_used_gb,
                        "l2": "working set (trajectories+gains > 8 GB) far exceeds the 126 MB L2",
                        "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
                        "timing": "value/e2e: the K steps (K x batch instances) are queued on ONE handle with resident_slots instance "
