@@ -137,12 +137,13 @@ IPDDP_D void eval_metrics(const DevView& v, int set, int b, int Nb, double mu, d
 }
 
 // Per-warp scratch shared by the warp-per-instance kernels that evaluate merit terms (k_forward, k_check):
-// u[NU] | chunk[32] | finite-bound index bytes (2*NU per stage type, padded to 8 doubles) | 4 per-knot arrays of N doubles.
+// u[NU] | chunk[32] | finite-bound index bytes (2*NU per stage type, padded to 8 doubles) | 4 per-knot arrays of N doubles
+// (k_init / k_admit keep the two state buffers of their rollout there: at least 2*NS doubles).
 template <class M> struct MeritLayout {
   static constexpr int NUP = M::NU > 0 ? M::NU : 1;
   static constexpr int BIDX = 2 * NUP;                       // bytes of one stage type's index list
   static constexpr int FIXED = NUP + 32 + ((BIDX * M::NSTAGE + 7) / 8);
-  static IPDDP_BOTH int per_warp_doubles(int N) { return FIXED + 4 * N; }
+  static IPDDP_BOTH int per_warp_doubles(int N) { return FIXED + (4 * N > 2 * Dims<M>::NS ? 4 * N : 2 * Dims<M>::NS); }
 };
 
 // finite-bound index lists in the reference's accumulation order (lower indices, then upper indices;

@@ -1,9 +1,6 @@
-// Thread-per-instance kernels: initialisation, convergence check / barrier update, and the
-// thread-per-(instance, knot) derivative kernel.  (The forward pass lives in kernel_forward.cuh.)
-//
-// These phases are short, sequential-in-time per instance and dominated by streaming each instance's
-// own contiguous records, so one thread walks one instance; instance records are contiguous, the
-// active lists are plain index indirection.
+// The short phases of a round: initialisation / admission and the convergence check with the barrier update (one warp
+// per instance), and the thread-per-(instance, knot) derivative kernel.  (The forward pass lives in kernel_forward.cuh.)
+// Instance records are contiguous, the active lists are plain index indirection.
 #pragma once
 #include "kernels_common.cuh"
 
@@ -15,27 +12,38 @@ namespace ipk {
 // distances, open-loop rollout, dual reset (src/solve.jl:182-198), J, c, theta, L, theta_max/min, filter.
 // warm != 0: keep the stored nominal primal trajectory (solve!(solver), src/solve.jl:6-17).
 // ---------------------------------------------------------------------------------------------
-// one instance (slot b) by one thread; x1p / ubarp: this instance's initial state and control guess.
-// returns true if the instance takes part in the first round (max_iterations > 0)
+// one instance (slot b) by one warp; x1p / ubarp: this instance's initial state and control guess; sm: the warp's
+// MeritLayout scratch.  The rollout is sequential in time (lane 0 evaluates the dynamics, state ping-pong in shared
+// memory), everything per knot -- projection of the controls, record writes, dual reset -- is spread over the lanes, the
+// merit terms come from warp_eval_metrics.  Returns (all lanes) true if the instance takes part in the first round
+// (max_iterations > 0).
 template <class M>
-IPDDP_D bool init_instance(const DevView& v, int warm, int b, const double* x1p, const double* ubarp) {
+IPDDP_D bool init_instance(const DevView& v, int warm, int b, const double* x1p, const double* ubarp, double* sm,
+                           int lane) {
   const int Nb = v.horizon[b];
   const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
   const double k1 = v.opt.kappa_1, k2 = v.opt.kappa_2;
   int set = 0;
-  if (warm) set = v.nomsel[b]; else v.nomsel[b] = 0;
+  if (warm) set = v.nomsel[b];
+  else if (lane == 0) v.nomsel[b] = 0;
 
-  double x[Dims<M>::NS];     // a chain's state size changes with the stage type: sized for the largest
+  double* us = sm;
+  double* chunk = us + MeritLayout<M>::NUP;
+  unsigned char* bidx = reinterpret_cast<unsigned char*>(chunk + 32);
+  double* part = us + MeritLayout<M>::FIXED;
+  // a chain's state size changes with the stage type: the two state buffers are sized for the largest; they live in
+  // the per-knot arrays, which warp_eval_metrics only uses after the rollout
+  double* xs = part;
+  double* xns = part + Dims<M>::NS;
   if (!warm) {
-    for (int i = 0; i < M::NX; ++i) x[i] = (M::NSTAGE == 1 || i < v.snx[v.type_of(0)]) ? x1p[i] : 0.0;
+    for (int i = lane; i < M::NX; i += 32) xs[i] = (M::NSTAGE == 1 || i < v.snx[v.type_of(0)]) ? x1p[i] : 0.0;
+    __syncwarp();
   }
   for (int t = 0; t < Nb; ++t) {
     double* r = v.rec(set, b, t);
     if (t == Nb - 1) {
-      if (!warm) {
-#pragma unroll
-        for (int i = 0; i < M::Terminal::NXT; ++i) r[i] = x[i];
-      }
+      if (!warm)
+        for (int i = lane; i < M::Terminal::NXT; i += 32) r[i] = xs[i];
       break;
     }
     const int type = v.type_of(t);
@@ -45,12 +53,9 @@ IPDDP_D bool init_instance(const DevView& v, int warm, int b, const double* x1p,
       const double* lo = v.lower_of(b, type);
       const double* up = v.upper_of(b, type);
       if (!warm) {
-#pragma unroll
-        for (int i = 0; i < S::NX; ++i) r[R::X + i] = x[i];
-        double u[S::NU > 0 ? S::NU : 1], xn[S::NXN];
+        for (int i = lane; i < S::NX; i += 32) r[R::X + i] = xs[i];
         const double* u0p = ubarp + (size_t)t * M::NU;
-#pragma unroll
-        for (int i = 0; i < S::NU; ++i) {
+        for (int i = lane; i < S::NU; i += 32) {
           const double u0 = u0p[i], l = lo[i], h = up[i];
           double ub;
           if (!is_inf(l) && is_inf(h)) {
@@ -70,71 +75,85 @@ IPDDP_D bool init_instance(const DevView& v, int warm, int b, const double* x1p,
           } else {
             ub = u0;
           }
-          u[i] = ub;
+          us[i] = ub;
           r[R::U + i] = ub;
           r[R::IL + i] = ub - l;
           r[R::IU + i] = h - ub;
         }
-        S::dyn(x, u, p, xn);
-#pragma unroll
-        for (int i = 0; i < S::NXN; ++i) x[i] = xn[i];
+        __syncwarp();
+        if (lane == 0) S::dyn(xs, us, p, xns);
+        __syncwarp();
+        double* sw = xs; xs = xns; xns = sw;
       }
       // reset_duals!
-#pragma unroll
-      for (int i = 0; i < S::NC; ++i) r[R::PHI + i] = 0.0;
-#pragma unroll
-      for (int i = 0; i < S::NU; ++i) {
+      for (int i = lane; i < S::NC; i += 32) r[R::PHI + i] = 0.0;
+      for (int i = lane; i < S::NU; i += 32) {
         r[R::ZL + i] = is_inf(lo[i]) ? 0.0 : 1.0;
         r[R::ZU + i] = is_inf(up[i]) ? 0.0 : 1.0;
       }
     });
   }
-  for (int t = 0; t < Nb; ++t)
-    for (int i = 0; i < Dims<M>::NS; ++i) v.lam[((size_t)b * v.N + t) * Dims<M>::NS + i] = 0.0;
+  {
+    double* lam = v.lam + (size_t)b * v.N * Dims<M>::NS;
+    for (int e = lane; e < Nb * Dims<M>::NS; e += 32) lam[e] = 0.0;
+  }
+  __syncwarp();
 
   // reset!(data) + prologue
   const double mu = v.opt.mu_init;
   double J, theta, L;
-  eval_metrics<M>(v, set, b, Nb, mu, &J, &theta, &L);
-  v.sdv(SD_MU, b) = mu;
-  v.sdv(SD_REG_LAST, b) = 0.0;
-  v.sdv(SD_OBJECTIVE, b) = J;
-  v.sdv(SD_PRIMAL_INF, b) = 0.0;
-  v.sdv(SD_DUAL_INF, b) = 0.0;
-  v.sdv(SD_CS_INF, b) = 0.0;
-  v.sdv(SD_L_CURR, b) = L;
-  v.sdv(SD_THETA_CURR, b) = theta;
-  v.sdv(SD_L_NEXT, b) = 0.0;
-  v.sdv(SD_THETA_NEXT, b) = 0.0;
-  v.sdv(SD_THETA_MAX, b) = 1e4 * jmax(1.0, theta);
-  v.sdv(SD_THETA_MIN, b) = 1e-4 * jmax(1.0, theta);
-  v.sdv(SD_STEP, b) = 0.0;
-  v.sdv(SD_DUAL_NUM, b) = 0.0;
-  for (int f = 0; f < SI_COUNT; ++f) v.siv(f, b) = 0;
-  reset_filter(v, b);
-  if (v.opt.max_iterations > 0) return true;
-  v.siv(SI_STATUS, b) = 8;
-  return false;
+  const BoundLists<M> bls = warp_bound_lists<M>(v, b, bidx, lane);
+  warp_eval_metrics<M>(v, v.rec(set, b, 0), Nb, mu, p, bls, chunk, part, part + v.N, part + 2 * v.N, lane, &J, &theta, &L);
+  if (lane == 0) {
+    v.sdv(SD_MU, b) = mu;
+    v.sdv(SD_REG_LAST, b) = 0.0;
+    v.sdv(SD_OBJECTIVE, b) = J;
+    v.sdv(SD_PRIMAL_INF, b) = 0.0;
+    v.sdv(SD_DUAL_INF, b) = 0.0;
+    v.sdv(SD_CS_INF, b) = 0.0;
+    v.sdv(SD_L_CURR, b) = L;
+    v.sdv(SD_THETA_CURR, b) = theta;
+    v.sdv(SD_L_NEXT, b) = 0.0;
+    v.sdv(SD_THETA_NEXT, b) = 0.0;
+    v.sdv(SD_THETA_MAX, b) = 1e4 * jmax(1.0, theta);
+    v.sdv(SD_THETA_MIN, b) = 1e-4 * jmax(1.0, theta);
+    v.sdv(SD_STEP, b) = 0.0;
+    v.sdv(SD_DUAL_NUM, b) = 0.0;
+    for (int f = 0; f < SI_COUNT; ++f) v.siv(f, b) = 0;
+    reset_filter(v, b);
+    if (v.opt.max_iterations <= 0) v.siv(SI_STATUS, b) = 8;
+  }
+  return v.opt.max_iterations > 0;
 }
 
+constexpr int INIT_WARPS = 4;   // same per-warp scratch as k_check (Launch::smem_merit bounds both)
+
 template <class M>
-__global__ void k_init(DevView v, int warm, int b0, int nb, int* list_next, int* counters) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= nb) return;
-  const int b = b0 + tid;
-  if (init_instance<M>(v, warm, b, v.x1 + (size_t)b * M::NX, v.ubar + (size_t)b * (v.N - 1) * M::NU))
-    append_next(v, list_next, counters, b);
-  else
-    mark_done(v, b, counters);
+__global__ void __launch_bounds__(INIT_WARPS * 32) k_init(DevView v, int warm, int b0, int nb, int* list_next,
+                                                          int* counters) {
+  IPDDP_DYN_SMEM(double, sm_all);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * INIT_WARPS + warp;
+  if (j >= nb) return;
+  const int b = b0 + j;
+  double* sm = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
+  const bool runs = init_instance<M>(v, warm, b, v.x1 + (size_t)b * M::NX, v.ubar + (size_t)b * (v.N - 1) * M::NU, sm, lane);
+  if (lane == 0) {
+    if (runs) append_next(v, list_next, counters, b);
+    else mark_done(v, b, counters);
+  }
 }
 
 // Queue mode: admit n queued instances inst0 .. inst0+n-1 into the slots slots[0..n) (NULL: slots 0..n-1): copy the
 // instance's parameters, bounds and horizon into the slot, initialise its trajectory from the queue's x1 / ubar
 // (k_init's work) and append the slot to the running round's list at list[j] (the host passes the end of the lightest
-// bucket: a fresh instance's first backward pass is one sweep).
+// bucket: a fresh instance's first backward pass is one sweep).  One warp per admitted instance.
 template <class M>
-__global__ void k_admit(DevView v, QueueView q, const int* slots, int n, int inst0, int* list, int* counters) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(INIT_WARPS * 32) k_admit(DevView v, QueueView q, const int* slots, int n, int inst0,
+                                                           int* list, int* counters) {
+  IPDDP_DYN_SMEM(double, sm_all);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * INIT_WARPS + warp;
   if (j >= n) return;
   const int b = slots ? slots[j] : j;
   const int i = inst0 + j;
@@ -143,16 +162,21 @@ __global__ void k_admit(DevView v, QueueView q, const int* slots, int n, int ins
   constexpr int NB = M::NSTAGE * M::NU;       // bounds per instance: [stage type][control]
   double* lo = const_cast<double*>(v.lower) + (size_t)b * NB;
   double* up = const_cast<double*>(v.upper) + (size_t)b * NB;
-  for (int e = 0; e < M::NP; ++e) ps[e] = q.p[(size_t)i * NP1 + e];
-  for (int e = 0; e < NB; ++e) { lo[e] = q.lower[(size_t)i * NB + e]; up[e] = q.upper[(size_t)i * NB + e]; }
+  for (int e = lane; e < M::NP; e += 32) ps[e] = q.p[(size_t)i * NP1 + e];
+  for (int e = lane; e < NB; e += 32) { lo[e] = q.lower[(size_t)i * NB + e]; up[e] = q.upper[(size_t)i * NB + e]; }
   int hz = q.horizon ? q.horizon[i] : v.N;
-  if (hz < 2 || hz > v.N) { atomicAdd(&counters[CNT_BAD], 1); hz = hz < 2 ? 2 : v.N; }
-  const_cast<int*>(v.horizon)[b] = hz;
-  v.inst_of[b] = i;
-  if (init_instance<M>(v, 0, b, q.x1 + (size_t)i * M::NX, q.ubar + (size_t)i * (v.N - 1) * M::NU))
-    list[j] = b;
-  else
-    mark_done(v, b, counters);
+  if (hz < 2 || hz > v.N) { if (lane == 0) atomicAdd(&counters[CNT_BAD], 1); hz = hz < 2 ? 2 : v.N; }
+  if (lane == 0) {
+    const_cast<int*>(v.horizon)[b] = hz;
+    v.inst_of[b] = i;
+  }
+  __syncwarp();
+  double* sm = sm_all + (size_t)warp * MeritLayout<M>::per_warp_doubles(v.N);
+  const bool runs = init_instance<M>(v, 0, b, q.x1 + (size_t)i * M::NX, q.ubar + (size_t)i * (v.N - 1) * M::NU, sm, lane);
+  if (lane == 0) {
+    if (runs) list[j] = b;
+    else mark_done(v, b, counters);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

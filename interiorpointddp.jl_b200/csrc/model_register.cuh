@@ -14,14 +14,17 @@ namespace ipk {
 
 template <class M> struct Launch {
   static void init(const DevView& v, int warm, int b0, int nb, int* list_next, int* counters, cudaStream_t s) {
-    const int th = 64;
-    IPDDP_LAUNCH((k_init<M>), (nb + th - 1) / th, th, 0, s, v, warm, b0, nb, list_next, counters);
+    if (nb <= 0) return;
+    const size_t smem = (size_t)INIT_WARPS * MeritLayout<M>::per_warp_doubles(v.N) * sizeof(double);
+    IPDDP_LAUNCH((k_init<M>), (nb + INIT_WARPS - 1) / INIT_WARPS, INIT_WARPS * 32, smem, s, v, warm, b0, nb, list_next,
+                 counters);
   }
   static void admit(const DevView& v, const QueueView& q, const int* slots, int n, int inst0, int* list, int* counters,
                     cudaStream_t s) {
     if (n <= 0) return;
-    const int th = 64;
-    IPDDP_LAUNCH((k_admit<M>), (n + th - 1) / th, th, 0, s, v, q, slots, n, inst0, list, counters);
+    const size_t smem = (size_t)INIT_WARPS * MeritLayout<M>::per_warp_doubles(v.N) * sizeof(double);
+    IPDDP_LAUNCH((k_admit<M>), (n + INIT_WARPS - 1) / INIT_WARPS, INIT_WARPS * 32, smem, s, v, q, slots, n, inst0, list,
+                 counters);
   }
   static long long smem_merit(int N) {
     const size_t a = FwLayout<M>::bytes(N), b = (size_t)CHK_WARPS * MeritLayout<M>::per_warp_doubles(N) * sizeof(double);
@@ -93,6 +96,8 @@ template <class M> struct Launch {
     if (cudaFuncSetAttribute(k_forward<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_forward_spec<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_check<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_init<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_admit<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return -1;
     // the sweep is occupancy bound through shared memory: ask for the largest shared-memory carveout
     if (cudaFuncSetAttribute(k_backward<M>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_backward_spec<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
