@@ -67,75 +67,6 @@ template <int NN> IPDDP_D double dot4c(const double* a, int sa, const double* b,
   return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
-// Objective, constraints (written to the record), theta = sum_t |c_t|_1 and the barrier Lagrangian of
-// one trajectory set, in the reference's evaluation order: objective (src/objectives.jl:37-46),
-// constraint! (src/data/methods.jl:20-32), constraint_violation_1norm (:69-76),
-// barrier_lagrangian! (:34-67: one running accumulator over (t, finite-lower idx, finite-upper idx),
-// times mu, plus J, plus sum_t dot(c_t, phi_t)).
-template <class M>
-IPDDP_D void eval_metrics(const DevView& v, int set, int b, int Nb, double mu, double* Jout, double* theta_out,
-                          double* Lout) {
-  const double* p = v.p + (size_t)b * (M::NP > 0 ? M::NP : 1);
-  double J = 0.0, theta = 0.0, bl = 0.0;
-  for (int t = 0; t < Nb; ++t) {
-    double* r = v.rec(set, b, t);
-    double Jp;
-    if (t < Nb - 1) {
-      const int type = v.type_of(t);
-      for_stage<M>(type, [&](auto tag) {
-        typedef IPDDP_STAGE(tag) S;
-        typedef Rec<S> R;
-        const double* lo = v.lower_of(b, type);
-        const double* up = v.upper_of(b, type);
-        double x[S::NX], u[S::NU > 0 ? S::NU : 1], c[S::NC > 0 ? S::NC : 1];
-#pragma unroll
-        for (int i = 0; i < S::NX; ++i) x[i] = r[R::X + i];
-#pragma unroll
-        for (int i = 0; i < S::NU; ++i) u[i] = r[R::U + i];
-        S::cost(x, u, p, &Jp);
-        if (S::NC > 0) {
-          S::con(x, u, p, c);
-          if (v.compl_mask[type]) {
-#pragma unroll
-            for (int i = 0; i < S::NC; ++i) if ((v.compl_mask[type] >> i) & 1ull) c[i] -= mu;
-          }
-          double n1 = 0.0;
-#pragma unroll
-          for (int i = 0; i < S::NC; ++i) { r[R::C + i] = c[i]; n1 += fabs(c[i]); }
-          theta += n1;
-        }
-#pragma unroll
-        for (int i = 0; i < S::NU; ++i)
-          if (!is_inf(lo[i])) bl -= dm::log(r[R::IL + i]);
-#pragma unroll
-        for (int i = 0; i < S::NU; ++i)
-          if (!is_inf(up[i])) bl -= dm::log(r[R::IU + i]);
-      });
-    } else {
-      typedef typename M::Terminal T;
-      double x[T::NXT];
-#pragma unroll
-      for (int i = 0; i < T::NXT; ++i) x[i] = r[i];
-      T::costN(x, p, &Jp);
-    }
-    J += Jp;
-  }
-  bl *= mu;
-  bl += J;
-  for (int t = 0; t < Nb - 1; ++t) {
-    const double* r = v.rec(set, b, t);
-    for_stage<M>(v.type_of(t), [&](auto tag) {
-      typedef IPDDP_STAGE(tag) S;
-      typedef Rec<S> R;
-      bl += dot4c<S::NC>(r + R::C, 1, r + R::PHI, 1);
-    });
-  }
-  bl += 0.0;  // terminal stage: dot of two empty vectors
-  *Jout = J;
-  *theta_out = theta;
-  *Lout = bl;
-}
-
 // Per-warp scratch shared by the warp-per-instance kernels that evaluate merit terms (k_forward, k_check):
 // u[NU] | chunk[32] | finite-bound index bytes (2*NU per stage type, padded to 8 doubles) | 4 per-knot arrays of N doubles
 // (k_init / k_admit keep the two state buffers of their rollout there: at least 2*NS doubles).
@@ -175,9 +106,12 @@ IPDDP_D BoundLists<M> warp_bound_lists(const DevView& v, int b, unsigned char* b
   return bl;
 }
 
-// Warp-parallel eval_metrics: the per-knot terms (l_t, c_t written to the record, |c_t|_1, c_t'phi_t) are evaluated
-// with lane = knot, the barrier logs 32 at a time, and every sum is then accumulated sequentially in exactly the
-// order eval_metrics uses -- bit-identical results.  All lanes return the same J, theta, L.
+// Objective, constraints (written to the record), theta = sum_t |c_t|_1 and the barrier Lagrangian of one trajectory
+// set, in the reference's evaluation order: objective (src/objectives.jl:37-46), constraint! (src/data/methods.jl:20-32),
+// constraint_violation_1norm (:69-76), barrier_lagrangian! (:34-67: one running accumulator over (t, finite-lower idx,
+// finite-upper idx), times mu, plus J, plus sum_t dot(c_t, phi_t)).  The per-knot terms (l_t, c_t, |c_t|_1, c_t'phi_t)
+// are evaluated with lane = knot, the barrier logs 32 at a time, and every sum is then accumulated sequentially in
+// exactly that order.  All lanes return the same J, theta, L.
 // recs: the instance's knot records of the trajectory set to evaluate (record t at recs + t * TR).
 template <class M>
 IPDDP_D void warp_eval_metrics(const DevView& v, double* recs, int Nb, double mu, const double* p, const BoundLists<M>& bls,
