@@ -83,6 +83,10 @@ def test_emulated_memcheck_asan():
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
     want = open(os.path.join(root, "profiles", "r1_sanity", "gpu_digests.jsonl")).read().strip().splitlines()
     assert r.stdout.strip().splitlines() == want
+    # round-2 paths: queue mode (k_admit / k_retire), warm start, varying horizons, heavy forward split, a stage chain
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_small.py"), "3"], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr and "sanitize_small done" in r.stdout, r.stderr[-3000:]
 
 
 def test_emulated_forward_heavy_split(oracle_mod):
