@@ -14,7 +14,8 @@ P = os.path.join(ROOT, "profiles")
 caps = [("r2_bw_bulk", "first k_backward launch of a solve: 16384 x 101 timestep-KKTs, one sweep each"),
         ("r2_bw_mid", "37th k_backward launch (mid-solve: 2x2 pivots, restarted sweeps)"),
         ("r2_fw_bulk", "second k_forward launch (16384 instances, TMA-staged rollout)"),
-        ("r2_derivs", "second k_derivs launch")]
+        ("r2_derivs", "second k_derivs launch"),
+        ("r2_init", "k_init: 16384 instances, one warp each (rollout, record writes, merit terms)")]
 outrows, vals = [], {}
 for name, what in caps:
     rep = os.path.join(G, name + ".ncu-rep")

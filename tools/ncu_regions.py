@@ -25,20 +25,35 @@ for r in rows[hi + 1:]:
 base = data[0][0]
 off2 = {o: (c, t) for o, c, t in seq}
 tot = sum(d[1] for d in data)
-# regions
+# regions: boundaries located in the sources (first line containing each marker), so edits do not shift the attribution
+CS = "/root/repo/interiorpointddp.jl_b200/csrc/"
+def first_line(path, marker):
+    for i, l in enumerate(open(CS + path), 1):
+        if marker in l: return i
+    raise SystemExit(f"marker {marker!r} not found in {path}")
+LD = [(first_line("ldlt_warp.cuh", m), name) for m, name in (
+    ("IPDDP_D int coff(", "ldlt helpers (coff, DivBy, max_ties, swaps, compaction)"),
+    ("// Access to the K x NR right-hand sides", "right-hand-side row updates (RhsL: first solve loop, interchanges)"),
+    ("// Scratch used by the factorisation", "ldlt scratch accessors"),
+    ("// General pivot step (column k)", "ldlt_step (general)"),
+    ("// Fast pivot step for 0 <= k < 32", "ldlt_step_fast"),
+    ("// The same fast step for a pivot column 32 <= k < 64", "ldlt_step_fast2"),
+    ("// dsytf2_rook('U') on the packed matrix A of order K", "factor driver"),
+    ("// second loop of dsytrs_rook('U')", "second solve"))]
+BW = [(first_line("kernel_backward.cuh", m), name) for m, name in (
+    ("template <class M> struct BwLayout", "bw setup / terminal knot"),
+    ("// ---- stage inputs", "bw assembly 1 (scatter, barrier terms)"),
+    ("// ---- xx_tmp = fx' Vxx+", "bw assembly 2 (products, contractions, park)"),
+    ("// ---- factorise + inertia", "bw factor call + ineq gains"),
+    ("// ---- Vxx = beta' B + omega' cx + C", "bw value update + write back"),
+    ("IPDDP_D int bw_sweep(", "bw sweep driver / kernel"))]
 def region(f, ln):
-    if f == "ldlt_warp.cuh":
-        if ln < 171: return "ldlt helpers (coff, DivBy, max_ties, swaps)"
-        if ln < 385: return "ldlt_step (general)"
-        if ln < 472: return "ldlt_step_fast"
-        if ln < 572: return "ldlt_step_fast2"
-        if ln < 605: return "factor driver"
-        return "second solve"
-    if f == "kernel_backward.cuh":
-        if ln < 250: return "bw assembly 1 (scatter, barrier terms)"
-        if ln < 320: return "bw assembly 2 (products, contractions, park)"
-        if ln < 350: return "bw factor call + ineq gains"
-        return "bw value update + write back"
+    for tab, name in (("ldlt_warp.cuh", LD), ("kernel_backward.cuh", BW)):
+        if f == tab:
+            r = "preamble"
+            for start, nm in name:
+                if ln >= start: r = nm
+            return r
     return f
 agg = {}; ops = {}
 for a, n, s, txt in data:
