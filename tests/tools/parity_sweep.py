@@ -1,12 +1,12 @@
 """Wide randomized GPU-vs-oracle parity sweep (run on a B200; a few minutes): every workload on instances far from the
 ones the test-suite uses, resident batches and queues of awkward sizes.  Prints one JSON line per case.
-    python tools/parity_sweep.py [instances_per_workload]"""
+    python tests/tools/parity_sweep.py [instances_per_workload]"""
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np  # noqa: E402

@@ -9,7 +9,7 @@ objective.  A scratch copy of oracle/ is compiled once per variant with -DORACLE
   2  sequential, separate multiply and add (no FMA)
   3  2 interleaved FMA partial sums, s0+s1
   4  8 interleaved FMA partial sums, ((s0+s1)+(s2+s3))+((s4+s5)+(s6+s7))
-    python tools/summation_order_study.py > profiles/r2_summation_order.json
+    python tests/tools/summation_order_study.py > profiles/r2_summation_order.json
 """
 import ctypes as C
 import json
@@ -19,7 +19,7 @@ import subprocess
 import sys
 import tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import ipddp_b200  # noqa: E402,F401
