@@ -851,7 +851,11 @@ int ipddp_solve_queue(ipddp_problem* h, const ipddp_queue* io) {
   }
   // ---- the rounds
   int next_inst = 0, retired = 0, n_active = 0, cur = 0, n_free = B, r = 0;
-  FILE* qlog = getenv("IPDDP_QUEUE_LOG") ? fopen(getenv("IPDDP_QUEUE_LOG"), "a") : nullptr;   // per-round series for profiling
+  struct LogFile {   // per-round series for profiling; closed on every return path
+    FILE* f;
+    ~LogFile() { if (f) fclose(f); }
+  } qlog_guard = {getenv("IPDDP_QUEUE_LOG") ? fopen(getenv("IPDDP_QUEUE_LOG"), "a") : nullptr};
+  FILE* qlog = qlog_guard.f;
   for (int k = 0; k < LIST_BUCKETS; ++k) h->nb[k] = 0;
   const int light = LIST_BUCKETS - 1;   // fresh instances join the bucket of the one-sweep instances
   const bool runs = hv.opt.max_iterations > 0;   // otherwise every instance terminates inside k_admit (status 8)
@@ -898,7 +902,7 @@ int ipddp_solve_queue(ipddp_problem* h, const ipddp_queue* io) {
     cur = 1 - cur;
     r += 1;
   }
-  if (qlog) fclose(qlog);
+  if (qlog) fflush(qlog);
   // ---- results to the caller
   {
     const size_t sd_b = (size_t)QSD_COUNT * Q * sizeof(double), si_b = (size_t)QSI_COUNT * Q * sizeof(int);
