@@ -27,9 +27,12 @@ def assert_same_bits(a, b, what):
 
 
 def full_solve_parity(lib, oracle, wl, B, N=101, maxit=1000, tol=1e-7, vary_horizon=False, first=0, n_trace=4,
-                      check_traj=True):
-    """Whole-solve parity: status, k, j, l, objective, errors, step sequence (trace) and trajectories."""
+                      check_traj=True, mutate=None):
+    """Whole-solve parity: status, k, j, l, objective, errors, step sequence (trace) and trajectories.  mutate(batch)
+    may edit the instances (bounds, initial guesses) before both sides solve them."""
     b = instances.make_batch(wl, B, N, vary_horizon=vary_horizon, first=first)
+    if mutate is not None:
+        mutate(b)
     opt = lib.default_options(optimality_tolerance=tol, max_iterations=maxit)
     s = BatchSolver(wl, B, N, options=opt, trace_capacity=maxit, lib=lib)
     s.set_batch(b)
@@ -59,6 +62,29 @@ def full_solve_parity(lib, oracle, wl, B, N=101, maxit=1000, tol=1e-7, vary_hori
     st = s.stats()
     s.close()
     return r, st
+
+
+def one_sided_bounds(b):
+    """Edits a concar batch so that every branch of the control projection and of the slack / dual bookkeeping occurs
+    (reference src/solver.jl:70-95, src/bounds.jl:12-26): upper-only (the branch that is broken upstream, restated by its
+    evident intent on both sides), lower-only with a guess below the bound, two-sided with guesses outside on either
+    side, and no bound at all."""
+    inf = np.inf
+    nu = b.lower.shape[1]
+    ub = b.ubar.reshape(b.B, -1, nu)
+    for i in range(b.B):
+        k = i % 4
+        if k == 0:      # control 0 upper-only, guess above the bound -> projected down
+            b.lower[i, 0] = -inf; ub[i, :, 0] = b.upper[i, 0] + 0.5
+        elif k == 1:    # control 1 lower-only, guess below the bound -> projected up; control 0 upper-only, guess inside
+            b.upper[i, 1] = inf; ub[i, :, 1] = b.lower[i, 1] - 1.0
+            b.lower[i, 0] = -inf
+        elif k == 2:    # two-sided, guesses outside on both sides
+            ub[i, :, 0] = b.upper[i, 0] + 1.0; ub[i, :, 1] = b.lower[i, 1] - 1.0
+        else:           # no bounds on the first two controls; an upper bound on a slack-like control
+            b.lower[i, 0] = -inf; b.upper[i, 0] = inf; b.lower[i, 1] = -inf; b.upper[i, 1] = inf
+            b.upper[i, 2] = 0.75
+    b.ubar = np.ascontiguousarray(ub.reshape(b.B, -1))
 
 
 def queue_parity(lib, oracle, wl, Q, B, N=101, maxit=1000, tol=1e-7, vary_horizon=False, first=0):

@@ -221,3 +221,16 @@ def test_emulated_queue_bad_horizon(emu):
     with pytest.raises(RuntimeError, match="horizon out of range"):
         s.solve_queue(b.x1, b.ubar, None, b.lower, b.upper, hz)
     s.close()
+
+
+def test_emulated_one_sided_bounds(emu, oracle_mod):
+    """Every branch of the control projection (reference src/solver.jl:70-95): upper-only, lower-only, two-sided with the
+    guess outside, unbounded -- per instance, speculative and bulk kernels."""
+    for spec in (-1, 0):
+        emu.L.ipddp_set_tuning(None, b"fw_spec_max", spec)
+        emu.L.ipddp_set_tuning(None, b"bw_spec_max", spec)
+        try:
+            helpers.full_solve_parity(emu, oracle_mod, "concar", 4, 11, maxit=40, n_trace=4, mutate=helpers.one_sided_bounds)
+        finally:
+            emu.L.ipddp_set_tuning(None, b"fw_spec_max", -1)
+            emu.L.ipddp_set_tuning(None, b"bw_spec_max", -1)
