@@ -91,12 +91,6 @@ def test_varying_horizon_parity(gpu, oracle_mod):
     helpers.full_solve_parity(gpu, oracle_mod, "concar", 12, 61, vary_horizon=True, first=200, n_trace=2)
 
 
-def test_one_sided_bounds(gpu, oracle_mod):
-    """Upper-only, lower-only, two-sided (guess outside) and unbounded controls per instance: every branch of the control
-    projection of reference src/solver.jl:70-95, incl. the upper-only one no experiment uses."""
-    helpers.full_solve_parity(gpu, oracle_mod, "concar", 16, 41, maxit=300, n_trace=4, mutate=helpers.one_sided_bounds)
-
-
 def test_max_iterations_and_short_horizon(gpu, oracle_mod):
     helpers.full_solve_parity(gpu, oracle_mod, "cartpole", 4, 101, maxit=7)          # status 8
     helpers.full_solve_parity(gpu, oracle_mod, "double_integrator", 1, 2)           # single running stage
@@ -303,3 +297,9 @@ def test_stage_chain_rejects_mismatched_stages(gpu):
 def test_error_convention_gpu(gpu):
     """API misuse -> return code + ipddp_last_error, algorithmic outcome -> per-instance status."""
     helpers.api_error_convention(gpu)
+
+
+def test_one_sided_bounds(gpu, oracle_mod):
+    """Upper-only, lower-only, two-sided (guess outside) and unbounded controls per instance: every branch of the control
+    projection of reference src/solver.jl:70-95, incl. the upper-only one no experiment uses."""
+    helpers.full_solve_parity(gpu, oracle_mod, "concar", 16, 41, maxit=300, n_trace=4, mutate=helpers.one_sided_bounds)
