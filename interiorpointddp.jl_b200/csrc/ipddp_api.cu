@@ -511,11 +511,11 @@ int ipddp_set_stage_types(ipddp_problem* h, const int* stage_types) {
   if (!stage_types) return fail("null stage type table");
   const DevView& v = h->v;
   const ModelVTable* vt = h->vt;
+  for (int t = 0; t < v.N - 1; ++t)
+    if (stage_types[t] < 0 || stage_types[t] >= vt->nstage) return fail("stage type out of range");
   for (int t = 0; t < v.N - 1; ++t) {
     const int k = stage_types[t];
-    if (k < 0 || k >= vt->nstage) return fail("stage type out of range");
     const int next_nx = t + 1 < v.N - 1 ? vt->snx[stage_types[t + 1]] : vt->nxt;
-    if (t + 1 < v.N - 1 && (stage_types[t + 1] < 0 || stage_types[t + 1] >= vt->nstage)) return fail("stage type out of range");
     if (vt->snxn[k] != next_nx)
       return fail("stage " + std::to_string(t) + " maps to " + std::to_string(vt->snxn[k]) + " states but the next knot has " +
                   std::to_string(next_nx));

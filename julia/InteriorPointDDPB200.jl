@@ -152,9 +152,9 @@ Batched counterpart of `Solver(T, dynamics, objectives, constraints, bounds; opt
 """
 function BatchProblem(model::String, B::Int, N::Int; options::Options=Options{Float64}(), device::Int=0,
                       indices_compl::Vector{Cint}=Cint[], trace_capacity::Int=0)
-    dims = [Ref{Cint}(0) for _ in 1:5]
+    nx = Ref{Cint}(0); nu = Ref{Cint}(0); nc = Ref{Cint}(0); np = Ref{Cint}(0); slots = Ref{Cint}(0)
     check(ccall((:ipddp_model_dims, LIB), Cint, (Cstring, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}),
-                model, dims...), "ipddp_model_dims")
+                model, nx, nu, nc, np, slots), "ipddp_model_dims")      # (ccall takes no splatted arguments)
     nst = Ref{Cint}(0); nxt = Ref{Cint}(0)
     snx = zeros(Cint, 4); snu = zeros(Cint, 4); snc = zeros(Cint, 4); snxn = zeros(Cint, 4)
     check(ccall((:ipddp_model_stages, LIB), Cint,
@@ -164,9 +164,9 @@ function BatchProblem(model::String, B::Int, N::Int; options::Options=Options{Fl
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ipddp_problem_create, LIB), Cint,
                 (Cstring, Cint, Cint, Ptr{Cint}, Cint, Ref{COptions}, Cint, Cint, Ref{Ptr{Cvoid}}),
-                model, B, N, isempty(indices_compl) ? C_NULL : pointer(indices_compl), length(indices_compl),
+                model, B, N, isempty(indices_compl) ? C_NULL : indices_compl, length(indices_compl),
                 Ref(COptions(options)), device, trace_capacity, h), "ipddp_problem_create")
-    p = BatchProblem(h[], model, B, N, dims[1][], dims[2][], dims[3][], dims[4][], Int(ns), Int(nst[]), zeros(Cint, B), zeros(Cint, B),
+    p = BatchProblem(h[], model, B, N, nx[], nu[], nc[], np[], Int(ns), Int(nst[]), zeros(Cint, B), zeros(Cint, B),
                      zeros(Cint, B), zeros(Cint, B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B), zeros(B))
     finalizer(q -> ccall((:ipddp_problem_destroy, LIB), Cint, (Ptr{Cvoid},), q.handle), p)
     return p
@@ -180,10 +180,12 @@ Batched `solve!(solver, x1, controls)` (reference src/solve.jl:1-4).  `x1` is nx
 """
 function solve!(p::BatchProblem, x1::Matrix{Float64}, controls::Array{Float64,3}; params=nothing,
                 lower::Matrix{Float64}, upper::Matrix{Float64}, horizons=nothing)
+    size(x1, 2) == p.B && size(controls, 3) == p.B || error("x1 must be nx x B and controls nu x (N-1) x B with B = $(p.B)")
+    hz = horizons === nothing ? nothing : convert(Vector{Cint}, horizons)
     check(ccall((:ipddp_set_inputs, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
                 p.handle, x1, controls, params === nothing ? C_NULL : params, lower, upper,
-                horizons === nothing ? C_NULL : horizons), "ipddp_set_inputs")
+                hz === nothing ? C_NULL : hz), "ipddp_set_inputs")
     check(ccall((:ipddp_solve, LIB), Cint, (Ptr{Cvoid}, Cint), p.handle, 0), "ipddp_solve")
     return fetch_results!(p)
 end
@@ -245,10 +247,12 @@ primal_inf, dual_inf, cs_inf, μ, reg_last, step_size, l, θ, barrier Lagrangian
 """
 function get_trace(p::BatchProblem, b::Integer)
     n = Ref{Cint}(0)
-    sig = (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ref{Cint})
-    check(ccall((:ipddp_get_trace, LIB), Cint, sig, p.handle, b - 1, C_NULL, n), "ipddp_get_trace")   # size query
+    # (the argument types of a ccall must be a literal tuple)
+    check(ccall((:ipddp_get_trace, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ref{Cint}), p.handle, b - 1, C_NULL, n),
+          "ipddp_get_trace")                                                                           # size query
     rows = zeros(12, n[])
-    check(ccall((:ipddp_get_trace, LIB), Cint, sig, p.handle, b - 1, rows, n), "ipddp_get_trace")
+    check(ccall((:ipddp_get_trace, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ref{Cint}), p.handle, b - 1, rows, n),
+          "ipddp_get_trace")
     return rows
 end
 
@@ -306,6 +310,7 @@ and the trajectories (states nx x N x Q, controls nu x (N-1) x Q).
 function solve_queue!(p::BatchProblem, x1::Matrix{Float64}, controls::Array{Float64,3}; params=nothing,
                       lower::Matrix{Float64}, upper::Matrix{Float64}, horizons=nothing)
     Q = size(x1, 2)
+    horizons = horizons === nothing ? nothing : convert(Vector{Cint}, horizons)
     ints = [zeros(Cint, Q) for _ in 1:8]
     dbls = [zeros(Cdouble, Q) for _ in 1:7]
     x = zeros(p.ns, p.N, Q); u = zeros(p.nu, p.N - 1, Q)
@@ -340,16 +345,24 @@ struct Dynamics
     num_control::Int
     quasi_newton::Bool
     user::Dict{String,Function}      # user-provided derivative closures (src/dynamics.jl:58-61)
+    inplace::Bool                    # closures in the reference's in-place form `f!(out, x, u)` (user-derivative form)
 end
 Dynamics(f::Function, num_state::Int, num_control::Int; quasi_newton::Bool=false) =
-    Dynamics(f, num_state, num_state, num_control, quasi_newton, Dict{String,Function}())
+    Dynamics(f, num_state, num_state, num_control, quasi_newton, Dict{String,Function}(), false)
+"""
+    Dynamics(f!, fx!, fu!, num_next_state, num_state, num_control; vfxx=nothing, vfux=nothing, vfuu=nothing, inplace=true)
+
+User-provided dynamics and derivatives (reference src/dynamics.jl:58-61).  As in the reference the closures are in-place:
+`f!(y, x, u)`, `fx!(J, x, u)`, `vfxx!(H, x, u, v)` (each optionally with a trailing parameter vector `p`); they are called
+once with symbolic arguments and compiled.  `inplace=false` takes closures that return their value instead.
+"""
 function Dynamics(f::Function, fx::Function, fu::Function, num_next_state::Int, num_state::Int, num_control::Int;
-                  vfxx=nothing, vfux=nothing, vfuu=nothing)
+                  vfxx=nothing, vfux=nothing, vfuu=nothing, inplace::Bool=true)
     user = Dict{String,Function}("fx" => fx, "fu" => fu)
     for (k, g) in (("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu))
         g === nothing || (user[k] = g)
     end
-    return Dynamics(f, num_next_state, num_state, num_control, false, user)
+    return Dynamics(f, num_next_state, num_state, num_control, false, user, inplace)
 end
 
 "Objective(f, num_state, num_control)  (reference src/objectives.jl:12)"
@@ -362,23 +375,33 @@ end
 "Constraint(c, num_state, num_control; quasi_newton=false, indices_compl=nothing) | Constraint(num_state, num_control)  (reference src/constraints.jl:16,52)"
 struct Constraint
     c::Union{Function,Nothing}
+    num_constraint::Int              # known up front only in the user-derivative form; otherwise length(c(x, u))
     num_state::Int
     num_control::Int
     quasi_newton::Bool
     indices_compl::Vector{Int}       # 1-based, as in the reference
     user::Dict{String,Function}
+    inplace::Bool                    # closures in the reference's in-place form `c!(out, x, u)` (user-derivative form)
 end
 Constraint(c::Function, num_state::Int, num_control::Int; quasi_newton::Bool=false, indices_compl=nothing) =
-    Constraint(c, num_state, num_control, quasi_newton, indices_compl === nothing ? Int[] : collect(Int, indices_compl),
-               Dict{String,Function}())
-Constraint(num_state::Int, num_control::Int) = Constraint(nothing, num_state, num_control, false, Int[], Dict{String,Function}())
+    Constraint(c, -1, num_state, num_control, quasi_newton, indices_compl === nothing ? Int[] : collect(Int, indices_compl),
+               Dict{String,Function}(), false)
+Constraint(num_state::Int, num_control::Int) =
+    Constraint(nothing, 0, num_state, num_control, false, Int[], Dict{String,Function}(), false)
+"""
+    Constraint(c!, cx!, cu!, num_constraint, num_state, num_control; indices_compl, vcxx, vcux, vcuu, inplace=true)
+
+User-provided constraints and derivatives (reference src/constraints.jl:60-64), in-place closures as in the reference
+(`c!(out, x, u)`, `cx!(J, x, u)`, `vcxx!(H, x, u, v)`); `inplace=false` takes closures that return their value.
+"""
 function Constraint(c::Function, cx::Function, cu::Function, num_constraint::Int, num_state::Int, num_control::Int;
-                    indices_compl=nothing, vcxx=nothing, vcux=nothing, vcuu=nothing)
+                    indices_compl=nothing, vcxx=nothing, vcux=nothing, vcuu=nothing, inplace::Bool=true)
     user = Dict{String,Function}("cx" => cx, "cu" => cu)
     for (k, g) in (("vcxx", vcxx), ("vcux", vcux), ("vcuu", vcuu))
         g === nothing || (user[k] = g)
     end
-    return Constraint(c, num_state, num_control, false, indices_compl === nothing ? Int[] : collect(Int, indices_compl), user)
+    return Constraint(c, num_constraint, num_state, num_control, false,
+                      indices_compl === nothing ? Int[] : collect(Int, indices_compl), user, inplace)
 end
 
 "Bound(lower, upper) | Bound(T, num_control) | Bound(num_control, lower, upper)  (reference src/bounds.jl:12-26)"
@@ -397,6 +420,15 @@ function Bound(lower::Vector{T}, upper::Vector{T}) where T
 end
 Bound(T, num_control::Int) = Bound(-T(Inf) .* ones(T, num_control), T(Inf) .* ones(T, num_control))
 Bound(num_control::Int, lower::T, upper::T) where T = Bound(lower .* ones(T, num_control), upper .* ones(T, num_control))
+
+# What makes two stage objects "the same" when stages are grouped into types: the identity of their closures and their
+# sizes / flags -- so `[Dynamics(f, nx, nu) for k = 1:N-1]` (reference experiments/ipddp2/pushing_1_obs.jl:98) is ONE stage
+# type exactly like `d = Dynamics(f, nx, nu); [d for k = 1:N-1]` (cartpole_friction.jl:53).
+user_ident(user) = Tuple(sort!([(k, objectid(g)) for (k, g) in user]))
+ident(d::Dynamics) = (objectid(d.f), d.num_next_state, d.num_state, d.num_control, d.quasi_newton, d.inplace, user_ident(d.user))
+ident(o::Objective) = (objectid(o.f), o.num_state, o.num_control)
+ident(c::Constraint) = (c.c === nothing ? UInt(0) : objectid(c.c), c.num_constraint, c.num_state, c.num_control,
+                        c.quasi_newton, c.inplace, Tuple(c.indices_compl), user_ident(c.user))
 
 "Mirror of the reference's SolverData fields users read (src/data/solver.jl:8-33); vectors of length `batch` (scalars for batch = 1)."
 Base.@kwdef mutable struct SolverData
@@ -448,7 +480,7 @@ function Solver(T, dynamics::Vector{Dynamics}, objectives::Vector{Objective}, co
     # ---- stage types: running stages built from the same objects (and equal bounds) share one type
     keys = Any[]; stage_type = Int[]
     for t in 1:N-1
-        key = (objectid(dynamics[t]), objectid(objectives[t]), objectid(constraints[t]), bnds[t].lower, bnds[t].upper)
+        key = (ident(dynamics[t]), ident(objectives[t]), ident(constraints[t]), bnds[t].lower, bnds[t].upper)
         k = findfirst(==(key), keys)
         k === nothing && (push!(keys, key); k = length(keys))
         push!(stage_type, k)
@@ -459,8 +491,8 @@ function Solver(T, dynamics::Vector{Dynamics}, objectives::Vector{Objective}, co
     rep = [findfirst(==(k), stage_type) for k in order]          # a representative stage of each type
     stage_type = [findfirst(==(k), order) - 1 for k in stage_type]
     opts = options === nothing ? Options{T}() : deepcopy(options)
-    lN = (x, args...) -> oN.f(x, T[], args...)
-    zeroN = (x, args...) -> 0 * x[1]
+    lN = (x, p) -> call_with_p(oN.f, (x, T[]), p)       # the terminal objective is called with an empty control vector
+    zeroN = (x, p) -> 0 * x[1]
     sms = StageModel[]
     for (k, t) in enumerate(rep)
         d, o, c = dynamics[t], objectives[t], constraints[t]
@@ -468,7 +500,9 @@ function Solver(T, dynamics::Vector{Dynamics}, objectives::Vector{Objective}, co
         push!(sms, trace("pending_s$(k - 1)", d.f, o.f, islast ? lN : zeroN, c.c, d.num_state, d.num_control;
                          num_parameter=num_parameter, qn_dynamics=d.quasi_newton, qn_constraint=c.quasi_newton,
                          indices_compl=c.indices_compl, user=merge(d.user, c.user),
-                         nx_term=islast ? oN.num_state : d.num_state))
+                         nx_term=islast ? oN.num_state : d.num_state, inplace_dynamics=d.inplace,
+                         inplace_constraint=c.inplace, num_next_state=d.num_next_state,
+                         num_constraint=max(c.num_constraint, 0)))
     end
     chain = length(sms) > 1 || sms[1].nxn != sms[1].nx || sms[1].nxt != sms[1].nx
     # the model's identity is its traced source
@@ -487,7 +521,7 @@ function Solver(T, dynamics::Vector{Dynamics}, objectives::Vector{Objective}, co
     for (k, sm) in enumerate(sms)
         ic = Cint.(sm.indices_compl .- 1)
         check(ccall((:ipddp_set_stage_compl, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Cint), prob.handle, k - 1,
-                    isempty(ic) ? C_NULL : pointer(ic), length(ic)), "ipddp_set_stage_compl")
+                    isempty(ic) ? C_NULL : ic, length(ic)), "ipddp_set_stage_compl")
     end
     snx = zeros(Cint, N); snu = zeros(Cint, N); snc = zeros(Cint, N)
     check(ccall((:ipddp_stage_layout, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), prob.handle, snx, snu, snc),

@@ -57,21 +57,37 @@ renamed(sm::StageModel, name::String) = StageModel(name, sm.nx, sm.nu, sm.nc, sm
 call_with_p(fn, args, p) = applicable(fn, args..., p) ? fn(args..., p) : fn(args...)
 
 """
+Value of a traced closure: `fn(args...[, p])`; for a closure in the reference's in-place form `fn!(out, args...[, p])`
+(what the reference's user-derivative constructors take, src/dynamics.jl:49-61, src/constraints.jl:60-64) the symbolic
+buffer `out` of the given shape after the call.
+"""
+function traced(fn, args, p, shape)
+    shape === nothing && return call_with_p(fn, args, p)
+    out = zeros(Num, shape...)
+    call_with_p(fn, (out, args...), p)
+    return out
+end
+
+"""
     trace(name, f, l, lN, c, nx, nu; num_parameter=0, qn_dynamics=false, qn_constraint=false, indices_compl=Int[],
-          user=Dict())
+          user=Dict(), inplace_dynamics=false, inplace_constraint=false, num_next_state=nx, num_constraint=0)
 
 The reference's symbolic differentiation (src/dynamics.jl:15-47, src/objectives.jl:12-33, src/constraints.jl:16-50) for one
 stage type.  `user` may hold user-provided derivative closures ("fx", "fu", "vfxx", ... as in src/dynamics.jl:58-61,
-src/constraints.jl:60-64): they are traced instead of differentiated and missing contractions stay zero.
+src/constraints.jl:60-64): they are traced instead of differentiated and missing contractions stay zero.  With
+`inplace_dynamics` / `inplace_constraint` the object's closures (f, fx, ... / c, cx, ...) follow the reference's in-place
+convention `f!(out, x, u)` and write into symbolic buffers sized by `num_next_state` / `num_constraint`.
 """
 function trace(name, f, l, lN, c, nx::Int, nu::Int; num_parameter::Int=0, qn_dynamics::Bool=false,
-               qn_constraint::Bool=false, indices_compl=Int[], user=Dict{String,Function}(), nx_term::Int=nx)
+               qn_constraint::Bool=false, indices_compl=Int[], user=Dict{String,Function}(), nx_term::Int=nx,
+               inplace_dynamics::Bool=false, inplace_constraint::Bool=false, num_next_state::Int=nx,
+               num_constraint::Int=0)
     x = Symbolics.variables(:x, 1:nx)
     u = Symbolics.variables(:u, 1:nu)
     p = Symbolics.variables(:p, 1:max(num_parameter, 1))
-    y = collect(call_with_p(f, (x, u), p))
+    y = collect(Num, traced(f, (x, u), p, inplace_dynamics ? (num_next_state,) : nothing))
     nxn = length(y)          # a stage of a chain may map onto a state of another size
-    cv = c === nothing ? Num[] : collect(call_with_p(c, (x, u), p))
+    cv = c === nothing ? Num[] : collect(Num, traced(c, (x, u), p, inplace_constraint ? (num_constraint,) : nothing))
     nc = length(cv)
     v = Symbolics.variables(:v, 1:max(nc, 1))
     lam = Symbolics.variables(:lam, 1:nxn)
@@ -79,19 +95,22 @@ function trace(name, f, l, lN, c, nx::Int, nu::Int; num_parameter::Int=0, qn_dyn
     xt = nx_term == nx ? x : Symbolics.variables(:x, 1:nx_term)     # the terminal cost may see a state of another size
     lNval = call_with_p(lN, (xt,), p)
     m = Dict{String,Matrix{Num}}()
-    usr(key, args...) = haskey(user, key) ? Matrix{Num}(call_with_p(user[key], args, p)) : nothing
-    pick(key, auto, args...; group_user=false, rows=0, cols=0) = begin
-        M = usr(key, args...)
-        M !== nothing ? M : (group_user && startswith(key, "v") ? zeros(Num, rows, cols) : auto())
+    # a user-provided closure is traced (into a rows x cols buffer if its object is in-place); of a user-derivative object
+    # the contractions that were not provided stay zero (the reference leaves those caches untouched); anything else is
+    # differentiated as the reference's symbolic constructors do
+    inplace_of(key) = (key[1] == 'c' || startswith(key, "vc")) ? inplace_constraint : inplace_dynamics
+    pick(key, auto, args...; group_user=false, rows, cols) = begin
+        haskey(user, key) && return Matrix{Num}(reshape(collect(Num, traced(user[key], args, p, inplace_of(key) ? (rows, cols) : nothing)), rows, cols))
+        (group_user && startswith(key, "v")) ? zeros(Num, rows, cols) : auto()
     end
     udyn = haskey(user, "fx"); ucon = haskey(user, "cx")
-    m["fx"] = pick("fx", () -> Symbolics.jacobian(y, x), x, u)
-    m["fu"] = pick("fu", () -> Symbolics.jacobian(y, u), x, u)
+    m["fx"] = pick("fx", () -> Symbolics.jacobian(y, x), x, u; rows=nxn, cols=nx)
+    m["fu"] = pick("fu", () -> Symbolics.jacobian(y, u), x, u; rows=nxn, cols=nu)
     lx = Symbolics.gradient(lval, x); lu = Symbolics.gradient(lval, u)
     m["lx"] = reshape(lx, :, 1); m["lu"] = reshape(lu, :, 1)
     m["lxx"] = Symbolics.jacobian(lx, x); m["luu"] = Symbolics.jacobian(lu, u); m["lux"] = Symbolics.jacobian(lu, x)
-    m["cx"] = nc == 0 ? zeros(Num, 0, nx) : pick("cx", () -> Symbolics.jacobian(cv, x), x, u)
-    m["cu"] = nc == 0 ? zeros(Num, 0, nu) : pick("cu", () -> Symbolics.jacobian(cv, u), x, u)
+    m["cx"] = nc == 0 ? zeros(Num, 0, nx) : pick("cx", () -> Symbolics.jacobian(cv, x), x, u; rows=nc, cols=nx)
+    m["cu"] = nc == 0 ? zeros(Num, 0, nu) : pick("cu", () -> Symbolics.jacobian(cv, u), x, u; rows=nc, cols=nu)
     vv = v[1:nc]
     if qn_constraint || nc == 0      # quasi-Newton constraint object: its contraction caches stay zero
         m["vcxx"] = zeros(Num, nx, nx); m["vcux"] = zeros(Num, nu, nx); m["vcuu"] = zeros(Num, nu, nu)
@@ -125,8 +144,7 @@ function classify(sm::StageModel, names::Vector{String}, consts::Vector{Float64}
         shown = startswith(nm, "N") ? nm[2:end] : nm
         for j in 1:size(M, 2), i in 1:size(M, 1)
             e = M[i, j]
-            (e isa Number && iszero(e)) && continue
-            iszero(Symbolics.value(e)) && continue
+            iszero(e) && continue                      # structural zero (Base.iszero(::Num))
             (shown in UPPER_ONLY && i > j) && continue
             if isconst_entry(e)
                 push!(consts, constval(e))
@@ -182,7 +200,7 @@ function emit_device(sm::StageModel)
     dn_entries, dn_dyn = classify(sm, dn_names, consts)
     all_entries = vcat(d_entries, vf_entries, dn_entries)
     fu = sm.mats["fu"]
-    fucol = [j - 1 for j in 1:sm.nu if any(!iszero(Symbolics.value(fu[i, j])) for i in 1:sm.nxn)]
+    fucol = [j - 1 for j in 1:sm.nu if any(!iszero(fu[i, j]) for i in 1:sm.nxn)]
     fuidx = fill(255, sm.nu)
     for (c, j) in enumerate(fucol)
         fuidx[j+1] = c - 1
