@@ -53,6 +53,28 @@ def _with_p(fn, nargs_without_p):
     return fn if _arity(fn) > nargs_without_p else (lambda *a: fn(*a[:nargs_without_p]))
 
 
+def _inplace(fn, nargs_without_p):
+    """Adapter for a closure in the reference's in-place form `fn!(out, args...[, p])` (src/dynamics.jl:49-61,
+    src/constraints.jl:60-64): the tracer hands it a symbolic buffer of the right shape as `out`."""
+    if fn is None:
+        return None
+    g = _with_p(fn, nargs_without_p + 1)
+    h = lambda *a: g(*a)
+    h._ipddp_inplace = True
+    return h
+
+
+def _filled(fn, n):
+    """value-returning view (x, u, p) -> list of an in-place vector closure fn!(out[n], x, u, p)"""
+    import sympy as sp
+
+    def g(x, u, p):
+        out = sp.zeros(n, 1)
+        fn(out, x, u, p)
+        return list(out)
+    return g
+
+
 # ------------------------------------------------------------------------------------------------
 # constructors (reference src/dynamics.jl:15, src/objectives.jl:12, src/constraints.jl:16,52, src/bounds.jl:12-26)
 # ------------------------------------------------------------------------------------------------
@@ -62,19 +84,24 @@ class Dynamics:
     User-provided derivatives (reference src/dynamics.jl:58-61):
     Dynamics(f, fx, fu, num_next_state, num_state, num_control; vfxx=None, vfux=None, vfuu=None) -- fx, fu are closures
     (x, u[, p]) -> matrix; the contractions (x, u, v[, p]) -> matrix are optional and stay zero when omitted, as in the
-    reference.  (The reference's closures are in-place `f!(out, x, u)`; here they return the value, because they are
-    traced symbolically into CUDA device functions.)"""
+    reference.  The closures are traced symbolically into CUDA device functions, so by default they return their value;
+    `inplace=True` takes the reference's own in-place form instead: `f(y, x, u)`, `fx(J, x, u)`, `vfxx(H, x, u, v)` fill
+    a (symbolic) output buffer."""
 
-    def __init__(self, f: Callable, *args, quasi_newton: bool = False, vfxx=None, vfux=None, vfuu=None):
+    def __init__(self, f: Callable, *args, quasi_newton: bool = False, vfxx=None, vfux=None, vfuu=None,
+                 inplace: bool = False):
         self.f = _with_p(f, 2)
         self._src = f
         self.user_derivs = {}
         if len(args) == 5 and callable(args[0]) and callable(args[1]):
             fx, fu, num_next_state, num_state, num_control = args
-            self.user_derivs = {"fx": _with_p(fx, 2), "fu": _with_p(fu, 2)}
+            wrap = _inplace if inplace else _with_p
+            if inplace:
+                self.f = _filled(_with_p(f, 3), int(num_next_state))
+            self.user_derivs = {"fx": wrap(fx, 2), "fu": wrap(fu, 2)}
             for k, fn in (("vfxx", vfxx), ("vfux", vfux), ("vfuu", vfuu)):
                 if fn is not None:
-                    self.user_derivs[k] = _with_p(fn, 3)
+                    self.user_derivs[k] = wrap(fn, 3)
             self._extra_src = [fx, fu, vfxx, vfux, vfuu]
         else:
             num_state, num_control = args
@@ -96,19 +123,21 @@ class Constraint:
     Constraint(num_state, num_control)."""
 
     def __init__(self, *args, quasi_newton: bool = False, indices_compl: Optional[Sequence[int]] = None,
-                 vcxx=None, vcux=None, vcuu=None):
+                 vcxx=None, vcux=None, vcuu=None, inplace: bool = False):
         self.user_derivs = {}
         self._extra_src = []
         if len(args) == 6 and callable(args[0]) and callable(args[1]):
             # user-provided derivatives (reference src/constraints.jl:60-64):
             # Constraint(c, cx, cu, num_constraint, num_state, num_control; indices_compl, vcxx, vcux, vcuu)
-            c, cx, cu, _num_constraint, nx, nu = args
-            self.c = _with_p(c, 2)
+            # inplace=True: the reference's in-place closures c(out, x, u), cx(J, x, u), vcxx(H, x, u, v)
+            c, cx, cu, num_constraint, nx, nu = args
+            wrap = _inplace if inplace else _with_p
+            self.c = _filled(_with_p(c, 3), int(num_constraint)) if inplace else _with_p(c, 2)
             self._src = c
-            self.user_derivs = {"cx": _with_p(cx, 2), "cu": _with_p(cu, 2)}
+            self.user_derivs = {"cx": wrap(cx, 2), "cu": wrap(cu, 2)}
             for k, fn in (("vcxx", vcxx), ("vcux", vcux), ("vcuu", vcuu)):
                 if fn is not None:
-                    self.user_derivs[k] = _with_p(fn, 3)
+                    self.user_derivs[k] = wrap(fn, 3)
             self._extra_src = [cx, cu, vcxx, vcux, vcuu]
         elif callable(args[0]):
             c, nx, nu = args

@@ -155,7 +155,11 @@ def trace(md: workloads.ModelDef) -> Dict[str, Bundle]:
         fn = ud.get(name)
         if fn is None:
             return None
-        M = sp.Matrix(fn(*args))
+        if getattr(fn, "_ipddp_inplace", False):     # the reference's in-place form: fn!(out, args...)
+            M = sp.zeros(rows, cols)
+            fn(M, *args)
+        else:
+            M = sp.Matrix(fn(*args))
         if M.shape != (rows, cols):
             if rows * cols == len(M):
                 M = M.reshape(rows, cols)

@@ -86,3 +86,54 @@ def test_model_identity_is_the_traced_source():
     scale["dt"] = 0.02
     assert api.model_digest(m1) != a                   # same closure object, different traced code
     assert api.model_digest(dataclasses.replace(md, indices_compl=[0])) != d0
+
+
+def test_inplace_user_closures_as_in_the_reference():
+    """The reference's user-derivative constructors take IN-PLACE closures (`f!(y, x, u)`, `fx!(J, x, u)`,
+    `vfxx!(H, x, u, v)`: src/dynamics.jl:49-61, src/constraints.jl:60-64).  `inplace=True` accepts that form; the model
+    it traces is the one the value-returning form gives."""
+    from ipddp_b200 import api
+    dt = 0.05
+    f = lambda x, u: [x[0] + dt * x[1], x[1] + dt * sp.sin(u[0]) * x[0]]
+    fx = lambda x, u: [[1, dt], [dt * sp.sin(u[0]), 1]]
+    fu = lambda x, u: [[0, 0], [dt * sp.cos(u[0]) * x[0], 0]]
+    vfux = lambda x, u, v: [[v[1] * dt * sp.cos(u[0]), 0], [0, 0]]
+    c = lambda x, u: [u[1] - x[0] * u[0]]
+    cx = lambda x, u: [[-u[0], 0]]
+    cu = lambda x, u: [[-x[0], 1]]
+
+    def f_ip(y, x, u):
+        y[0] = x[0] + dt * x[1]
+        y[1] = x[1] + dt * sp.sin(u[0]) * x[0]
+
+    def fx_ip(J, x, u):
+        J[0, 0] = 1; J[0, 1] = dt; J[1, 0] = dt * sp.sin(u[0]); J[1, 1] = 1
+
+    def fu_ip(J, x, u):
+        J[1, 0] = dt * sp.cos(u[0]) * x[0]
+
+    def vfux_ip(H, x, u, v):
+        H[0, 0] = v[1] * dt * sp.cos(u[0])
+
+    def c_ip(out, x, u):
+        out[0] = u[1] - x[0] * u[0]
+
+    def cx_ip(J, x, u):
+        J[0, 0] = -u[0]
+
+    def cu_ip(J, x, u):
+        J[0, 0] = -x[0]; J[0, 1] = 1
+
+    dv = api.Dynamics(f, fx, fu, 2, 2, 2, vfux=vfux)
+    di = api.Dynamics(f_ip, fx_ip, fu_ip, 2, 2, 2, vfux=vfux_ip, inplace=True)
+    cv = api.Constraint(c, cx, cu, 1, 2, 2)
+    ci = api.Constraint(c_ip, cx_ip, cu_ip, 1, 2, 2, inplace=True)
+
+    def model(d, cc):
+        return workloads.ModelDef(name="m", nx=2, nu=2, np_=0, f=d.f, stage_cost=lambda x, u, p: u[0] ** 2 + x[1] ** 2,
+                                  term_cost=lambda x, p: x[0] ** 2, c=cc.c, lower=lambda p: [-1, -1], upper=lambda p: [1, 1],
+                                  u_init=[0.0, 0.0], dt=dt, user_derivs={**d.user_derivs, **cc.user_derivs},
+                                  user_dynamics=True, user_constraint=True)
+    mv, mi = model(dv, cv), model(di, ci)
+    assert generate.emit_device(mv, generate.trace(mv)) == generate.emit_device(mi, generate.trace(mi))
+    assert api.model_digest(mv) == api.model_digest(mi)
