@@ -74,3 +74,25 @@ def test_package_params_tables_are_the_reference_fixtures():
     assert names == sorted(os.listdir(instances.PARAMS_DIR)) and len(names) == 4
     for n in names:
         assert filecmp.cmp(os.path.join(gold, n), os.path.join(instances.PARAMS_DIR, n), shallow=False), n
+
+
+def test_table_residual_is_the_one_ulp_noise_floor(oracle_mod):
+    """Why only ~54 % of the acrobot rows reproduce the reference's iteration counts: the count is a chaotic function of
+    last-bit rounding.  Moving every model parameter to the next representable double makes the oracle disagree WITH
+    ITSELF on as many rows as it disagrees with the reference's table (tests/tools/perturbation_study.py, all classes:
+    profiles/r2_perturbation_stability.json) -- no implementation that is not bit-identical to the reference's toolchain
+    (OpenBLAS kernel choice, Symbolics' expression order, Julia's libm) can match more rows than that."""
+    wl, n = "acrobot", 100
+    g = instances.load_golden_results(wl)
+    b = instances.make_batch(wl, n, 101)
+    opt = oracle_mod.default_options(optimality_tolerance=1e-7)
+    base, _, _ = oracle_mod.solve_batch(wl, 101, b.p, b.lower, b.upper, b.x1, b.ubar, options=opt)
+    pert, _, _ = oracle_mod.solve_batch(wl, 101, np.nextafter(b.p, np.inf), b.lower, b.upper, b.x1, b.ubar, options=opt)
+    vs_table = sum(1 for i in range(n) if base[i].k == g["iterations"][i]
+                   and abs(base[i].objective - g["objective"][i]) <= 1e-8 * max(1.0, abs(g["objective"][i])))
+    vs_self = sum(1 for i in range(n) if base[i].k == pert[i].k and f"{base[i].objective:.8e}" == f"{pert[i].objective:.8e}")
+    assert vs_table >= 50 and vs_self >= 40
+    assert vs_self <= vs_table + 15, (vs_self, vs_table)      # the table is reproduced about as well as the oracle reproduces itself
+    # the perturbation is harmless where it should be: every instance still converges to (nearly) the same optimum or another
+    # local one of similar cost
+    assert sum(1 for r in pert if r.status == 0) >= 95

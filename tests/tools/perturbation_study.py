@@ -1,0 +1,70 @@
+"""CPU study (no GPU): how stable are the ORACLE's own iteration counts under a one-ulp change of the inputs?
+
+The reference's results tables pin iteration count and 9-digit objective per instance.  The oracle reproduces 93 / 97 /
+54 / 63 of 100 rows (cartpole / concar_quad / acrobot / concar) and no fixed summation order does better
+(profiles/r2_summation_order.json).  If those counts are a chaotic function of last-bit rounding, then the oracle must
+disagree WITH ITSELF at a similar rate once any input moves by one unit in the last place -- a perturbation far below
+anything the reference's toolchain (OpenBLAS kernel choice, Symbolics' expression order, Julia's libm) can be assumed to
+preserve.  This script measures exactly that: every golden instance is solved unperturbed and with
+  a) the first model parameter moved to the next representable double,
+  b) the initial control guess of the last control of every stage moved to the next representable double,
+  c) every model parameter moved to the next representable double,
+and rows with the same iteration count AND the same 9-digit objective as the unperturbed solve are counted, next to the
+rows that agree with the reference's table.
+    python tests/tools/perturbation_study.py > profiles/r2_perturbation_stability.json
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np  # noqa: E402
+import ipddp_b200  # noqa: E402,F401
+from ipddp_b200 import instances  # noqa: E402
+import oracle  # noqa: E402
+
+
+def same9(a, b):
+    return f"{a:.8e}" == f"{b:.8e}"
+
+
+def main():
+    oracle.build()
+    opt = oracle.default_options(optimality_tolerance=1e-7)
+    out = {}
+    for wl in ("cartpole", "concar_quad", "acrobot", "concar"):
+        g = instances.load_golden_results(wl)
+        n = len(g["seed"])
+        b = instances.make_batch(wl, n, 101)
+        nu = b.lower.shape[1]
+
+        def solve(p, ubar):
+            res, _, _ = oracle.solve_batch(wl, 101, p, b.lower, b.upper, b.x1, ubar, options=opt)
+            return [(r.k, r.objective, r.status) for r in res]
+        base = solve(b.p, b.ubar)
+        variants = {}
+        p_up = b.p.copy(); p_up[:, 0] = np.nextafter(p_up[:, 0], np.inf)
+        p_all = np.nextafter(b.p, np.inf)
+        u_up = b.ubar.copy().reshape(n, -1, nu); u_up[:, :, nu - 1] = np.nextafter(u_up[:, :, nu - 1], np.inf)
+        variants["first parameter + 1 ulp"] = solve(p_up, b.ubar)
+        variants["every parameter + 1 ulp"] = solve(p_all, b.ubar)
+        variants["last control's initial guess + 1 ulp"] = solve(b.p, np.ascontiguousarray(u_up.reshape(n, -1)))
+        row = {"rows": n,
+               "oracle_vs_reference_table": sum(1 for i in range(n) if base[i][0] == g["iterations"][i]
+                                                and abs(base[i][1] - g["objective"][i]) <= 1e-8 * max(1.0, abs(g["objective"][i]))),
+               "oracle_vs_itself": {}}
+        for name, v in variants.items():
+            same_k = sum(1 for i in range(n) if v[i][0] == base[i][0])
+            both = sum(1 for i in range(n) if v[i][0] == base[i][0] and same9(v[i][1], base[i][1]))
+            gap = float(np.mean([abs(v[i][0] - base[i][0]) for i in range(n)]))
+            row["oracle_vs_itself"][name] = {"same_iterations": same_k, "same_iterations_and_9_digit_objective": both,
+                                             "mean_abs_iteration_gap": round(gap, 2)}
+        out[wl] = row
+        print(wl, json.dumps(row), file=sys.stderr)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
