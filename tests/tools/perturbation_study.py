@@ -34,7 +34,7 @@ def main():
     oracle.build()
     opt = oracle.default_options(optimality_tolerance=1e-7)
     out = {}
-    for wl in ("cartpole", "concar_quad", "acrobot", "concar"):
+    for wl in ("cartpole", "concar_quad", "acrobot", "concar", "pushing"):
         g = instances.load_golden_results(wl)
         n = len(g["seed"])
         b = instances.make_batch(wl, n, 101)
