@@ -205,55 +205,41 @@ def model_digest(md: workloads.ModelDef, bundles=None) -> str:
     return hashlib.sha256(key.encode()).hexdigest()[:12]
 
 
-def build_model_plugin(md: workloads.ModelDef, force: bool = False, bundles=None) -> str:
-    """Generates csrc for `md` and compiles it for sm_100a into a plugin exporting `ipddp_plugin_vtable`."""
+def _compile_plugin(name: str, src: str, force: bool = False) -> str:
+    """Compiles an emitted model header for sm_100a into `<name>_<hash>.so` exporting `ipddp_plugin_vtable` (three lines
+    of CUDA around the header).  The plugin embeds the kernel templates and the DevView layout, so the
+    cache key covers them and the compiler flags too."""
     os.makedirs(PLUGIN_DIR, exist_ok=True)
-    bundles = bundles if bundles is not None else generate.trace(md)
-    src = generate.emit_device(md, bundles).replace('#include "../model_common.cuh"',
-                                                    f'#include "{os.path.join(HERE, "csrc", "model_common.cuh")}"')
+    src = src.replace('#include "../model_common.cuh"', f'#include "{os.path.join(HERE, "csrc", "model_common.cuh")}"')
     from . import build as _b
-    # the plugin embeds the kernel templates and the DevView layout: key the cache on them too
     tag = hashlib.sha256((src + _b.content_hash(_b._headers(), " ".join(_b.FLAGS))).encode()).hexdigest()[:12]
-    so = os.path.join(PLUGIN_DIR, f"{md.name}_{tag}.so")
+    so = os.path.join(PLUGIN_DIR, f"{name}_{tag}.so")
     if os.path.exists(so) and not force:
         return so
-    cuh = os.path.join(PLUGIN_DIR, f"{md.name}_{tag}.cuh")
-    cu = os.path.join(PLUGIN_DIR, f"{md.name}_{tag}.cu")
+    cuh = os.path.join(PLUGIN_DIR, f"{name}_{tag}.cuh")
+    cu = os.path.join(PLUGIN_DIR, f"{name}_{tag}.cu")
     with open(cuh, "w") as fh:
         fh.write(src)
     with open(cu, "w") as fh:
         fh.write(f'#include "{cuh}"\n#include "{os.path.join(HERE, "csrc", "model_register.cuh")}"\n'
-                 f'IPDDP_REGISTER_MODEL(Model_{md.name}, ipddp_plugin_vtable)\n')
-    cmd = [_b.NVCC] + _b.FLAGS + ["-shared", cu, "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+                 f'IPDDP_REGISTER_MODEL(Model_{name}, ipddp_plugin_vtable)\n')
+    r = subprocess.run([_b.NVCC] + _b.FLAGS + ["-shared", cu, "-o", so], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for model plugin:\n" + r.stdout + r.stderr)
     return so
+
+
+def build_model_plugin(md: workloads.ModelDef, force: bool = False, bundles=None) -> str:
+    """Generates the device code of `md` and compiles it into a plugin."""
+    bundles = bundles if bundles is not None else generate.trace(md)
+    return _compile_plugin(md.name, generate.emit_device(md, bundles), force)
 
 
 def build_chain_plugin(chain, all_bundles, force: bool = False) -> str:
     """Plugin of a stage chain (several stage types, sizes that change along the horizon): one header with the stage
     structs and the composite model (generate.emit_device_chain)."""
-    os.makedirs(PLUGIN_DIR, exist_ok=True)
-    inc = f'#include "{os.path.join(HERE, "csrc", "model_common.cuh")}"'
     src = generate.emit_device_chain(chain, [generate.emit_device(md, b) for md, b in zip(chain.stages, all_bundles)])
-    src = src.replace('#include "../model_common.cuh"', inc)
-    from . import build as _b
-    tag = hashlib.sha256((src + _b.content_hash(_b._headers(), " ".join(_b.FLAGS))).encode()).hexdigest()[:12]
-    so = os.path.join(PLUGIN_DIR, f"{chain.name}_{tag}.so")
-    if os.path.exists(so) and not force:
-        return so
-    cuh = os.path.join(PLUGIN_DIR, f"{chain.name}_{tag}.cuh")
-    cu = os.path.join(PLUGIN_DIR, f"{chain.name}_{tag}.cu")
-    with open(cuh, "w") as fh:
-        fh.write(src)
-    with open(cu, "w") as fh:
-        fh.write(f'#include "{cuh}"\n#include "{os.path.join(HERE, "csrc", "model_register.cuh")}"\n'
-                 f'IPDDP_REGISTER_MODEL(Model_{chain.name}, ipddp_plugin_vtable)\n')
-    r = subprocess.run([_b.NVCC] + _b.FLAGS + ["-shared", cu, "-o", so], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed for model plugin:\n" + r.stdout + r.stderr)
-    return so
+    return _compile_plugin(chain.name, src, force)
 
 
 @dataclass

@@ -1,0 +1,94 @@
+"""The reference-facing host API (Dynamics / Objective / Constraint / Bound / Options / Solver / solve / get_trajectory,
+api.py) end to end WITHOUT a GPU: the test bodies of tests/test_gpu_api.py run against the SIMT emulator -- the same
+tracing, the same emitted model headers, the same C ABI calls; only the compiler of the plugin (g++ against
+tests/emu/cpu_simt.h instead of nvcc) and the library behind `_lib.load()` differ (tests/emu/emu_plugins.py, test
+infrastructure).  The GPU suite runs the same bodies on the B200."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+import test_gpu_api as cases  # noqa: E402  (its pytestmark only applies to tests collected from that module)
+
+
+@pytest.fixture()
+def emu_api(monkeypatch):
+    import emu_plugins
+    return emu_plugins.install(monkeypatch)
+
+
+def test_emulated_double_integrator_via_reference_api(emu_api, oracle_mod):
+    cases.test_double_integrator_via_reference_api(oracle_mod)
+
+
+def test_emulated_user_provided_derivative_constructors(emu_api, oracle_mod):
+    cases.test_user_provided_derivative_constructors(oracle_mod)
+
+
+def test_emulated_solver_with_stage_sizes_that_change_along_the_horizon(emu_api, oracle_mod):
+    cases.test_solver_with_stage_sizes_that_change_along_the_horizon(oracle_mod)
+
+
+def test_emulated_user_model_with_parameters_batched(emu_api, oracle_mod):
+    cases.test_user_model_with_parameters_batched(oracle_mod)
+
+
+def test_emulated_indices_compl(emu_api, oracle_mod):
+    cases.test_indices_compl(oracle_mod)
+
+
+def test_emulated_quasi_newton_option(emu_api, oracle_mod):
+    cases.test_quasi_newton_option(oracle_mod)
+
+
+def test_emulated_inplace_user_closures_solve_like_value_closures(emu_api, oracle_mod):
+    """The reference's in-place user-derivative closures (`f!(y, x, u)`, `fx!(J, x, u)`, ...: src/dynamics.jl:49-61,
+    src/constraints.jl:60-64) behind `inplace=True`: same model digest, same solve (the golden double-integrator row)
+    as the value-returning closures of test_user_provided_derivative_constructors."""
+    import math
+    import numpy as np
+    from ipddp_b200 import Dynamics, Objective, Constraint, Bound, Options, Solver, solve, get_trajectory
+    import helpers
+    dt, N = 0.01, 101
+
+    def f(y, x, u):
+        y[0] = x[0] + dt * x[1]
+        y[1] = x[1] + dt * u[0]
+
+    def fx(J, x, u):
+        J[0, 0] = 1.0; J[0, 1] = dt; J[1, 1] = 1.0
+
+    def fu(J, x, u):
+        J[1, 0] = dt
+
+    def c(out, x, u):
+        out[0] = u[1] - u[2] - u[0] * x[1]
+
+    def cx(J, x, u):
+        J[0, 1] = -u[0]
+
+    def cu(J, x, u):
+        J[0, 0] = -x[1]; J[0, 1] = 1.0; J[0, 2] = -1.0
+
+    def vcux(H, x, u, v):
+        H[0, 1] = -v[0]
+
+    dyn = Dynamics(f, fx, fu, 2, 2, 3, inplace=True)
+    path = Constraint(c, cx, cu, 1, 2, 3, vcux=vcux, inplace=True)
+    stage = Objective(lambda x, u: dt * (u[1] + u[2]), 2, 3)
+    term = Objective(lambda x, u: 500.0 * ((x[0] - 1.0) * (x[0] - 1.0) + (x[1] - 0.0) * (x[1] - 0.0)), 2, 0)
+    bound = Bound([-10.0, 0.0, 0.0], [10.0, math.inf, math.inf])
+    solver = Solver(float, [dyn] * (N - 1), [stage] * (N - 1) + [term], [path] * (N - 1) + [Constraint(2, 0)],
+                    [bound] * (N - 1) + [Bound(float, 0)], options=Options(optimality_tolerance=1e-7))
+    solve(solver, np.zeros(2), [np.array([0.01, 0.01, 0.01]) for _ in range(N - 1)] + [np.zeros(0)])
+    d = solver.data
+    assert d.status == 0 and d.k == 31 and abs(d.objective - 1.26574863e+00) < 5e-9
+    o = oracle_mod.OracleSolver("double_integrator", N, [], bound.lower, bound.upper,
+                                options=oracle_mod.default_options(optimality_tolerance=1e-7))
+    ro = o.solve(np.zeros(2), np.tile([0.01, 0.01, 0.01], N - 1))
+    assert ro.k == d.k
+    helpers.assert_same_bits(d.objective, ro.objective, "objective")
+    x_sol, _ = get_trajectory(solver)
+    helpers.assert_same_bits(np.concatenate(x_sol), o.array("x"), "states")
