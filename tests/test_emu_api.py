@@ -92,3 +92,24 @@ def test_emulated_inplace_user_closures_solve_like_value_closures(emu_api, oracl
     helpers.assert_same_bits(d.objective, ro.objective, "objective")
     x_sol, _ = get_trajectory(solver)
     helpers.assert_same_bits(np.concatenate(x_sol), o.array("x"), "states")
+
+
+def test_emulated_experiment_harness_reproduces_the_reference_table(emu_api, tmp_path):
+    """tools/run_experiments.py (one batched launch per class, tables in the reference's file format) on the
+    emulator: the double-integrator table comes out with the reference's own text in the seed / iterations / status /
+    objective columns and its primal infeasibility (experiments/ipddp2/results/double_integrator.txt; the timing columns
+    are this machine's), and parses with the reference's regexes.  (The 100-row classes take the emulator minutes per row;
+    the B200 regenerates all six tables: profiles/r2_experiments.)"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(os.path.dirname(here), "tools"))
+    import run_experiments
+    from ipddp_b200 import results_io
+    fname = "double_integrator"
+    summ = run_experiments.run_class(emu_api, "double_integrator", fname, str(tmp_path))
+    assert summ["same_both"] == summ["instances"] == summ["converged_gpu"] == 1
+    got = open(tmp_path / (fname + ".txt")).read().splitlines()
+    want = open(os.path.join(here, "golden", "results", fname + ".txt")).read().splitlines()
+    assert got[0] == want[0] and len(got) == len(want) == 2
+    ca, cb = got[1].split(), want[1].split()
+    assert ca[:5] == cb[:5], (got[1], want[1])
+    assert len(results_io.read_results(str(tmp_path / (fname + ".txt")))) == 1
