@@ -113,3 +113,24 @@ def test_emulated_experiment_harness_reproduces_the_reference_table(emu_api, tmp
     ca, cb = got[1].split(), want[1].split()
     assert ca[:5] == cb[:5], (got[1], want[1])
     assert len(results_io.read_results(str(tmp_path / (fname + ".txt")))) == 1
+
+
+def test_emulated_fresh_objects_per_stage_are_one_stage_type(emu_api):
+    """`[Dynamics(f, nx, nu) for k = 1:N-1]` (reference experiments/ipddp2/pushing_1_obs.jl:98,104: a new object per stage
+    around the same closure) must give the same single stage type as one shared object (cartpole_friction.jl:53)."""
+    import math
+    import numpy as np
+    from ipddp_b200 import Dynamics, Objective, Constraint, Bound, Options, Solver, solve
+    dt, N = 0.01, 101
+    f = lambda x, u: [x[0] + dt * x[1], x[1] + dt * u[0]]
+    stage_obj = lambda x, u: dt * (u[1] + u[2])
+    term_obj = lambda x, u: 500.0 * ((x[0] - 1.0) * (x[0] - 1.0) + (x[1] - 0.0) * (x[1] - 0.0))
+    con = lambda x, u: [u[1] - u[2] - u[0] * x[1]]
+    solver = Solver(float, [Dynamics(f, 2, 3) for _ in range(N - 1)],
+                    [Objective(stage_obj, 2, 3) for _ in range(N - 1)] + [Objective(term_obj, 2, 0)],
+                    [Constraint(con, 2, 3) for _ in range(N - 1)] + [Constraint(2, 0)],
+                    [Bound([-10.0, 0.0, 0.0], [10.0, math.inf, math.inf]) for _ in range(N - 1)] + [Bound(float, 0)],
+                    options=Options(optimality_tolerance=1e-7))
+    assert solver._bs.nstage == 1 and set(solver.stage_type) == {0}
+    solve(solver, np.zeros(2), [np.array([0.01, 0.01, 0.01]) for _ in range(N - 1)] + [np.zeros(0)])
+    assert solver.data.status == 0 and solver.data.k == 31 and abs(solver.data.objective - 1.26574863e+00) < 5e-9
