@@ -168,10 +168,56 @@ function c_body(exprs::Vector{Num}, args::Vector, argnames::Vector{Symbol})
                                    rhsnames=argnames, expression=Val{true})
     src = String(src)
     body = src[findfirst('{', src)+1:findlast('}', src)-1]
-    # integer powers by repeated multiplication (Julia evaluates x^2, x^3 by multiplication; `pow` would round differently)
-    body = replace(body, r"pow\(([A-Za-z_][A-Za-z_0-9]*\[\d+\]), 2\)" => s"((\1)*(\1))")
-    body = replace(body, r"pow\(([A-Za-z_][A-Za-z_0-9]*\[\d+\]), 3\)" => s"((\1)*(\1)*(\1))")
-    return body
+    return expand_literal_pows(body)
+end
+
+"""
+`pow(<expr>, 2)` -> `((<expr>)*(<expr>))`, `pow(<expr>, 3)` -> `((<expr>)*(<expr>)*(<expr>))` for arbitrary (nested)
+base expressions: the reference's generated Julia code evaluates literal powers 2 and 3 by multiplication
+(`Base.literal_pow`), which `pow` would not reproduce to the last bit.  Other exponents stay `pow` (the deterministic
+`dm::pow`).  The base is a pure expression, so repeating it is safe; nvcc evaluates it once.
+"""
+function expand_literal_pows(s::AbstractString)
+    cs = collect(s)
+    n = length(cs)
+    out = Char[]
+    i = 1
+    while i <= n
+        ident_before = i > 1 && (isletter(cs[i-1]) || isdigit(cs[i-1]) || cs[i-1] == '_')
+        if !ident_before && i + 3 <= n && cs[i] == 'p' && cs[i+1] == 'o' && cs[i+2] == 'w' && cs[i+3] == '('
+            depth = 1
+            j = i + 4
+            comma = 0
+            while j <= n
+                c = cs[j]
+                if c == '('
+                    depth += 1
+                elseif c == ')'
+                    depth -= 1
+                    depth == 0 && break
+                elseif c == ',' && depth == 1
+                    comma = j
+                end
+                j += 1
+            end
+            if j <= n && comma > 0                      # cs[j] is the parenthesis that closes this pow(
+                base = expand_literal_pows(String(cs[i+4:comma-1]))
+                ex = strip(String(cs[comma+1:j-1]))
+                if ex == "2"
+                    append!(out, collect("(($base)*($base))"))
+                elseif ex == "3"
+                    append!(out, collect("(($base)*($base)*($base))"))
+                else
+                    append!(out, collect("pow($base, $ex)"))
+                end
+                i = j + 1
+                continue
+            end
+        end
+        push!(out, cs[i])
+        i += 1
+    end
+    return String(out)
 end
 
 store_calls(body::String) = replace(body, r"du\[(\d+)\]\s*=\s*(.*?);" => s"st(\1, \2);")
