@@ -55,18 +55,20 @@ def reduce_stats(stats: Dict[str, float], device=None, group=None) -> Dict[str, 
 
 
 def solve_sharded(workload: str, total: int, N: int, options=None, device: int = 0, rank: int = 0, world: int = 1,
-                  seed: int = 0, vary_horizon: bool = False):
+                  seed: int = 0, vary_horizon: bool = False, lib=None, reduce_device=None):
     """Each rank solves its shard of the workload's canonical instance stream on its own GPU and returns
-    (local BatchResult, reduced statistics)."""
+    (local BatchResult, reduced statistics).  `lib` / `reduce_device`: the loaded C-ABI library and the device the
+    statistics vector is reduced on (defaults: the CUDA library, this rank's GPU -> NCCL); the world-size-2 CPU test passes
+    its emulator build and the CPU (gloo)."""
     import torch
     from . import instances
     from .batch import BatchSolver
     lo, hi = shard_bounds(total, rank, world)
     batch = instances.make_batch(workload, hi - lo, N, seed=seed, first=lo, vary_horizon=vary_horizon)
-    s = BatchSolver(workload, hi - lo, N, options=options, device=device)
+    s = BatchSolver(workload, hi - lo, N, options=options, device=device, lib=lib)
     s.set_batch(batch)
     r = s.solve()
     st = local_stats(r.status, r.k, r.primal_inf, s.counters(), s.stats().ms_total)
     s.close()
-    red = reduce_stats(st, device=torch.device("cuda", device))
+    red = reduce_stats(st, device=reduce_device if reduce_device is not None else torch.device("cuda", device))
     return r, red
