@@ -10,6 +10,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+
+def _free_port():
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return str(so.getsockname()[1])
+
 WORKER = r'''
 import os, sys, json
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
@@ -42,7 +49,7 @@ def test_two_rank_sharding_and_reduction(tmp_path):
     import oracle
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", WORLD_SIZE="2")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=_free_port(), WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
                               stderr=subprocess.PIPE, text=True) for r in range(2)]
     outs = [p.communicate(timeout=600) for p in procs]
@@ -113,7 +120,7 @@ def test_two_rank_solve_sharded_on_the_emulator(tmp_path, oracle_mod):
     from ipddp_b200 import instances
     script = tmp_path / "worker_sharded.py"
     script.write_text(WORKER_SHARDED.format(root=ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29543", WORLD_SIZE="2")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=_free_port(), WORLD_SIZE="2")
     env.pop("IPDDP_EMU_ORDER", None)
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
                               stderr=subprocess.PIPE, text=True) for r in range(2)]
