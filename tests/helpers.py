@@ -523,3 +523,43 @@ def api_error_convention(lib):
         assert "unknown array" in err()
     finally:
         s.close()
+
+
+# Every Options field the algorithm reads (reference src/options.jl:1-38), moved away from its default by a value that
+# changes the iterates of small pushing / concar solves (checked on the oracle: tests/test_emu_parity.py asserts it).
+OPTION_VARIANTS = dict(mu_init=0.3, kappa_1=0.05, reg_1=1e-3, kappa_bar_w_p=50.0, kappa_w_p=5.0, kappa_w_m=0.5, kappa_eps=5.0,
+                       kappa_mu=0.3, theta_mu=1.4, tau_min=0.95, s_max=10.0, s_L=2.0, delta=1e-4, s_theta=1.2, eta_L=0.4,
+                       gamma_theta=0.3)
+OPTION_GROUPS = [dict(mu_init=0.3, kappa_eps=5.0, kappa_mu=0.3, theta_mu=1.4, s_max=10.0, tau_min=0.95),
+                 dict(reg_1=1e-3, kappa_bar_w_p=50.0, kappa_w_p=5.0, kappa_w_m=0.5, reg_min=1e-3),
+                 dict(s_L=2.0, delta=1e-4, s_theta=1.2, eta_L=0.4, gamma_theta=0.3, gamma_L=0.3)]
+
+
+def options_parity(lib, oracle, variants, wl="pushing", B=4, N=21, maxit=120, first=3, mutate=None):
+    """Solves the same instances once per option set in `variants` (list of dicts) on the library and on the oracle:
+    status, k, j, l, objective and trajectories bit for bit.  Returns, per variant, whether it changed the iterates with
+    respect to the default options (so that callers can assert the sweep is discriminating)."""
+    b = instances.make_batch(wl, B, N, first=first)
+    if mutate is not None:
+        mutate(b)
+
+    def run(kw):
+        base = dict(optimality_tolerance=1e-7, max_iterations=maxit)
+        base.update(kw)
+        s = BatchSolver(wl, B, N, options=lib.default_options(**base), lib=lib)
+        s.set_batch(b)
+        r = s.solve()
+        x, u = s.trajectory()
+        s.close()
+        res, xo, uo = oracle.solve_batch(wl, N, b.p, b.lower, b.upper, b.x1, b.ubar, options=oracle.default_options(**base),
+                                         want_traj=True)
+        for i in range(B):
+            o = res[i]
+            got = (int(r.status[i]), int(r.k[i]), int(r.j[i]), int(r.l[i]))
+            assert got == (o.status, o.k, o.j, o.l), f"{wl} options {kw} inst {i}: {got} vs oracle {(o.status, o.k, o.j, o.l)}"
+            assert_same_bits(r.objective[i], o.objective, f"{wl} options {kw} inst {i} objective")
+        assert_same_bits(x, xo, f"{wl} options {kw} states")
+        assert_same_bits(u, uo, f"{wl} options {kw} controls")
+        return [(o.status, o.k, o.objective) for o in res]
+    base = run({})
+    return [run(kw) != base for kw in variants]

@@ -234,3 +234,16 @@ def test_emulated_one_sided_bounds(emu, oracle_mod):
         finally:
             emu.L.ipddp_set_tuning(None, b"fw_spec_max", -1)
             emu.L.ipddp_set_tuning(None, b"bw_spec_max", -1)
+
+
+def test_emulated_options_reach_the_kernels(emu, oracle_mod):
+    """The 31 Options fields travel through the C ABI as one struct (reference src/options.jl:1-38).  Three option sets that
+    together move every barrier / regularisation / line-search parameter away from its default, plus the projection
+    parameters on instances whose guesses lie outside their bounds: each set changes the iterates, and the kernels follow
+    the oracle bit for bit -- a kernel that kept a default where it should read the option would not.  (One option at a
+    time: the GPU suite, test_gpu_parity.py::test_every_option_reaches_the_kernels.)"""
+    changed = helpers.options_parity(emu, oracle_mod, helpers.OPTION_GROUPS, B=2)
+    assert all(changed), changed
+    changed = helpers.options_parity(emu, oracle_mod, [dict(kappa_1=1e-3, kappa_2=0.2), dict(kappa_2=1e-4)], wl="concar", B=4,
+                                     N=11, maxit=60, first=0, mutate=helpers.one_sided_bounds)
+    assert all(changed), changed

@@ -303,3 +303,14 @@ def test_one_sided_bounds(gpu, oracle_mod):
     """Upper-only, lower-only, two-sided (guess outside) and unbounded controls per instance: every branch of the control
     projection of reference src/solver.jl:70-95, incl. the upper-only one no experiment uses."""
     helpers.full_solve_parity(gpu, oracle_mod, "concar", 16, 41, maxit=300, n_trace=4, mutate=helpers.one_sided_bounds)
+
+
+def test_every_option_reaches_the_kernels(gpu, oracle_mod):
+    """One Options field at a time (reference src/options.jl:1-38) moved away from its default: each changes the iterates of
+    small pushing solves, and the GPU follows the oracle bit for bit every time."""
+    variants = [{k: v} for k, v in helpers.OPTION_VARIANTS.items()] + helpers.OPTION_GROUPS
+    changed = helpers.options_parity(gpu, oracle_mod, variants)
+    assert all(changed), [v for v, c in zip(variants, changed) if not c]
+    changed = helpers.options_parity(gpu, oracle_mod, [dict(kappa_1=1e-3, kappa_2=0.2), dict(kappa_2=1e-4)], wl="concar", B=4,
+                                     N=11, maxit=60, first=0, mutate=helpers.one_sided_bounds)
+    assert all(changed), changed
