@@ -2,7 +2,6 @@
 -> solve) run in a container without a GPU.  The emitted model header -- the very text the product hands to nvcc -- is
 compiled with g++ against the SIMT emulator (cpu_simt.h) into a plugin for tests/emu/libipddp_emu.so, and `_lib.load()` is
 pointed at that library.  Never imported by the package."""
-import ctypes
 import hashlib
 import os
 import subprocess
@@ -26,8 +25,13 @@ def compile_plugin(name, src, force=False):
     with open(cu, "w") as fh:
         fh.write(f'#include "{cuh}"\n#include "{os.path.join(csrc, "model_register.cuh")}"\n'
                  f'IPDDP_REGISTER_MODEL(Model_{name}, ipddp_plugin_vtable)\n')
-    # always rebuilt: the kernel templates the plugin embeds change with the sources under test
-    subprocess.check_call([build_emu.CXX] + build_emu.FLAGS + ["-shared", cu, "-o", so])
+    # always rebuilt: the kernel templates the plugin embeds change with the sources under test.  The plugin is linked
+    # against the emulator library for the SIMT runtime (emu::launch ...): resolved through its own dependency list, so
+    # the library is never loaded RTLD_GLOBAL (that would interpose the kernels of the differently-flagged emulator builds
+    # other tests load into the same process).
+    emu_dir, emu_name = os.path.split(build_emu.LIB)
+    subprocess.check_call([build_emu.CXX] + build_emu.FLAGS + ["-shared", cu, "-o", so, f"-L{emu_dir}", f"-l:{emu_name}",
+                                                                f"-Wl,-rpath,{emu_dir}"])
     return so
 
 
@@ -35,7 +39,6 @@ def install(monkeypatch):
     """Points the package at the emulator for the duration of a test; returns the emulator's Lib."""
     from ipddp_b200 import _lib, api
     path = build_emu.build()
-    ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)      # the plugins resolve the emulator runtime (emu::launch ...) from here
     lib = _lib.Lib(path)
     monkeypatch.setattr(_lib, "load", lambda *a, **k: lib)
     monkeypatch.setattr(api, "_compile_plugin", compile_plugin)
