@@ -26,13 +26,13 @@ def test_block_check_catches_a_missing_end(tmp_path):
 
 def test_julia_sources_lex_cleanly():
     """Pygments' Julia lexer finds no token it cannot classify (unterminated strings, stray characters, bad escapes) in the
-    package sources.  Substitution strings s"..." (raw, with \\1 back-references) are not known to that lexer and are
-    neutralised first."""
+    package sources.  Regex and substitution literals (r"...", s"...": raw strings whose backslash sequences that lexer
+    does not accept) are neutralised first."""
     import re
     from pygments.lexers import JuliaLexer
     from pygments.token import Token
     for f in sorted(glob.glob(os.path.join(ROOT, "julia", "*.jl"))):
         src = open(f, encoding="utf-8").read()
-        src = re.sub(r'\bs"([^"\\]|\\.)*"', '"s"', src)
+        src = re.sub(r'\b[rs]"([^"\\]|\\.)*"', '"raw"', src)
         bad = [(src.count("\n", 0, i) + 1, v) for i, t, v in JuliaLexer().get_tokens_unprocessed(src) if t in Token.Error]
         assert bad == [], (f, bad[:5])
