@@ -31,3 +31,19 @@ def test_forward_kernels_use_tma_bulk_copies_and_the_library_is_sm_100a_only():
     assert "UBLKCP" in sass, "no TMA bulk copy (cp.async.bulk) in k_forward"
     assert "SYNCS" in sass, "no mbarrier operation in k_forward"
     assert "DFMA" in sass
+
+
+@pytest.mark.skipif(not os.path.exists(CUOBJDUMP), reason="cuobjdump not available")
+def test_backward_kernel_keeps_its_occupancy_design_point():
+    """k_backward runs 20 warps per SM at 96 registers without spills (the register file holds 5 warps of
+    96 registers per SM sub-partition); k_forward 168 registers.  A source change that pushes ptxas past either is a
+    performance regression that no parity test would notice."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("libipddp_b200.so not built")
+    out = subprocess.run([CUOBJDUMP, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    usage = {m.group(1): (int(m.group(2)), int(m.group(3)))
+             for m in re.finditer(r"Function (\S+?):\s*\n\s*REG:(\d+) STACK:(\d+)", out)}
+    bw = usage["_ZN3ipk10k_backwardI14Model_cartpoleEEv7DevView8ListView"]
+    fw = usage["_ZN3ipk9k_forwardI14Model_cartpoleEEv7DevViewPKiPiS5_"]
+    assert bw[0] <= 96 and bw[1] == 0, bw
+    assert fw[0] <= 168, fw
