@@ -160,7 +160,7 @@ def test_emulated_phases(emu, oracle_mod, wl):
 
 
 def test_emulated_ldlt(emu, oracle_mod):
-    helpers.ldlt_parity(emu, oracle_mod, np.random.default_rng(3), nmat=24, nmax=35)
+    helpers.ldlt_parity(emu, oracle_mod, np.random.default_rng(3), nmat=24, nmax=64)     # the C ABI accepts nu + nc <= 64
 
 
 def test_emulated_exact_division(emu):

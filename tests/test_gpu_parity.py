@@ -314,3 +314,9 @@ def test_every_option_reaches_the_kernels(gpu, oracle_mod):
     changed = helpers.options_parity(gpu, oracle_mod, [dict(kappa_1=1e-3, kappa_2=0.2), dict(kappa_2=1e-4)], wl="concar", B=4,
                                      N=11, maxit=60, first=0, mutate=helpers.one_sided_bounds)
     assert all(changed), changed
+
+
+def test_ldlt_bit_exact_up_to_the_largest_kkt(gpu, oracle_mod):
+    """ipddp_problem_create accepts models with nu + nc <= 64: the warp LDL^T at n = 48 and 64 (two lane slots per column
+    beyond 32) against the oracle's dsytf2_rook / dsytrs_rook, as test_ldlt_bit_exact does up to the largest built-in model."""
+    helpers.ldlt_parity(gpu, oracle_mod, np.random.default_rng(13), nmat=200, nmax=64)
