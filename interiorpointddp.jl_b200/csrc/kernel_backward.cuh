@@ -23,6 +23,14 @@
 
 namespace ipk {
 
+// e / D for a compile-time divisor and the small non-negative indices of the gains blocks (e * D < 2^32): one multiply-high
+// with ceil(2^32 / D) instead of the ~20 instructions of the signed division.  D == 1 has no 32-bit multiplier
+// (ceil(2^32 / 1) wraps to 0): models with a single control (or a 1 x 1 KKT matrix) take the identity.
+template <int D> IPDDP_D int div_small(int e) {
+  if constexpr (D == 1) return e;
+  else return (int)__umulhi((unsigned)e, 0xffffffffu / (unsigned)D + 1u);
+}
+
 template <class M> struct BwLayout {
   // Sizes come from M: for a stage chain M carries the maxima over its stage types, so one layout serves every knot; the
   // arithmetic of a knot indexes the buffers with its own stage type's dimensions.  NS = largest state size that can sit in
@@ -315,7 +323,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
     double* g = out.gains + (size_t)t * v.G;
     double* qo = out.Qu + (size_t)t * M::NU;
     for (int e = lane; e < K * NR; e += 32) {     // e = position in the column-major gains block (row e % K, column e / K)
-      const int jc = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)K + 1u)), rr = e - jc * K;
+      const int jc = div_small<K>(e), rr = e - jc * K;
       const double w = rhs[RL::at(rr, jc)]; g[e] = w; rhs[RL::at(rr, jc)] = w * -1.0; if (e < NU) qo[e] = w;
     }
     __syncwarp();
@@ -329,7 +337,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
     // ---- ineq gains to HBM                                            (:159-172)
     double* gi = g + K * NR;
     for (int e = lane; e < NU * NR; e += 32) {
-      const int j = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)NU + 1u));   // e / NU (the signed division compiles to ~20 instructions)
+      const int j = div_small<NU>(e);
       const int i = e - j * NU;
       if (j == 0) {
         const double al = rhs[RL::at(i, 0)];
@@ -417,7 +425,7 @@ IPDDP_D int bw_knot(const DevView& v, int b, int t, int set, double* sm, const B
     }
     __syncwarp();
     for (int e = lane; e < K * NR; e += 32) {     // eq gains replace the parked copy
-      const int jc = (int)(__umulhi((unsigned)e, 0xffffffffu / (unsigned)K + 1u)), rr = e - jc * K;
+      const int jc = div_small<K>(e), rr = e - jc * K;
       g[e] = rhs[RL::at(rr, jc)];
     }
     for (int e = lane; e < NX * NX; e += 32) Vxx[e] = nVxx[e];

@@ -625,13 +625,20 @@ IPDDP_D int warp_ldlt_factor(double* __restrict__ A, double* __restrict__ Bm, do
 // 4 lanes per right-hand side accumulate the dgemv('T') dot product in the dot4 order (partial sums by i mod 4,
 // ascending i, 2-step butterfly); zero multipliers are skipped through the per-column row masks.
 template <int K, int NR>
+IPDDP_D void warp_ldlt_solve_forward_wide(const double* __restrict__ A, double* __restrict__ Bm,
+                                          const unsigned char* __restrict__ scratch, int lane);
+
+template <int K, int NR>
 IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __restrict__ Bm,
                                      const unsigned char* __restrict__ scratch, int lane) {
+  if constexpr (NR > 8) {     // more than 7 states: the right-hand sides are taken in groups of 8 columns
+    warp_ldlt_solve_forward_wide<K, NR>(A, Bm, scratch, lane);
+    return;
+  }
   typedef LdltScratch<K> S;
   const double* dinv = S::dinv(scratch);
   const unsigned long long* cinfo = S::info(scratch);
   const unsigned* nzhi = S::nzhi(scratch);
-  static_assert(NR <= 8, "at most 8 right-hand sides");
 #pragma unroll
   for (int s = 0; s < (K > 32 ? 2 : 1); ++s) {
     const int r = lane + 32 * s;
@@ -712,6 +719,108 @@ IPDDP_D void warp_ldlt_solve_forward(const double* __restrict__ A, double* __res
         if (act && g == 0) { bj(k) = bj(k) - sa; bj(k + 1) = bj(k + 1) - sb; }
         __syncwarp();
       }
+      int kp = -pv - 1;
+      if (kp != k) { RL::swap_rows(Bm, k, kp, lane); __syncwarp(); }
+      kp = -S::ipiv_of(cinfo[k + 1]) - 1;
+      if (kp != k + 1) { RL::swap_rows(Bm, k + 1, kp, lane); __syncwarp(); }
+      k += 2;
+    }
+  }
+}
+
+// The same loop for NR > 8 right-hand sides (models with more than 7 states; the reference's experiments have at most 4):
+// lane (g, j) serves the columns j, j + 8, j + 16, ... one after the other inside every pivot step.  The columns of B are
+// independent of each other, so every column sees exactly the operations, in exactly the order, of the loop above.
+template <int K, int NR>
+IPDDP_D void warp_ldlt_solve_forward_wide(const double* __restrict__ A, double* __restrict__ Bm,
+                                          const unsigned char* __restrict__ scratch, int lane) {
+  typedef LdltScratch<K> S;
+  typedef RhsL<K, NR> RL;
+  const double* dinv = S::dinv(scratch);
+  const unsigned long long* cinfo = S::info(scratch);
+  const unsigned* nzhi = S::nzhi(scratch);
+  constexpr int NG = (NR + 7) / 8;
+#pragma unroll
+  for (int s = 0; s < (K > 32 ? 2 : 1); ++s) {
+    const int r = lane + 32 * s;
+    if (r < K) {
+      const double d = dinv[r];
+      double br[RL::LD];
+      RL::load_row(Bm, r, br);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) br[j] = br[j] * d;
+      RL::store_row(Bm, r, br);
+    }
+  }
+  __syncwarp();
+  const int g = lane & 3;
+  const int j0 = lane >> 2;
+  const unsigned gm = 0x11111111u << g;
+  int k = 0;
+  while (k < K) {
+    const unsigned long long cw = cinfo[k];      // column 0 carries an empty mask
+    const int pv = S::ipiv_of(cw);
+    const bool one = pv > 0;
+    const unsigned mlo = (unsigned)cw;
+    unsigned mhi = 0u;
+    if (K > 32 && k > 32) mhi = nzhi[k];        // rows >= 32 can only be non-zero in columns k > 32
+    const bool any = (mlo | mhi) != 0u;
+    const double* xa = A + coff(k);
+    const double* xb = A + coff(k + (one ? 0 : 1));
+    const int kp1 = pv - 1;                      // 1 x 1 pivot: the row interchanged with row k
+    for (int q = 0; q < NG; ++q) {
+      const int j = j0 + 8 * q;
+      const bool act = j < NR;
+      const int jc = act ? j : 0;
+      auto bj = [&](int i) -> double& { return Bm[RL::at(i, jc)]; };
+      double sa = 0.0, sb = 0.0;
+      if (any) {
+        if (act) {
+          unsigned m = mlo & gm;
+          while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1u;
+            const double bv = bj(i);
+            sa = IPDDP_FMA(xa[i], bv, sa);
+            if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
+          }
+          if (K > 32 && mhi != 0u) {
+            m = mhi & gm;
+            while (m) {
+              const int i = 32 + __ffs(m) - 1;
+              m &= m - 1u;
+              const double bv = bj(i);
+              sa = IPDDP_FMA(xa[i], bv, sa);
+              if (!one) sb = IPDDP_FMA(xb[i], bv, sb);
+            }
+          }
+        }
+        __syncwarp();
+        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 1);
+        sa = sa + __shfl_xor_sync(IPDDP_FULL_MASK, sa, 2);
+        if (!one) {
+          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 1);
+          sb = sb + __shfl_xor_sync(IPDDP_FULL_MASK, sb, 2);
+        }
+      }
+      if (act && g == 0) {
+        if (one) {
+          if (any || kp1 != k) {     // B(k, j) -= sa, then the interchange k <-> kp in one read-modify-write
+            double v = bj(k);
+            if (any) v = v - sa;
+            if (kp1 != k) { const double t = bj(kp1); bj(kp1) = v; v = t; }
+            bj(k) = v;
+          }
+        } else if (any) {
+          bj(k) = bj(k) - sa;
+          bj(k + 1) = bj(k + 1) - sb;
+        }
+      }
+    }
+    __syncwarp();
+    if (one) {
+      k += 1;
+    } else {
       int kp = -pv - 1;
       if (kp != k) { RL::swap_rows(Bm, k, kp, lane); __syncwarp(); }
       kp = -S::ipiv_of(cinfo[k + 1]) - 1;
