@@ -46,8 +46,10 @@ def emulator_with_models(models):
     """The emulator library with `models` registered through ipddp_model_load (plugins compiled from the emitted headers)."""
     from ipddp_b200 import _lib
     from ipddp_b200.codegen import generate
+    import concurrent.futures as cf
     lib = _lib.Lib(build_emu.build())
-    for md, bundles in models:
-        so = emu_plugins.compile_plugin(md.name, generate.emit_device(md, bundles))
+    with cf.ThreadPoolExecutor(max_workers=min(8, max(1, len(models)))) as ex:      # g++ runs outside the GIL
+        sos = list(ex.map(lambda m: emu_plugins.compile_plugin(m[0].name, generate.emit_device(m[0], m[1])), models))
+    for so in sos:
         lib.check(lib.L.ipddp_model_load(so.encode()), "ipddp_model_load")
     return lib
