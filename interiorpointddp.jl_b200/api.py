@@ -323,6 +323,13 @@ class Solver:
         # exactly when their emitted sources agree.  A user-chosen `name` is bound to the source it was first built from
         # in this process; the same name with different code is rebuilt and re-registered (ipddp_model_load replaces it).
         all_bundles = [generate.trace(md) for md in mds]
+        for md, bd in zip(mds, all_bundles):      # the kernels' limits, before any compiler is started
+            n_c = bd["con"].outputs[0][1]
+            if md.nu < 1:
+                raise ValueError("a running stage needs at least one control")
+            if md.nu + n_c > 64:
+                raise ValueError(f"num_control + num_constraint = {md.nu + n_c} > 64: the warp-level KKT factorisation holds at "
+                                 "most 64 rows (two lane slots per column)")
         chain = len(mds) > 1 or all_bundles[0]["dyn"].outputs[0][1] != mds[0].nx or (oN.num_state != mds[0].nx)
         digest = hashlib.sha256("|".join(model_digest(md, bd) for md, bd in zip(mds, all_bundles)).encode()).hexdigest()[:12]
         tag = name or ("user_" + digest)

@@ -504,6 +504,10 @@ function Solver(T, dynamics::Vector{Dynamics}, objectives::Vector{Objective}, co
                          inplace_constraint=c.inplace, num_next_state=d.num_next_state,
                          num_constraint=max(c.num_constraint, 0)))
     end
+    for sm in sms      # the kernels' limits, before any compiler is started
+        sm.nu >= 1 || error("a running stage needs at least one control")
+        sm.nu + sm.nc <= 64 || error("num_control + num_constraint = $(sm.nu + sm.nc) > 64: the warp-level KKT factorisation holds at most 64 rows")
+    end
     chain = length(sms) > 1 || sms[1].nxn != sms[1].nx || sms[1].nxt != sms[1].nx
     # the model's identity is its traced source
     tag = name === nothing ? "user_" * bytes2hex(sha256(join(emit_device(sm) for sm in sms)))[1:12] : String(name)

@@ -134,3 +134,16 @@ def test_emulated_fresh_objects_per_stage_are_one_stage_type(emu_api):
     assert solver._bs.nstage == 1 and set(solver.stage_type) == {0}
     solve(solver, np.zeros(2), [np.array([0.01, 0.01, 0.01]) for _ in range(N - 1)] + [np.zeros(0)])
     assert solver.data.status == 0 and solver.data.k == 31 and abs(solver.data.objective - 1.26574863e+00) < 5e-9
+
+
+def test_solver_refuses_models_beyond_the_kernels_limits(emu_api):
+    """num_control + num_constraint > 64 is refused with a plain message before any compiler runs (the C ABI would refuse it
+    too: ipddp_problem_create)."""
+    import math
+    from ipddp_b200 import Dynamics, Objective, Constraint, Bound, Solver
+    nu, N = 65, 3
+    dyn = Dynamics(lambda x, u: [x[0] + 0.1 * u[0]], 1, nu)
+    with pytest.raises(ValueError, match="> 64"):
+        Solver(float, [dyn] * (N - 1), [Objective(lambda x, u: sum(ui * ui for ui in u), 1, nu)] * (N - 1)
+               + [Objective(lambda x, u: x[0] * x[0], 1, 0)], [Constraint(1, nu)] * (N - 1) + [Constraint(1, 0)],
+               [Bound(float, nu)] * (N - 1) + [Bound(float, 0)])
