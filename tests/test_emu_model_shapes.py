@@ -168,3 +168,45 @@ def _solve_and_compare(md, emu, orc, name, nx, nu, np_, N):
             assert (cnt["n_sweeps"][i], cnt["n_kkt"][i], cnt["n_rollouts"][i]) == (o.n_sweeps, o.n_kkt, o.n_rollouts)
         helpers.assert_same_bits(x, xo, f"{name} states")
         helpers.assert_same_bits(u, uo, f"{name} controls")
+
+
+def test_emulated_chain_with_a_single_control_stage_and_a_state_that_grows_past_seven(tmp_path, monkeypatch):
+    """A stage chain (reference README.md:18) built from shapes no built-in model has: a single-control stage, a stage that
+    maps 2 states onto 9, and a 9-state stage with the terminal cost -- per-stage arithmetic of both fixes above inside the
+    chain dispatch, resident batch (speculative and bulk kernels) and queue mode."""
+    import sympy as sp
+    import build_emu
+    import emu_plugins
+    import user_model_harness as H
+    from ipddp_b200 import _lib
+    from ipddp_b200.codegen import generate, workloads
+    dt, M = DT, workloads.ModelDef
+    zero = lambda x, p: 0.0 * x[0]
+    s0 = M(name="odd_s0", nx=2, nu=1, np_=0, f=lambda x, u, p: [x[0] + dt * x[1], x[1] + dt * (u[0] - sp.sin(x[0]))],
+           stage_cost=lambda x, u, p: dt * u[0] * u[0], term_cost=zero, c=lambda x, u, p: [], lower=lambda p: [-2.0],
+           upper=lambda p: [INF], u_init=[0.05], dt=dt)
+    s1 = M(name="odd_s1", nx=2, nu=3, np_=0,
+           f=lambda x, u, p: [x[0] + dt * x[1], x[1] + dt * u[0]] + [dt * (x[i % 2] * 0.5 + 0.1 * i) + 0.0 * u[1] for i in range(7)],
+           stage_cost=lambda x, u, p: dt * (u[0] * u[0] + u[1] + u[2]), term_cost=zero, c=lambda x, u, p: [u[1] - u[2] - u[0] * x[1]],
+           lower=lambda p: [-3.0, 0.0, 0.0], upper=lambda p: [3.0, INF, INF], u_init=[0.01] * 3, dt=dt)
+    s2 = M(name="odd_s2", nx=9, nu=2, np_=0,
+           f=lambda x, u, p: [x[i] + dt * (0.3 * x[(i + 1) % 9] - 0.2 * x[i] + (u[i % 2] if i < 4 else 0.0)) for i in range(9)],
+           stage_cost=lambda x, u, p: dt * (0.5 * u[0] * u[0] + u[1]) + 0.1 * dt * x[8] * x[8],
+           term_cost=lambda x, p: 20.0 * sum((x[i] - 0.1 * i) ** 2 for i in range(9)), c=lambda x, u, p: [],
+           lower=lambda p: [-3.0, 0.0], upper=lambda p: [3.0, INF], u_init=[0.01] * 2, dt=dt, nx_term=9)
+    chain = workloads.ChainDef("odd", [s0, s1, s2])
+    monkeypatch.setitem(workloads.CHAINS, "odd", lambda: chain)
+    bundles = [generate.trace(md) for md in chain.stages]
+    orc = H.scratch_oracle(tmp_path, list(zip(chain.stages, bundles)))
+    emu = _lib.Lib(build_emu.build())
+    src = generate.emit_device_chain(chain, [generate.emit_device(md, b) for md, b in zip(chain.stages, bundles)])
+    emu.check(emu.L.ipddp_model_load(emu_plugins.compile_plugin("odd", src).encode()), "ipddp_model_load")
+    try:
+        for spec in (-1, 0):
+            emu.L.ipddp_set_tuning(None, b"fw_spec_max", spec)
+            emu.L.ipddp_set_tuning(None, b"bw_spec_max", spec)
+            helpers.chain_parity(emu, orc, "odd", 3, 9, maxit=40)
+    finally:
+        emu.L.ipddp_set_tuning(None, b"fw_spec_max", -1)
+        emu.L.ipddp_set_tuning(None, b"bw_spec_max", -1)
+    helpers.chain_parity(emu, orc, "odd", 5, 9, maxit=40, queue_slots=2)
