@@ -242,7 +242,7 @@ def test_emulated_options_reach_the_kernels(emu, oracle_mod):
     parameters on instances whose guesses lie outside their bounds: each set changes the iterates, and the kernels follow
     the oracle bit for bit -- a kernel that kept a default where it should read the option would not.  (One option at a
     time: the GPU suite, test_gpu_parity.py::test_every_option_reaches_the_kernels.)"""
-    changed = helpers.options_parity(emu, oracle_mod, helpers.OPTION_GROUPS, B=2)
+    changed = helpers.options_parity(emu, oracle_mod, helpers.OPTION_GROUPS, wl="acrobot", B=2, N=11, maxit=40, first=0)
     assert all(changed), changed
     changed = helpers.options_parity(emu, oracle_mod, [dict(kappa_1=1e-3, kappa_2=0.2), dict(kappa_2=1e-4)], wl="concar", B=4,
                                      N=11, maxit=60, first=0, mutate=helpers.one_sided_bounds)
