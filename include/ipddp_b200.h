@@ -118,7 +118,9 @@ int ipddp_stage_layout(ipddp_problem* h, int* nx, int* nu, int* nc);
 /* Replaces Solver(T, dynamics, objectives, constraints, bounds; options) (src/solver.jl:11-26) and the
  * workspace constructors behind it (src/data/*.jl) for a batch of B instances with up to N knots.
  * indices_compl: 0-based constraint indices that get `- mu` (src/data/methods.jl:27-29), may be NULL.
- * trace_capacity: rows of per-iteration trace kept per instance (0 = none).  device: CUDA ordinal. */
+ * trace_capacity: rows of per-iteration trace kept per instance (0 = none).  device: CUDA ordinal.
+ * Limits (an error is returned, nothing is truncated): B >= 1, N >= 2, nu + nc <= 64 per stage type, N bounded by the
+ * shared memory of the merit kernels (the message states the bound); any number of states. */
 int ipddp_problem_create(const char* model, int B, int N, const int* indices_compl, int n_compl,
                          const ipddp_options* opt, int device, int trace_capacity, ipddp_problem** out);
 int ipddp_problem_destroy(ipddp_problem* h);
