@@ -1111,7 +1111,17 @@ int ipddp_get_duals(ipddp_problem* h, double* phi, double* zl, double* zu, doubl
   if (phi && gather(h, 0, 5, v.nc, v.N - 1, phi) != 0) return -1;
   if (zl && gather(h, 0, 6, v.nu, v.N - 1, zl) != 0) return -1;
   if (zu && gather(h, 0, 7, v.nu, v.N - 1, zu) != 0) return -1;
-  if (lam) CK(cudaMemcpy(lam, v.lam, (size_t)v.B * v.N * v.ns * sizeof(double), cudaMemcpyDeviceToHost));
+  if (lam) {
+    CK(cudaMemcpy(lam, v.lam, (size_t)v.B * v.N * v.ns * sizeof(double), cudaMemcpyDeviceToHost));
+    // The costate lives in its own buffer here and keeps the values of the last sweep.  In the reference it is part of
+    // the nominal dual set: update_nominal_trajectory! overwrites it with the (never written) current costate, i.e. zeros,
+    // after every accepted step (src/data/methods.jl:89), and the next sweep rewrites it.  A solve that ends with an
+    // accepted step -- max_iterations reached, status 8 -- therefore reports zeros.
+    std::vector<int> status(v.B);
+    CK(cudaMemcpy(status.data(), v.si + (size_t)SI_STATUS * v.B, (size_t)v.B * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < v.B; ++b)
+      if (status[b] == 8) memset(lam + (size_t)b * v.N * v.ns, 0, (size_t)v.N * v.ns * sizeof(double));
+  }
   return 0;
 }
 

@@ -563,3 +563,26 @@ def options_parity(lib, oracle, variants, wl="pushing", B=4, N=21, maxit=120, fi
         return [(o.status, o.k, o.objective) for o in res]
     base = run({})
     return [run(kw) != base for kw in variants]
+
+
+def duals_parity(lib, oracle, wl="concar", B=3, N=11):
+    """ipddp_get_duals (reference problem.nominal_*_duals) after a solve that converges and after one that stops at
+    max_iterations: phi, zl, zu and the costate against the oracle.  The costate of a status-8 exit is zero in the reference
+    (update_nominal_trajectory! clears it after the last accepted step, src/data/methods.jl:89)."""
+    b = instances.make_batch(wl, B, N)
+    for maxit, want in ((5, 8), (80, 0)):
+        s = BatchSolver(wl, B, N, options=lib.default_options(optimality_tolerance=1e-7, max_iterations=maxit), lib=lib)
+        s.set_batch(b)
+        r = s.solve()
+        assert (r.status == want).all(), (maxit, r.status)
+        phi, zl, zu, lam = s.duals()
+        s.close()
+        for i in range(B):
+            o = oracle.OracleSolver(wl, N, b.p[i], b.lower[i], b.upper[i],
+                                    options=oracle.default_options(optimality_tolerance=1e-7, max_iterations=maxit))
+            ro = o.solve(b.x1[i], b.ubar[i])
+            assert ro.status == want
+            for name, arr in (("phi", phi), ("zl", zl), ("zu", zu), ("lam", lam)):
+                assert_same_bits(np.asarray(arr[i]).reshape(-1), o.array(name), f"{wl} {name} inst {i} (status {want})")
+            if want == 8:
+                assert not lam[i].any()

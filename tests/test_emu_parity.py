@@ -247,3 +247,7 @@ def test_emulated_options_reach_the_kernels(emu, oracle_mod):
     changed = helpers.options_parity(emu, oracle_mod, [dict(kappa_1=1e-3, kappa_2=0.2), dict(kappa_2=1e-4)], wl="concar", B=4,
                                      N=11, maxit=60, first=0, mutate=helpers.one_sided_bounds)
     assert all(changed), changed
+
+
+def test_emulated_duals_after_converged_and_max_iteration_exits(emu, oracle_mod):
+    helpers.duals_parity(emu, oracle_mod)

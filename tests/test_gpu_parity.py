@@ -320,3 +320,7 @@ def test_ldlt_bit_exact_up_to_the_largest_kkt(gpu, oracle_mod):
     """ipddp_problem_create accepts models with nu + nc <= 64: the warp LDL^T at n = 48 and 64 (two lane slots per column
     beyond 32) against the oracle's dsytf2_rook / dsytrs_rook, as test_ldlt_bit_exact does up to the largest built-in model."""
     helpers.ldlt_parity(gpu, oracle_mod, np.random.default_rng(13), nmat=200, nmax=64)
+
+
+def test_duals_after_converged_and_max_iteration_exits(gpu, oracle_mod):
+    helpers.duals_parity(gpu, oracle_mod)
